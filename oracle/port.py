@@ -1,0 +1,303 @@
+"""ctypes binding of librs_oracle.so (rs_oracle.c).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "librs_oracle.so")
+
+LSB, MSB, MSB16, MSB32, JPEG = 0, 1, 2, 3, 4
+OK, RDE, IOE = 0, 1, 2
+
+
+class OracleError(Exception):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+        self.msg = msg
+
+
+class RawDecoderException(OracleError):
+    pass
+
+
+class IOException(OracleError):
+    pass
+
+
+def raise_for(code, msg):
+    if code == OK:
+        return
+    if code == IOE:
+        raise IOException(code, msg)
+    raise RawDecoderException(code, msg)
+
+
+class Err(C.Structure):
+    _fields_ = [("code", C.c_int), ("msg", C.c_char * 240)]
+
+    def check(self, rc):
+        raise_for(rc, self.msg.decode("utf-8", "replace"))
+
+
+class Image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("w", C.c_int), ("h", C.c_int),
+                ("cpp", C.c_int), ("pitch", C.c_int), ("is_cfa", C.c_int),
+                ("sub_x", C.c_int), ("sub_y", C.c_int)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("mcu_x", C.c_int), ("mcu_y", C.c_int), ("dim_x", C.c_int),
+                ("dim_y", C.c_int)]
+
+
+class Dht(C.Structure):
+    _fields_ = [("ncpl", C.c_uint8 * 16), ("values", C.c_uint8 * 162),
+                ("nvalues", C.c_int)]
+
+
+def build(force=False):
+    """(Re)build librs_oracle.so with gcc; returns its path."""
+    src = os.path.join(_HERE, "rs_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "rs_oracle.h"))):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.rso_huff_create.restype = C.c_void_p
+        _lib.rso_huff_destroy.argtypes = [C.c_void_p]
+        _lib.rso_huff_symbols.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.rso_huff_decode.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int,
+                                         C.c_int, C.c_void_p, C.POINTER(Err)]
+        _lib.rso_encode_diffs.restype = C.c_int64
+        _lib.rso_ljpeg_encode.restype = C.c_int64
+        _lib.rso_cr2_encode.restype = C.c_int64
+    return _lib
+
+
+def image_pitch(w, cpp=1):
+    return lib().rso_image_pitch(w, cpp)
+
+
+def new_image(w, h, cpp=1, fill=0xA5A5):
+    """Uncropped uint16 buffer, shape (h, pitch/2), like RawImageData::createData."""
+    pitch = image_pitch(w, cpp)
+    return np.full((h, pitch // 2), fill, dtype=np.uint16)
+
+
+def _img(arr, w, cpp, is_cfa=True, sub=(1, 1)):
+    assert arr.dtype == np.uint16 and arr.flags.c_contiguous
+    return Image(arr.ctypes.data, w, arr.shape[0], cpp, arr.shape[1] * 2,
+                 1 if is_cfa else 0, sub[0], sub[1])
+
+
+def _u8(data):
+    if isinstance(data, np.ndarray):
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        return data.ctypes.data_as(C.c_char_p), data.size
+    b = bytes(data)
+    return b, len(b)
+
+
+def pump_getbits(order, data, lens, want_pos=False):
+    p, n = _u8(data)
+    lens_a = (C.c_int * len(lens))(*lens)
+    out = (C.c_uint32 * len(lens))()
+    pos = C.c_int(0)
+    e = Err()
+    rc = lib().rso_pump_getbits_pos(order, p, n, lens_a, len(lens), out,
+                                    C.byref(pos), C.byref(e))
+    e.check(rc)
+    return (list(out), pos.value) if want_pos else list(out)
+
+
+def huff_extend(diff, length):
+    return lib().rso_huff_extend(C.c_uint32(diff), C.c_uint32(length))
+
+
+class Huff:
+    """HuffmanCode + PrefixCodeDecoder<> (DHT counts/values -> decoder)."""
+
+    def __init__(self, ncpl, values, full=True, fix16=False):
+        self.ncpl = bytes(ncpl)
+        self.values = bytes(values)
+        assert len(self.ncpl) == 16
+        e = Err()
+        self.h = lib().rso_huff_create(self.ncpl, self.values, len(self.values),
+                                       int(full), int(fix16), C.byref(e))
+        if not self.h:
+            raise_for(e.code or RDE, e.msg.decode("utf-8", "replace"))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().rso_huff_destroy(self.h)
+            self.h = None
+
+    def symbols(self):
+        codes = (C.c_uint16 * 162)()
+        lens = (C.c_uint8 * 162)()
+        n = lib().rso_huff_symbols(self.h, codes, lens)
+        return [(codes[i], lens[i]) for i in range(n)]
+
+    def decode(self, data, n, order=JPEG):
+        p, sz = _u8(data)
+        out = (C.c_int32 * n)()
+        e = Err()
+        rc = lib().rso_huff_decode(self.h, order, p, sz, n, out, C.byref(e))
+        e.check(rc)
+        return list(out)
+
+    def dht(self):
+        d = Dht()
+        for i in range(16):
+            d.ncpl[i] = self.ncpl[i]
+        for i, v in enumerate(self.values):
+            d.values[i] = v
+        d.nvalues = len(self.values)
+        return d
+
+
+def _hts(hts):
+    arr = (C.c_void_p * len(hts))(*[h.h for h in hts])
+    return arr
+
+
+def unpack(data, img, w, cpp, crop, in_pitch, bps, order):
+    """UncompressedDecompressor(...).readUncompressedRaw() into img (in place)."""
+    p, n = _u8(data)
+    im = _img(img, w, cpp)
+    e = Err()
+    rc = lib().rso_unpack(p, C.c_uint32(n), C.byref(im), crop[0], crop[1], crop[2],
+                          crop[3], in_pitch, bps, order, C.byref(e))
+    e.check(rc)
+    return img
+
+
+def ljpeg_decompress(img, w, cpp, img_frame, mcu, frame_dim, hts, init_pred,
+                     rows_per_restart, data):
+    p, n = _u8(data)
+    im = _img(img, w, cpp)
+    fr = Frame(mcu[0], mcu[1], frame_dim[0], frame_dim[1])
+    ip = (C.c_uint16 * len(init_pred))(*init_pred)
+    consumed = C.c_uint32(0)
+    e = Err()
+    rc = lib().rso_ljpeg_decompress(C.byref(im), img_frame[0], img_frame[1],
+                                    img_frame[2], img_frame[3], fr, _hts(hts), ip,
+                                    len(hts), rows_per_restart, p, C.c_uint32(n),
+                                    C.byref(consumed), C.byref(e))
+    e.check(rc)
+    return consumed.value
+
+
+def ljpeg_decode(blob, img, w, cpp, off, size, max_dim, fix16=False):
+    p, n = _u8(blob)
+    im = _img(img, w, cpp)
+    e = Err()
+    rc = lib().rso_ljpeg_decode(p, C.c_uint32(n), C.byref(im), off[0], off[1],
+                                size[0], size[1], max_dim[0], max_dim[1],
+                                int(fix16), C.byref(e))
+    e.check(rc)
+    return img
+
+
+def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h,
+                   compression, fix_ljpeg=False, bps=14, big_endian=False,
+                   nthreads=1):
+    p, n = _u8(file_bytes)
+    im = _img(img, w, cpp)
+    offs = (C.c_uint64 * len(tile_off))(*tile_off)
+    lens = (C.c_uint32 * len(tile_len))(*tile_len)
+    e = Err()
+    rc = lib().rso_dng_decompress(p, C.c_uint64(n), offs, lens, len(tile_off),
+                                  C.byref(im), tile_w, tile_h, compression,
+                                  int(fix_ljpeg), bps, int(big_endian), nthreads,
+                                  C.byref(e))
+    e.check(rc)
+    return img
+
+
+def cr2_decompress(img, w, fmt, frame, slicing, hts, init_pred, data, is_cfa=True):
+    p, n = _u8(data)
+    im = _img(img, w, 1, is_cfa)
+    ip = (C.c_uint16 * len(init_pred))(*init_pred)
+    consumed = C.c_uint32(0)
+    e = Err()
+    rc = lib().rso_cr2_decompress(C.byref(im), fmt[0], fmt[1], fmt[2], frame[0],
+                                  frame[1], slicing[0], slicing[1], slicing[2],
+                                  _hts(hts), ip, len(hts), p, C.c_uint32(n),
+                                  C.byref(consumed), C.byref(e))
+    e.check(rc)
+    return consumed.value
+
+
+def cr2_ljpeg_decode(blob, img, w, slicing, is_cfa=True, sub=(1, 1)):
+    p, n = _u8(blob)
+    im = _img(img, w, 1, is_cfa, sub)
+    e = Err()
+    rc = lib().rso_cr2_ljpeg_decode(p, C.c_uint32(n), C.byref(im), slicing[0],
+                                    slicing[1], slicing[2], C.byref(e))
+    e.check(rc)
+    return img
+
+
+# ---------------- test-input tooling ----------------
+def encode_diffs(diffs, hts, comp_of):
+    d = np.ascontiguousarray(diffs, dtype=np.int32)
+    cap = d.size * 5 + 64
+    out = np.empty(cap, dtype=np.uint8)
+    co = (C.c_uint8 * len(comp_of))(*comp_of)
+    n = lib().rso_encode_diffs(d.ctypes.data_as(C.c_void_p), C.c_uint64(d.size),
+                               _hts(hts), co, len(comp_of),
+                               out.ctypes.data_as(C.c_void_p), C.c_uint64(cap))
+    if n < 0:
+        raise ValueError("encode_diffs failed (%d)" % n)
+    return out[:n].tobytes()
+
+
+def _dhts(tabs):
+    arr = (Dht * len(tabs))()
+    for i, t in enumerate(tabs):
+        arr[i] = t.dht() if isinstance(t, Huff) else t
+    return arr
+
+
+def ljpeg_encode(samples, frame_w, frame_h, mcu, prec, tabs, tab_of_comp,
+                 restart_rows=0, fix16=False):
+    """samples: 2-D uint16 array, rows = frame_h*mcu_y, cols >= frame_w*mcu_x."""
+    s = np.ascontiguousarray(samples, dtype=np.uint16)
+    assert s.shape[0] >= frame_h * mcu[1] and s.shape[1] >= frame_w * mcu[0]
+    cap = int(frame_w) * frame_h * mcu[0] * mcu[1] * 5 + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    toc = (C.c_uint8 * len(tab_of_comp))(*tab_of_comp)
+    n = lib().rso_ljpeg_encode(s.ctypes.data_as(C.c_void_p), s.shape[1], frame_w,
+                               frame_h, mcu[0], mcu[1], prec, _dhts(tabs), len(tabs),
+                               toc, restart_rows, int(fix16),
+                               out.ctypes.data_as(C.c_void_p), C.c_uint64(cap))
+    if n < 0:
+        raise ValueError("ljpeg_encode failed (%d)" % n)
+    return out[:n].copy()
+
+
+def cr2_encode(img, w, fmt, frame, slicing, prec, tabs, tab_of_comp, is_cfa=True):
+    im = _img(img, w, 1, is_cfa)
+    cap = int(img.shape[0]) * w * 5 + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    toc = (C.c_uint8 * len(tab_of_comp))(*tab_of_comp)
+    n = lib().rso_cr2_encode(C.byref(im), fmt[0], fmt[1], fmt[2], frame[0], frame[1],
+                             slicing[0], slicing[1], slicing[2], prec, _dhts(tabs),
+                             len(tabs), toc, out.ctypes.data_as(C.c_void_p),
+                             C.c_uint64(cap))
+    if n < 0:
+        raise ValueError("cr2_encode failed (%d)" % n)
+    return out[:n].copy()

@@ -1,0 +1,188 @@
+"""ctypes binding of oracle/_ref/libref.so -- the UNMODIFIED reference compiled
+from /root/reference (see oracle/Makefile, oracle/ref_driver.cpp).
+TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .port import (Err, raise_for, _u8, Huff, JPEG)  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_ref", "libref.so")
+REF_SRC = "/root/reference/src/librawspeed"
+
+
+class HuffDesc(C.Structure):
+    _fields_ = [("ncpl", C.c_uint8 * 16), ("values", C.c_uint8 * 162),
+                ("nvalues", C.c_int)]
+
+
+def build():
+    """Build _ref/libref.so when the reference sources are present (this
+    container); on the GPU box the prebuilt file is used as-is."""
+    if os.path.isdir(REF_SRC):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-j8", "ref"])
+    return os.path.exists(_LIB)
+
+
+def available():
+    return os.path.exists(_LIB)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            build()
+        _lib = C.CDLL(_LIB)
+        _lib.ref_encode_diffs.restype = C.c_int64
+    return _lib
+
+
+def image_pitch(w, h, cpp=1):
+    return lib().ref_image_pitch(w, h, cpp)
+
+
+def pump_getbits(order, data, lens, want_pos=False):
+    p, n = _u8(data)
+    lens_a = (C.c_int * len(lens))(*lens)
+    out = (C.c_uint32 * len(lens))()
+    pos = C.c_int(0)
+    e = Err()
+    rc = lib().ref_pump_getbits(order, p, n, lens_a, len(lens), out, C.byref(pos),
+                                C.byref(e))
+    e.check(rc)
+    return (list(out), pos.value) if want_pos else list(out)
+
+
+def huff_check(ncpl, values, full=True, fix16=False):
+    e = Err()
+    rc = lib().ref_huff_check(bytes(ncpl), bytes(values), len(values), int(full),
+                              int(fix16), C.byref(e))
+    e.check(rc)
+
+
+def huff_decode(ncpl, values, data, n, full=True, fix16=False, order=JPEG):
+    p, sz = _u8(data)
+    out = (C.c_int32 * n)()
+    e = Err()
+    rc = lib().ref_huff_decode(bytes(ncpl), bytes(values), len(values), int(full),
+                               int(fix16), order, p, sz, n, out, C.byref(e))
+    e.check(rc)
+    return list(out)
+
+
+def encode_diffs(diffs, ncpl, values, fix16=False):
+    d = np.ascontiguousarray(diffs, dtype=np.int32)
+    cap = d.size * 5 + 64
+    out = np.empty(cap, dtype=np.uint8)
+    n = lib().ref_encode_diffs(d.ctypes.data_as(C.c_void_p), C.c_uint64(d.size),
+                               bytes(ncpl), bytes(values), len(values), int(fix16),
+                               out.ctypes.data_as(C.c_void_p), C.c_uint64(cap))
+    if n < 0:
+        raise ValueError("ref_encode_diffs failed")
+    return out[:n].tobytes()
+
+
+def _descs(tabs):
+    arr = (HuffDesc * len(tabs))()
+    for i, t in enumerate(tabs):
+        for k in range(16):
+            arr[i].ncpl[k] = t.ncpl[k]
+        for k, v in enumerate(t.values):
+            arr[i].values[k] = v
+        arr[i].nvalues = len(t.values)
+    return arr
+
+
+def unpack(data, img, w, cpp, crop, in_pitch, bps, order, reps=1):
+    p, n = _u8(data)
+    ms = C.c_double(0)
+    e = Err()
+    rc = lib().ref_unpack(p, C.c_uint32(n), C.c_void_p(img.ctypes.data), w,
+                          img.shape[0], cpp, img.shape[1] * 2, crop[0], crop[1],
+                          crop[2], crop[3], in_pitch, bps, order, reps, C.byref(ms),
+                          C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
+def ljpeg_decompress(img, w, cpp, img_frame, mcu, frame_dim, tabs, tab_of_comp,
+                     init_pred, rows_per_restart, data, fix16=False):
+    p, n = _u8(data)
+    toc = (C.c_int * len(tab_of_comp))(*tab_of_comp)
+    ip = (C.c_uint16 * len(init_pred))(*init_pred)
+    consumed = C.c_uint32(0)
+    e = Err()
+    rc = lib().ref_ljpeg_decompress(
+        C.c_void_p(img.ctypes.data), w, img.shape[0], cpp, img.shape[1] * 2,
+        img_frame[0], img_frame[1], img_frame[2], img_frame[3], mcu[0], mcu[1],
+        frame_dim[0], frame_dim[1], _descs(tabs), toc, ip, len(tab_of_comp),
+        int(fix16), rows_per_restart, p, C.c_uint32(n), C.byref(consumed),
+        C.byref(e))
+    e.check(rc)
+    return consumed.value
+
+
+def ljpeg_decode(blob, img, w, cpp, off, size, max_dim, fix16=False):
+    p, n = _u8(blob)
+    e = Err()
+    rc = lib().ref_ljpeg_decode(p, C.c_uint32(n), C.c_void_p(img.ctypes.data), w,
+                                img.shape[0], cpp, img.shape[1] * 2, off[0], off[1],
+                                size[0], size[1], max_dim[0], max_dim[1], int(fix16),
+                                C.byref(e))
+    e.check(rc)
+    return img
+
+
+def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h,
+                   compression, fix_ljpeg=False, bps=14, big_endian=False,
+                   nthreads=1, reps=1):
+    """Returns best-of-`reps` wall time (ms) of AbstractDngDecompressor::decompress()."""
+    p, n = _u8(file_bytes)
+    offs = (C.c_uint64 * len(tile_off))(*tile_off)
+    lens = (C.c_uint32 * len(tile_len))(*tile_len)
+    ms = C.c_double(0)
+    e = Err()
+    rc = lib().ref_dng_decompress(p, C.c_uint64(n), offs, lens, len(tile_off),
+                                  C.c_void_p(img.ctypes.data), w, img.shape[0], cpp,
+                                  img.shape[1] * 2, tile_w, tile_h, compression,
+                                  int(fix_ljpeg), bps, int(big_endian), nthreads,
+                                  reps, C.byref(ms), C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
+def cr2_decompress(img, w, fmt, frame, slicing, tabs, tab_of_comp, init_pred, data,
+                   is_cfa=True, reps=1, want_ms=False):
+    p, n = _u8(data)
+    toc = (C.c_int * len(tab_of_comp))(*tab_of_comp)
+    ip = (C.c_uint16 * len(init_pred))(*init_pred)
+    consumed = C.c_uint32(0)
+    ms = C.c_double(0)
+    e = Err()
+    rc = lib().ref_cr2_decompress(C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                  img.shape[1] * 2, int(is_cfa), fmt[0], fmt[1],
+                                  fmt[2], frame[0], frame[1], slicing[0], slicing[1],
+                                  slicing[2], _descs(tabs), toc, ip,
+                                  len(tab_of_comp), p, C.c_uint32(n),
+                                  C.byref(consumed), reps, C.byref(ms), C.byref(e))
+    e.check(rc)
+    return (consumed.value, ms.value) if want_ms else consumed.value
+
+
+def cr2_ljpeg_decode(blob, img, w, slicing, is_cfa=True, sub=(1, 1), reps=1):
+    p, n = _u8(blob)
+    ms = C.c_double(0)
+    e = Err()
+    rc = lib().ref_cr2_ljpeg_decode(p, C.c_uint32(n), C.c_void_p(img.ctypes.data), w,
+                                    img.shape[0], img.shape[1] * 2, int(is_cfa),
+                                    sub[0], sub[1], slicing[0], slicing[1],
+                                    slicing[2], reps, C.byref(ms), C.byref(e))
+    e.check(rc)
+    return ms.value

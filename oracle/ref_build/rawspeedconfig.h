@@ -1,0 +1,19 @@
+#pragma once
+#if defined(__SSE2__)
+#define WITH_SSE2
+#endif
+static constexpr unsigned long long RAWSPEED_CACHELINESIZE = 64;
+static constexpr unsigned long long RAWSPEED_PAGESIZE = 4096;
+static constexpr unsigned long long RAWSPEED_LARGEPAGESIZE = 4096;
+#define HAVE_OPENMP
+#define HAVE_CXX_THREAD_LOCAL
+#ifndef __has_feature
+#define __has_feature(x) 0
+#endif
+#ifndef __has_extension
+#define __has_extension __has_feature
+#endif
+#define RAWSPEED_UNLIKELY_FUNCTION __attribute__((cold))
+#define RAWSPEED_NOINLINE __attribute__((noinline))
+#define RAWSPEED_READONLY __attribute__((pure))
+#define RAWSPEED_READNONE __attribute__((const))

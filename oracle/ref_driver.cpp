@@ -1,0 +1,405 @@
+/*
+ * ref_driver.cpp -- thin extern "C" shim over the UNMODIFIED reference
+ * (darktable-org/rawspeed), compiled from the sources where they lie under
+ * /root/reference by oracle/Makefile into oracle/_ref/libref.so.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Used (a) to pin oracle/rs_oracle.c against the
+ * real reference, (b) as the "reference" CPU baseline in bench.py.  Nothing in
+ * rawspeed_b200/ may load it.  No reference source is copied: this file only
+ * *calls* the reference's public classes:
+ *   UncompressedDecompressor   decompressors/UncompressedDecompressor.h:64-75
+ *   LJpegDecompressor          decompressors/LJpegDecompressor.h:44-94
+ *   LJpegDecoder               decompressors/LJpegDecoder.h:31-48
+ *   AbstractDngDecompressor    decompressors/AbstractDngDecompressor.h:135-150
+ *   Cr2Decompressor            decompressors/Cr2Decompressor.h:125-174
+ *   Cr2LJpegDecoder            decompressors/Cr2LJpegDecoder.h:30-40
+ *   BitStreamer{LSB,MSB,MSB16,MSB32,JPEG}, PrefixCodeDecoder<>, HuffmanCode<>
+ */
+#include "rawspeedconfig.h"
+
+#include "adt/Array1DRef.h"
+#include "adt/Point.h"
+#include "bitstreams/BitStreamerJPEG.h"
+#include "bitstreams/BitStreamerLSB.h"
+#include "bitstreams/BitStreamerMSB.h"
+#include "bitstreams/BitStreamerMSB16.h"
+#include "bitstreams/BitStreamerMSB32.h"
+#include "bitstreams/BitStreams.h"
+#include "bitstreams/BitVacuumerJPEG.h"
+#include "codes/HuffmanCode.h"
+#include "codes/PrefixCodeDecoder.h"
+#include "codes/PrefixCodeVectorEncoder.h"
+#include "common/RawImage.h"
+#include "common/RawspeedException.h"
+#include "decoders/RawDecoderException.h"
+#include "decompressors/AbstractDngDecompressor.h"
+#include "decompressors/Cr2Decompressor.h"
+#include "decompressors/Cr2LJpegDecoder.h"
+#include "decompressors/LJpegDecoder.h"
+#include "decompressors/LJpegDecompressor.h"
+#include "decompressors/UncompressedDecompressor.h"
+#include "io/Buffer.h"
+#include "io/ByteStream.h"
+#include "io/Endianness.h"
+#include "io/IOException.h"
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace rawspeed;
+
+// The consumer supplies the thread count (common/Common.h:41).
+static int g_threads = 1;
+extern "C" int rawspeed_get_number_of_processor_cores() { return g_threads; }
+
+namespace {
+
+struct RefErr {
+  int code;
+  char msg[240];
+};
+
+template <typename F> int guarded(RefErr* e, F&& f) {
+  if (e) {
+    e->code = 0;
+    e->msg[0] = 0;
+  }
+  try {
+    f();
+    return 0;
+  } catch (const IOException& ex) {
+    if (e) {
+      e->code = 2;
+      std::snprintf(e->msg, sizeof e->msg, "%s", ex.what());
+    }
+    return 2;
+  } catch (const RawDecoderException& ex) {
+    if (e) {
+      e->code = 1;
+      std::snprintf(e->msg, sizeof e->msg, "%s", ex.what());
+    }
+    return 1;
+  } catch (const RawspeedException& ex) {
+    if (e) {
+      e->code = 3;
+      std::snprintf(e->msg, sizeof e->msg, "%s", ex.what());
+    }
+    return 3;
+  }
+}
+
+RawImage makeImage(int w, int h, int cpp, bool isCfa, int subX, int subY) {
+  RawImage img = RawImage::create(iPoint2D(w, h), RawImageType::UINT16, cpp);
+  img->isCFA = isCfa;
+  img->metadata.subsampling = iPoint2D(subX, subY);
+  return img;
+}
+
+void copyOut(const RawImage& img, uint16_t* out, int outPitchBytes) {
+  const auto a = img->getU16DataAsUncroppedArray2DRef();
+  for (int r = 0; r < a.height(); ++r)
+    std::memcpy(reinterpret_cast<uint8_t*>(out) +
+                    static_cast<size_t>(r) * outPitchBytes,
+                &a(r, 0), sizeof(uint16_t) * a.width());
+}
+void copyIn(const RawImage& img, const uint16_t* in, int inPitchBytes) {
+  const auto a = img->getU16DataAsUncroppedArray2DRef();
+  for (int r = 0; r < a.height(); ++r)
+    std::memcpy(&a(r, 0),
+                reinterpret_cast<const uint8_t*>(in) +
+                    static_cast<size_t>(r) * inPitchBytes,
+                sizeof(uint16_t) * a.width());
+}
+
+PrefixCodeDecoder<> makeHT(const uint8_t* ncpl, const uint8_t* values,
+                           int nvalues, bool full, bool fix16) {
+  HuffmanCode<BaselineCodeTag> hc;
+  hc.setNCodesPerLength(Buffer(ncpl, 16));
+  hc.setCodeValues(Array1DRef<const uint8_t>(values, nvalues));
+  PrefixCodeDecoder<> ht(std::move(hc));
+  ht.setup(full, fix16);
+  return ht;
+}
+
+template <typename Pump>
+void pumpGet(const uint8_t* data, int size, const int* lens, int n,
+             uint32_t* out, int* pos) {
+  Pump p(Array1DRef<const std::byte>(reinterpret_cast<const std::byte*>(data),
+                                     size));
+  for (int i = 0; i < n; ++i)
+    out[i] = p.getBits(lens[i]);
+  if (pos)
+    *pos = p.getStreamPosition();
+}
+
+} // namespace
+
+extern "C" {
+
+int ref_image_pitch(int w, int h, int cpp) {
+  RawImage img = RawImage::create(iPoint2D(w, h), RawImageType::UINT16, cpp);
+  return img->pitch;
+}
+
+void ref_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+
+int ref_pump_getbits(int order, const uint8_t* data, int size, const int* lens,
+                     int n, uint32_t* out, int* pos, RefErr* e) {
+  return guarded(e, [&] {
+    switch (static_cast<BitOrder>(order)) {
+    case BitOrder::LSB:
+      pumpGet<BitStreamerLSB>(data, size, lens, n, out, pos);
+      break;
+    case BitOrder::MSB:
+      pumpGet<BitStreamerMSB>(data, size, lens, n, out, pos);
+      break;
+    case BitOrder::MSB16:
+      pumpGet<BitStreamerMSB16>(data, size, lens, n, out, pos);
+      break;
+    case BitOrder::MSB32:
+      pumpGet<BitStreamerMSB32>(data, size, lens, n, out, pos);
+      break;
+    case BitOrder::JPEG:
+      pumpGet<BitStreamerJPEG>(data, size, lens, n, out, pos);
+      break;
+    }
+  });
+}
+
+int ref_huff_check(const uint8_t* ncpl, const uint8_t* values, int nvalues,
+                   int full, int fix16, RefErr* e) {
+  return guarded(e, [&] { (void)makeHT(ncpl, values, nvalues, full, fix16); });
+}
+
+int ref_huff_decode(const uint8_t* ncpl, const uint8_t* values, int nvalues,
+                    int full, int fix16, int order, const uint8_t* data,
+                    int size, int n, int32_t* out, RefErr* e) {
+  return guarded(e, [&] {
+    auto ht = makeHT(ncpl, values, nvalues, full, fix16);
+    const Array1DRef<const std::byte> in(
+        reinterpret_cast<const std::byte*>(data), size);
+    if (order == static_cast<int>(BitOrder::JPEG)) {
+      BitStreamerJPEG bs(in);
+      for (int i = 0; i < n; ++i)
+        out[i] = full ? ht.decodeDifference(bs) : ht.decodeCodeValue(bs);
+    } else {
+      BitStreamerMSB bs(in);
+      for (int i = 0; i < n; ++i)
+        out[i] = full ? ht.decodeDifference(bs) : ht.decodeCodeValue(bs);
+    }
+  });
+}
+
+// Encode differences with the reference's own writer half.
+int64_t ref_encode_diffs(const int32_t* diffs, uint64_t n, const uint8_t* ncpl,
+                         const uint8_t* values, int nvalues, int fix16,
+                         uint8_t* out, uint64_t cap) {
+  HuffmanCode<BaselineCodeTag> hc;
+  hc.setNCodesPerLength(Buffer(ncpl, 16));
+  hc.setCodeValues(Array1DRef<const uint8_t>(values, nvalues));
+  PrefixCodeVectorEncoder<BaselineCodeTag> enc(
+      static_cast<PrefixCode<BaselineCodeTag>>(std::move(hc)));
+  enc.setup(true, fix16);
+  std::vector<uint8_t> buf;
+  buf.reserve(n * 2 + 16);
+  {
+    auto bsInserter = std::back_inserter(buf);
+    using BitVacuumer = BitVacuumerJPEG<decltype(bsInserter)>;
+    auto bv = BitVacuumer(bsInserter);
+    for (uint64_t i = 0; i < n; ++i)
+      enc.encodeDifference(bv, diffs[i]);
+  }
+  if (buf.size() > cap)
+    return -1;
+  std::memcpy(out, buf.data(), buf.size());
+  return static_cast<int64_t>(buf.size());
+}
+
+int ref_unpack(const uint8_t* in, uint32_t in_size, uint16_t* img_data, int w,
+               int h, int cpp, int pitch, int crop_x, int crop_y, int crop_w,
+               int crop_h, int in_pitch, int bps, int order, int reps,
+               double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, cpp, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      UncompressedDecompressor u(
+          ByteStream(DataBuffer(Buffer(in, in_size), Endianness::little)), img,
+          iRectangle2D({crop_x, crop_y}, {crop_w, crop_h}), in_pitch, bps,
+          static_cast<BitOrder>(order));
+      u.readUncompressedRaw();
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(
+          best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
+  });
+}
+
+struct RefHuffDesc {
+  uint8_t ncpl[16];
+  uint8_t values[162];
+  int nvalues;
+};
+
+int ref_ljpeg_decompress(uint16_t* img_data, int w, int h, int cpp, int pitch,
+                         int fx, int fy, int fw, int fh, int mcu_x, int mcu_y,
+                         int dim_x, int dim_y, const RefHuffDesc* tabs,
+                         const int* tab_of_comp, const uint16_t* init_pred,
+                         int nrec, int fix16, int rows_per_restart,
+                         const uint8_t* in, uint32_t in_size,
+                         uint32_t* consumed, RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, cpp, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    std::vector<std::unique_ptr<PrefixCodeDecoder<>>> hts;
+    int maxTab = 0;
+    for (int i = 0; i < nrec; ++i)
+      maxTab = std::max(maxTab, tab_of_comp[i]);
+    for (int t = 0; t <= maxTab; ++t)
+      hts.emplace_back(std::make_unique<PrefixCodeDecoder<>>(
+          makeHT(tabs[t].ncpl, tabs[t].values, tabs[t].nvalues, true, fix16)));
+    std::vector<LJpegDecompressor::PerComponentRecipe> rec;
+    rec.reserve(nrec);
+    for (int i = 0; i < nrec; ++i)
+      rec.push_back({*hts[tab_of_comp[i]], init_pred[i]});
+    LJpegDecompressor d(
+        img, iRectangle2D({fx, fy}, {fw, fh}),
+        LJpegDecompressor::Frame{iPoint2D(mcu_x, mcu_y), iPoint2D(dim_x, dim_y)},
+        rec, rows_per_restart,
+        Array1DRef<const uint8_t>(in, static_cast<int>(in_size)));
+    const auto c = d.decode();
+    if (consumed)
+      *consumed = c;
+    copyOut(img, img_data, pitch);
+  });
+}
+
+int ref_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_data,
+                     int w, int h, int cpp, int pitch, uint32_t off_x,
+                     uint32_t off_y, uint32_t tw, uint32_t th, int max_w,
+                     int max_h, int fix16, RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, cpp, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    LJpegDecoder d(ByteStream(DataBuffer(Buffer(in, in_size), Endianness::little)),
+                   img);
+    d.decode(off_x, off_y, tw, th, iPoint2D(max_w, max_h), fix16);
+    copyOut(img, img_data, pitch);
+  });
+}
+
+int ref_dng_decompress(const uint8_t* file, uint64_t file_size,
+                       const uint64_t* tile_off, const uint32_t* tile_len,
+                       int ntiles, uint16_t* img_data, int w, int h, int cpp,
+                       int pitch, int tile_w, int tile_h, int compression,
+                       int fix_ljpeg, int bps, int big_endian, int nthreads,
+                       int reps, double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    const Buffer whole(file, static_cast<Buffer::size_type>(file_size));
+    double best = 1e30;
+    RawImage img = makeImage(w, h, cpp, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const iPoint2D dim(w, h);
+      DngTilingDescription dsc(dim, tile_w, tile_h);
+      AbstractDngDecompressor d(img, dsc, compression, fix_ljpeg, bps, 1);
+      d.slices.reserve(ntiles);
+      for (int n = 0; n < ntiles; ++n) {
+        ByteStream bs(DataBuffer(
+            whole.getSubView(static_cast<Buffer::size_type>(tile_off[n]),
+                             tile_len[n]),
+            big_endian ? Endianness::big : Endianness::little));
+        d.slices.emplace_back(d.dsc, n, bs);
+      }
+      const auto t0 = std::chrono::steady_clock::now();
+      d.decompress();
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(
+          best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
+  });
+}
+
+int ref_cr2_decompress(uint16_t* img_data, int w, int h, int pitch, int is_cfa,
+                       int n_comp, int x_s_f, int y_s_f, int frame_w,
+                       int frame_h, int num_slices, int slice_w,
+                       int last_slice_w, const RefHuffDesc* tabs,
+                       const int* tab_of_comp, const uint16_t* init_pred,
+                       int nrec, const uint8_t* in, uint32_t in_size,
+                       uint32_t* consumed, int reps, double* best_ms,
+                       RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, 1, is_cfa, 1, 1);
+    copyIn(img, img_data, pitch);
+    std::vector<std::unique_ptr<PrefixCodeDecoder<>>> hts;
+    int maxTab = 0;
+    for (int i = 0; i < nrec; ++i)
+      maxTab = std::max(maxTab, tab_of_comp[i]);
+    for (int t = 0; t <= maxTab; ++t)
+      hts.emplace_back(std::make_unique<PrefixCodeDecoder<>>(
+          makeHT(tabs[t].ncpl, tabs[t].values, tabs[t].nvalues, true, false)));
+    using D = Cr2Decompressor<PrefixCodeDecoder<>>;
+    std::vector<D::PerComponentRecipe> rec;
+    rec.reserve(nrec);
+    for (int i = 0; i < nrec; ++i)
+      rec.push_back({*hts[tab_of_comp[i]], init_pred[i]});
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      D d(img, std::make_tuple(n_comp, x_s_f, y_s_f), iPoint2D(frame_w, frame_h),
+          Cr2SliceWidths(num_slices, slice_w, last_slice_w), rec,
+          Array1DRef<const uint8_t>(in, static_cast<int>(in_size)));
+      const auto c = d.decompress();
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(
+          best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+      if (consumed)
+        *consumed = c;
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
+  });
+}
+
+int ref_cr2_ljpeg_decode(const uint8_t* in, uint32_t in_size,
+                         uint16_t* img_data, int w, int h, int pitch, int is_cfa,
+                         int sub_x, int sub_y, int num_slices, int slice_w,
+                         int last_slice_w, int reps, double* best_ms,
+                         RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, 1, is_cfa, sub_x, sub_y);
+    copyIn(img, img_data, pitch);
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      Cr2LJpegDecoder d(
+          ByteStream(DataBuffer(Buffer(in, in_size), Endianness::little)), img);
+      if (num_slices == 0 && slice_w == 0 && last_slice_w == 0)
+        d.decode(Cr2SliceWidths());
+      else
+        d.decode(Cr2SliceWidths(num_slices, slice_w, last_slice_w));
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(
+          best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,165 @@
+/*
+ * rs_oracle.h -- CPU restatement of rawspeed's per-pixel decode hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under rawspeed_b200/ may include, link,
+ * import or execute this.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, and only as the checker.
+ *
+ * Every function cites the reference file:line (relative to
+ * /root/reference/src/librawspeed) whose behaviour it restates.  The
+ * restatement is pinned against (a) the reference's own unit-test vectors
+ * (tests/golden/ JSON files, transcribed from test/librawspeed/...) and (b) the
+ * real reference compiled into oracle/_ref (see oracle/Makefile), see
+ * tests/test_oracle_vs_ref.py.
+ *
+ * Plain C99, no dependencies beyond libc (+ OpenMP for the tile fan-out that
+ * restates AbstractDngDecompressor.cpp:240-252).
+ */
+#ifndef RS_ORACLE_H
+#define RS_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Exception classes of the reference (common/RawspeedException.h:33-95). */
+enum { RSO_OK = 0, RSO_RDE = 1 /* RawDecoderException */, RSO_IOE = 2 /* IOException */ };
+
+/* bitstreams/BitStreams.h:28-35 (same numeric values as enum class BitOrder) */
+enum { RSO_LSB = 0, RSO_MSB = 1, RSO_MSB16 = 2, RSO_MSB32 = 3, RSO_JPEG = 4 };
+
+typedef struct {
+  int code;      /* RSO_OK / RSO_RDE / RSO_IOE */
+  char msg[240]; /* what() */
+} rso_err;
+
+/* uint16 image view == RawImageData (common/RawImage.cpp:68-113): `pitch` bytes
+ * between rows, `w` pixels of `cpp` components each. */
+typedef struct {
+  uint16_t* data;
+  int w, h, cpp;
+  int pitch; /* bytes */
+  int is_cfa; /* RawImageData::isCFA, only consulted by the CR2 path */
+  int sub_x, sub_y; /* ImageMetaData::subsampling (RawImage.h:93), default 1,1 */
+} rso_image;
+
+/* createData(): pitch = roundUp(w*cpp*2, 16) (RawImage.cpp:68-84) */
+int rso_image_pitch(int w, int cpp);
+
+/* ---- bit pumps (bitstreams/BitStreamer.h:135-326, BitStream.h:59-141) ---- */
+/* Probe used by the golden-vector tests: construct pump of `order` over
+ * data[0..size) and perform n getBits(lens[i]) calls -> out[i].
+ * Returns RSO_OK or the exception class (message in e). */
+int rso_pump_getbits(int order, const uint8_t* data, int size, const int* lens,
+                     int n, uint32_t* out, rso_err* e);
+/* Like above, but reports getStreamPosition() after the reads
+ * (BitStreamer.h:229-232, BitStreamerJPEG.h:185-189). */
+int rso_pump_getbits_pos(int order, const uint8_t* data, int size,
+                         const int* lens, int n, uint32_t* out, int* stream_pos,
+                         rso_err* e);
+
+/* ---- Huffman (codes/HuffmanCode.h:66-166, PrefixCodeLUTDecoder.h:95-216,
+ *               PrefixCodeLookupDecoder.h:97-164, AbstractPrefixCodeDecoder.h:43-76) */
+typedef struct rso_huff rso_huff;
+/* ncpl[16] = DHT counts for lengths 1..16, values[nvalues]. */
+rso_huff* rso_huff_create(const uint8_t ncpl[16], const uint8_t* values,
+                          int nvalues, int full_decode, int fix_dng16,
+                          rso_err* e);
+void rso_huff_destroy(rso_huff*);
+/* generateCodeSymbols(): writes up to 162 (code,len) pairs; returns count. */
+int rso_huff_symbols(const rso_huff*, uint16_t* codes, uint8_t* lens);
+/* decodeDifference()/decodeCodeValue() n times from a JPEG (order=RSO_JPEG) or
+ * MSB pump over data. */
+int rso_huff_decode(const rso_huff*, int order, const uint8_t* data, int size,
+                    int n, int32_t* out, rso_err* e);
+/* extend() truth table probe (AbstractPrefixCodeDecoder.h:68-76) */
+int rso_huff_extend(uint32_t diff, uint32_t len);
+
+/* ---- UncompressedDecompressor (decompressors/UncompressedDecompressor.cpp:106-268) */
+int rso_unpack(const uint8_t* in, uint32_t in_size, rso_image* img, int crop_x,
+               int crop_y, int crop_w, int crop_h, int in_pitch, int bps,
+               int order, rso_err* e);
+
+/* ---- LJpegDecompressor (decompressors/LJpegDecompressor.cpp:52-370) ---- */
+typedef struct {
+  int mcu_x, mcu_y; /* Frame::mcu */
+  int dim_x, dim_y; /* Frame::dim (in MCUs) */
+} rso_ljpeg_frame;
+
+int rso_ljpeg_decompress(rso_image* img, int fx, int fy, int fw, int fh,
+                         rso_ljpeg_frame frame, const rso_huff* const* ht,
+                         const uint16_t* init_pred, int nrec,
+                         int rows_per_restart, const uint8_t* in, uint32_t in_size,
+                         uint32_t* consumed, rso_err* e);
+
+/* ---- LJpegDecoder::decode (LJpegDecoder.cpp:66-165 + AbstractLJpegDecoder.cpp:65-291)
+ * Parses a complete SOI..EOI LJPEG blob and decodes it into the tile. */
+int rso_ljpeg_decode(const uint8_t* in, uint32_t in_size, rso_image* img,
+                     uint32_t off_x, uint32_t off_y, uint32_t w, uint32_t h,
+                     int max_w, int max_h, int fix_dng16, rso_err* e);
+
+/* ---- AbstractDngDecompressor::decompress (AbstractDngDecompressor.cpp:54-131,240-252)
+ * compression 1 (uncompressed) and 7 (LJPEG).  tile_off/tile_len index `file`.
+ * `big_endian` = byte order of the tile ByteStreams (only matters for comp 1,
+ * bps 8/16/32).  nthreads = rawspeed_get_number_of_processor_cores(). */
+int rso_dng_decompress(const uint8_t* file, uint64_t file_size,
+                       const uint64_t* tile_off, const uint32_t* tile_len,
+                       int ntiles, rso_image* img, int tile_w, int tile_h,
+                       int compression, int fix_ljpeg, int bps, int big_endian,
+                       int nthreads, rso_err* e);
+
+/* ---- Cr2Decompressor (decompressors/Cr2DecompressorImpl.h:279-468) ---- */
+int rso_cr2_decompress(rso_image* img, int n_comp, int x_s_f, int y_s_f,
+                       int frame_w, int frame_h, int num_slices, int slice_w,
+                       int last_slice_w, const rso_huff* const* ht,
+                       const uint16_t* init_pred, int nrec, const uint8_t* in,
+                       uint32_t in_size, uint32_t* consumed, rso_err* e);
+
+/* ---- Cr2LJpegDecoder::decode (Cr2LJpegDecoder.cpp:58-167) ---- */
+int rso_cr2_ljpeg_decode(const uint8_t* in, uint32_t in_size, rso_image* img,
+                         int num_slices, int slice_w, int last_slice_w,
+                         rso_err* e);
+
+/* ===== test-input tooling (NOT part of the decode path) =====
+ * The reference's writer half (BitVacuumerJPEG.h:44-96,
+ * PrefixCodeVectorEncoder.h:79-90, AbstractPrefixCodeEncoder.h:47-58) is
+ * restated so synthetic LJPEG/CR2 streams can be produced on the GPU box. */
+
+/* Encode the entropy-coded segment for `n` differences (full decode tables);
+ * comp_of[i % group] selects ht for sample i.  Output is FF00-stuffed, padded
+ * with 1-bits to a byte.  Returns bytes written or <0 if cap too small. */
+int64_t rso_encode_diffs(const int32_t* diffs, uint64_t n,
+                         const rso_huff* const* ht, const uint8_t* comp_of,
+                         int group, uint8_t* out, uint64_t cap);
+
+/* Build a complete LJPEG blob (SOI,SOF3,DHT...,[DRI],SOS,data,EOI) for a tile.
+ * samples: tile_rows x (frame_w*ncomp) uint16 (MCU mcu_x x mcu_y, ncomp=mcu_x*mcu_y;
+ * for mcu_y==2 two image rows per LJPEG row).  tables: ntab (ncpl,values) pairs;
+ * tab_of_comp selects the table id per component.  restart_rows: 0 = no DRI.
+ * Returns bytes written, <0 on overflow. */
+typedef struct {
+  uint8_t ncpl[16];
+  uint8_t values[162];
+  int nvalues;
+} rso_dht;
+
+int64_t rso_ljpeg_encode(const uint16_t* samples, int src_pitch_elems,
+                         int frame_w, int frame_h, int mcu_x, int mcu_y,
+                         int prec, const rso_dht* tabs, int ntab,
+                         const uint8_t* tab_of_comp, int restart_rows,
+                         int fix_dng16, uint8_t* out, uint64_t cap);
+
+/* Build a CR2-style LJPEG blob whose scan holds the image in Canon slice order
+ * (inverse of Cr2DecompressorImpl.h:396-468) for formats <2,1,1>/<4,1,1>/<3,2,1>/<3,2,2>. */
+int64_t rso_cr2_encode(const rso_image* img, int n_comp, int x_s_f, int y_s_f,
+                       int frame_w, int frame_h, int num_slices, int slice_w,
+                       int last_slice_w, int prec, const rso_dht* tabs, int ntab,
+                       const uint8_t* tab_of_comp, uint8_t* out, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

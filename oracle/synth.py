@@ -1,0 +1,134 @@
+"""Seeded synthetic inputs for the hot path.
+TEST INFRASTRUCTURE ONLY -- inputs for tests and bench, never product code."""
+from concurrent.futures import ThreadPoolExecutor
+import os
+
+import numpy as np
+
+from . import port
+
+# DHT used by the synthetic LJPEG streams: 17 codes, lengths 2..14.
+DEFAULT_NCPL = bytes([0, 1, 5, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0])
+DEFAULT_VALUES = bytes([6, 4, 5, 7, 3, 8, 2, 9, 1, 10, 0, 11, 12, 13, 14, 15, 16])
+# A second, different table (for multi-table scans): lengths 2..15, other order.
+ALT_NCPL = bytes([0, 2, 2, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 1, 0])
+ALT_VALUES = bytes([5, 6, 4, 7, 3, 8, 2, 9, 1, 10, 0, 11, 12, 13, 14, 15, 16])
+
+
+def lcg_u32(n, seed):
+    """s_{k+1} = s_k*1664525 + 1013904223 (mod 2^32); returns s_1..s_n."""
+    a = np.uint32(1664525)
+    c = np.uint32(1013904223)
+    out = np.empty(n, dtype=np.uint32)
+    block = 1 << 16
+    # closed form inside a block, sequential across blocks
+    apow = np.cumprod(np.full(block, a, dtype=np.uint32), dtype=np.uint32)  # a^1..a^B
+    geo = np.empty(block, dtype=np.uint32)  # 1 + a + ... + a^(k-1), k=1..B
+    geo[0] = 1
+    geo[1:] = (np.cumsum(apow[:-1], dtype=np.uint32) + np.uint32(1)).astype(np.uint32)
+    s = np.uint32(seed)
+    with np.errstate(over="ignore"):
+        for lo in range(0, n, block):
+            m = min(block, n - lo)
+            out[lo:lo + m] = apow[:m] * s + c * geo[:m]
+            s = out[lo + m - 1]
+    return out
+
+
+def lcg_bytes(n, seed):
+    """byte_k = s_k >> 24 (SURVEY 8d C1/C2 input)."""
+    return (lcg_u32(n, seed) >> np.uint32(24)).astype(np.uint8)
+
+
+def packed_frame(w, h, bps, seed, pitch=None):
+    """Random packed frame of `h` rows, pitch bytes per row (default minimal)."""
+    row_bytes = w * bps // 8
+    pitch = pitch or row_bytes
+    return lcg_bytes(pitch * h, seed), pitch
+
+
+def image_model(w, h, seed=12345, wild=False, bits=14):
+    """px(x,y) = (2000 + ((7x+3y)&1023) + noise6 - 32) & mask  (SURVEY 8d C3);
+    `wild`: full-range noise (long codes, diff lengths up to 15/16)."""
+    mask = (1 << bits) - 1
+    r = lcg_u32(w * h, seed).reshape(h, w)
+    if wild:
+        return ((r >> np.uint32(32 - bits)) & np.uint32(mask)).astype(np.uint16)
+    y, x = np.mgrid[0:h, 0:w].astype(np.uint32)
+    noise6 = (r >> np.uint32(26)) & np.uint32(63)
+    v = (np.uint32(2000) + ((np.uint32(7) * x + np.uint32(3) * y) & np.uint32(1023))
+         + noise6 - np.uint32(32)) & np.uint32(mask)
+    return v.astype(np.uint16)
+
+
+def default_tables(n=1):
+    tabs = [port.Huff(DEFAULT_NCPL, DEFAULT_VALUES)]
+    if n > 1:
+        tabs.append(port.Huff(ALT_NCPL, ALT_VALUES))
+    return tabs
+
+
+class DngTiles:
+    """A synthetic tiled-DNG payload: `blob` holds the per-tile LJPEG streams."""
+
+    def __init__(self, blob, offsets, lengths, w, h, cpp, tile_w, tile_h):
+        self.blob, self.offsets, self.lengths = blob, offsets, lengths
+        self.w, self.h, self.cpp = w, h, cpp
+        self.tile_w, self.tile_h = tile_w, tile_h
+
+
+def make_dng_ljpeg(img, tile_w, tile_h, ncomp=2, prec=14, tabs=None,
+                   tab_of_comp=None, restart_rows=0, fix16=False, mcu=None,
+                   align=1, threads=None, cpp=1):
+    """Encode `img` (h x (w*cpp) uint16, logical pixels only) as DNG LJPEG tiles
+    (edge tiles encoded full-size with edge replication, as DNG writers do)."""
+    h, wc = img.shape
+    w = wc // cpp
+    tabs = tabs or default_tables(1)
+    mcu = mcu or (ncomp, 1)
+    tab_of_comp = tab_of_comp or [0] * (mcu[0] * mcu[1])
+    tiles_x = (w + tile_w - 1) // tile_w
+    tiles_y = (h + tile_h - 1) // tile_h
+    frame_w = tile_w * cpp // mcu[0]
+    frame_h = tile_h // mcu[1]
+
+    def enc(n):
+        ty, tx = divmod(n, tiles_x)
+        ys = np.minimum(np.arange(ty * tile_h, (ty + 1) * tile_h), h - 1)
+        xs = np.minimum(np.arange(tx * tile_w, (tx + 1) * tile_w), w - 1)
+        if cpp == 1:
+            tile = img[np.ix_(ys, xs)]
+        else:
+            cols = (xs[:, None] * cpp + np.arange(cpp)[None, :]).reshape(-1)
+            tile = img[np.ix_(ys, cols)]
+        return port.ljpeg_encode(np.ascontiguousarray(tile), frame_w, frame_h, mcu,
+                                 prec, tabs, tab_of_comp, restart_rows, fix16)
+
+    n_tiles = tiles_x * tiles_y
+    threads = threads or min(32, os.cpu_count() or 1)
+    if n_tiles > 4 and threads > 1:
+        with ThreadPoolExecutor(threads) as ex:
+            blobs = list(ex.map(enc, range(n_tiles)))
+    else:
+        blobs = [enc(n) for n in range(n_tiles)]
+    offsets, lengths, pos = [], [], 0
+    for b in blobs:
+        pos = (pos + align - 1) // align * align
+        offsets.append(pos)
+        lengths.append(len(b))
+        pos += len(b)
+    blob = np.zeros(pos, dtype=np.uint8)
+    for o, b in zip(offsets, blobs):
+        blob[o:o + len(b)] = b
+    return DngTiles(blob, offsets, lengths, w, h, cpp, tile_w, tile_h)
+
+
+def md5_of_row_md5s(img, row_bytes=None):
+    """rstest's image hash: md5 of the concatenated per-row md5 digests of the
+    uncropped buffer (src/utilities/rstest/rstest.cpp:131-146)."""
+    import hashlib
+    rows = []
+    for r in range(img.shape[0]):
+        b = img[r].tobytes()
+        rows.append(hashlib.md5(b if row_bytes is None else b[:row_bytes]).digest())
+    return hashlib.md5(b"".join(rows)).hexdigest()
