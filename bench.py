@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the rawspeed_b200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Metric (BASELINE.json): MPixels/s decoded (bit-exact); achieved HBM GB/s vs roofline.
+Headline workload (configs[1]): 14-bit packed unpack, 8256x5504 (45 MP) frames,
+a batch of --frames frames per step, inputs resident in HBM (`value`) and through
+the host-buffer C-ABI call with H2D/D2H inside the timed region (`e2e`).
+`others` carries the same device-timed measurement for the LJPEG configs
+(configs[2] DNG tiles, configs[3] CR2).
+
+One JSON line on stdout (rank 0).  A "step" = one pass of the hot path over one
+batch of synthetic input.  Under torchrun each rank decodes its own batch (the
+path shards by frame with no data-path collective -> weak scaling); the optional
+NVLink output gather is timed separately (`gather`).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, BPS = 8256, 5504, 14
+PIX = W * H
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------
+def unpack_jobs(rs, frames, in_frame_bytes, out_frame_bytes, pitch, out_pitch, order):
+    jobs = []
+    for f in range(frames):
+        j = rs.UnpackJob()
+        j.in_offset = f * in_frame_bytes
+        j.in_size = pitch * H
+        j.out_offset = f * out_frame_bytes
+        j.out_pitch = out_pitch
+        j.row0, j.rows, j.samples, j.out_col0 = 0, H, W, 0
+        j.in_pitch, j.bps, j.order = pitch, BPS, order
+        jobs.append(j)
+    return jobs
+
+
+def align(x, a=256):
+    return (x + a - 1) // a * a
+
+
+def time_steps(torch, fn, steps, warmup, dist=None):
+    """W untimed + K timed steps, CUDA events on the launching (current) stream,
+    barrier + synchronize on both sides, max over ranks.  Returns total ms."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    torch.cuda.synchronize()
+    return ms
+
+
+def wall_steps(torch, fn, steps, warmup, dist=None):
+    """Same contract for the host-API path (its timed region is host-driven:
+    pinned H2D + kernels + D2H, synchronous); wall clock bracketed by syncs."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def cpu_reference_unpack(sample_frames=1, reps=3):
+    """The reference's own CPU path on this box's host cores (bounded sample)."""
+    import oracle
+    from oracle import port, synth
+    ncores = os.cpu_count() or 1
+    data, pitch = synth.packed_frame(W, H, BPS, seed=2)
+    img = port.new_image(W, H)
+    if oracle.HAVE_REF:
+        ref = oracle.ref
+        # (a) as shipped: UncompressedDecompressor is single threaded
+        ms1 = min(ref.unpack(data, img, W, 1, (0, 0, W, H), pitch, BPS, port.MSB, reps=1)
+                  for _ in range(reps))
+        # (b) the reference's best OpenMP shape: rows split into one strip per core,
+        #     fanned out by its own AbstractDngDecompressor (compression 1)
+        th = (H + ncores - 1) // ncores
+        nt = (H + th - 1) // th
+        offs = [n * th * pitch for n in range(nt)]
+        lens = [min(th, H - n * th) * pitch for n in range(nt)]
+        # tile height th: last tile shorter; AbstractDngDecompressor wants full-size
+        # tiles in the buffer only for the rows it reads
+        msn = min(ref.dng_decompress(data, offs, lens, img, W, 1, W, th, 1, bps=BPS,
+                                     nthreads=ncores, reps=1) for _ in range(reps))
+        return {"kind": "reference", "cores": ncores,
+                "value": PIX / (msn * 1e-3) / 1e6, "unit": "MPixels/s",
+                "single_thread_value": PIX / (ms1 * 1e-3) / 1e6,
+                "sample": "1 frame 8256x5504 14-bit MSB, best of %d; value = "
+                          "AbstractDngDecompressor(compression 1) over %d row strips with %d "
+                          "OpenMP threads; single_thread_value = UncompressedDecompressor as "
+                          "shipped (no OpenMP)" % (reps, nt, ncores)}
+    t0 = time.perf_counter()
+    port.unpack(data, img, W, 1, (0, 0, W, H), pitch, BPS, port.MSB)
+    ms = (time.perf_counter() - t0) * 1e3
+    return {"kind": "port", "cores": 1, "value": PIX / (ms * 1e-3) / 1e6,
+            "unit": "MPixels/s", "sample": "1 frame 8256x5504 14-bit MSB, oracle C port"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = None
+    ms_tot = 0.0
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_reference_unpack(reps=1)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {
+        "impl": "reference", "metric": "MPixels/s decoded (bit-exact)", "value": v,
+        "unit": "MPixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": PIX / v / 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": "configs[1]: 14-bit packed unpack 8256x5504 (45 MP), 1 frame per "
+                               "step (bounded sample of the GPU arm's batch)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--skip-others", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+    torch.cuda.set_device(local)
+    import rawspeed_b200 as rs
+    from oracle import port, synth  # checker + synthetic inputs only
+    ctx = rs.Context(local)
+
+    F = args.frames
+    peak, peak_src = measured_peaks()
+
+    # ---------------- headline: 14-bit packed unpack ----------------
+    data, pitch = synth.packed_frame(W, H, BPS, seed=2 + rank)
+    out_pitch = rs.image_pitch(W)
+    in_fb = align(pitch * H)
+    out_fb = align(out_pitch * H)
+    h_in = torch.empty(F * in_fb, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(F * out_fb, dtype=torch.uint8).pin_memory()
+    hv = h_in.numpy()
+    for f in range(F):
+        # distinct frames: frame f = frame 0 with its bytes rotated by f
+        hv[f * in_fb:f * in_fb + pitch * H] = np.roll(data, f * 7919)
+    d_in = h_in.cuda()
+    d_out = torch.zeros(F * out_fb, dtype=torch.uint8, device="cuda")
+    plan = rs.unpack_plan(ctx, unpack_jobs(rs, F, in_fb, out_fb, pitch, out_pitch, rs.MSB))
+    in_b, out_b, pixels = plan.bytes()
+
+    # parity gate (not timed): frame 0 and the last frame against the oracle
+    plan.run(d_in, d_out)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    bit_exact = True
+    for f in (0, F - 1):
+        want = port.new_image(W, H)
+        port.unpack(hv[f * in_fb:f * in_fb + pitch * H], want, W, 1, (0, 0, W, H), pitch, BPS, port.MSB)
+        g = got[f * out_fb:f * out_fb + out_pitch * H].view(np.uint16).reshape(H, out_pitch // 2)
+        bit_exact &= bool(np.array_equal(g[:, :W], want[:, :W]))
+    if not bit_exact:
+        print(json.dumps({"error": "GPU output differs from the oracle; no number reported"}))
+        sys.exit(1)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    ms = time_steps(torch, lambda: plan.run(d_in, d_out), args.steps, args.warmup, dist)
+    launches = ctx.launches - l0 - args.warmup * plan.launches
+    # keep the GPU under the same load while the sampler is still running
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_per_step = ms / args.steps
+    value = world * pixels * args.steps / (ms * 1e-3) / 1e6
+    ach = (in_b + out_b) / (ms_per_step * 1e-3) / 1e9  # per GPU, one launch per step
+    roofline = {"bound": "hbm", "kernel": "unpack_kernel<14,MSB>", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": in_b + out_b,
+                "read_only_frac": (in_b / (ms_per_step * 1e-3) / 1e9) / peak,
+                "launches_per_step": plan.launches}
+
+    # ---------------- e2e: host buffers through the C-ABI call ----------------
+    def e2e_step():
+        plan.run_host(h_in.numpy(), h_out.numpy())
+    e2e_steps = max(3, min(args.steps, 5))
+    ms_e = wall_steps(torch, e2e_step, e2e_steps, 1, dist)
+    e2e = {"value": world * pixels * e2e_steps / (ms_e * 1e-3) / 1e6, "unit": "MPixels/s",
+           "h2d_bytes_per_step": int(F * in_fb), "d2h_bytes_per_step": int(F * out_fb),
+           "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
+           "api": "rsb200_plan_run_host (pinned host buffers, H2D + kernel + D2H per step)"}
+    ok = np.array_equal(h_out.numpy()[:out_pitch * H], got[:out_pitch * H])
+    e2e["bit_exact"] = bool(ok)
+
+    others = {}
+    if not args.skip_others:
+        others = bench_others(torch, rs, ctx, port, synth, args, dist, peak)
+
+    gather = None
+    if dist is not None:
+        gather = bench_gather(torch, dist, d_out, world, rank, plan, d_in, args)
+
+    if rank == 0:
+        cpu = None if args.skip_cpu else cpu_reference_unpack()
+        line = {
+            "metric": "MPixels/s decoded (bit-exact)", "value": value, "unit": "MPixels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": "configs[1]: 14-bit packed (MSB) unpack, 8256x5504 (45 MP), "
+                                   "%d frames per step per GPU" % F,
+                       "frames_per_step_per_gpu": F, "bytes_per_step_per_gpu": in_b + out_b,
+                       "l2": "inputs+outputs of one step (%.2f GB) exceed the 126 MB L2; no flush "
+                             "needed" % ((in_b + out_b) / 1e9),
+                       "parallelism": "frames sharded across ranks, no data-path collective"},
+            "bit_exact": bit_exact, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "others": others,
+        }
+        if gather:
+            line["gather"] = gather
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_gather(torch, dist, d_out, world, rank, plan, d_in, args):
+    """north_star's NVLink output gather (all ranks' decoded frames -> every rank),
+    timed separately from the decode: NCCL all_gather on the decode stream."""
+    shard = d_out
+    full = torch.empty(world * shard.numel(), dtype=torch.uint8, device="cuda")
+
+    def step():
+        plan.run(d_in, d_out)
+        dist.all_gather_into_tensor(full, shard)
+    n = max(2, min(args.steps, 5))
+    ms = time_steps(torch, step, n, 1, dist)
+    return {"what": "decode + ncclAllGather of the uint16 outputs over NVLink",
+            "ms_per_step": ms / n, "gathered_bytes_per_rank": int(full.numel()),
+            "busbw_GBps": (full.numel() * (world - 1) / world) / (ms / n * 1e-3) / 1e9}
+
+
+def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
+    """configs[2] (DNG LJPEG tiles) and configs[3] (CR2): device-timed decode."""
+    from helpers import dng_ljpeg_scans, parse_ljpeg, TableSet
+    out = {}
+    steps = max(3, min(args.steps, 10))
+    # ---- C3: 8256x5504 DNG, 726 LJPEG tiles of 256x256, 2 components ----
+    img = synth.image_model(W, H, 12345)
+    t = synth.make_dng_ljpeg(img, 256, 256)
+    out_pitch = rs.image_pitch(W)
+    tabs, scans = dng_ljpeg_scans(t, out_pitch)
+    plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
+    d_in = torch.zeros(t.blob.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[:t.blob.size] = torch.from_numpy(t.blob)
+    d_out = torch.zeros(H * out_pitch, dtype=torch.uint8, device="cuda")
+    plan.run((d_in.data_ptr(), t.blob.size), d_out)
+    res = plan.results()
+    got = d_out.cpu().numpy().view(np.uint16).reshape(H, out_pitch // 2)
+    exact = bool(np.array_equal(got[:, :W], img)) and all(s == 0 for s, _ in res)
+    ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), t.blob.size), d_out), steps, 3, dist)
+    in_b, out_b, pixels = plan.bytes()
+    per = ms / steps
+    out["configs[2] DNG LJPEG 8256x5504 (726 tiles 256x256)"] = {
+        "MPixels/s": pixels / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
+        "compressed_bytes_per_pixel": t.blob.size / PIX,
+        "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
+        "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak, "launches_per_frame": plan.launches}
+    del plan, d_in, d_out
+    # ---- C4: CR2 6720x4480, 3 slices, 2 and 4 components ----
+    from test_gpu_cr2 import cr2_job
+    cw, ch = 6720, 4480
+    cimg = port.new_image(cw, ch)
+    cimg[:, :cw] = synth.image_model(cw, ch, 4)
+    hts = synth.default_tables(2)
+    for fmt, frame in [((2, 1, 1), (3360, 4480)), ((4, 1, 1), (1680, 4480))]:
+        blob = port.cr2_encode(cimg, cw, fmt, frame, (3, 2240, 2240), 14, hts, [0, 1, 0, 1][:fmt[0]])
+        ts = TableSet()
+        job = cr2_job(blob, cw, ch, fmt, (3, 2240, 2240), cimg.shape[1] * 2, ts)
+        plan = rs.cr2_plan(ctx, ts.tabs, [job])
+        d_in = torch.zeros(blob.size + 64, dtype=torch.uint8, device="cuda")
+        d_in[:blob.size] = torch.from_numpy(blob)
+        d_out = torch.zeros(cimg.size * 2, dtype=torch.uint8, device="cuda")
+        plan.run((d_in.data_ptr(), blob.size), d_out)
+        res = plan.results()
+        got = d_out.cpu().numpy().view(np.uint16).reshape(cimg.shape)
+        exact = bool(np.array_equal(got[:, :cw], cimg[:, :cw])) and res[0][0] == 0
+        ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), blob.size), d_out), 3, 1, dist)
+        per = ms / 3
+        out["configs[3] CR2 6720x4480 3 slices <%d,1,1>" % fmt[0]] = {
+            "MPixels/s": cw * ch / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
+            "compressed_bytes_per_pixel": blob.size / (cw * ch)}
+        del plan, d_in, d_out
+    return out
+
+
+if __name__ == "__main__":
+    main()

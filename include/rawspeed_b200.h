@@ -1,0 +1,205 @@
+/*
+ * rawspeed_b200.h -- C ABI of the B200-native RAW decompression engine.
+ *
+ * This is the drop-in boundary for rawspeed's per-pixel decode hot path.  The
+ * reference (darktable-org/rawspeed) has no FFI layer; its seam is four C++
+ * decompressor classes whose method bodies are the hot path.  Each entry point
+ * below replaces one of those bodies (paths relative to
+ * /root/reference/src/librawspeed):
+ *
+ *   rsb200_unpack_plan_create + rsb200_plan_run
+ *       <- UncompressedDecompressor::readUncompressedRaw / decodePackedInt<Pump>
+ *          decompressors/UncompressedDecompressor.cpp:188-200, 202-268
+ *          (and AbstractDngDecompressor::decompressThread<1>,
+ *           decompressors/AbstractDngDecompressor.cpp:54-110, one job per tile)
+ *   rsb200_ljpeg_plan_create + rsb200_plan_run
+ *       <- LJpegDecompressor::decode / decodeN / decodeRowN
+ *          decompressors/LJpegDecompressor.cpp:184-370
+ *          (and AbstractDngDecompressor::decompressThread<7>,
+ *           decompressors/AbstractDngDecompressor.cpp:112-131: all tiles of a
+ *           frame -- or of a batch of frames -- in one plan)
+ *   rsb200_cr2_plan_create + rsb200_plan_run
+ *       <- Cr2Decompressor<PrefixCodeDecoder<>>::decompress / decompressN_X_Y
+ *          decompressors/Cr2DecompressorImpl.h:396-487
+ *   rsb200_huff_table
+ *       <- HuffmanCode<BaselineCodeTag> + PrefixCodeDecoder<>::setup
+ *          codes/HuffmanCode.h:66-166, codes/PrefixCodeLUTDecoder.h:95-148
+ *          (the DHT contents; the device LUT is built by the library)
+ *
+ * Everything the reference does *around* those bodies -- marker parsing,
+ * geometry validation, exceptions, RawImage allocation -- stays on the host
+ * (rawspeed_b200/csrc/host/, the C++ mirror of the reference classes, calls
+ * this ABI).  Signatures are POD only: plain pointers and sizes, no C++/torch
+ * types.  The caller owns every buffer it passes; the library owns its device
+ * staging/scratch memory.
+ *
+ * There is NO CPU fallback: every entry point fails with RSB200_ERR_CUDA if no
+ * CUDA device / kernel image is usable.
+ *
+ * Threading: a ctx/plan is single-use-at-a-time (like a reference decoder
+ * instance, decoders/RawDecoder.h:39-43); different contexts may run
+ * concurrently.
+ */
+#ifndef RAWSPEED_B200_H
+#define RAWSPEED_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSB200_ABI_VERSION 1
+
+/* Status codes.  RDE/IOE map onto the reference's exception classes
+ * (common/RawspeedException.h:33-95): the host shim turns them into
+ * RawDecoderException / IOException. */
+enum {
+  RSB200_OK = 0,
+  RSB200_ERR_RDE = 1,  /* -> RawDecoderException (e.g. "bad Huffman code") */
+  RSB200_ERR_IOE = 2,  /* -> IOException (bit stream over-read)            */
+  RSB200_ERR_CUDA = 3, /* CUDA failure; message in rsb200_last_error()     */
+  RSB200_ERR_ARG = 4   /* malformed descriptor                             */
+};
+
+/* bitstreams/BitStreams.h:28-35 (enum class BitOrder), same values. */
+enum { RSB200_LSB = 0, RSB200_MSB = 1, RSB200_MSB16 = 2, RSB200_MSB32 = 3 };
+
+typedef struct rsb200_ctx rsb200_ctx;
+typedef struct rsb200_plan rsb200_plan;
+
+int rsb200_abi_version(void);
+
+/* Bind a context to CUDA device `device` (one process per GPU). */
+int rsb200_create(int device, rsb200_ctx** ctx);
+void rsb200_destroy(rsb200_ctx* ctx);
+/* Text of the last failure on this context ("" if none). */
+const char* rsb200_last_error(const rsb200_ctx* ctx);
+/* Number of kernels this context has launched so far (bench: gpu_launches). */
+uint64_t rsb200_kernel_launches(const rsb200_ctx* ctx);
+/* Name of the dominant kernel of a plan kind + its per-launch resource use. */
+int rsb200_device_sm_count(const rsb200_ctx* ctx);
+
+/* ------------------------------------------------------------------ */
+/* K1: packed N-bit unpack.  One job = one strip/tile (one                */
+/* UncompressedDecompressor instance).                                 */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t in_offset;  /* byte offset of the strip inside the input buffer       */
+  uint64_t in_size;    /* bytes of the strip (>= rows*in_pitch; bytes past it read
+                          as 0, BitStreamer.h:100-131)                           */
+  uint64_t out_offset; /* byte offset of image row 0 inside the output buffer    */
+  int32_t out_pitch;   /* bytes between output rows (RawImageData::pitch)        */
+  int32_t row0;        /* first output row  (offset.y)                           */
+  int32_t rows;        /* rows to decode    (min(h+oy, dim.y) - oy)              */
+  int32_t samples;     /* samples per row   (size.x * cpp)                       */
+  int32_t out_col0;    /* first output sample column: 0 for packed integers (the
+                          reference ignores offset.x there,
+                          UncompressedDecompressor.cpp:196); offset.x*cpp for the
+                          16-bit LSB row-copy form (:255-264)                    */
+  int32_t in_pitch;    /* bytes between input rows                               */
+  int32_t bps;         /* 1..16                                                  */
+  int32_t order;       /* RSB200_LSB/MSB/MSB16/MSB32                             */
+} rsb200_unpack_job;
+
+int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_job* jobs,
+                              int njobs, rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
+/* K2+K3: lossless JPEG (Huffman + predictor 1).                        */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint8_t ncodes_per_len[16]; /* DHT Li, i = 1..16                               */
+  uint8_t values[162];        /* DHT Vij: SSSS per code, in code order           */
+  uint16_t nvalues;
+  uint8_t fix_dng16; /* PrefixCodeDecoder::setup(fullDecode=true, fixDNGBug16)   */
+  uint8_t reserved[3];
+} rsb200_huff_table;
+
+/* One entropy-coded segment: one restart interval of one tile (or the whole
+ * tile when DRI is absent).  Geometry follows LJpegDecompressor
+ * (LJpegDecompressor.cpp:52-152). */
+typedef struct {
+  uint64_t in_offset; /* first entropy-coded byte inside the input buffer        */
+  uint32_t in_size;   /* bytes available from there (to the end of the tile's
+                         buffer); the first FFxx (xx!=0) ends the data           */
+  uint32_t rows;      /* LJPEG rows decoded in this segment                      */
+  uint32_t frame_w;   /* MCUs per LJPEG row (Frame::dim.x); all are decoded, only
+                         the first ceil(store_w/mcu_w) are kept                  */
+  uint8_t mcu_w;      /* Frame::mcu: {1,1} {2,1} {3,1} {4,1} {2,2}               */
+  uint8_t mcu_h;
+  uint8_t table[4];   /* index into the plan's table array, per component       */
+  uint8_t reserved[2];
+  uint16_t init_pred[4]; /* PerComponentRecipe::initPred                        */
+  uint64_t out_offset;   /* byte offset of the image (row 0, col 0)             */
+  uint32_t out_pitch;    /* bytes                                               */
+  uint32_t out_x;        /* first output sample column = cpp * imgFrame.pos.x   */
+  uint32_t out_y;        /* first output row of this segment                    */
+  uint32_t store_w;      /* samples kept per row = cpp * imgFrame.dim.x         */
+} rsb200_ljpeg_scan;
+
+typedef struct {
+  uint32_t status;   /* RSB200_OK / RSB200_ERR_RDE / RSB200_ERR_IOE              */
+  uint32_t consumed; /* BitStreamerJPEG::getStreamPosition() after the segment
+                        (BitStreamerJPEG.h:185-189): bytes from in_offset       */
+} rsb200_scan_result;
+
+int rsb200_ljpeg_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables,
+                             int ntables, const rsb200_ljpeg_scan* scans,
+                             int nscans, rsb200_plan** plan);
+
+/* Canon CR2: one job = one frame = one entropy-coded stream
+ * (Cr2DecompressorImpl.h:396-468).  Values are the *validated* ones the
+ * Cr2Decompressor ctor (:279-363) works with. */
+typedef struct {
+  uint64_t in_offset;
+  uint32_t in_size;
+  uint8_t n_comp, x_s_f, y_s_f; /* format <N_COMP, X_S_F, Y_S_F>                 */
+  uint8_t reserved0;
+  uint8_t table[4];
+  uint16_t init_pred[4];
+  int32_t frame_w, frame_h;  /* LJPEG frame (SOF3 w,h after the Canon height fix) */
+  int32_t num_slices;        /* Cr2SliceWidths (CANONCR2SLICE): widths in sample   */
+  int32_t slice_w;           /*   columns, as passed to the Cr2Decompressor ctor   */
+  int32_t last_slice_w;
+  int32_t img_w, img_h;      /* RawImage dim (cpp == 1)                           */
+  uint64_t out_offset;
+  uint32_t out_pitch;
+  uint32_t reserved1;
+} rsb200_cr2_job;
+
+int rsb200_cr2_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables,
+                           int ntables, const rsb200_cr2_job* jobs, int njobs,
+                           rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
+/* Plan execution                                                       */
+/* ------------------------------------------------------------------ */
+/* Device-resident: d_in / d_out are device pointers (16-byte aligned; d_in must
+ * be readable up to the next 16-byte boundary past in_bytes).  Enqueues the
+ * kernels on `stream` (a cudaStream_t, may be 0) and returns without waiting. */
+int rsb200_plan_run(rsb200_plan* plan, const void* d_in, size_t in_bytes,
+                    void* d_out, size_t out_bytes, void* stream);
+/* Host buffers: H2D copy of `in`, kernels, D2H copy of `out` (pinned staging is
+ * the library's), then waits.  `out` must hold the current image contents for
+ * bytes the decode does not write (it is uploaded first when partial != 0). */
+int rsb200_plan_run_host(rsb200_plan* plan, const uint8_t* in, size_t in_bytes,
+                         uint8_t* out, size_t out_bytes, int partial);
+/* Waits for the plan's last run and returns per-segment status/consumed
+ * (nresults = number of scans/jobs; unpack plans report RSB200_OK only).
+ * Return value: first non-OK status, or RSB200_OK. */
+int rsb200_plan_results(rsb200_plan* plan, rsb200_scan_result* results,
+                        int nresults);
+/* Algorithmic byte counts of one run (input bytes read + output bytes written),
+ * for roofline accounting. */
+int rsb200_plan_bytes(const rsb200_plan* plan, uint64_t* in_bytes,
+                      uint64_t* out_bytes, uint64_t* pixels);
+/* Kernels launched by one rsb200_plan_run(). */
+int rsb200_plan_launches(const rsb200_plan* plan);
+void rsb200_plan_destroy(rsb200_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAWSPEED_B200_H */

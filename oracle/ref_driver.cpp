@@ -18,6 +18,7 @@
 #include "rawspeedconfig.h"
 
 #include "adt/Array1DRef.h"
+#include "adt/PartitioningOutputIterator.h"
 #include "adt/Point.h"
 #include "bitstreams/BitStreamerJPEG.h"
 #include "bitstreams/BitStreamerLSB.h"
@@ -207,7 +208,7 @@ int64_t ref_encode_diffs(const int32_t* diffs, uint64_t n, const uint8_t* ncpl,
   std::vector<uint8_t> buf;
   buf.reserve(n * 2 + 16);
   {
-    auto bsInserter = std::back_inserter(buf);
+    auto bsInserter = PartitioningOutputIterator(std::back_inserter(buf));
     using BitVacuumer = BitVacuumerJPEG<decltype(bsInserter)>;
     auto bv = BitVacuumer(bsInserter);
     for (uint64_t i = 0; i < n; ++i)

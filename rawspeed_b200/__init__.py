@@ -1,0 +1,20 @@
+"""rawspeed_b200 -- B200-native (sm_100a) RAW decompression engine for the
+per-pixel decode hot path of darktable-org/rawspeed.
+
+    csrc/             hand-written CUDA kernels + the extern "C" ABI
+                      (include/rawspeed_b200.h) + the C++ host mirror of the
+                      reference's decompressor classes (csrc/host/)
+    _abi.py / api.py  ctypes face of the ABI (plans, contexts)
+    build.py          in-tree nvcc build for sm_100a
+
+Nothing in this package imports oracle/ (the CPU checker).  There is no CPU
+fallback: without the CUDA library and a GPU the API raises."""
+from .api import (Context, Plan, Rsb200Error, RawDecoderException, IOException,  # noqa: F401
+                  huff_table, unpack_plan, ljpeg_plan, cr2_plan, image_pitch, new_image,
+                  UnpackJob, LJpegScan, Cr2Job, HuffTable, LSB, MSB, MSB16, MSB32)
+from . import build as _build  # noqa: F401
+
+__all__ = ["Context", "Plan", "Rsb200Error", "RawDecoderException", "IOException",
+           "huff_table", "unpack_plan", "ljpeg_plan", "cr2_plan", "image_pitch",
+           "new_image", "UnpackJob", "LJpegScan", "Cr2Job", "HuffTable", "LSB", "MSB",
+           "MSB16", "MSB32"]

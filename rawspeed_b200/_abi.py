@@ -1,0 +1,99 @@
+"""ctypes binding of the C ABI (include/rawspeed_b200.h).
+
+The product path is the CUDA library; if it cannot be built/loaded this module
+raises -- there is no CPU fallback."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+OK, ERR_RDE, ERR_IOE, ERR_CUDA, ERR_ARG = 0, 1, 2, 3, 4
+LSB, MSB, MSB16, MSB32 = 0, 1, 2, 3
+
+
+class UnpackJob(C.Structure):
+    _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint64),
+                ("out_offset", C.c_uint64), ("out_pitch", C.c_int32),
+                ("row0", C.c_int32), ("rows", C.c_int32), ("samples", C.c_int32),
+                ("out_col0", C.c_int32), ("in_pitch", C.c_int32), ("bps", C.c_int32),
+                ("order", C.c_int32)]
+
+
+class HuffTable(C.Structure):
+    _fields_ = [("ncodes_per_len", C.c_uint8 * 16), ("values", C.c_uint8 * 162),
+                ("nvalues", C.c_uint16), ("fix_dng16", C.c_uint8),
+                ("reserved", C.c_uint8 * 3)]
+
+
+class LJpegScan(C.Structure):
+    _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint32),
+                ("rows", C.c_uint32), ("frame_w", C.c_uint32), ("mcu_w", C.c_uint8),
+                ("mcu_h", C.c_uint8), ("table", C.c_uint8 * 4),
+                ("reserved", C.c_uint8 * 2), ("init_pred", C.c_uint16 * 4),
+                ("out_offset", C.c_uint64), ("out_pitch", C.c_uint32),
+                ("out_x", C.c_uint32), ("out_y", C.c_uint32), ("store_w", C.c_uint32)]
+
+
+class ScanResult(C.Structure):
+    _fields_ = [("status", C.c_uint32), ("consumed", C.c_uint32)]
+
+
+class Cr2Job(C.Structure):
+    _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint32),
+                ("n_comp", C.c_uint8), ("x_s_f", C.c_uint8), ("y_s_f", C.c_uint8),
+                ("reserved0", C.c_uint8), ("table", C.c_uint8 * 4),
+                ("init_pred", C.c_uint16 * 4), ("frame_w", C.c_int32),
+                ("frame_h", C.c_int32), ("num_slices", C.c_int32),
+                ("slice_w", C.c_int32), ("last_slice_w", C.c_int32),
+                ("img_w", C.c_int32), ("img_h", C.c_int32), ("out_offset", C.c_uint64),
+                ("out_pitch", C.c_uint32), ("reserved1", C.c_uint32)]
+
+
+EXPORTS = [
+    "rsb200_abi_version", "rsb200_create", "rsb200_destroy", "rsb200_last_error",
+    "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
+    "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
+    "rsb200_plan_run_host", "rsb200_plan_results", "rsb200_plan_bytes",
+    "rsb200_plan_launches", "rsb200_plan_destroy",
+]
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building if needed) the CUDA library.  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    L = C.CDLL(path)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.rsb200_abi_version.restype = i32
+    L.rsb200_create.argtypes = [i32, C.POINTER(vp)]
+    L.rsb200_destroy.argtypes = [vp]
+    L.rsb200_destroy.restype = None
+    L.rsb200_last_error.argtypes = [vp]
+    L.rsb200_last_error.restype = C.c_char_p
+    L.rsb200_kernel_launches.argtypes = [vp]
+    L.rsb200_kernel_launches.restype = u64
+    L.rsb200_device_sm_count.argtypes = [vp]
+    L.rsb200_unpack_plan_create.argtypes = [vp, C.POINTER(UnpackJob), i32, C.POINTER(vp)]
+    L.rsb200_ljpeg_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,
+                                           C.POINTER(LJpegScan), i32, C.POINTER(vp)]
+    L.rsb200_cr2_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,
+                                         C.POINTER(Cr2Job), i32, C.POINTER(vp)]
+    L.rsb200_plan_run.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp]
+    L.rsb200_plan_run_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i32]
+    L.rsb200_plan_results.argtypes = [vp, C.POINTER(ScanResult), i32]
+    L.rsb200_plan_bytes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.rsb200_plan_launches.argtypes = [vp]
+    L.rsb200_plan_destroy.argtypes = [vp]
+    L.rsb200_plan_destroy.restype = None
+    _lib = L
+    return L

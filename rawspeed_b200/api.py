@@ -1,0 +1,176 @@
+"""Python face of the C ABI: contexts and plans.
+
+Device memory, streams and process groups come from PyTorch (plumbing); the
+decode itself is the hand-written CUDA in csrc/ reached through ctypes.  If the
+CUDA library or a GPU is missing every call raises: no CPU fallback exists."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import (Cr2Job, HuffTable, LJpegScan, ScanResult, UnpackJob,  # noqa: F401
+                   LSB, MSB, MSB16, MSB32)
+
+
+class Rsb200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rsb200 error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+class RawDecoderException(Rsb200Error):
+    """Mirrors rawspeed::RawDecoderException (decoders/RawDecoderException.h)."""
+
+
+class IOException(Rsb200Error):
+    """Mirrors rawspeed::IOException (io/IOException.h)."""
+
+
+def _raise(code, msg):
+    if code == _abi.ERR_RDE:
+        raise RawDecoderException(code, msg)
+    if code == _abi.ERR_IOE:
+        raise IOException(code, msg)
+    raise Rsb200Error(code, msg)
+
+
+class Context:
+    """One per process / GPU (rsb200_create)."""
+
+    def __init__(self, device=0):
+        self._lib = _abi.load()
+        h = C.c_void_p()
+        rc = self._lib.rsb200_create(int(device), C.byref(h))
+        if rc != _abi.OK:
+            raise Rsb200Error(rc, "rsb200_create(device=%d) failed: no usable CUDA "
+                              "device; there is no CPU fallback" % device)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.rsb200_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def err(self):
+        return self._lib.rsb200_last_error(self.h).decode("utf-8", "replace")
+
+    @property
+    def launches(self):
+        return int(self._lib.rsb200_kernel_launches(self.h))
+
+    @property
+    def sm_count(self):
+        return int(self._lib.rsb200_device_sm_count(self.h))
+
+    def check(self, rc):
+        if rc != _abi.OK:
+            _raise(rc, self.err())
+
+
+def huff_table(ncpl, values, fix16=False):
+    t = HuffTable()
+    for i in range(16):
+        t.ncodes_per_len[i] = ncpl[i]
+    for i, v in enumerate(values):
+        t.values[i] = v
+    t.nvalues = len(values)
+    t.fix_dng16 = 1 if fix16 else 0
+    return t
+
+
+def _ptr_bytes(x):
+    """(device pointer, nbytes) of a torch CUDA tensor or (ptr, nbytes) tuple."""
+    if isinstance(x, tuple):
+        return int(x[0]), int(x[1])
+    return int(x.data_ptr()), int(x.numel() * x.element_size())
+
+
+class Plan:
+    def __init__(self, ctx, handle, nunits):
+        self.ctx = ctx
+        self.h = handle
+        self.nunits = nunits
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx._lib.rsb200_plan_destroy(self.h)
+        self.h = None
+
+    __del__ = close
+
+    def run(self, d_in, d_out, stream=None):
+        """Enqueue the decode on `stream` (torch.cuda.Stream, raw handle or None
+        = torch's current stream).  Asynchronous."""
+        ip, ib = _ptr_bytes(d_in)
+        op, ob = _ptr_bytes(d_out)
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        elif hasattr(stream, "cuda_stream"):
+            stream = stream.cuda_stream
+        rc = self.ctx._lib.rsb200_plan_run(self.h, ip, ib, op, ob, C.c_void_p(stream))
+        self.ctx.check(rc)
+
+    def run_host(self, in_np, out_np, partial=False):
+        """Host buffers in, host buffers out (H2D + kernels + D2H, synchronous)."""
+        assert in_np.flags.c_contiguous and out_np.flags.c_contiguous
+        rc = self.ctx._lib.rsb200_plan_run_host(
+            self.h, in_np.ctypes.data, in_np.nbytes, out_np.ctypes.data,
+            out_np.nbytes, 1 if partial else 0)
+        self.ctx.check(rc)
+
+    def results(self, check=True):
+        """Per-segment (status, consumed); waits for the last run."""
+        arr = (ScanResult * self.nunits)()
+        rc = self.ctx._lib.rsb200_plan_results(self.h, arr, self.nunits)
+        if check:
+            self.ctx.check(rc)
+        return [(r.status, r.consumed) for r in arr]
+
+    def bytes(self):
+        a, b, p = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.ctx._lib.rsb200_plan_bytes(self.h, C.byref(a), C.byref(b), C.byref(p))
+        return a.value, b.value, p.value
+
+    @property
+    def launches(self):
+        return int(self.ctx._lib.rsb200_plan_launches(self.h))
+
+
+def unpack_plan(ctx, jobs):
+    arr = (UnpackJob * len(jobs))(*jobs)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_unpack_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def ljpeg_plan(ctx, tables, scans):
+    ta = (HuffTable * len(tables))(*tables)
+    sa = (LJpegScan * len(scans))(*scans)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_ljpeg_plan_create(ctx.h, ta, len(tables), sa, len(scans),
+                                                C.byref(h)))
+    return Plan(ctx, h, len(scans))
+
+
+def cr2_plan(ctx, tables, jobs):
+    ta = (HuffTable * len(tables))(*tables)
+    ja = (Cr2Job * len(jobs))(*jobs)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_cr2_plan_create(ctx.h, ta, len(tables), ja, len(jobs),
+                                              C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def image_pitch(w, cpp=1):
+    """RawImageData::createData(): pitch = roundUp(w*cpp*2, 16) (RawImage.cpp:80-82)."""
+    return (w * cpp * 2 + 15) // 16 * 16
+
+
+def new_image(w, h, cpp=1, fill=0):
+    return np.full((h, image_pitch(w, cpp) // 2), fill, dtype=np.uint16)

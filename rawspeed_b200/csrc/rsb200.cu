@@ -1,0 +1,738 @@
+// rsb200.cu -- C ABI of the B200-native RAW decompression engine
+// (include/rawspeed_b200.h).  Host-side plan construction + kernel launches.
+// No CPU fallback lives here: every entry point needs a CUDA device.
+
+#include "../../include/rawspeed_b200.h"
+
+#include "ljpeg.cuh"
+#include "unpack.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace rsb200;
+
+// ------------------------------------------------------------------
+struct rsb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  uint64_t launches = 0;
+  char err[512] = {0};
+  // host-API staging (grow only)
+  uint8_t* d_in = nullptr;
+  size_t d_in_cap = 0;
+  uint8_t* d_out = nullptr;
+  size_t d_out_cap = 0;
+  cudaStream_t stream = nullptr;
+};
+
+static int set_err(rsb200_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof c->err, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                    \
+  do {                                                                         \
+    cudaError_t e_ = (expr);                                                   \
+    if (e_ != cudaSuccess)                                                     \
+      return set_err((ctx), RSB200_ERR_CUDA, "%s failed: %s", #expr,           \
+                     cudaGetErrorString(e_));                                  \
+  } while (0)
+
+struct UnpackGroup {
+  int bps_t;  // template bps (0 = generic)
+  bool lsb;
+  UnpackJobDev* d_jobs = nullptr;
+  int njobs = 0;
+  uint32_t nblocks = 0;
+};
+
+struct rsb200_plan {
+  rsb200_ctx* ctx = nullptr;
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2
+  int nunits = 0;
+  uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
+  int launches_per_run = 0;
+  // required extents (validation of run() arguments)
+  uint64_t need_in = 0, need_out = 0;
+  // unpack
+  std::vector<UnpackGroup> groups;
+  // ljpeg
+  DevTable* d_tables = nullptr;
+  DevScan* d_scans = nullptr;
+  DevStrip* d_strips = nullptr;
+  K3RowRef* d_rows = nullptr;
+  uint16_t* d_diffs = nullptr;
+  uint16_t* d_colvals = nullptr;
+  DevResult* d_results = nullptr;
+  DevResult* h_results = nullptr; // pinned
+  uint32_t nrows = 0;
+  int nscans = 0;
+  cudaStream_t last_stream = nullptr;
+  bool ran = false;
+};
+
+extern "C" int rsb200_abi_version(void) { return RSB200_ABI_VERSION; }
+
+extern "C" int rsb200_create(int device, rsb200_ctx** out) {
+  if (!out)
+    return RSB200_ERR_ARG;
+  *out = nullptr;
+  rsb200_ctx* c = new (std::nothrow) rsb200_ctx();
+  if (!c)
+    return RSB200_ERR_CUDA;
+  c->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) {
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) {
+      c->sm_count = prop.multiProcessorCount;
+      if (prop.major < 10)
+        e = cudaErrorNoKernelImageForDevice; // sm_100a only, no fallback path
+    }
+  }
+  if (e == cudaSuccess)
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "rsb200_create: no usable CUDA device (%s); there is no CPU "
+                    "fallback\n",
+            cudaGetErrorString(e));
+    delete c;
+    return RSB200_ERR_CUDA;
+  }
+  // opt in to the dynamic shared memory the kernels need
+  cudaFuncSetAttribute(k2_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(K2Shared));
+  *out = c;
+  return RSB200_OK;
+}
+
+extern "C" void rsb200_destroy(rsb200_ctx* c) {
+  if (!c)
+    return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_in);
+  cudaFree(c->d_out);
+  if (c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char* rsb200_last_error(const rsb200_ctx* c) { return c ? c->err : ""; }
+extern "C" uint64_t rsb200_kernel_launches(const rsb200_ctx* c) { return c ? c->launches : 0; }
+extern "C" int rsb200_device_sm_count(const rsb200_ctx* c) { return c ? c->sm_count : 0; }
+
+// ------------------------------------------------------------------
+// unpack plan
+// ------------------------------------------------------------------
+static int unpack_template_bps(int bps) {
+  return (bps == 8 || bps == 10 || bps == 12 || bps == 14 || bps == 16) ? bps : 0;
+}
+
+extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_job* jobs,
+                                         int njobs, rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "unpack_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  p->kind = 0;
+  p->nunits = njobs;
+  std::map<std::pair<int, bool>, std::vector<UnpackJobDev>> buckets;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_unpack_job& j = jobs[i];
+    if (j.bps < 1 || j.bps > 16 || j.order < 0 || j.order > 3 || j.rows < 0 ||
+        j.samples <= 0 || j.in_pitch <= 0 || j.out_pitch <= 0 || j.row0 < 0 ||
+        j.out_col0 < 0 ||
+        ((uint64_t)j.samples * (uint64_t)j.bps) % 8 != 0 ||
+        (uint64_t)j.in_pitch < ((uint64_t)j.samples * j.bps) / 8 ||
+        (uint64_t)j.rows * (uint64_t)j.in_pitch > j.in_size ||
+        (uint64_t)(j.out_col0 + j.samples) * 2 > (uint64_t)j.out_pitch) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "unpack job %d: malformed descriptor", i);
+    }
+    if (j.rows == 0)
+      continue;
+    UnpackJobDev d;
+    memset(&d, 0, sizeof d);
+    d.in_offset = j.in_offset;
+    d.in_size = j.in_size;
+    d.out_offset = j.out_offset;
+    d.out_pitch = j.out_pitch;
+    d.row0 = j.row0;
+    d.rows = j.rows;
+    d.samples = j.samples;
+    d.out_col0 = j.out_col0;
+    d.in_pitch = j.in_pitch;
+    d.bps = j.bps;
+    d.order = j.order;
+    const int groups = (j.samples + 7) / 8;
+    d.nchunks = (groups + UNPACK_MAX_CHUNK_GROUPS - 1) / UNPACK_MAX_CHUNK_GROUPS;
+    d.chunk_groups = (groups + d.nchunks - 1) / d.nchunks;
+    d.vec_ok = ((j.out_offset % 16) == 0 && (j.out_pitch % 16) == 0 &&
+                (j.out_col0 % 8) == 0)
+                   ? 1u
+                   : 0u;
+    buckets[{unpack_template_bps(j.bps), j.order == RSB200_LSB}].push_back(d);
+    p->in_bytes += (uint64_t)j.rows * ((uint64_t)j.samples * j.bps / 8);
+    p->out_bytes += (uint64_t)j.rows * (uint64_t)j.samples * 2;
+    p->pixels += (uint64_t)j.rows * (uint64_t)j.samples;
+    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + (uint64_t)j.rows * j.in_pitch);
+    p->need_out = std::max<uint64_t>(
+        p->need_out, j.out_offset + (uint64_t)(j.row0 + j.rows - 1) * j.out_pitch +
+                         2ull * (uint64_t)(j.out_col0 + j.samples));
+  }
+  for (auto& kv : buckets) {
+    UnpackGroup g;
+    g.bps_t = kv.first.first;
+    g.lsb = kv.first.second;
+    uint32_t nb = 0;
+    for (auto& d : kv.second) {
+      d.block_begin = nb;
+      nb += (uint32_t)d.rows * (uint32_t)d.nchunks;
+    }
+    g.njobs = (int)kv.second.size();
+    g.nblocks = nb;
+    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(UnpackJobDev) * kv.second.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(UnpackJobDev) * kv.second.size(),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "unpack plan upload failed: %s",
+                     cudaGetErrorString(e));
+    }
+    p->groups.push_back(g);
+  }
+  p->launches_per_run = (int)p->groups.size();
+  *out = p;
+  return RSB200_OK;
+}
+
+template <int BPS, bool LSBO>
+static cudaError_t launch_unpack(const UnpackGroup& g, const uint8_t* in, uint64_t in_total,
+                                 uint8_t* outp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(unpack_kernel<BPS, LSBO>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, UNPACK_SMEM_BYTES);
+    attr_set = true;
+  }
+  unpack_kernel<BPS, LSBO><<<g.nblocks, UNPACK_THREADS, UNPACK_SMEM_BYTES, st>>>(
+      in, in_total, outp, g.d_jobs, g.njobs);
+  return cudaGetLastError();
+}
+
+static cudaError_t run_unpack_group(const UnpackGroup& g, const uint8_t* in,
+                                    uint64_t in_total, uint8_t* outp, cudaStream_t st) {
+#define RSB_CASE(B)                                                            \
+  case B:                                                                      \
+    return g.lsb ? launch_unpack<B, true>(g, in, in_total, outp, st)           \
+                 : launch_unpack<B, false>(g, in, in_total, outp, st);
+  switch (g.bps_t) {
+    RSB_CASE(8)
+    RSB_CASE(10)
+    RSB_CASE(12)
+    RSB_CASE(14)
+    RSB_CASE(16)
+  default:
+    return g.lsb ? launch_unpack<0, true>(g, in, in_total, outp, st)
+                 : launch_unpack<0, false>(g, in, in_total, outp, st);
+  }
+#undef RSB_CASE
+}
+
+// ------------------------------------------------------------------
+// Huffman table -> device table (HuffmanCode.h:66-93 code assignment,
+// PrefixCodeLookupDecoder.h:97-113 maxcode/offset, LUT as documented in ljpeg.cuh)
+// ------------------------------------------------------------------
+static bool build_dev_table(const rsb200_huff_table& h, DevTable& t) {
+  memset(&t, 0, sizeof t);
+  unsigned count = 0, maxlen = 0;
+  for (unsigned l = 1; l <= 16; ++l) {
+    count += h.ncodes_per_len[l - 1];
+    if (h.ncodes_per_len[l - 1])
+      maxlen = l;
+  }
+  if (maxlen == 0 || count > 162 || count != h.nvalues)
+    return false;
+  // Kraft / canonical assignment
+  unsigned maxCodes = 2;
+  uint32_t code = 0;
+  unsigned n = 0;
+  for (unsigned l = 0; l < 18; ++l) {
+    t.maxcode[l] = -1;
+    t.valoff[l] = 0;
+  }
+  for (unsigned l = 1; l <= maxlen; ++l) {
+    const unsigned nc = h.ncodes_per_len[l - 1];
+    if (nc > maxCodes)
+      return false;
+    maxCodes = (maxCodes - nc) * 2;
+    if (nc) {
+      t.valoff[l] = (int32_t)code - (int32_t)n;
+      for (unsigned i = 0; i < nc; ++i, ++n, ++code) {
+        const unsigned ssss = h.values[n];
+        if (ssss > 16)
+          return false;
+        if (l <= (unsigned)LUT_BITS) {
+          const unsigned total = l + (ssss == 16 ? (h.fix_dng16 ? 16u : 0u) : ssss);
+          const uint16_t e = (uint16_t)(l | (ssss << 5) | (total << 10));
+          const uint32_t lo = code << (LUT_BITS - l);
+          const uint32_t hi = lo | ((1u << (LUT_BITS - l)) - 1u);
+          for (uint32_t c = lo; c <= hi; ++c)
+            t.lut[c] = e;
+        }
+      }
+      t.maxcode[l] = (int32_t)code - 1;
+    }
+    code <<= 1;
+  }
+  memcpy(t.values, h.values, count);
+  t.maxlen = (int32_t)maxlen;
+  t.fix16 = h.fix_dng16 ? 1 : 0;
+  return true;
+}
+
+struct ScanBuild {
+  std::vector<DevScan> scans;
+  std::vector<DevStrip> strips;
+  std::vector<K3RowRef> rows;
+  uint64_t diff_elems = 0;
+  uint64_t col_elems = 0;
+};
+
+static void assign_tables(DevScan& d, const uint8_t* table, int ncomp,
+                          const uint8_t* comp_of_pos, int group) {
+  // block-local slots: slot of component c
+  int slot_of_comp[4] = {0, 0, 0, 0};
+  int nslots = 0;
+  for (int s = 0; s < 4; ++s)
+    d.table_idx[s] = -1;
+  for (int c = 0; c < ncomp; ++c) {
+    int found = -1;
+    for (int s = 0; s < nslots; ++s)
+      if (d.table_idx[s] == (int)table[c])
+        found = s;
+    if (found < 0) {
+      found = nslots++;
+      d.table_idx[found] = table[c];
+    }
+    slot_of_comp[c] = found;
+  }
+  d.multi_table = nslots > 1;
+  for (int p = 0; p < group && p < 12; ++p)
+    d.table_of[p] = (uint8_t)slot_of_comp[comp_of_pos[p] & 3];
+}
+
+static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
+                             const rsb200_huff_table* tables, int ntables, ScanBuild& b) {
+  std::vector<DevTable> ht((size_t)ntables);
+  for (int i = 0; i < ntables; ++i)
+    if (!build_dev_table(tables[i], ht[(size_t)i])) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "huffman table %d is malformed", i);
+    }
+  p->kind = 1;
+  p->nscans = (int)b.scans.size();
+  p->nunits = p->nscans;
+  p->nrows = (uint32_t)b.rows.size();
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** dptr, const void* src, size_t bytes) {
+    if (e != cudaSuccess)
+      return;
+    e = cudaMalloc(dptr, bytes ? bytes : 16);
+    if (e == cudaSuccess && bytes)
+      e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+  };
+  up((void**)&p->d_tables, ht.data(), sizeof(DevTable) * ht.size());
+  up((void**)&p->d_scans, b.scans.data(), sizeof(DevScan) * b.scans.size());
+  up((void**)&p->d_strips, b.strips.data(), sizeof(DevStrip) * b.strips.size());
+  up((void**)&p->d_rows, b.rows.data(), sizeof(K3RowRef) * b.rows.size());
+  if (e == cudaSuccess)
+    e = cudaMalloc((void**)&p->d_diffs, (b.diff_elems + 64) * sizeof(uint16_t));
+  if (e == cudaSuccess)
+    e = cudaMalloc((void**)&p->d_colvals, (b.col_elems + 64) * sizeof(uint16_t));
+  if (e == cudaSuccess)
+    e = cudaMalloc((void**)&p->d_results, sizeof(DevResult) * b.scans.size());
+  if (e == cudaSuccess)
+    e = cudaMallocHost((void**)&p->h_results, sizeof(DevResult) * b.scans.size());
+  if (e != cudaSuccess) {
+    rsb200_plan_destroy(p);
+    return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
+                   cudaGetErrorString(e));
+  }
+  p->launches_per_run = 3;
+  return RSB200_OK;
+}
+
+extern "C" int rsb200_ljpeg_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables,
+                                        int ntables, const rsb200_ljpeg_scan* scans,
+                                        int nscans, rsb200_plan** out) {
+  if (!ctx || !tables || ntables <= 0 || !scans || nscans <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "ljpeg_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  ScanBuild b;
+  b.scans.reserve((size_t)nscans);
+  static const uint8_t ident[12] = {0, 1, 2, 3, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nscans; ++i) {
+    const rsb200_ljpeg_scan& s = scans[i];
+    const int group = s.mcu_w * s.mcu_h;
+    const bool mcu_ok = (s.mcu_h == 1 && s.mcu_w >= 1 && s.mcu_w <= 4) ||
+                        (s.mcu_w == 2 && s.mcu_h == 2);
+    bool ok = mcu_ok && s.rows > 0 && s.frame_w > 0 && s.store_w > 0 &&
+              (uint64_t)s.frame_w * s.mcu_w >= s.store_w &&
+              (uint64_t)(s.out_x + s.store_w) * 2 <= s.out_pitch &&
+              (uint64_t)s.rows * s.frame_w * group < (1ull << 32) &&
+              s.in_size < (1u << 28);
+    for (int c = 0; ok && c < group; ++c)
+      ok = s.table[c] < ntables;
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "ljpeg scan %d: malformed descriptor", i);
+    }
+    DevScan d;
+    memset(&d, 0, sizeof d);
+    d.in_offset = s.in_offset;
+    d.in_size = s.in_size;
+    d.rows = s.rows;
+    d.row_samples = s.frame_w * (uint32_t)group;
+    d.n_samples = d.rows * d.row_samples;
+    d.group = (uint8_t)group;
+    d.ncomp = (uint8_t)group;
+    d.kind = 0;
+    d.pattern = PAT_PLAIN;
+    assign_tables(d, s.table, group, ident, group);
+    for (int c = 0; c < group; ++c) {
+      d.first_idx[c] = (uint8_t)c;
+      d.init_pred[c] = s.init_pred[c];
+    }
+    d.out_offset = s.out_offset;
+    d.out_pitch = s.out_pitch;
+    d.out_x = s.out_x;
+    d.out_y = s.out_y;
+    d.store_w = s.store_w;
+    d.mcu_w = s.mcu_w;
+    d.mcu_h = s.mcu_h;
+    d.diff_offset = b.diff_elems;
+    b.diff_elems += ((uint64_t)d.n_samples + 7) & ~7ull;
+    d.col_offset = b.col_elems;
+    b.col_elems += (uint64_t)d.rows * 4;
+    d.row_begin = (uint32_t)b.rows.size();
+    for (uint32_t r = 0; r < d.rows; ++r)
+      b.rows.push_back(K3RowRef{(uint32_t)i, r});
+    b.scans.push_back(d);
+    p->in_bytes += s.in_size;
+    p->out_bytes += (uint64_t)s.rows * s.mcu_h * s.store_w * 2;
+    p->pixels += (uint64_t)s.rows * s.mcu_h * s.store_w;
+    p->need_in = std::max<uint64_t>(p->need_in, s.in_offset + s.in_size);
+    p->need_out = std::max<uint64_t>(
+        p->need_out, s.out_offset +
+                         (uint64_t)(s.out_y + s.rows * s.mcu_h - 1) * s.out_pitch +
+                         2ull * (s.out_x + s.store_w));
+  }
+  int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b);
+  if (rc != RSB200_OK)
+    return rc;
+  *out = p;
+  return RSB200_OK;
+}
+
+// Vertical output strips of a CR2 frame, restating the slice iterators of
+// Cr2DecompressorImpl.h:76-248 (slices in stream order -> output tiles clamped
+// to the image height -> vertically adjacent tiles coalesced).
+static bool cr2_strips(int dimX /*groups*/, int dimY, int frameY, int numSlices,
+                       int sliceW, int lastSliceW, std::vector<DevStrip>& out) {
+  int sliceId = 0, sliceRow = 0, px = 0, py = 0;
+  uint32_t g = 0;
+  bool done = false;
+  while (sliceId < numSlices && !done) {
+    const int w = (sliceId + 1 == numSlices) ? lastSliceW : sliceW;
+    const int h = std::min(dimY - py, frameY - sliceRow);
+    if (w <= 0 || h <= 0)
+      return false;
+    if (px + w > dimX || py + h > dimY)
+      return false;
+    if (!out.empty() && out.back().x == px && out.back().w == w &&
+        out.back().y + out.back().h == py) {
+      out.back().h += h; // ContinuesColumn
+    } else {
+      if (!out.empty() && !(py == 0 && px == out.back().x + out.back().w))
+        return false; // invalid tiling
+      out.push_back(DevStrip{g, px, py, w, h});
+    }
+    g += (uint32_t)w * (uint32_t)h;
+    if (px + w == dimX && py + h == dimY)
+      done = true;
+    sliceRow += h;
+    py += h;
+    if (sliceRow == frameY) {
+      ++sliceId;
+      sliceRow = 0;
+    }
+    if (py == dimY) {
+      py = 0;
+      px += w;
+    }
+  }
+  return done;
+}
+
+extern "C" int rsb200_cr2_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables,
+                                      int ntables, const rsb200_cr2_job* jobs, int njobs,
+                                      rsb200_plan** out) {
+  if (!ctx || !tables || ntables <= 0 || !jobs || njobs <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "cr2_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  ScanBuild b;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_cr2_job& j = jobs[i];
+    const bool sub = (j.x_s_f != 1 || j.y_s_f != 1);
+    const bool fmt_ok = (j.n_comp == 2 && !sub) || (j.n_comp == 4 && !sub) ||
+                        (j.n_comp == 3 && j.x_s_f == 2 && (j.y_s_f == 1 || j.y_s_f == 2));
+    // Dsc (Cr2DecompressorImpl.h:250-275)
+    const int pixelsPerGroup = j.x_s_f * j.y_s_f;
+    const int groupSize = !sub ? j.n_comp : 2 + pixelsPerGroup;
+    const int sliceColStep = j.n_comp * j.x_s_f;
+    bool ok = fmt_ok && j.img_w > 0 && j.img_h > 0 && j.img_w % groupSize == 0 &&
+              j.frame_w > 0 && j.frame_h > 0 && j.frame_w % j.x_s_f == 0 &&
+              j.frame_h % j.y_s_f == 0 && j.num_slices >= 1 &&
+              j.last_slice_w > 0 && (j.num_slices == 1 || j.slice_w > 0) &&
+              j.slice_w % sliceColStep == 0 && j.last_slice_w % sliceColStep == 0 &&
+              (uint64_t)j.img_w * 2 <= j.out_pitch && j.in_size < (1u << 28);
+    for (int c = 0; ok && c < j.n_comp; ++c)
+      ok = j.table[c] < ntables;
+    DevScan d;
+    memset(&d, 0, sizeof d);
+    if (ok) {
+      const int dimX = j.img_w / groupSize, dimY = j.img_h;
+      const int frameX = j.frame_w / j.x_s_f, frameY = j.frame_h / j.y_s_f;
+      ok = (uint64_t)frameX * frameY >= (uint64_t)dimX * dimY;
+      d.strip_begin = (uint32_t)b.strips.size();
+      if (ok)
+        ok = cr2_strips(dimX, dimY, frameY, j.num_slices, j.slice_w / sliceColStep,
+                        j.last_slice_w / sliceColStep, b.strips);
+      d.n_strips = (uint16_t)(b.strips.size() - d.strip_begin);
+      const uint64_t total_groups = (uint64_t)dimX * dimY;
+      d.row_samples = (uint32_t)frameX * (uint32_t)groupSize;
+      d.rows = (uint32_t)((total_groups + frameX - 1) / frameX);
+      d.n_samples = (uint32_t)(total_groups * groupSize);
+      ok = ok && total_groups * groupSize < (1ull << 32);
+    }
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "cr2 job %d: malformed descriptor", i);
+    }
+    d.in_offset = j.in_offset;
+    d.in_size = j.in_size;
+    d.group = (uint8_t)groupSize;
+    d.ncomp = j.n_comp;
+    d.kind = 1;
+    d.pattern = !sub ? PAT_PLAIN : (j.y_s_f == 1 ? PAT_H2V1 : PAT_H2V2);
+    uint8_t comp_of_pos[12];
+    for (int q = 0; q < groupSize; ++q)
+      comp_of_pos[q] = (uint8_t)(!sub ? q : (q < pixelsPerGroup ? 0 : q - pixelsPerGroup + 1));
+    assign_tables(d, j.table, j.n_comp, comp_of_pos, groupSize);
+    for (int c = 0; c < j.n_comp; ++c) {
+      d.first_idx[c] = (uint8_t)(c == 0 ? 0 : groupSize - (j.n_comp - c));
+      d.init_pred[c] = j.init_pred[c];
+    }
+    d.out_offset = j.out_offset;
+    d.out_pitch = j.out_pitch;
+    d.mcu_w = (uint8_t)groupSize;
+    d.mcu_h = 1;
+    d.store_w = (uint32_t)j.img_w;
+    d.diff_offset = b.diff_elems;
+    b.diff_elems += (((uint64_t)d.rows * d.row_samples) + 7) & ~7ull;
+    d.col_offset = b.col_elems;
+    b.col_elems += (uint64_t)d.rows * 4;
+    d.row_begin = (uint32_t)b.rows.size();
+    for (uint32_t r = 0; r < d.rows; ++r)
+      b.rows.push_back(K3RowRef{(uint32_t)i, r});
+    b.scans.push_back(d);
+    p->in_bytes += j.in_size;
+    p->out_bytes += (uint64_t)j.img_w * j.img_h * 2;
+    p->pixels += (uint64_t)j.img_w * j.img_h;
+    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + j.in_size);
+    p->need_out = std::max<uint64_t>(
+        p->need_out, j.out_offset + (uint64_t)(j.img_h - 1) * j.out_pitch + 2ull * j.img_w);
+  }
+  int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b);
+  if (rc != RSB200_OK)
+    return rc;
+  *out = p;
+  return RSB200_OK;
+}
+
+// ------------------------------------------------------------------
+// execution
+// ------------------------------------------------------------------
+extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes,
+                               void* d_out, size_t out_bytes, void* stream) {
+  if (!p || !d_in || !d_out)
+    return RSB200_ERR_ARG;
+  rsb200_ctx* ctx = p->ctx;
+  if (in_bytes < p->need_in || out_bytes < p->need_out)
+    return set_err(ctx, RSB200_ERR_ARG,
+                   "plan_run: buffers too small (in %zu < %llu or out %zu < %llu)",
+                   in_bytes, (unsigned long long)p->need_in, out_bytes,
+                   (unsigned long long)p->need_out);
+  if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+    return set_err(ctx, RSB200_ERR_ARG, "plan_run: device pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* in = (const uint8_t*)d_in;
+  uint8_t* outp = (uint8_t*)d_out;
+  if (p->kind == 0) {
+    for (const UnpackGroup& g : p->groups) {
+      if (!g.nblocks)
+        continue;
+      CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
+      ctx->launches++;
+    }
+  } else {
+    k2_entropy_kernel<<<p->nscans, K2_THREADS, sizeof(K2Shared), st>>>(
+        in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->d_diffs, p->d_results);
+    CUDA_TRY(ctx, cudaGetLastError());
+    const int col_warps = p->nscans * 4;
+    k3_column_kernel<<<(col_warps * 32 + 127) / 128, 128, 0, st>>>(
+        p->d_scans, p->nscans, p->d_diffs, p->d_colvals);
+    CUDA_TRY(ctx, cudaGetLastError());
+    const uint32_t rows_per_block = K3_THREADS / 32;
+    k3_row_kernel<<<(p->nrows + rows_per_block - 1) / rows_per_block, K3_THREADS, 0, st>>>(
+        p->d_scans, p->d_rows, p->nrows, p->d_diffs, p->d_colvals, p->d_strips, outp);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 3;
+  }
+  p->last_stream = st;
+  p->ran = true;
+  return RSB200_OK;
+}
+
+static int ensure_cap(rsb200_ctx* ctx, uint8_t** buf, size_t* cap, size_t need) {
+  need = (need + 255) & ~(size_t)255;
+  if (*cap >= need)
+    return RSB200_OK;
+  if (*buf)
+    cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  CUDA_TRY(ctx, cudaMalloc((void**)buf, need + 256));
+  *cap = need;
+  return RSB200_OK;
+}
+
+extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
+                                    uint8_t* out, size_t out_bytes, int partial) {
+  if (!p || !in || !out)
+    return RSB200_ERR_ARG;
+  rsb200_ctx* ctx = p->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_cap(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes + 16);
+  if (rc)
+    return rc;
+  rc = ensure_cap(ctx, &ctx->d_out, &ctx->d_out_cap, out_bytes);
+  if (rc)
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (partial)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_out, out, out_bytes, cudaMemcpyHostToDevice, st));
+  rc = rsb200_plan_run(p, ctx->d_in, in_bytes, ctx->d_out, out_bytes, (void*)st);
+  if (rc)
+    return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return RSB200_OK;
+}
+
+extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, int n) {
+  if (!p)
+    return RSB200_ERR_ARG;
+  rsb200_ctx* ctx = p->ctx;
+  if (!p->ran)
+    return set_err(ctx, RSB200_ERR_ARG, "plan_results: plan has not been run");
+  if (p->kind == 0) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
+    for (int i = 0; results && i < n; ++i) {
+      results[i].status = RSB200_OK;
+      results[i].consumed = 0;
+    }
+    return RSB200_OK;
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->h_results, p->d_results, sizeof(DevResult) * p->nscans,
+                                cudaMemcpyDeviceToHost, p->last_stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
+  int first = RSB200_OK;
+  for (int i = 0; i < p->nscans; ++i) {
+    if (results && i < n) {
+      results[i].status = p->h_results[i].status;
+      results[i].consumed = p->h_results[i].consumed;
+    }
+    if (first == RSB200_OK && p->h_results[i].status != 0) {
+      first = (int)p->h_results[i].status;
+      set_err(ctx, first,
+              first == RSB200_ERR_RDE ? "segment %d: bad Huffman code"
+                                      : "segment %d: Buffer overflow read in BitStreamer",
+              i);
+    }
+  }
+  return first;
+}
+
+extern "C" int rsb200_plan_bytes(const rsb200_plan* p, uint64_t* in_bytes,
+                                 uint64_t* out_bytes, uint64_t* pixels) {
+  if (!p)
+    return RSB200_ERR_ARG;
+  if (in_bytes)
+    *in_bytes = p->in_bytes;
+  if (out_bytes)
+    *out_bytes = p->out_bytes;
+  if (pixels)
+    *pixels = p->pixels;
+  return RSB200_OK;
+}
+
+extern "C" int rsb200_plan_launches(const rsb200_plan* p) {
+  return p ? p->launches_per_run : 0;
+}
+
+extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
+  if (!p)
+    return;
+  if (p->ctx)
+    cudaSetDevice(p->ctx->device);
+  for (UnpackGroup& g : p->groups)
+    cudaFree(g.d_jobs);
+  cudaFree(p->d_tables);
+  cudaFree(p->d_scans);
+  cudaFree(p->d_strips);
+  cudaFree(p->d_rows);
+  cudaFree(p->d_diffs);
+  cudaFree(p->d_colvals);
+  cudaFree(p->d_results);
+  if (p->h_results)
+    cudaFreeHost(p->h_results);
+  delete p;
+}

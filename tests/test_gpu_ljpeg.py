@@ -1,0 +1,128 @@
+"""K2+K3 parity: CUDA LJPEG decode vs the oracle through the C ABI (bit-exact)."""
+import numpy as np
+import pytest
+
+import rawspeed_b200 as rs
+from oracle import port, synth
+from helpers import dng_ljpeg_scans, gpu_run
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_tiles(ctx, img, tile_w, tile_h, **kw):
+    h, w = img.shape
+    cpp = kw.pop("cpp", 1)
+    w //= cpp
+    t = synth.make_dng_ljpeg(img, tile_w, tile_h, cpp=cpp, **kw)
+    want = port.new_image(w, h, cpp)
+    got0 = want.copy()
+    port.dng_decompress(t.blob, t.offsets, t.lengths, want, w, cpp, tile_w, tile_h, 7,
+                        fix_ljpeg=kw.get("fix16", False), nthreads=4)
+    tabs, scans = dng_ljpeg_scans(t, got0.shape[1] * 2, fix16=kw.get("fix16", False))
+    plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
+    got, res = gpu_run(plan, t.blob, got0)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[:, :w * cpp], img)
+    return t, res
+
+
+def test_single_small_tile(ctx):
+    img = synth.image_model(64, 32, 1)
+    _check_tiles(ctx, img, 64, 32)
+
+
+def test_tiles_ragged_edges(ctx):
+    img = synth.image_model(300, 200, 7)
+    _check_tiles(ctx, img, 128, 64)
+
+
+def test_wild_noise_long_codes(ctx):
+    img = synth.image_model(256, 96, 9, wild=True)
+    _check_tiles(ctx, img, 128, 32)
+
+
+def test_sixteen_bit_ssss16(ctx):
+    # full 16-bit range: differences of -32768 (SSSS=16) occur
+    img = synth.image_model(128, 64, 11, wild=True, bits=16)
+    img[0, 0:8] = [0, 0x8000, 0, 0x8000, 0xFFFF, 0x7FFF, 0, 0x8000]
+    _check_tiles(ctx, img, 64, 64, prec=16)
+    _check_tiles(ctx, img, 64, 64, prec=16, fix16=True)
+
+
+def test_components_1_3_4_and_2x2(ctx):
+    img = synth.image_model(96, 48, 13)
+    _check_tiles(ctx, img, 48, 24, ncomp=1)
+    _check_tiles(ctx, img, 96, 48, ncomp=4)
+    _check_tiles(ctx, img, 48, 48, ncomp=3)
+    _check_tiles(ctx, img, 48, 24, ncomp=4, mcu=(2, 2))
+    img3 = synth.image_model(96 * 3, 40, 14)
+    _check_tiles(ctx, img3, 32, 20, ncomp=3, cpp=3)
+
+
+def test_two_tables(ctx):
+    img = synth.image_model(200, 100, 15)
+    tabs = synth.default_tables(2)
+    _check_tiles(ctx, img, 100, 50, tabs=tabs, tab_of_comp=[0, 1])
+    _check_tiles(ctx, img, 100, 50, ncomp=4, tabs=tabs, tab_of_comp=[1, 0, 0, 1])
+
+
+def test_restart_intervals(ctx):
+    img = synth.image_model(160, 96, 17)
+    _check_tiles(ctx, img, 80, 48, restart_rows=1)
+    _check_tiles(ctx, img, 80, 48, restart_rows=5)
+
+
+def test_odd_width_trailing_pixels(ctx):
+    img = synth.image_model(101, 33, 19)
+    _check_tiles(ctx, img, 64, 16)
+
+
+def test_consumed_matches_reference(ctx):
+    img = synth.image_model(128, 64, 21)
+    t = synth.make_dng_ljpeg(img, 64, 32)
+    tabs, scans = dng_ljpeg_scans(t, port.image_pitch(128))
+    plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
+    got, res = gpu_run(plan, t.blob, port.new_image(128, 64))
+    hts = synth.default_tables(1)
+    for (status, consumed), s, off, ln in zip(res, scans, t.offsets, t.lengths):
+        assert status == 0
+        data = t.blob[s.in_offset:off + ln]
+        o = port.new_image(128, 64)
+        want = port.ljpeg_decompress(o, 128, 1, (s.out_x, s.out_y, s.store_w, s.rows),
+                                     (2, 1), (s.frame_w, s.rows), [hts[0], hts[0]],
+                                     [1 << 13] * 2, s.rows, data)
+        assert consumed == want
+
+
+def test_c3_45mp_dng(ctx):
+    """BASELINE configs[2]: DNG LJPEG predictor 1, 8256x5504, 726 tiles 256x256."""
+    img = synth.image_model(8256, 5504, 12345)
+    t = synth.make_dng_ljpeg(img, 256, 256)
+    tabs, scans = dng_ljpeg_scans(t, port.image_pitch(8256))
+    assert len(scans) == 726
+    plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
+    got, res = gpu_run(plan, t.blob, port.new_image(8256, 5504))
+    assert all(s == 0 for s, _ in res)
+    assert np.array_equal(got[:, :8256], img)   # round trip == the reference's output
+    want = port.new_image(8256, 5504)
+    port.dng_decompress(t.blob, t.offsets, t.lengths, want, 8256, 1, 256, 256, 7, nthreads=8)
+    assert np.array_equal(got, want)
+
+
+def test_bad_huffman_code_reports_rde(ctx):
+    img = synth.image_model(64, 32, 23, wild=True)
+    # table without SSSS >= 12: craft a stream with an unassigned all-ones code
+    t = synth.make_dng_ljpeg(img, 64, 32)
+    tabs, scans = dng_ljpeg_scans(t, port.image_pitch(64))
+    blob = t.blob.copy()
+    s = scans[0]
+    blob[s.in_offset + 40:s.in_offset + 48] = 0xFE  # 15+ one-bits: not a code of this table
+    plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
+    import torch
+    d_in = torch.from_numpy(np.concatenate([blob, np.zeros(64, np.uint8)])).cuda()
+    d_out = torch.zeros(32 * port.image_pitch(64) // 2, dtype=torch.int16, device="cuda")
+    plan.run((d_in.data_ptr(), blob.size), d_out)
+    with pytest.raises(rs.RawDecoderException):
+        plan.results()
+    with pytest.raises(port.RawDecoderException):
+        port.dng_decompress(blob, t.offsets, t.lengths, port.new_image(64, 32), 64, 1, 64, 32, 7)
