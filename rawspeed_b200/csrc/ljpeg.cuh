@@ -284,6 +284,7 @@ struct K2Shared {
   DevTable tab[4];
   DevScan sc;
   uint32_t exitpos[K2_THREADS];
+  uint32_t exitph[K2_THREADS];
   uint32_t ffmask[K2_THREADS];
   uint32_t scan[K2_THREADS];  // symbol-count prefix
   uint32_t ffscan[K2_THREADS]; // FF-count prefix
@@ -465,18 +466,30 @@ __global__ void __launch_bounds__(K2_THREADS)
     else
       d = k2_scan_sub<false>(sh, sc, base, limit, my_start, sub_byte, ffmask, 0);
     sh.exitpos[tid] = d.exitpos;
+    if (multi)
+      sh.exitph[tid] = (my_phase + d.count) % sc.group;
     __syncthreads();
-    for (int round = 0; round < K2_THREADS + 1; ++round) {
+    // Fixed-point iteration.  A thread's state is (start position, start phase);
+    // each round it adopts its predecessor's exit state (hop by hop, so a wrong
+    // guess heals locally through self-synchronisation).  When no position
+    // changed in a round the symbol counts are consistent and the phases are
+    // taken from a block prefix sum instead (propagates instantly when the
+    // tables of the components differ only slightly).  Termination: thread 0 is
+    // exact, so after round r threads 0..r are final; the loop ends when every
+    // thread's start equals its predecessor's exit => the sequential parse.
+    for (int round = 0; round < K2_THREADS + 2; ++round) {
       uint32_t new_start = (tid == 0) ? carry_pos : sh.exitpos[tid - 1];
-      if (!active && tid != 0)
-        new_start = sh.exitpos[tid - 1];
       uint32_t new_phase = my_phase;
-      if (multi) {
+      if (multi)
+        new_phase = (tid == 0) ? (carry_sym % sc.group) : sh.exitph[tid - 1];
+      const bool pos_changed = new_start != my_start;
+      const int any_pos = __syncthreads_or(pos_changed ? 1 : 0);
+      if (multi && !any_pos) {
         uint32_t tot;
         const uint32_t incl = block_scan_incl(d.count, sh.warp_tmp[round & 1], &tot);
         new_phase = (carry_sym + incl - d.count) % sc.group;
       }
-      const bool changed = (new_start != my_start) || (multi && new_phase != my_phase);
+      const bool changed = pos_changed || (multi && new_phase != my_phase);
       const int any = __syncthreads_or(changed ? 1 : 0);
       if (!any)
         break;
@@ -489,6 +502,8 @@ __global__ void __launch_bounds__(K2_THREADS)
           d = k2_scan_sub<false>(sh, sc, base, limit, my_start, sub_byte, ffmask, 0);
       }
       sh.exitpos[tid] = d.exitpos;
+      if (multi)
+        sh.exitph[tid] = (my_phase + d.count) % sc.group;
       __syncthreads();
     }
 

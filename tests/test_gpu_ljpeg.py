@@ -116,7 +116,8 @@ def test_bad_huffman_code_reports_rde(ctx):
     tabs, scans = dng_ljpeg_scans(t, port.image_pitch(64))
     blob = t.blob.copy()
     s = scans[0]
-    blob[s.in_offset + 40:s.in_offset + 48] = 0xFE  # 15+ one-bits: not a code of this table
+    # 39 consecutive one-bits (FF is stuffed): no code of this table starts with 15 ones
+    blob[s.in_offset + 40:s.in_offset + 49] = [0xFF, 0, 0xFF, 0, 0xFF, 0, 0xFF, 0, 0xFE]
     plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
     import torch
     d_in = torch.from_numpy(np.concatenate([blob, np.zeros(64, np.uint8)])).cuda()

@@ -77,15 +77,18 @@ def test_unpack_c2_14bit_45mp(ctx):
 
 
 def test_unpack_unaligned_offsets_and_tiles(ctx):
-    """DNG compression-1 tiles: several jobs in one plan, arbitrary byte offsets,
-    sub-rectangle outputs (AbstractDngDecompressor.cpp:54-110)."""
-    W, H, tw, th, bps = 100, 60, 32, 16, 12
+    """DNG compression-1 tiles: several jobs in one plan, arbitrary byte offsets
+    (AbstractDngDecompressor.cpp:54-110).  One tile column: the reference writes
+    packed integers at column 0 of the row whatever the tile's x offset
+    (UncompressedDecompressor.cpp:196), so several tile columns would race in
+    the reference itself."""
+    W, H, tw, th, bps = 96, 60, 96, 16, 12
     rng = np.random.default_rng(3)
-    tiles_x, tiles_y = (W + tw - 1) // tw, (H + th - 1) // th
+    tiles_y = (H + th - 1) // th
     pitch = tw * bps // 8
     blob = np.zeros(0, dtype=np.uint8)
     offs = []
-    for n in range(tiles_x * tiles_y):
+    for n in range(tiles_y):
         pad = rng.integers(0, 7)
         offs.append(blob.size + pad)
         blob = np.concatenate([blob, np.zeros(pad, np.uint8),
@@ -95,12 +98,31 @@ def test_unpack_unaligned_offsets_and_tiles(ctx):
     port.dng_decompress(blob, offs, [pitch * th] * len(offs), want, W, 1, tw, th, 1, bps=bps)
     jobs = []
     for n, off in enumerate(offs):
+        h = min(th, H - n * th)
+        jobs.append(_job(pitch * th, got0, W, h, n * th, pitch, bps, rs.MSB, in_offset=off))
+    plan = rs.unpack_plan(ctx, jobs)
+    got, _ = gpu_run(plan, blob, got0)
+    assert np.array_equal(got, want)
+
+
+def test_unpack_16bit_lsb_tiles_honour_x_offset(ctx):
+    """bps == 16 LSB is a row copy that does honour offset.x
+    (UncompressedDecompressor.cpp:255-264): several tile columns are well defined."""
+    W, H, tw, th = 100, 40, 32, 16
+    tiles_x, tiles_y = (W + tw - 1) // tw, (H + th - 1) // th
+    pitch = tw * 2
+    blob = synth.lcg_bytes(pitch * th * tiles_x * tiles_y + 13, 4)
+    offs = [13 + n * pitch * th for n in range(tiles_x * tiles_y)]
+    want = port.new_image(W, H)
+    got0 = want.copy()
+    port.dng_decompress(blob, offs, [pitch * th] * len(offs), want, W, 1, tw, th, 1, bps=16)
+    jobs = []
+    for n, off in enumerate(offs):
         ty, tx = divmod(n, tiles_x)
         w = min(tw, W - tx * tw)
         h = min(th, H - ty * th)
-        # NOTE the reference writes packed ints at column 0 of the row regardless
-        # of the tile's x offset (UncompressedDecompressor.cpp:196); mirrored here.
-        jobs.append(_job(pitch * th, got0, w, h, ty * th, pitch, bps, rs.MSB, in_offset=off))
+        jobs.append(_job(pitch * th, got0, w, h, ty * th, pitch, 16, rs.LSB, in_offset=off,
+                         col0=tx * tw))
     plan = rs.unpack_plan(ctx, jobs)
     got, _ = gpu_run(plan, blob, got0)
     assert np.array_equal(got, want)
