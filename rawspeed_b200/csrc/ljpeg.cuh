@@ -41,7 +41,7 @@ constexpr uint32_t POS_END = 0xFFFFFFFFu;
 
 // LUT entry (uint16): [4:0] code length (0 = not in LUT), [9:5] SSSS,
 // [15:10] total bits consumed by code + mantissa.
-struct DevTable {
+struct alignas(16) DevTable {
   uint16_t lut[1 << LUT_BITS];
   int32_t maxcode[18];  // per code length 1..16; -1 = no code of this length
   int32_t valoff[18];   // code - valoff[len] = index into values
@@ -76,7 +76,7 @@ struct DevScan {
   uint32_t strip_begin;  // CR2: first entry in the strip table
   uint64_t col_offset;   // first element of this scan in the column-chain scratch
   uint32_t row_begin;    // first global row index of this scan (K3 work list)
-  uint32_t reserved;
+  uint32_t rs_inv;       // ceil(2^32 / row_samples) (fast row lookup in the fused kernel)
 };
 
 // CR2 vertical output strip (Cr2DecompressorImpl.h:162-205), in groups

@@ -5,6 +5,7 @@
 #include "../../include/rawspeed_b200.h"
 
 #include "ljpeg.cuh"
+#include "ljpeg_fused.cuh"
 #include "unpack.cuh"
 
 #include <algorithm>
@@ -58,6 +59,14 @@ struct UnpackGroup {
   uint32_t nblocks = 0;
 };
 
+struct UnpackFastGroup {
+  int bps;
+  bool lsb;
+  UnpackFastJobDev* d_jobs = nullptr;
+  int njobs = 0;
+  uint32_t nblocks = 0;
+};
+
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
   int kind = 0; // 0 unpack, 1 ljpeg/cr2
@@ -68,6 +77,7 @@ struct rsb200_plan {
   uint64_t need_in = 0, need_out = 0;
   // unpack
   std::vector<UnpackGroup> groups;
+  std::vector<UnpackFastGroup> fast_groups;
   // ljpeg
   DevTable* d_tables = nullptr;
   DevScan* d_scans = nullptr;
@@ -79,6 +89,8 @@ struct rsb200_plan {
   DevResult* h_results = nullptr; // pinned
   uint32_t nrows = 0;
   int nscans = 0;
+  bool fused = false; // LJPEG tiles: single fused kernel, no scratch buffers
+  int ntab_slots = 4;
   cudaStream_t last_stream = nullptr;
   bool ran = false;
 };
@@ -115,6 +127,8 @@ extern "C" int rsb200_create(int device, rsb200_ctx** out) {
   // opt in to the dynamic shared memory the kernels need
   cudaFuncSetAttribute(k2_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(K2Shared));
+  cudaFuncSetAttribute(k2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)fused_smem_bytes(4));
   *out = c;
   return RSB200_OK;
 }
@@ -153,6 +167,7 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
   p->kind = 0;
   p->nunits = njobs;
   std::map<std::pair<int, bool>, std::vector<UnpackJobDev>> buckets;
+  std::map<std::pair<int, bool>, std::vector<UnpackFastJobDev>> fast_buckets;
   for (int i = 0; i < njobs; ++i) {
     const rsb200_unpack_job& j = jobs[i];
     if (j.bps < 1 || j.bps > 16 || j.order < 0 || j.order > 3 || j.rows < 0 ||
@@ -187,7 +202,30 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
                 (j.out_col0 % 8) == 0)
                    ? 1u
                    : 0u;
-    buckets[{unpack_template_bps(j.bps), j.order == RSB200_LSB}].push_back(d);
+    const uint32_t ipr = (uint32_t)((j.samples + 15) / 16);
+    const bool fast = unpack_template_bps(j.bps) != 0 && (j.in_offset % 4) == 0 &&
+                      (j.in_pitch % 4) == 0 && ipr >= 64 &&
+                      (uint64_t)j.rows * ipr < 0xFFFF0000ull;
+    if (fast) {
+      UnpackFastJobDev f;
+      memset(&f, 0, sizeof f);
+      f.in_offset = j.in_offset;
+      f.out_offset = j.out_offset;
+      f.out_pitch = j.out_pitch;
+      f.row0 = j.row0;
+      f.rows = j.rows;
+      f.samples = j.samples;
+      f.out_col0 = j.out_col0;
+      f.in_pitch = j.in_pitch;
+      f.order = j.order;
+      f.ipr = ipr;
+      f.total_items = (uint32_t)j.rows * ipr;
+      f.vec_ok = d.vec_ok;
+      f.row_bytes = (uint32_t)((uint64_t)j.samples * j.bps / 8);
+      fast_buckets[{j.bps, j.order == RSB200_LSB}].push_back(f);
+    } else {
+      buckets[{unpack_template_bps(j.bps), j.order == RSB200_LSB}].push_back(d);
+    }
     p->in_bytes += (uint64_t)j.rows * ((uint64_t)j.samples * j.bps / 8);
     p->out_bytes += (uint64_t)j.rows * (uint64_t)j.samples * 2;
     p->pixels += (uint64_t)j.rows * (uint64_t)j.samples;
@@ -218,7 +256,29 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
     }
     p->groups.push_back(g);
   }
-  p->launches_per_run = (int)p->groups.size();
+  for (auto& kv : fast_buckets) {
+    UnpackFastGroup g;
+    g.bps = kv.first.first;
+    g.lsb = kv.first.second;
+    uint32_t nb = 0;
+    for (auto& f : kv.second) {
+      f.block_begin = nb;
+      nb += (f.total_items + UNPACK_IPB - 1) / UNPACK_IPB;
+    }
+    g.njobs = (int)kv.second.size();
+    g.nblocks = nb;
+    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(UnpackFastJobDev) * kv.second.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(UnpackFastJobDev) * kv.second.size(),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "unpack plan upload failed: %s",
+                     cudaGetErrorString(e));
+    }
+    p->fast_groups.push_back(g);
+  }
+  p->launches_per_run = (int)(p->groups.size() + p->fast_groups.size());
   *out = p;
   return RSB200_OK;
 }
@@ -252,6 +312,38 @@ static cudaError_t run_unpack_group(const UnpackGroup& g, const uint8_t* in,
   default:
     return g.lsb ? launch_unpack<0, true>(g, in, in_total, outp, st)
                  : launch_unpack<0, false>(g, in, in_total, outp, st);
+  }
+#undef RSB_CASE
+}
+
+template <int BPS, bool LSBO>
+static cudaError_t launch_unpack_fast(const UnpackFastGroup& g, const uint8_t* in,
+                                      uint8_t* outp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(unpack_fast_kernel<BPS, LSBO>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, UNPACK_FAST_SMEM);
+    attr_set = true;
+  }
+  unpack_fast_kernel<BPS, LSBO><<<g.nblocks, UNPACK_THREADS, UNPACK_FAST_SMEM, st>>>(
+      in, outp, g.d_jobs, g.njobs);
+  return cudaGetLastError();
+}
+
+static cudaError_t run_unpack_fast_group(const UnpackFastGroup& g, const uint8_t* in,
+                                         uint8_t* outp, cudaStream_t st) {
+#define RSB_CASE(B)                                                            \
+  case B:                                                                      \
+    return g.lsb ? launch_unpack_fast<B, true>(g, in, outp, st)                \
+                 : launch_unpack_fast<B, false>(g, in, outp, st);
+  switch (g.bps) {
+    RSB_CASE(8)
+    RSB_CASE(10)
+    RSB_CASE(12)
+    RSB_CASE(14)
+    RSB_CASE(16)
+  default:
+    return cudaErrorInvalidValue;
   }
 #undef RSB_CASE
 }
@@ -340,7 +432,8 @@ static void assign_tables(DevScan& d, const uint8_t* table, int ncomp,
 }
 
 static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
-                             const rsb200_huff_table* tables, int ntables, ScanBuild& b) {
+                             const rsb200_huff_table* tables, int ntables, ScanBuild& b,
+                             bool fused) {
   std::vector<DevTable> ht((size_t)ntables);
   for (int i = 0; i < ntables; ++i)
     if (!build_dev_table(tables[i], ht[(size_t)i])) {
@@ -348,6 +441,17 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
       return set_err(ctx, RSB200_ERR_ARG, "huffman table %d is malformed", i);
     }
   p->kind = 1;
+  p->fused = fused;
+  p->ntab_slots = 1;
+  for (const DevScan& d : b.scans)
+    for (int sl = 0; sl < 4; ++sl)
+      if (d.table_idx[sl] >= 0)
+        p->ntab_slots = std::max(p->ntab_slots, sl + 1);
+  if (fused) {
+    b.rows.clear();
+    b.diff_elems = 0;
+    b.col_elems = 0;
+  }
   p->nscans = (int)b.scans.size();
   p->nunits = p->nscans;
   p->nrows = (uint32_t)b.rows.size();
@@ -376,7 +480,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
                    cudaGetErrorString(e));
   }
-  p->launches_per_run = 3;
+  p->launches_per_run = fused ? 1 : 3;
   return RSB200_OK;
 }
 
@@ -416,6 +520,8 @@ extern "C" int rsb200_ljpeg_plan_create(rsb200_ctx* ctx, const rsb200_huff_table
     d.rows = s.rows;
     d.row_samples = s.frame_w * (uint32_t)group;
     d.n_samples = d.rows * d.row_samples;
+    d.rs_inv = d.row_samples <= 1 ? 0xFFFFFFFFu
+                                  : (uint32_t)(((1ull << 32) + d.row_samples - 1) / d.row_samples);
     d.group = (uint8_t)group;
     d.ncomp = (uint8_t)group;
     d.kind = 0;
@@ -449,7 +555,7 @@ extern "C" int rsb200_ljpeg_plan_create(rsb200_ctx* ctx, const rsb200_huff_table
                          (uint64_t)(s.out_y + s.rows * s.mcu_h - 1) * s.out_pitch +
                          2ull * (s.out_x + s.store_w));
   }
-  int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b);
+  int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/true);
   if (rc != RSB200_OK)
     return rc;
   *out = p;
@@ -579,7 +685,7 @@ extern "C" int rsb200_cr2_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* 
     p->need_out = std::max<uint64_t>(
         p->need_out, j.out_offset + (uint64_t)(j.img_h - 1) * j.out_pitch + 2ull * j.img_w);
   }
-  int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b);
+  int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/false);
   if (rc != RSB200_OK)
     return rc;
   *out = p;
@@ -605,12 +711,23 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
   const uint8_t* in = (const uint8_t*)d_in;
   uint8_t* outp = (uint8_t*)d_out;
   if (p->kind == 0) {
+    for (const UnpackFastGroup& g : p->fast_groups) {
+      if (!g.nblocks)
+        continue;
+      CUDA_TRY(ctx, run_unpack_fast_group(g, in, outp, st));
+      ctx->launches++;
+    }
     for (const UnpackGroup& g : p->groups) {
       if (!g.nblocks)
         continue;
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->fused) {
+    k2_fused_kernel<<<p->nscans, F_NT, fused_smem_bytes(p->ntab_slots), st>>>(
+        in, (uint64_t)in_bytes, p->d_scans, p->d_tables, outp, p->d_results);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 1;
   } else {
     k2_entropy_kernel<<<p->nscans, K2_THREADS, sizeof(K2Shared), st>>>(
         in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->d_diffs, p->d_results);
@@ -724,6 +841,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   if (p->ctx)
     cudaSetDevice(p->ctx->device);
   for (UnpackGroup& g : p->groups)
+    cudaFree(g.d_jobs);
+  for (UnpackFastGroup& g : p->fast_groups)
     cudaFree(g.d_jobs);
   cudaFree(p->d_tables);
   cudaFree(p->d_scans);

@@ -196,4 +196,143 @@ __global__ void __launch_bounds__(UNPACK_THREADS)
   }
 }
 
+// ------------------------------------------------------------------
+// Fast path: even bit depths, 4-byte aligned strips/pitches, wide rows.
+// Work item = 16 samples = 2*BPS bytes (a whole number of 32-bit words), so all
+// bit offsets are compile-time constants.  The items of a job are numbered
+// row-major across rows ("flattened"), a CTA takes UNPACK_IPB consecutive items
+// -- usually spanning a few rows -- and stages each row segment with its own
+// 1-D bulk async copy (TMA) onto one mbarrier.
+// ------------------------------------------------------------------
+constexpr int UNPACK_IPB = 512;    // items per CTA (2 per thread)
+constexpr int UNPACK_MAXSEG = 12;  // row segments per CTA (rows >= 64 items wide)
+constexpr int UNPACK_FAST_SMEM = UNPACK_IPB * 32 + UNPACK_MAXSEG * 48;
+
+struct UnpackFastJobDev {
+  uint64_t in_offset;
+  uint64_t out_offset;
+  int32_t out_pitch, row0, rows, samples, out_col0, in_pitch, order;
+  uint32_t ipr;         // items per row
+  uint32_t total_items; // rows * ipr
+  uint32_t block_begin;
+  uint32_t vec_ok;
+  uint32_t row_bytes;
+};
+
+template <int BPS, bool LSBO>
+__device__ __forceinline__ void unpack_item16(const uint32_t* __restrict__ sw,
+                                              uint32_t sel, uint32_t (&o)[8]) {
+  constexpr int NW = BPS / 2; // words per item
+  uint32_t Wd[NW + 1];
+#pragma unroll
+  for (int i = 0; i < NW; ++i)
+    Wd[i] = LSBO ? sw[i] : __byte_perm(sw[i], 0, sel);
+  Wd[NW] = 0;
+  uint32_t v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    constexpr uint32_t mask = BPS == 32 ? 0xFFFFFFFFu : ((1u << BPS) - 1u);
+    const int bit = j * BPS;
+    const int w = bit >> 5, sh = bit & 31;
+    if (LSBO) {
+      if (sh + BPS <= 32)
+        v[j] = (Wd[w] >> sh) & mask;
+      else
+        v[j] = __funnelshift_r(Wd[w], Wd[w + 1], sh) & mask;
+    } else {
+      if (sh + BPS <= 32)
+        v[j] = (Wd[w] >> (32 - sh - BPS)) & mask;
+      else
+        v[j] = __funnelshift_l(Wd[w + 1], Wd[w], sh) >> (32 - BPS);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    o[k] = v[2 * k] | (v[2 * k + 1] << 16);
+}
+
+template <int BPS, bool LSBO>
+__global__ void __launch_bounds__(UNPACK_THREADS)
+    unpack_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                       const UnpackFastJobDev* __restrict__ jobs, int njobs) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int32_t seg_delta[UNPACK_MAXSEG + 1]; // smem offset - row-relative byte
+
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block_begin <= blockIdx.x)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const UnpackFastJobDev& job = jobs[lo];
+  constexpr uint32_t IB = 2 * BPS; // bytes per item
+  const uint32_t ipr = job.ipr;
+  const uint32_t I0 = (blockIdx.x - job.block_begin) * UNPACK_IPB;
+  const uint32_t I1 = min(I0 + UNPACK_IPB, job.total_items);
+  const uint32_t r0 = I0 / ipr;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    const uint32_t r1 = (I1 - 1) / ipr;
+    // pass 1: sizes
+    uint32_t total = 0;
+    for (uint32_t r = r0; r <= r1; ++r) {
+      const uint32_t ia = max(I0, r * ipr) - r * ipr;
+      const uint32_t ib = min(I1, (r + 1) * ipr) - r * ipr;
+      const uint64_t g0 = job.in_offset + (uint64_t)r * job.in_pitch + (uint64_t)ia * IB;
+      const uint64_t g1 = job.in_offset + (uint64_t)r * job.in_pitch +
+                          min((uint64_t)ib * IB, (uint64_t)job.row_bytes);
+      const uint64_t a0 = g0 & ~15ull, a1 = (g1 + 15) & ~15ull;
+      total += (uint32_t)(a1 - a0);
+    }
+    mbar_expect_tx(&bar, total);
+    uint32_t soff = 0;
+    for (uint32_t r = r0; r <= r1; ++r) {
+      const uint32_t ia = max(I0, r * ipr) - r * ipr;
+      const uint32_t ib = min(I1, (r + 1) * ipr) - r * ipr;
+      const uint64_t rowg = job.in_offset + (uint64_t)r * job.in_pitch;
+      const uint64_t g0 = rowg + (uint64_t)ia * IB;
+      const uint64_t g1 = rowg + min((uint64_t)ib * IB, (uint64_t)job.row_bytes);
+      const uint64_t a0 = g0 & ~15ull, a1 = (g1 + 15) & ~15ull;
+      bulk_g2s(smem + soff, in + a0, (uint32_t)(a1 - a0), &bar);
+      // smem address of row-relative byte x of row r: soff + (rowg + x - a0)
+      seg_delta[r - r0] = (int32_t)soff + (int32_t)(int64_t)(rowg - a0);
+      soff += (uint32_t)(a1 - a0);
+    }
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  const uint32_t sel = unpack_perm_selector(job.order);
+  const uint64_t obase = job.out_offset + 2ull * (uint64_t)job.out_col0;
+#pragma unroll
+  for (int it = 0; it < UNPACK_IPB / UNPACK_THREADS; ++it) {
+    const uint32_t I = I0 + it * UNPACK_THREADS + threadIdx.x;
+    if (I >= I1)
+      break;
+    const uint32_t r = I / ipr;
+    const uint32_t i = I - r * ipr;
+    const uint32_t saddr = (uint32_t)(seg_delta[r - r0] + (int32_t)(i * IB));
+    uint32_t o[8];
+    unpack_item16<BPS, LSBO>(reinterpret_cast<const uint32_t*>(smem + saddr), sel, o);
+    uint8_t* dst = out + obase + (uint64_t)(job.row0 + (int)r) * (uint64_t)job.out_pitch +
+                   32ull * i;
+    const uint32_t s_first = i * 16;
+    if (job.vec_ok && s_first + 16 <= (uint32_t)job.samples) {
+      stg_cs_v4(dst, make_uint4(o[0], o[1], o[2], o[3]));
+      stg_cs_v4(dst + 16, make_uint4(o[4], o[5], o[6], o[7]));
+    } else {
+      uint16_t* d16 = reinterpret_cast<uint16_t*>(dst);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (s_first + j < (uint32_t)job.samples)
+          d16[j] = (uint16_t)(o[j >> 1] >> ((j & 1) * 16));
+    }
+  }
+}
+
 } // namespace rsb200
