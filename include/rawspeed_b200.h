@@ -186,6 +186,12 @@ int rsb200_plan_run(rsb200_plan* plan, const void* d_in, size_t in_bytes,
  * bytes the decode does not write (it is uploaded first when partial != 0). */
 int rsb200_plan_run_host(rsb200_plan* plan, const uint8_t* in, size_t in_bytes,
                          uint8_t* out, size_t out_bytes, int partial);
+/* Same, for a plan whose output is ONE RawImage (pitch bytes between rows): only
+ * row_bytes of every row are copied back, so the host's row padding is left
+ * untouched (RawImageData::createData(), common/RawImage.cpp:68-113). */
+int rsb200_plan_run_host_image(rsb200_plan* plan, const uint8_t* in, size_t in_bytes,
+                               uint8_t* out, uint32_t pitch, uint32_t row_bytes,
+                               uint32_t rows, int partial);
 /* Waits for the plan's last run and returns per-segment status/consumed
  * (nresults = number of scans/jobs; unpack plans report RSB200_OK only).
  * Return value: first non-OK status, or RSB200_OK. */

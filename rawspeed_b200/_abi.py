@@ -53,7 +53,7 @@ EXPORTS = [
     "rsb200_abi_version", "rsb200_create", "rsb200_destroy", "rsb200_last_error",
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
-    "rsb200_plan_run_host", "rsb200_plan_results", "rsb200_plan_bytes",
+    "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",
 ]
 
@@ -90,6 +90,8 @@ def load():
                                          C.POINTER(Cr2Job), i32, C.POINTER(vp)]
     L.rsb200_plan_run.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp]
     L.rsb200_plan_run_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i32]
+    L.rsb200_plan_run_host_image.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.c_uint32,
+                                             C.c_uint32, i32]
     L.rsb200_plan_results.argtypes = [vp, C.POINTER(ScanResult), i32]
     L.rsb200_plan_bytes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.rsb200_plan_launches.argtypes = [vp]

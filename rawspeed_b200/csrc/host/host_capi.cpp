@@ -1,0 +1,204 @@
+// host_capi.cpp -- plain-C entry points over the C++ host mirror, so that the
+// Python parity tests (and any C consumer) can drive the reference-shaped
+// classes: same inputs as the reference's fuzz drivers
+// (fuzz/librawspeed/decompressors/*.cpp), exceptions reported as codes.
+#include "rawspeed_host.h"
+
+#include <cstring>
+
+using namespace rawspeed_b200;
+
+extern "C" {
+
+struct rsb200h_err {
+  int code; // 0 ok, 1 RawDecoderException, 2 IOException
+  char msg[240];
+};
+
+struct rsb200h_huff {
+  uint8_t ncpl[16];
+  uint8_t values[162];
+  int nvalues;
+};
+}
+
+namespace {
+template <typename F> int guarded(rsb200h_err* e, F&& f) {
+  if (e) {
+    e->code = 0;
+    e->msg[0] = 0;
+  }
+  try {
+    f();
+    return 0;
+  } catch (const IOException& ex) {
+    if (e) {
+      e->code = 2;
+      std::snprintf(e->msg, sizeof e->msg, "%s", ex.what());
+    }
+    return 2;
+  } catch (const RawspeedException& ex) {
+    if (e) {
+      e->code = 1;
+      std::snprintf(e->msg, sizeof e->msg, "%s", ex.what());
+    }
+    return 1;
+  }
+}
+
+RawImage makeImage(const uint16_t* src, int w, int h, int cpp, int pitch, bool isCfa, int subX,
+                   int subY) {
+  RawImage img = RawImage::create(iPoint2D(w, h), RawImageType::UINT16, (uint32_t)cpp);
+  img->isCFA = isCfa;
+  img->subsampling = iPoint2D(subX, subY);
+  if (img->pitch != pitch)
+    ThrowRDE("test harness: pitch mismatch (%d vs %d)", img->pitch, pitch);
+  std::memcpy(img->getByteData(), src, (size_t)pitch * h);
+  return img;
+}
+void copyOut(RawImage& img, uint16_t* dst) {
+  std::memcpy(dst, img->getByteData(), img->getByteSize());
+}
+
+PrefixCodeDecoder<> makeHT(const rsb200h_huff& t, bool fix16) {
+  HuffmanCode<> hc;
+  hc.setNCodesPerLength(Buffer(t.ncpl, 16));
+  hc.setCodeValues(t.values, t.nvalues);
+  PrefixCodeDecoder<> ht(std::move(hc));
+  ht.setup(true, fix16);
+  return ht;
+}
+} // namespace
+
+extern "C" {
+
+int rsb200h_unpack(const uint8_t* in, uint32_t in_size, uint16_t* img_data, int w, int h,
+                   int cpp, int pitch, int crop_x, int crop_y, int crop_w, int crop_h,
+                   int in_pitch, int bps, int order, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, cpp, pitch, true, 1, 1);
+    UncompressedDecompressor u(ByteStream(in, in_size), img,
+                               iRectangle2D(crop_x, crop_y, crop_w, crop_h), in_pitch, bps,
+                               static_cast<BitOrder>(order));
+    u.readUncompressedRaw();
+    copyOut(img, img_data);
+  });
+}
+
+int rsb200h_ljpeg_decompress(uint16_t* img_data, int w, int h, int cpp, int pitch, int fx, int fy,
+                             int fw, int fh, int mcu_x, int mcu_y, int dim_x, int dim_y,
+                             const rsb200h_huff* tabs, const int* tab_of_comp,
+                             const uint16_t* init_pred, int nrec, int fix16,
+                             int rows_per_restart, const uint8_t* in, uint32_t in_size,
+                             uint32_t* consumed, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, cpp, pitch, true, 1, 1);
+    std::vector<std::unique_ptr<PrefixCodeDecoder<>>> hts;
+    int maxTab = 0;
+    for (int i = 0; i < nrec; ++i)
+      maxTab = std::max(maxTab, tab_of_comp[i]);
+    for (int t = 0; t <= maxTab; ++t)
+      hts.emplace_back(std::make_unique<PrefixCodeDecoder<>>(makeHT(tabs[t], fix16)));
+    std::vector<LJpegDecompressor::PerComponentRecipe> rec;
+    for (int i = 0; i < nrec; ++i)
+      rec.push_back({*hts[(size_t)tab_of_comp[i]], init_pred[i]});
+    LJpegDecompressor d(img, iRectangle2D(fx, fy, fw, fh),
+                        LJpegDecompressor::Frame{iPoint2D(mcu_x, mcu_y), iPoint2D(dim_x, dim_y)},
+                        rec, rows_per_restart, Buffer(in, in_size));
+    const uint32_t c = d.decode();
+    if (consumed)
+      *consumed = c;
+    copyOut(img, img_data);
+  });
+}
+
+int rsb200h_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_data, int w, int h,
+                         int cpp, int pitch, uint32_t off_x, uint32_t off_y, uint32_t tw,
+                         uint32_t th, int max_w, int max_h, int fix16, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, cpp, pitch, true, 1, 1);
+    LJpegDecoder d(ByteStream(in, in_size), img);
+    d.decode(off_x, off_y, tw, th, iPoint2D(max_w, max_h), fix16 != 0);
+    copyOut(img, img_data);
+  });
+}
+
+int rsb200h_dng_decompress(const uint8_t* file, uint64_t file_size, const uint64_t* tile_off,
+                           const uint32_t* tile_len, int ntiles, uint16_t* img_data, int w, int h,
+                           int cpp, int pitch, int tile_w, int tile_h, int compression,
+                           int fix_ljpeg, int bps, int big_endian, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, cpp, pitch, true, 1, 1);
+    const iPoint2D dim(w, h);
+    DngTilingDescription dsc(dim, (uint32_t)tile_w, (uint32_t)tile_h);
+    AbstractDngDecompressor d(img, dsc, compression, fix_ljpeg != 0, (uint32_t)bps, 1);
+    const Buffer whole(file, (Buffer::size_type)file_size);
+    d.slices.reserve((size_t)ntiles);
+    for (int n = 0; n < ntiles; ++n)
+      d.slices.emplace_back(d.dsc, (unsigned)n,
+                            ByteStream(whole.getSubView((Buffer::size_type)tile_off[n], tile_len[n]),
+                                       big_endian ? Endianness::big : Endianness::little));
+    try {
+      d.decompress();
+    } catch (...) {
+      copyOut(img, img_data);
+      throw;
+    }
+    copyOut(img, img_data);
+  });
+}
+
+int rsb200h_cr2_decompress(uint16_t* img_data, int w, int h, int pitch, int is_cfa, int n_comp,
+                           int x_s_f, int y_s_f, int frame_w, int frame_h, int num_slices,
+                           int slice_w, int last_slice_w, const rsb200h_huff* tabs,
+                           const int* tab_of_comp, const uint16_t* init_pred, int nrec,
+                           const uint8_t* in, uint32_t in_size, uint32_t* consumed,
+                           rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, 1, pitch, is_cfa != 0, 1, 1);
+    std::vector<std::unique_ptr<PrefixCodeDecoder<>>> hts;
+    int maxTab = 0;
+    for (int i = 0; i < nrec; ++i)
+      maxTab = std::max(maxTab, tab_of_comp[i]);
+    for (int t = 0; t <= maxTab; ++t)
+      hts.emplace_back(std::make_unique<PrefixCodeDecoder<>>(makeHT(tabs[t], false)));
+    std::vector<Cr2Decompressor<>::PerComponentRecipe> rec;
+    for (int i = 0; i < nrec; ++i)
+      rec.push_back({*hts[(size_t)tab_of_comp[i]], init_pred[i]});
+    Cr2Decompressor<> d(img, std::make_tuple(n_comp, x_s_f, y_s_f), iPoint2D(frame_w, frame_h),
+                        Cr2SliceWidths((uint16_t)num_slices, (uint16_t)slice_w,
+                                       (uint16_t)last_slice_w),
+                        rec, Buffer(in, in_size));
+    const uint32_t c = d.decompress();
+    if (consumed)
+      *consumed = c;
+    copyOut(img, img_data);
+  });
+}
+
+int rsb200h_cr2_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_data, int w, int h,
+                             int pitch, int is_cfa, int sub_x, int sub_y, int num_slices,
+                             int slice_w, int last_slice_w, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, 1, pitch, is_cfa != 0, sub_x, sub_y);
+    Cr2LJpegDecoder d(ByteStream(in, in_size), img);
+    if (num_slices == 0 && slice_w == 0 && last_slice_w == 0)
+      d.decode(Cr2SliceWidths());
+    else
+      d.decode(Cr2SliceWidths((uint16_t)num_slices, (uint16_t)slice_w, (uint16_t)last_slice_w));
+    copyOut(img, img_data);
+  });
+}
+
+int rsb200h_huff_check(const uint8_t* ncpl, const uint8_t* values, int nvalues, int full,
+                       int fix16, rsb200h_err* e) {
+  return guarded(e, [&] {
+    HuffmanCode<> hc;
+    hc.setNCodesPerLength(Buffer(ncpl, 16));
+    hc.setCodeValues(values, nvalues);
+    PrefixCodeDecoder<> ht(std::move(hc));
+    ht.setup(full != 0, fix16 != 0);
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,1105 @@
+// rawspeed_host.cpp -- host side of the drop-in: the reference's decompressor
+// classes re-implemented above the C ABI (see rawspeed_host.h for the map of
+// reference files).  Everything here is header parsing / validation / exception
+// plumbing; every per-pixel loop of the reference is a call into
+// librawspeed_b200.so (CUDA).  There is no CPU decode path in this file.
+#include "rawspeed_host.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+namespace rawspeed_b200 {
+
+// ------------------------------------------------------------------ exceptions
+static std::string vfmt(const char* fmt, va_list ap) {
+  char buf[512];
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  return buf;
+}
+void ThrowRDE(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  std::string s = vfmt(fmt, ap);
+  va_end(ap);
+  throw RawDecoderException(s);
+}
+void ThrowIOE(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  std::string s = vfmt(fmt, ap);
+  va_end(ap);
+  throw IOException(s);
+}
+
+// ------------------------------------------------------------------ engine
+rsb200_ctx* engine() {
+  static rsb200_ctx* ctx = nullptr;
+  static std::mutex m;
+  std::lock_guard<std::mutex> g(m);
+  if (!ctx) {
+    int dev = 0;
+    if (const char* e = std::getenv("RSB200_DEVICE"))
+      dev = std::atoi(e);
+    if (rsb200_create(dev, &ctx) != RSB200_OK || !ctx)
+      ThrowRDE("rawspeed_b200: no usable CUDA device (there is no CPU fallback)");
+  }
+  return ctx;
+}
+
+void engineCheck(int rc, const char* what) {
+  if (rc == RSB200_OK)
+    return;
+  const char* msg = rsb200_last_error(engine());
+  if (rc == RSB200_ERR_IOE)
+    ThrowIOE("%s", (msg && *msg) ? msg : "Buffer overflow read in BitStreamer");
+  ThrowRDE("%s: %s", what, (msg && *msg) ? msg : "device error");
+}
+
+namespace {
+struct PlanGuard {
+  rsb200_plan* p = nullptr;
+  ~PlanGuard() {
+    if (p)
+      rsb200_plan_destroy(p);
+  }
+};
+
+// run a plan whose output is (part of) a RawImage held in host memory
+void runOnImage(rsb200_plan* plan, const uint8_t* in, size_t inBytes, RawImage& img,
+                bool partial) {
+  engineCheck(rsb200_plan_run_host_image(plan, in, inBytes, img->getByteData(),
+                                         (uint32_t)img->pitch,
+                                         (uint32_t)(img->dim.x * (int)img->getBpp()),
+                                         (uint32_t)img->dim.y, partial ? 1 : 0),
+              "rsb200_plan_run_host_image");
+}
+} // namespace
+
+// ------------------------------------------------------------------ RawImage
+void RawImageData::setCpp(uint32_t v) {
+  if (isAllocated())
+    ThrowRDE("Attempted to set Components per pixel after data allocation");
+  if (v > 4)
+    ThrowRDE("Only up to 4 components per pixel is support - attempted to set: %u", v);
+  bpp = bpp / cpp * v;
+  cpp = v;
+}
+
+void RawImageData::createData() {
+  if (dim.x > 65535 || dim.y > 65535)
+    ThrowRDE("Dimensions too large for allocation.");
+  if (dim.x <= 0 || dim.y <= 0)
+    ThrowRDE("Dimension of one sides is less than 1 - cannot allocate image.");
+  if (cpp <= 0 || bpp <= 0)
+    ThrowRDE("Unspecified component count - cannot allocate image.");
+  if (isAllocated())
+    ThrowRDE("Duplicate data allocation in createData.");
+  pitch = (int)(((size_t)dim.x * bpp + 15) / 16 * 16);
+  data.resize((size_t)pitch * dim.y + 16);
+  storage = reinterpret_cast<uint8_t*>(((uintptr_t)data.data() + 15) & ~(uintptr_t)15);
+}
+
+void RawImageData::setError(const std::string& err) {
+  std::lock_guard<std::mutex> g(errMutex);
+  errors.push_back(err);
+}
+bool RawImageData::isTooManyErrors(unsigned many, std::string* firstErr) {
+  std::lock_guard<std::mutex> g(errMutex);
+  if (errors.size() < many)
+    return false;
+  if (firstErr)
+    *firstErr = errors[0];
+  return true;
+}
+std::vector<std::string> RawImageData::getErrors() {
+  std::lock_guard<std::mutex> g(errMutex);
+  return errors;
+}
+
+RawImage RawImage::create(const iPoint2D& dim, RawImageType type, uint32_t cpp) {
+  if (type != RawImageType::UINT16)
+    ThrowRDE("rawspeed_b200: only UINT16 images are on the accelerated path");
+  RawImage r;
+  r.p_ = std::make_shared<RawImageData>();
+  r.p_->dim = dim;
+  r.p_->cpp = cpp;
+  r.p_->bpp = 2 * cpp;
+  r.p_->createData();
+  return r;
+}
+
+// ------------------------------------------------------------------ Huffman
+template <typename Tag> uint32_t HuffmanCode<Tag>::setNCodesPerLength(Buffer data) {
+  if (data.getSize() != 16)
+    ThrowRDE("Codes-per-length table must have 16 entries");
+  uint32_t cnt = 0;
+  int maxLen = 0;
+  for (int l = 1; l <= 16; ++l) {
+    nCodesPerLength[l - 1] = data.begin()[l - 1];
+    cnt += nCodesPerLength[l - 1];
+    if (nCodesPerLength[l - 1])
+      maxLen = l;
+  }
+  if (maxLen == 0)
+    ThrowRDE("Codes-per-length table is empty");
+  if (cnt > 162)
+    ThrowRDE("Too big code-values table");
+  // a code of length l needs a free node at depth l (Kraft)
+  unsigned freeNodes = 2;
+  for (int l = 1; l <= maxLen; ++l) {
+    const unsigned n = nCodesPerLength[l - 1];
+    if (n > (1U << l))
+      ThrowRDE("Corrupt Huffman. Can never have %u codes in %d-bit len", n, l);
+    if (n > freeNodes)
+      ThrowRDE("Corrupt Huffman. Can only fit %u out of %u codes in %d-bit len", freeNodes, n, l);
+    freeNodes = (freeNodes - n) * 2;
+  }
+  count = cnt;
+  return cnt;
+}
+
+template <typename Tag> void HuffmanCode<Tag>::setCodeValues(const uint8_t* values, int n) {
+  if ((uint32_t)n != count)
+    ThrowRDE("Malformed code");
+  codeValues.assign(values, values + n);
+}
+
+template <typename Tag> void PrefixCodeDecoder<Tag>::setup(bool fullDecode_, bool fixDNGBug16_) {
+  fullDecode = fullDecode_;
+  fixDNGBug16 = fixDNGBug16_;
+  if (code.codeValues.empty())
+    ThrowRDE("Empty code alphabet?");
+  if (fullDecode)
+    for (uint8_t v : code.codeValues)
+      if (v > 16)
+        ThrowRDE("Corrupt Huffman code: difference length %u longer than %u", v, 16);
+}
+
+template <typename Tag> rsb200_huff_table PrefixCodeDecoder<Tag>::deviceTable() const {
+  rsb200_huff_table t;
+  std::memset(&t, 0, sizeof t);
+  std::memcpy(t.ncodes_per_len, code.nCodesPerLength.data(), 16);
+  std::memcpy(t.values, code.codeValues.data(), code.codeValues.size());
+  t.nvalues = (uint16_t)code.codeValues.size();
+  t.fix_dng16 = fixDNGBug16 ? 1 : 0;
+  return t;
+}
+
+template class HuffmanCode<BaselineCodeTag>;
+template class PrefixCodeDecoder<BaselineCodeTag>;
+
+static uint8_t tableIndex(std::vector<rsb200_huff_table>& tables, const rsb200_huff_table& t) {
+  for (size_t i = 0; i < tables.size(); ++i)
+    if (!std::memcmp(&tables[i], &t, sizeof t))
+      return (uint8_t)i;
+  if (tables.size() >= 255)
+    ThrowRDE("Too many distinct Huffman tables in one batch");
+  tables.push_back(t);
+  return (uint8_t)(tables.size() - 1);
+}
+
+// ------------------------------------------------------------------ K1
+UncompressedDecompressor::UncompressedDecompressor(ByteStream input_, RawImage img_,
+                                                   const iRectangle2D& crop,
+                                                   int inputPitchBytes_, int bitPerPixel_,
+                                                   BitOrder order_)
+    : input(input_.getStream((uint32_t)crop.dim.y, (uint32_t)inputPitchBytes_)),
+      mRaw(std::move(img_)), size(crop.dim), offset(crop.pos),
+      inputPitchBytes(inputPitchBytes_), bitPerPixel(bitPerPixel_), order(order_) {
+  if (!size.hasPositiveArea())
+    ThrowRDE("Empty tile.");
+  if (inputPitchBytes < 1)
+    ThrowRDE("Input pitch is non-positive");
+  if (order == BitOrder::JPEG)
+    ThrowRDE("JPEG bit order not supported.");
+  const uint32_t w = size.x, h = size.y, cpp = mRaw->getCpp();
+  const uint64_t ox = offset.x, oy = offset.y;
+  if (cpp < 1 || cpp > 3)
+    ThrowRDE("Unsupported number of components per pixel: %u", cpp);
+  if (bitPerPixel < 1 || bitPerPixel > 32 || bitPerPixel > 16)
+    ThrowRDE("Unsupported bit depth");
+  const uint64_t outPixelBits = (uint64_t)w * cpp * bitPerPixel;
+  if (outPixelBits % 8 != 0)
+    ThrowRDE("Bad combination of cpp (%u), bps (%d) and width (%u), the pitch is %llu bits, "
+             "which is not a multiple of 8 (1 byte)",
+             cpp, bitPerPixel, w, (unsigned long long)outPixelBits);
+  const uint64_t outPixelBytes = outPixelBits / 8;
+  if ((uint64_t)(unsigned)inputPitchBytes < outPixelBytes)
+    ThrowRDE("Specified pitch is smaller than minimally-required pitch");
+  const uint32_t fullRows = input.getRemainSize() / (uint32_t)inputPitchBytes;
+  if (fullRows < h) {
+    if (fullRows == 0)
+      ThrowIOE("Not enough data to decode a single line. Image file truncated.");
+    ThrowIOE("Image truncated, only %u of %u lines found", fullRows, h);
+  }
+  skipBytes = (uint32_t)(inputPitchBytes - outPixelBytes);
+  if (oy > (uint64_t)mRaw->dim.y)
+    ThrowRDE("Invalid y offset");
+  if (ox + size.x > (uint64_t)mRaw->dim.x)
+    ThrowRDE("Invalid x offset");
+}
+
+bool UncompressedDecompressor::describe(const uint8_t* fileBase, rsb200_unpack_job* job) const {
+  const uint32_t cpp = mRaw->getCpp();
+  const uint64_t oy = offset.y;
+  const uint64_t hEnd = std::min<uint64_t>((uint64_t)size.y + oy, (uint64_t)mRaw->dim.y);
+  const bool copy16 = (order == BitOrder::LSB && bitPerPixel == 16);
+  if (!copy16 && input.getRemainSize() < 4) // BitStreamer ctor (BitStreamer.h:56-60)
+    ThrowIOE("Bit stream size is smaller than MaxProcessBytes");
+  if (hEnd <= oy)
+    return false;
+  std::memset(job, 0, sizeof *job);
+  job->in_offset = (uint64_t)(input.begin() - fileBase);
+  job->in_size = input.getRemainSize();
+  job->out_offset = 0;
+  job->out_pitch = mRaw->pitch;
+  job->row0 = (int32_t)oy;
+  job->rows = (int32_t)(hEnd - oy);
+  job->samples = (int32_t)(size.x * (int)cpp);
+  // packed integers ignore the crop's x offset (UncompressedDecompressor.cpp:196),
+  // the 16-bit little-endian row copy honours it (:255-264)
+  job->out_col0 = copy16 ? (int32_t)(offset.x * (int)cpp) : 0;
+  job->in_pitch = inputPitchBytes;
+  job->bps = bitPerPixel;
+  job->order = (int32_t)order;
+  return true;
+}
+
+void UncompressedDecompressor::readUncompressedRaw() {
+  rsb200_unpack_job job;
+  if (!describe(input.begin(), &job))
+    return;
+  PlanGuard pg;
+  engineCheck(rsb200_unpack_plan_create(engine(), &job, 1, &pg.p), "rsb200_unpack_plan_create");
+  runOnImage(pg.p, input.begin(), input.getRemainSize(), mRaw, /*partial=*/true);
+}
+
+// ------------------------------------------------------------------ LJPEG
+LJpegDecompressor::LJpegDecompressor(RawImage img, iRectangle2D imgFrame_, Frame frame_,
+                                     std::vector<PerComponentRecipe> rec_,
+                                     int numLJpegRowsPerRestartInterval_, Buffer input_)
+    : mRaw(std::move(img)), input(input_), imgFrame(imgFrame_), frame(frame_),
+      rec(std::move(rec_)), numLJpegRowsPerRestartInterval(numLJpegRowsPerRestartInterval_) {
+  const int cpp = (int)mRaw->getCpp();
+  if (cpp < 1 || cpp > 3)
+    ThrowRDE("Unexpected component count (%u)", mRaw->getCpp());
+  if (!mRaw->dim.hasPositiveArea())
+    ThrowRDE("Image has zero size");
+  if (!imgFrame.hasPositiveArea())
+    ThrowRDE("Tile has zero size");
+  if (imgFrame.pos.x >= mRaw->dim.x)
+    ThrowRDE("X offset outside of image");
+  if (imgFrame.pos.y >= mRaw->dim.y)
+    ThrowRDE("Y offset outside of image");
+  if (imgFrame.dim.x > mRaw->dim.x)
+    ThrowRDE("Tile wider than image");
+  if (imgFrame.dim.y > mRaw->dim.y)
+    ThrowRDE("Tile taller than image");
+  if (imgFrame.pos.x + imgFrame.dim.x > mRaw->dim.x)
+    ThrowRDE("Tile overflows image horizontally");
+  if (imgFrame.pos.y + imgFrame.dim.y > mRaw->dim.y)
+    ThrowRDE("Tile overflows image vertically");
+  if (!frame.dim.hasPositiveArea())
+    ThrowRDE("Frame has zero size");
+  const iPoint2D m = frame.mcu;
+  const bool mcuOk = (m.y == 1 && m.x >= 1 && m.x <= 4) || (m.x == 2 && m.y == 2);
+  if (!mcuOk)
+    ThrowRDE("Unexpected MCU size: {%i, %i}", m.x, m.y);
+  if (rec.size() != (size_t)(m.x * m.y))
+    ThrowRDE("Must have exactly one recepie per component");
+  for (const auto& r : rec)
+    if (!r.ht.isFullDecode())
+      ThrowRDE("Huffman table is not of a full decoding variety");
+  if (numLJpegRowsPerRestartInterval < 1)
+    ThrowRDE("Number of rows per restart interval must be positives");
+  if ((int64_t)m.x * frame.dim.x > std::numeric_limits<int>::max() ||
+      (int64_t)m.y * frame.dim.y > std::numeric_limits<int>::max())
+    ThrowRDE("LJpeg frame is too big");
+  if ((int64_t)cpp * imgFrame.dim.x > std::numeric_limits<int>::max())
+    ThrowRDE("Img frame is too big");
+  if (imgFrame.dim.x < m.x || imgFrame.dim.y < m.y)
+    ThrowRDE("Tile size is smaller than a single frame MCU");
+  if (imgFrame.dim.y % m.y != 0)
+    ThrowRDE("Output row count is not a multiple of MCU row count");
+  const int tileRequiredWidth = cpp * imgFrame.dim.x;
+  const int mcusToConsume = (tileRequiredWidth + m.x - 1) / m.x;
+  if (frame.dim.x < mcusToConsume || m.y * frame.dim.y < imgFrame.dim.y ||
+      m.x * frame.dim.x < tileRequiredWidth)
+    ThrowRDE("LJpeg frame (%d, %d) is smaller than expected (%d, %d)", m.x * frame.dim.x,
+             m.y * frame.dim.y, tileRequiredWidth, imgFrame.dim.y);
+  const int rows = imgFrame.dim.y / m.y;
+  numRestartIntervals = (rows + numLJpegRowsPerRestartInterval - 1) / numLJpegRowsPerRestartInterval;
+}
+
+void LJpegDecompressor::describe(const uint8_t* fileBase, std::vector<rsb200_huff_table>& tables,
+                                 std::vector<rsb200_ljpeg_scan>& scans,
+                                 uint64_t outOffset) const {
+  const int cpp = (int)mRaw->getCpp();
+  const iPoint2D m = frame.mcu;
+  const int totalRows = imgFrame.dim.y / m.y;
+  const uint8_t* data = input.begin();
+  const uint32_t size = input.getSize();
+  uint8_t tab[4] = {0, 0, 0, 0};
+  for (size_t c = 0; c < rec.size(); ++c)
+    tab[c] = tableIndex(tables, rec[c].ht.deviceTable());
+  intervalStart.assign(1, 0);
+  markerPos.clear();
+  // Restart intervals: the entropy data of interval k ends at the first FFxx
+  // (xx != 00); it must be RST((k) % 8) (LJpegDecompressor.cpp:286-297).
+  for (int k = 1; k < numRestartIntervals; ++k) {
+    uint32_t p = intervalStart.back();
+    bool foundMarker = false;
+    while (p + 1 < size) {
+      const uint8_t* q = (const uint8_t*)std::memchr(data + p, 0xFF, size - 1 - p);
+      if (!q)
+        break;
+      p = (uint32_t)(q - data);
+      if (data[p + 1] != 0x00) {
+        foundMarker = true;
+        break;
+      }
+      p += 2;
+    }
+    if (!foundMarker)
+      ThrowRDE("Jpeg marker not encountered");
+    const uint8_t c1 = data[p + 1];
+    if (c1 == 0xFF)
+      ThrowRDE("Jpeg marker not encountered");
+    if (c1 < 0xD0 || c1 > 0xD7)
+      ThrowRDE("Not a restart marker!");
+    if ((c1 - 0xD0) != ((k - 1) % 8))
+      ThrowRDE("Unexpected restart marker found");
+    markerPos.push_back(p);
+    intervalStart.push_back(p + 2);
+  }
+  for (int k = 0; k < numRestartIntervals; ++k) {
+    const uint32_t start = intervalStart[(size_t)k];
+    if (size < start || size - start < 8) // BitStreamerJPEG: MaxProcessBytes == 8
+      ThrowIOE("Bit stream size is smaller than MaxProcessBytes");
+    rsb200_ljpeg_scan s;
+    std::memset(&s, 0, sizeof s);
+    s.in_offset = (uint64_t)(data - fileBase) + start;
+    s.in_size = size - start;
+    s.rows = (uint32_t)std::min(numLJpegRowsPerRestartInterval,
+                                totalRows - k * numLJpegRowsPerRestartInterval);
+    s.frame_w = (uint32_t)frame.dim.x;
+    s.mcu_w = (uint8_t)m.x;
+    s.mcu_h = (uint8_t)m.y;
+    for (size_t c = 0; c < rec.size(); ++c) {
+      s.table[c] = tab[c];
+      s.init_pred[c] = rec[c].initPred;
+    }
+    s.out_offset = outOffset;
+    s.out_pitch = (uint32_t)mRaw->pitch;
+    s.out_x = (uint32_t)(cpp * imgFrame.pos.x);
+    s.out_y = (uint32_t)(imgFrame.pos.y + m.y * numLJpegRowsPerRestartInterval * k);
+    s.store_w = (uint32_t)(cpp * imgFrame.dim.x);
+    scans.push_back(s);
+  }
+}
+
+uint32_t LJpegDecompressor::finish(const rsb200_scan_result* res, int nres) const {
+  if (nres != numRestartIntervals)
+    ThrowRDE("internal: result count mismatch");
+  for (int k = 0; k < numRestartIntervals; ++k) {
+    if (res[k].status == RSB200_ERR_RDE)
+      ThrowRDE("bad Huffman code");
+    if (res[k].status == RSB200_ERR_IOE)
+      ThrowIOE("Buffer overflow read in BitStreamer");
+    if (res[k].status != RSB200_OK)
+      ThrowRDE("device error %u", res[k].status);
+    if (k + 1 < numRestartIntervals) {
+      // the pump must have stopped exactly on the restart marker
+      if ((uint64_t)intervalStart[(size_t)k] + res[k].consumed != markerPos[(size_t)k])
+        ThrowRDE("Jpeg marker not encountered");
+    }
+  }
+  const uint64_t pos = (uint64_t)intervalStart.back() + res[numRestartIntervals - 1].consumed;
+  if (pos > input.getSize()) // inputStream.skipBytes(bs.getStreamPosition())
+    ThrowIOE("Out of bounds access in ByteStream");
+  return (uint32_t)pos;
+}
+
+uint32_t LJpegDecompressor::decode() const {
+  std::vector<rsb200_huff_table> tables;
+  std::vector<rsb200_ljpeg_scan> scans;
+  describe(input.begin(), tables, scans);
+  PlanGuard pg;
+  engineCheck(rsb200_ljpeg_plan_create(engine(), tables.data(), (int)tables.size(), scans.data(),
+                                       (int)scans.size(), &pg.p),
+              "rsb200_ljpeg_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, input.begin(), input.getSize(), img, /*partial=*/true);
+  std::vector<rsb200_scan_result> res(scans.size());
+  (void)rsb200_plan_results(pg.p, res.data(), (int)res.size());
+  return finish(res.data(), (int)res.size());
+}
+
+// ------------------------------------------------------------------ marker walk
+AbstractLJpegDecoder::AbstractLJpegDecoder(ByteStream bs, RawImage img)
+    : input(bs), mRaw(std::move(img)) {
+  input.setByteOrder(Endianness::big);
+  if (!mRaw->dim.hasPositiveArea())
+    ThrowRDE("Image has zero size");
+}
+
+uint8_t AbstractLJpegDecoder::getNextMarker(bool allowskip) {
+  // first FF xx with xx not in {00, FF}; without skipping it must be right here
+  ByteStream probe = input;
+  bool found = false;
+  while (probe.getRemainSize() >= 2) {
+    const uint8_t c0 = probe.peekByte(0), c1 = probe.peekByte(1);
+    if (c0 == 0xFF && c1 != 0 && c1 != 0xFF) {
+      found = true;
+      break;
+    }
+    if (!allowskip)
+      break;
+    probe.skipBytes(1);
+  }
+  if (!found)
+    ThrowRDE("(Noskip) Expected marker not found. Probably corrupt file.");
+  input = probe;
+  const uint8_t m = input.peekByte(1);
+  input.skipBytes(2);
+  return m;
+}
+
+void AbstractLJpegDecoder::parseSOF(ByteStream s, SOFInfo* sof) {
+  sof->prec = s.getByte();
+  sof->h = s.getU16();
+  sof->w = s.getU16();
+  sof->cps = s.getByte();
+  if (sof->prec < 2 || sof->prec > 16)
+    ThrowRDE("Invalid precision (%u).", sof->prec);
+  if (sof->h == 0 || sof->w == 0)
+    ThrowRDE("Frame width or height set to zero");
+  if (sof->cps > 4 || sof->cps < 1)
+    ThrowRDE("Only from 1 to 4 components are supported.");
+  if (sof->cps < mRaw->getCpp())
+    ThrowRDE("Component count should be no less than sample count (%u vs %u).", sof->cps,
+             mRaw->getCpp());
+  if (sof->cps > (uint32_t)mRaw->dim.x)
+    ThrowRDE("Component count should be no greater than row length (%u vs %d).", sof->cps,
+             mRaw->dim.x);
+  if (s.getRemainSize() != 3 * sof->cps)
+    ThrowRDE("Header size mismatch.");
+  for (uint32_t i = 0; i < sof->cps; i++) {
+    sof->compInfo[i].componentId = s.getByte();
+    const uint32_t subs = s.getByte();
+    sof->compInfo[i].superV = subs & 0xf;
+    sof->compInfo[i].superH = subs >> 4;
+    if (sof->compInfo[i].superV < 1 || sof->compInfo[i].superV > 4)
+      ThrowRDE("Horizontal sampling factor is invalid.");
+    if (sof->compInfo[i].superH < 1 || sof->compInfo[i].superH > 4)
+      ThrowRDE("Horizontal sampling factor is invalid.");
+    if (s.getByte() != 0)
+      ThrowRDE("Quantized components not supported.");
+  }
+  if ((int)sof->compInfo[0].superH != mRaw->subsampling.x ||
+      (int)sof->compInfo[0].superV != mRaw->subsampling.y)
+    ThrowRDE("LJpeg's subsampling does not match image's subsampling.");
+  sof->initialized = true;
+}
+
+void AbstractLJpegDecoder::parseDHT(ByteStream dht) {
+  while (dht.getRemainSize() > 0) {
+    const uint32_t b = dht.getByte();
+    if ((b >> 4) != 0)
+      ThrowRDE("Unsupported Table class.");
+    const uint32_t htIndex = b & 0xf;
+    if (htIndex >= huff.size())
+      ThrowRDE("Invalid huffman table destination id.");
+    if (huff[htIndex] != nullptr)
+      ThrowRDE("Duplicate table definition");
+    HuffmanCode<> hc;
+    const uint32_t nCodes = hc.setNCodesPerLength(dht.getBuffer(16));
+    if (nCodes > 17) // Hasselblad uses 17
+      ThrowRDE("Invalid DHT table.");
+    const Buffer vals = dht.getBuffer(nCodes);
+    hc.setCodeValues(vals.begin(), (int)nCodes);
+    for (size_t i = 0; i < huffmanCodeStore.size(); ++i)
+      if (*huffmanCodeStore[i] == hc)
+        huff[htIndex] = PrefixCodeDecoderStore[i].get();
+    if (!huff[htIndex]) {
+      huffmanCodeStore.emplace_back(std::make_unique<HuffmanCode<>>(hc));
+      auto dHT = std::make_unique<PrefixCodeDecoder<>>(std::move(hc));
+      dHT->setup(fullDecodeHT, fixDng16Bug);
+      huff[htIndex] = dHT.get();
+      PrefixCodeDecoderStore.emplace_back(std::move(dHT));
+    }
+  }
+}
+
+void AbstractLJpegDecoder::parseDRI(ByteStream dri) {
+  if (dri.getRemainSize() != 2)
+    ThrowRDE("Invalid DRI header length.");
+  numMCUsPerRestartInterval = dri.getU16();
+}
+
+void AbstractLJpegDecoder::parseSOS(ByteStream sos) {
+  if (sos.getRemainSize() != 1 + 2 * frame.cps + 3)
+    ThrowRDE("Invalid SOS header length.");
+  if (const uint32_t soscps = sos.getByte(); frame.cps != soscps)
+    ThrowRDE("Component number mismatch.");
+  for (uint32_t i = 0; i < frame.cps; i++) {
+    const uint32_t cs = sos.getByte();
+    const uint32_t td = sos.getByte() >> 4;
+    if (td >= huff.size() || !huff[td])
+      ThrowRDE("Invalid Huffman table selection.");
+    int ciIndex = -1;
+    for (uint32_t j = 0; j < frame.cps; ++j)
+      if (frame.compInfo[j].componentId == cs)
+        ciIndex = (int)j;
+    if (ciIndex == -1)
+      ThrowRDE("Invalid Component Selector");
+    frame.compInfo[(size_t)ciIndex].dcTblNo = td;
+  }
+  predictorMode = sos.getByte();
+  if (predictorMode > 8) // Hasselblad uses '8'
+    ThrowRDE("Invalid predictor mode.");
+  if (sos.getByte() != 0)
+    ThrowRDE("Se/Ah not zero.");
+  Pt = sos.getByte();
+  if (Pt > 15)
+    ThrowRDE("Invalid Point transform.");
+  if (Pt != 0)
+    ThrowRDE("Point transform not supported.");
+  prepareScan(); // == the validating half of decodeScan()
+  pendingScan = true;
+}
+
+std::vector<const PrefixCodeDecoder<>*>
+AbstractLJpegDecoder::getPrefixCodeDecoders(int N_COMP) const {
+  std::vector<const PrefixCodeDecoder<>*> ht((size_t)N_COMP);
+  for (int i = 0; i < N_COMP; ++i) {
+    const unsigned t = frame.compInfo[(size_t)i].dcTblNo;
+    if (t >= huff.size())
+      ThrowRDE("Decoding table %u for comp %i does not exist (tables = %u)", t, i,
+               (unsigned)huff.size());
+    ht[(size_t)i] = huff[t];
+  }
+  return ht;
+}
+
+std::vector<uint16_t> AbstractLJpegDecoder::getInitialPredictors(int N_COMP) const {
+  if (frame.prec < (Pt + 1))
+    ThrowRDE("Invalid precision (%u) and point transform (%u) combination!", frame.prec, Pt);
+  return std::vector<uint16_t>((size_t)N_COMP, (uint16_t)(1u << (frame.prec - Pt - 1)));
+}
+
+void AbstractLJpegDecoder::markerLoop(bool resume) {
+  if (!resume) {
+    if (getNextMarker(false) != 0xD8)
+      ThrowRDE("Image did not start with SOI. Probably not an LJPEG");
+  }
+  for (uint8_t m; (m = getNextMarker(true)) != 0xD9;) {
+    ByteStream data(input.getStream(input.peekU16()));
+    data.setByteOrder(Endianness::big);
+    data.skipBytes(2);
+    switch (m) {
+    case 0xC4: // DHT
+      if (found.SOS)
+        ThrowRDE("Found second DHT marker after SOS");
+      parseDHT(data);
+      found.DHT = true;
+      break;
+    case 0xC3: // SOF3
+      if (found.SOS)
+        ThrowRDE("Found second SOF marker after SOS");
+      if (found.SOF)
+        ThrowRDE("Found second SOF marker");
+      parseSOF(data, &frame);
+      found.SOF = true;
+      break;
+    case 0xDA: // SOS
+      if (found.SOS)
+        ThrowRDE("Found second SOS marker");
+      if (!found.DHT)
+        ThrowRDE("Did not find DHT marker before SOS.");
+      if (!found.SOF)
+        ThrowRDE("Did not find SOF marker before SOS.");
+      parseSOS(data);
+      if (immediate) {
+        const uint32_t scanLength = runScan();
+        pendingScan = false;
+        input.skipBytes(scanLength);
+        found.SOS = true;
+        break;
+      }
+      return; // batch mode: resume in decodeSOIAfterScan()
+    case 0xDB: // DQT
+      ThrowRDE("Not a valid RAW file.");
+    case 0xDD: // DRI
+      if (found.DRI)
+        ThrowRDE("Found second DRI marker");
+      parseDRI(data);
+      found.DRI = true;
+      break;
+    default:
+      break;
+    }
+  }
+  if (!found.SOS)
+    ThrowRDE("Did not find SOS marker.");
+}
+
+void AbstractLJpegDecoder::decodeSOI() {
+  immediate = true;
+  markerLoop(false);
+}
+void AbstractLJpegDecoder::decodeSOIUntilScan() {
+  immediate = false;
+  markerLoop(false);
+}
+void AbstractLJpegDecoder::decodeSOIAfterScan(uint32_t scanLength) {
+  pendingScan = false;
+  input.skipBytes(scanLength);
+  found.SOS = true;
+  markerLoop(true);
+}
+
+// ------------------------------------------------------------------ LJpegDecoder
+LJpegDecoder::LJpegDecoder(ByteStream bs, const RawImage& img) : AbstractLJpegDecoder(bs, img) {
+  const uint32_t cpp = mRaw->getCpp();
+  if (cpp < 1 || cpp > 3)
+    ThrowRDE("Unexpected component count (%u)", cpp);
+  if (!mRaw->dim.hasPositiveArea())
+    ThrowRDE("Image has zero size");
+}
+
+bool LJpegDecoder::prepare(uint32_t offsetX, uint32_t offsetY, uint32_t width, uint32_t height,
+                           iPoint2D maxDim_, bool fixDng16Bug_) {
+  if (offsetX >= (unsigned)mRaw->dim.x)
+    ThrowRDE("X offset outside of image");
+  if (offsetY >= (unsigned)mRaw->dim.y)
+    ThrowRDE("Y offset outside of image");
+  if (width > (unsigned)mRaw->dim.x)
+    ThrowRDE("Tile wider than image");
+  if (height > (unsigned)mRaw->dim.y)
+    ThrowRDE("Tile taller than image");
+  if (offsetX + width > (unsigned)mRaw->dim.x)
+    ThrowRDE("Tile overflows image horizontally");
+  if (offsetY + height > (unsigned)mRaw->dim.y)
+    ThrowRDE("Tile overflows image vertically");
+  if (width == 0 || height == 0)
+    return false; // nothing needed from this tile
+  if (!maxDim_.hasPositiveArea() || (unsigned)maxDim_.x < width || (unsigned)maxDim_.y < height)
+    ThrowRDE("Requested tile is larger than tile's maximal dimensions");
+  offX = offsetX;
+  offY = offsetY;
+  w = width;
+  h = height;
+  maxDim = maxDim_;
+  fixDng16Bug = fixDng16Bug_;
+  decodeSOIUntilScan();
+  return scanPending();
+}
+
+void LJpegDecoder::decode(uint32_t offsetX, uint32_t offsetY, uint32_t width, uint32_t height,
+                          iPoint2D maxDim_, bool fixDng16Bug_) {
+  if (!prepare(offsetX, offsetY, width, height, maxDim_, fixDng16Bug_))
+    return;
+  const uint32_t consumed = runScan();
+  decodeSOIAfterScan(consumed);
+}
+
+void LJpegDecoder::prepareScan() {
+  if (predictorMode != 1)
+    ThrowRDE("Unsupported predictor mode: %u", predictorMode);
+  for (uint32_t i = 0; i < frame.cps; i++)
+    if (frame.compInfo[i].superH != 1 || frame.compInfo[i].superV != 1)
+      ThrowRDE("Unsupported subsampling");
+  const int N_COMP = (int)frame.cps;
+  const auto hts = getPrefixCodeDecoders(N_COMP);
+  const auto initPred = getInitialPredictors(N_COMP);
+  std::vector<LJpegDecompressor::PerComponentRecipe> rec;
+  rec.reserve((size_t)N_COMP);
+  for (int i = 0; i < N_COMP; ++i)
+    rec.push_back({*hts[(size_t)i], initPred[(size_t)i]});
+  const iRectangle2D imgFrame((int)offX, (int)offY, (int)w, (int)h);
+  const iPoint2D jpegFrameDim((int)frame.w, (int)frame.h);
+  if ((int64_t)maxDim.x * (int)mRaw->getCpp() > std::numeric_limits<int>::max())
+    ThrowRDE("Maximal output tile is too large");
+  const iPoint2D maxRes((int)mRaw->getCpp() * maxDim.x, maxDim.y);
+  if (maxRes.area() != (uint64_t)N_COMP * jpegFrameDim.area())
+    ThrowRDE("LJpeg frame area does not match maximal tile area");
+  if (maxRes.x % jpegFrameDim.x != 0 || maxRes.y % jpegFrameDim.y != 0)
+    ThrowRDE("Maximal output tile size is not a multiple of LJpeg frame size");
+  const iPoint2D MCUSize(maxRes.x / jpegFrameDim.x, maxRes.y / jpegFrameDim.y);
+  if (MCUSize.area() != (uint64_t)N_COMP)
+    ThrowRDE("Unexpected MCU size, does not match LJpeg component count");
+  int rowsPerInterval;
+  if (numMCUsPerRestartInterval == 0)
+    rowsPerInterval = jpegFrameDim.y;
+  else {
+    if (numMCUsPerRestartInterval % jpegFrameDim.x != 0)
+      ThrowRDE("Restart interval is not a multiple of frame row size");
+    rowsPerInterval = numMCUsPerRestartInterval / jpegFrameDim.x;
+  }
+  d = std::make_unique<LJpegDecompressor>(mRaw, imgFrame,
+                                          LJpegDecompressor::Frame{MCUSize, jpegFrameDim}, rec,
+                                          rowsPerInterval, input.peekRemainingBuffer());
+}
+
+uint32_t LJpegDecoder::runScan() { return d->decode(); }
+
+// ------------------------------------------------------------------ CR2
+Cr2SliceWidths::Cr2SliceWidths(uint16_t numSlices_, uint16_t sliceWidth_, uint16_t lastSliceWidth_)
+    : numSlices(numSlices_), sliceWidth(sliceWidth_), lastSliceWidth(lastSliceWidth_) {
+  if (numSlices < 1)
+    ThrowRDE("Bad slice count: %d", numSlices);
+}
+
+namespace {
+struct Cr2Dsc { // Dsc of Cr2DecompressorImpl.h:250-275
+  int N_COMP, X_S_F, Y_S_F, sliceColStep, pixelsPerGroup, groupSize;
+  bool subSampled;
+  explicit Cr2Dsc(std::tuple<int, int, int> f)
+      : N_COMP(std::get<0>(f)), X_S_F(std::get<1>(f)), Y_S_F(std::get<2>(f)),
+        sliceColStep(N_COMP * X_S_F), pixelsPerGroup(X_S_F * Y_S_F),
+        groupSize((X_S_F != 1 || Y_S_F != 1) ? 2 + X_S_F * Y_S_F : N_COMP),
+        subSampled(X_S_F != 1 || Y_S_F != 1) {}
+};
+struct Rect {
+  int x, y, w, h;
+};
+} // namespace
+
+template <typename HT>
+Cr2Decompressor<HT>::Cr2Decompressor(RawImage mRaw_, std::tuple<int, int, int> format_,
+                                     iPoint2D frame_, Cr2SliceWidths slicing_,
+                                     std::vector<PerComponentRecipe> rec_, Buffer input_)
+    : mRaw(std::move(mRaw_)), format(format_), frame(frame_), slicing(slicing_),
+      rawSlicing(slicing_), rawFrame(frame_), rec(std::move(rec_)), input(input_) {
+  if (mRaw->getCpp() != 1 || mRaw->getBpp() != 2)
+    ThrowRDE("Unexpected cpp: %u", mRaw->getCpp());
+  const auto f = format;
+  const bool known = f == std::make_tuple(3, 2, 2) || f == std::make_tuple(3, 2, 1) ||
+                     f == std::make_tuple(2, 1, 1) || f == std::make_tuple(4, 1, 1);
+  if (!known)
+    ThrowRDE("Unknown format <%i,%i,%i>", std::get<0>(f), std::get<1>(f), std::get<2>(f));
+  const Cr2Dsc dsc(format);
+  dim = mRaw->dim;
+  if (!dim.hasPositiveArea() || dim.x % dsc.groupSize != 0)
+    ThrowRDE("Unexpected image dimension multiplicity");
+  dim.x /= dsc.groupSize;
+  if (!frame.hasPositiveArea() || frame.x % dsc.X_S_F != 0 || frame.y % dsc.Y_S_F != 0)
+    ThrowRDE("Unexpected LJpeg frame dimension multiplicity");
+  frame.x /= dsc.X_S_F;
+  frame.y /= dsc.Y_S_F;
+  if (mRaw->dim.x > 19440 || mRaw->dim.y > 5920)
+    ThrowRDE("Unexpected image dimensions found: (%d; %d)", mRaw->dim.x, mRaw->dim.y);
+  for (int s = 0; s < slicing.numSlices; s++)
+    if (slicing.widthOfSlice(s) <= 0)
+      ThrowRDE("Bad slice width: %i", slicing.widthOfSlice(s));
+  if (dsc.subSampled == mRaw->isCFA)
+    ThrowRDE("Cannot decode subsampled image to CFA data or vice versa");
+  if ((int)rec.size() != dsc.N_COMP)
+    ThrowRDE("HT/Initial predictor count does not match component count");
+  for (const auto& r : rec)
+    if (!r.ht.isFullDecode())
+      ThrowRDE("Huffman table is not of a full decoding variety");
+  for (int* width : {&slicing.sliceWidth, &slicing.lastSliceWidth}) {
+    if (*width % dsc.sliceColStep != 0)
+      ThrowRDE("Slice width (%d) should be multiple of pixel group size (%d)", *width,
+               dsc.sliceColStep);
+    *width /= dsc.sliceColStep;
+  }
+  if (frame.area() < dim.area())
+    ThrowRDE("Frame area smaller than the image area");
+  // Walk the output tiles of the slices in stream order (slices are frame.y tall
+  // and wrap into the next image column when they hit the bottom) and validate
+  // the tiling like the reference's ctor does (Cr2DecompressorImpl.h:336-362).
+  int sliceId = 0, sliceRow = 0, px = 0, py = 0;
+  bool haveLast = false;
+  Rect last{0, 0, 0, 0};
+  while (sliceId < slicing.numSlices) {
+    const int wS = slicing.widthOfSlice(sliceId);
+    const Rect t{px, py, wS, std::min(dim.y - py, frame.y - sliceRow)};
+    if (haveLast) {
+      const bool continues = last.x == t.x && last.y + last.h == t.y && last.w == t.w;
+      const bool newColumn = t.y == 0 && t.x == last.x + last.w;
+      if (!continues && !newColumn)
+        ThrowRDE("Invalid tiling - slice width change mid-output row?");
+    }
+    if (t.x + t.w <= dim.x && t.y + t.h <= dim.y) {
+      last = t;
+      haveLast = true;
+    } else {
+      if (t.x < dim.x && t.y < dim.y)
+        ThrowRDE("Output tile partially outside of image");
+      break;
+    }
+    sliceRow += t.h;
+    py += t.h;
+    if (sliceRow == frame.y) {
+      ++sliceId;
+      sliceRow = 0;
+    }
+    if (py == dim.y) {
+      py = 0;
+      px += t.w;
+    }
+  }
+  if (!haveLast)
+    ThrowRDE("No tiles are provided");
+  if (last.x + last.w != dim.x || last.y + last.h != dim.y)
+    ThrowRDE("Tiles do not cover the entire image area.");
+}
+
+template <typename HT> uint32_t Cr2Decompressor<HT>::decompress() const {
+  if (input.getSize() < 8) // BitStreamerJPEG ctor
+    ThrowIOE("Bit stream size is smaller than MaxProcessBytes");
+  std::vector<rsb200_huff_table> tables;
+  rsb200_cr2_job j;
+  std::memset(&j, 0, sizeof j);
+  j.in_offset = 0;
+  j.in_size = input.getSize();
+  j.n_comp = (uint8_t)std::get<0>(format);
+  j.x_s_f = (uint8_t)std::get<1>(format);
+  j.y_s_f = (uint8_t)std::get<2>(format);
+  for (size_t c = 0; c < rec.size(); ++c) {
+    j.table[c] = tableIndex(tables, rec[c].ht.deviceTable());
+    j.init_pred[c] = rec[c].initPred;
+  }
+  j.frame_w = rawFrame.x;
+  j.frame_h = rawFrame.y;
+  j.num_slices = rawSlicing.numSlices;
+  j.slice_w = rawSlicing.sliceWidth;
+  j.last_slice_w = rawSlicing.lastSliceWidth;
+  j.img_w = mRaw->dim.x;
+  j.img_h = mRaw->dim.y;
+  j.out_offset = 0;
+  j.out_pitch = (uint32_t)mRaw->pitch;
+  PlanGuard pg;
+  engineCheck(rsb200_cr2_plan_create(engine(), tables.data(), (int)tables.size(), &j, 1, &pg.p),
+              "rsb200_cr2_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, input.begin(), input.getSize(), img, /*partial=*/false);
+  rsb200_scan_result res{};
+  (void)rsb200_plan_results(pg.p, &res, 1);
+  if (res.status == RSB200_ERR_RDE)
+    ThrowRDE("bad Huffman code");
+  if (res.status == RSB200_ERR_IOE)
+    ThrowIOE("Buffer overflow read in BitStreamer");
+  if (res.status != RSB200_OK)
+    ThrowRDE("device error %u", res.status);
+  return res.consumed;
+}
+
+template class Cr2Decompressor<PrefixCodeDecoder<>>;
+
+Cr2LJpegDecoder::Cr2LJpegDecoder(ByteStream bs, const RawImage& img)
+    : AbstractLJpegDecoder(bs, img) {
+  if (mRaw->getCpp() != 1 || mRaw->getBpp() != 2)
+    ThrowRDE("Unexpected cpp: %u", mRaw->getCpp());
+  if (!mRaw->dim.x || !mRaw->dim.y || mRaw->dim.x > 19440 || mRaw->dim.y > 5920)
+    ThrowRDE("Unexpected image dimensions found: (%d; %d)", mRaw->dim.x, mRaw->dim.y);
+}
+
+void Cr2LJpegDecoder::prepareScan() {
+  if (numMCUsPerRestartInterval != 0)
+    ThrowRDE("Non-zero restart interval not supported.");
+  if (predictorMode != 1)
+    ThrowRDE("Unsupported predictor mode.");
+  if (slicing.empty()) {
+    const int slicesWidth = (int)(frame.w * frame.cps);
+    if (slicesWidth > mRaw->dim.x)
+      ThrowRDE("Don't know slicing pattern, and failed to guess it.");
+    slicing = Cr2SliceWidths(1, 0, (uint16_t)slicesWidth);
+  }
+  bool isSubSampled = false;
+  for (uint32_t i = 0; i < frame.cps; i++)
+    isSubSampled = isSubSampled || frame.compInfo[i].superH != 1 || frame.compInfo[i].superV != 1;
+  if (frame.cps != 3 && frame.w * frame.cps > 2 * frame.h)
+    frame.h *= 2; // Canon doubled the width and halved the height (e.g. 5Ds)
+  std::tuple<int, int, int> format;
+  if (isSubSampled) {
+    if (mRaw->isCFA)
+      ThrowRDE("Cannot decode subsampled image to CFA data");
+    if (frame.cps != 3)
+      ThrowRDE("Unsupported number of subsampled components: %u", frame.cps);
+    bool ok = frame.compInfo[0].superH == 2 &&
+              (frame.compInfo[0].superV == 1 || frame.compInfo[0].superV == 2);
+    for (uint32_t i = 1; i < frame.cps; i++)
+      ok = ok && frame.compInfo[i].superH == 1 && frame.compInfo[i].superV == 1;
+    if (!ok)
+      ThrowRDE("Unsupported subsampling ([[%u, %u], [%u, %u], [%u, %u]])",
+               frame.compInfo[0].superH, frame.compInfo[0].superV, frame.compInfo[1].superH,
+               frame.compInfo[1].superV, frame.compInfo[2].superH, frame.compInfo[2].superV);
+    if (frame.compInfo[0].superV == 2)
+      format = {3, 2, 2};
+    else {
+      slicing.sliceWidth = slicing.sliceWidth * 3 / 2; // sRaw slice-width quirk
+      slicing.lastSliceWidth = slicing.lastSliceWidth * 3 / 2;
+      format = {3, 2, 1};
+    }
+  } else {
+    if (frame.cps == 2)
+      format = {2, 1, 1};
+    else if (frame.cps == 4)
+      format = {4, 1, 1};
+    else
+      ThrowRDE("Unsupported number of components: %u", frame.cps);
+  }
+  const int N_COMP = std::get<0>(format);
+  const auto hts = getPrefixCodeDecoders(N_COMP);
+  const auto initPred = getInitialPredictors(N_COMP);
+  std::vector<Cr2Decompressor<>::PerComponentRecipe> rec;
+  for (int i = 0; i < N_COMP; ++i)
+    rec.push_back({*hts[(size_t)i], initPred[(size_t)i]});
+  d = std::make_unique<Cr2Decompressor<>>(mRaw, format, iPoint2D((int)frame.w, (int)frame.h),
+                                          slicing, rec, input.peekRemainingBuffer());
+}
+
+uint32_t Cr2LJpegDecoder::runScan() { return d->decompress(); }
+
+void Cr2LJpegDecoder::decode(const Cr2SliceWidths& slicing_) {
+  slicing = slicing_;
+  for (int s = 0; s < slicing.numSlices; s++)
+    if (slicing.widthOfSlice(s) <= 0)
+      ThrowRDE("Bad slice width: %i", slicing.widthOfSlice(s));
+  decodeSOI();
+}
+
+// ------------------------------------------------------------------ DNG
+namespace {
+// the byte span of the file covered by the tiles (they all view one file buffer)
+void tileSpan(const std::vector<DngSliceElement>& slices, const uint8_t** base, size_t* len) {
+  const uint8_t* lo = nullptr;
+  const uint8_t* hi = nullptr;
+  for (const auto& e : slices) {
+    const uint8_t* b = e.bs.begin();
+    const uint8_t* en = b + e.bs.getSize();
+    if (!lo || b < lo)
+      lo = b;
+    if (!hi || en > hi)
+      hi = en;
+  }
+  *base = lo;
+  *len = (size_t)(hi - lo);
+}
+} // namespace
+
+void AbstractDngDecompressor::decompressUncompressed() const {
+  const uint8_t* base;
+  size_t span;
+  tileSpan(slices, &base, &span);
+  std::vector<rsb200_unpack_job> jobs;
+  for (const auto& e : slices) {
+    try {
+      bool big_endian = e.bs.getByteOrder() == Endianness::big;
+      if (mBps != 8 && mBps != 16 && mBps != 32)
+        big_endian = true; // DNG: not 8/16/32 bit => always big endian
+      const uint32_t inputPixelBits = mRaw->getCpp() * mBps;
+      if (e.dsc.tileW > (uint32_t)std::numeric_limits<int>::max() / inputPixelBits)
+        ThrowIOE("Integer overflow when calculating input pitch");
+      const int inputPitchBits = (int)(inputPixelBits * e.dsc.tileW);
+      if (inputPitchBits % 8 != 0)
+        ThrowRDE("Bad combination of cpp (%u), bps (%u) and width (%u), the pitch is %d bits, "
+                 "which is not a multiple of 8 (1 byte)",
+                 mRaw->getCpp(), mBps, e.width, inputPitchBits);
+      const int inputPitch = inputPitchBits / 8;
+      if (inputPitch == 0)
+        ThrowRDE("Data input pitch is too short. Can not decode!");
+      UncompressedDecompressor u(e.bs, mRaw,
+                                 iRectangle2D((int)e.offX, (int)e.offY, (int)e.width,
+                                              (int)e.height),
+                                 inputPitch, (int)mBps, big_endian ? BitOrder::MSB : BitOrder::LSB);
+      rsb200_unpack_job job;
+      if (u.describe(base, &job))
+        jobs.push_back(job);
+    } catch (const RawDecoderException& err) {
+      mRaw->setError(err.what());
+    } catch (const IOException& err) {
+      mRaw->setError(err.what());
+    }
+  }
+  if (jobs.empty())
+    return;
+  PlanGuard pg;
+  engineCheck(rsb200_unpack_plan_create(engine(), jobs.data(), (int)jobs.size(), &pg.p),
+              "rsb200_unpack_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, base, span, img, /*partial=*/true);
+}
+
+void AbstractDngDecompressor::decompressLJpeg() const {
+  const uint8_t* base;
+  size_t span;
+  tileSpan(slices, &base, &span);
+  struct Tile {
+    std::unique_ptr<LJpegDecoder> dec;
+    int firstScan = 0, nScans = 0;
+  };
+  std::vector<Tile> tiles;
+  std::vector<rsb200_huff_table> tables;
+  std::vector<rsb200_ljpeg_scan> scans;
+  for (const auto& e : slices) {
+    try {
+      auto dec = std::make_unique<LJpegDecoder>(e.bs, mRaw);
+      if (!dec->prepare(e.offX, e.offY, e.width, e.height,
+                        iPoint2D((int)e.dsc.tileW, (int)e.dsc.tileH), mFixLjpeg))
+        continue;
+      const size_t before = scans.size();
+      try {
+        dec->scan()->describe(base, tables, scans);
+      } catch (...) {
+        scans.resize(before);
+        throw;
+      }
+      Tile t;
+      t.firstScan = (int)before;
+      t.nScans = (int)(scans.size() - before);
+      t.dec = std::move(dec);
+      tiles.push_back(std::move(t));
+    } catch (const RawDecoderException& err) {
+      mRaw->setError(err.what());
+    } catch (const IOException& err) {
+      mRaw->setError(err.what());
+    }
+  }
+  if (scans.empty())
+    return;
+  PlanGuard pg;
+  engineCheck(rsb200_ljpeg_plan_create(engine(), tables.data(), (int)tables.size(), scans.data(),
+                                       (int)scans.size(), &pg.p),
+              "rsb200_ljpeg_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, base, span, img, /*partial=*/true);
+  std::vector<rsb200_scan_result> res(scans.size());
+  (void)rsb200_plan_results(pg.p, res.data(), (int)res.size());
+  for (auto& t : tiles) {
+    try {
+      const uint32_t consumed = t.dec->scan()->finish(res.data() + t.firstScan, t.nScans);
+      t.dec->decodeSOIAfterScan(consumed);
+    } catch (const RawDecoderException& err) {
+      mRaw->setError(err.what());
+    } catch (const IOException& err) {
+      mRaw->setError(err.what());
+    }
+  }
+}
+
+void AbstractDngDecompressor::decompress() const {
+  if (compression == 1)
+    decompressUncompressed();
+  else if (compression == 7)
+    decompressLJpeg();
+  else if (compression == 8)
+    mRaw->setError("deflate support is disabled.");
+  else if (compression == 9)
+    mRaw->setError("VC-5 is not on the accelerated path.");
+  else if (compression == 0x884c)
+    mRaw->setError("jpeg support is disabled.");
+  else
+    mRaw->setError("AbstractDngDecompressor: Unknown compression");
+  std::string firstErr;
+  if (mRaw->isTooManyErrors(1, &firstErr))
+    ThrowRDE("Too many errors encountered. Giving up. First Error:\n%s", firstErr.c_str());
+}
+
+} // namespace rawspeed_b200

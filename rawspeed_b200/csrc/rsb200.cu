@@ -784,6 +784,33 @@ extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in
   return RSB200_OK;
 }
 
+extern "C" int rsb200_plan_run_host_image(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
+                                          uint8_t* out, uint32_t pitch, uint32_t row_bytes,
+                                          uint32_t rows, int partial) {
+  if (!p || !in || !out || row_bytes > pitch)
+    return RSB200_ERR_ARG;
+  rsb200_ctx* ctx = p->ctx;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t out_bytes = (size_t)pitch * rows;
+  int rc = ensure_cap(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes + 16);
+  if (rc)
+    return rc;
+  rc = ensure_cap(ctx, &ctx->d_out, &ctx->d_out_cap, out_bytes);
+  if (rc)
+    return rc;
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (partial)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_out, out, out_bytes, cudaMemcpyHostToDevice, st));
+  rc = rsb200_plan_run(p, ctx->d_in, in_bytes, ctx->d_out, out_bytes, (void*)st);
+  if (rc)
+    return rc;
+  CUDA_TRY(ctx, cudaMemcpy2DAsync(out, pitch, ctx->d_out, pitch, row_bytes, rows,
+                                  cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return RSB200_OK;
+}
+
 extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, int n) {
   if (!p)
     return RSB200_ERR_ARG;

@@ -1,0 +1,137 @@
+"""ctypes face of librawspeed_b200_host.so -- the C++ mirror of the reference's
+decompressor classes (csrc/host/).  Same call shapes as the reference's fuzz
+drivers; exceptions come back as RawDecoderException / IOException."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .api import RawDecoderException, IOException, Rsb200Error
+
+
+class _Err(C.Structure):
+    _fields_ = [("code", C.c_int), ("msg", C.c_char * 240)]
+
+    def check(self, rc):
+        if rc == 0:
+            return
+        msg = self.msg.decode("utf-8", "replace")
+        if rc == 2:
+            raise IOException(2, msg)
+        raise RawDecoderException(1, msg)
+
+
+class _Huff(C.Structure):
+    _fields_ = [("ncpl", C.c_uint8 * 16), ("values", C.c_uint8 * 162), ("nvalues", C.c_int)]
+
+
+EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
+           "rsb200h_dng_decompress", "rsb200h_cr2_decompress", "rsb200h_cr2_ljpeg_decode",
+           "rsb200h_huff_check"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_build.HOST_LIB):
+            _build.build()
+        _lib = C.CDLL(_build.HOST_LIB)
+    return _lib
+
+
+def _u8(data):
+    if isinstance(data, np.ndarray):
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        return data.ctypes.data_as(C.c_char_p), data.size
+    b = bytes(data)
+    return b, len(b)
+
+
+def _tabs(tabs):
+    arr = (_Huff * len(tabs))()
+    for i, (ncpl, values) in enumerate(tabs):
+        for k in range(16):
+            arr[i].ncpl[k] = ncpl[k]
+        for k, v in enumerate(values):
+            arr[i].values[k] = v
+        arr[i].nvalues = len(values)
+    return arr
+
+
+def huff_check(ncpl, values, full=True, fix16=False):
+    e = _Err()
+    e.check(lib().rsb200h_huff_check(bytes(ncpl), bytes(values), len(values), int(full),
+                                     int(fix16), C.byref(e)))
+
+
+def unpack(data, img, w, cpp, crop, in_pitch, bps, order):
+    p, n = _u8(data)
+    e = _Err()
+    e.check(lib().rsb200h_unpack(p, C.c_uint32(n), C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                 cpp, img.shape[1] * 2, crop[0], crop[1], crop[2], crop[3],
+                                 in_pitch, bps, order, C.byref(e)))
+    return img
+
+
+def ljpeg_decompress(img, w, cpp, img_frame, mcu, frame_dim, tabs, tab_of_comp, init_pred,
+                     rows_per_restart, data, fix16=False):
+    p, n = _u8(data)
+    toc = (C.c_int * len(tab_of_comp))(*tab_of_comp)
+    ip = (C.c_uint16 * len(init_pred))(*init_pred)
+    consumed = C.c_uint32(0)
+    e = _Err()
+    e.check(lib().rsb200h_ljpeg_decompress(
+        C.c_void_p(img.ctypes.data), w, img.shape[0], cpp, img.shape[1] * 2, img_frame[0],
+        img_frame[1], img_frame[2], img_frame[3], mcu[0], mcu[1], frame_dim[0], frame_dim[1],
+        _tabs(tabs), toc, ip, len(tab_of_comp), int(fix16), rows_per_restart, p, C.c_uint32(n),
+        C.byref(consumed), C.byref(e)))
+    return consumed.value
+
+
+def ljpeg_decode(blob, img, w, cpp, off, size, max_dim, fix16=False):
+    p, n = _u8(blob)
+    e = _Err()
+    e.check(lib().rsb200h_ljpeg_decode(p, C.c_uint32(n), C.c_void_p(img.ctypes.data), w,
+                                       img.shape[0], cpp, img.shape[1] * 2, off[0], off[1],
+                                       size[0], size[1], max_dim[0], max_dim[1], int(fix16),
+                                       C.byref(e)))
+    return img
+
+
+def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h, compression,
+                   fix_ljpeg=False, bps=14, big_endian=False):
+    p, n = _u8(file_bytes)
+    offs = (C.c_uint64 * len(tile_off))(*tile_off)
+    lens = (C.c_uint32 * len(tile_len))(*tile_len)
+    e = _Err()
+    e.check(lib().rsb200h_dng_decompress(p, C.c_uint64(n), offs, lens, len(tile_off),
+                                         C.c_void_p(img.ctypes.data), w, img.shape[0], cpp,
+                                         img.shape[1] * 2, tile_w, tile_h, compression,
+                                         int(fix_ljpeg), bps, int(big_endian), C.byref(e)))
+    return img
+
+
+def cr2_decompress(img, w, fmt, frame, slicing, tabs, tab_of_comp, init_pred, data, is_cfa=True):
+    p, n = _u8(data)
+    toc = (C.c_int * len(tab_of_comp))(*tab_of_comp)
+    ip = (C.c_uint16 * len(init_pred))(*init_pred)
+    consumed = C.c_uint32(0)
+    e = _Err()
+    e.check(lib().rsb200h_cr2_decompress(
+        C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2, int(is_cfa), fmt[0],
+        fmt[1], fmt[2], frame[0], frame[1], slicing[0], slicing[1], slicing[2], _tabs(tabs), toc,
+        ip, len(tab_of_comp), p, C.c_uint32(n), C.byref(consumed), C.byref(e)))
+    return consumed.value
+
+
+def cr2_ljpeg_decode(blob, img, w, slicing, is_cfa=True, sub=(1, 1)):
+    p, n = _u8(blob)
+    e = _Err()
+    e.check(lib().rsb200h_cr2_ljpeg_decode(p, C.c_uint32(n), C.c_void_p(img.ctypes.data), w,
+                                           img.shape[0], img.shape[1] * 2, int(is_cfa), sub[0],
+                                           sub[1], slicing[0], slicing[1], slicing[2],
+                                           C.byref(e)))
+    return img

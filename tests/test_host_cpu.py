@@ -1,0 +1,87 @@
+"""Host-layer logic that needs no GPU: the C++ mirror validates inputs exactly
+like the reference (same exception class) before anything reaches the device."""
+import numpy as np
+import pytest
+
+from oracle import port, synth
+from rawspeed_b200 import host
+import rawspeed_b200 as rs
+
+
+def test_host_library_exports():
+    L = host.lib()
+    for n in host.EXPORTS:
+        assert hasattr(L, n), n
+
+
+def test_huffman_validation_matches_oracle():
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        ncpl = [0] * 16
+        for _ in range(int(rng.integers(1, 6))):
+            ncpl[int(rng.integers(0, 16))] += int(rng.integers(1, 4))
+        values = [int(v) for v in rng.integers(0, 18, sum(ncpl))]
+        ok_a = ok_b = True
+        try:
+            port.Huff(ncpl, values)
+        except port.OracleError:
+            ok_a = False
+        try:
+            host.huff_check(ncpl, values)
+        except rs.Rsb200Error:
+            ok_b = False
+        assert ok_a == ok_b, (ncpl, values)
+
+
+def _same_class(fn_oracle, fn_host):
+    with pytest.raises(port.OracleError) as eo:
+        fn_oracle()
+    with pytest.raises(rs.Rsb200Error) as eh:
+        fn_host()
+    want = rs.IOException if isinstance(eo.value, port.IOException) else rs.RawDecoderException
+    assert type(eh.value) is want, (eo.value, eh.value)
+
+
+def test_unpack_ctor_errors_same_class():
+    w, h, bps = 16, 4, 12
+    data = synth.lcg_bytes(24 * 4, 1)
+    cases = [dict(crop=(0, 0, w, h), pitch=23), dict(crop=(0, 0, w, 5), pitch=24),
+             dict(crop=(1, 0, w, h), pitch=24), dict(crop=(0, 9, w, h), pitch=24),
+             dict(crop=(0, 0, 15, h), pitch=24, bps=13), dict(crop=(0, 0, 0, h), pitch=24),
+             dict(crop=(0, 0, w, h), pitch=24, bps=17), dict(crop=(0, 0, w, h), pitch=24, order=4)]
+    for c in cases:
+        b, o = c.get("bps", bps), c.get("order", port.MSB)
+        _same_class(lambda: port.unpack(data, port.new_image(w, h), w, 1, c["crop"], c["pitch"], b, o),
+                    lambda: host.unpack(data, port.new_image(w, h), w, 1, c["crop"], c["pitch"], b, o))
+
+
+def test_ljpeg_header_errors_same_class():
+    img = synth.image_model(64, 32, 3)
+    good = port.ljpeg_encode(img, 32, 32, (2, 1), 14, synth.default_tables(1), [0, 0])
+    bad = []
+    b = good.copy(); b[1] = 0xD9; bad.append(b)                      # no SOI
+    b = good.copy(); b[3] = 0xC0; bad.append(b)                      # SOF0 instead of SOF3 -> no SOF
+    b = good.copy(); b[6] = 1; bad.append(b)                         # precision 1
+    b = good.copy(); b[6] = 17; bad.append(b)                        # precision 17
+    b = good.copy(); b[11] = 5; bad.append(b)                        # 5 components
+    bad.append(good[:20].copy())                                      # truncated header
+    b = good.copy(); b[9:11] = [0, 16]; bad.append(b)                # frame width mismatch
+    for i, blob in enumerate(bad):
+        _same_class(lambda: port.ljpeg_decode(blob, port.new_image(64, 32), 64, 1, (0, 0), (64, 32), (64, 32)),
+                    lambda: host.ljpeg_decode(blob, port.new_image(64, 32), 64, 1, (0, 0), (64, 32), (64, 32)))
+    # tile geometry errors are raised before the stream is looked at
+    for off, size, mx in [((64, 0), (64, 32), (64, 32)), ((0, 0), (65, 32), (64, 32)),
+                          ((0, 0), (64, 32), (32, 32)), ((0, 8), (64, 32), (64, 32))]:
+        _same_class(lambda: port.ljpeg_decode(good, port.new_image(64, 32), 64, 1, off, size, mx),
+                    lambda: host.ljpeg_decode(good, port.new_image(64, 32), 64, 1, off, size, mx))
+
+
+def test_cr2_ctor_errors_same_class():
+    w, h = 64, 40
+    img = port.new_image(w, h)
+    img[:, :w] = synth.image_model(w, h, 31)
+    hts = synth.default_tables(2)
+    blob = port.cr2_encode(img, w, (2, 1, 1), (32, 40), (2, 32, 32), 14, hts, [0, 1])
+    for slicing in [(2, 31, 33), (2, 32, 16), (2, 32, 48), (1, 0, 62)]:
+        _same_class(lambda: port.cr2_ljpeg_decode(blob, port.new_image(w, h), w, slicing),
+                    lambda: host.cr2_ljpeg_decode(blob, port.new_image(w, h), w, slicing))
