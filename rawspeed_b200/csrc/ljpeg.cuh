@@ -372,12 +372,20 @@ __global__ void __launch_bounds__(K2_THREADS)
     k2_entropy_kernel(const uint8_t* __restrict__ in, uint64_t in_total,
                       const DevScan* __restrict__ scans,
                       const DevTable* __restrict__ tables,
-                      uint16_t* __restrict__ diffs, DevResult* __restrict__ results) {
+                      uint16_t* __restrict__ diffs, DevResult* __restrict__ results_all,
+                      const uint32_t* __restrict__ scan_ids,
+                      const uint32_t* __restrict__ enable) {
   extern __shared__ __align__(16) uint8_t k2_smem_raw[];
   K2Shared& sh = *reinterpret_cast<K2Shared*>(k2_smem_raw);
   const int tid = threadIdx.x;
+  // exact single-CTA decoder; in a plan it only runs for segments whose
+  // speculative multi-CTA parse failed verification (enable[] != 0)
+  if (enable && !enable[blockIdx.x])
+    return;
+  const uint32_t scan_idx = scan_ids ? scan_ids[blockIdx.x] : blockIdx.x;
+  DevResult* results = results_all + scan_idx - blockIdx.x; // so that results[blockIdx.x] is ours
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[blockIdx.x]);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[scan_idx]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.sc);
     for (int i = tid; i < (int)(sizeof(DevScan) / 4); i += K2_THREADS)
       dst[i] = src[i];
@@ -601,7 +609,8 @@ __global__ void __launch_bounds__(K2_THREADS)
 // (LJpegDecompressor.cpp:326-332 / Cr2DecompressorImpl.h:437-451), mod 2^16.
 // One warp per (segment, component).
 // ------------------------------------------------------------------
-__global__ void k3_column_kernel(const DevScan* __restrict__ scans, int nscans,
+__global__ void k3_column_kernel(const DevScan* __restrict__ scans,
+                                 const uint32_t* __restrict__ scan_ids, int nscans,
                                  const uint16_t* __restrict__ diffs,
                                  uint16_t* __restrict__ colvals) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -609,7 +618,7 @@ __global__ void k3_column_kernel(const DevScan* __restrict__ scans, int nscans,
   const int si = warp >> 2, c = warp & 3;
   if (si >= nscans)
     return;
-  const DevScan& sc = scans[si];
+  const DevScan& sc = scans[scan_ids ? scan_ids[si] : (uint32_t)si];
   if (c >= sc.ncomp)
     return;
   const uint16_t* d = diffs + sc.diff_offset + sc.first_idx[c];

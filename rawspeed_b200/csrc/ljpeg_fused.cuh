@@ -377,50 +377,43 @@ __device__ __forceinline__ void f_row_col(uint32_t g, uint32_t RS, uint32_t inv,
   s = (uint32_t)d;
 }
 
-template <bool MULTI>
-__device__ __forceinline__ void
-fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
-           const DevTable* __restrict__ tables, uint8_t* __restrict__ out,
-           DevResult* __restrict__ results) {
+// per-CTA description of the byte range being decoded + TMA pipeline state
+struct FStream {
+  const uint8_t* gbase; // 16-byte aligned base of the segment window
+  uint32_t limit;       // valid raw bytes from gbase (this CTA never looks further)
+  uint32_t skew;        // offset of the first entropy-coded byte from gbase
+  uint64_t readable;    // bytes that may be touched by the bulk copies
+  uint32_t chunk_begin; // first chunk this CTA processes
+  uint32_t chunk_end;   // one past the last chunk that may be prefetched
+  bool pending;         // a bulk copy is in flight (uniform)
+  uint32_t pending_par; // ... and completes the mbarrier phase of this parity
+};
+
+struct FChunk {
+  uint32_t len;        // clean bytes in ub (carried tail + this chunk)
+  uint32_t Lc;         // clean bytes decodable in this chunk
+  uint32_t end_all;    // Lc * 8
+  uint32_t mpos;       // chunk-relative raw offset of the end marker (or ~0)
+  uint32_t total_emit; // clean bytes produced by this chunk
+  bool final_chunk;
+};
+
+__device__ __forceinline__ void f_issue_chunk(FusedShared& sh, const FStream& st, uint32_t chunk) {
+  // window [chunk*F_RAW, +F_WIN) clamped to the readable (16-byte padded) buffer
+  const uint64_t g0 = (uint64_t)chunk * F_RAW;
+  uint32_t n = 0;
+  if (g0 < st.readable)
+    n = (uint32_t)min((uint64_t)F_WIN, st.readable - g0);
+  mbar_expect_tx(&sh.bar, n);
+  if (n)
+    bulk_g2s(sh.raw, st.gbase + g0, n, &sh.bar);
+}
+
+// ================= B: unstuff one raw chunk into sh.ub =================
+__device__ __forceinline__ FChunk f_unstuff(FusedShared& sh, FStream& st, const FusedCarry& cy,
+                                            uint32_t chunk) {
   const int tid = threadIdx.x;
-  const DevScan& sc = sh.sc;
-  const uint64_t abase = sc.in_offset & ~15ull;
-  const uint32_t skew = (uint32_t)(sc.in_offset - abase);
-  const uint8_t* gbase = in + abase;
-  const uint32_t limit = skew + sc.in_size; // valid raw bytes from gbase
-  const uint64_t readable = ((in_total + 15) & ~15ull) - abase;
-  const uint32_t G = sc.group;
-  const uint32_t RS = sc.row_samples;
-  const uint32_t nchunks_max = (limit + F_RAW - 1) / F_RAW;
-
-  auto issue_chunk = [&](uint32_t chunk) {
-    // window [chunk*F_RAW, +F_WIN) clamped to the readable (16-byte padded) buffer
-    const uint64_t g0 = (uint64_t)chunk * F_RAW;
-    uint32_t n = 0;
-    if (g0 < readable)
-      n = (uint32_t)min((uint64_t)F_WIN, readable - g0);
-    mbar_expect_tx(&sh.bar, n);
-    if (n)
-      bulk_g2s(sh.raw, gbase + g0, n, &sh.bar);
-  };
-  if (tid == 0)
-    issue_chunk(0);
-  bool pending = true; // a bulk copy has been issued and not yet waited for (uniform)
-  uint32_t pending_par = 0;
-  uint32_t my_status = 0;
-
-  for (uint32_t chunk = 0;; ++chunk) {
-    const FusedCarry cy = sh.cy;
-    if (cy.sym >= sc.n_samples)
-      break;
-    if (cy.ended) {
-      my_status |= 2u; // data exhausted but samples are still missing
-      break;
-    }
-    mbar_wait(&sh.bar, chunk & 1);
-    pending = false;
-
-    // ================= B: unstuff =================
+  FChunk co;
     const uint32_t* rw = sh.raw;
     const uint32_t raw0 = chunk * F_RAW + tid * F_SUB; // raw offset of my first byte
     uint32_t w[8];
@@ -431,30 +424,30 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
       w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
       w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
     }
-    if (raw0 + 32 > limit) {
+    if (raw0 + 32 > st.limit) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const uint32_t b = raw0 + 4 * k;
-        if (b + 4 > limit)
-          w[k] = b >= limit ? 0u : (w[k] & (0xFFFFFFFFu >> (32 - 8 * (limit - b))));
+        if (b + 4 > st.limit)
+          w[k] = b >= st.limit ? 0u : (w[k] & (0xFFFFFFFFu >> (32 - 8 * (st.limit - b))));
       }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (__vcmpeq4(w[k], 0xFFFFFFFFu))
         ffm |= byte_eq_mask(w[k], 0xFFFFFFFFu) << (4 * k);
-    // bytes that belong to the segment: [skew, limit)
+    // bytes that belong to the segment: [st.skew, st.limit)
     uint32_t valid = 0xFFFFFFFFu;
-    if (raw0 < skew)
-      valid = (skew - raw0 >= 32) ? 0u : (0xFFFFFFFFu << (skew - raw0));
-    if (raw0 + 32 > limit)
-      valid &= (raw0 >= limit) ? 0u : (0xFFFFFFFFu >> (32 - (limit - raw0)));
+    if (raw0 < st.skew)
+      valid = (st.skew - raw0 >= 32) ? 0u : (0xFFFFFFFFu << (st.skew - raw0));
+    if (raw0 + 32 > st.limit)
+      valid &= (raw0 >= st.limit) ? 0u : (0xFFFFFFFFu >> (32 - (st.limit - raw0)));
     ffm &= valid;
     uint32_t prev_ff;
     if (tid == 0)
       prev_ff = cy.prev_ff;
     else
-      prev_ff = ((rw[tid * 8 - 1] >> 24) == 0xFFu) && (raw0 - 1 >= skew) && (raw0 - 1 < limit);
+      prev_ff = ((rw[tid * 8 - 1] >> 24) == 0xFFu) && (raw0 - 1 >= st.skew) && (raw0 - 1 < st.limit);
     uint32_t stuff = 0, mk = 0;
     if (ffm | prev_ff) {
       uint32_t zm = 0;
@@ -462,7 +455,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
       for (int k = 0; k < 8; ++k)
         zm |= byte_eq_mask(w[k], 0u) << (4 * k);
       uint32_t nb = rw[tid * 8 + 8] & 0xFFu; // first byte after my range
-      if (raw0 + 32 >= limit)
+      if (raw0 + 32 >= st.limit)
         nb = 0; // past the end bytes read as zero -> FF is followed by "00"
       stuff = zm & ((ffm << 1) | prev_ff) & valid;
       mk = ffm & ~((zm >> 1) | ((nb == 0u ? 1u : 0u) << 31));
@@ -491,12 +484,12 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
     const uint32_t incl = f_block_scan(n_emit, sh.warp_tmp[0], &total_emit);
     // (the scan's barrier also means every thread has read its raw words: the
     //  staging buffer is free -> prefetch the next chunk now, overlapping C-E)
-    const bool final_chunk = (mpos != 0xFFFFFFFFu) || ((chunk + 1) * (uint32_t)F_RAW >= limit);
-    if (!final_chunk && chunk + 1 < nchunks_max) {
+    const bool final_chunk = (mpos != 0xFFFFFFFFu) || ((chunk + 1) * (uint32_t)F_RAW >= st.limit);
+    if (!final_chunk && chunk + 1 < st.chunk_end) {
       if (tid == 0)
-        issue_chunk(chunk + 1);
-      pending = true;
-      pending_par = (chunk + 1) & 1u;
+        f_issue_chunk(sh, st, chunk + 1);
+      st.pending = true;
+      st.pending_par = (chunk + 1 - st.chunk_begin) & 1u;
     }
     const uint32_t dst0 = cy.tail_len + incl - n_emit; // clean byte index in ub
     sh.anchor[tid] = dst0;
@@ -546,7 +539,8 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
         }
       }
     }
-    const uint32_t len = cy.tail_len + total_emit; // clean bytes now in ub
+    co.len = cy.tail_len + total_emit; // clean bytes now in ub
+    const uint32_t len = co.len;
     __syncthreads();
     // zero padding behind the data (read by look-ahead loads / after the end)
     if (tid < 16)
@@ -556,14 +550,29 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
       if (wz < (F_RAW + 64) / 4)
         sh.ub[wz] = 0;
     }
-    const uint32_t Lc = final_chunk ? len : (len > F_LA ? len - F_LA : 0u); // decodable bytes
-    const uint32_t end_all = Lc * 8;
+    co.Lc = final_chunk ? len : (len > F_LA ? len - F_LA : 0u); // decodable bytes
+    co.end_all = co.Lc * 8;
+    co.mpos = mpos;
+    co.total_emit = total_emit;
+    co.final_chunk = final_chunk;
     __syncthreads();
+    return co;
 
-    // ================= C: self-synchronising decode =================
+}
+
+struct FSync {
+  uint32_t my_start, my_phase;
+  FSub d;
+};
+
+// ================= C: self-synchronising decode of the chunk in sh.ub =================
+template <bool MULTI>
+__device__ __forceinline__ FSync f_sync(FusedShared& sh, const FusedCarry& cy, const FChunk& co,
+                                        uint32_t G) {
+  const int tid = threadIdx.x;
     const uint32_t sub_lo = tid * F_SUB * 8u;
-    const uint32_t sub_hi = min(sub_lo + F_SUB * 8u, end_all);
-    const bool active = sub_lo < end_all;
+    const uint32_t sub_hi = min(sub_lo + F_SUB * 8u, co.end_all);
+    const bool active = sub_lo < co.end_all;
     uint32_t my_start = (tid == 0) ? cy.pos : sub_lo;
     uint32_t my_phase = (tid == 0) ? (cy.sym % G) : 0u;
     if (!active)
@@ -609,6 +618,64 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
         sh.exitph[tid] = (my_phase + d.count) % G;
       __syncthreads();
     }
+
+    FSync so;
+    so.my_start = my_start;
+    so.my_phase = my_phase;
+    so.d = d;
+    return so;
+}
+
+template <bool MULTI>
+__device__ __forceinline__ void
+fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
+           const DevTable* __restrict__ tables, uint8_t* __restrict__ out,
+           DevResult* __restrict__ results) {
+  const int tid = threadIdx.x;
+  const DevScan& sc = sh.sc;
+  const uint64_t abase = sc.in_offset & ~15ull;
+  const uint32_t skew = (uint32_t)(sc.in_offset - abase);
+  const uint8_t* gbase = in + abase;
+  const uint32_t limit = skew + sc.in_size; // valid raw bytes from gbase
+  const uint64_t readable = ((in_total + 15) & ~15ull) - abase;
+  const uint32_t G = sc.group;
+  const uint32_t RS = sc.row_samples;
+  const uint32_t nchunks_max = (limit + F_RAW - 1) / F_RAW;
+
+  FStream st;
+  st.gbase = gbase;
+  st.limit = limit;
+  st.skew = skew;
+  st.readable = readable;
+  st.chunk_begin = 0;
+  st.chunk_end = nchunks_max;
+  st.pending = true;
+  st.pending_par = 0;
+  if (tid == 0)
+    f_issue_chunk(sh, st, 0);
+  uint32_t my_status = 0;
+
+  for (uint32_t chunk = 0;; ++chunk) {
+    const FusedCarry cy = sh.cy;
+    if (cy.sym >= sc.n_samples)
+      break;
+    if (cy.ended) {
+      my_status |= 2u; // data exhausted but samples are still missing
+      break;
+    }
+    mbar_wait(&sh.bar, chunk & 1);
+    st.pending = false;
+
+    // ================= B: unstuff =================
+    const FChunk co = f_unstuff(sh, st, cy, chunk);
+    const uint32_t len = co.len, Lc = co.Lc, end_all = co.end_all, mpos = co.mpos;
+    const uint32_t total_emit = co.total_emit;
+    const bool final_chunk = co.final_chunk;
+
+    // ================= C: self-synchronising decode =================
+    const FSync so = f_sync<MULTI>(sh, cy, co, G);
+    const uint32_t my_start = so.my_start;
+    const FSub d = so.d;
 
     // ================= D: symbol indices =================
     uint32_t total_syms;
@@ -928,8 +995,8 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
     }
   }
   // never leave a bulk copy in flight into this CTA's shared memory
-  if (pending)
-    mbar_wait(&sh.bar, pending_par);
+  if (st.pending)
+    mbar_wait(&sh.bar, st.pending_par);
   {
     const int bad = __syncthreads_or((int)(my_status & 1u));
     const int over = __syncthreads_or((int)(my_status & 2u));
@@ -941,12 +1008,15 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
 __global__ void __launch_bounds__(F_NT, 5)
     k2_fused_kernel(const uint8_t* __restrict__ in, uint64_t in_total,
                     const DevScan* __restrict__ scans, const DevTable* __restrict__ tables,
-                    uint8_t* __restrict__ out, DevResult* __restrict__ results) {
+                    uint8_t* __restrict__ out, DevResult* __restrict__ results_all,
+                    const uint32_t* __restrict__ scan_ids) {
   extern __shared__ __align__(128) uint8_t f_smem_raw[];
   FusedShared& sh = *reinterpret_cast<FusedShared*>(f_smem_raw);
   const int tid = threadIdx.x;
+  const uint32_t scan_idx = scan_ids ? scan_ids[blockIdx.x] : blockIdx.x;
+  DevResult* results = results_all + scan_idx - blockIdx.x; // results[blockIdx.x] is ours
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[blockIdx.x]);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[scan_idx]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.sc);
     for (int i = tid; i < (int)(sizeof(DevScan) / 4); i += F_NT)
       dst[i] = src[i];

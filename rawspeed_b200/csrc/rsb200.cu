@@ -6,6 +6,7 @@
 
 #include "ljpeg.cuh"
 #include "ljpeg_fused.cuh"
+#include "ljpeg_ranges.cuh"
 #include "unpack.cuh"
 
 #include <algorithm>
@@ -89,8 +90,19 @@ struct rsb200_plan {
   DevResult* h_results = nullptr; // pinned
   uint32_t nrows = 0;
   int nscans = 0;
-  bool fused = false; // LJPEG tiles: single fused kernel, no scratch buffers
   int ntab_slots = 4;
+  // small LJPEG tile segments: one fused CTA each; big segments (CR2 frames,
+  // untiled strips): multi-CTA count/verify/diffs + K3
+  uint32_t* d_small_ids = nullptr;
+  int nsmall = 0;
+  uint32_t* d_big_ids = nullptr;
+  int nbig = 0;
+  BigScanInfo* d_big = nullptr;
+  DevRange* d_ranges = nullptr;
+  RangeState* d_states = nullptr;
+  RangeFinal* d_finals = nullptr;
+  uint32_t* d_fallback = nullptr;
+  int nranges = 0;
   cudaStream_t last_stream = nullptr;
   bool ran = false;
 };
@@ -128,6 +140,10 @@ extern "C" int rsb200_create(int device, rsb200_ctx** out) {
   cudaFuncSetAttribute(k2_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(K2Shared));
   cudaFuncSetAttribute(k2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)fused_smem_bytes(4));
+  cudaFuncSetAttribute(k2_range_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)fused_smem_bytes(4));
+  cudaFuncSetAttribute(k2_range_diffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)fused_smem_bytes(4));
   *out = c;
   return RSB200_OK;
@@ -431,9 +447,11 @@ static void assign_tables(DevScan& d, const uint8_t* table, int ncomp,
     d.table_of[p] = (uint8_t)slot_of_comp[comp_of_pos[p] & 3];
 }
 
+constexpr uint32_t BIG_SEGMENT_BYTES = 256u << 10; // above this a segment gets several CTAs
+
 static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
                              const rsb200_huff_table* tables, int ntables, ScanBuild& b,
-                             bool fused) {
+                             bool /*unused*/) {
   std::vector<DevTable> ht((size_t)ntables);
   for (int i = 0; i < ntables; ++i)
     if (!build_dev_table(tables[i], ht[(size_t)i])) {
@@ -441,19 +459,50 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
       return set_err(ctx, RSB200_ERR_ARG, "huffman table %d is malformed", i);
     }
   p->kind = 1;
-  p->fused = fused;
   p->ntab_slots = 1;
   for (const DevScan& d : b.scans)
     for (int sl = 0; sl < 4; ++sl)
       if (d.table_idx[sl] >= 0)
         p->ntab_slots = std::max(p->ntab_slots, sl + 1);
-  if (fused) {
-    b.rows.clear();
-    b.diff_elems = 0;
-    b.col_elems = 0;
-  }
   p->nscans = (int)b.scans.size();
   p->nunits = p->nscans;
+  // classify the segments and lay out the scratch of the multi-CTA path
+  std::vector<uint32_t> small_ids, big_ids;
+  std::vector<BigScanInfo> big;
+  std::vector<DevRange> ranges;
+  b.rows.clear();
+  b.diff_elems = 0;
+  b.col_elems = 0;
+  for (size_t i = 0; i < b.scans.size(); ++i) {
+    DevScan& d = b.scans[i];
+    const bool is_big = d.kind == 1 || d.in_size > BIG_SEGMENT_BYTES;
+    if (!is_big) {
+      small_ids.push_back((uint32_t)i);
+      continue;
+    }
+    big_ids.push_back((uint32_t)i);
+    d.diff_offset = b.diff_elems;
+    b.diff_elems += (((uint64_t)d.rows * d.row_samples) + 7) & ~7ull;
+    d.col_offset = b.col_elems;
+    b.col_elems += (uint64_t)d.rows * 4;
+    d.row_begin = (uint32_t)b.rows.size();
+    for (uint32_t r = 0; r < d.rows; ++r)
+      b.rows.push_back(K3RowRef{(uint32_t)i, r});
+    const uint32_t skew = (uint32_t)(d.in_offset & 15ull);
+    const uint32_t range_bytes = (uint32_t)R_CHUNKS * F_RAW;
+    const uint32_t nr = (skew + d.in_size + range_bytes - 1) / range_bytes;
+    BigScanInfo bi;
+    bi.scan = (uint32_t)i;
+    bi.first_range = (uint32_t)ranges.size();
+    bi.nranges = std::max(nr, 1u);
+    bi.pad = 0;
+    big.push_back(bi);
+    for (uint32_t r = 0; r < bi.nranges; ++r)
+      ranges.push_back(DevRange{(uint32_t)i, r});
+  }
+  p->nsmall = (int)small_ids.size();
+  p->nbig = (int)big_ids.size();
+  p->nranges = (int)ranges.size();
   p->nrows = (uint32_t)b.rows.size();
   cudaError_t e = cudaSuccess;
   auto up = [&](void** dptr, const void* src, size_t bytes) {
@@ -463,16 +512,24 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     if (e == cudaSuccess && bytes)
       e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
   };
+  auto alloc = [&](void** dptr, size_t bytes) {
+    if (e == cudaSuccess)
+      e = cudaMalloc(dptr, bytes ? bytes : 16);
+  };
   up((void**)&p->d_tables, ht.data(), sizeof(DevTable) * ht.size());
   up((void**)&p->d_scans, b.scans.data(), sizeof(DevScan) * b.scans.size());
   up((void**)&p->d_strips, b.strips.data(), sizeof(DevStrip) * b.strips.size());
   up((void**)&p->d_rows, b.rows.data(), sizeof(K3RowRef) * b.rows.size());
-  if (e == cudaSuccess)
-    e = cudaMalloc((void**)&p->d_diffs, (b.diff_elems + 64) * sizeof(uint16_t));
-  if (e == cudaSuccess)
-    e = cudaMalloc((void**)&p->d_colvals, (b.col_elems + 64) * sizeof(uint16_t));
-  if (e == cudaSuccess)
-    e = cudaMalloc((void**)&p->d_results, sizeof(DevResult) * b.scans.size());
+  up((void**)&p->d_small_ids, small_ids.data(), sizeof(uint32_t) * small_ids.size());
+  up((void**)&p->d_big_ids, big_ids.data(), sizeof(uint32_t) * big_ids.size());
+  up((void**)&p->d_big, big.data(), sizeof(BigScanInfo) * big.size());
+  up((void**)&p->d_ranges, ranges.data(), sizeof(DevRange) * ranges.size());
+  alloc((void**)&p->d_states, sizeof(RangeState) * ranges.size());
+  alloc((void**)&p->d_finals, sizeof(RangeFinal) * ranges.size());
+  alloc((void**)&p->d_fallback, sizeof(uint32_t) * big.size());
+  alloc((void**)&p->d_diffs, (b.diff_elems + 64) * sizeof(uint16_t));
+  alloc((void**)&p->d_colvals, (b.col_elems + 64) * sizeof(uint16_t));
+  alloc((void**)&p->d_results, sizeof(DevResult) * b.scans.size());
   if (e == cudaSuccess)
     e = cudaMallocHost((void**)&p->h_results, sizeof(DevResult) * b.scans.size());
   if (e != cudaSuccess) {
@@ -480,7 +537,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
                    cudaGetErrorString(e));
   }
-  p->launches_per_run = fused ? 1 : 3;
+  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->nbig ? 7 : 0);
   return RSB200_OK;
 }
 
@@ -723,24 +780,38 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
-  } else if (p->fused) {
-    k2_fused_kernel<<<p->nscans, F_NT, fused_smem_bytes(p->ntab_slots), st>>>(
-        in, (uint64_t)in_bytes, p->d_scans, p->d_tables, outp, p->d_results);
-    CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 1;
   } else {
-    k2_entropy_kernel<<<p->nscans, K2_THREADS, sizeof(K2Shared), st>>>(
-        in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->d_diffs, p->d_results);
-    CUDA_TRY(ctx, cudaGetLastError());
-    const int col_warps = p->nscans * 4;
-    k3_column_kernel<<<(col_warps * 32 + 127) / 128, 128, 0, st>>>(
-        p->d_scans, p->nscans, p->d_diffs, p->d_colvals);
-    CUDA_TRY(ctx, cudaGetLastError());
-    const uint32_t rows_per_block = K3_THREADS / 32;
-    k3_row_kernel<<<(p->nrows + rows_per_block - 1) / rows_per_block, K3_THREADS, 0, st>>>(
-        p->d_scans, p->d_rows, p->nrows, p->d_diffs, p->d_colvals, p->d_strips, outp);
-    CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 3;
+    const size_t fsm = fused_smem_bytes(p->ntab_slots);
+    if (p->nsmall) {
+      k2_fused_kernel<<<p->nsmall, F_NT, fsm, st>>>(in, (uint64_t)in_bytes, p->d_scans,
+                                                     p->d_tables, outp, p->d_results,
+                                                     p->d_small_ids);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    }
+    if (p->nbig) {
+      k2_clear_results_kernel<<<(p->nbig + 127) / 128, 128, 0, st>>>(p->d_big, p->nbig,
+                                                                     p->d_results);
+      k2_range_count_kernel<<<p->nranges, F_NT, fsm, st>>>(in, (uint64_t)in_bytes, p->d_scans,
+                                                           p->d_tables, p->d_ranges, p->d_states);
+      k2_range_verify_kernel<<<p->nbig, V_NT, 0, st>>>(p->d_scans, p->d_big, p->d_states,
+                                                       p->d_finals, p->d_fallback);
+      k2_range_diffs_kernel<<<p->nranges, F_NT, fsm, st>>>(in, (uint64_t)in_bytes, p->d_scans,
+                                                           p->d_tables, p->d_ranges, p->d_finals,
+                                                           p->d_diffs, p->d_results);
+      // exact redo of segments whose speculative parse failed verification (no-op otherwise)
+      k2_entropy_kernel<<<p->nbig, K2_THREADS, sizeof(K2Shared), st>>>(
+          in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->d_diffs, p->d_results,
+          p->d_big_ids, p->d_fallback);
+      const int col_warps = p->nbig * 4;
+      k3_column_kernel<<<(col_warps * 32 + 127) / 128, 128, 0, st>>>(
+          p->d_scans, p->d_big_ids, p->nbig, p->d_diffs, p->d_colvals);
+      const uint32_t rows_per_block = K3_THREADS / 32;
+      k3_row_kernel<<<(p->nrows + rows_per_block - 1) / rows_per_block, K3_THREADS, 0, st>>>(
+          p->d_scans, p->d_rows, p->nrows, p->d_diffs, p->d_colvals, p->d_strips, outp);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches += 7;
+    }
   }
   p->last_stream = st;
   p->ran = true;
@@ -878,6 +949,13 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   cudaFree(p->d_diffs);
   cudaFree(p->d_colvals);
   cudaFree(p->d_results);
+  cudaFree(p->d_small_ids);
+  cudaFree(p->d_big_ids);
+  cudaFree(p->d_big);
+  cudaFree(p->d_ranges);
+  cudaFree(p->d_states);
+  cudaFree(p->d_finals);
+  cudaFree(p->d_fallback);
   if (p->h_results)
     cudaFreeHost(p->h_results);
   delete p;

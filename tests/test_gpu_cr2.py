@@ -70,6 +70,13 @@ def test_cr2_sraw(ctx):
     _run(ctx, 96, 20, (3, 2, 2), (32, 40), (2, 48, 48), [0, 1, 1], is_cfa=False, seed=34)
 
 
+def test_cr2_mid_size_multi_cta(ctx):
+    """~1 MB streams: several 64 KiB ranges per frame (speculative multi-CTA parse)."""
+    _run(ctx, 1440, 960, (2, 1, 1), (720, 960), (3, 480, 480), [0, 1], seed=5)
+    _run(ctx, 1440, 960, (4, 1, 1), (360, 960), (3, 480, 480), [0, 1, 0, 1], seed=6)
+    _run(ctx, 1440, 960, (2, 1, 1), (720, 960), (3, 480, 480), [0, 0], seed=7)
+
+
 def test_c4_cr2_6720x4480(ctx):
     """BASELINE configs[3]: Canon CR2 3-slice LJPEG 6720x4480, 2 and 4 components."""
     for fmt, frame in [((2, 1, 1), (3360, 4480)), ((4, 1, 1), (1680, 4480))]:

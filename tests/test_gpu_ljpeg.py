@@ -127,3 +127,22 @@ def test_bad_huffman_code_reports_rde(ctx):
         plan.results()
     with pytest.raises(port.RawDecoderException):
         port.dng_decompress(blob, t.offsets, t.lengths, port.new_image(64, 32), 64, 1, 64, 32, 7)
+
+
+def test_big_untiled_strip_multi_cta(ctx):
+    """One LJPEG segment far above the multi-CTA threshold (several ranges of 64 KiB):
+    count / verify / diffs kernels + K3, single and two-table variants, 2 and 4
+    components, with and without restart intervals."""
+    img = synth.image_model(2048, 700, 41)
+    _check_tiles(ctx, img, 2048, 700)
+    _check_tiles(ctx, img, 2048, 700, tabs=synth.default_tables(2), tab_of_comp=[0, 1])
+    _check_tiles(ctx, img, 2048, 700, ncomp=4, tabs=synth.default_tables(2),
+                 tab_of_comp=[0, 1, 1, 0])
+    wild = synth.image_model(1536, 512, 43, wild=True)
+    _check_tiles(ctx, wild, 1536, 512)
+    _check_tiles(ctx, wild, 768, 512, restart_rows=150)
+
+
+def test_mixed_small_and_big_segments(ctx):
+    img = synth.image_model(2100, 520, 47)
+    _check_tiles(ctx, img, 2048, 512)   # tiles: one big (2048x512), small edge tiles
