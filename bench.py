@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--ljpeg-frames", type=int, default=8, help="frames in the LJPEG batch leg")
     ap.add_argument("--skip-others", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
@@ -328,7 +329,7 @@ def main():
 
     gather = None
     if dist is not None:
-        gather = bench_gather(torch, dist, d_out, world, rank, plan, d_in, args)
+        gather = bench_gather(torch, dist, d_out, world, rank, plan, d_in, args, F, out_fb)
 
     if rank == 0:
         cpu = None if args.skip_cpu else cpu_reference_unpack()
@@ -354,20 +355,23 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_gather(torch, dist, d_out, world, rank, plan, d_in, args):
-    """north_star's NVLink output gather (all ranks' decoded frames -> every rank),
-    timed separately from the decode: NCCL all_gather on the decode stream."""
-    shard = d_out
-    full = torch.empty(world * shard.numel(), dtype=torch.uint8, device="cuda")
+def bench_gather(torch, dist, d_out, world, rank, plan, d_in, args, frames, out_fb):
+    """north_star's NVLink output gather (every rank ends up with all decoded
+    frames), timed separately from the decode: rawspeed_b200.shard.gather_frames
+    = one NCCL all_gather on the decode stream."""
+    from rawspeed_b200 import shard
+    local = d_out.view(frames, out_fb)
 
     def step():
         plan.run(d_in, d_out)
-        dist.all_gather_into_tensor(full, shard)
+        shard.gather_frames(local, frames * world, dist)
     n = max(2, min(args.steps, 5))
     ms = time_steps(torch, step, n, 1, dist)
-    return {"what": "decode + ncclAllGather of the uint16 outputs over NVLink",
-            "ms_per_step": ms / n, "gathered_bytes_per_rank": int(full.numel()),
-            "busbw_GBps": (full.numel() * (world - 1) / world) / (ms / n * 1e-3) / 1e9}
+    total = frames * world * out_fb
+    return {"what": "decode + ncclAllGather of the uint16 outputs over NVLink (all ranks get all frames)",
+            "ms_per_step": ms / n, "gathered_bytes_per_rank": int(total),
+            "MPixels/s": world * frames * PIX / (ms / n * 1e-3) / 1e6,
+            "busbw_GBps": (total * (world - 1) / world) / (ms / n * 1e-3) / 1e9}
 
 
 def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
@@ -391,12 +395,54 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
     ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), t.blob.size), d_out), steps, 3, dist)
     in_b, out_b, pixels = plan.bytes()
     per = ms / steps
-    out["configs[2] DNG LJPEG 8256x5504 (726 tiles 256x256)"] = {
+    c3 = {
         "MPixels/s": pixels / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
         "compressed_bytes_per_pixel": t.blob.size / PIX,
         "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
-        "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak, "launches_per_frame": plan.launches}
-    del plan, d_in, d_out
+        "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak,
+        "read_only_roofline_frac": in_b / (per * 1e-3) / 1e9 / peak,
+        "kernel": "k2_fused_kernel", "launches_per_frame": plan.launches}
+    out["configs[2] DNG LJPEG 8256x5504 (726 tiles 256x256)"] = c3
+    del plan, d_out
+    # ---- C5-style batch: NB frames of C3 resident in HBM, one plan, one launch ----
+    NB = args.ljpeg_frames
+    fb = (t.blob.size + 255) // 256 * 256
+    ob = (H * out_pitch + 255) // 256 * 256
+    d_inb = torch.zeros(NB * fb + 64, dtype=torch.uint8, device="cuda")
+    scans_b, tabs_b = [], None
+    for f in range(NB):
+        d_inb[f * fb:f * fb + t.blob.size] = d_in[:t.blob.size]
+        tabs_b, sc = dng_ljpeg_scans(t, out_pitch, out_offset=f * ob, in_base=f * fb, tabs=tabs_b)
+        scans_b += sc
+    planb = rs.ljpeg_plan(ctx, tabs_b.tabs, scans_b)
+    d_outb = torch.zeros(NB * ob, dtype=torch.uint8, device="cuda")
+    planb.run((d_inb.data_ptr(), NB * fb), d_outb)
+    resb = planb.results()
+    gb = d_outb[(NB - 1) * ob:(NB - 1) * ob + H * out_pitch].cpu().numpy().view(np.uint16).reshape(H, out_pitch // 2)
+    exact_b = bool(np.array_equal(gb[:, :W], img)) and all(s_ == 0 for s_, _ in resb)
+    msb = time_steps(torch, lambda: planb.run((d_inb.data_ptr(), NB * fb), d_outb), steps, 3, dist)
+    in_bb, out_bb, pix_b = planb.bytes()
+    perb = msb / steps
+    out["configs[4]-style batch: %d LJPEG frames of configs[2] per GPU, one launch" % NB] = {
+        "MPixels/s_per_gpu": pix_b / (perb * 1e-3) / 1e6, "ms_per_step": perb, "bit_exact": exact_b,
+        "achieved_GBps": (in_bb + out_bb) / (perb * 1e-3) / 1e9,
+        "roofline_frac": (in_bb + out_bb) / (perb * 1e-3) / 1e9 / peak,
+        "read_only_roofline_frac": in_bb / (perb * 1e-3) / 1e9 / peak}
+    del planb, d_inb, d_outb, d_in
+    if not args.skip_cpu and int(os.environ.get("RANK", "0")) == 0:
+        import oracle
+        if oracle.HAVE_REF:
+            ncores = os.cpu_count() or 1
+            tmp = port.new_image(W, H)
+            ms_cpu = min(oracle.ref.dng_decompress(t.blob, t.offsets, t.lengths, tmp, W, 1, 256, 256, 7,
+                                                   nthreads=ncores, reps=1) for _ in range(3))
+            ms_1 = oracle.ref.dng_decompress(t.blob, t.offsets, t.lengths, tmp, W, 1, 256, 256, 7,
+                                             nthreads=1, reps=1)
+            c3["cpu_reference"] = {"kind": "reference", "cores": ncores,
+                                   "MPixels/s": PIX / (ms_cpu * 1e-3) / 1e6,
+                                   "single_thread_MPixels/s": PIX / (ms_1 * 1e-3) / 1e6,
+                                   "sample": "AbstractDngDecompressor::decompress() (OpenMP over the 726 "
+                                             "tiles), 1 frame, best of 3"}
     # ---- C4: CR2 6720x4480, 3 slices, 2 and 4 components ----
     from test_gpu_cr2 import cr2_job
     cw, ch = 6720, 4480
@@ -417,9 +463,19 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
         exact = bool(np.array_equal(got[:, :cw], cimg[:, :cw])) and res[0][0] == 0
         ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), blob.size), d_out), 3, 1, dist)
         per = ms / 3
-        out["configs[3] CR2 6720x4480 3 slices <%d,1,1>" % fmt[0]] = {
-            "MPixels/s": cw * ch / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
-            "compressed_bytes_per_pixel": blob.size / (cw * ch)}
+        ent = {"MPixels/s": cw * ch / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
+               "compressed_bytes_per_pixel": blob.size / (cw * ch),
+               "kernels": "k2_range_count/verify/diffs + k3_column/row"}
+        if not args.skip_cpu and int(os.environ.get("RANK", "0")) == 0:
+            import oracle
+            if oracle.HAVE_REF:
+                tmp = port.new_image(cw, ch)
+                msr = min(oracle.ref.cr2_ljpeg_decode(blob, tmp, cw, (3, 2240, 2240), reps=1)
+                          for _ in range(2))
+                ent["cpu_reference"] = {"kind": "reference", "cores": 1,
+                                        "MPixels/s": cw * ch / (msr * 1e-3) / 1e6,
+                                        "sample": "Cr2LJpegDecoder::decode (single threaded by design)"}
+        out["configs[3] CR2 6720x4480 3 slices <%d,1,1>" % fmt[0]] = ent
         del plan, d_in, d_out
     return out
 

@@ -32,6 +32,7 @@ struct rsb200_ctx {
   uint8_t* d_out = nullptr;
   size_t d_out_cap = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr}; // H2D / kernel / D2H overlap
 };
 
 static int set_err(rsb200_ctx* c, int code, const char* fmt, ...) {
@@ -66,6 +67,7 @@ struct UnpackFastGroup {
   UnpackFastJobDev* d_jobs = nullptr;
   int njobs = 0;
   uint32_t nblocks = 0;
+  std::vector<UnpackFastJobDev> h_jobs; // host copy (pipelined host runs)
 };
 
 struct rsb200_plan {
@@ -129,6 +131,8 @@ extern "C" int rsb200_create(int device, rsb200_ctx** out) {
   }
   if (e == cudaSuccess)
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+    e = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     fprintf(stderr, "rsb200_create: no usable CUDA device (%s); there is no CPU "
                     "fallback\n",
@@ -157,6 +161,9 @@ extern "C" void rsb200_destroy(rsb200_ctx* c) {
   cudaFree(c->d_out);
   if (c->stream)
     cudaStreamDestroy(c->stream);
+  for (int i = 0; i < 3; ++i)
+    if (c->pipe[i])
+      cudaStreamDestroy(c->pipe[i]);
   delete c;
 }
 
@@ -283,6 +290,7 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
     }
     g.njobs = (int)kv.second.size();
     g.nblocks = nb;
+    g.h_jobs = kv.second;
     cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(UnpackFastJobDev) * kv.second.size());
     if (e == cudaSuccess)
       e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(UnpackFastJobDev) * kv.second.size(),
@@ -334,24 +342,26 @@ static cudaError_t run_unpack_group(const UnpackGroup& g, const uint8_t* in,
 
 template <int BPS, bool LSBO>
 static cudaError_t launch_unpack_fast(const UnpackFastGroup& g, const uint8_t* in,
-                                      uint8_t* outp, cudaStream_t st) {
+                                      uint8_t* outp, cudaStream_t st, uint32_t block_base = 0,
+                                      uint32_t nblocks = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(unpack_fast_kernel<BPS, LSBO>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, UNPACK_FAST_SMEM);
     attr_set = true;
   }
-  unpack_fast_kernel<BPS, LSBO><<<g.nblocks, UNPACK_THREADS, UNPACK_FAST_SMEM, st>>>(
-      in, outp, g.d_jobs, g.njobs);
+  unpack_fast_kernel<BPS, LSBO><<<nblocks ? nblocks : g.nblocks, UNPACK_THREADS,
+                                  UNPACK_FAST_SMEM, st>>>(in, outp, g.d_jobs, g.njobs, block_base);
   return cudaGetLastError();
 }
 
 static cudaError_t run_unpack_fast_group(const UnpackFastGroup& g, const uint8_t* in,
-                                         uint8_t* outp, cudaStream_t st) {
+                                         uint8_t* outp, cudaStream_t st,
+                                         uint32_t block_base = 0, uint32_t nblocks = 0) {
 #define RSB_CASE(B)                                                            \
   case B:                                                                      \
-    return g.lsb ? launch_unpack_fast<B, true>(g, in, outp, st)                \
-                 : launch_unpack_fast<B, false>(g, in, outp, st);
+    return g.lsb ? launch_unpack_fast<B, true>(g, in, outp, st, block_base, nblocks) \
+                 : launch_unpack_fast<B, false>(g, in, outp, st, block_base, nblocks);
   switch (g.bps) {
     RSB_CASE(8)
     RSB_CASE(10)
@@ -831,6 +841,51 @@ static int ensure_cap(rsb200_ctx* ctx, uint8_t** buf, size_t* cap, size_t need) 
   return RSB200_OK;
 }
 
+// A batch of packed frames (one job per frame, disjoint input and output spans):
+// job j's H2D copy, kernel and D2H copy are chained on stream j % 3, so the
+// upload of the next frame and the download of the previous one overlap the
+// unpack of the current one (both PCIe directions busy).
+static bool unpack_pipeline_ok(const rsb200_plan* p) {
+  if (p->kind != 0 || !p->groups.empty() || p->fast_groups.size() != 1)
+    return false;
+  const auto& jobs = p->fast_groups[0].h_jobs;
+  if (jobs.size() < 2)
+    return false;
+  for (size_t j = 0; j + 1 < jobs.size(); ++j) {
+    const uint64_t in_end = jobs[j].in_offset + (uint64_t)jobs[j].rows * jobs[j].in_pitch;
+    const uint64_t out_end = jobs[j].out_offset +
+                             (uint64_t)(jobs[j].row0 + jobs[j].rows) * jobs[j].out_pitch;
+    if (in_end > jobs[j + 1].in_offset || out_end > jobs[j + 1].out_offset)
+      return false;
+  }
+  return true;
+}
+
+static int run_host_unpack_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
+                                     uint8_t* out, size_t out_bytes) {
+  rsb200_ctx* ctx = p->ctx;
+  const UnpackFastGroup& g = p->fast_groups[0];
+  for (size_t j = 0; j < g.h_jobs.size(); ++j) {
+    const UnpackFastJobDev& jb = g.h_jobs[j];
+    cudaStream_t st = ctx->pipe[j % 3];
+    const uint64_t i0 = jb.in_offset & ~15ull;
+    uint64_t i1 = jb.in_offset + (uint64_t)jb.rows * jb.in_pitch;
+    i1 = std::min<uint64_t>((i1 + 15) & ~15ull, in_bytes);
+    const uint64_t o0 = jb.out_offset + (uint64_t)jb.row0 * jb.out_pitch;
+    const uint64_t o1 = std::min<uint64_t>(o0 + (uint64_t)jb.rows * jb.out_pitch, out_bytes);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in + i0, in + i0, i1 - i0, cudaMemcpyHostToDevice, st));
+    const uint32_t nb = (jb.total_items + UNPACK_IPB - 1) / UNPACK_IPB;
+    CUDA_TRY(ctx, run_unpack_fast_group(g, ctx->d_in, ctx->d_out, st, jb.block_begin, nb));
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out + o0, ctx->d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < 3; ++i)
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+  p->last_stream = ctx->pipe[0];
+  p->ran = true;
+  return RSB200_OK;
+}
+
 extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
                                     uint8_t* out, size_t out_bytes, int partial) {
   if (!p || !in || !out)
@@ -843,6 +898,10 @@ extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in
   rc = ensure_cap(ctx, &ctx->d_out, &ctx->d_out_cap, out_bytes);
   if (rc)
     return rc;
+  if (in_bytes < p->need_in || out_bytes < p->need_out)
+    return set_err(ctx, RSB200_ERR_ARG, "plan_run_host: buffers too small");
+  if (!partial && unpack_pipeline_ok(p))
+    return run_host_unpack_pipelined(p, in, in_bytes, out, out_bytes);
   cudaStream_t st = ctx->stream;
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
   if (partial)

@@ -254,15 +254,17 @@ __device__ __forceinline__ void unpack_item16(const uint32_t* __restrict__ sw,
 template <int BPS, bool LSBO>
 __global__ void __launch_bounds__(UNPACK_THREADS)
     unpack_fast_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                       const UnpackFastJobDev* __restrict__ jobs, int njobs) {
+                       const UnpackFastJobDev* __restrict__ jobs, int njobs,
+                       uint32_t block_base) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ int32_t seg_delta[UNPACK_MAXSEG + 1]; // smem offset - row-relative byte
 
+  const uint32_t bid = blockIdx.x + block_base; // sub-launches of a plan start mid-grid
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].block_begin <= blockIdx.x)
+    if (jobs[mid].block_begin <= bid)
       lo = mid;
     else
       hi = mid - 1;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(UNPACK_THREADS)
   const UnpackFastJobDev& job = jobs[lo];
   constexpr uint32_t IB = 2 * BPS; // bytes per item
   const uint32_t ipr = job.ipr;
-  const uint32_t I0 = (blockIdx.x - job.block_begin) * UNPACK_IPB;
+  const uint32_t I0 = (bid - job.block_begin) * UNPACK_IPB;
   const uint32_t I1 = min(I0 + UNPACK_IPB, job.total_items);
   const uint32_t r0 = I0 / ipr;
 
