@@ -236,6 +236,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
     ap.add_argument("--ljpeg-frames", type=int, default=8, help="frames in the LJPEG batch leg")
+    ap.add_argument("--preload-s", type=float, default=0.6,
+                    help="seconds of untimed identical load before the timed steps (clock sampling)")
     ap.add_argument("--skip-others", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
@@ -293,19 +295,25 @@ def main():
         print(json.dumps({"error": "GPU output differs from the oracle; no number reported"}))
         sys.exit(1)
 
+    # clocks are sampled (nvidia-smi, 100 ms period) while the GPU runs the same
+    # step back to back: an untimed pre-load of ~0.6 s, then the timed K steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < args.preload_s:
+        for _ in range(50):
+            plan.run(d_in, d_out)
+        torch.cuda.synchronize()
     l0 = ctx.launches
     ms = time_steps(torch, lambda: plan.run(d_in, d_out), args.steps, args.warmup, dist)
     launches = ctx.launches - l0 - args.warmup * plan.launches
-    # keep the GPU under the same load while the sampler is still running
     clocks = sampler.stop() if rank == 0 else None
 
     ms_per_step = ms / args.steps
     value = world * pixels * args.steps / (ms * 1e-3) / 1e6
     ach = (in_b + out_b) / (ms_per_step * 1e-3) / 1e9  # per GPU, one launch per step
-    roofline = {"bound": "hbm", "kernel": "unpack_kernel<14,MSB>", "achieved": ach, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "unpack_fast_kernel<14,MSB>", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": in_b + out_b,
                 "read_only_frac": (in_b / (ms_per_step * 1e-3) / 1e9) / peak,
