@@ -26,6 +26,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// explicit shared-window loads: a 32-bit shared address kept in a register, so
+// hot loops do not re-derive the generic->shared base (S2R/LEA) per access
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((uint16_t)v) : "memory");
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP) ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),

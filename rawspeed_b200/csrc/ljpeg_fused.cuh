@@ -64,6 +64,7 @@ struct FusedShared {
   uint32_t rowbase[F_RBMAX + 1][2];
   uint32_t mpos;
   uint32_t last_raw_byte;
+  uint32_t lutaddr[12]; // shared address of the LUT used at each position of a group
   DevTable tab[4]; // only the first `ntab` are staged / allocated
 };
 
@@ -154,19 +155,20 @@ __device__ __forceinline__ FSub f_scan_sub(const FusedShared& sh, uint32_t start
     r.count = 0;
     return r;
   }
-  const uint32_t* ub = sh.ub;
+  const uint32_t ub_s = smem_u32(sh.ub);
+  const uint32_t la_s = smem_u32(sh.lutaddr);
+  uint32_t lut_s = smem_u32(sh.tab[0].lut);
   uint32_t p = start, wi = p >> 5;
-  uint32_t cur = ub[wi], nxt = ub[wi + 1];
+  uint32_t cur = lds_u32(ub_s + 4 * wi), nxt = lds_u32(ub_s + 4 * wi + 4);
   uint32_t cnt = 0;
   const uint32_t G = sh.sc.group;
-  const uint16_t* lut0 = sh.tab[0].lut;
   do {
     const uint32_t x = __funnelshift_l(nxt, cur, p & 31);
-    const DevTable* t = MULTI ? &sh.tab[sh.sc.table_of[phase]] : &sh.tab[0];
-    const uint16_t* lut = MULTI ? t->lut : lut0;
-    uint32_t len = lut[x >> (32 - LUT_BITS)] >> 10;
+    if (MULTI)
+      lut_s = lds_u32(la_s + 4 * phase);
+    uint32_t len = lds_u16(lut_s + ((x >> (31 - LUT_BITS)) & (((1u << LUT_BITS) - 1u) << 1))) >> 10;
     if (len == 0) // long or invalid code (rare)
-      len = f_long_symbol(t, x);
+      len = f_long_symbol(MULTI ? &sh.tab[sh.sc.table_of[phase]] : &sh.tab[0], x);
     ++cnt;
     if (MULTI)
       phase = (phase + 1 == G) ? 0 : phase + 1;
@@ -175,7 +177,7 @@ __device__ __forceinline__ FSub f_scan_sub(const FusedShared& sh, uint32_t start
     if (nwi != wi) {
       wi = nwi;
       cur = nxt;
-      nxt = ub[wi + 1];
+      nxt = lds_u32(ub_s + 4 * wi + 4);
     }
   } while (p < end_bit);
   r.exitpos = p;
@@ -705,20 +707,22 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
       if (d.count) {
         const uint32_t lo = max(rel0, done), hi = min(rel0 + d.count, done + take);
         if (lo < hi) {
-          const uint32_t* ub = sh.ub;
+          const uint32_t ub_s = smem_u32(sh.ub);
+          const uint32_t la_s = smem_u32(sh.lutaddr);
+          uint32_t lut_s = smem_u32(sh.tab[0].lut);
           uint32_t p = my_start, wi = p >> 5;
-          uint32_t cur = ub[wi], nxt = ub[wi + 1];
+          uint32_t cur = lds_u32(ub_s + 4 * wi), nxt = lds_u32(ub_s + 4 * wi + 4);
           uint32_t phase = MULTI ? (sym0 % G) : 0u;
-          const DevTable* t = &sh.tab[0];
           uint32_t k = rel0;
+          constexpr uint32_t LMASK = ((1u << LUT_BITS) - 1u) << 1;
           // symbols of earlier batches: lengths only
           for (; k < lo; ++k) {
             const uint32_t x = __funnelshift_l(nxt, cur, p & 31);
             if (MULTI)
-              t = &sh.tab[sc.table_of[phase]];
-            uint32_t tl = t->lut[x >> (32 - LUT_BITS)] >> 10;
+              lut_s = lds_u32(la_s + 4 * phase);
+            uint32_t tl = lds_u16(lut_s + ((x >> (31 - LUT_BITS)) & LMASK)) >> 10;
             if (tl == 0)
-              tl = f_long_symbol(t, x);
+              tl = f_long_symbol(MULTI ? &sh.tab[sc.table_of[phase]] : &sh.tab[0], x);
             if (MULTI)
               phase = (phase + 1 == G) ? 0 : phase + 1;
             p += tl;
@@ -726,32 +730,35 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
             if (nwi != wi) {
               wi = nwi;
               cur = nxt;
-              nxt = ub[wi + 1];
+              nxt = lds_u32(ub_s + 4 * wi + 4);
             }
           }
-          uint16_t* dst = DB + cb.leftover + (lo - done);
+          uint32_t dst = smem_u32(DB + cb.leftover + (lo - done));
           uint32_t plast = 0xFFFFFFFFu, bad = 0;
+          const uint32_t pl_k = klast; // chunk-relative index of the segment's last symbol
           for (; k < hi; ++k) {
             const uint32_t x = __funnelshift_l(nxt, cur, p & 31);
             if (MULTI)
-              t = &sh.tab[sc.table_of[phase]];
-            const uint32_t e = t->lut[x >> (32 - LUT_BITS)];
+              lut_s = lds_u32(la_s + 4 * phase);
+            const uint32_t e = lds_u16(lut_s + ((x >> (31 - LUT_BITS)) & LMASK));
             uint32_t codelen = e & 31u, ssss = (e >> 5) & 31u, tl = e >> 10;
             if (codelen == 0) {
-              const SymLen s = decode_sym(t, x);
+              const SymLen s = decode_sym(MULTI ? &sh.tab[sc.table_of[phase]] : &sh.tab[0], x);
               codelen = s.codelen;
               ssss = s.ssss;
               tl = s.total;
               bad |= (s.codelen == 0);
             }
-            // AbstractPrefixCodeDecoder::extend, branch free
+            // AbstractPrefixCodeDecoder::extend, branch free:
+            // v = top ssss bits after the code; negative range iff their first bit is 0
             const uint32_t tt = x << codelen;
             const uint32_t v = __funnelshift_l(tt, 0u, ssss);
-            int diff = (int)v - (((int)tt >= 0) ? (int)((1u << ssss) - 1u) : 0);
+            int diff = (int)v + (((int)tt >= 0) ? (int)(0xFFFFFFFFu << ssss) + 1 : 0);
             if (ssss == 16)
               diff = -32768;
-            *dst++ = (uint16_t)diff;
-            if (k == klast)
+            sts_u16(dst, (uint32_t)diff);
+            dst += 2;
+            if (k == pl_k)
               plast = p;
             if (MULTI)
               phase = (phase + 1 == G) ? 0 : phase + 1;
@@ -760,7 +767,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
             if (nwi != wi) {
               wi = nwi;
               cur = nxt;
-              nxt = ub[wi + 1];
+              nxt = lds_u32(ub_s + 4 * wi + 4);
             }
           }
           if (bad)
@@ -1031,6 +1038,8 @@ __global__ void __launch_bounds__(F_NT, 5)
     for (int i = tid; i < (int)(sizeof(DevTable) / 16); i += F_NT)
       dst[i] = src[i];
   }
+  if (tid < 12)
+    sh.lutaddr[tid] = smem_u32(sh.tab[sc.table_of[tid] & 3].lut);
   if (tid == 0) {
     results[blockIdx.x].consumed = 0;
     mbar_init(&sh.bar, 1);

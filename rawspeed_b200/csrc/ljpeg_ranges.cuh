@@ -101,6 +101,8 @@ __device__ __forceinline__ void r_stage(FusedShared& sh, const DevScan* scans,
     for (int i = tid; i < (int)(sizeof(DevTable) / 16); i += F_NT)
       dst[i] = src[i];
   }
+  if (tid < 12)
+    sh.lutaddr[tid] = smem_u32(sh.tab[sh.sc.table_of[tid] & 3].lut);
 }
 
 __device__ __forceinline__ void r_stream(const FusedShared& sh, const uint8_t* in,
