@@ -69,7 +69,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    # RSB200_LIB: load another build of the same library (profiling variants made by
+    # tools/phase_timing.py); still the CUDA library, never a fallback
+    path = os.environ.get("RSB200_LIB") or _build.LIB
     if not os.path.exists(path):
         path = _build.build()
     L = C.CDLL(path)

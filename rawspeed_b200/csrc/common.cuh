@@ -26,20 +26,35 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-// explicit shared-window loads: a 32-bit shared address kept in a register, so
-// hot loops do not re-derive the generic->shared base (S2R/LEA) per access
-__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+// Explicit shared-window accesses for the hot loops.  The address operand is a
+// 32-bit shared address held in a register plus a compile-time byte offset; the
+// base comes from smem_base_opaque() ONCE per kernel: nvcc otherwise
+// re-materialises the generic->shared conversion (S2R SR_CgaCtaId + LEA) next to
+// every access inside the loops.
+__device__ __forceinline__ uint32_t smem_base_opaque(const void* p) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(smem_u32(p)));
+  return r;
+}
+template <int OFF = 0> __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
   uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr) : "memory");
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(saddr), "n"(OFF) : "memory");
   return v;
 }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+template <int OFF = 0> __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(OFF) : "memory");
   return v;
 }
-__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((uint16_t)v) : "memory");
+template <int OFF = 0> __device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(saddr), "n"(OFF), "h"((uint16_t)v) : "memory");
+}
+// c + (a * b >> 32): with b a power of two this is "c + (a >> k)" on the FMA
+// pipe (IMAD.HI), which the decode loops use to off-load the busier ALU pipe
+__device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
 }
 
 // ---- mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP) ----

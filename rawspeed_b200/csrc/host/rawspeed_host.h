@@ -457,8 +457,8 @@ class AbstractDngDecompressor {
 public:
   AbstractDngDecompressor(RawImage img, const DngTilingDescription& dsc_, int compression_,
                           bool mFixLjpeg_, uint32_t mBps_, uint32_t mPredictor_)
-      : mRaw(std::move(img)), dsc(dsc_), compression(compression_), mFixLjpeg(mFixLjpeg_),
-        mBps(mBps_), mPredictor(mPredictor_) {}
+      : dsc(dsc_), compression(compression_), mFixLjpeg(mFixLjpeg_), mBps(mBps_),
+        mPredictor(mPredictor_), mRaw(std::move(img)) {}
   // all tiles of the frame go to the device in ONE plan (the reference fans them
   // out over OpenMP threads, AbstractDngDecompressor.cpp:54-131,240-252)
   void decompress() const;

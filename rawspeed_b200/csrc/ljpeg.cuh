@@ -249,8 +249,8 @@ __device__ __forceinline__ SymLen decode_sym(const DevTable* __restrict__ t,
   s.ssss = (e >> 5) & 31;
   s.total = e >> 10;
   if (s.codelen == 0) {
-    // code longer than LUT_BITS (or corrupt): T.81 F.16 walk
-    int len = LUT_BITS + 1;
+    // not in the LUT (code longer than LUT_BITS, SSSS = 16, or corrupt): T.81 F.16 walk
+    int len = 1;
     for (; len <= t->maxlen; ++len) {
       const int code = (int)(x >> (32 - len));
       if (code <= t->maxcode[len]) {

@@ -64,6 +64,7 @@ struct FusedShared {
   uint32_t rowbase[F_RBMAX + 1][2];
   uint32_t mpos;
   uint32_t last_raw_byte;
+  uint32_t bad_code;    // set by the difference decode when a needed code is not in the table
   uint32_t lutaddr[12]; // shared address of the LUT used at each position of a group
   DevTable tab[4]; // only the first `ntab` are staged / allocated
 };
@@ -135,6 +136,21 @@ __device__ __forceinline__ void f_block_scan_v2(uint32_t& a, uint32_t& b, uint32
   b = __vadd2(b, addb);
 }
 
+// Optional per-phase cycle accounting (profiling builds only: -DRSB200_PHASE_TIMING).
+#ifdef RSB200_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define F_TICK(i)                                                                  \
+  do {                                                                             \
+    if (threadIdx.x == 0) {                                                        \
+      const long long t_now = clock64();                                           \
+      atomicAdd(&g_phase_cycles[i], (unsigned long long)(t_now - t_phase));        \
+      t_phase = t_now;                                                             \
+    }                                                                              \
+  } while (0)
+#else
+#define F_TICK(i) do { } while (0)
+#endif
+
 struct FSub {
   uint32_t exitpos;
   uint32_t count;
@@ -145,9 +161,73 @@ __device__ __noinline__ uint32_t f_long_symbol(const DevTable* t, uint32_t x) {
   return (uint32_t)decode_sym(t, x).total;
 }
 
+// ---- hot-loop view of the clean buffer and the LUTs ----
+// `sb` = smem_base_opaque(&sh).  Every access is "register + constant":
+constexpr int FO_UB = (int)offsetof(FusedShared, ub);
+constexpr int FO_DBUF = (int)offsetof(FusedShared, dbuf);
+constexpr int FO_LUTADDR = (int)offsetof(FusedShared, lutaddr);
+constexpr int FO_LUT0 = (int)(offsetof(FusedShared, tab) + offsetof(DevTable, lut));
+constexpr uint32_t F_LUT_TOPMASK = ~((1u << (32 - LUT_BITS)) - 1u); // top LUT_BITS bits of the window
+
+struct FBits {
+  uint32_t p;        // bit position in ub
+  uint32_t cur, nxt; // words p/32 and p/32+1
+  __device__ __forceinline__ void open(uint32_t sb, uint32_t start) {
+    p = start;
+    const uint32_t wa = sb + ((start >> 3) & ~3u);
+    cur = lds_u32<FO_UB>(wa);
+    nxt = lds_u32<FO_UB + 4>(wa);
+  }
+  // the next 32 bits of the stream
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, p); }
+  __device__ __forceinline__ void skip(uint32_t sb, uint32_t n) {
+    const uint32_t pn = p + n;
+    if ((pn ^ p) & ~31u) { // crossed into the next word (n <= 32)
+      cur = nxt;
+      nxt = lds_u32<FO_UB + 4>(mad_hi(pn & ~31u, 1u << 29, sb)); // sb + 4*(pn/32)
+    }
+    p = pn;
+  }
+};
+
+// LUT entry of the code at the top of window x.  lutbase: MULTI -> absolute
+// shared address of the LUT of this position in the group; else unused.
+template <bool MULTI>
+__device__ __forceinline__ uint32_t f_lut_entry(uint32_t sb, uint32_t lutbase, uint32_t x) {
+  // base + 2*(x >> (32-LUT_BITS)), the shift done by IMAD.HI
+  if (MULTI)
+    return lds_u16<0>(mad_hi(x & F_LUT_TOPMASK, 1u << (LUT_BITS + 1), lutbase));
+  return lds_u16<FO_LUT0>(mad_hi(x & F_LUT_TOPMASK, 1u << (LUT_BITS + 1), sb));
+}
+
+// One difference: Huffman code + SSSS mantissa bits at the top of window x
+// (PrefixCodeLUTDecoder.h:172-216 + AbstractPrefixCodeDecoder.h:43-76).
+// Returns the difference mod 2^16 in the low half; tl = bits consumed.
+template <bool MULTI>
+__device__ __forceinline__ uint32_t f_decode_diff(FusedShared& sh, uint32_t sb,
+                                                  uint32_t lutbase, uint32_t phase, uint32_t x,
+                                                  uint32_t& tl) {
+  const uint32_t e = f_lut_entry<MULTI>(sb, lutbase, x);
+  tl = e >> 10;
+  if (e == 0) { // code longer than the LUT, SSSS = 16, or corrupt
+    const SymLen s = decode_sym(MULTI ? &sh.tab[sh.sc.table_of[phase]] : &sh.tab[0], x);
+    tl = s.total;
+    if (s.codelen == 0)
+      sh.bad_code = 1u; // "bad Huffman code" (kept out of the registers of the hot loop)
+    return (uint32_t)sym_diff(s, x);
+  }
+  // extend(), branch free.  tt = bits after the code; f = all ones iff their
+  // first bit is 0 (negative range); (f:tt) << ssss leaves v with ones above it in
+  // that case, and v - (2^ssss - 1) == (v | ~mask) + 1.  Funnel shifts wrap at 32,
+  // so the code-length / SSSS fields of e are used unmasked.
+  const uint32_t tt = __funnelshift_l(0u, x, e);
+  const uint32_t f = (uint32_t)((int32_t)~tt >> 31);
+  return __funnelshift_l(tt, f, e >> 5) - f;
+}
+
 // lengths-only decode of one subsequence of the clean buffer
 template <bool MULTI>
-__device__ __forceinline__ FSub f_scan_sub(const FusedShared& sh, uint32_t start,
+__device__ __forceinline__ FSub f_scan_sub(const FusedShared& sh, uint32_t sb, uint32_t start,
                                            uint32_t end_bit, uint32_t phase) {
   FSub r;
   if (start >= end_bit) {
@@ -155,32 +235,23 @@ __device__ __forceinline__ FSub f_scan_sub(const FusedShared& sh, uint32_t start
     r.count = 0;
     return r;
   }
-  const uint32_t ub_s = smem_u32(sh.ub);
-  const uint32_t la_s = smem_u32(sh.lutaddr);
-  uint32_t lut_s = smem_u32(sh.tab[0].lut);
-  uint32_t p = start, wi = p >> 5;
-  uint32_t cur = lds_u32(ub_s + 4 * wi), nxt = lds_u32(ub_s + 4 * wi + 4);
-  uint32_t cnt = 0;
+  FBits b;
+  b.open(sb, start);
+  uint32_t cnt = 0, lutbase = 0;
   const uint32_t G = sh.sc.group;
   do {
-    const uint32_t x = __funnelshift_l(nxt, cur, p & 31);
+    const uint32_t x = b.peek();
     if (MULTI)
-      lut_s = lds_u32(la_s + 4 * phase);
-    uint32_t len = lds_u16(lut_s + ((x >> (31 - LUT_BITS)) & (((1u << LUT_BITS) - 1u) << 1))) >> 10;
-    if (len == 0) // long or invalid code (rare)
+      lutbase = lds_u32<FO_LUTADDR>(sb + 4 * phase);
+    uint32_t len = f_lut_entry<MULTI>(sb, lutbase, x) >> 10;
+    if (len == 0) // long code, SSSS = 16, or invalid code (rare)
       len = f_long_symbol(MULTI ? &sh.tab[sh.sc.table_of[phase]] : &sh.tab[0], x);
     ++cnt;
     if (MULTI)
       phase = (phase + 1 == G) ? 0 : phase + 1;
-    p += len;
-    const uint32_t nwi = p >> 5;
-    if (nwi != wi) {
-      wi = nwi;
-      cur = nxt;
-      nxt = lds_u32(ub_s + 4 * wi + 4);
-    }
-  } while (p < end_bit);
-  r.exitpos = p;
+    b.skip(sb, len);
+  } while (b.p < end_bit);
+  r.exitpos = b.p;
   r.count = cnt;
   return r;
 }
@@ -569,8 +640,8 @@ struct FSync {
 
 // ================= C: self-synchronising decode of the chunk in sh.ub =================
 template <bool MULTI>
-__device__ __forceinline__ FSync f_sync(FusedShared& sh, const FusedCarry& cy, const FChunk& co,
-                                        uint32_t G) {
+__device__ __forceinline__ FSync f_sync(FusedShared& sh, uint32_t sb, const FusedCarry& cy,
+                                        const FChunk& co, uint32_t G) {
   const int tid = threadIdx.x;
     const uint32_t sub_lo = tid * F_SUB * 8u;
     const uint32_t sub_hi = min(sub_lo + F_SUB * 8u, co.end_all);
@@ -583,7 +654,7 @@ __device__ __forceinline__ FSync f_sync(FusedShared& sh, const FusedCarry& cy, c
     d.exitpos = my_start;
     d.count = 0;
     if (active)
-      d = f_scan_sub<MULTI>(sh, my_start, sub_hi, my_phase);
+      d = f_scan_sub<MULTI>(sh, sb, my_start, sub_hi, my_phase);
     sh.exitpos[tid] = d.exitpos;
     if (MULTI)
       sh.exitph[tid] = (my_phase + d.count) % G;
@@ -613,7 +684,7 @@ __device__ __forceinline__ FSync f_sync(FusedShared& sh, const FusedCarry& cy, c
       if (changed) {
         my_start = new_start;
         my_phase = new_phase;
-        d = f_scan_sub<MULTI>(sh, my_start, sub_hi, my_phase);
+        d = f_scan_sub<MULTI>(sh, sb, my_start, sub_hi, my_phase);
       }
       sh.exitpos[tid] = d.exitpos; // (reads of exitpos[tid-1] precede the vote barrier)
       if (MULTI)
@@ -642,6 +713,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
   const uint64_t readable = ((in_total + 15) & ~15ull) - abase;
   const uint32_t G = sc.group;
   const uint32_t RS = sc.row_samples;
+  const uint32_t sb = smem_base_opaque(&sh); // shared address of sh, for the hot loops
   const uint32_t nchunks_max = (limit + F_RAW - 1) / F_RAW;
 
   FStream st;
@@ -656,6 +728,9 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
   if (tid == 0)
     f_issue_chunk(sh, st, 0);
   uint32_t my_status = 0;
+#ifdef RSB200_PHASE_TIMING
+  long long t_phase = clock64();
+#endif
 
   for (uint32_t chunk = 0;; ++chunk) {
     const FusedCarry cy = sh.cy;
@@ -667,17 +742,20 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
     }
     mbar_wait(&sh.bar, chunk & 1);
     st.pending = false;
+    F_TICK(0);
 
     // ================= B: unstuff =================
     const FChunk co = f_unstuff(sh, st, cy, chunk);
     const uint32_t len = co.len, Lc = co.Lc, end_all = co.end_all, mpos = co.mpos;
     const uint32_t total_emit = co.total_emit;
     const bool final_chunk = co.final_chunk;
+    F_TICK(1);
 
     // ================= C: self-synchronising decode =================
-    const FSync so = f_sync<MULTI>(sh, cy, co, G);
+    const FSync so = f_sync<MULTI>(sh, sb, cy, co, G);
     const uint32_t my_start = so.my_start;
     const FSub d = so.d;
+    F_TICK(2);
 
     // ================= D: symbol indices =================
     uint32_t total_syms;
@@ -707,71 +785,48 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
       if (d.count) {
         const uint32_t lo = max(rel0, done), hi = min(rel0 + d.count, done + take);
         if (lo < hi) {
-          const uint32_t ub_s = smem_u32(sh.ub);
-          const uint32_t la_s = smem_u32(sh.lutaddr);
-          uint32_t lut_s = smem_u32(sh.tab[0].lut);
-          uint32_t p = my_start, wi = p >> 5;
-          uint32_t cur = lds_u32(ub_s + 4 * wi), nxt = lds_u32(ub_s + 4 * wi + 4);
+          FBits b;
+          b.open(sb, my_start);
           uint32_t phase = MULTI ? (sym0 % G) : 0u;
-          uint32_t k = rel0;
-          constexpr uint32_t LMASK = ((1u << LUT_BITS) - 1u) << 1;
+          uint32_t lutbase = 0;
           // symbols of earlier batches: lengths only
-          for (; k < lo; ++k) {
-            const uint32_t x = __funnelshift_l(nxt, cur, p & 31);
+          for (uint32_t k = rel0; k < lo; ++k) {
+            const uint32_t x = b.peek();
             if (MULTI)
-              lut_s = lds_u32(la_s + 4 * phase);
-            uint32_t tl = lds_u16(lut_s + ((x >> (31 - LUT_BITS)) & LMASK)) >> 10;
+              lutbase = lds_u32<FO_LUTADDR>(sb + 4 * phase);
+            uint32_t tl = f_lut_entry<MULTI>(sb, lutbase, x) >> 10;
             if (tl == 0)
               tl = f_long_symbol(MULTI ? &sh.tab[sc.table_of[phase]] : &sh.tab[0], x);
             if (MULTI)
               phase = (phase + 1 == G) ? 0 : phase + 1;
-            p += tl;
-            const uint32_t nwi = p >> 5;
-            if (nwi != wi) {
-              wi = nwi;
-              cur = nxt;
-              nxt = lds_u32(ub_s + 4 * wi + 4);
-            }
+            b.skip(sb, tl);
           }
-          uint32_t dst = smem_u32(DB + cb.leftover + (lo - done));
-          uint32_t plast = 0xFFFFFFFFu, bad = 0;
+          // dst walks dbuf; the segment's last symbol (its position feeds
+          // `consumed`) splits the walk in two so the loop body stays free of it
+          uint32_t dst = sb + 2u * (doff + cb.leftover + (lo - done));
+          const uint32_t dst_end = dst + 2u * (hi - lo);
           const uint32_t pl_k = klast; // chunk-relative index of the segment's last symbol
-          for (; k < hi; ++k) {
-            const uint32_t x = __funnelshift_l(nxt, cur, p & 31);
-            if (MULTI)
-              lut_s = lds_u32(la_s + 4 * phase);
-            const uint32_t e = lds_u16(lut_s + ((x >> (31 - LUT_BITS)) & LMASK));
-            uint32_t codelen = e & 31u, ssss = (e >> 5) & 31u, tl = e >> 10;
-            if (codelen == 0) {
-              const SymLen s = decode_sym(MULTI ? &sh.tab[sc.table_of[phase]] : &sh.tab[0], x);
-              codelen = s.codelen;
-              ssss = s.ssss;
-              tl = s.total;
-              bad |= (s.codelen == 0);
+          uint32_t stop = (pl_k >= lo && pl_k < hi) ? dst + 2u * (pl_k - lo) : dst_end;
+          uint32_t plast = 0xFFFFFFFFu;
+          for (;;) {
+            while (dst != stop) {
+              const uint32_t x = b.peek();
+              if (MULTI)
+                lutbase = lds_u32<FO_LUTADDR>(sb + 4 * phase);
+              uint32_t tl;
+              const uint32_t diff = f_decode_diff<MULTI>(sh, sb, lutbase, phase, x, tl);
+              sts_u16<FO_DBUF>(dst, diff);
+              dst += 2;
+              if (MULTI)
+                phase = (phase + 1 == G) ? 0 : phase + 1;
+              b.skip(sb, tl);
             }
-            // AbstractPrefixCodeDecoder::extend, branch free:
-            // v = top ssss bits after the code; negative range iff their first bit is 0
-            const uint32_t tt = x << codelen;
-            const uint32_t v = __funnelshift_l(tt, 0u, ssss);
-            int diff = (int)v + (((int)tt >= 0) ? (int)(0xFFFFFFFFu << ssss) + 1 : 0);
-            if (ssss == 16)
-              diff = -32768;
-            sts_u16(dst, (uint32_t)diff);
-            dst += 2;
-            if (k == pl_k)
-              plast = p;
-            if (MULTI)
-              phase = (phase + 1 == G) ? 0 : phase + 1;
-            p += tl;
-            const uint32_t nwi = p >> 5;
-            if (nwi != wi) {
-              wi = nwi;
-              cur = nxt;
-              nxt = lds_u32(ub_s + 4 * wi + 4);
-            }
+            if (stop == dst_end)
+              break;
+            plast = b.p;
+            stop = dst_end;
           }
-          if (bad)
-            my_status |= 1u;
+          const uint32_t p = b.p;
           if (final_chunk && p > len * 8u)
             my_status |= 2u; // a needed symbol runs past the end of the data
           if (plast != 0xFFFFFFFFu) {
@@ -784,6 +839,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
         }
       }
       __syncthreads();
+      F_TICK(3);
 
       // ================= E: predictor on whole groups =================
       const uint32_t have = cb.leftover + take;
@@ -802,6 +858,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
       else
         f_prefix_scalar(sh, DB, S0, n, G, cb.pc01, cb.pc23, ta, tb);
       __syncthreads();
+      F_TICK(4);
       // E2: row constants.  Rows starting inside this batch: first sample index
       // ri = r*RS - S0 in [0, n).  One warp scans them 32 at a time.
       const uint32_t r_first = (S0 + RS - 1) / RS;                // first row starting >= S0
@@ -856,6 +913,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
         }
       }
       __syncthreads();
+      F_TICK(5);
       // E3: values -> image.  Units of 8 samples, aligned on the global index.
       {
         const uint32_t u_first = S0 >> 3, u_last = (S0 + n + 7) >> 3; // [u_first, u_last)
@@ -924,6 +982,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
         }
       }
       __syncthreads();
+      F_TICK(6);
       // E4: carry
       if (tid == 0) {
         FusedCarry& c2 = sh.cy;
@@ -945,6 +1004,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
       if ((uint32_t)tid < have - n)
         sh.dbuf[((S0 + n) & 7u) + tid] = (uint16_t)keep;
       __syncthreads();
+      F_TICK(7);
       done += take;
       if (done >= chunk_syms)
         break;
@@ -999,13 +1059,15 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
         c2.ended = final_chunk ? 1u : 0u;
       }
       __syncthreads();
+      F_TICK(8);
     }
   }
   // never leave a bulk copy in flight into this CTA's shared memory
   if (st.pending)
     mbar_wait(&sh.bar, st.pending_par);
   {
-    const int bad = __syncthreads_or((int)(my_status & 1u));
+    int bad = __syncthreads_or((int)(my_status & 1u));
+    bad |= (int)sh.bad_code; // (after the barrier)
     const int over = __syncthreads_or((int)(my_status & 2u));
     if (tid == 0)
       results[blockIdx.x].status = bad ? 1u : (over ? 2u : 0u);
@@ -1042,6 +1104,7 @@ __global__ void __launch_bounds__(F_NT, 5)
     sh.lutaddr[tid] = smem_u32(sh.tab[sc.table_of[tid] & 3].lut);
   if (tid == 0) {
     results[blockIdx.x].consumed = 0;
+    sh.bad_code = 0;
     mbar_init(&sh.bar, 1);
     fence_mbar_init();
     FusedCarry c;

@@ -137,6 +137,7 @@ __device__ __forceinline__ void range_count_body(FusedShared& sh, const uint8_t*
                                                  RangeState* out) {
   const int tid = threadIdx.x;
   const uint32_t G = sh.sc.group;
+  const uint32_t sb = smem_base_opaque(&sh);
   FStream st;
   uint32_t c_own0, c_own1;
   const uint32_t c_first = r == 0 ? 0u : r * R_CHUNKS - 1u; // one halo chunk for r > 0
@@ -166,7 +167,7 @@ __device__ __forceinline__ void range_count_body(FusedShared& sh, const uint8_t*
     mbar_wait(&sh.bar, (chunk - c_first) & 1u);
     st.pending = false;
     const FChunk co = f_unstuff(sh, st, cy, chunk);
-    const FSync so = f_sync<MULTI>(sh, cy, co, G);
+    const FSync so = f_sync<MULTI>(sh, sb, cy, co, G);
     uint32_t total_syms;
     (void)f_block_scan(so.d.count, sh.warp_tmp[3], &total_syms);
     const uint32_t nsub = (co.end_all + F_SUB * 8u - 1) / (F_SUB * 8u);
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(F_NT, 5)
   const DevRange rg = ranges[blockIdx.x];
   r_stage(sh, scans, tables, rg.scan);
   if (threadIdx.x == 0) {
+    sh.bad_code = 0;
     mbar_init(&sh.bar, 1);
     fence_mbar_init();
   }
@@ -354,6 +356,7 @@ __device__ __forceinline__ void range_diffs_body(FusedShared& sh, const uint8_t*
   const int tid = threadIdx.x;
   const DevScan& sc = sh.sc;
   const uint32_t G = sc.group;
+  const uint32_t sb = smem_base_opaque(&sh);
   FStream st;
   uint32_t c_own0, c_own1;
   r_stream(sh, in, in_total, r, r * R_CHUNKS, st, c_own0, c_own1);
@@ -386,7 +389,7 @@ __device__ __forceinline__ void range_diffs_body(FusedShared& sh, const uint8_t*
     mbar_wait(&sh.bar, (chunk - c_own0) & 1u);
     st.pending = false;
     const FChunk co = f_unstuff(sh, st, cy, chunk);
-    const FSync so = f_sync<MULTI>(sh, cy, co, G);
+    const FSync so = f_sync<MULTI>(sh, sb, cy, co, G);
     const FSub d = so.d;
     uint32_t total_syms;
     const uint32_t sincl = f_block_scan(d.count, sh.warp_tmp[3], &total_syms);
@@ -398,46 +401,31 @@ __device__ __forceinline__ void range_diffs_body(FusedShared& sh, const uint8_t*
     const uint32_t klast = sc.n_samples - 1 - cy.sym; // the segment's very last symbol
     if (d.count && rel0 < chunk_syms) {
       const uint32_t hi = min(rel0 + d.count, chunk_syms);
-      const uint32_t* ub = sh.ub;
-      uint32_t p = so.my_start, wi = p >> 5;
-      uint32_t cur = ub[wi], nxt = ub[wi + 1];
+      FBits b;
+      b.open(sb, so.my_start);
       uint32_t phase = MULTI ? (sym0 % G) : 0u;
-      const DevTable* t = &sh.tab[0];
+      uint32_t lutbase = 0;
       uint16_t* dst = dout + sym0;
-      uint32_t plast = 0xFFFFFFFFu, bad = 0;
-      for (uint32_t k = rel0; k < hi; ++k) {
-        const uint32_t x = __funnelshift_l(nxt, cur, p & 31);
-        if (MULTI)
-          t = &sh.tab[sc.table_of[phase]];
-        const uint32_t e = t->lut[x >> (32 - LUT_BITS)];
-        uint32_t codelen = e & 31u, ssss = (e >> 5) & 31u, tl = e >> 10;
-        if (codelen == 0) {
-          const SymLen s = decode_sym(t, x);
-          codelen = s.codelen;
-          ssss = s.ssss;
-          tl = s.total;
-          bad |= (s.codelen == 0);
+      uint16_t* const dst_end = dst + (hi - rel0);
+      uint16_t* stop = (klast >= rel0 && klast < hi) ? dst + (klast - rel0) : dst_end;
+      uint32_t plast = 0xFFFFFFFFu;
+      for (;;) {
+        while (dst != stop) {
+          const uint32_t x = b.peek();
+          if (MULTI)
+            lutbase = lds_u32<FO_LUTADDR>(sb + 4 * phase);
+          uint32_t tl;
+          *dst++ = (uint16_t)f_decode_diff<MULTI>(sh, sb, lutbase, phase, x, tl);
+          if (MULTI)
+            phase = (phase + 1 == G) ? 0 : phase + 1;
+          b.skip(sb, tl);
         }
-        const uint32_t tt = x << codelen;
-        const uint32_t v = __funnelshift_l(tt, 0u, ssss);
-        int diff = (int)v - (((int)tt >= 0) ? (int)((1u << ssss) - 1u) : 0);
-        if (ssss == 16)
-          diff = -32768;
-        *dst++ = (uint16_t)diff;
-        if (k == klast)
-          plast = p;
-        if (MULTI)
-          phase = (phase + 1 == G) ? 0 : phase + 1;
-        p += tl;
-        const uint32_t nwi = p >> 5;
-        if (nwi != wi) {
-          wi = nwi;
-          cur = nxt;
-          nxt = ub[wi + 1];
-        }
+        if (stop == dst_end)
+          break;
+        plast = b.p;
+        stop = dst_end;
       }
-      if (bad)
-        my_status |= 1u;
+      const uint32_t p = b.p;
       if (co.final_chunk && p > co.len * 8u)
         my_status |= 2u;
       if (plast != 0xFFFFFFFFu) {
@@ -488,7 +476,8 @@ __device__ __forceinline__ void range_diffs_body(FusedShared& sh, const uint8_t*
   if (st.pending)
     mbar_wait(&sh.bar, st.pending_par);
   {
-    const int bad = __syncthreads_or((int)(my_status & 1u));
+    int bad = __syncthreads_or((int)(my_status & 1u));
+    bad |= (int)sh.bad_code; // (after the barrier)
     const int over = __syncthreads_or((int)(my_status & 2u));
     if (tid == 0 && (bad || over))
       atomicOr(&result->status, bad ? 1u : 2u);
@@ -508,6 +497,7 @@ __global__ void __launch_bounds__(F_NT, 5)
     return;
   r_stage(sh, scans, tables, rg.scan);
   if (threadIdx.x == 0) {
+    sh.bad_code = 0;
     mbar_init(&sh.bar, 1);
     fence_mbar_init();
   }

@@ -171,6 +171,21 @@ extern "C" const char* rsb200_last_error(const rsb200_ctx* c) { return c ? c->er
 extern "C" uint64_t rsb200_kernel_launches(const rsb200_ctx* c) { return c ? c->launches : 0; }
 extern "C" int rsb200_device_sm_count(const rsb200_ctx* c) { return c ? c->sm_count : 0; }
 
+#ifdef RSB200_PHASE_TIMING
+// profiling builds only (tools/phase_timing.py): read/reset the per-phase cycle sums
+extern "C" int rsb200_debug_phase_cycles(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (out16 && cudaMemcpyFromSymbol(out16, rsb200::g_phase_cycles, 16 * sizeof(unsigned long long)) != cudaSuccess)
+    return RSB200_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(rsb200::g_phase_cycles, z, sizeof z) != cudaSuccess)
+      return RSB200_ERR_CUDA;
+  }
+  return RSB200_OK;
+}
+#endif
+
 // ------------------------------------------------------------------
 // unpack plan
 // ------------------------------------------------------------------
@@ -407,7 +422,9 @@ static bool build_dev_table(const rsb200_huff_table& h, DevTable& t) {
         const unsigned ssss = h.values[n];
         if (ssss > 16)
           return false;
-        if (l <= (unsigned)LUT_BITS) {
+        // SSSS = 16 stays out of the LUT: the decode loops resolve LUT hits with a
+        // branch-free extend() that only covers SSSS <= 15; the rare 16 takes the walk
+        if (l <= (unsigned)LUT_BITS && ssss != 16) {
           const unsigned total = l + (ssss == 16 ? (h.fix_dng16 ? 16u : 0u) : ssss);
           const uint16_t e = (uint16_t)(l | (ssss << 5) | (total << 10));
           const uint32_t lo = code << (LUT_BITS - l);

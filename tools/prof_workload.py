@@ -1,5 +1,5 @@
 """Small single-plan driver for ncu captures (profiling only, not a benchmark).
-    python tools/prof_workload.py ljpeg|ljpeg2|unpack|cr2 [reps]"""
+    python tools/prof_workload.py ljpeg|ljpeg2|unpack|cr2|cr2_4 [reps]"""
 import os
 import sys
 
@@ -47,6 +47,21 @@ elif what == "unpack":
         d_in[f * fb:f * fb + data.size] = torch.from_numpy(data)
     d_out = torch.zeros(F * ob, dtype=torch.uint8, device="cuda")
     args = (d_in, d_out)
+elif what in ("cr2", "cr2_4"):
+    from test_gpu_cr2 import cr2_job
+    cw, ch = 6720, 4480
+    cimg = port.new_image(cw, ch)
+    cimg[:, :cw] = synth.image_model(cw, ch, 4)
+    fmt, frame = ((2, 1, 1), (3360, 4480)) if what == "cr2" else ((4, 1, 1), (1680, 4480))
+    blob = port.cr2_encode(cimg, cw, fmt, frame, (3, 2240, 2240), 14, synth.default_tables(2),
+                           [0, 1, 0, 1][:fmt[0]])
+    ts = TableSet()
+    job = cr2_job(blob, cw, ch, fmt, (3, 2240, 2240), cimg.shape[1] * 2, ts)
+    plan = rs.cr2_plan(ctx, ts.tabs, [job])
+    d_in = torch.zeros(blob.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[:blob.size] = torch.from_numpy(blob)
+    d_out = torch.zeros(cimg.size * 2, dtype=torch.uint8, device="cuda")
+    args = ((d_in.data_ptr(), blob.size), d_out)
 else:
     raise SystemExit("unknown workload")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
