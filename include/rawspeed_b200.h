@@ -107,6 +107,54 @@ int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_job* jobs,
                               int njobs, rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* K1b: the remaining UncompressedDecompressor forms (fixed layouts).   */
+/*   decode8BitRaw<uncorrected>          UncompressedDecompressor.cpp:270-294 */
+/*   decode12BitRawWithControl<e>        UncompressedDecompressor.cpp:299-359 */
+/*   decode12BitRawUnpackedLeftAligned<e> UncompressedDecompressor.cpp:366-390 */
+/*   decodePackedFP<Pump, Binary16/24>   UncompressedDecompressor.cpp:171-186 */
+/*   32-bit float row copy               UncompressedDecompressor.cpp:214-224 */
+/* ------------------------------------------------------------------ */
+enum {
+  RSB200_RAW_8BIT = 1,             /* out = in byte (uncorrectedRawValues, or no table) */
+  RSB200_RAW_8BIT_TABLE = 2,       /* out = table[in byte] (RawImageDataU16::setWithLookUp,
+                                      common/RawImage.h:335-353; the dither counter of
+                                      decode8BitRaw starts at 0 and therefore stays 0, so
+                                      the dithered form is table[2*v] exactly)           */
+  RSB200_RAW_12BIT_CONTROL_BE = 3, /* 3 bytes -> 2 px, 1 control byte after every 10 px */
+  RSB200_RAW_12BIT_CONTROL_LE = 4,
+  RSB200_RAW_12BIT_LEFT_BE = 5,    /* 16-bit words, value = word >> 4                   */
+  RSB200_RAW_12BIT_LEFT_LE = 6,
+  RSB200_RAW_FP16_MSB = 7,         /* binary16 -> binary32 (common/FloatingPoint.h:116-160) */
+  RSB200_RAW_FP16_LSB = 8,
+  RSB200_RAW_FP24_MSB = 9,         /* binary24 -> binary32                              */
+  RSB200_RAW_FP24_LSB = 10,
+  RSB200_RAW_F32_COPY = 11         /* 32-bit rows copied as they are                    */
+};
+
+typedef struct {
+  uint64_t in_offset;  /* byte offset of the strip inside the input buffer          */
+  uint64_t in_size;    /* bytes of the strip (>= rows * in_pitch, checked)          */
+  uint64_t out_offset; /* byte offset of image row 0 inside the output buffer       */
+  int32_t out_pitch;   /* bytes between output rows                                 */
+  int32_t row0;        /* first output row                                          */
+  int32_t rows;
+  int32_t samples;     /* samples per row (w, or w*cpp for the float forms)         */
+  int32_t out_col0;    /* first output sample column (0 for the integer forms;
+                          offset.x for decodePackedFP, offset.x*cpp for the copy)   */
+  int32_t in_pitch;    /* bytes between input rows (8-bit: w; control: perline;
+                          left-aligned: 2w; float: inputPitchBytes)                 */
+  int32_t format;      /* RSB200_RAW_*                                              */
+  int32_t table;       /* RSB200_RAW_8BIT_TABLE: index into the plan's tables       */
+} rsb200_raw_job;
+
+/* `tables`: ntables x 65536 uint16 entries (TableLookUp::getTable content for the
+ * non-dithered form; for a dithered table pass entries 2*v, see above), may be
+ * NULL when no job uses RSB200_RAW_8BIT_TABLE.  Output samples are uint16 for
+ * formats 1-6 and 32-bit for 7-11. */
+int rsb200_raw_plan_create(rsb200_ctx* ctx, const rsb200_raw_job* jobs, int njobs,
+                           const uint16_t* tables, int ntables, rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
 /* K2+K3: lossless JPEG (Huffman + predictor 1).                        */
 /* ------------------------------------------------------------------ */
 typedef struct {

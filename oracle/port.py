@@ -184,6 +184,63 @@ def unpack(data, img, w, cpp, crop, in_pitch, bps, order):
     return img
 
 
+FORM_READ, FORM_8BIT, FORM_8BIT_UNCORRECTED = 0, 1, 2
+FORM_12BIT_CONTROL_BE, FORM_12BIT_CONTROL_LE, FORM_12BIT_LEFT_BE, FORM_12BIT_LEFT_LE = 3, 4, 5, 6
+
+
+def new_image_f32(w, h, cpp=1, fill=0xA5A5A5A5):
+    """Uncropped 32-bit buffer of an F32 RawImage (bpp = 4*cpp, pitch rounded to 16),
+    kept as uint32 so bit patterns (NaN payloads) compare exactly."""
+    pitch = (w * cpp * 4 + 15) // 16 * 16
+    return np.full((h, pitch // 4), fill, dtype=np.uint32)
+
+
+def build_table(curve, dither):
+    """TableLookUp::setTable (common/TableLookUp.cpp:48-85): the storage of table 0.
+    Non-dithered: 65536 entries t[i] = curve[min(i, n-1)].  Dithered: 2*65536 entries,
+    t[2i] = clampBits(center - (upper-lower+2)/4, 16), t[2i+1] = upper-lower."""
+    curve = np.asarray(curve, dtype=np.int64)
+    n = curve.size
+    assert 0 < n <= 65536
+    if not dither:
+        idx = np.minimum(np.arange(65536), n - 1)
+        return curve[idx].astype(np.uint16)
+    t = np.zeros(2 * 65536, dtype=np.uint16)
+    center = curve
+    lower = np.concatenate([curve[:1], curve[:-1]])
+    upper = np.concatenate([curve[1:], curve[-1:]])
+    lower = np.minimum(lower, center)
+    upper = np.maximum(upper, center)
+    delta = upper - lower
+    t[0:2 * n:2] = np.clip(center - ((upper - lower + 2) // 4), 0, 65535).astype(np.uint16)
+    t[1:2 * n:2] = delta.astype(np.uint16)
+    t[2 * n::2] = np.uint16(curve[-1])
+    return t
+
+
+def unpack_form(data, img, w, cpp, crop, in_pitch, bps, order, form, table=None,
+                dither=False):
+    """The other UncompressedDecompressor members (rso_unpack_form); `img` is a
+    uint16 image, or a uint32 array from new_image_f32 for the F32 forms."""
+    p, n = _u8(data)
+    is_f32 = img.dtype == np.uint32
+    assert img.flags.c_contiguous
+    im = Image(img.ctypes.data, w, img.shape[0], cpp, img.shape[1] * img.itemsize, 1, 1, 1)
+    tp = None
+    if table is not None:
+        table = np.ascontiguousarray(table, dtype=np.uint16)
+        tp = table.ctypes.data_as(C.POINTER(C.c_uint16))
+    e = Err()
+    L = lib()
+    L.rso_unpack_form.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(Image), C.c_int] + \
+        [C.c_int] * 8 + [C.POINTER(C.c_uint16), C.c_int, C.POINTER(Err)]
+    rc = L.rso_unpack_form(p, C.c_uint32(n), C.byref(im), int(is_f32), crop[0], crop[1],
+                           crop[2], crop[3], in_pitch, bps, order, form, tp, int(dither),
+                           C.byref(e))
+    e.check(rc)
+    return img
+
+
 def ljpeg_decompress(img, w, cpp, img_frame, mcu, frame_dim, hts, init_pred,
                      rows_per_restart, data):
     p, n = _u8(data)

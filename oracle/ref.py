@@ -112,6 +112,30 @@ def unpack(data, img, w, cpp, crop, in_pitch, bps, order, reps=1):
     return ms.value
 
 
+def unpack_form(data, img, w, cpp, crop, in_pitch, bps, order, form, curve=None,
+                dither=False, reps=1):
+    """Reference UncompressedDecompressor members other than the packed-int read
+    (ref_unpack_form): img uint16, or uint32 (= F32 image bit patterns)."""
+    p, n = _u8(data)
+    ms = C.c_double(0)
+    e = Err()
+    cp, nc = None, 0
+    if curve is not None:
+        curve = np.ascontiguousarray(curve, dtype=np.uint16)
+        cp, nc = curve.ctypes.data_as(C.POINTER(C.c_uint16)), curve.size
+    L = lib()
+    L.ref_unpack_form.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p] + [C.c_int] * 13 + \
+        [C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+         C.POINTER(Err)]
+    rc = L.ref_unpack_form(p, C.c_uint32(n), C.c_void_p(img.ctypes.data),
+                           int(img.dtype == np.uint32), w, img.shape[0], cpp,
+                           img.shape[1] * img.itemsize, crop[0], crop[1], crop[2], crop[3],
+                           in_pitch, bps, order, form, cp, nc, int(dither), reps,
+                           C.byref(ms), C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
 def ljpeg_decompress(img, w, cpp, img_frame, mcu, frame_dim, tabs, tab_of_comp,
                      init_pred, rows_per_restart, data, fix16=False):
     p, n = _u8(data)

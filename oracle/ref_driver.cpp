@@ -245,6 +245,58 @@ int ref_unpack(const uint8_t* in, uint32_t in_size, uint16_t* img_data, int w,
   });
 }
 
+// UncompressedDecompressor: the members other than readUncompressedRaw() on a
+// uint16 image.  form: 0 readUncompressedRaw (is_f32: F32 image), 1/2
+// decode8BitRaw<false/true>, 3/4 decode12BitRawWithControl<big/little>, 5/6
+// decode12BitRawUnpackedLeftAligned<big/little>.  curve != nullptr ->
+// mRaw->setTable(curve, dither) first (RawImage.cpp setTable / TableLookUp.cpp).
+int ref_unpack_form(const uint8_t* in, uint32_t in_size, void* img_data, int is_f32,
+                    int w, int h, int cpp, int pitch, int crop_x, int crop_y, int crop_w,
+                    int crop_h, int in_pitch, int bps, int order, int form,
+                    const uint16_t* curve, int ncurve, int dither, int reps,
+                    double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = RawImage::create(iPoint2D(w, h),
+                                    is_f32 ? RawImageType::F32 : RawImageType::UINT16, cpp);
+    const int bpp = (is_f32 ? 4 : 2) * cpp;
+    auto rowPtr = [&](int r) {
+      if (is_f32)
+        return reinterpret_cast<uint8_t*>(&img->getF32DataAsUncroppedArray2DRef()(r, 0));
+      return reinterpret_cast<uint8_t*>(&img->getU16DataAsUncroppedArray2DRef()(r, 0));
+    };
+    for (int r = 0; r < h; ++r)
+      std::memcpy(rowPtr(r), static_cast<const uint8_t*>(img_data) + static_cast<size_t>(r) * pitch,
+                  static_cast<size_t>(w) * bpp);
+    if (curve)
+      img->setTable(std::vector<uint16_t>(curve, curve + ncurve), dither != 0);
+    double best = 1e30;
+    for (int rep = 0; rep < (reps < 1 ? 1 : reps); ++rep) {
+      const auto t0 = std::chrono::steady_clock::now();
+      UncompressedDecompressor u(
+          ByteStream(DataBuffer(Buffer(in, in_size), Endianness::little)), img,
+          iRectangle2D({crop_x, crop_y}, {crop_w, crop_h}), in_pitch, bps,
+          static_cast<BitOrder>(order));
+      switch (form) {
+      case 0: u.readUncompressedRaw(); break;
+      case 1: u.decode8BitRaw<false>(); break;
+      case 2: u.decode8BitRaw<true>(); break;
+      case 3: u.decode12BitRawWithControl<Endianness::big>(); break;
+      case 4: u.decode12BitRawWithControl<Endianness::little>(); break;
+      case 5: u.decode12BitRawUnpackedLeftAligned<Endianness::big>(); break;
+      case 6: u.decode12BitRawUnpackedLeftAligned<Endianness::little>(); break;
+      default: ThrowRDE("unknown form");
+      }
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    for (int r = 0; r < h; ++r)
+      std::memcpy(static_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, rowPtr(r),
+                  static_cast<size_t>(w) * bpp);
+  });
+}
+
 struct RefHuffDesc {
   uint8_t ncpl[16];
   uint8_t values[162];

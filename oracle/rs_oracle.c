@@ -554,10 +554,48 @@ int rso_huff_decode(const rso_huff* h, int order, const uint8_t* data, int size,
 /* ------------------------------------------------------------------ */
 /* UncompressedDecompressor                                            */
 /* ------------------------------------------------------------------ */
+/* extendBinaryFloatingPoint<Narrow, Binary32> (common/FloatingPoint.h:116-160);
+ * fw/ew = fraction/exponent widths of the narrow type */
+static uint32_t fp_extend(uint32_t narrow, int fw, int ew) {
+  uint32_t sign = (narrow >> (fw + ew)) & 1u;
+  uint32_t ne = (narrow >> fw) & ((1u << ew) - 1u);
+  uint32_t nf = narrow & ((1u << fw) - 1u);
+  int32_t bias = (1 << (ew - 1)) - 1;
+  uint32_t we = (uint32_t)((int32_t)ne - bias + 127);
+  uint32_t wf = nf << (23 - fw);
+  if (ne == ((1u << ew) - 1u)) {
+    we = 255; /* infinity or NaN; the fraction is kept/widened */
+  } else if (ne == 0) {
+    if (nf == 0) {
+      we = 0;
+      wf = 0;
+    } else {
+      we = (uint32_t)(1 - bias + 127);
+      while (!(wf & (1u << 23))) {
+        we -= 1;
+        wf <<= 1;
+      }
+      wf &= (1u << 23) - 1u;
+    }
+  }
+  return (sign << 31) | (we << 23) | wf;
+}
+
+/* sanityCheck(const uint32_t* h, int bytesPerLine) (UncompressedDecompressor.cpp:52-74) */
+static void unpack_sanity(rso_ctx* c, const bstream* input, uint32_t h, uint32_t bpl) {
+  uint32_t fullRows = bs_remain(input) / bpl;
+  if (fullRows >= h)
+    return;
+  if (fullRows == 0)
+    THROW_IOE(c, "Not enough data to decode a single line. Image file truncated.");
+  THROW_IOE(c, "Image truncated, only %u of %u lines found", fullRows, h);
+}
+
 static void unpack_impl(rso_ctx* c, const uint8_t* in_data, uint32_t in_size,
                         rso_image* img, int crop_x, int crop_y, int crop_w,
                         int crop_h, int inputPitchBytes, int bitPerPixel,
-                        int order) {
+                        int order, int f32, int form, const uint16_t* table,
+                        int table_dither) {
   /* ctor: UncompressedDecompressor.cpp:106-169 */
   bstream all, input;
   uint32_t w, h, cpp;
@@ -587,7 +625,7 @@ static void unpack_impl(rso_ctx* c, const uint8_t* in_data, uint32_t in_size,
   oy = (uint64_t)crop_y;
   if (cpp < 1 || cpp > 3)
     THROW_RDE(c, "Unsupported number of components per pixel: %u", cpp);
-  if (bitPerPixel < 1 || bitPerPixel > 32 || bitPerPixel > 16 /* UINT16 image */)
+  if (bitPerPixel < 1 || bitPerPixel > 32 || (bitPerPixel > 16 && !f32 /* UINT16 image */))
     THROW_RDE(c, "Unsupported bit depth");
   outPixelBits = (uint64_t)w * cpp * (uint64_t)bitPerPixel;
   if (outPixelBits % 8 != 0)
@@ -611,6 +649,125 @@ static void unpack_impl(rso_ctx* c, const uint8_t* in_data, uint32_t in_size,
     THROW_RDE(c, "Invalid y offset");
   if (ox + (uint64_t)crop_w > (uint64_t)img->w)
     THROW_RDE(c, "Invalid x offset");
+
+  if (form != RSO_FORM_READ) {
+    /* the fixed-layout members; all write out(row, col) from (0,0) and use only
+     * `size` (UncompressedDecompressor.cpp:270-390) */
+    uint32_t row, col;
+    if (form == RSO_FORM_8BIT || form == RSO_FORM_8BIT_UNCORRECTED) {
+      /* decode8BitRaw<uncorrected> (:270-294); setWithLookUp (RawImage.h:335-353) */
+      uint32_t random = 0;
+      unpack_sanity(c, &input, h, 1u * w);
+      if ((uint64_t)w * h > bs_remain(&input))
+        THROW_IOE(c, "Buffer overflow: image file may be truncated");
+      for (row = 0; row < h; row++) {
+        uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch);
+        for (col = 0; col < w; col++) {
+          uint16_t value = input.data[(size_t)row * w + col];
+          if (form == RSO_FORM_8BIT_UNCORRECTED || !table) {
+            o[col] = value;
+          } else if (table_dither) {
+            uint32_t base = table[2 * value + 0], delta = table[2 * value + 1];
+            uint32_t r = random;
+            uint32_t pix = base + ((delta * (r & 2047) + 1024) >> 12);
+            random = 15700 * (r & 65535) + (r >> 16);
+            o[col] = (uint16_t)pix;
+          } else {
+            o[col] = table[value];
+          }
+        }
+      }
+      return;
+    }
+    if (form == RSO_FORM_12BIT_CONTROL_BE || form == RSO_FORM_12BIT_CONTROL_LE) {
+      /* decode12BitRawWithControl<e> (:299-359), bytesPerLine (:86-104) */
+      const int little = form == RSO_FORM_12BIT_CONTROL_LE;
+      uint32_t perline, x;
+      if ((12 * w) % 8 != 0)
+        THROW_IOE(c, "Bad image width");
+      perline = (12 * w) / 8 + ((w + 2) / 10);
+      unpack_sanity(c, &input, h, perline);
+      if ((uint64_t)perline * h > bs_remain(&input))
+        THROW_IOE(c, "Buffer overflow: image file may be truncated");
+      for (row = 0; row < h; row++) {
+        const uint8_t* in = input.data + (size_t)row * perline;
+        uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch);
+        col = 0;
+        for (x = 0; x < w; x += 2) {
+          uint32_t g1 = in[col + 0], g2 = in[col + 1], g3 = in[col + 2];
+          /* process(x, invert=false, g1, g2); process(x+1, invert=true, g3, g2) */
+          if (!little) {
+            o[x] = (uint16_t)((g1 << 4) | (g2 >> 4));
+            o[x + 1] = (uint16_t)(((g2 & 0x0f) << 8) | g3);
+          } else {
+            o[x] = (uint16_t)(((g2 & 0x0f) << 8) | g1);
+            o[x + 1] = (uint16_t)((g3 << 4) | (g2 >> 4));
+          }
+          col += 3;
+          if ((x % 10) == 8)
+            col++;
+        }
+      }
+      return;
+    }
+    if (form == RSO_FORM_12BIT_LEFT_BE || form == RSO_FORM_12BIT_LEFT_LE) {
+      /* decode12BitRawUnpackedLeftAligned<e> (:366-390) */
+      unpack_sanity(c, &input, h, 2u * w);
+      if ((uint64_t)w * h * 2 > bs_remain(&input))
+        THROW_IOE(c, "Buffer overflow: image file may be truncated");
+      for (row = 0; row < h; row++) {
+        const uint8_t* in = input.data + (size_t)row * 2 * w;
+        uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch);
+        for (col = 0; col < w; ++col) {
+          uint32_t g1 = in[2 * col], g2 = in[2 * col + 1];
+          uint16_t pix = form == RSO_FORM_12BIT_LEFT_LE ? (uint16_t)((g2 << 8) | g1)
+                                                        : (uint16_t)((g1 << 8) | g2);
+          o[col] = pix >> 4;
+        }
+      }
+      return;
+    }
+    THROW_RDE(c, "unknown form");
+  }
+
+  if (f32) {
+    /* readUncompressedRaw, F32 image (:214-247) */
+    uint64_t y = oy, hh = h + oy;
+    int rows, row;
+    if (hh > (uint64_t)img->h)
+      hh = (uint64_t)img->h;
+    rows = (int)hh;
+    row = (int)y;
+    if (bitPerPixel == 32) {
+      int r;
+      uint64_t need = (uint64_t)inputPitchBytes * (uint64_t)(rows - row);
+      if (need > bs_remain(&input))
+        THROW_IOE(c, "Buffer overflow: image file may be truncated");
+      for (r = row; r < rows; ++r)
+        memcpy((uint8_t*)img->data + (size_t)r * (size_t)img->pitch +
+                   (size_t)crop_x * cpp * 4,
+               input.data + (size_t)(r - row) * (size_t)inputPitchBytes,
+               (size_t)w * cpp * 4);
+      return;
+    }
+    if ((order == RSO_MSB || order == RSO_LSB) && (bitPerPixel == 16 || bitPerPixel == 24)) {
+      /* decodePackedFP<Pump, Binary16/24> (:171-186): out(row, offset.x + col) */
+      pump bits;
+      int cols = crop_w * (int)cpp, x;
+      pump_init(&bits, c, order, input.data, (int)bs_remain(&input));
+      for (; row < rows; row++) {
+        uint32_t* o = (uint32_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch);
+        for (x = 0; x < cols; x++) {
+          uint32_t b = pump_get_bits(&bits, bitPerPixel);
+          o[crop_x + x] = bitPerPixel == 16 ? fp_extend(b, 10, 5) : fp_extend(b, 16, 7);
+        }
+        pump_skip_bytes(&bits, (int)skipBytes);
+      }
+      return;
+    }
+    THROW_RDE(c, "Unsupported floating-point input bitwidth/bit packing: %d / %u",
+              bitPerPixel, (unsigned)order);
+  }
 
   /* readUncompressedRaw: UncompressedDecompressor.cpp:202-268 */
   {
@@ -656,7 +813,17 @@ int rso_unpack(const uint8_t* in, uint32_t in_size, rso_image* img, int crop_x,
                int order, rso_err* e) {
   RSO_ENTER(c, e);
   unpack_impl(&c, in, in_size, img, crop_x, crop_y, crop_w, crop_h, in_pitch,
-              bps, order);
+              bps, order, 0, RSO_FORM_READ, NULL, 0);
+  return RSO_OK;
+}
+
+int rso_unpack_form(const uint8_t* in, uint32_t in_size, rso_image* img, int is_f32,
+                    int crop_x, int crop_y, int crop_w, int crop_h, int in_pitch, int bps,
+                    int order, int form, const uint16_t* table, int table_dither,
+                    rso_err* e) {
+  RSO_ENTER(c, e);
+  unpack_impl(&c, in, in_size, img, crop_x, crop_y, crop_w, crop_h, in_pitch,
+              bps, order, is_f32, form, table, table_dither);
   return RSO_OK;
 }
 
@@ -1278,7 +1445,7 @@ int rso_dng_decompress(const uint8_t* file, uint64_t file_size,
           THROW_RDE(&c, "Data input pitch is too short. Can not decode!");
         unpack_impl(&c, file + tile_off[n], tile_len[n], img, (int)offX,
                     (int)offY, (int)width, (int)height, inputPitch, bps,
-                    be ? RSO_MSB : RSO_LSB);
+                    be ? RSO_MSB : RSO_LSB, 0, RSO_FORM_READ, NULL, 0);
       }
     }
     if (d) {

@@ -83,6 +83,30 @@ int rso_unpack(const uint8_t* in, uint32_t in_size, rso_image* img, int crop_x,
                int crop_y, int crop_w, int crop_h, int in_pitch, int bps,
                int order, rso_err* e);
 
+/* The other members of UncompressedDecompressor (same constructor, then one of):
+ *   RSO_FORM_READ               readUncompressedRaw() (with is_f32: the F32 image
+ *                               branches, UncompressedDecompressor.cpp:214-247:
+ *                               32-bit row copy, decodePackedFP<MSB/LSB, Binary16/24>)
+ *   RSO_FORM_8BIT[_UNCORRECTED] decode8BitRaw<false/true>()            (:270-294)
+ *   RSO_FORM_12BIT_CONTROL_*    decode12BitRawWithControl<big/little>() (:299-359)
+ *   RSO_FORM_12BIT_LEFT_*       decode12BitRawUnpackedLeftAligned<e>()  (:366-390)
+ * For an F32 image `img->data` points at 32-bit samples (pitch in bytes, bpp 4*cpp).
+ * `table` = TableLookUp::tables of table 0 (65536 entries, or 2*65536 when
+ * dithered: common/TableLookUp.cpp:40-85), NULL = RawImageData::table == nullptr. */
+enum {
+  RSO_FORM_READ = 0,
+  RSO_FORM_8BIT = 1,
+  RSO_FORM_8BIT_UNCORRECTED = 2,
+  RSO_FORM_12BIT_CONTROL_BE = 3,
+  RSO_FORM_12BIT_CONTROL_LE = 4,
+  RSO_FORM_12BIT_LEFT_BE = 5,
+  RSO_FORM_12BIT_LEFT_LE = 6
+};
+int rso_unpack_form(const uint8_t* in, uint32_t in_size, rso_image* img, int is_f32,
+                    int crop_x, int crop_y, int crop_w, int crop_h, int in_pitch, int bps,
+                    int order, int form, const uint16_t* table, int table_dither,
+                    rso_err* e);
+
 /* ---- LJpegDecompressor (decompressors/LJpegDecompressor.cpp:52-370) ---- */
 typedef struct {
   int mcu_x, mcu_y; /* Frame::mcu */

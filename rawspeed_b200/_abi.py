@@ -19,6 +19,19 @@ class UnpackJob(C.Structure):
                 ("order", C.c_int32)]
 
 
+class RawJob(C.Structure):
+    _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint64),
+                ("out_offset", C.c_uint64), ("out_pitch", C.c_int32),
+                ("row0", C.c_int32), ("rows", C.c_int32), ("samples", C.c_int32),
+                ("out_col0", C.c_int32), ("in_pitch", C.c_int32), ("format", C.c_int32),
+                ("table", C.c_int32)]
+
+
+(RAW_8BIT, RAW_8BIT_TABLE, RAW_12BIT_CONTROL_BE, RAW_12BIT_CONTROL_LE, RAW_12BIT_LEFT_BE,
+ RAW_12BIT_LEFT_LE, RAW_FP16_MSB, RAW_FP16_LSB, RAW_FP24_MSB, RAW_FP24_LSB,
+ RAW_F32_COPY) = range(1, 12)
+
+
 class HuffTable(C.Structure):
     _fields_ = [("ncodes_per_len", C.c_uint8 * 16), ("values", C.c_uint8 * 162),
                 ("nvalues", C.c_uint16), ("fix_dng16", C.c_uint8),
@@ -52,6 +65,7 @@ class Cr2Job(C.Structure):
 EXPORTS = [
     "rsb200_abi_version", "rsb200_create", "rsb200_destroy", "rsb200_last_error",
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
+    "rsb200_raw_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",
@@ -86,6 +100,8 @@ def load():
     L.rsb200_kernel_launches.restype = u64
     L.rsb200_device_sm_count.argtypes = [vp]
     L.rsb200_unpack_plan_create.argtypes = [vp, C.POINTER(UnpackJob), i32, C.POINTER(vp)]
+    L.rsb200_raw_plan_create.argtypes = [vp, C.POINTER(RawJob), i32, C.POINTER(C.c_uint16),
+                                         i32, C.POINTER(vp)]
     L.rsb200_ljpeg_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,
                                            C.POINTER(LJpegScan), i32, C.POINTER(vp)]
     L.rsb200_cr2_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,

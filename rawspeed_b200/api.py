@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Cr2Job, HuffTable, LJpegScan, ScanResult, UnpackJob,  # noqa: F401
+from ._abi import (Cr2Job, HuffTable, LJpegScan, RawJob, ScanResult, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -146,6 +146,19 @@ def unpack_plan(ctx, jobs):
     arr = (UnpackJob * len(jobs))(*jobs)
     h = C.c_void_p()
     ctx.check(ctx._lib.rsb200_unpack_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def raw_plan(ctx, jobs, tables=None):
+    """Plan over the fixed-layout UncompressedDecompressor forms (RAW_* formats).
+    tables: array (ntables, 65536) uint16 for RAW_8BIT_TABLE jobs, or None."""
+    arr = (RawJob * len(jobs))(*jobs)
+    h = C.c_void_p()
+    tp, nt = None, 0
+    if tables is not None:
+        tables = np.ascontiguousarray(tables, dtype=np.uint16).reshape(-1, 65536)
+        tp, nt = tables.ctypes.data_as(C.POINTER(C.c_uint16)), tables.shape[0]
+    ctx.check(ctx._lib.rsb200_raw_plan_create(ctx.h, arr, len(jobs), tp, nt, C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

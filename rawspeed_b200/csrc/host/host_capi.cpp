@@ -85,6 +85,40 @@ int rsb200h_unpack(const uint8_t* in, uint32_t in_size, uint16_t* img_data, int 
   });
 }
 
+// The other UncompressedDecompressor members.  form: 0 readUncompressedRaw (is_f32: on
+// an F32 image), 1/2 decode8BitRaw<false/true>, 3/4 decode12BitRawWithControl<big/
+// little>, 5/6 decode12BitRawUnpackedLeftAligned<big/little>; curve != NULL ->
+// mRaw->setTable(curve, dither) first.
+int rsb200h_unpack_form(const uint8_t* in, uint32_t in_size, void* img_data, int is_f32, int w,
+                        int h, int cpp, int pitch, int crop_x, int crop_y, int crop_w,
+                        int crop_h, int in_pitch, int bps, int order, int form,
+                        const uint16_t* curve, int ncurve, int dither, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = RawImage::create(iPoint2D(w, h),
+                                    is_f32 ? RawImageType::F32 : RawImageType::UINT16,
+                                    (uint32_t)cpp);
+    if (img->pitch != pitch)
+      ThrowRDE("test harness: pitch mismatch (%d vs %d)", img->pitch, pitch);
+    std::memcpy(img->getByteData(), img_data, (size_t)pitch * h);
+    if (curve)
+      img->setTable(std::vector<uint16_t>(curve, curve + ncurve), dither != 0);
+    UncompressedDecompressor u(ByteStream(in, in_size), img,
+                               iRectangle2D(crop_x, crop_y, crop_w, crop_h), in_pitch, bps,
+                               static_cast<BitOrder>(order));
+    switch (form) {
+    case 0: u.readUncompressedRaw(); break;
+    case 1: u.decode8BitRaw<false>(); break;
+    case 2: u.decode8BitRaw<true>(); break;
+    case 3: u.decode12BitRawWithControl<Endianness::big>(); break;
+    case 4: u.decode12BitRawWithControl<Endianness::little>(); break;
+    case 5: u.decode12BitRawUnpackedLeftAligned<Endianness::big>(); break;
+    case 6: u.decode12BitRawUnpackedLeftAligned<Endianness::little>(); break;
+    default: ThrowRDE("unknown form");
+    }
+    std::memcpy(img_data, img->getByteData(), img->getByteSize());
+  });
+}
+
 int rsb200h_ljpeg_decompress(uint16_t* img_data, int w, int h, int cpp, int pitch, int fx, int fy,
                              int fw, int fh, int mcu_x, int mcu_y, int dim_x, int dim_y,
                              const rsb200h_huff* tabs, const int* tab_of_comp,

@@ -119,15 +119,46 @@ std::vector<std::string> RawImageData::getErrors() {
 }
 
 RawImage RawImage::create(const iPoint2D& dim, RawImageType type, uint32_t cpp) {
-  if (type != RawImageType::UINT16)
-    ThrowRDE("rawspeed_b200: only UINT16 images are on the accelerated path");
   RawImage r;
   r.p_ = std::make_shared<RawImageData>();
   r.p_->dim = dim;
+  r.p_->dataType = type;
   r.p_->cpp = cpp;
-  r.p_->bpp = 2 * cpp;
+  r.p_->bpp = (type == RawImageType::F32 ? 4u : 2u) * cpp; // RawImageDataFloat / U16 ctors
   r.p_->createData();
   return r;
+}
+
+// TableLookUp::TableLookUp(1, dither) + setTable(0, table) (common/TableLookUp.cpp:40-85)
+void RawImageData::setTable(const std::vector<uint16_t>& table, bool dither) {
+  constexpr int MAXE = 65536;
+  const int nfilled = (int)table.size();
+  if (nfilled == 0)
+    ThrowRDE("Table lookup with 0 entries is unsupported");
+  if (nfilled > MAXE)
+    ThrowRDE("Table lookup with %i entries is unsupported", nfilled);
+  ditherTable = dither;
+  tableStorage.assign((size_t)MAXE * 2, 0);
+  if (!dither) {
+    for (int i = 0; i < MAXE; ++i)
+      tableStorage[i] = (i < nfilled) ? table[i] : table[nfilled - 1];
+    return;
+  }
+  for (int i = 0; i < nfilled; ++i) {
+    const int center = table[i];
+    int lower = i > 0 ? table[i - 1] : center;
+    int upper = i < (nfilled - 1) ? table[i + 1] : center;
+    lower = std::min(lower, center); // non-monotonic LUT: no interpolation across the cross-over
+    upper = std::max(upper, center);
+    const int delta = upper - lower;
+    const int base = center - ((upper - lower + 2) / 4);
+    tableStorage[(size_t)i * 2] = (uint16_t)std::min(std::max(base, 0), 65535);
+    tableStorage[(size_t)i * 2 + 1] = (uint16_t)delta;
+  }
+  for (int i = nfilled; i < MAXE; ++i) {
+    tableStorage[(size_t)i * 2] = table[nfilled - 1];
+    tableStorage[(size_t)i * 2 + 1] = 0;
+  }
 }
 
 // ------------------------------------------------------------------ Huffman
@@ -218,7 +249,8 @@ UncompressedDecompressor::UncompressedDecompressor(ByteStream input_, RawImage i
   const uint64_t ox = offset.x, oy = offset.y;
   if (cpp < 1 || cpp > 3)
     ThrowRDE("Unsupported number of components per pixel: %u", cpp);
-  if (bitPerPixel < 1 || bitPerPixel > 32 || bitPerPixel > 16)
+  if (bitPerPixel < 1 || bitPerPixel > 32 ||
+      (bitPerPixel > 16 && mRaw->getDataType() == RawImageType::UINT16))
     ThrowRDE("Unsupported bit depth");
   const uint64_t outPixelBits = (uint64_t)w * cpp * bitPerPixel;
   if (outPixelBits % 8 != 0)
@@ -267,7 +299,124 @@ bool UncompressedDecompressor::describe(const uint8_t* fileBase, rsb200_unpack_j
   return true;
 }
 
+// sanityCheck(const uint32_t* h, int bytesPerLine) (UncompressedDecompressor.cpp:52-74)
+void UncompressedDecompressor::sanityCheck(uint32_t h, int bytesPerLine) const {
+  const uint32_t fullRows = input.getRemainSize() / (uint32_t)bytesPerLine;
+  if (fullRows >= h)
+    return;
+  if (fullRows == 0)
+    ThrowIOE("Not enough data to decode a single line. Image file truncated.");
+  ThrowIOE("Image truncated, only %u of %u lines found", fullRows, h);
+}
+
+// one device job over the whole stream for a fixed-layout form
+void UncompressedDecompressor::runFixed(int format, uint32_t w, uint32_t h,
+                                        uint32_t bytesPerLine) {
+  if ((uint64_t)bytesPerLine * h > input.getRemainSize()) // ByteStream::getData
+    ThrowIOE("Buffer overflow: image file may be truncated");
+  rsb200_raw_job job;
+  std::memset(&job, 0, sizeof job);
+  job.in_offset = 0;
+  job.in_size = input.getRemainSize();
+  job.out_pitch = mRaw->pitch;
+  job.rows = (int32_t)h;
+  job.samples = (int32_t)w;
+  job.in_pitch = (int32_t)bytesPerLine;
+  job.format = format;
+  PlanGuard pg;
+  const uint16_t* tables = nullptr;
+  std::vector<uint16_t> dev;
+  if (format == RSB200_RAW_8BIT_TABLE) {
+    // dithered table: decode8BitRaw's dither counter starts at 0 and the update
+    // 15700*(r&65535)+(r>>16) keeps it there, so pix == base == tables[2*v]
+    // (RawImage.h:335-353); the device gets one 65536-entry table either way
+    const std::vector<uint16_t>& t = mRaw->tableData();
+    dev.resize(65536);
+    for (int i = 0; i < 65536; ++i)
+      dev[i] = mRaw->tableDither() ? t[(size_t)2 * i] : t[i];
+    tables = dev.data();
+  }
+  engineCheck(rsb200_raw_plan_create(engine(), &job, 1, tables, tables ? 1 : 0, &pg.p),
+              "rsb200_raw_plan_create");
+  runOnImage(pg.p, input.begin(), input.getRemainSize(), mRaw, /*partial=*/true);
+}
+
+template <bool uncorrectedRawValues> void UncompressedDecompressor::decode8BitRaw() {
+  const uint32_t w = size.x, h = size.y;
+  sanityCheck(h, (int)w);
+  const bool lut = !uncorrectedRawValues && mRaw->hasTable();
+  runFixed(lut ? RSB200_RAW_8BIT_TABLE : RSB200_RAW_8BIT, w, h, w);
+}
+template void UncompressedDecompressor::decode8BitRaw<false>();
+template void UncompressedDecompressor::decode8BitRaw<true>();
+
+template <Endianness e> void UncompressedDecompressor::decode12BitRawWithControl() {
+  const uint32_t w = size.x, h = size.y;
+  if ((12 * w) % 8 != 0) // bytesPerLine (UncompressedDecompressor.cpp:86-104)
+    ThrowIOE("Bad image width");
+  const uint32_t perline = (12 * w) / 8 + ((w + 2) / 10);
+  sanityCheck(h, (int)perline);
+  runFixed(e == Endianness::big ? RSB200_RAW_12BIT_CONTROL_BE : RSB200_RAW_12BIT_CONTROL_LE, w, h,
+           perline);
+}
+template void UncompressedDecompressor::decode12BitRawWithControl<Endianness::little>();
+template void UncompressedDecompressor::decode12BitRawWithControl<Endianness::big>();
+
+template <Endianness e> void UncompressedDecompressor::decode12BitRawUnpackedLeftAligned() {
+  const uint32_t w = size.x, h = size.y;
+  sanityCheck(h, (int)(2 * w));
+  runFixed(e == Endianness::big ? RSB200_RAW_12BIT_LEFT_BE : RSB200_RAW_12BIT_LEFT_LE, w, h, 2 * w);
+}
+template void UncompressedDecompressor::decode12BitRawUnpackedLeftAligned<Endianness::little>();
+template void UncompressedDecompressor::decode12BitRawUnpackedLeftAligned<Endianness::big>();
+
+// readUncompressedRaw() on an F32 image (UncompressedDecompressor.cpp:214-247)
+void UncompressedDecompressor::readF32() {
+  const uint32_t cpp = mRaw->getCpp();
+  const uint64_t oy = offset.y;
+  const uint64_t hEnd = std::min<uint64_t>((uint64_t)size.y + oy, (uint64_t)mRaw->dim.y);
+  int format;
+  int32_t col0;
+  if (bitPerPixel == 32) {
+    format = RSB200_RAW_F32_COPY;
+    col0 = (int32_t)(offset.x * (int)cpp);
+    if ((uint64_t)inputPitchBytes * (hEnd - oy) > input.getRemainSize())
+      ThrowIOE("Buffer overflow: image file may be truncated");
+  } else if ((order == BitOrder::MSB || order == BitOrder::LSB) &&
+             (bitPerPixel == 16 || bitPerPixel == 24)) {
+    const bool msb = order == BitOrder::MSB;
+    format = bitPerPixel == 16 ? (msb ? RSB200_RAW_FP16_MSB : RSB200_RAW_FP16_LSB)
+                               : (msb ? RSB200_RAW_FP24_MSB : RSB200_RAW_FP24_LSB);
+    col0 = (int32_t)offset.x; // decodePackedFP: out(row, offset.x + col)
+    if (input.getRemainSize() < 4) // BitStreamer ctor (BitStreamer.h:56-60)
+      ThrowIOE("Bit stream size is smaller than MaxProcessBytes");
+  } else {
+    ThrowRDE("Unsupported floating-point input bitwidth/bit packing: %d / %u", bitPerPixel,
+             (unsigned)order);
+  }
+  if (hEnd <= oy)
+    return;
+  rsb200_raw_job job;
+  std::memset(&job, 0, sizeof job);
+  job.in_size = input.getRemainSize();
+  job.out_pitch = mRaw->pitch;
+  job.row0 = (int32_t)oy;
+  job.rows = (int32_t)(hEnd - oy);
+  job.samples = (int32_t)(size.x * (int)cpp);
+  job.out_col0 = col0;
+  job.in_pitch = inputPitchBytes;
+  job.format = format;
+  PlanGuard pg;
+  engineCheck(rsb200_raw_plan_create(engine(), &job, 1, nullptr, 0, &pg.p),
+              "rsb200_raw_plan_create");
+  runOnImage(pg.p, input.begin(), input.getRemainSize(), mRaw, /*partial=*/true);
+}
+
 void UncompressedDecompressor::readUncompressedRaw() {
+  if (mRaw->getDataType() == RawImageType::F32) {
+    readF32();
+    return;
+  }
   rsb200_unpack_job job;
   if (!describe(input.begin(), &job))
     return;

@@ -179,7 +179,14 @@ public:
   iPoint2D subsampling{1, 1}; // ImageMetaData::subsampling
   uint32_t getCpp() const { return cpp; }
   uint32_t getBpp() const { return bpp; }
-  RawImageType getDataType() const { return RawImageType::UINT16; }
+  RawImageType getDataType() const { return dataType; }
+  // RawImageData::setTable(table, dither) -> TableLookUp (common/TableLookUp.cpp:40-85)
+  void setTable(const std::vector<uint16_t>& table_, bool dither);
+  void clearTable() { tableStorage.clear(); }
+  bool hasTable() const { return !tableStorage.empty(); }
+  bool tableDither() const { return ditherTable; }
+  // TableLookUp::tables of table 0: 65536 entries, or 2*65536 {base, delta} when dithered
+  const std::vector<uint16_t>& tableData() const { return tableStorage; }
   void setCpp(uint32_t v);
   void createData(); // pitch = roundUp(dim.x*bpp, 16) (RawImage.cpp:68-113)
   bool isAllocated() const { return !data.empty(); }
@@ -194,6 +201,9 @@ public:
 private:
   friend class RawImage;
   uint32_t cpp = 1, bpp = 2;
+  RawImageType dataType = RawImageType::UINT16;
+  std::vector<uint16_t> tableStorage;
+  bool ditherTable = false;
   std::vector<uint8_t> data;
   uint8_t* storage = nullptr; // 16-byte aligned start inside `data`
   std::mutex errMutex;
@@ -253,10 +263,18 @@ public:
   UncompressedDecompressor(ByteStream input, RawImage img, const iRectangle2D& crop,
                            int inputPitchBytes, int bitPerPixel, BitOrder order);
   void readUncompressedRaw();
+  // the fixed-layout members (UncompressedDecompressor.cpp:270-390); all write the
+  // image from (0,0) and use only the crop's size, like the reference
+  template <bool uncorrectedRawValues> void decode8BitRaw();
+  template <Endianness e> void decode12BitRawWithControl();
+  template <Endianness e> void decode12BitRawUnpackedLeftAligned();
   // batch support (AbstractDngDecompressor): describe instead of decode
   bool describe(const uint8_t* fileBase, rsb200_unpack_job* job) const;
 
 private:
+  void sanityCheck(uint32_t h, int bytesPerLine) const;
+  void runFixed(int format, uint32_t w, uint32_t h, uint32_t bytesPerLine);
+  void readF32();
   ByteStream input;
   RawImage mRaw;
   iPoint2D size, offset;

@@ -7,6 +7,7 @@
 #include "ljpeg.cuh"
 #include "ljpeg_fused.cuh"
 #include "ljpeg_ranges.cuh"
+#include "rawforms.cuh"
 #include "unpack.cuh"
 
 #include <algorithm>
@@ -61,6 +62,13 @@ struct UnpackGroup {
   uint32_t nblocks = 0;
 };
 
+struct RawGroup {
+  int format = 0;
+  RawJobDev* d_jobs = nullptr;
+  int njobs = 0;
+  uint32_t total_items = 0;
+};
+
 struct UnpackFastGroup {
   int bps;
   bool lsb;
@@ -72,7 +80,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -81,6 +89,9 @@ struct rsb200_plan {
   // unpack
   std::vector<UnpackGroup> groups;
   std::vector<UnpackFastGroup> fast_groups;
+  // fixed-layout raw forms
+  std::vector<RawGroup> raw_groups;
+  uint16_t* d_raw_tables = nullptr;
   // ljpeg
   DevTable* d_tables = nullptr;
   DevScan* d_scans = nullptr;
@@ -320,6 +331,145 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
   p->launches_per_run = (int)(p->groups.size() + p->fast_groups.size());
   *out = p;
   return RSB200_OK;
+}
+
+// ------------------------------------------------------------------
+// fixed-layout raw forms (K1b)
+// ------------------------------------------------------------------
+extern "C" int rsb200_raw_plan_create(rsb200_ctx* ctx, const rsb200_raw_job* jobs, int njobs,
+                                      const uint16_t* tables, int ntables, rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out || ntables < 0 || (ntables > 0 && !tables))
+    return set_err(ctx, RSB200_ERR_ARG, "raw_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  p->kind = 2;
+  p->nunits = njobs;
+  std::map<int, std::vector<RawJobDev>> buckets;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_raw_job& j = jobs[i];
+    const bool fmt_ok = j.format >= RSB200_RAW_8BIT && j.format <= RSB200_RAW_F32_COPY;
+    const uint32_t ob = fmt_ok ? raw_out_sample_bytes(j.format) : 2u;
+    bool ok = fmt_ok && j.rows >= 0 && j.samples > 0 && j.in_pitch > 0 && j.out_pitch > 0 &&
+              j.row0 >= 0 && j.out_col0 >= 0 && (j.out_offset % ob) == 0 &&
+              ((uint32_t)j.out_pitch % ob) == 0 &&
+              (uint64_t)(j.out_col0 + j.samples) * ob <= (uint64_t)j.out_pitch &&
+              (uint64_t)j.rows * (uint64_t)j.in_pitch <= j.in_size;
+    if (ok) {
+      // bytes one row really occupies
+      uint64_t need = raw_in_bytes(j.format, (uint32_t)j.samples);
+      if (j.format == RSB200_RAW_12BIT_CONTROL_BE || j.format == RSB200_RAW_12BIT_CONTROL_LE) {
+        ok = (j.samples % 2) == 0; // (12*w) % 8 == 0, UncompressedDecompressor.cpp:89-90
+        need += (uint64_t)(j.samples + 2) / 10;
+      }
+      ok = ok && need <= (uint64_t)j.in_pitch;
+      if (j.format == RSB200_RAW_8BIT_TABLE)
+        ok = ok && j.table >= 0 && j.table < ntables;
+    }
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "raw job %d: malformed descriptor", i);
+    }
+    if (j.rows == 0)
+      continue;
+    RawJobDev d;
+    memset(&d, 0, sizeof d);
+    d.in_offset = j.in_offset;
+    d.out_offset = j.out_offset;
+    d.out_pitch = (uint32_t)j.out_pitch;
+    d.in_pitch = (uint32_t)j.in_pitch;
+    d.row0 = (uint32_t)j.row0;
+    d.rows = (uint32_t)j.rows;
+    d.samples = (uint32_t)j.samples;
+    d.out_col0 = (uint32_t)j.out_col0;
+    d.format = (uint32_t)j.format;
+    d.table = (uint32_t)j.table;
+    const uint32_t K = raw_item_samples(j.format);
+    d.ipr = ((uint32_t)j.samples + K - 1) / K;
+    if ((uint64_t)d.ipr * d.rows >= 0xFFFF0000ull) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "raw job %d: too large", i);
+    }
+    buckets[j.format].push_back(d);
+    p->in_bytes += (uint64_t)j.rows * raw_in_bytes(j.format, (uint32_t)j.samples);
+    p->out_bytes += (uint64_t)j.rows * (uint64_t)j.samples * ob;
+    p->pixels += (uint64_t)j.rows * (uint64_t)j.samples;
+    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + (uint64_t)j.rows * j.in_pitch);
+    p->need_out = std::max<uint64_t>(
+        p->need_out, j.out_offset + (uint64_t)(j.row0 + j.rows - 1) * j.out_pitch +
+                         (uint64_t)ob * (uint64_t)(j.out_col0 + j.samples));
+  }
+  if (ntables > 0) {
+    const size_t tb = (size_t)ntables * 65536u * sizeof(uint16_t);
+    cudaError_t e = cudaMalloc(&p->d_raw_tables, tb);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->d_raw_tables, tables, tb, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "raw plan upload failed: %s", cudaGetErrorString(e));
+    }
+  }
+  for (auto& kv : buckets) {
+    RawGroup g;
+    g.format = kv.first;
+    uint64_t items = 0;
+    for (auto& d : kv.second) {
+      d.item_begin = (uint32_t)items;
+      items += (uint64_t)d.ipr * d.rows;
+    }
+    if (items >= 0xFFFF0000ull) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_ARG, "raw plan: too many items of format %d", g.format);
+    }
+    g.total_items = (uint32_t)items;
+    g.njobs = (int)kv.second.size();
+    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(RawJobDev) * kv.second.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(RawJobDev) * kv.second.size(),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "raw plan upload failed: %s", cudaGetErrorString(e));
+    }
+    p->raw_groups.push_back(g);
+  }
+  p->launches_per_run = (int)p->raw_groups.size();
+  *out = p;
+  return RSB200_OK;
+}
+
+template <int FORMAT>
+static cudaError_t launch_rawform(const RawGroup& g, const uint8_t* in, uint64_t in_total,
+                                  uint8_t* outp, const uint16_t* tables, cudaStream_t st) {
+  const uint32_t nb = (g.total_items + RAW_NT - 1) / RAW_NT;
+  rawform_kernel<FORMAT><<<nb, RAW_NT, 0, st>>>(in, in_total, outp, g.d_jobs, g.njobs,
+                                                g.total_items, tables);
+  return cudaGetLastError();
+}
+
+static cudaError_t run_raw_group(const RawGroup& g, const uint8_t* in, uint64_t in_total,
+                                 uint8_t* outp, const uint16_t* tables, cudaStream_t st) {
+  switch (g.format) {
+#define RSB_CASE(F)                                                               \
+  case F:                                                                         \
+    return launch_rawform<F>(g, in, in_total, outp, tables, st);
+    RSB_CASE(RSB200_RAW_8BIT)
+    RSB_CASE(RSB200_RAW_8BIT_TABLE)
+    RSB_CASE(RSB200_RAW_12BIT_CONTROL_BE)
+    RSB_CASE(RSB200_RAW_12BIT_CONTROL_LE)
+    RSB_CASE(RSB200_RAW_12BIT_LEFT_BE)
+    RSB_CASE(RSB200_RAW_12BIT_LEFT_LE)
+    RSB_CASE(RSB200_RAW_FP16_MSB)
+    RSB_CASE(RSB200_RAW_FP16_LSB)
+    RSB_CASE(RSB200_RAW_FP24_MSB)
+    RSB_CASE(RSB200_RAW_FP24_LSB)
+    RSB_CASE(RSB200_RAW_F32_COPY)
+#undef RSB_CASE
+  default:
+    return cudaErrorInvalidValue;
+  }
 }
 
 template <int BPS, bool LSBO>
@@ -807,6 +957,13 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->kind == 2) {
+    for (const RawGroup& g : p->raw_groups) {
+      if (!g.total_items)
+        continue;
+      CUDA_TRY(ctx, run_raw_group(g, in, (uint64_t)in_bytes, outp, p->d_raw_tables, st));
+      ctx->launches++;
+    }
   } else {
     const size_t fsm = fused_smem_bytes(p->ntab_slots);
     if (p->nsmall) {
@@ -964,7 +1121,7 @@ extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, 
   rsb200_ctx* ctx = p->ctx;
   if (!p->ran)
     return set_err(ctx, RSB200_ERR_ARG, "plan_results: plan has not been run");
-  if (p->kind == 0) {
+  if (p->kind != 1) {
     CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
     for (int i = 0; results && i < n; ++i) {
       results[i].status = RSB200_OK;
@@ -1018,6 +1175,9 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     cudaFree(g.d_jobs);
   for (UnpackFastGroup& g : p->fast_groups)
     cudaFree(g.d_jobs);
+  for (RawGroup& g : p->raw_groups)
+    cudaFree(g.d_jobs);
+  cudaFree(p->d_raw_tables);
   cudaFree(p->d_tables);
   cudaFree(p->d_scans);
   cudaFree(p->d_strips);

@@ -76,6 +76,26 @@ def unpack(data, img, w, cpp, crop, in_pitch, bps, order):
     return img
 
 
+def unpack_form(data, img, w, cpp, crop, in_pitch, bps, order, form, curve=None, dither=False):
+    """UncompressedDecompressor: readUncompressedRaw on an F32 image (img uint32) or one of
+    the fixed-layout members (form 1..6), via the C++ host mirror."""
+    p, n = _u8(data)
+    e = _Err()
+    cp, nc = None, 0
+    if curve is not None:
+        curve = np.ascontiguousarray(curve, dtype=np.uint16)
+        cp, nc = curve.ctypes.data_as(C.POINTER(C.c_uint16)), curve.size
+    L = lib()
+    L.rsb200h_unpack_form.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p] + [C.c_int] * 13 + \
+        [C.POINTER(C.c_uint16), C.c_int, C.c_int, C.POINTER(_Err)]
+    e.check(L.rsb200h_unpack_form(p, C.c_uint32(n), C.c_void_p(img.ctypes.data),
+                                  int(img.dtype == np.uint32), w, img.shape[0], cpp,
+                                  img.shape[1] * img.itemsize, crop[0], crop[1], crop[2],
+                                  crop[3], in_pitch, bps, order, form, cp, nc, int(dither),
+                                  C.byref(e)))
+    return img
+
+
 def ljpeg_decompress(img, w, cpp, img_frame, mcu, frame_dim, tabs, tab_of_comp, init_pred,
                      rows_per_restart, data, fix16=False):
     p, n = _u8(data)

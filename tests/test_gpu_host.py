@@ -143,3 +143,80 @@ def test_cr2_sraw():
         port.cr2_ljpeg_decode(blob, a, w, slicing, is_cfa=False, sub=(fmt[1], fmt[2]))
         host.cr2_ljpeg_decode(blob, b, w, slicing, is_cfa=False, sub=(fmt[1], fmt[2]))
         assert np.array_equal(a, b)
+
+
+# ---- the other UncompressedDecompressor members (fixed layouts, F32 images) ----
+def _form_both(data, mk, w, cpp, crop, pitch, bps, order, form, curve=None, dither=False):
+    a, b = mk(), mk()
+    table = port.build_table(curve, dither) if curve is not None else None
+    ea = eb = None
+    try:
+        port.unpack_form(data, a, w, cpp, crop, pitch, bps, order, form, table, dither)
+    except port.OracleError as e:
+        ea = e
+    try:
+        host.unpack_form(data, b, w, cpp, crop, pitch, bps, order, form, curve, dither)
+    except rs.Rsb200Error as e:
+        eb = e
+    if ea is None:
+        assert eb is None, eb
+        assert np.array_equal(a, b)
+    else:
+        want = rs.IOException if isinstance(ea, port.IOException) else rs.RawDecoderException
+        assert type(eb) is want, (ea, eb)
+        assert ea.msg[:30] in str(eb)
+    return ea
+
+
+@pytest.mark.parametrize("form", [port.FORM_8BIT, port.FORM_8BIT_UNCORRECTED])
+@pytest.mark.parametrize("curve_kind", ["none", "plain", "dither", "short"])
+def test_host_decode8bit(form, curve_kind):
+    w, h = 70, 9
+    data = synth.lcg_bytes(w * h + 5, seed=3)
+    curve, dither = None, False
+    if curve_kind != "none":
+        n = 256 if curve_kind != "short" else 100
+        curve = (np.arange(n, dtype=np.uint32) ** 2 // 2 % 65536).astype(np.uint16)
+        curve[n // 2] = 3
+        dither = curve_kind == "dither"
+    assert _form_both(data, lambda: port.new_image(w, h), w, 1, (0, 0, w, h), w, 8, port.LSB,
+                      form, curve, dither) is None
+
+
+@pytest.mark.parametrize("form", [port.FORM_12BIT_CONTROL_BE, port.FORM_12BIT_CONTROL_LE,
+                                  port.FORM_12BIT_LEFT_BE, port.FORM_12BIT_LEFT_LE])
+def test_host_decode12_forms(form):
+    for w in (10, 38, 64, 250):
+        h = 5
+        control = form in (port.FORM_12BIT_CONTROL_BE, port.FORM_12BIT_CONTROL_LE)
+        perline = 12 * w // 8 + (w + 2) // 10 if control else 2 * w
+        data = synth.lcg_bytes(perline * h, seed=w)
+        # the reference's callers construct with the real line pitch
+        assert _form_both(data, lambda: port.new_image(w, h), w, 1, (0, 0, w, h), perline,
+                          12 if control else 16, port.MSB if control else port.LSB, form) is None
+
+
+@pytest.mark.parametrize("order", [port.LSB, port.MSB])
+@pytest.mark.parametrize("bps", [16, 24, 32])
+def test_host_float_image(order, bps):
+    for cpp in (1, 3):
+        w, h, ox, oy = 24, 6, 4, 1
+        pitch = w * cpp * bps // 8 + 4
+        data = np.random.default_rng(bps + cpp).integers(0, 256, pitch * h, dtype=np.uint8)
+        assert _form_both(data, lambda: port.new_image_f32(w + 8, h + 2, cpp), w + 8, cpp,
+                          (ox, oy, w, h), pitch, bps, order, port.FORM_READ) is None
+
+
+def test_host_forms_error_classes():
+    w, h = 20, 6
+    data = synth.lcg_bytes(w * h, seed=5)
+    # member needs more bytes than the stream the constructor accepted -> IOException
+    e = _form_both(data, lambda: port.new_image(w, h), w, 1, (0, 0, w, h), w, 8, port.LSB,
+                   port.FORM_12BIT_LEFT_LE)
+    assert isinstance(e, port.IOException)
+    e = _form_both(data, lambda: port.new_image(7, 2), 7, 1, (0, 0, 7, 2), 7, 8, port.LSB,
+                   port.FORM_12BIT_CONTROL_LE)   # 12*7 % 8 != 0
+    assert isinstance(e, port.IOException)
+    e = _form_both(data, lambda: port.new_image_f32(8, 2), 8, 1, (0, 0, 8, 2), 16, 16,
+                   port.MSB16, port.FORM_READ)   # unsupported float packing
+    assert isinstance(e, port.RawDecoderException)
