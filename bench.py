@@ -522,6 +522,60 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
                                         "sample": "Cr2LJpegDecoder::decode (single threaded by design)"}
         out["configs[3] CR2 6720x4480 3 slices <%d,1,1>" % fmt[0]] = ent
         del plan, d_in, d_out
+    out.update(bench_forms(torch, rs, ctx, port, synth, args, dist, peak))
+    return out
+
+
+def bench_forms(torch, rs, ctx, port, synth, args, dist, peak):
+    """the fixed-layout UncompressedDecompressor forms, one 8256x5504
+    frame each, device-timed like the headline (inputs resident in HBM)."""
+    from rawspeed_b200 import formats as F
+    out = {}
+    steps = max(3, min(args.steps, 10))
+    cases = [("decode12BitRawWithControl<big>", F.RAW_12BIT_CONTROL_BE, 12 * W // 8 + (W + 2) // 10,
+              port.FORM_12BIT_CONTROL_BE, 12, port.MSB, False),
+             ("decode12BitRawUnpackedLeftAligned<little>", F.RAW_12BIT_LEFT_LE, 2 * W,
+              port.FORM_12BIT_LEFT_LE, 16, port.LSB, False),
+             ("decode8BitRaw<uncorrected>", F.RAW_8BIT, W, port.FORM_8BIT_UNCORRECTED, 8, port.LSB, False),
+             ("decodePackedFP<MSB, binary16> -> float", F.RAW_FP16_MSB, 2 * W, port.FORM_READ, 16,
+              port.MSB, True)]
+    for name, fmt, pitch, form, bps, order, f32 in cases:
+        data = synth.lcg_bytes(pitch * H, seed=7)
+        want = port.new_image_f32(W, H) if f32 else port.new_image(W, H)
+        got0 = want.copy()
+        j = rs.RawJob()
+        j.in_offset, j.in_size, j.out_offset = 0, data.size, 0
+        j.out_pitch = want.shape[1] * want.itemsize
+        j.row0, j.rows, j.samples, j.out_col0 = 0, H, W, 0
+        j.in_pitch, j.format, j.table = pitch, fmt, 0
+        plan = rs.raw_plan(ctx, [j])
+        d_in = torch.zeros(data.size + 64, dtype=torch.uint8, device="cuda")
+        d_in[:data.size] = torch.from_numpy(data.copy())
+        d_out = torch.from_numpy(got0.view(np.uint8).reshape(-1).copy()).cuda()
+        plan.run((d_in.data_ptr(), data.size), d_out)
+        torch.cuda.synchronize()
+        port.unpack_form(data, want, W, 1, (0, 0, W, H), pitch, bps, order, form)
+        exact = bool(np.array_equal(d_out.cpu().numpy().view(want.dtype).reshape(want.shape), want))
+        ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), data.size), d_out), steps, 3, dist)
+        in_b, out_b, pixels = plan.bytes()
+        per = ms / steps
+        ent = {"MPixels/s": pixels / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
+               "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
+               "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak,
+               "kernel": "rawform_kernel<%d>" % fmt,
+               "note": "single 45 MP frame per launch (%.0f MB moved): a short launch, below "
+                       "the batch figure" % ((in_b + out_b) / 1e6)}
+        if not args.skip_cpu and int(os.environ.get("RANK", "0")) == 0:
+            import oracle
+            if oracle.HAVE_REF:
+                tmp = want.copy()
+                msr = min(oracle.ref.unpack_form(data, tmp, W, 1, (0, 0, W, H), pitch, bps, order,
+                                                 form, reps=1) for _ in range(2))
+                ent["cpu_reference"] = {"kind": "reference", "cores": 1,
+                                        "MPixels/s": PIX / (msr * 1e-3) / 1e6,
+                                        "sample": "1 frame, best of 2 (single threaded by design)"}
+        out["8(f)1 " + name + " 8256x5504"] = ent
+        del plan, d_in, d_out
     return out
 
 
