@@ -45,7 +45,7 @@ class Err(C.Structure):
 class Image(C.Structure):
     _fields_ = [("data", C.c_void_p), ("w", C.c_int), ("h", C.c_int),
                 ("cpp", C.c_int), ("pitch", C.c_int), ("is_cfa", C.c_int),
-                ("sub_x", C.c_int), ("sub_y", C.c_int)]
+                ("sub_x", C.c_int), ("sub_y", C.c_int), ("is_f32", C.c_int)]
 
 
 class Frame(C.Structure):
@@ -97,9 +97,10 @@ def new_image(w, h, cpp=1, fill=0xA5A5):
 
 
 def _img(arr, w, cpp, is_cfa=True, sub=(1, 1)):
-    assert arr.dtype == np.uint16 and arr.flags.c_contiguous
-    return Image(arr.ctypes.data, w, arr.shape[0], cpp, arr.shape[1] * 2,
-                 1 if is_cfa else 0, sub[0], sub[1])
+    """uint16 array = UINT16 image; uint32 array (new_image_f32) = F32 image."""
+    assert arr.dtype in (np.uint16, np.uint32) and arr.flags.c_contiguous
+    return Image(arr.ctypes.data, w, arr.shape[0], cpp, arr.shape[1] * arr.itemsize,
+                 1 if is_cfa else 0, sub[0], sub[1], int(arr.dtype == np.uint32))
 
 
 def _u8(data):
@@ -225,7 +226,7 @@ def unpack_form(data, img, w, cpp, crop, in_pitch, bps, order, form, table=None,
     p, n = _u8(data)
     is_f32 = img.dtype == np.uint32
     assert img.flags.c_contiguous
-    im = Image(img.ctypes.data, w, img.shape[0], cpp, img.shape[1] * img.itemsize, 1, 1, 1)
+    im = _img(img, w, cpp)
     tp = None
     if table is not None:
         table = np.ascontiguousarray(table, dtype=np.uint16)

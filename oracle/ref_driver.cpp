@@ -352,7 +352,7 @@ int ref_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_data,
 
 int ref_dng_decompress(const uint8_t* file, uint64_t file_size,
                        const uint64_t* tile_off, const uint32_t* tile_len,
-                       int ntiles, uint16_t* img_data, int w, int h, int cpp,
+                       int ntiles, void* img_data, int is_f32, int w, int h, int cpp,
                        int pitch, int tile_w, int tile_h, int compression,
                        int fix_ljpeg, int bps, int big_endian, int nthreads,
                        int reps, double* best_ms, RefErr* e) {
@@ -360,8 +360,18 @@ int ref_dng_decompress(const uint8_t* file, uint64_t file_size,
     ref_set_threads(nthreads);
     const Buffer whole(file, static_cast<Buffer::size_type>(file_size));
     double best = 1e30;
-    RawImage img = makeImage(w, h, cpp, true, 1, 1);
-    copyIn(img, img_data, pitch);
+    RawImage img = RawImage::create(iPoint2D(w, h),
+                                    is_f32 ? RawImageType::F32 : RawImageType::UINT16, cpp);
+    img->isCFA = true;
+    const int bpp = (is_f32 ? 4 : 2) * cpp;
+    auto rowPtr = [&](int r) {
+      if (is_f32)
+        return reinterpret_cast<uint8_t*>(&img->getF32DataAsUncroppedArray2DRef()(r, 0));
+      return reinterpret_cast<uint8_t*>(&img->getU16DataAsUncroppedArray2DRef()(r, 0));
+    };
+    for (int r = 0; r < h; ++r)
+      std::memcpy(rowPtr(r), static_cast<const uint8_t*>(img_data) + static_cast<size_t>(r) * pitch,
+                  static_cast<size_t>(w) * bpp);
     for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
       const iPoint2D dim(w, h);
       DngTilingDescription dsc(dim, tile_w, tile_h);
@@ -382,7 +392,9 @@ int ref_dng_decompress(const uint8_t* file, uint64_t file_size,
     }
     if (best_ms)
       *best_ms = best;
-    copyOut(img, img_data, pitch);
+    for (int r = 0; r < h; ++r)
+      std::memcpy(static_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, rowPtr(r),
+                  static_cast<size_t>(w) * bpp);
   });
 }
 

@@ -1431,8 +1431,8 @@ int rso_dng_decompress(const uint8_t* file, uint64_t file_size,
         int be = big_endian;
         uint32_t inputPixelBits;
         int inputPitchBits, inputPitch;
-        if (bps != 8 && bps != 16 && bps != 32)
-          be = 1; /* UINT16 image */
+        if (bps != 8 && bps != 16 && bps != 32 && !img->is_f32)
+          be = 1; /* UINT16 images only (AbstractDngDecompressor.cpp:66-77) */
         inputPixelBits = (uint32_t)img->cpp * (uint32_t)bps;
         if ((uint32_t)tile_w > (uint32_t)INT_MAX / inputPixelBits)
           THROW_IOE(&c, "Integer overflow when calculating input pitch");
@@ -1445,7 +1445,7 @@ int rso_dng_decompress(const uint8_t* file, uint64_t file_size,
           THROW_RDE(&c, "Data input pitch is too short. Can not decode!");
         unpack_impl(&c, file + tile_off[n], tile_len[n], img, (int)offX,
                     (int)offY, (int)width, (int)height, inputPitch, bps,
-                    be ? RSO_MSB : RSO_LSB, 0, RSO_FORM_READ, NULL, 0);
+                    be ? RSO_MSB : RSO_LSB, img->is_f32, RSO_FORM_READ, NULL, 0);
       }
     }
     if (d) {

@@ -44,6 +44,8 @@ typedef struct {
   int pitch; /* bytes */
   int is_cfa; /* RawImageData::isCFA, only consulted by the CR2 path */
   int sub_x, sub_y; /* ImageMetaData::subsampling (RawImage.h:93), default 1,1 */
+  int is_f32; /* RawImageType::F32: `data` holds 32-bit samples (only the
+                 uncompressed paths accept it) */
 } rso_image;
 
 /* createData(): pitch = roundUp(w*cpp*2, 16) (RawImage.cpp:68-84) */

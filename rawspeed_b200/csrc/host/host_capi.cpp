@@ -158,11 +158,16 @@ int rsb200h_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_data
 }
 
 int rsb200h_dng_decompress(const uint8_t* file, uint64_t file_size, const uint64_t* tile_off,
-                           const uint32_t* tile_len, int ntiles, uint16_t* img_data, int w, int h,
-                           int cpp, int pitch, int tile_w, int tile_h, int compression,
+                           const uint32_t* tile_len, int ntiles, void* img_data, int is_f32, int w,
+                           int h, int cpp, int pitch, int tile_w, int tile_h, int compression,
                            int fix_ljpeg, int bps, int big_endian, rsb200h_err* e) {
   return guarded(e, [&] {
-    RawImage img = makeImage(img_data, w, h, cpp, pitch, true, 1, 1);
+    RawImage img = RawImage::create(iPoint2D(w, h),
+                                    is_f32 ? RawImageType::F32 : RawImageType::UINT16,
+                                    (uint32_t)cpp);
+    if (img->pitch != pitch)
+      ThrowRDE("test harness: pitch mismatch (%d vs %d)", img->pitch, pitch);
+    std::memcpy(img->getByteData(), img_data, (size_t)pitch * h);
     const iPoint2D dim(w, h);
     DngTilingDescription dsc(dim, (uint32_t)tile_w, (uint32_t)tile_h);
     AbstractDngDecompressor d(img, dsc, compression, fix_ljpeg != 0, (uint32_t)bps, 1);
@@ -175,10 +180,10 @@ int rsb200h_dng_decompress(const uint8_t* file, uint64_t file_size, const uint64
     try {
       d.decompress();
     } catch (...) {
-      copyOut(img, img_data);
+      std::memcpy(img_data, img->getByteData(), img->getByteSize());
       throw;
     }
-    copyOut(img, img_data);
+    std::memcpy(img_data, img->getByteData(), img->getByteSize());
   });
 }
 

@@ -370,8 +370,9 @@ template <Endianness e> void UncompressedDecompressor::decode12BitRawUnpackedLef
 template void UncompressedDecompressor::decode12BitRawUnpackedLeftAligned<Endianness::little>();
 template void UncompressedDecompressor::decode12BitRawUnpackedLeftAligned<Endianness::big>();
 
-// readUncompressedRaw() on an F32 image (UncompressedDecompressor.cpp:214-247)
-void UncompressedDecompressor::readF32() {
+// readUncompressedRaw() on an F32 image (UncompressedDecompressor.cpp:214-247): the job
+// it amounts to.  false = nothing to decode.
+bool UncompressedDecompressor::describeF32(const uint8_t* fileBase, rsb200_raw_job* job) const {
   const uint32_t cpp = mRaw->getCpp();
   const uint64_t oy = offset.y;
   const uint64_t hEnd = std::min<uint64_t>((uint64_t)size.y + oy, (uint64_t)mRaw->dim.y);
@@ -380,7 +381,7 @@ void UncompressedDecompressor::readF32() {
   if (bitPerPixel == 32) {
     format = RSB200_RAW_F32_COPY;
     col0 = (int32_t)(offset.x * (int)cpp);
-    if ((uint64_t)inputPitchBytes * (hEnd - oy) > input.getRemainSize())
+    if (hEnd > oy && (uint64_t)inputPitchBytes * (hEnd - oy) > input.getRemainSize())
       ThrowIOE("Buffer overflow: image file may be truncated");
   } else if ((order == BitOrder::MSB || order == BitOrder::LSB) &&
              (bitPerPixel == 16 || bitPerPixel == 24)) {
@@ -395,17 +396,24 @@ void UncompressedDecompressor::readF32() {
              (unsigned)order);
   }
   if (hEnd <= oy)
-    return;
+    return false;
+  std::memset(job, 0, sizeof *job);
+  job->in_offset = (uint64_t)(input.begin() - fileBase);
+  job->in_size = input.getRemainSize();
+  job->out_pitch = mRaw->pitch;
+  job->row0 = (int32_t)oy;
+  job->rows = (int32_t)(hEnd - oy);
+  job->samples = (int32_t)(size.x * (int)cpp);
+  job->out_col0 = col0;
+  job->in_pitch = inputPitchBytes;
+  job->format = format;
+  return true;
+}
+
+void UncompressedDecompressor::readF32() {
   rsb200_raw_job job;
-  std::memset(&job, 0, sizeof job);
-  job.in_size = input.getRemainSize();
-  job.out_pitch = mRaw->pitch;
-  job.row0 = (int32_t)oy;
-  job.rows = (int32_t)(hEnd - oy);
-  job.samples = (int32_t)(size.x * (int)cpp);
-  job.out_col0 = col0;
-  job.in_pitch = inputPitchBytes;
-  job.format = format;
+  if (!describeF32(input.begin(), &job))
+    return;
   PlanGuard pg;
   engineCheck(rsb200_raw_plan_create(engine(), &job, 1, nullptr, 0, &pg.p),
               "rsb200_raw_plan_create");
@@ -1138,11 +1146,14 @@ void AbstractDngDecompressor::decompressUncompressed() const {
   size_t span;
   tileSpan(slices, &base, &span);
   std::vector<rsb200_unpack_job> jobs;
+  std::vector<rsb200_raw_job> fjobs; // floating-point DNG: F32 image
+  const bool f32 = mRaw->getDataType() == RawImageType::F32;
   for (const auto& e : slices) {
     try {
       bool big_endian = e.bs.getByteOrder() == Endianness::big;
-      if (mBps != 8 && mBps != 16 && mBps != 32)
-        big_endian = true; // DNG: not 8/16/32 bit => always big endian
+      if (mBps != 8 && mBps != 16 && mBps != 32 && !f32)
+        big_endian = true; // DNG: not 8/16/32 bit => always big endian (UINT16 images only,
+                           // AbstractDngDecompressor.cpp:66-77)
       const uint32_t inputPixelBits = mRaw->getCpp() * mBps;
       if (e.dsc.tileW > (uint32_t)std::numeric_limits<int>::max() / inputPixelBits)
         ThrowIOE("Integer overflow when calculating input pitch");
@@ -1158,6 +1169,12 @@ void AbstractDngDecompressor::decompressUncompressed() const {
                                  iRectangle2D((int)e.offX, (int)e.offY, (int)e.width,
                                               (int)e.height),
                                  inputPitch, (int)mBps, big_endian ? BitOrder::MSB : BitOrder::LSB);
+      if (f32) {
+        rsb200_raw_job fjob;
+        if (u.describeF32(base, &fjob))
+          fjobs.push_back(fjob);
+        continue;
+      }
       rsb200_unpack_job job;
       if (u.describe(base, &job))
         jobs.push_back(job);
@@ -1167,11 +1184,15 @@ void AbstractDngDecompressor::decompressUncompressed() const {
       mRaw->setError(err.what());
     }
   }
-  if (jobs.empty())
+  if (jobs.empty() && fjobs.empty())
     return;
   PlanGuard pg;
-  engineCheck(rsb200_unpack_plan_create(engine(), jobs.data(), (int)jobs.size(), &pg.p),
-              "rsb200_unpack_plan_create");
+  if (f32)
+    engineCheck(rsb200_raw_plan_create(engine(), fjobs.data(), (int)fjobs.size(), nullptr, 0, &pg.p),
+                "rsb200_raw_plan_create");
+  else
+    engineCheck(rsb200_unpack_plan_create(engine(), jobs.data(), (int)jobs.size(), &pg.p),
+                "rsb200_unpack_plan_create");
   RawImage img = mRaw;
   runOnImage(pg.p, base, span, img, /*partial=*/true);
 }

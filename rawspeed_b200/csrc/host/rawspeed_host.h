@@ -270,6 +270,7 @@ public:
   template <Endianness e> void decode12BitRawUnpackedLeftAligned();
   // batch support (AbstractDngDecompressor): describe instead of decode
   bool describe(const uint8_t* fileBase, rsb200_unpack_job* job) const;
+  bool describeF32(const uint8_t* fileBase, rsb200_raw_job* job) const; // F32 image
 
 private:
   void sanityCheck(uint32_t h, int bytesPerLine) const;

@@ -128,9 +128,11 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h, 
     lens = (C.c_uint32 * len(tile_len))(*tile_len)
     e = _Err()
     e.check(lib().rsb200h_dng_decompress(p, C.c_uint64(n), offs, lens, len(tile_off),
-                                         C.c_void_p(img.ctypes.data), w, img.shape[0], cpp,
-                                         img.shape[1] * 2, tile_w, tile_h, compression,
-                                         int(fix_ljpeg), bps, int(big_endian), C.byref(e)))
+                                         C.c_void_p(img.ctypes.data),
+                                         int(img.dtype == np.uint32), w, img.shape[0], cpp,
+                                         img.shape[1] * img.itemsize, tile_w, tile_h,
+                                         compression, int(fix_ljpeg), bps, int(big_endian),
+                                         C.byref(e)))
     return img
 
 

@@ -220,3 +220,18 @@ def test_host_forms_error_classes():
     e = _form_both(data, lambda: port.new_image_f32(8, 2), 8, 1, (0, 0, 8, 2), 16, 16,
                    port.MSB16, port.FORM_READ)   # unsupported float packing
     assert isinstance(e, port.RawDecoderException)
+
+
+@pytest.mark.parametrize("bps", [16, 24, 32])
+def test_host_float_dng_tiles(bps):
+    """Floating-point DNG (compression 1) through AbstractDngDecompressor on an F32 image."""
+    W, H, tw, th = 100, 60, 32, 16
+    pitch = tw * bps // 8
+    blob = synth.lcg_bytes(pitch * th * 16 + 64, bps)
+    offs = [7 + n * pitch * th for n in range(16)]
+    lens = [pitch * th] * 16
+    for be in (False, True):
+        a, b = port.new_image_f32(W, H), port.new_image_f32(W, H)
+        port.dng_decompress(blob, offs, lens, a, W, 1, tw, th, 1, bps=bps, big_endian=be)
+        host.dng_decompress(blob, offs, lens, b, W, 1, tw, th, 1, bps=bps, big_endian=be)
+        assert np.array_equal(a, b), (bps, be)

@@ -136,3 +136,20 @@ def test_odd_width_with_control_is_ioe():
     _, err = both(data, lambda: port.new_image(w, h), w, 1, (0, 0, w, h), w, 8, port.LSB,
                   port.FORM_12BIT_CONTROL_LE)
     assert isinstance(err, port.IOException)
+
+
+@pytest.mark.parametrize("bps", [16, 24, 32])
+@pytest.mark.parametrize("big_endian", [False, True])
+def test_float_dng_tiles(bps, big_endian):
+    """Floating-point DNG, compression 1: AbstractDngDecompressor over an F32 image
+    (bps 16/24 are always read MSB; 32 follows the tile byte order... as raw copy)."""
+    W, H, tw, th = 100, 60, 32, 16
+    pitch = tw * bps // 8
+    ntiles = 4 * 4
+    blob = synth.lcg_bytes(pitch * th * ntiles + 64, bps)
+    offs = [7 + n * pitch * th for n in range(ntiles)]
+    lens = [pitch * th] * ntiles
+    a, b = port.new_image_f32(W, H), port.new_image_f32(W, H)
+    port.dng_decompress(blob, offs, lens, a, W, 1, tw, th, 1, bps=bps, big_endian=big_endian)
+    ref.dng_decompress(blob, offs, lens, b, W, 1, tw, th, 1, bps=bps, big_endian=big_endian)
+    assert np.array_equal(a, b)
