@@ -155,6 +155,33 @@ int rsb200_raw_plan_create(rsb200_ctx* ctx, const rsb200_raw_job* jobs, int njob
                            const uint16_t* tables, int ntables, rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* K5: Canon sRaw interpolation.                         */
+/*   Cr2sRawInterpolator::interpolate(version)                          */
+/*   interpolators/Cr2sRawInterpolator.cpp:96-187 (4:2:2), :189-453     */
+/*   (4:2:0), YUV_TO_RGB<0|1|2> + STORE_RGB :455-497                    */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t in_offset;  /* byte offset of row 0 of the subsampled uint16 image (the
+                          output of the CR2 decode: 4 (4:2:2) or 6 (4:2:0) samples
+                          per MCU); multiple of 4                               */
+  uint32_t in_pitch;   /* bytes between its rows; multiple of 4                  */
+  uint32_t num_mcus;   /* MCUs per input row (input.width() / 4 or / 6), >= 2    */
+  uint32_t in_rows;    /* rows of the subsampled image                           */
+  uint8_t sub_x;       /* ImageMetaData::subsampling: (2,1) = 4:2:2, (2,2) = 4:2:0 */
+  uint8_t sub_y;
+  uint8_t version;     /* 0, 1, 2 (4:2:0: 1 or 2)                                */
+  uint8_t reserved;
+  int32_t sraw_coeffs[3];
+  int32_t hue;
+  uint64_t out_offset; /* byte offset of the 3-component output image; multiple of 4 */
+  uint32_t out_pitch;  /* bytes; rows written: in_rows * sub_y, 2*num_mcus pixels each */
+  uint32_t reserved1;
+} rsb200_sraw_job;
+
+int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* jobs, int njobs,
+                            rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
 /* K2+K3: lossless JPEG (Huffman + predictor 1).                        */
 /* ------------------------------------------------------------------ */
 typedef struct {

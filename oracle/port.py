@@ -285,6 +285,23 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h,
     return img
 
 
+def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version):
+    """Cr2sRawInterpolator(out, inp, coeffs, hue).interpolate(version).
+    inp: uint16 array (rows, pitch/2) of which in_w columns are the subsampled data;
+    out: uint16 3-component image buffer from new_image(out_w, out_h, 3)."""
+    assert inp.dtype == np.uint16 and inp.flags.c_contiguous
+    im = _img(out, out_w, 3, False, sub)
+    k = (C.c_int * 3)(*coeffs)
+    e = Err()
+    L = lib()
+    L.rso_sraw_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Image),
+                                       C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(Err)]
+    rc = L.rso_sraw_interpolate(inp.ctypes.data, in_w, inp.shape[0], inp.shape[1] * 2,
+                                C.byref(im), k, hue, version, C.byref(e))
+    e.check(rc)
+    return out
+
+
 def cr2_decompress(img, w, fmt, frame, slicing, hts, init_pred, data, is_cfa=True):
     p, n = _u8(data)
     im = _img(img, w, 1, is_cfa)

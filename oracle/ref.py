@@ -182,6 +182,23 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h,
     return ms.value
 
 
+def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version, nthreads=1, reps=1):
+    """Reference Cr2sRawInterpolator; returns best wall ms."""
+    k = (C.c_int * 3)(*coeffs)
+    ms = C.c_double(0)
+    e = Err()
+    L = lib()
+    L.ref_sraw_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + \
+        [C.c_int] * 5 + [C.POINTER(C.c_int)] + [C.c_int] * 4 + [C.POINTER(C.c_double),
+                                                               C.POINTER(Err)]
+    rc = L.ref_sraw_interpolate(inp.ctypes.data, in_w, inp.shape[0], inp.shape[1] * 2,
+                                out.ctypes.data, out_w, out.shape[0], out.shape[1] * 2,
+                                sub[0], sub[1], k, hue, version, nthreads, reps, C.byref(ms),
+                                C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
 def cr2_decompress(img, w, fmt, frame, slicing, tabs, tab_of_comp, init_pred, data,
                    is_cfa=True, reps=1, want_ms=False):
     p, n = _u8(data)

@@ -39,6 +39,7 @@
 #include "decompressors/LJpegDecoder.h"
 #include "decompressors/LJpegDecompressor.h"
 #include "decompressors/UncompressedDecompressor.h"
+#include "interpolators/Cr2sRawInterpolator.h"
 #include "io/Buffer.h"
 #include "io/ByteStream.h"
 #include "io/Endianness.h"
@@ -294,6 +295,31 @@ int ref_unpack_form(const uint8_t* in, uint32_t in_size, void* img_data, int is_
     for (int r = 0; r < h; ++r)
       std::memcpy(static_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, rowPtr(r),
                   static_cast<size_t>(w) * bpp);
+  });
+}
+
+// Cr2sRawInterpolator(mRaw, input, sraw_coeffs, hue).interpolate(version)
+// (interpolators/Cr2sRawInterpolator.h:36-60); out image: cpp 3, subsampling set.
+int ref_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
+                         uint16_t* out_data, int out_w, int out_h, int out_pitch, int sub_x,
+                         int sub_y, const int* coeffs, int hue, int version, int nthreads,
+                         int reps, double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(out_w, out_h, 3, false, sub_x, sub_y);
+    copyIn(img, out_data, out_pitch);
+    const Array2DRef<const uint16_t> input(in, in_w, in_h, in_pitch / 2);
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      Cr2sRawInterpolator i(img, input, {coeffs[0], coeffs[1], coeffs[2]}, hue);
+      i.interpolate(version);
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, out_data, out_pitch);
   });
 }
 

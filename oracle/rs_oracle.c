@@ -2166,3 +2166,136 @@ done:
     rso_huff_destroy(hts[k]);
   return ret;
 }
+
+
+/* ------------------------------------------------------------------ */
+/* Cr2sRawInterpolator (interpolators/Cr2sRawInterpolator.cpp)          */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int Y, Cb, Cr;
+} ycc;
+
+static uint16_t clamp16(int x) { return (uint16_t)(x < 0 ? 0 : (x > 65535 ? 65535 : x)); }
+
+/* YUV_TO_RGB<version> + STORE_RGB (:455-497) */
+static void sraw_store(const ycc* p, uint16_t* o, const int* k, int version) {
+  int r, g, b;
+  if (version == 0) { /* EOS 40D */
+    r = k[0] * (p->Y + p->Cr - 512);
+    g = k[1] * (p->Y + ((-778 * p->Cb - (p->Cr * 2048)) >> 12) - 512);
+    b = k[2] * (p->Y + (p->Cb - 512));
+  } else if (version == 1) {
+    r = k[0] * (p->Y + ((50 * p->Cb + 22929 * p->Cr) >> 12));
+    g = k[1] * (p->Y + ((-5640 * p->Cb - 11751 * p->Cr) >> 12));
+    b = k[2] * (p->Y + ((29040 * p->Cb - 101 * p->Cr) >> 12));
+  } else { /* EOS 5D Mk III */
+    r = k[0] * (p->Y + p->Cr);
+    g = k[1] * (p->Y + ((-778 * p->Cb - (p->Cr * 2048)) >> 12));
+    b = k[2] * (p->Y + p->Cb);
+  }
+  o[0] = clamp16(r >> 8);
+  o[1] = clamp16(g >> 8);
+  o[2] = clamp16(b >> 8);
+}
+
+/* full chroma sample of MCU m of input row `row`: LoadCbCr + process(hue) (:66-86) */
+static ycc sraw_chroma(const uint16_t* row, int per, int ys, int m, int hue) {
+  ycc c;
+  c.Y = 0;
+  c.Cb = (int)row[per * m + ys] - 16384 + hue;
+  c.Cr = (int)row[per * m + ys + 1] - 16384 + hue;
+  return c;
+}
+
+int rso_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
+                         rso_image* out, const int* k, int hue, int version,
+                         rso_err* e) {
+  RSO_ENTER(c, e);
+  const int sx = out->sub_x, sy = out->sub_y;
+  if (sy == 1 && sx == 2) {
+    /* interpolate_422 (:96-187): rows independent */
+    const int numMCUs = in_w / 4;
+    int row, m;
+    for (row = 0; row < out->h; row++) {
+      const uint16_t* ir = (const uint16_t*)((const uint8_t*)in + (size_t)row * in_pitch);
+      uint16_t* o = (uint16_t*)((uint8_t*)out->data + (size_t)row * out->pitch);
+      for (m = 0; m < numMCUs; ++m) {
+        ycc p0 = sraw_chroma(ir, 4, 2, m, hue), p1;
+        p0.Y = ir[4 * m];
+        p1.Y = ir[4 * m + 1];
+        if (m + 1 < numMCUs) {
+          ycc n = sraw_chroma(ir, 4, 2, m + 1, hue);
+          p1.Cb = (p0.Cb + n.Cb) >> 1;
+          p1.Cr = (p0.Cr + n.Cr) >> 1;
+        } else { /* last pixel of the line keeps the previous chroma */
+          p1.Cb = p0.Cb;
+          p1.Cr = p0.Cr;
+        }
+        sraw_store(&p0, o + 6 * m, k, version);
+        sraw_store(&p1, o + 6 * m + 3, k, version);
+      }
+    }
+    return RSO_OK;
+  }
+  if (sy == 2 && sx == 2) {
+    /* interpolate_420 (:189-453) */
+    const int numMCUs = in_w / 6;
+    int row, m, i, j;
+    for (row = 0; row < in_h; ++row) {
+      const uint16_t* r0 = (const uint16_t*)((const uint8_t*)in + (size_t)row * in_pitch);
+      const uint16_t* r1 = (const uint16_t*)((const uint8_t*)r0 + in_pitch);
+      const int lastRow = row + 1 == in_h;
+      for (m = 0; m < numMCUs; ++m) {
+        const int lastCol = m + 1 == numMCUs;
+        ycc px[2][2];
+        ycc c00 = sraw_chroma(r0, 6, 4, m, hue), c01, c10, c11;
+        for (i = 0; i < 2; ++i)
+          for (j = 0; j < 2; ++j)
+            px[i][j].Y = r0[6 * m + 2 * i + j];
+        px[0][0].Cb = c00.Cb;
+        px[0][0].Cr = c00.Cr;
+        if (!lastCol)
+          c01 = sraw_chroma(r0, 6, 4, m + 1, hue);
+        if (!lastRow)
+          c10 = sraw_chroma(r1, 6, 4, m, hue);
+        if (!lastRow && !lastCol)
+          c11 = sraw_chroma(r1, 6, 4, m + 1, hue);
+        if (!lastRow && !lastCol) {
+          px[0][1].Cb = (c00.Cb + c01.Cb) >> 1;
+          px[0][1].Cr = (c00.Cr + c01.Cr) >> 1;
+          px[1][0].Cb = (c00.Cb + c10.Cb) >> 1;
+          px[1][0].Cr = (c00.Cr + c10.Cr) >> 1;
+          px[1][1].Cb = (c00.Cb + c01.Cb + c10.Cb + c11.Cb) >> 2;
+          px[1][1].Cr = (c00.Cr + c01.Cr + c10.Cr + c11.Cr) >> 2;
+        } else if (!lastRow) { /* last MCU of the line (:349-374) */
+          px[1][0].Cb = (c00.Cb + c10.Cb) >> 1;
+          px[1][0].Cr = (c00.Cr + c10.Cr) >> 1;
+          px[0][1].Cb = px[0][0].Cb;
+          px[0][1].Cr = px[0][0].Cr;
+          px[1][1].Cb = px[1][0].Cb;
+          px[1][1].Cr = px[1][0].Cr;
+        } else if (!lastCol) { /* last line (:405-430) */
+          px[0][1].Cb = (c00.Cb + c01.Cb) >> 1;
+          px[0][1].Cr = (c00.Cr + c01.Cr) >> 1;
+          px[1][0].Cb = px[0][0].Cb;
+          px[1][0].Cr = px[0][0].Cr;
+          px[1][1].Cb = px[0][1].Cb;
+          px[1][1].Cr = px[0][1].Cr;
+        } else { /* last MCU of the last line (:434-452) */
+          for (i = 0; i < 2; ++i)
+            for (j = 0; j < 2; ++j) {
+              px[i][j].Cb = c00.Cb;
+              px[i][j].Cr = c00.Cr;
+            }
+        }
+        for (i = 0; i < 2; ++i) {
+          uint16_t* o = (uint16_t*)((uint8_t*)out->data + (size_t)(2 * row + i) * out->pitch);
+          for (j = 0; j < 2; ++j)
+            sraw_store(&px[i][j], o + 6 * m + 3 * j, k, version);
+        }
+      }
+    }
+    return RSO_OK;
+  }
+  THROW_RDE(&c, "Unknown subsampling: (%i; %i)", sx, sy);
+}

@@ -137,6 +137,14 @@ int rso_dng_decompress(const uint8_t* file, uint64_t file_size,
                        int compression, int fix_ljpeg, int bps, int big_endian,
                        int nthreads, rso_err* e);
 
+/* ---- Cr2sRawInterpolator (interpolators/Cr2sRawInterpolator.cpp:32-544) ----
+ * in: the subsampled image as decoded (in_w uint16 per row = 4 or 6 per MCU);
+ * out: 3-component image (out->sub_x/sub_y = ImageMetaData::subsampling selects
+ * 4:2:2 (2,1) or 4:2:0 (2,2)); version 0..2 = the YUV_TO_RGB<version> variants. */
+int rso_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
+                         rso_image* out, const int* sraw_coeffs, int hue, int version,
+                         rso_err* e);
+
 /* ---- Cr2Decompressor (decompressors/Cr2DecompressorImpl.h:279-468) ---- */
 int rso_cr2_decompress(rso_image* img, int n_comp, int x_s_f, int y_s_f,
                        int frame_w, int frame_h, int num_slices, int slice_w,

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Cr2Job, HuffTable, LJpegScan, RawJob, ScanResult, UnpackJob,  # noqa: F401
+from ._abi import (Cr2Job, HuffTable, LJpegScan, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -159,6 +159,14 @@ def raw_plan(ctx, jobs, tables=None):
         tables = np.ascontiguousarray(tables, dtype=np.uint16).reshape(-1, 65536)
         tp, nt = tables.ctypes.data_as(C.POINTER(C.c_uint16)), tables.shape[0]
     ctx.check(ctx._lib.rsb200_raw_plan_create(ctx.h, arr, len(jobs), tp, nt, C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def sraw_plan(ctx, jobs):
+    """Canon sRaw interpolation (Cr2sRawInterpolator) over subsampled uint16 images."""
+    arr = (SrawJob * len(jobs))(*jobs)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_sraw_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

@@ -229,6 +229,19 @@ int rsb200h_cr2_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_
   });
 }
 
+int rsb200h_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
+                             uint16_t* out_data, int out_w, int out_h, int out_pitch, int sub_x,
+                             int sub_y, const int* coeffs, int hue, int version,
+                             rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(out_data, out_w, out_h, 3, out_pitch, false, sub_x, sub_y);
+    Cr2sRawInterpolator i(img, Array2DRef<const uint16_t>(in, in_w, in_h, in_pitch / 2),
+                          {coeffs[0], coeffs[1], coeffs[2]}, hue);
+    i.interpolate(version);
+    copyOut(img, out_data);
+  });
+}
+
 int rsb200h_huff_check(const uint8_t* ncpl, const uint8_t* values, int nvalues, int full,
                        int fix16, rsb200h_err* e) {
   return guarded(e, [&] {

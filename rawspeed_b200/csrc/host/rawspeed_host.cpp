@@ -433,6 +433,41 @@ void UncompressedDecompressor::readUncompressedRaw() {
   runOnImage(pg.p, input.begin(), input.getRemainSize(), mRaw, /*partial=*/true);
 }
 
+// ------------------------------------------------------------------ sRaw
+// Cr2sRawInterpolator::interpolate (interpolators/Cr2sRawInterpolator.cpp:499-542)
+void Cr2sRawInterpolator::interpolate(int version) {
+  const iPoint2D sub = mRaw->subsampling;
+  const bool is422 = sub.y == 1 && sub.x == 2, is420 = sub.y == 2 && sub.x == 2;
+  if (!is422 && !is420)
+    ThrowRDE("Unknown subsampling: (%i; %i)", sub.x, sub.y);
+  if (version < 0 || version > 2 || (is420 && version == 0))
+    ThrowRDE("rawspeed_b200: sRaw version %d is not defined for this subsampling", version);
+  const int per = is420 ? 6 : 4;
+  rsb200_sraw_job job;
+  std::memset(&job, 0, sizeof job);
+  job.in_offset = 0;
+  job.in_pitch = (uint32_t)input.pitch() * 2u;
+  job.num_mcus = (uint32_t)(input.width() / per);
+  job.in_rows = (uint32_t)input.height();
+  job.sub_x = (uint8_t)sub.x;
+  job.sub_y = (uint8_t)sub.y;
+  job.version = (uint8_t)version;
+  for (int i = 0; i < 3; ++i)
+    job.sraw_coeffs[i] = sraw_coeffs[(size_t)i];
+  job.hue = hue;
+  job.out_offset = 0;
+  job.out_pitch = (uint32_t)mRaw->pitch;
+  if (mRaw->getCpp() != 3 || (int)(job.num_mcus * 2) > mRaw->dim.x ||
+      (int)(job.in_rows * (uint32_t)sub.y) > mRaw->dim.y)
+    ThrowRDE("rawspeed_b200: sRaw output image does not match the subsampled input");
+  PlanGuard pg;
+  engineCheck(rsb200_sraw_plan_create(engine(), &job, 1, &pg.p), "rsb200_sraw_plan_create");
+  RawImage img = mRaw;
+  const size_t inBytes = (size_t)(input.height() - 1) * job.in_pitch + (size_t)input.width() * 2;
+  runOnImage(pg.p, reinterpret_cast<const uint8_t*>(input.begin()), inBytes, img,
+             /*partial=*/true);
+}
+
 // ------------------------------------------------------------------ LJPEG
 LJpegDecompressor::LJpegDecompressor(RawImage img, iRectangle2D imgFrame_, Frame frame_,
                                      std::vector<PerComponentRecipe> rec_,

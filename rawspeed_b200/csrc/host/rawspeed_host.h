@@ -447,6 +447,39 @@ private:
   std::unique_ptr<Cr2Decompressor<>> d;
 };
 
+// ---------------------------------------------------------------- sRaw
+// adt/Array2DRef.h: non-owning 2-D view (pitch in elements)
+template <typename T> class Array2DRef {
+public:
+  Array2DRef(T* data_, int width_, int height_, int pitch_)
+      : data(data_), w(width_), h(height_), pitchElts(pitch_) {}
+  int width() const { return w; }
+  int height() const { return h; }
+  int pitch() const { return pitchElts; }
+  T* begin() const { return data; }
+  T& operator()(int row, int col) const { return data[(size_t)row * pitchElts + col]; }
+
+private:
+  T* data;
+  int w, h, pitchElts;
+};
+
+// interpolators/Cr2sRawInterpolator.h:36-60 -- same constructor and interpolate();
+// the per-pixel work (chroma interpolation + YCbCr->RGB) runs on the device.
+class Cr2sRawInterpolator final {
+public:
+  Cr2sRawInterpolator(const RawImage& mRaw_, Array2DRef<const uint16_t> input_,
+                      std::array<int, 3> sraw_coeffs_, int hue_)
+      : mRaw(mRaw_), input(input_), sraw_coeffs(sraw_coeffs_), hue(hue_) {}
+  void interpolate(int version);
+
+private:
+  const RawImage& mRaw;
+  const Array2DRef<const uint16_t> input;
+  std::array<int, 3> sraw_coeffs;
+  int hue;
+};
+
 // ---------------------------------------------------------------- DNG
 struct DngTilingDescription {
   const iPoint2D& dim;

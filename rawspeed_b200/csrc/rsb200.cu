@@ -8,6 +8,7 @@
 #include "ljpeg_fused.cuh"
 #include "ljpeg_ranges.cuh"
 #include "rawforms.cuh"
+#include "sraw.cuh"
 #include "unpack.cuh"
 
 #include <algorithm>
@@ -69,6 +70,14 @@ struct RawGroup {
   uint32_t total_items = 0;
 };
 
+struct SrawGroup {
+  int version = 0;
+  bool is420 = false;
+  SrawJobDev* d_jobs = nullptr;
+  int njobs = 0;
+  uint32_t total_mcus = 0;
+};
+
 struct UnpackFastGroup {
   int bps;
   bool lsb;
@@ -80,7 +89,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -92,6 +101,7 @@ struct rsb200_plan {
   // fixed-layout raw forms
   std::vector<RawGroup> raw_groups;
   uint16_t* d_raw_tables = nullptr;
+  std::vector<SrawGroup> sraw_groups;
   // ljpeg
   DevTable* d_tables = nullptr;
   DevScan* d_scans = nullptr;
@@ -470,6 +480,109 @@ static cudaError_t run_raw_group(const RawGroup& g, const uint8_t* in, uint64_t 
   default:
     return cudaErrorInvalidValue;
   }
+}
+
+// ------------------------------------------------------------------
+// sRaw interpolation (K5)
+// ------------------------------------------------------------------
+extern "C" int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* jobs, int njobs,
+                                       rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "sraw_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  p->kind = 3;
+  p->nunits = njobs;
+  std::map<std::pair<int, bool>, std::vector<SrawJobDev>> buckets;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_sraw_job& j = jobs[i];
+    const bool is422 = j.sub_x == 2 && j.sub_y == 1, is420 = j.sub_x == 2 && j.sub_y == 2;
+    const uint32_t per = is420 ? 6u : 4u;
+    const bool ok = (is422 || is420) && j.version <= 2 && !(is420 && j.version == 0) &&
+                    j.num_mcus >= 2 && j.in_rows >= 1 && (j.in_offset % 4) == 0 &&
+                    (j.in_pitch % 4) == 0 && (j.out_offset % 4) == 0 && (j.out_pitch % 4) == 0 &&
+                    (uint64_t)j.num_mcus * per * 2 <= j.in_pitch &&
+                    (uint64_t)j.num_mcus * 12 <= j.out_pitch &&
+                    (uint64_t)j.num_mcus * j.in_rows < 0xFFFF0000ull;
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "sraw job %d: malformed descriptor", i);
+    }
+    SrawJobDev d;
+    memset(&d, 0, sizeof d);
+    d.in_offset = j.in_offset;
+    d.out_offset = j.out_offset;
+    d.in_pitch = j.in_pitch;
+    d.out_pitch = j.out_pitch;
+    d.num_mcus = j.num_mcus;
+    d.in_rows = j.in_rows;
+    d.k0 = j.sraw_coeffs[0];
+    d.k1 = j.sraw_coeffs[1];
+    d.k2 = j.sraw_coeffs[2];
+    d.hue = j.hue;
+    buckets[{(int)j.version, is420}].push_back(d);
+    const uint64_t out_rows = (uint64_t)j.in_rows * j.sub_y;
+    p->in_bytes += (uint64_t)j.in_rows * j.num_mcus * per * 2;
+    p->out_bytes += out_rows * j.num_mcus * 12;
+    p->pixels += out_rows * j.num_mcus * 2;
+    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + (uint64_t)(j.in_rows - 1) * j.in_pitch +
+                                                    (uint64_t)j.num_mcus * per * 2);
+    p->need_out = std::max<uint64_t>(p->need_out, j.out_offset + (out_rows - 1) * j.out_pitch +
+                                                      (uint64_t)j.num_mcus * 12);
+  }
+  for (auto& kv : buckets) {
+    SrawGroup g;
+    g.version = kv.first.first;
+    g.is420 = kv.first.second;
+    uint64_t n = 0;
+    for (auto& d : kv.second) {
+      d.mcu_begin = (uint32_t)n;
+      n += (uint64_t)d.num_mcus * d.in_rows;
+    }
+    if (n >= 0xFFFF0000ull) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_ARG, "sraw plan: too many MCUs");
+    }
+    g.total_mcus = (uint32_t)n;
+    g.njobs = (int)kv.second.size();
+    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(SrawJobDev) * kv.second.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(SrawJobDev) * kv.second.size(),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "sraw plan upload failed: %s", cudaGetErrorString(e));
+    }
+    p->sraw_groups.push_back(g);
+  }
+  p->launches_per_run = (int)p->sraw_groups.size();
+  *out = p;
+  return RSB200_OK;
+}
+
+static cudaError_t run_sraw_group(const SrawGroup& g, const uint8_t* in, uint8_t* outp,
+                                  cudaStream_t st) {
+  const uint32_t nb = (g.total_mcus + SRAW_NT - 1) / SRAW_NT;
+#define RSB_SRAW(V, T)                                                                     \
+  sraw_kernel<V, T><<<nb, SRAW_NT, 0, st>>>(in, outp, g.d_jobs, g.njobs, g.total_mcus)
+  if (g.is420) {
+    if (g.version == 1)
+      RSB_SRAW(1, true);
+    else
+      RSB_SRAW(2, true);
+  } else {
+    if (g.version == 0)
+      RSB_SRAW(0, false);
+    else if (g.version == 1)
+      RSB_SRAW(1, false);
+    else
+      RSB_SRAW(2, false);
+  }
+#undef RSB_SRAW
+  return cudaGetLastError();
 }
 
 template <int BPS, bool LSBO>
@@ -957,6 +1070,11 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->kind == 3) {
+    for (const SrawGroup& g : p->sraw_groups) {
+      CUDA_TRY(ctx, run_sraw_group(g, in, outp, st));
+      ctx->launches++;
+    }
   } else if (p->kind == 2) {
     for (const RawGroup& g : p->raw_groups) {
       if (!g.total_items)
@@ -1176,6 +1294,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   for (UnpackFastGroup& g : p->fast_groups)
     cudaFree(g.d_jobs);
   for (RawGroup& g : p->raw_groups)
+    cudaFree(g.d_jobs);
+  for (SrawGroup& g : p->sraw_groups)
     cudaFree(g.d_jobs);
   cudaFree(p->d_raw_tables);
   cudaFree(p->d_tables);

@@ -136,6 +136,19 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h, 
     return img
 
 
+def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version):
+    """Cr2sRawInterpolator(out, inp, coeffs, hue).interpolate(version) via the host mirror."""
+    k = (C.c_int * 3)(*coeffs)
+    e = _Err()
+    L = lib()
+    L.rsb200h_sraw_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + \
+        [C.c_int] * 5 + [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(_Err)]
+    e.check(L.rsb200h_sraw_interpolate(inp.ctypes.data, in_w, inp.shape[0], inp.shape[1] * 2,
+                                       out.ctypes.data, out_w, out.shape[0], out.shape[1] * 2,
+                                       sub[0], sub[1], k, hue, version, C.byref(e)))
+    return out
+
+
 def cr2_decompress(img, w, fmt, frame, slicing, tabs, tab_of_comp, init_pred, data, is_cfa=True):
     p, n = _u8(data)
     toc = (C.c_int * len(tab_of_comp))(*tab_of_comp)
