@@ -249,6 +249,33 @@ int rsb200_cr2_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables,
                            rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* Pentax PEF Huffman codec.                              */
+/*   PentaxDecompressor::decompress  decompressors/PentaxDecompressor.cpp:158-176 */
+/*   (plain MSB bit stream, one table, per-parity left predictor, row   */
+/*   starts from two rows up).  The table comes from the host:          */
+/*   SetupPrefixCodeDecoder_Legacy/_Modern :69-141.                     */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t in_offset; /* first byte of the compressed stream                    */
+  uint32_t in_size;   /* bytes available                                        */
+  uint32_t table;     /* index into the plan's table array                      */
+  int32_t width;      /* image width (even, <= 8384) and height (<= 6208)       */
+  int32_t height;
+  uint64_t out_offset; /* byte offset of image row 0                            */
+  uint32_t out_pitch;  /* bytes                                                 */
+  uint32_t reserved;
+} rsb200_pentax_job;
+
+/* rsb200_plan_results() for such a plan: status RSB200_ERR_RDE with consumed ==
+ * 0 = "bad Huffman code"; with consumed == 0x80000000 | (row << 14) | col =
+ * "decoded value out of bounds at col:row" (the first such pixel in stream order);
+ * RSB200_ERR_IOE = stream exhausted. */
+#define RSB200_PENTAX_OOB 0x80000000u
+int rsb200_pentax_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables, int ntables,
+                              const rsb200_pentax_job* jobs, int njobs, rsb200_plan** plan);
+
+
+/* ------------------------------------------------------------------ */
 /* Plan execution                                                       */
 /* ------------------------------------------------------------------ */
 /* Device-resident: d_in / d_out are device pointers (16-byte aligned; d_in must

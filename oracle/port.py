@@ -285,6 +285,51 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h,
     return img
 
 
+def pentax_decompress(img, w, data, meta=None, meta_be=True):
+    """PentaxDecompressor(img, meta).decompress(data) into img (in place)."""
+    p, n = _u8(data)
+    im = _img(img, w, 1)
+    mp, mn = (None, 0) if meta is None else _u8(meta)
+    e = Err()
+    L = lib()
+    L.rso_pentax_decompress.argtypes = [C.POINTER(Image), C.c_char_p, C.c_int, C.c_int,
+                                        C.c_char_p, C.c_uint32, C.POINTER(Err)]
+    rc = L.rso_pentax_decompress(C.byref(im), mp, mn, int(meta_be), p, C.c_uint32(n),
+                                 C.byref(e))
+    e.check(rc)
+    return img
+
+
+def pentax_table(meta=None, meta_be=True):
+    """(ncpl[16], values) the PentaxDecompressor constructor builds."""
+    mp, mn = (None, 0) if meta is None else _u8(meta)
+    ncpl = (C.c_uint8 * 16)()
+    vals = (C.c_uint8 * 16)()
+    e = Err()
+    L = lib()
+    L.rso_pentax_table.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint8),
+                                   C.POINTER(C.c_uint8), C.POINTER(Err)]
+    L.rso_pentax_table.restype = C.c_int
+    n = L.rso_pentax_table(mp, mn, int(meta_be), ncpl, vals, C.byref(e))
+    if e.code != OK:
+        raise_for(e.code, e.msg.decode("utf-8", "replace"))
+    return list(ncpl), list(vals)[:n]
+
+
+def encode_diffs_plain(diffs, ht):
+    """Huffman-encode diffs with one table into a plain MSB stream (test inputs)."""
+    d = np.ascontiguousarray(diffs, dtype=np.int32)
+    cap = d.size * 5 + 64
+    out = np.empty(cap, dtype=np.uint8)
+    L = lib()
+    L.rso_encode_diffs_plain.restype = C.c_int64
+    n = L.rso_encode_diffs_plain(d.ctypes.data_as(C.c_void_p), C.c_uint64(d.size), ht.h,
+                                 out.ctypes.data_as(C.c_void_p), C.c_uint64(cap))
+    if n < 0:
+        raise ValueError("encode_diffs_plain failed (%d)" % n)
+    return out[:n].copy()
+
+
 def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version):
     """Cr2sRawInterpolator(out, inp, coeffs, hue).interpolate(version).
     inp: uint16 array (rows, pitch/2) of which in_w columns are the subsampled data;

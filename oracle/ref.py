@@ -182,6 +182,22 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h,
     return ms.value
 
 
+def pentax_decompress(img, w, data, meta=None, meta_be=True, reps=1):
+    p, n = _u8(data)
+    mp, mn = (None, 0) if meta is None else _u8(meta)
+    ms = C.c_double(0)
+    e = Err()
+    L = lib()
+    L.ref_pentax_decompress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                        C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_int,
+                                        C.POINTER(C.c_double), C.POINTER(Err)]
+    rc = L.ref_pentax_decompress(C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                 img.shape[1] * 2, mp, mn, int(meta_be), p, C.c_uint32(n),
+                                 reps, C.byref(ms), C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
 def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version, nthreads=1, reps=1):
     """Reference Cr2sRawInterpolator; returns best wall ms."""
     k = (C.c_int * 3)(*coeffs)

@@ -40,6 +40,7 @@
 #include "decompressors/LJpegDecompressor.h"
 #include "decompressors/UncompressedDecompressor.h"
 #include "interpolators/Cr2sRawInterpolator.h"
+#include "decompressors/PentaxDecompressor.h"
 #include "io/Buffer.h"
 #include "io/ByteStream.h"
 #include "io/Endianness.h"
@@ -320,6 +321,31 @@ int ref_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
     if (best_ms)
       *best_ms = best;
     copyOut(img, out_data, out_pitch);
+  });
+}
+
+// PentaxDecompressor(mRaw, metaData).decompress(data) (PentaxDecompressor.h)
+int ref_pentax_decompress(uint16_t* img_data, int w, int h, int pitch, const uint8_t* meta,
+                          int meta_size, int meta_be, const uint8_t* data, uint32_t size,
+                          int reps, double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, 1, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      Optional<ByteStream> md;
+      if (meta)
+        md = ByteStream(DataBuffer(Buffer(meta, meta_size),
+                                   meta_be ? Endianness::big : Endianness::little));
+      PentaxDecompressor p(img, md);
+      p.decompress(ByteStream(DataBuffer(Buffer(data, size), Endianness::little)));
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
   });
 }
 

@@ -1853,6 +1853,7 @@ typedef struct {
   uint64_t acc; /* bit accumulator, MSB-first */
   int nbits;
   int overflow;
+  int plain; /* no FF00 stuffing (BitVacuumerMSB-style byte order) */
 } bitw;
 
 static void bw_byte(bitw* w, uint8_t b) {
@@ -1862,7 +1863,7 @@ static void bw_byte(bitw* w, uint8_t b) {
   else
     w->overflow = 1;
   w->n++;
-  if (b == 0xFF) {
+  if (b == 0xFF && !w->plain) {
     if (w->n < w->cap)
       w->out[w->n] = 0x00;
     else
@@ -2298,4 +2299,142 @@ int rso_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
     return RSO_OK;
   }
   THROW_RDE(&c, "Unknown subsampling: (%i; %i)", sx, sy);
+}
+
+/* ------------------------------------------------------------------ */
+/* PentaxDecompressor (decompressors/PentaxDecompressor.cpp)            */
+/* ------------------------------------------------------------------ */
+/* ByteStream::getU16 with the stream's byte order */
+static uint16_t bs_get_u16e(bstream* s, int big_endian) {
+  const uint16_t v = bs_get_u16be(s);
+  return big_endian ? v : (uint16_t)((v >> 8) | (v << 8));
+}
+static const uint8_t pentax_tree_ncpl[16] = {0, 2, 3, 1, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0};
+static const uint8_t pentax_tree_vals[13] = {3, 4, 2, 5, 1, 6, 0, 7, 8, 9, 10, 11, 12};
+
+/* SetupPrefixCodeDecoder_Legacy / _Modern (:69-141) -> (ncpl, values) */
+static int pentax_table_impl(rso_ctx* c, const uint8_t* meta, int meta_size, int meta_be,
+                             uint8_t* ncpl, uint8_t* values) {
+  uint32_t depth, i, j;
+  uint32_t v0[16], v1[16], v2[16];
+  uint8_t n17[17];
+  bstream st;
+  if (!meta) {
+    memcpy(ncpl, pentax_tree_ncpl, 16);
+    memcpy(values, pentax_tree_vals, 13);
+    return 13;
+  }
+  st.c = c;
+  st.data = meta;
+  st.size = (uint32_t)meta_size;
+  st.pos = 0;
+  /* meta_be: byte order of the ByteStream handed in (TiffEntry::getData(): the
+   * file's, PefDecoder.cpp:102-113) */
+  depth = (uint32_t)bs_get_u16e(&st, meta_be) + 12;
+  if (depth > 15)
+    THROW_RDE(c, "Depth of huffman table is too great (%u).", depth);
+  bs_skip(&st, 12);
+  for (i = 0; i < depth; i++)
+    v0[i] = bs_get_u16e(&st, meta_be);
+  for (i = 0; i < depth; i++) {
+    bs_check(&st, 1); /* ByteStream::getByte -> check(1) */
+    v1[i] = st.data[st.pos++];
+    if (v1[i] == 0 || v1[i] > 12)
+      THROW_RDE(c, "Data corrupt: v1[%u]=%u, expected [1..12]", depth, v1[i]);
+  }
+  memset(n17, 0, sizeof n17);
+  for (i = 0; i < depth; i++) {
+    /* extractHighBits(v0, v1, effectiveBitwidth=12) = v0 >> (12 - v1) */
+    v2[i] = v0[i] >> (12 - v1[i]);
+    n17[v1[i]]++;
+  }
+  memcpy(ncpl, n17 + 1, 16);
+  /* "Find smallest": repeatedly take the LAST index holding the minimum */
+  for (i = 0; i < depth; i++) {
+    uint32_t sm_val = 0xfffffff, sm_num = 0xff;
+    for (j = 0; j < depth; j++) {
+      if (v2[j] <= sm_val) {
+        sm_num = j;
+        sm_val = v2[j];
+      }
+    }
+    values[i] = (uint8_t)sm_num;
+    v2[sm_num] = 0xffffffff;
+  }
+  return (int)depth;
+}
+
+int rso_pentax_table(const uint8_t* meta, int meta_size, int meta_be, uint8_t* ncpl,
+                     uint8_t* values, rso_err* e) {
+  RSO_ENTER(c, e);
+  return pentax_table_impl(&c, meta, meta_size, meta_be, ncpl, values);
+}
+
+int rso_pentax_decompress(rso_image* img, const uint8_t* meta, int meta_size, int meta_be,
+                          const uint8_t* data, uint32_t size, rso_err* e) {
+  uint8_t ncpl[16], values[16];
+  int nv, row, col;
+  rso_huff* volatile h = NULL;
+  pump bs;
+  rso_ctx c;
+  rso_err le;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb)) {
+    free((void*)h);
+    return c.e->code;
+  }
+  /* ctor (:55-67) */
+  if (img->cpp != 1 || img->is_f32)
+    THROW_RDE(&c, "Unexpected component count / data type");
+  if (!img->w || !img->h || img->w % 2 != 0 || img->w > 8384 || img->h > 6208)
+    THROW_RDE(&c, "Unexpected image dimensions found: (%d; %d)", img->w, img->h);
+  nv = pentax_table_impl(&c, meta, meta_size, meta_be, ncpl, values);
+  h = (rso_huff*)malloc(sizeof(rso_huff));
+  if (!h)
+    THROW_RDE(&c, "out of memory");
+  huff_build(&c, (rso_huff*)h, ncpl, values, nv, 1, 0);
+  /* decompress (:158-176) */
+  pump_init(&bs, &c, RSO_MSB, data, (int)size);
+  for (row = 0; row < img->h; row++) {
+    uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch);
+    int pred[2] = {0, 0};
+    if (row >= 2) {
+      const uint16_t* up = (const uint16_t*)((const uint8_t*)img->data +
+                                             (size_t)(row - 2) * (size_t)img->pitch);
+      pred[0] = up[0];
+      pred[1] = up[1];
+    }
+    for (col = 0; col < img->w; col++) {
+      int value;
+      pred[col & 1] += huff_decode((const rso_huff*)h, &bs, 1);
+      value = pred[col & 1];
+      if (((unsigned)value >> 16) != 0) /* !isIntN(value, 16) (adt/Bit.h:83-90): 0..65535 */
+        THROW_RDE(&c, "decoded value out of bounds at %d:%d", col, row);
+      o[col] = (uint16_t)value;
+    }
+  }
+  free((void*)h);
+  return RSO_OK;
+}
+
+int64_t rso_encode_diffs_plain(const int32_t* diffs, uint64_t n, const rso_huff* ht,
+                               uint8_t* out, uint64_t cap) {
+  bitw w;
+  uint64_t i;
+  memset(&w, 0, sizeof w);
+  w.out = out;
+  w.cap = cap;
+  w.plain = 1;
+  for (i = 0; i < n; ++i)
+    if (enc_diff(&w, ht, diffs[i]))
+      return -2;
+  if (w.nbits > 0)
+    bw_put(&w, 0, 8 - w.nbits);
+  while (w.n % 4)
+    bw_put(&w, 0, 8);
+  for (i = 0; i < 16; ++i)
+    bw_put(&w, 0, 8);
+  return w.overflow ? -1 : (int64_t)w.n;
 }

@@ -137,6 +137,22 @@ int rso_dng_decompress(const uint8_t* file, uint64_t file_size,
                        int compression, int fix_ljpeg, int bps, int big_endian,
                        int nthreads, rso_err* e);
 
+/* ---- PentaxDecompressor (decompressors/PentaxDecompressor.cpp:55-177) ----
+ * meta == NULL: SetupPrefixCodeDecoder_Legacy (the built-in pentax_tree); else the
+ * "modern" table description read from `meta` (:83-141; meta_be = byte order of that ByteStream).  Decodes `data` (plain MSB
+ * bit stream) into the whole image; predictor = same-parity pixel two to the left,
+ * row starts from two rows up (:158-176). */
+int rso_pentax_decompress(rso_image* img, const uint8_t* meta, int meta_size, int meta_be,
+                          const uint8_t* data, uint32_t size, rso_err* e);
+/* Table the constructor would build: fills ncpl[16], values[<=16]; returns the
+ * number of codes (<0 and e set on a throw). */
+int rso_pentax_table(const uint8_t* meta, int meta_size, int meta_be, uint8_t* ncpl,
+                     uint8_t* values, rso_err* e);
+/* Writer for tests: Huffman-encode `diffs` with ONE table into a plain MSB stream
+ * (no stuffing), zero-padded to a multiple of 4 bytes + 16 zero bytes. */
+int64_t rso_encode_diffs_plain(const int32_t* diffs, uint64_t n, const rso_huff* ht,
+                               uint8_t* out, uint64_t cap);
+
 /* ---- Cr2sRawInterpolator (interpolators/Cr2sRawInterpolator.cpp:32-544) ----
  * in: the subsampled image as decoded (in_w uint16 per row = 4 or 6 per MCU);
  * out: 3-component image (out->sub_x/sub_y = ImageMetaData::subsampling selects

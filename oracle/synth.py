@@ -132,3 +132,40 @@ def md5_of_row_md5s(img, row_bytes=None):
         b = img[r].tobytes()
         rows.append(hashlib.md5(b if row_bytes is None else b[:row_bytes]).digest())
     return hashlib.md5(b"".join(rows)).hexdigest()
+
+
+def pentax_modern_meta(big_endian=True):
+    """A "modern" Pentax table description (PentaxDecompressor.cpp:83-141): depth 15 codes,
+    canonical, lengths {2,2,3,3,3,4,5,6,7,8,9,10,11,12,12}."""
+    lens = [3, 3, 3, 2, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 12]   # length of the code of value i
+    order = sorted(range(15), key=lambda i: (lens[i], i))
+    code, prev, codes = 0, 0, {}
+    for i in order:
+        code <<= (lens[i] - prev)
+        prev = lens[i]
+        codes[i] = code
+        code += 1
+    v0 = [codes[i] << (12 - lens[i]) for i in range(15)]
+    out = bytearray()
+    u16 = (lambda v: [v >> 8, v & 255]) if big_endian else (lambda v: [v & 255, v >> 8])
+    out += bytes(u16(15 - 12))
+    out += bytes(12)
+    for v in v0:
+        out += bytes(u16(v))
+    out += bytes(lens)
+    return bytes(out)
+
+
+def make_pentax(img, table):
+    """Encode a uint16 image (values < 32768, even width) the way PentaxDecompressor
+    decodes it: per-parity left predictor, row starts from two rows up, one plain MSB
+    stream.  `table` = (ncpl, values) as returned by port.pentax_table()."""
+    from . import port
+    h, w = img.shape
+    a = img.astype(np.int32)
+    d = np.zeros((h, w), dtype=np.int32)
+    d[:, 2:] = a[:, 2:] - a[:, :-2]
+    d[2:, :2] = a[2:, :2] - a[:-2, :2]
+    d[:2, :2] = a[:2, :2]
+    ht = port.Huff(table[0], table[1])
+    return port.encode_diffs_plain(d.reshape(-1), ht)

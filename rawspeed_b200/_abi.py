@@ -41,6 +41,15 @@ class SrawJob(C.Structure):
                 ("reserved1", C.c_uint32)]
 
 
+class PentaxJob(C.Structure):
+    _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint32), ("table", C.c_uint32),
+                ("width", C.c_int32), ("height", C.c_int32), ("out_offset", C.c_uint64),
+                ("out_pitch", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+PENTAX_OOB = 0x80000000
+
+
 class HuffTable(C.Structure):
     _fields_ = [("ncodes_per_len", C.c_uint8 * 16), ("values", C.c_uint8 * 162),
                 ("nvalues", C.c_uint16), ("fix_dng16", C.c_uint8),
@@ -75,6 +84,7 @@ EXPORTS = [
     "rsb200_abi_version", "rsb200_create", "rsb200_destroy", "rsb200_last_error",
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_raw_plan_create", "rsb200_sraw_plan_create",
+    "rsb200_pentax_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",
@@ -112,6 +122,8 @@ def load():
     L.rsb200_raw_plan_create.argtypes = [vp, C.POINTER(RawJob), i32, C.POINTER(C.c_uint16),
                                          i32, C.POINTER(vp)]
     L.rsb200_sraw_plan_create.argtypes = [vp, C.POINTER(SrawJob), i32, C.POINTER(vp)]
+    L.rsb200_pentax_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,
+                                            C.POINTER(PentaxJob), i32, C.POINTER(vp)]
     L.rsb200_ljpeg_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,
                                            C.POINTER(LJpegScan), i32, C.POINTER(vp)]
     L.rsb200_cr2_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,

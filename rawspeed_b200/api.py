@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Cr2Job, HuffTable, LJpegScan, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -167,6 +167,16 @@ def sraw_plan(ctx, jobs):
     arr = (SrawJob * len(jobs))(*jobs)
     h = C.c_void_p()
     ctx.check(ctx._lib.rsb200_sraw_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def pentax_plan(ctx, tables, jobs):
+    """Pentax PEF streams (PentaxDecompressor::decompress), one job per image."""
+    ta = (HuffTable * len(tables))(*tables)
+    ja = (PentaxJob * len(jobs))(*jobs)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_pentax_plan_create(ctx.h, ta, len(tables), ja, len(jobs),
+                                                 C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

@@ -229,6 +229,24 @@ int rsb200h_cr2_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_
   });
 }
 
+int rsb200h_pentax_decompress(uint16_t* img_data, int w, int h, int pitch, const uint8_t* meta,
+                              int meta_size, int meta_be, const uint8_t* data, uint32_t size,
+                              rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, 1, pitch, true, 1, 1);
+    ByteStream md(meta, meta ? (Buffer::size_type)meta_size : 0,
+                  meta_be ? Endianness::big : Endianness::little);
+    PentaxDecompressor p(img, meta ? &md : nullptr);
+    try {
+      p.decompress(ByteStream(data, size));
+    } catch (...) {
+      copyOut(img, img_data);
+      throw;
+    }
+    copyOut(img, img_data);
+  });
+}
+
 int rsb200h_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
                              uint16_t* out_data, int out_w, int out_h, int out_pitch, int sub_x,
                              int sub_y, const int* coeffs, int hue, int version,

@@ -433,6 +433,105 @@ void UncompressedDecompressor::readUncompressedRaw() {
   runOnImage(pg.p, input.begin(), input.getRemainSize(), mRaw, /*partial=*/true);
 }
 
+// ------------------------------------------------------------------ Pentax
+PentaxDecompressor::PentaxDecompressor(RawImage img, const ByteStream* metaData)
+    : mRaw(std::move(img)), ht(SetupPrefixCodeDecoder(metaData)) {
+  if (mRaw->getCpp() != 1 || mRaw->getDataType() != RawImageType::UINT16 ||
+      mRaw->getBpp() != sizeof(uint16_t))
+    ThrowRDE("Unexpected component count / data type");
+  if (!mRaw->dim.x || !mRaw->dim.y || mRaw->dim.x % 2 != 0 || mRaw->dim.x > 8384 ||
+      mRaw->dim.y > 6208)
+    ThrowRDE("Unexpected image dimensions found: (%d; %d)", mRaw->dim.x, mRaw->dim.y);
+}
+
+HuffmanCode<> PentaxDecompressor::SetupPrefixCodeDecoder_Legacy() {
+  // PentaxDecompressor::pentax_tree (PentaxDecompressor.cpp:46-53)
+  static const uint8_t ncpl[16] = {0, 2, 3, 1, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0};
+  static const uint8_t vals[13] = {3, 4, 2, 5, 1, 6, 0, 7, 8, 9, 10, 11, 12};
+  HuffmanCode<> hc;
+  hc.setNCodesPerLength(Buffer(ncpl, 16));
+  hc.setCodeValues(vals, 13);
+  return hc;
+}
+
+HuffmanCode<> PentaxDecompressor::SetupPrefixCodeDecoder_Modern(ByteStream stream) {
+  const uint32_t depth = (uint32_t)stream.getU16() + 12;
+  if (depth > 15)
+    ThrowRDE("Depth of huffman table is too great (%u).", depth);
+  stream.skipBytes(12);
+  uint32_t v0[16], v1[16], v2[16];
+  for (uint32_t i = 0; i < depth; i++)
+    v0[i] = stream.getU16();
+  for (uint32_t i = 0; i < depth; i++) {
+    v1[i] = stream.getByte();
+    if (v1[i] == 0 || v1[i] > 12)
+      ThrowRDE("Data corrupt: v1[%u]=%u, expected [1..12]", depth, v1[i]);
+  }
+  uint8_t nCodesPerLength[17] = {0};
+  for (uint32_t c = 0; c < depth; c++) {
+    v2[c] = v0[c] >> (12 - v1[c]); // extractHighBits(v0, v1, effectiveBitwidth = 12)
+    nCodesPerLength[v1[c]]++;
+  }
+  HuffmanCode<> hc;
+  hc.setNCodesPerLength(Buffer(nCodesPerLength + 1, 16));
+  // code values in increasing code order: repeatedly the LAST index holding the minimum
+  uint8_t codeValues[16];
+  for (uint32_t i = 0; i < depth; i++) {
+    uint32_t sm_val = 0xfffffff, sm_num = 0xff;
+    for (uint32_t j = 0; j < depth; j++) {
+      if (v2[j] <= sm_val) {
+        sm_num = j;
+        sm_val = v2[j];
+      }
+    }
+    codeValues[i] = (uint8_t)sm_num;
+    v2[sm_num] = 0xffffffff;
+  }
+  hc.setCodeValues(codeValues, (int)depth);
+  return hc;
+}
+
+PrefixCodeDecoder<> PentaxDecompressor::SetupPrefixCodeDecoder(const ByteStream* metaData) {
+  PrefixCodeDecoder<> d(metaData ? SetupPrefixCodeDecoder_Modern(*metaData)
+                                 : SetupPrefixCodeDecoder_Legacy());
+  d.setup(true, false);
+  return d;
+}
+
+void PentaxDecompressor::decompress(ByteStream data) const {
+  if (data.getRemainSize() < 4) // BitStreamerMSB ctor (BitStreamer.h:56-60)
+    ThrowIOE("Bit stream size is smaller than MaxProcessBytes");
+  rsb200_huff_table t = ht.deviceTable();
+  rsb200_pentax_job job;
+  std::memset(&job, 0, sizeof job);
+  job.in_offset = 0;
+  job.in_size = data.getRemainSize();
+  job.table = 0;
+  job.width = mRaw->dim.x;
+  job.height = mRaw->dim.y;
+  job.out_offset = 0;
+  job.out_pitch = (uint32_t)mRaw->pitch;
+  PlanGuard pg;
+  engineCheck(rsb200_pentax_plan_create(engine(), &t, 1, &job, 1, &pg.p),
+              "rsb200_pentax_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, data.begin() + data.getPosition(), data.getRemainSize(), img,
+             /*partial=*/true);
+  rsb200_scan_result res;
+  const int rc = rsb200_plan_results(pg.p, &res, 1);
+  if (rc == RSB200_OK)
+    return;
+  if (res.status == RSB200_ERR_RDE && (res.consumed & RSB200_PENTAX_OOB)) {
+    const uint32_t key = res.consumed & ~RSB200_PENTAX_OOB;
+    ThrowRDE("decoded value out of bounds at %d:%d", (int)(key & 0x3FFFu), (int)(key >> 14));
+  }
+  if (res.status == RSB200_ERR_RDE)
+    ThrowRDE("bad Huffman code");
+  if (res.status == RSB200_ERR_IOE)
+    ThrowIOE("Buffer overflow read in BitStreamer");
+  engineCheck(rc, "rsb200_plan_results");
+}
+
 // ------------------------------------------------------------------ sRaw
 // Cr2sRawInterpolator::interpolate (interpolators/Cr2sRawInterpolator.cpp:499-542)
 void Cr2sRawInterpolator::interpolate(int version) {

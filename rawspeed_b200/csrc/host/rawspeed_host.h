@@ -447,6 +447,26 @@ private:
   std::unique_ptr<Cr2Decompressor<>> d;
 };
 
+// ---------------------------------------------------------------- Pentax
+// decompressors/PentaxDecompressor.h: same constructor (image + optional table
+// description from the maker note) and decompress(ByteStream).  Table set-up and
+// validation on the host (PentaxDecompressor.cpp:55-153), the Huffman decode and
+// the predictor on the device.
+class PentaxDecompressor final {
+public:
+  // metaData == nullptr: the built-in legacy table
+  PentaxDecompressor(RawImage img, const ByteStream* metaData);
+  void decompress(ByteStream data) const;
+  const PrefixCodeDecoder<>& table() const { return ht; }
+
+private:
+  static HuffmanCode<> SetupPrefixCodeDecoder_Legacy();
+  static HuffmanCode<> SetupPrefixCodeDecoder_Modern(ByteStream stream);
+  static PrefixCodeDecoder<> SetupPrefixCodeDecoder(const ByteStream* metaData);
+  RawImage mRaw;
+  const PrefixCodeDecoder<> ht;
+};
+
 // ---------------------------------------------------------------- sRaw
 // adt/Array2DRef.h: non-owning 2-D view (pitch in elements)
 template <typename T> class Array2DRef {

@@ -60,10 +60,12 @@ struct DevScan {
   uint8_t group;        // samples per MCU / CR2 group
   uint8_t ncomp;
   uint8_t multi_table;  // components use different tables -> phase matters
-  uint8_t kind;         // 0 = LJPEG tile, 1 = CR2
+  uint8_t kind;         // 0 = LJPEG tile, 1 = CR2, 2 = Pentax (K3P reconstruction)
   uint8_t table_of[12]; // slot (0..3) of the block-local table of sample p
   uint8_t pattern;      // component pattern of a group (PAT_*)
-  uint8_t pad0[11];
+  uint8_t pump;         // 0 = JPEG bit source (FF00 stuffing, FFxx ends the data);
+                        // 1 = plain MSB (BitStreamerMSB: bytes as they are)
+  uint8_t pad0[10];
   int32_t table_idx[4]; // plan table index per slot (-1 unused)
   uint8_t first_idx[4]; // position in the group of the first sample of comp c
   uint16_t init_pred[4];
@@ -110,6 +112,7 @@ struct BitSrc {
   int fake;        // zero bits pushed after the end marker (multiple of 8)
   uint32_t cur_w0; // cached aligned word containing bytepos
   uint32_t cur_idx;
+  bool plain = false; // BitStreamerMSB: no stuffing, no markers
 
   __device__ __forceinline__ uint32_t load_word(uint32_t idx) const {
     const uint32_t b = idx << 2;
@@ -173,7 +176,7 @@ struct BitSrc {
       uint32_t w0 = (idx == cur_idx) ? cur_w0 : load_word(idx);
       uint32_t w1 = load_word(idx + 1);
       const uint32_t raw = __funnelshift_r(w0, w1, (bytepos & 3) * 8);
-      if (__vcmpeq4(raw, 0xFFFFFFFFu) == 0u) {
+      if (plain || __vcmpeq4(raw, 0xFFFFFFFFu) == 0u) {
         push32(__byte_perm(raw, 0, 0x0123));
         bytepos += 4;
         cur_idx = idx + 1;
@@ -224,8 +227,9 @@ struct BitSrc {
     if (nbytes < 8)
       win &= (1ull << (8 * nbytes)) - 1ull;
     const uint32_t l = (uint32_t)win, h = (uint32_t)(win >> 32);
-    const int nff = (__popc(__vcmpeq4(l, 0xFFFFFFFFu)) +
-                     __popc(__vcmpeq4(h, 0xFFFFFFFFu))) >> 3;
+    const int nff = plain ? 0
+                          : (__popc(__vcmpeq4(l, 0xFFFFFFFFu)) +
+                             __popc(__vcmpeq4(h, 0xFFFFFFFFu))) >> 3;
     const uint32_t b = bytepos - (uint32_t)nbytes - (uint32_t)nff;
     const uint32_t o = (8u - ((uint32_t)real & 7u)) & 7u;
     return 8u * b + o;
@@ -343,6 +347,7 @@ k2_scan_sub(const K2Shared& sh, const DevScan& sc, const uint32_t* base,
   uint32_t m = ffmask & (0x7FFFFFFFu) & (0xFFFFFFFFu << sb);
   int left = (int)(sub_end_bit - start) - 8 * __popc(m);
   BitSrc bs;
+  bs.plain = sc.pump != 0;
   bs.init(base, limit, start);
   uint32_t cnt = 0;
   const DevTable* t0 = &sh.tab[0];
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(K2_THREADS)
 
     // FF map of my subsequence (bit k = byte k is FF)
     uint32_t ffmask = 0;
-    if (active) {
+    if (active && sc.pump == 0) { // (the plain MSB pump has no stuffing: mask stays 0)
 #pragma unroll
       for (int k = 0; k < SUBSEQ_BYTES / 4; ++k) {
         const uint32_t idx = (sub_byte >> 2) + k;
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(K2_THREADS)
 
     // ---- self-synchronisation ----
     uint32_t my_start = (tid == 0) ? carry_pos : sub_byte * 8u;
-    if (tid != 0 && sub_byte > 0 && active) {
+    if (tid != 0 && sub_byte > 0 && active && sc.pump == 0) {
       // a guess must not begin on a stuffing byte
       BitSrc probe;
       probe.w = base;
@@ -526,6 +531,7 @@ __global__ void __launch_bounds__(K2_THREADS)
     // ---- decode + write differences ----
     if (d.count != 0 && sym0 < sc.n_samples) {
       BitSrc bs;
+      bs.plain = sc.pump != 0;
       bs.init(base, limit, my_start);
       uint32_t phase = sym0 % sc.group;
       uint32_t consumed_bits = 0;
@@ -562,7 +568,7 @@ __global__ void __launch_bounds__(K2_THREADS)
           bool marker = false;
           while (need > 0) {
             const uint32_t c0 = bs.byte_at(p);
-            if (c0 == 0xFFu) {
+            if (c0 == 0xFFu && sc.pump == 0) {
               const uint32_t c1 = bs.byte_at(p + 1);
               if (c1 != 0u) {
                 marker = true;
@@ -619,7 +625,7 @@ __global__ void k3_column_kernel(const DevScan* __restrict__ scans,
   if (si >= nscans)
     return;
   const DevScan& sc = scans[scan_ids ? scan_ids[si] : (uint32_t)si];
-  if (c >= sc.ncomp)
+  if (c >= sc.ncomp || sc.kind == 2) // (kind 2: pentax.cuh reconstructs)
     return;
   const uint16_t* d = diffs + sc.diff_offset + sc.first_idx[c];
   uint16_t* cv = colvals + sc.col_offset + c;
@@ -814,6 +820,8 @@ __global__ void __launch_bounds__(K3_THREADS)
     return;
   const K3RowRef ref = rows[wrow];
   const DevScan& sc = scans[ref.scan];
+  if (sc.kind == 2) // pentax.cuh reconstructs
+    return;
   // warp-uniform dispatch on the group layout
   if (sc.pattern == PAT_H2V1)
     k3_row_body<4, PAT_H2V1>(sc, ref.row, diffs, colvals, strips, out);

@@ -458,6 +458,7 @@ struct FStream {
   uint64_t readable;    // bytes that may be touched by the bulk copies
   uint32_t chunk_begin; // first chunk this CTA processes
   uint32_t chunk_end;   // one past the last chunk that may be prefetched
+  bool plain;           // plain MSB bit source: no FF00 stuffing, no end marker
   bool pending;         // a bulk copy is in flight (uniform)
   uint32_t pending_par; // ... and completes the mbarrier phase of this parity
 };
@@ -505,10 +506,12 @@ __device__ __forceinline__ FChunk f_unstuff(FusedShared& sh, FStream& st, const 
           w[k] = b >= st.limit ? 0u : (w[k] & (0xFFFFFFFFu >> (32 - 8 * (st.limit - b))));
       }
     }
+    if (!st.plain) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (__vcmpeq4(w[k], 0xFFFFFFFFu))
-        ffm |= byte_eq_mask(w[k], 0xFFFFFFFFu) << (4 * k);
+      for (int k = 0; k < 8; ++k)
+        if (__vcmpeq4(w[k], 0xFFFFFFFFu))
+          ffm |= byte_eq_mask(w[k], 0xFFFFFFFFu) << (4 * k);
+    }
     // bytes that belong to the segment: [st.skew, st.limit)
     uint32_t valid = 0xFFFFFFFFu;
     if (raw0 < st.skew)
@@ -521,6 +524,8 @@ __device__ __forceinline__ FChunk f_unstuff(FusedShared& sh, FStream& st, const 
       prev_ff = cy.prev_ff;
     else
       prev_ff = ((rw[tid * 8 - 1] >> 24) == 0xFFu) && (raw0 - 1 >= st.skew) && (raw0 - 1 < st.limit);
+    if (st.plain)
+      prev_ff = 0;
     uint32_t stuff = 0, mk = 0;
     if (ffm | prev_ff) {
       uint32_t zm = 0;
@@ -723,6 +728,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
   st.readable = readable;
   st.chunk_begin = 0;
   st.chunk_end = nchunks_max;
+  st.plain = sc.pump != 0;
   st.pending = true;
   st.pending_par = 0;
   if (tid == 0)
@@ -829,7 +835,7 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
           const uint32_t p = b.p;
           if (final_chunk && p > len * 8u)
             my_status |= 2u; // a needed symbol runs past the end of the data
-          if (plast != 0xFFFFFFFFu) {
+          if (plast != 0xFFFFFFFFu && !st.plain) {
             bool ovr = false;
             results[blockIdx.x].consumed =
                 f_stream_position(sh, cy, gbase, limit, skew, chunk, plast, &ovr);
@@ -1040,20 +1046,20 @@ fused_body(FusedShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
             uint32_t adv = Lc;
             while (adv) {
               const uint32_t c0 = f_raw_byte(gbase, limit, rp);
-              rp += (c0 == 0xFFu) ? 2 : 1;
+              rp += (c0 == 0xFFu && !st.plain) ? 2 : 1;
               --adv;
             }
           }
           while (k) {
             --rp;
-            if (rp > skew && f_raw_byte(gbase, limit, rp) == 0u &&
+            if (!st.plain && rp > skew && f_raw_byte(gbase, limit, rp) == 0u &&
                 f_raw_byte(gbase, limit, rp - 1) == 0xFFu)
               --rp; // stuffing byte: its FF is the clean byte
             --k;
           }
           c2.tail_raw = rp;
         }
-        c2.prev_ff = (sh.last_raw_byte == 0xFFu) &&
+        c2.prev_ff = !st.plain && (sh.last_raw_byte == 0xFFu) &&
                      ((chunk + 1) * (uint32_t)F_RAW - 1 < limit) &&
                      ((chunk + 1) * (uint32_t)F_RAW - 1 >= skew);
         c2.ended = final_chunk ? 1u : 0u;

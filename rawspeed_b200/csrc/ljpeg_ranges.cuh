@@ -127,6 +127,7 @@ __device__ __forceinline__ void r_stream(const FusedShared& sh, const uint8_t* i
   }
   st.chunk_begin = c_first;
   st.chunk_end = (st.limit + F_RAW - 1) / F_RAW;
+  st.plain = sc.pump != 0;
   st.pending = true;
   st.pending_par = 0;
 }
@@ -428,7 +429,7 @@ __device__ __forceinline__ void range_diffs_body(FusedShared& sh, const uint8_t*
       const uint32_t p = b.p;
       if (co.final_chunk && p > co.len * 8u)
         my_status |= 2u;
-      if (plast != 0xFFFFFFFFu) {
+      if (plast != 0xFFFFFFFFu && !st.plain) {
         // the reference's pump looks at the whole buffer, not just this range
         const uint32_t full_limit = st.skew + sc.in_size;
         bool ovr = false;
@@ -459,7 +460,7 @@ __device__ __forceinline__ void range_diffs_body(FusedShared& sh, const uint8_t*
         uint32_t k = tail;
         while (k) {
           --rp;
-          if (rp > st.skew && f_raw_byte(st.gbase, st.limit, rp) == 0u &&
+          if (!st.plain && rp > st.skew && f_raw_byte(st.gbase, st.limit, rp) == 0u &&
               f_raw_byte(st.gbase, st.limit, rp - 1) == 0xFFu)
             --rp;
           --k;
@@ -512,11 +513,14 @@ __global__ void __launch_bounds__(F_NT, 5)
 
 // results of the multi-CTA path are accumulated with atomicOr: clear them first
 __global__ void k2_clear_results_kernel(const BigScanInfo* __restrict__ big, int nbig,
-                                        DevResult* __restrict__ results) {
+                                        DevResult* __restrict__ results,
+                                        uint32_t* __restrict__ oob) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nbig) {
     results[big[i].scan].status = 0;
     results[big[i].scan].consumed = 0;
+    if (oob)
+      oob[big[i].scan] = 0xFFFFFFFFu; // (pentax.cuh: first out-of-bounds pixel)
   }
 }
 

@@ -9,6 +9,7 @@
 #include "ljpeg_ranges.cuh"
 #include "rawforms.cuh"
 #include "sraw.cuh"
+#include "pentax.cuh"
 #include "unpack.cuh"
 
 #include <algorithm>
@@ -126,6 +127,10 @@ struct rsb200_plan {
   RangeFinal* d_finals = nullptr;
   uint32_t* d_fallback = nullptr;
   int nranges = 0;
+  // Pentax segments (DevScan::kind == 2): first out-of-bounds pixel per segment
+  uint32_t* d_oob = nullptr;
+  uint32_t* h_oob = nullptr; // pinned
+  bool has_pentax = false, has_k3 = false;
   cudaStream_t last_stream = nullptr;
   bool ran = false;
 };
@@ -765,7 +770,9 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   b.col_elems = 0;
   for (size_t i = 0; i < b.scans.size(); ++i) {
     DevScan& d = b.scans[i];
-    const bool is_big = d.kind == 1 || d.in_size > BIG_SEGMENT_BYTES;
+    const bool is_big = d.kind != 0 || d.in_size > BIG_SEGMENT_BYTES;
+    if (is_big)
+      (d.kind == 2 ? p->has_pentax : p->has_k3) = true;
     if (!is_big) {
       small_ids.push_back((uint32_t)i);
       continue;
@@ -822,12 +829,80 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   alloc((void**)&p->d_results, sizeof(DevResult) * b.scans.size());
   if (e == cudaSuccess)
     e = cudaMallocHost((void**)&p->h_results, sizeof(DevResult) * b.scans.size());
+  if (p->has_pentax) {
+    alloc((void**)&p->d_oob, sizeof(uint32_t) * b.scans.size());
+    if (e == cudaSuccess)
+      e = cudaMallocHost((void**)&p->h_oob, sizeof(uint32_t) * b.scans.size());
+  }
   if (e != cudaSuccess) {
     rsb200_plan_destroy(p);
     return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
                    cudaGetErrorString(e));
   }
-  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->nbig ? 7 : 0);
+  p->launches_per_run = (p->nsmall ? 1 : 0) +
+                        (p->nbig ? 5 + (p->has_k3 ? 2 : 0) + (p->has_pentax ? 2 : 0) : 0);
+  return RSB200_OK;
+}
+
+// ------------------------------------------------------------------
+// Pentax: one long plain-MSB Huffman stream per image (K2R + K3P)
+// ------------------------------------------------------------------
+extern "C" int rsb200_pentax_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables,
+                                         int ntables, const rsb200_pentax_job* jobs, int njobs,
+                                         rsb200_plan** out) {
+  if (!ctx || !tables || ntables <= 0 || !jobs || njobs <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "pentax_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  ScanBuild b;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_pentax_job& j = jobs[i];
+    // PentaxDecompressor ctor (PentaxDecompressor.cpp:55-67)
+    const bool ok = j.width > 0 && j.height > 0 && j.width % 2 == 0 && j.width <= 8384 &&
+                    j.height <= 6208 && (int)j.table < ntables && j.in_size < (1u << 28) &&
+                    (uint64_t)j.width * 2 <= j.out_pitch && (j.out_offset % 4) == 0 &&
+                    (j.out_pitch % 4) == 0;
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "pentax job %d: malformed descriptor", i);
+    }
+    DevScan d;
+    memset(&d, 0, sizeof d);
+    d.in_offset = j.in_offset;
+    d.in_size = j.in_size;
+    d.row_samples = (uint32_t)j.width;
+    d.rows = (uint32_t)j.height;
+    d.n_samples = (uint32_t)j.width * (uint32_t)j.height;
+    d.group = 2;
+    d.ncomp = 2;
+    d.kind = 2;
+    d.pump = 1;
+    d.pattern = PAT_PLAIN;
+    const uint8_t tab[4] = {(uint8_t)j.table, (uint8_t)j.table, 0, 0};
+    const uint8_t comp_of_pos[2] = {0, 1};
+    assign_tables(d, tab, 2, comp_of_pos, 2);
+    d.first_idx[0] = 0;
+    d.first_idx[1] = 1;
+    d.out_offset = j.out_offset;
+    d.out_pitch = j.out_pitch;
+    d.mcu_w = 2;
+    d.mcu_h = 1;
+    d.store_w = (uint32_t)j.width;
+    b.scans.push_back(d);
+    p->in_bytes += j.in_size;
+    p->out_bytes += (uint64_t)j.width * j.height * 2;
+    p->pixels += (uint64_t)j.width * j.height;
+    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + j.in_size);
+    p->need_out = std::max<uint64_t>(
+        p->need_out, j.out_offset + (uint64_t)(j.height - 1) * j.out_pitch + 2ull * j.width);
+  }
+  int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/false);
+  if (rc != RSB200_OK)
+    return rc;
+  *out = p;
   return RSB200_OK;
 }
 
@@ -1093,7 +1168,7 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
     }
     if (p->nbig) {
       k2_clear_results_kernel<<<(p->nbig + 127) / 128, 128, 0, st>>>(p->d_big, p->nbig,
-                                                                     p->d_results);
+                                                                     p->d_results, p->d_oob);
       k2_range_count_kernel<<<p->nranges, F_NT, fsm, st>>>(in, (uint64_t)in_bytes, p->d_scans,
                                                            p->d_tables, p->d_ranges, p->d_states);
       k2_range_verify_kernel<<<p->nbig, V_NT, 0, st>>>(p->d_scans, p->d_big, p->d_states,
@@ -1106,13 +1181,24 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
           in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->d_diffs, p->d_results,
           p->d_big_ids, p->d_fallback);
       const int col_warps = p->nbig * 4;
-      k3_column_kernel<<<(col_warps * 32 + 127) / 128, 128, 0, st>>>(
-          p->d_scans, p->d_big_ids, p->nbig, p->d_diffs, p->d_colvals);
       const uint32_t rows_per_block = K3_THREADS / 32;
-      k3_row_kernel<<<(p->nrows + rows_per_block - 1) / rows_per_block, K3_THREADS, 0, st>>>(
-          p->d_scans, p->d_rows, p->nrows, p->d_diffs, p->d_colvals, p->d_strips, outp);
+      int nk3 = 0;
+      if (p->has_k3) {
+        k3_column_kernel<<<(col_warps * 32 + 127) / 128, 128, 0, st>>>(
+            p->d_scans, p->d_big_ids, p->nbig, p->d_diffs, p->d_colvals);
+        k3_row_kernel<<<(p->nrows + rows_per_block - 1) / rows_per_block, K3_THREADS, 0, st>>>(
+            p->d_scans, p->d_rows, p->nrows, p->d_diffs, p->d_colvals, p->d_strips, outp);
+        nk3 += 2;
+      }
+      if (p->has_pentax) {
+        k3p_column_kernel<<<(col_warps * 32 + 127) / 128, 128, 0, st>>>(
+            p->d_scans, p->d_big_ids, p->nbig, p->d_diffs, p->d_colvals, p->d_oob);
+        k3p_row_kernel<<<(p->nrows + rows_per_block - 1) / rows_per_block, K3_THREADS, 0, st>>>(
+            p->d_scans, p->d_rows, p->nrows, p->d_diffs, p->d_colvals, outp, p->d_oob);
+        nk3 += 2;
+      }
       CUDA_TRY(ctx, cudaGetLastError());
-      ctx->launches += 7;
+      ctx->launches += 5 + nk3;
     }
   }
   p->last_stream = st;
@@ -1249,9 +1335,27 @@ extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, 
   }
   CUDA_TRY(ctx, cudaMemcpyAsync(p->h_results, p->d_results, sizeof(DevResult) * p->nscans,
                                 cudaMemcpyDeviceToHost, p->last_stream));
+  if (p->d_oob)
+    CUDA_TRY(ctx, cudaMemcpyAsync(p->h_oob, p->d_oob, sizeof(uint32_t) * p->nscans,
+                                  cudaMemcpyDeviceToHost, p->last_stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
   int first = RSB200_OK;
   for (int i = 0; i < p->nscans; ++i) {
+    if (p->d_oob && p->h_results[i].status == 0 && p->h_oob[i] != 0xFFFFFFFFu) {
+      // Pentax: a decoded value left 0..65535 (PentaxDecompressor.cpp:170-171)
+      p->h_results[i].status = RSB200_ERR_RDE;
+      p->h_results[i].consumed = RSB200_PENTAX_OOB | p->h_oob[i];
+      if (results && i < n) {
+        results[i].status = p->h_results[i].status;
+        results[i].consumed = p->h_results[i].consumed;
+      }
+      if (first == RSB200_OK) {
+        first = RSB200_ERR_RDE;
+        set_err(ctx, first, "decoded value out of bounds at %u:%u", p->h_oob[i] & 0x3FFFu,
+                p->h_oob[i] >> 14);
+      }
+      continue;
+    }
     if (results && i < n) {
       results[i].status = p->h_results[i].status;
       results[i].consumed = p->h_results[i].consumed;
@@ -1312,6 +1416,9 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   cudaFree(p->d_states);
   cudaFree(p->d_finals);
   cudaFree(p->d_fallback);
+  cudaFree(p->d_oob);
+  if (p->h_oob)
+    cudaFreeHost(p->h_oob);
   if (p->h_results)
     cudaFreeHost(p->h_results);
   delete p;

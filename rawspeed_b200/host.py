@@ -136,6 +136,21 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h, 
     return img
 
 
+def pentax_decompress(img, w, data, meta=None, meta_be=True):
+    """PentaxDecompressor(img, meta).decompress(data) via the host mirror."""
+    p, n = _u8(data)
+    mp, mn = (None, 0) if meta is None else _u8(meta)
+    e = _Err()
+    L = lib()
+    L.rsb200h_pentax_decompress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                            C.c_int, C.c_int, C.c_char_p, C.c_uint32,
+                                            C.POINTER(_Err)]
+    e.check(L.rsb200h_pentax_decompress(C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                        img.shape[1] * 2, mp, mn, int(meta_be), p,
+                                        C.c_uint32(n), C.byref(e)))
+    return img
+
+
 def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version):
     """Cr2sRawInterpolator(out, inp, coeffs, hue).interpolate(version) via the host mirror."""
     k = (C.c_int * 3)(*coeffs)

@@ -38,6 +38,7 @@ def test_struct_layouts_match_header(tmp_path):
 int main(void){
   printf("%zu %zu %zu %zu %zu\n", sizeof(rsb200_unpack_job), sizeof(rsb200_huff_table),
          sizeof(rsb200_ljpeg_scan), sizeof(rsb200_scan_result), sizeof(rsb200_cr2_job));
+  printf("%zu %zu %zu\n", sizeof(rsb200_pentax_job), offsetof(rsb200_pentax_job, width), offsetof(rsb200_pentax_job, out_pitch));
   printf("%zu %zu %zu %zu\n", sizeof(rsb200_sraw_job), offsetof(rsb200_sraw_job, sraw_coeffs), offsetof(rsb200_sraw_job, out_offset), offsetof(rsb200_sraw_job, out_pitch));
   printf("%zu %zu %zu\n", sizeof(rsb200_raw_job), offsetof(rsb200_raw_job, format), offsetof(rsb200_raw_job, table));
   printf("%zu %zu %zu %zu\n", offsetof(rsb200_ljpeg_scan, init_pred), offsetof(rsb200_ljpeg_scan, out_offset),
@@ -49,6 +50,7 @@ int main(void){
     got = [int(x) for x in out]
     want = [C.sizeof(_abi.UnpackJob), C.sizeof(_abi.HuffTable), C.sizeof(_abi.LJpegScan),
             C.sizeof(_abi.ScanResult), C.sizeof(_abi.Cr2Job),
+            C.sizeof(_abi.PentaxJob), _abi.PentaxJob.width.offset, _abi.PentaxJob.out_pitch.offset,
             C.sizeof(_abi.SrawJob), _abi.SrawJob.sraw_coeffs.offset,
             _abi.SrawJob.out_offset.offset, _abi.SrawJob.out_pitch.offset,
             C.sizeof(_abi.RawJob), _abi.RawJob.format.offset, _abi.RawJob.table.offset,
