@@ -523,6 +523,85 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
         out["configs[3] CR2 6720x4480 3 slices <%d,1,1>" % fmt[0]] = ent
         del plan, d_in, d_out
     out.update(bench_forms(torch, rs, ctx, port, synth, args, dist, peak))
+    out.update(bench_codecs(torch, rs, ctx, port, synth, args, dist, peak))
+    return out
+
+
+def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
+    """Canon sRaw interpolation and the Pentax PEF codec, device-timed."""
+    out = {}
+    steps = max(3, min(args.steps, 10))
+    rank0 = int(os.environ.get("RANK", "0")) == 0
+    # ---- Cr2sRawInterpolator, 4:2:0 version 2, 5040x3360 RGB output (mRAW class) ----
+    num_mcus, rows = 2520, 1680
+    rng = np.random.default_rng(5)
+    in_w = num_mcus * 6
+    pitch = (in_w * 2 + 15) // 16 * 16
+    inp = np.zeros((rows, pitch // 2), dtype=np.uint16)
+    inp[:, :in_w] = rng.integers(0, 16384, (rows, in_w), dtype=np.uint16)
+    out_w, out_h = 2 * num_mcus, 2 * rows
+    want = port.new_image(out_w, out_h, 3)
+    j = rs.SrawJob()
+    j.in_offset, j.in_pitch, j.num_mcus, j.in_rows = 0, pitch, num_mcus, rows
+    j.sub_x, j.sub_y, j.version = 2, 2, 2
+    j.sraw_coeffs[0], j.sraw_coeffs[1], j.sraw_coeffs[2] = 2000, 1024, 1500
+    j.hue, j.out_offset, j.out_pitch = 0, 0, want.shape[1] * 2
+    plan = rs.sraw_plan(ctx, [j])
+    d_in = torch.from_numpy(inp.view(np.int16)).cuda()
+    d_out = torch.from_numpy(want.view(np.int16).copy()).cuda()
+    plan.run(d_in, d_out)
+    torch.cuda.synchronize()
+    port.sraw_interpolate(inp, in_w, want, out_w, (2, 2), (2000, 1024, 1500), 0, 2)
+    exact = bool(np.array_equal(d_out.cpu().numpy().view(np.uint16), want))
+    ms = time_steps(torch, lambda: plan.run(d_in, d_out), steps, 3, dist)
+    in_b, out_b, pixels = plan.bytes()
+    per = ms / steps
+    ent = {"MPixels/s": pixels / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
+           "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
+           "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak, "kernel": "sraw_kernel<2,420>"}
+    if not args.skip_cpu and rank0:
+        import oracle
+        if oracle.HAVE_REF:
+            ncores = os.cpu_count() or 1
+            tmp = want.copy()
+            msr = min(oracle.ref.sraw_interpolate(inp, in_w, tmp, out_w, (2, 2), (2000, 1024, 1500), 0, 2,
+                                                  nthreads=ncores) for _ in range(3))
+            ent["cpu_reference"] = {"kind": "reference", "cores": ncores,
+                                    "MPixels/s": pixels / (msr * 1e-3) / 1e6,
+                                    "sample": "Cr2sRawInterpolator::interpolate(2), OpenMP rows, best of 3"}
+    out["8(f)2 Cr2sRawInterpolator 4:2:0 -> 5040x3360 RGB"] = ent
+    del plan, d_in, d_out
+    # ---- PentaxDecompressor, 6016x4000 (K-3 class), legacy table ----
+    w, h = 6016, 4000
+    table = port.pentax_table(None)
+    img = (synth.image_model(w, h, seed=11, bits=12) & 0x0FFF).astype(np.uint16)
+    data = synth.make_pentax(img, table)
+    got0 = port.new_image(w, h)
+    pj = rs.PentaxJob()
+    pj.in_offset, pj.in_size, pj.table, pj.width, pj.height = 0, data.size, 0, w, h
+    pj.out_offset, pj.out_pitch = 0, got0.shape[1] * 2
+    plan = rs.pentax_plan(ctx, [rs.huff_table(table[0], table[1])], [pj])
+    d_in = torch.zeros(data.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[:data.size] = torch.from_numpy(data)
+    d_out = torch.from_numpy(got0.view(np.int16).copy()).cuda()
+    plan.run((d_in.data_ptr(), data.size), d_out)
+    res = plan.results()
+    exact = bool(np.array_equal(d_out.cpu().numpy().view(np.uint16)[:, :w], img)) and res[0][0] == 0
+    ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), data.size), d_out), 3, 1, dist)
+    per = ms / 3
+    ent = {"MPixels/s": w * h / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
+           "compressed_bytes_per_pixel": data.size / (w * h),
+           "kernels": "k2_range_count/verify/diffs (plain MSB pump) + k3p_column/row"}
+    if not args.skip_cpu and rank0:
+        import oracle
+        if oracle.HAVE_REF:
+            tmp = port.new_image(w, h)
+            msr = min(oracle.ref.pentax_decompress(tmp, w, data) for _ in range(2))
+            ent["cpu_reference"] = {"kind": "reference", "cores": 1,
+                                    "MPixels/s": w * h / (msr * 1e-3) / 1e6,
+                                    "sample": "PentaxDecompressor::decompress (single threaded by design)"}
+    out["8(f)2 PentaxDecompressor 6016x4000"] = ent
+    del plan, d_in, d_out
     return out
 
 
