@@ -256,6 +256,9 @@ def main():
     ap.add_argument("--sustain-s", type=float, default=1.0,
                     help="seconds of the same step back to back after the timed steps "
                          "(clock sampling + sustained figure)")
+    ap.add_argument("--c5", action="store_true",
+                    help="run BASELINE configs[4]: the 256-frame LJPEG batch sharded over the "
+                         "ranks (256/N frames per GPU, strong scaling) + NCCL gather of the outputs")
     ap.add_argument("--skip-others", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
@@ -450,7 +453,8 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
     out["configs[2] DNG LJPEG 8256x5504 (726 tiles 256x256)"] = c3
     del plan, d_out
     # ---- C5-style batch: NB frames of C3 resident in HBM, one plan, one launch ----
-    NB = args.ljpeg_frames
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    NB = max(1, 256 // world) if args.c5 else args.ljpeg_frames
     fb = (t.blob.size + 255) // 256 * 256
     ob = (H * out_pitch + 255) // 256 * 256
     d_inb = torch.zeros(NB * fb + 64, dtype=torch.uint8, device="cuda")
@@ -468,11 +472,31 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
     msb = time_steps(torch, lambda: planb.run((d_inb.data_ptr(), NB * fb), d_outb), steps, 3, dist)
     in_bb, out_bb, pix_b = planb.bytes()
     perb = msb / steps
-    out["configs[4]-style batch: %d LJPEG frames of configs[2] per GPU, one launch" % NB] = {
+    label = ("configs[4]: 256-frame LJPEG batch, %d frames per GPU x %d GPUs, one launch per GPU"
+             % (NB, world)) if args.c5 else \
+        "configs[4]-style batch: %d LJPEG frames of configs[2] per GPU, one launch" % NB
+    entb = {
         "MPixels/s_per_gpu": pix_b / (perb * 1e-3) / 1e6, "ms_per_step": perb, "bit_exact": exact_b,
         "achieved_GBps": (in_bb + out_bb) / (perb * 1e-3) / 1e9,
         "roofline_frac": (in_bb + out_bb) / (perb * 1e-3) / 1e9 / peak,
         "read_only_roofline_frac": in_bb / (perb * 1e-3) / 1e9 / peak}
+    if args.c5:
+        entb["MPixels/s_all_gpus"] = world * pix_b / (perb * 1e-3) / 1e6
+        entb["frames"] = NB * world
+        entb["note"] = ("the 256 frames are copies of one synthetic frame (same statistics; generating "
+                        "256 distinct frames on the host would take minutes); ms_per_step is the max "
+                        "over ranks")
+        if dist is not None:
+            from rawspeed_b200 import shard
+            local = d_outb.view(NB, ob)
+
+            def step_g():
+                planb.run((d_inb.data_ptr(), NB * fb), d_outb)
+                shard.gather_frames(local, NB * world, dist)
+            msg = time_steps(torch, step_g, 3, 1, dist)
+            entb["decode_plus_gather_ms"] = msg / 3
+            entb["decode_plus_gather_MPixels/s"] = world * pix_b / (msg / 3 * 1e-3) / 1e6
+    out[label] = entb
     del planb, d_inb, d_outb, d_in
     if not args.skip_cpu and int(os.environ.get("RANK", "0")) == 0:
         import oracle
