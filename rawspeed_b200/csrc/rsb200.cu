@@ -7,6 +7,7 @@
 #include "ljpeg.cuh"
 #include "ljpeg_fused.cuh"
 #include "ljpeg_ranges.cuh"
+#include "ljpeg_thread.cuh"
 #include "rawforms.cuh"
 #include "sraw.cuh"
 #include "pentax.cuh"
@@ -14,6 +15,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -119,6 +121,9 @@ struct rsb200_plan {
   // untiled strips): multi-CTA count/verify/diffs + K3
   uint32_t* d_small_ids = nullptr;
   int nsmall = 0;
+  uint32_t* d_thread_ids = nullptr; // segments decoded one per thread (K2T)
+  int nthread = 0;
+  int ntables = 0;
   uint32_t* d_big_ids = nullptr;
   int nbig = 0;
   BigScanInfo* d_big = nullptr;
@@ -744,6 +749,15 @@ static void assign_tables(DevScan& d, const uint8_t* table, int ncomp,
 
 constexpr uint32_t BIG_SEGMENT_BYTES = 256u << 10; // above this a segment gets several CTAs
 
+// Segments the one-thread-per-segment kernel handles: plain LJPEG tiles whose rows
+// are whole 8-sample units written with aligned 128-bit stores.
+constexpr size_t K2T_MIN_SEGMENTS = 8192;
+static bool thread_eligible(const DevScan& d) {
+  return d.kind == 0 && d.pump == 0 && d.mcu_h == 1 &&
+         (d.group == 1 || d.group == 2 || d.group == 4) && (d.row_samples & 7u) == 0 &&
+         ((d.out_offset | d.out_pitch) & 15u) == 0 && (d.out_x & 7u) == 0;
+}
+
 static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
                              const rsb200_huff_table* tables, int ntables, ScanBuild& b,
                              bool /*unused*/) {
@@ -762,7 +776,24 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   p->nscans = (int)b.scans.size();
   p->nunits = p->nscans;
   // classify the segments and lay out the scratch of the multi-CTA path
-  std::vector<uint32_t> small_ids, big_ids;
+  std::vector<uint32_t> small_ids, big_ids, thread_ids;
+  // K2T (one thread per segment) pays off once the launch holds enough independent
+  // segments to fill the machine with serial decoders; RSB200_LJPEG_PATH=thread|fused
+  // forces the choice (tests exercise both kernels on the same inputs).
+  bool use_thread = false;
+  if (ntables <= T_MAXTAB) {
+    size_t n_el = 0;
+    for (const DevScan& d : b.scans)
+      if (d.kind == 0 && d.in_size <= BIG_SEGMENT_BYTES && thread_eligible(d))
+        ++n_el;
+    use_thread = n_el >= K2T_MIN_SEGMENTS;
+    if (const char* e = getenv("RSB200_LJPEG_PATH")) {
+      if (!strcmp(e, "thread"))
+        use_thread = true;
+      else if (!strcmp(e, "fused"))
+        use_thread = false;
+    }
+  }
   std::vector<BigScanInfo> big;
   std::vector<DevRange> ranges;
   b.rows.clear();
@@ -774,7 +805,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     if (is_big)
       (d.kind == 2 ? p->has_pentax : p->has_k3) = true;
     if (!is_big) {
-      small_ids.push_back((uint32_t)i);
+      (use_thread && thread_eligible(d) ? thread_ids : small_ids).push_back((uint32_t)i);
       continue;
     }
     big_ids.push_back((uint32_t)i);
@@ -798,6 +829,8 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
       ranges.push_back(DevRange{(uint32_t)i, r});
   }
   p->nsmall = (int)small_ids.size();
+  p->nthread = (int)thread_ids.size();
+  p->ntables = ntables;
   p->nbig = (int)big_ids.size();
   p->nranges = (int)ranges.size();
   p->nrows = (uint32_t)b.rows.size();
@@ -818,6 +851,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   up((void**)&p->d_strips, b.strips.data(), sizeof(DevStrip) * b.strips.size());
   up((void**)&p->d_rows, b.rows.data(), sizeof(K3RowRef) * b.rows.size());
   up((void**)&p->d_small_ids, small_ids.data(), sizeof(uint32_t) * small_ids.size());
+  up((void**)&p->d_thread_ids, thread_ids.data(), sizeof(uint32_t) * thread_ids.size());
   up((void**)&p->d_big_ids, big_ids.data(), sizeof(uint32_t) * big_ids.size());
   up((void**)&p->d_big, big.data(), sizeof(BigScanInfo) * big.size());
   up((void**)&p->d_ranges, ranges.data(), sizeof(DevRange) * ranges.size());
@@ -839,7 +873,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
                    cudaGetErrorString(e));
   }
-  p->launches_per_run = (p->nsmall ? 1 : 0) +
+  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->nthread ? 1 : 0) +
                         (p->nbig ? 5 + (p->has_k3 ? 2 : 0) + (p->has_pentax ? 2 : 0) : 0);
   return RSB200_OK;
 }
@@ -1166,6 +1200,13 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 1;
     }
+    if (p->nthread) {
+      k2_thread_kernel<<<(p->nthread + T_NT - 1) / T_NT, T_NT, thread_smem_bytes(p->ntables), st>>>(
+          in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->ntables, outp, p->d_results,
+          p->d_thread_ids, (uint32_t)p->nthread);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    }
     if (p->nbig) {
       k2_clear_results_kernel<<<(p->nbig + 127) / 128, 128, 0, st>>>(p->d_big, p->nbig,
                                                                      p->d_results, p->d_oob);
@@ -1410,6 +1451,7 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   cudaFree(p->d_colvals);
   cudaFree(p->d_results);
   cudaFree(p->d_small_ids);
+  cudaFree(p->d_thread_ids);
   cudaFree(p->d_big_ids);
   cudaFree(p->d_big);
   cudaFree(p->d_ranges);
