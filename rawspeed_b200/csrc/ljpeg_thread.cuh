@@ -49,94 +49,74 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
   return r;
 }
 
-struct TTail {
-  uint32_t acc, rp, fake, ended;
-};
-// 4 clean bytes starting at raw position rp, byte by byte from memory (end of the
-// segment: bytes past the limit read as 0 and count as missing data).  A free
-// function with by-value state so that the bit source itself stays in registers.
-__device__ __noinline__ TTail t_refill_tail(const uint8_t* gbase, uint32_t limit, uint32_t rp,
-                                            uint32_t fake, uint32_t ended) {
-  uint32_t acc = 0;
-  for (int got = 0; got < 4; ++got) {
-    if (!ended && rp >= limit)
-      ended = 2;
-    if (ended) {
-      acc <<= 8;
-      fake += 8;
-      continue;
-    }
-    const uint32_t c0 = __ldg(gbase + rp);
-    if (c0 != 0xFFu) {
-      acc = (acc << 8) | c0;
-      rp += 1;
-      continue;
-    }
-    // (an FF that is the very last byte is followed by a virtual 00)
-    const uint32_t c1 = rp + 1 < limit ? (uint32_t)__ldg(gbase + rp + 1) : 0u;
-    if (c1 == 0u) {
-      acc = (acc << 8) | 0xFFu;
-      rp += 2;
-      continue;
-    }
-    ended = 1; // marker: position stays on the FF
-    acc <<= 8;
-    fake += 8;
+// ---- refill of the bit cache, everything that is not "4 plain bytes" ----
+// One aligned raw word `w` (bytes k0..kend-1 of it belong to the segment), `wn` =
+// the word after it (look-ahead for an FF in the last byte; bytes past the limit
+// already zeroed).  flags: bit 0 = the first byte is the stuffing 00 of an FF that
+// ended the previous word.  Returns .x = the clean bytes (right aligned), .y =
+// number of clean bytes | flags' << 8 (bit 0 as above, bit 1 = end marker found) |
+// bytes not delivered << 16 (stuffing, bytes outside the segment, marker and after).
+__device__ __noinline__ uint2 t_refill_word(uint32_t w, uint32_t wn, uint32_t k0, uint32_t kend,
+                                            uint32_t flags) {
+  uint32_t acc = 0, n = 0, out_flags = 0;
+  uint64_t v = ((uint64_t)wn << 32) | w;
+  v >>= 8 * k0;
+  uint32_t k = k0;
+  if ((flags & 1u) && k < kend) { // stuffing byte of the previous word's FF
+    v >>= 8;
+    ++k;
   }
-  TTail o;
-  o.acc = acc;
-  o.rp = rp;
-  o.fake = fake;
-  o.ended = ended;
-  return o;
-}
-
-// 4 clean bytes when an FF is among the next raw bytes: lo4 = raw bytes rp..rp+3,
-// hi4 = rp+4..rp+7 (all inside the segment).  Returns .x = the 4 bytes (big endian,
-// zero padded after a marker), .y = raw bytes used | clean bytes got << 8.
-__device__ __noinline__ uint2 t_refill_ff(uint32_t lo4, uint32_t hi4) {
-  uint64_t v = ((uint64_t)hi4 << 32) | lo4;
-  uint32_t acc = 0, used = 0, got = 0;
-  for (int i = 0; i < 4; ++i) {
+  while (k < kend) {
     const uint32_t c0 = (uint32_t)v & 0xFFu;
-    const uint32_t c1 = ((uint32_t)v >> 8) & 0xFFu;
     if (c0 != 0xFFu) {
       acc = (acc << 8) | c0;
+      ++n;
       v >>= 8;
-      used += 1;
-      ++got;
-    } else if (c1 == 0u) {
-      acc = (acc << 8) | 0xFFu;
+      ++k;
+      continue;
+    }
+    const uint32_t c1 = ((uint32_t)v >> 8) & 0xFFu; // (past the limit: 0 -> "FF 00")
+    if (c1 != 0u) {
+      out_flags |= 2u; // FF xx: end of the data, the FF is not data
+      break;
+    }
+    acc = (acc << 8) | 0xFFu;
+    ++n;
+    if (k + 1 < 4u) {
       v >>= 16;
-      used += 2;
-      ++got;
+      k += 2;
     } else {
-      break; // marker: rp stays on the FF, the rest of the refill is zero bits
+      out_flags |= 1u; // its 00 is the first byte of the next word
+      ++k;
     }
   }
-  if (got < 4)
-    acc = got ? acc << (8 * (4 - got)) : 0u;
-  return make_uint2(acc, used | (got << 8));
+  return make_uint2(acc, n | (out_flags << 8) | ((4u - n) << 16));
 }
 
-// The reference's bit source (BitStreamerJPEG over BitStreamer), one per thread.
+// The JPEG bit source (BitStreamerJPEG.h:106-183), one per thread: 64-bit cache
+// refilled by whole aligned raw words whenever fewer than 32 bits are left.
+// (The reference refills 4 DATA bytes at a time; the schedule differs but the bit
+// sequence is the same, and `consumed` is rebuilt from the bit offset of the
+// last symbol -- see t_stream_position.)
 struct TSrc {
   uint32_t hi, lo;   // unread bits, MSB aligned in hi:lo
   int nbits;         // number of unread bits (real + fake)
   uint32_t fake;     // zero bits supplied after the end of the data
-  uint32_t rp;       // raw byte position (relative to gbase) of the next unread byte
-  uint32_t sh8;      // 8 * (rp & 3)
-  uint32_t w0, w1, w2;      // raw words rp/4, rp/4+1, rp/4+2 (little endian)
+  uint32_t rp;       // raw offset (from gbase, multiple of 4) of the next unread word
+  uint32_t dropped;  // raw bytes before rp that are not data (lead-in, stuffing)
+  uint32_t w0;              // raw word at rp
   uint32_t n0, n1, n2, n3;  // the following words, nleft of them valid
   uint32_t m0, m1, m2, m3;  // the 16-byte block after those
   int nleft;
   uint32_t next_blk;  // index of the block to fetch after m
   uint32_t nblk;      // blocks that may be read (16-byte padded input buffer)
   const uint4* blocks;
-  const uint8_t* gbase;
   uint32_t limit;     // valid raw bytes from gbase
-  uint32_t safe_end;  // rp below this: 12 raw bytes ahead are inside the segment
-  uint32_t ended;     // 1: marker seen (rp pinned on it), 2: ran off the end of the data
+  uint32_t fast_end;  // rp below this: the word at rp lies inside the segment
+  uint32_t flags;     // bit 0: byte at rp is a pending stuffing 00; bit 1: data ended
+  uint32_t k0;        // bytes to skip in the next word (segment start inside a word)
+  // two (rp, dropped, flags) snapshots, >= 64 raw bytes apart, for t_stream_position
+  uint32_t a0_rp, a0_dr, a1_rp, a1_dr;
 
   __device__ __forceinline__ uint4 fetch(uint32_t b) const {
     if (b < nblk)
@@ -144,9 +124,7 @@ struct TSrc {
     return make_uint4(0u, 0u, 0u, 0u);
   }
   __device__ __forceinline__ void pop() {
-    w0 = w1;
-    w1 = w2;
-    w2 = n0;
+    w0 = n0;
     n0 = n1;
     n1 = n2;
     n2 = n3;
@@ -159,67 +137,79 @@ struct TSrc {
   }
   __device__ __forceinline__ void init(const uint8_t* gb, uint32_t skew, uint32_t lim,
                                        uint64_t readable) {
-    gbase = gb;
     blocks = reinterpret_cast<const uint4*>(gb);
     limit = lim;
     nblk = (uint32_t)(readable >> 4);
-    safe_end = lim >= 16u ? lim - 16u : 0u;
     hi = lo = 0;
     nbits = 0;
     fake = 0;
-    ended = 0;
+    flags = 0;
     const uint4 a = fetch(0), b = fetch(1);
     n0 = a.x; n1 = a.y; n2 = a.z; n3 = a.w;
     m0 = b.x; m1 = b.y; m2 = b.z; m3 = b.w;
     nleft = 4;
     next_blk = 2;
-    w0 = w1 = w2 = 0;
+    w0 = 0;
 #pragma unroll 1
-    for (uint32_t k = 0; k < 3u + (skew >> 2); ++k)
+    for (uint32_t k = 0; k < 1u + (skew >> 2); ++k)
       pop();
-    rp = skew;
-    sh8 = 8u * (skew & 3u);
+    rp = skew & ~3u;
+    k0 = skew & 3u;
+    dropped = 0;
+    fast_end = lim & ~3u; // rp < fast_end: the whole word lies inside the segment
+    a0_rp = a1_rp = 0xFFFFFFFFu; // (no snapshot: walk from the segment start)
+    a0_dr = a1_dr = 0;
   }
-  // BitStreamer::fill(32): ONE refill of 4 data bytes when fewer than 32 bits are
-  // left (BitStreamer.h:216-229) -- the reference's cadence, which is what makes
-  // rp equal to its getStreamPosition() at every moment.
-  __device__ __forceinline__ void fill() {
-    if (nbits >= 32)
-      return;
-    uint32_t acc, nrp;
-    if (!ended && rp < safe_end) {
-      const uint32_t raw4 = __funnelshift_r(w0, w1, sh8);
-      acc = __byte_perm(raw4, 0, 0x0123);
-      nrp = rp + 4;
-      // any byte == FF  <=>  any byte of ~raw4 == 0
-      if ((~raw4 - 0x01010101u) & raw4 & 0x80808080u) {
-        const uint2 r = t_refill_ff(raw4, __funnelshift_r(w1, w2, sh8));
-        acc = r.x;
-        nrp = rp + (r.y & 0xFFu);
-        const uint32_t got = r.y >> 8;
-        if (got < 4u) {
-          ended = 1;
-          fake += 8u * (4u - got);
-        }
-      }
-#pragma unroll 1
-      for (uint32_t a = (nrp >> 2) - (rp >> 2); a; --a)
-        pop();
-      sh8 = 8u * (nrp & 3u);
-    } else {
-      // end of the segment (rp only grows and `ended` is final: the word FIFO is
-      // never used again)
-      const TTail o = t_refill_tail(gbase, limit, rp, fake, ended);
-      acc = o.acc;
-      nrp = o.rp;
-      fake = o.fake;
-      ended = o.ended;
+  // one raw word -> cache
+  __device__ __forceinline__ void refill() {
+    const uint32_t w = w0;
+    uint32_t be = __byte_perm(w, 0, 0x0123), nb = 32;
+    if ((rp & 63u) == 0u && (flags | k0) == 0u) { // snapshot: rp is a data byte boundary
+      a1_rp = a0_rp;
+      a1_dr = a0_dr;
+      a0_rp = rp;
+      a0_dr = dropped;
     }
-    rp = nrp;
-    // append 32 bits: acc << (32 - nbits) as a 64-bit quantity (nbits < 32)
-    hi |= acc >> nbits;
-    lo = acc << (32 - nbits); // (lo holds no unread bits while nbits <= 32)
-    nbits += 32;
+    // any byte == FF  <=>  any byte of ~w == 0
+    const uint32_t ff = (~w - 0x01010101u) & w & 0x80808080u;
+    if (rp < fast_end && (ff | flags | k0) == 0u) {
+      pop();
+      rp += 4;
+    } else if (flags & 2u) {
+      be = 0; // data ended: zero bits from here on
+      fake += 32;
+    } else {
+      const uint32_t kend = rp >= limit ? 0u : min(4u, limit - rp);
+      uint32_t wn = n0;
+      if (rp + 4u >= limit)
+        wn = 0;
+      else if (rp + 8u > limit)
+        wn &= 0xFFFFFFFFu >> (8u * (rp + 8u - limit));
+      const uint2 r = t_refill_word(w, wn, k0, kend, flags);
+      const uint32_t n = r.y & 0xFFu;
+      flags = (r.y >> 8) & 3u;
+      if (kend < 4u)
+        flags |= 2u; // ran off the end of the segment
+      dropped += 4u - n; // (rp - dropped keeps counting the data bytes delivered)
+      rp += 4;
+      k0 = 0;
+      be = n ? r.x << (32u - 8u * n) : 0u;
+      if (flags & 2u) {
+        fake += 32u - 8u * n; // zero bits complete this refill; they are missing data
+      } else {
+        nb = 8u * n;
+        pop();
+      }
+    }
+    hi |= __funnelshift_rc(be, 0u, (uint32_t)nbits); // be >> nbits (nbits <= 32)
+    lo = __funnelshift_lc(0u, be, 32u - (uint32_t)nbits); // (lo holds no unread bits while nbits <= 32)
+    nbits += (int)nb;
+  }
+  // at least 32 bits in the cache (one symbol is at most 32 bits long)
+  __device__ __forceinline__ void fill() {
+#pragma unroll 1
+    while (nbits < 32)
+      refill();
   }
   __device__ __forceinline__ void skip(uint32_t n) { // n <= 32
     hi = __funnelshift_lc(lo, hi, n);
@@ -227,6 +217,35 @@ struct TSrc {
     nbits -= (int)n;
   }
 };
+
+// BitStreamerJPEG::getStreamPosition() of the reference after the last symbol, whose
+// first bit is data bit T of the segment: the reference has done R = T/32 + 1 (+1 if
+// T % 32 != 0) refills of 4 data bytes by then (BitStreamer::fill(32) before every
+// symbol, BitStreamer.h:216-229), so its position is the raw offset after 4R data
+// bytes, or the end marker if that comes first.  Walks forward from a snapshot.
+__device__ __noinline__ uint32_t t_stream_position(const uint8_t* gbase, uint32_t limit,
+                                                   uint32_t skew, uint32_t T, uint32_t a_rp,
+                                                   uint32_t a_dr) {
+  const uint32_t R = (T >> 5) + 1u + ((T & 31u) ? 1u : 0u);
+  const uint32_t need = 4u * R;
+  uint32_t rawp = skew, c = 0;
+  if (a_rp != 0xFFFFFFFFu) {
+    rawp = a_rp;
+    c = a_rp - (skew & ~3u) - a_dr;
+  }
+  auto byte_at = [&](uint32_t q) { return q < limit ? (uint32_t)__ldg(gbase + q) : 0u; };
+  while (c < need) {
+    if (byte_at(rawp) == 0xFFu) {
+      if (byte_at(rawp + 1) != 0u)
+        break; // marker: the position stays on it
+      rawp += 2;
+    } else {
+      rawp += 1;
+    }
+    ++c;
+  }
+  return rawp - skew;
+}
 
 // symbols the LUT does not resolve (T.81 F.16 walk); .x = difference, .y = bits
 // consumed | bad-code flag << 31
@@ -257,7 +276,7 @@ __device__ __forceinline__ uint32_t t_decode_diff(const DevTable* t, uint32_t lu
 // two samples (components ca, cb of the MCU) -> one output word
 #define T_PAIR(ca, cb, word)                                                    \
   do {                                                                          \
-    uint32_t tl_;                                                               \
+    uint32_t& tl_ = last_tl;                                                    \
     bs.fill();                                                                  \
     const uint32_t da_ = t_decode_diff(tabp[ca], lutb[ca], bs.hi, tl_, bad);    \
     bs.skip(tl_);                                                               \
@@ -297,7 +316,7 @@ thread_body(const ThreadShared& sh, const DevScan* __restrict__ scp,
   const uint32_t store_w = scp->store_w;
   const uint32_t out_pitch = scp->out_pitch;
   uint8_t* orow = out + scp->out_offset + (uint64_t)scp->out_y * out_pitch + 2ull * scp->out_x;
-  uint32_t bad = 0;
+  uint32_t bad = 0, last_tl = 0;
 
   for (uint32_t r = 0; r < rows; ++r) {
 #pragma unroll
@@ -355,7 +374,13 @@ thread_body(const ThreadShared& sh, const DevScan* __restrict__ scp,
   // consumed: no refill follows the last symbol, so rp is the reference's stream position
   const bool over = (uint32_t)bs.nbits < bs.fake;
   res->status = bad ? 1u : (over ? 2u : 0u);
-  res->consumed = bs.rp - skew;
+  {
+    // data bits consumed in total, minus the last symbol = bit offset of the last symbol
+    const uint32_t clean = bs.rp - (skew & ~3u) - bs.dropped;
+    const uint32_t T = 8u * clean + bs.fake - (uint32_t)bs.nbits - last_tl;
+    // the older snapshot is guaranteed to lie before the 4R-th data byte
+    res->consumed = t_stream_position(in + abase, limit, skew, T, bs.a1_rp, bs.a1_dr);
+  }
 }
 #undef T_PAIR
 
