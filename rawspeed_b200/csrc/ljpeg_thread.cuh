@@ -1,250 +1,58 @@
 // ljpeg_thread.cuh -- K2T: LJPEG tile decode for LARGE batches, one THREAD per
 // entropy-coded segment (DNG tile / restart interval), sm_100a.
 //
-// Same semantics as k2_fused_kernel (see ljpeg.cuh / ljpeg_fused.cuh for the
-// reference citations: BitStreamerJPEG.h:106-183, PrefixCodeLUTDecoder.h:172-216,
+// Same results as k2_fused_kernel (see ljpeg.cuh / ljpeg_fused.cuh for the
+// reference citations: PrefixCodeLUTDecoder.h:172-216,
 // AbstractPrefixCodeDecoder.h:43-76, LJpegDecompressor.cpp:184-339).
 //
 // Why a second kernel: a batch of frames holds 10^4..10^5 independent segments
 // (726 tiles per 45 MP frame).  With that many streams the serial dependency of
-// a Huffman stream is no longer a problem -- each thread simply IS the
-// reference's sequential decoder (64-bit bit cache, fill(32) before every
-// symbol, 4 clean bytes per refill, FF00 unstuffing, first FFxx ends the data)
-// and the machine is kept busy by the number of streams.  No synchronisation
-// rounds, no second decode pass, no shared-memory staging: ~25 instructions
-// per sample instead of ~160 issue slots in the block-per-segment kernel, at
-// the price of a fixed latency (one tile's serial decode, ~2 ms), which is why
-// the plan only takes this path when the launch holds enough segments.
+// a Huffman stream stops being a problem: every thread simply is a sequential
+// decoder and the machine is kept busy by the number of streams -- no
+// synchronisation rounds, no second decode pass (~30 instructions per sample
+// instead of ~160 issue slots per sample in the block-per-segment kernel).  The
+// price is latency (a 256x256 tile is 65536 dependent symbols), which is why the
+// plan only takes this path when a launch holds enough segments.
 //
-//   * input: every thread streams its segment with 128-bit loads, one 16-byte
-//     block ahead (double buffered in registers), raw words kept in a small
-//     register FIFO so the 4-byte refill is one funnel shift + byte swap;
+// A warp runs 32 different streams, so everything data dependent in the loop
+// costs issue slots for all 32 lanes.  The stuffing / marker / end-of-buffer logic
+// of the JPEG bit source is therefore done beforehand by K2C (ljpeg_clean.cuh,
+// cooperative, one CTA per segment); the decoders read clean big-endian words:
+//   * bit window = two registers + position, `peek` is one funnel shift, a word
+//     crossing is four predicated instructions (next word prefetched two ahead);
 //   * Huffman LUTs of the plan (<= 4 tables) in shared memory;
-//   * predictor 1 in registers (mod 2^16), first MCU of a row predicted from
+//   * predictor 1 in registers (mod 2^16), the first MCU of a row predicted from
 //     the first MCU of the previous row; 8 samples are packed and written with
 //     one 128-bit store (rows of a tile are 16-byte aligned);
-//   * `consumed` falls out of the refill cadence (it IS the reference's cadence).
+//   * `consumed` (the reference's BitStreamerJPEG::getStreamPosition()) is rebuilt
+//     from the bit offset of the last symbol through K2C's anchors.
 #pragma once
 
-#include "ljpeg.cuh"
+#include "ljpeg_clean.cuh"
 
 namespace rsb200 {
 
-constexpr int T_NT = 64;       // threads (= segments) per CTA
+constexpr int T_NT = 128;      // threads (= segments) per CTA
 constexpr int T_MAXTAB = 4;    // plan tables staged in shared memory
 
+// Per-thread ring of clean data in shared memory: T_SLOTS blocks of 16 bytes, block
+// b of the stream in slot b % T_SLOTS, slot s of thread t at ring[s][t].  A warp runs
+// 32 unrelated streams, and the scoreboard that guards a load's destination register
+// is per WARP: a per-lane "load the next word when I cross into a new one" makes
+// every lane wait for whatever load another lane issued a moment ago.  So global
+// loads happen only at the start of a unit, the same instruction for all lanes,
+// land in the ring at the end of that unit, and are first needed in the next one;
+// inside a unit lanes only touch their ring.
+constexpr int T_SLOTS = 8;
+constexpr uint32_t T_AHEAD = 96; // bytes kept requested ahead of the read position
+
 struct ThreadShared {
+  uint4 ring[T_SLOTS][T_NT];
   DevTable tab[T_MAXTAB];
 };
 
 __host__ __device__ inline size_t thread_smem_bytes(int ntab) {
-  return sizeof(DevTable) * (size_t)ntab;
-}
-
-__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
-
-// ---- refill of the bit cache, everything that is not "4 plain bytes" ----
-// One aligned raw word `w` (bytes k0..kend-1 of it belong to the segment), `wn` =
-// the word after it (look-ahead for an FF in the last byte; bytes past the limit
-// already zeroed).  flags: bit 0 = the first byte is the stuffing 00 of an FF that
-// ended the previous word.  Returns .x = the clean bytes (right aligned), .y =
-// number of clean bytes | flags' << 8 (bit 0 as above, bit 1 = end marker found) |
-// bytes not delivered << 16 (stuffing, bytes outside the segment, marker and after).
-__device__ __noinline__ uint2 t_refill_word(uint32_t w, uint32_t wn, uint32_t k0, uint32_t kend,
-                                            uint32_t flags) {
-  uint32_t acc = 0, n = 0, out_flags = 0;
-  uint64_t v = ((uint64_t)wn << 32) | w;
-  v >>= 8 * k0;
-  uint32_t k = k0;
-  if ((flags & 1u) && k < kend) { // stuffing byte of the previous word's FF
-    v >>= 8;
-    ++k;
-  }
-  while (k < kend) {
-    const uint32_t c0 = (uint32_t)v & 0xFFu;
-    if (c0 != 0xFFu) {
-      acc = (acc << 8) | c0;
-      ++n;
-      v >>= 8;
-      ++k;
-      continue;
-    }
-    const uint32_t c1 = ((uint32_t)v >> 8) & 0xFFu; // (past the limit: 0 -> "FF 00")
-    if (c1 != 0u) {
-      out_flags |= 2u; // FF xx: end of the data, the FF is not data
-      break;
-    }
-    acc = (acc << 8) | 0xFFu;
-    ++n;
-    if (k + 1 < 4u) {
-      v >>= 16;
-      k += 2;
-    } else {
-      out_flags |= 1u; // its 00 is the first byte of the next word
-      ++k;
-    }
-  }
-  return make_uint2(acc, n | (out_flags << 8) | ((4u - n) << 16));
-}
-
-// The JPEG bit source (BitStreamerJPEG.h:106-183), one per thread: 64-bit cache
-// refilled by whole aligned raw words whenever fewer than 32 bits are left.
-// (The reference refills 4 DATA bytes at a time; the schedule differs but the bit
-// sequence is the same, and `consumed` is rebuilt from the bit offset of the
-// last symbol -- see t_stream_position.)
-struct TSrc {
-  uint32_t hi, lo;   // unread bits, MSB aligned in hi:lo
-  int nbits;         // number of unread bits (real + fake)
-  uint32_t fake;     // zero bits supplied after the end of the data
-  uint32_t rp;       // raw offset (from gbase, multiple of 4) of the next unread word
-  uint32_t dropped;  // raw bytes before rp that are not data (lead-in, stuffing)
-  uint32_t w0;              // raw word at rp
-  uint32_t n0, n1, n2, n3;  // the following words, nleft of them valid
-  uint32_t m0, m1, m2, m3;  // the 16-byte block after those
-  int nleft;
-  uint32_t next_blk;  // index of the block to fetch after m
-  uint32_t nblk;      // blocks that may be read (16-byte padded input buffer)
-  const uint4* blocks;
-  uint32_t limit;     // valid raw bytes from gbase
-  uint32_t fast_end;  // rp below this: the word at rp lies inside the segment
-  uint32_t flags;     // bit 0: byte at rp is a pending stuffing 00; bit 1: data ended
-  uint32_t k0;        // bytes to skip in the next word (segment start inside a word)
-  // two (rp, dropped, flags) snapshots, >= 64 raw bytes apart, for t_stream_position
-  uint32_t a0_rp, a0_dr, a1_rp, a1_dr;
-
-  __device__ __forceinline__ uint4 fetch(uint32_t b) const {
-    if (b < nblk)
-      return ldg_stream_v4(blocks + b);
-    return make_uint4(0u, 0u, 0u, 0u);
-  }
-  __device__ __forceinline__ void pop() {
-    w0 = n0;
-    n0 = n1;
-    n1 = n2;
-    n2 = n3;
-    if (--nleft == 0) {
-      n0 = m0; n1 = m1; n2 = m2; n3 = m3;
-      nleft = 4;
-      const uint4 q = fetch(next_blk++);
-      m0 = q.x; m1 = q.y; m2 = q.z; m3 = q.w;
-    }
-  }
-  __device__ __forceinline__ void init(const uint8_t* gb, uint32_t skew, uint32_t lim,
-                                       uint64_t readable) {
-    blocks = reinterpret_cast<const uint4*>(gb);
-    limit = lim;
-    nblk = (uint32_t)(readable >> 4);
-    hi = lo = 0;
-    nbits = 0;
-    fake = 0;
-    flags = 0;
-    const uint4 a = fetch(0), b = fetch(1);
-    n0 = a.x; n1 = a.y; n2 = a.z; n3 = a.w;
-    m0 = b.x; m1 = b.y; m2 = b.z; m3 = b.w;
-    nleft = 4;
-    next_blk = 2;
-    w0 = 0;
-#pragma unroll 1
-    for (uint32_t k = 0; k < 1u + (skew >> 2); ++k)
-      pop();
-    rp = skew & ~3u;
-    k0 = skew & 3u;
-    dropped = 0;
-    fast_end = lim & ~3u; // rp < fast_end: the whole word lies inside the segment
-    a0_rp = a1_rp = 0xFFFFFFFFu; // (no snapshot: walk from the segment start)
-    a0_dr = a1_dr = 0;
-  }
-  // one raw word -> cache
-  __device__ __forceinline__ void refill() {
-    const uint32_t w = w0;
-    uint32_t be = __byte_perm(w, 0, 0x0123), nb = 32;
-    if ((rp & 63u) == 0u && (flags | k0) == 0u) { // snapshot: rp is a data byte boundary
-      a1_rp = a0_rp;
-      a1_dr = a0_dr;
-      a0_rp = rp;
-      a0_dr = dropped;
-    }
-    // any byte == FF  <=>  any byte of ~w == 0
-    const uint32_t ff = (~w - 0x01010101u) & w & 0x80808080u;
-    if (rp < fast_end && (ff | flags | k0) == 0u) {
-      pop();
-      rp += 4;
-    } else if (flags & 2u) {
-      be = 0; // data ended: zero bits from here on
-      fake += 32;
-    } else {
-      const uint32_t kend = rp >= limit ? 0u : min(4u, limit - rp);
-      uint32_t wn = n0;
-      if (rp + 4u >= limit)
-        wn = 0;
-      else if (rp + 8u > limit)
-        wn &= 0xFFFFFFFFu >> (8u * (rp + 8u - limit));
-      const uint2 r = t_refill_word(w, wn, k0, kend, flags);
-      const uint32_t n = r.y & 0xFFu;
-      flags = (r.y >> 8) & 3u;
-      if (kend < 4u)
-        flags |= 2u; // ran off the end of the segment
-      dropped += 4u - n; // (rp - dropped keeps counting the data bytes delivered)
-      rp += 4;
-      k0 = 0;
-      be = n ? r.x << (32u - 8u * n) : 0u;
-      if (flags & 2u) {
-        fake += 32u - 8u * n; // zero bits complete this refill; they are missing data
-      } else {
-        nb = 8u * n;
-        pop();
-      }
-    }
-    hi |= __funnelshift_rc(be, 0u, (uint32_t)nbits); // be >> nbits (nbits <= 32)
-    lo = __funnelshift_lc(0u, be, 32u - (uint32_t)nbits); // (lo holds no unread bits while nbits <= 32)
-    nbits += (int)nb;
-  }
-  // at least 32 bits in the cache (one symbol is at most 32 bits long)
-  __device__ __forceinline__ void fill() {
-#pragma unroll 1
-    while (nbits < 32)
-      refill();
-  }
-  __device__ __forceinline__ void skip(uint32_t n) { // n <= 32
-    hi = __funnelshift_lc(lo, hi, n);
-    asm("shl.b32 %0, %0, %1;" : "+r"(lo) : "r"(n)); // (PTX shifts clamp: n = 32 -> 0)
-    nbits -= (int)n;
-  }
-};
-
-// BitStreamerJPEG::getStreamPosition() of the reference after the last symbol, whose
-// first bit is data bit T of the segment: the reference has done R = T/32 + 1 (+1 if
-// T % 32 != 0) refills of 4 data bytes by then (BitStreamer::fill(32) before every
-// symbol, BitStreamer.h:216-229), so its position is the raw offset after 4R data
-// bytes, or the end marker if that comes first.  Walks forward from a snapshot.
-__device__ __noinline__ uint32_t t_stream_position(const uint8_t* gbase, uint32_t limit,
-                                                   uint32_t skew, uint32_t T, uint32_t a_rp,
-                                                   uint32_t a_dr) {
-  const uint32_t R = (T >> 5) + 1u + ((T & 31u) ? 1u : 0u);
-  const uint32_t need = 4u * R;
-  uint32_t rawp = skew, c = 0;
-  if (a_rp != 0xFFFFFFFFu) {
-    rawp = a_rp;
-    c = a_rp - (skew & ~3u) - a_dr;
-  }
-  auto byte_at = [&](uint32_t q) { return q < limit ? (uint32_t)__ldg(gbase + q) : 0u; };
-  while (c < need) {
-    if (byte_at(rawp) == 0xFFu) {
-      if (byte_at(rawp + 1) != 0u)
-        break; // marker: the position stays on it
-      rawp += 2;
-    } else {
-      rawp += 1;
-    }
-    ++c;
-  }
-  return rawp - skew;
+  return sizeof(uint4) * T_SLOTS * T_NT + sizeof(DevTable) * (size_t)ntab;
 }
 
 // symbols the LUT does not resolve (T.81 F.16 walk); .x = difference, .y = bits
@@ -273,34 +81,90 @@ __device__ __forceinline__ uint32_t t_decode_diff(const DevTable* t, uint32_t lu
   return __funnelshift_l(tt, f, e >> 5) - f;
 }
 
+// BitStreamerJPEG::getStreamPosition() of the reference after the last symbol, whose
+// first bit is data bit T of the segment: the reference has done R = T/32 + 1 (+1 if
+// T % 32 != 0) refills of 4 data bytes by then (BitStreamer::fill(32) before every
+// symbol, BitStreamer.h:216-229; 4 data bytes per refill, BitStreamerJPEG.h:106-183),
+// so its position is the raw offset behind 4R data bytes, or the end marker if that
+// comes first; past the end of the buffer the bytes read as zero data.
+__device__ __noinline__ uint32_t t_stream_position(const uint8_t* gbase, uint32_t limit,
+                                                   uint32_t skew, uint32_t T,
+                                                   const uint32_t* anc, uint32_t n_anchor,
+                                                   uint32_t clean_len) {
+  const uint32_t R = (T >> 5) + 1u + ((T & 31u) ? 1u : 0u);
+  const uint32_t need = 4u * R;
+  // last anchor whose clean count is <= need (the raw position of data byte `need`
+  // is at least skew + need); anchors that count the whole data may lie behind the
+  // end marker and are not used
+  uint32_t a = min((skew + need) >> T_ANCHOR_SHIFT, n_anchor - 1u);
+  while (a > 0 && (__ldg(anc + a) > need || __ldg(anc + a) >= clean_len))
+    --a;
+  while (a + 1 < n_anchor && __ldg(anc + a + 1) <= need && __ldg(anc + a + 1) < clean_len)
+    ++a;
+  uint32_t rawp = a << T_ANCHOR_SHIFT, c = __ldg(anc + a);
+  if (rawp < skew)
+    rawp = skew;
+  auto byte_at = [&](uint32_t q) { return q < limit ? (uint32_t)__ldg(gbase + q) : 0u; };
+  // a stuffing byte may sit exactly at rawp (its FF ended the previous block)
+  if (rawp > skew && byte_at(rawp - 1) == 0xFFu && byte_at(rawp) == 0u)
+    rawp += 1;
+  while (c < need) {
+    if (byte_at(rawp) == 0xFFu) {
+      if (byte_at(rawp + 1) != 0u)
+        break; // marker: the position stays on it
+      rawp += 2;
+    } else {
+      rawp += 1;
+    }
+    ++c;
+  }
+  return rawp - skew;
+}
+
 // two samples (components ca, cb of the MCU) -> one output word
+#define T_SYM(c, val)                                                           \
+  do {                                                                          \
+    const uint32_t x_ = __funnelshift_l(nxt, cur, p);                           \
+    const uint32_t d_ = t_decode_diff(tabp[c], lutb[c], x_, last_tl, bad);      \
+    const uint32_t pn_ = p + last_tl;                                           \
+    if ((pn_ ^ p) & 32u) { /* into the next word (a symbol is <= 32 bits) */    \
+      cur = nxt;                                                                \
+      nxt = nn;                                                                 \
+      /* word wi of the stream: slot (wi / 4) % T_SLOTS, word wi % 4 */         \
+      nn = lds_u32<0>(ringb + ((wi & (4u * T_SLOTS - 4u)) * (4u * T_NT)) +      \
+                      ((wi & 3u) << 2));                                        \
+      ++wi;                                                                     \
+    }                                                                           \
+    p = pn_;                                                                    \
+    pred[c] += d_;                                                              \
+    val = pred[c];                                                              \
+  } while (0)
+
 #define T_PAIR(ca, cb, word)                                                    \
   do {                                                                          \
-    uint32_t& tl_ = last_tl;                                                    \
-    bs.fill();                                                                  \
-    const uint32_t da_ = t_decode_diff(tabp[ca], lutb[ca], bs.hi, tl_, bad);    \
-    bs.skip(tl_);                                                               \
-    pred[ca] += da_;                                                            \
-    const uint32_t va_ = pred[ca];                                              \
-    bs.fill();                                                                  \
-    const uint32_t db_ = t_decode_diff(tabp[cb], lutb[cb], bs.hi, tl_, bad);    \
-    bs.skip(tl_);                                                               \
-    pred[cb] += db_;                                                            \
-    word = __byte_perm(va_, pred[cb], 0x5410);                                  \
+    uint32_t va_, vb_;                                                          \
+    T_SYM(ca, va_);                                                             \
+    T_SYM(cb, vb_);                                                             \
+    word = __byte_perm(va_, vb_, 0x5410);                                       \
   } while (0)
 
 template <int G>
 __device__ __forceinline__ void
-thread_body(const ThreadShared& sh, const DevScan* __restrict__ scp,
-            const uint8_t* __restrict__ in, uint64_t in_total, uint8_t* __restrict__ out,
-            DevResult* __restrict__ res) {
-  const uint64_t in_offset = scp->in_offset;
-  const uint64_t abase = in_offset & ~15ull;
-  const uint32_t skew = (uint32_t)(in_offset - abase);
-  const uint32_t limit = skew + scp->in_size;
-  const uint64_t readable = ((in_total + 15) & ~15ull) - abase;
-  TSrc bs;
-  bs.init(in + abase, skew, limit, readable);
+thread_body(ThreadShared& sh, const DevScan* __restrict__ scp, const DevTScan& ts,
+            const DevTInfo info, const uint8_t* __restrict__ in,
+            const uint32_t* __restrict__ clean, const uint32_t* __restrict__ anchors,
+            uint8_t* __restrict__ out, DevResult* __restrict__ res) {
+  const uint4* cb = reinterpret_cast<const uint4*>(clean + ts.clean_off); // 16-byte blocks
+  const uint32_t bmax = (ts.cap_words >> 2) - 1u;
+  const uint32_t ringb = smem_u32(&sh.ring[0][threadIdx.x]);
+  // prefill: blocks 0 .. T_AHEAD/16 - 1
+  uint32_t nblk = T_AHEAD / 16; // blocks requested so far
+#pragma unroll
+  for (uint32_t b = 0; b < T_AHEAD / 16; ++b)
+    sh.ring[b][threadIdx.x] = __ldg(cb + min(b, bmax));
+  uint32_t cur = sh.ring[0][threadIdx.x].x, nxt = sh.ring[0][threadIdx.x].y,
+           nn = sh.ring[0][threadIdx.x].z;
+  uint32_t wi = 3, p = 0;
 
   uint32_t lutb[G];
   const DevTable* tabp[G];
@@ -323,6 +187,27 @@ thread_body(const ThreadShared& sh, const DevScan* __restrict__ scp,
     for (int c = 0; c < G; ++c)
       pred[c] = rowstart[c];
     for (uint32_t u = 0; u < units; ++u) {
+      // ---- start of the unit: request up to two more blocks (a unit consumes at
+      //      most 32 bytes); they are stored to the ring at the END of this unit, so no
+      //      load is in flight across the loop edge (ptxas waits for those at the loop
+      //      head) and the decode of the unit hides their latency ----
+      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+      uint32_t pend = 0, qb0 = 0, qb1 = 0;
+      {
+        const uint32_t pos = p >> 3; // bytes consumed
+        if (nblk * 16u - pos < T_AHEAD) {
+          qb0 = nblk;
+          q0 = __ldg(cb + min(nblk, bmax));
+          ++nblk;
+          pend = 1u;
+          if (nblk * 16u - pos < T_AHEAD) {
+            qb1 = nblk;
+            q1 = __ldg(cb + min(nblk, bmax));
+            ++nblk;
+            pend = 3u;
+          }
+        }
+      }
       // 8 samples = 4 words, collected in a rotating 128-bit register
       uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
       if (G == 4) {
@@ -356,6 +241,11 @@ thread_body(const ThreadShared& sh, const DevScan* __restrict__ scp,
           rowstart[3] = o1 >> 16;
         }
       }
+      // ---- end of the unit: the blocks requested at its start go into the ring ----
+      if (pend & 1u)
+        sh.ring[qb0 & (T_SLOTS - 1)][threadIdx.x] = q0;
+      if (pend & 2u)
+        sh.ring[qb1 & (T_SLOTS - 1)][threadIdx.x] = q1;
       const uint32_t s = u << 3;
       if (s + 8 <= store_w) {
         stg_cs_v4(orow + 16ull * u, make_uint4(o0, o1, o2, o3));
@@ -370,25 +260,30 @@ thread_body(const ThreadShared& sh, const DevScan* __restrict__ scp,
     }
     orow += out_pitch;
   }
-  // status: a needed symbol used bits that are not there (DESIGN.md "known deviations");
-  // consumed: no refill follows the last symbol, so rp is the reference's stream position
-  const bool over = (uint32_t)bs.nbits < bs.fake;
+  // status: a needed symbol used bits that are not there (DESIGN.md "known deviations")
+  const bool over = p > 8u * info.clean_len;
   res->status = bad ? 1u : (over ? 2u : 0u);
   {
-    // data bits consumed in total, minus the last symbol = bit offset of the last symbol
-    const uint32_t clean = bs.rp - (skew & ~3u) - bs.dropped;
-    const uint32_t T = 8u * clean + bs.fake - (uint32_t)bs.nbits - last_tl;
-    // the older snapshot is guaranteed to lie before the 4R-th data byte
-    res->consumed = t_stream_position(in + abase, limit, skew, T, bs.a1_rp, bs.a1_dr);
+    const uint64_t in_offset = scp->in_offset;
+    const uint64_t abase = in_offset & ~15ull;
+    const uint32_t skew = (uint32_t)(in_offset - abase);
+    res->consumed = t_stream_position(in + abase, skew + scp->in_size, skew, p - last_tl,
+                                      anchors + ts.anchor_off, ts.n_anchor, info.clean_len);
   }
 }
 #undef T_PAIR
+#undef T_SYM
 
-__global__ void __launch_bounds__(T_NT)
-    k2_thread_kernel(const uint8_t* __restrict__ in, uint64_t in_total,
-                     const DevScan* __restrict__ scans, const DevTable* __restrict__ tables,
-                     int ntab, uint8_t* __restrict__ out, DevResult* __restrict__ results,
-                     const uint32_t* __restrict__ scan_ids, uint32_t nids) {
+#ifndef RSB200_T_LB
+#define RSB200_T_LB 6
+#endif
+__global__ void __launch_bounds__(T_NT, RSB200_T_LB)
+    k2_thread_kernel(const uint8_t* __restrict__ in, const DevScan* __restrict__ scans,
+                     const DevTable* __restrict__ tables, int ntab, uint8_t* __restrict__ out,
+                     DevResult* __restrict__ results, const uint32_t* __restrict__ scan_ids,
+                     uint32_t nids, const DevTScan* __restrict__ tscans,
+                     const DevTInfo* __restrict__ infos, const uint32_t* __restrict__ clean,
+                     const uint32_t* __restrict__ anchors) {
   extern __shared__ __align__(16) uint8_t t_smem_raw[];
   ThreadShared& sh = *reinterpret_cast<ThreadShared*>(t_smem_raw);
   const int tid = threadIdx.x;
@@ -406,13 +301,15 @@ __global__ void __launch_bounds__(T_NT)
   const uint32_t scan_idx = scan_ids[id];
   const DevScan* scp = scans + scan_idx;
   DevResult* res = results + scan_idx;
+  const DevTScan ts = tscans[id];
+  const DevTInfo info = infos[id];
   const uint32_t G = scp->group;
   if (G == 1)
-    thread_body<1>(sh, scp, in, in_total, out, res);
+    thread_body<1>(sh, scp, ts, info, in, clean, anchors, out, res);
   else if (G == 2)
-    thread_body<2>(sh, scp, in, in_total, out, res);
+    thread_body<2>(sh, scp, ts, info, in, clean, anchors, out, res);
   else
-    thread_body<4>(sh, scp, in, in_total, out, res);
+    thread_body<4>(sh, scp, ts, info, in, clean, anchors, out, res);
 }
 
 } // namespace rsb200

@@ -121,7 +121,11 @@ struct rsb200_plan {
   // untiled strips): multi-CTA count/verify/diffs + K3
   uint32_t* d_small_ids = nullptr;
   int nsmall = 0;
-  uint32_t* d_thread_ids = nullptr; // segments decoded one per thread (K2T)
+  uint32_t* d_thread_ids = nullptr; // segments decoded one per thread (K2C + K2T)
+  DevTScan* d_tscans = nullptr;
+  DevTInfo* d_tinfos = nullptr;
+  uint32_t* d_clean = nullptr;      // unstuffed data of those segments
+  uint32_t* d_anchors = nullptr;
   int nthread = 0;
   int ntables = 0;
   uint32_t* d_big_ids = nullptr;
@@ -175,6 +179,8 @@ extern "C" int rsb200_create(int device, rsb200_ctx** out) {
   cudaFuncSetAttribute(k2_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(K2Shared));
   cudaFuncSetAttribute(k2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)fused_smem_bytes(4));
+  cudaFuncSetAttribute(k2_clean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)fused_smem_bytes(4));
   cudaFuncSetAttribute(k2_range_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)fused_smem_bytes(4));
@@ -751,7 +757,7 @@ constexpr uint32_t BIG_SEGMENT_BYTES = 256u << 10; // above this a segment gets 
 
 // Segments the one-thread-per-segment kernel handles: plain LJPEG tiles whose rows
 // are whole 8-sample units written with aligned 128-bit stores.
-constexpr size_t K2T_MIN_SEGMENTS = 8192;
+constexpr size_t K2T_MIN_SEGMENTS = 16384; // measured crossover on B200: ~22 frames of 726 tiles
 static bool thread_eligible(const DevScan& d) {
   return d.kind == 0 && d.pump == 0 && d.mcu_h == 1 &&
          (d.group == 1 || d.group == 2 || d.group == 4) && (d.row_samples & 7u) == 0 &&
@@ -852,6 +858,29 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   up((void**)&p->d_rows, b.rows.data(), sizeof(K3RowRef) * b.rows.size());
   up((void**)&p->d_small_ids, small_ids.data(), sizeof(uint32_t) * small_ids.size());
   up((void**)&p->d_thread_ids, thread_ids.data(), sizeof(uint32_t) * thread_ids.size());
+  if (!thread_ids.empty()) {
+    std::vector<DevTScan> tsc(thread_ids.size());
+    uint64_t clean_words = 0, n_anchor = 0;
+    for (size_t k = 0; k < thread_ids.size(); ++k) {
+      const DevScan& d = b.scans[thread_ids[k]];
+      const uint32_t skew = (uint32_t)(d.in_offset & 15ull);
+      DevTScan t;
+      t.clean_off = clean_words;
+      t.cap_words = (((d.in_size + 15u) & ~15u) + 64u) / 4u;
+      t.anchor_off = (uint32_t)n_anchor;
+      t.n_anchor = ((skew + d.in_size) >> T_ANCHOR_SHIFT) + 1u;
+      t.pad = 0;
+      clean_words += t.cap_words;
+      n_anchor += t.n_anchor;
+      tsc[k] = t;
+    }
+    if (n_anchor >= (1ull << 32))
+      e = cudaErrorInvalidValue;
+    up((void**)&p->d_tscans, tsc.data(), sizeof(DevTScan) * tsc.size());
+    alloc((void**)&p->d_tinfos, sizeof(DevTInfo) * tsc.size());
+    alloc((void**)&p->d_clean, clean_words * 4 + 256);
+    alloc((void**)&p->d_anchors, n_anchor * 4 + 256);
+  }
   up((void**)&p->d_big_ids, big_ids.data(), sizeof(uint32_t) * big_ids.size());
   up((void**)&p->d_big, big.data(), sizeof(BigScanInfo) * big.size());
   up((void**)&p->d_ranges, ranges.data(), sizeof(DevRange) * ranges.size());
@@ -873,7 +902,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
                    cudaGetErrorString(e));
   }
-  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->nthread ? 1 : 0) +
+  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->nthread ? 2 : 0) +
                         (p->nbig ? 5 + (p->has_k3 ? 2 : 0) + (p->has_pentax ? 2 : 0) : 0);
   return RSB200_OK;
 }
@@ -1201,11 +1230,14 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       ctx->launches += 1;
     }
     if (p->nthread) {
+      k2_clean_kernel<<<p->nthread, F_NT, fused_smem_bytes(0), st>>>(
+          in, (uint64_t)in_bytes, p->d_scans, p->d_thread_ids, p->d_tscans, p->d_clean,
+          p->d_anchors, p->d_tinfos);
       k2_thread_kernel<<<(p->nthread + T_NT - 1) / T_NT, T_NT, thread_smem_bytes(p->ntables), st>>>(
-          in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->ntables, outp, p->d_results,
-          p->d_thread_ids, (uint32_t)p->nthread);
+          in, p->d_scans, p->d_tables, p->ntables, outp, p->d_results, p->d_thread_ids,
+          (uint32_t)p->nthread, p->d_tscans, p->d_tinfos, p->d_clean, p->d_anchors);
       CUDA_TRY(ctx, cudaGetLastError());
-      ctx->launches += 1;
+      ctx->launches += 2;
     }
     if (p->nbig) {
       k2_clear_results_kernel<<<(p->nbig + 127) / 128, 128, 0, st>>>(p->d_big, p->nbig,
@@ -1452,6 +1484,10 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   cudaFree(p->d_results);
   cudaFree(p->d_small_ids);
   cudaFree(p->d_thread_ids);
+  cudaFree(p->d_tscans);
+  cudaFree(p->d_tinfos);
+  cudaFree(p->d_clean);
+  cudaFree(p->d_anchors);
   cudaFree(p->d_big_ids);
   cudaFree(p->d_big);
   cudaFree(p->d_ranges);

@@ -41,7 +41,10 @@ def _dng(img, tw, th, cpp=1, **kw):
     return t
 
 
-def test_abstract_dng_decompressor_ljpeg():
+@pytest.mark.parametrize("ljpeg_path", ["auto", "thread"])
+def test_abstract_dng_decompressor_ljpeg(ljpeg_path, monkeypatch):
+    if ljpeg_path != "auto":
+        monkeypatch.setenv("RSB200_LJPEG_PATH", ljpeg_path)
     _dng(synth.image_model(300, 200, 7), 128, 64)
     _dng(synth.image_model(256, 96, 9, wild=True), 128, 32)
     img16 = synth.image_model(128, 64, 11, wild=True, bits=16)
@@ -70,7 +73,10 @@ def test_abstract_dng_decompressor_uncompressed():
         assert np.array_equal(a, b), (bps, be)
 
 
-def test_ljpeg_decoder_single_tile_and_consumed():
+@pytest.mark.parametrize("ljpeg_path", ["auto", "thread"])
+def test_ljpeg_decoder_single_tile_and_consumed(ljpeg_path, monkeypatch):
+    if ljpeg_path != "auto":
+        monkeypatch.setenv("RSB200_LJPEG_PATH", ljpeg_path)
     img = synth.image_model(64, 40, 3)
     hts = synth.default_tables(1)
     for rr in (0, 1, 7):
@@ -100,7 +106,10 @@ def test_ljpeg_decoder_single_tile_and_consumed():
                 assert ca == cb, pad
 
 
-def test_stream_errors_same_class():
+@pytest.mark.parametrize("ljpeg_path", ["auto", "thread"])
+def test_stream_errors_same_class(ljpeg_path, monkeypatch):
+    if ljpeg_path != "auto":
+        monkeypatch.setenv("RSB200_LJPEG_PATH", ljpeg_path)
     img = synth.image_model(64, 32, 23, wild=True)
     t = synth.make_dng_ljpeg(img, 64, 32)
     info = parse_ljpeg(t.blob)

@@ -9,6 +9,17 @@ from helpers import dng_ljpeg_scans, gpu_run
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["auto", "thread"])
+def ljpeg_path(request, monkeypatch):
+    """Every case runs twice: with the plan's own choice of kernel (block per segment for
+    these sizes) and with the one-thread-per-segment path (K2C + K2T) forced."""
+    if request.param != "auto":
+        monkeypatch.setenv("RSB200_LJPEG_PATH", request.param)
+    else:
+        monkeypatch.delenv("RSB200_LJPEG_PATH", raising=False)
+    return request.param
+
+
 def _check_tiles(ctx, img, tile_w, tile_h, **kw):
     h, w = img.shape
     cpp = kw.pop("cpp", 1)
@@ -146,3 +157,47 @@ def test_big_untiled_strip_multi_cta(ctx):
 def test_mixed_small_and_big_segments(ctx):
     img = synth.image_model(2100, 520, 47)
     _check_tiles(ctx, img, 2048, 512)   # tiles: one big (2048x512), small edge tiles
+
+
+def test_many_segments_take_the_thread_path(ctx, ljpeg_path):
+    """>= 16384 segments in one plan: the plan itself picks K2C + K2T (two launches)."""
+    if ljpeg_path != "auto":
+        pytest.skip("covered by the auto case")
+    img = synth.image_model(4096, 4096, 51)
+    t = synth.make_dng_ljpeg(img, 32, 32)
+    tabs, scans = dng_ljpeg_scans(t, port.image_pitch(4096))
+    assert len(scans) == 16384
+    plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
+    assert plan.launches == 2
+    got, res = gpu_run(plan, t.blob, port.new_image(4096, 4096))
+    assert all(s == 0 for s, _ in res)
+    want = port.new_image(4096, 4096)
+    port.dng_decompress(t.blob, t.offsets, t.lengths, want, 4096, 1, 32, 32, 7, nthreads=8)
+    assert np.array_equal(got, want)
+    # consumed of a few segments against the reference restatement
+    hts = synth.default_tables(1)
+    for k in (0, 1, 8191, 16383):
+        s, off, ln = scans[k], t.offsets[k], t.lengths[k]
+        o = port.new_image(4096, 4096)
+        c = port.ljpeg_decompress(o, 4096, 1, (s.out_x, s.out_y, s.store_w, s.rows), (2, 1),
+                                  (s.frame_w, s.rows), [hts[0], hts[0]], [1 << 13] * 2, s.rows,
+                                  t.blob[s.in_offset:off + ln])
+        assert res[k][1] == c
+
+
+def test_truncated_and_garbage_tail_segments(ctx):
+    """Streams that end early (status 2 -> IOException) and streams followed by garbage
+    before EOI (consumed still the reference's) -- same outcome on both kernels."""
+    img = synth.image_model(128, 64, 53)
+    t = synth.make_dng_ljpeg(img, 64, 32)
+    tabs, scans = dng_ljpeg_scans(t, port.image_pitch(128))
+    # cut the first segment short by 40 bytes: its data ends at the buffer end of the segment
+    short = [rs.LJpegScan.from_buffer_copy(s) for s in scans]
+    short[0].in_size = scans[0].in_size - 40
+    plan = rs.ljpeg_plan(ctx, tabs.tabs, short[:1])
+    import torch
+    d_in = torch.from_numpy(np.concatenate([t.blob, np.zeros(64, np.uint8)])).cuda()
+    d_out = torch.zeros(64 * port.image_pitch(128) // 2, dtype=torch.int16, device="cuda")
+    plan.run((d_in.data_ptr(), t.blob.size), d_out)
+    with pytest.raises(rs.IOException):
+        plan.results()
