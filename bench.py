@@ -252,7 +252,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
-    ap.add_argument("--ljpeg-frames", type=int, default=8, help="frames in the LJPEG batch leg")
+    ap.add_argument("--ljpeg-frames", type=int, default=8, help="frames in the small LJPEG batch leg")
+    ap.add_argument("--ljpeg-big-frames", type=int, default=64,
+                    help="frames in the large LJPEG batch leg (one-thread-per-segment path)")
     ap.add_argument("--sustain-s", type=float, default=1.0,
                     help="seconds of the same step back to back after the timed steps "
                          "(clock sampling + sustained figure)")
@@ -452,52 +454,64 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
         "kernel": "k2_fused_kernel", "launches_per_frame": plan.launches}
     out["configs[2] DNG LJPEG 8256x5504 (726 tiles 256x256)"] = c3
     del plan, d_out
-    # ---- C5-style batch: NB frames of C3 resident in HBM, one plan, one launch ----
+    # ---- C5-style batches: NB frames of C3 resident in HBM, one plan per batch ----
+    # 8 frames stay on the block-per-segment kernel (K2F); from ~22 frames (16384 segments)
+    # the plan switches to the one-thread-per-segment path (K2C unstuff pre-pass + K2T).
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    NB = max(1, 256 // world) if args.c5 else args.ljpeg_frames
     fb = (t.blob.size + 255) // 256 * 256
     ob = (H * out_pitch + 255) // 256 * 256
-    d_inb = torch.zeros(NB * fb + 64, dtype=torch.uint8, device="cuda")
-    scans_b, tabs_b = [], None
-    for f in range(NB):
-        d_inb[f * fb:f * fb + t.blob.size] = d_in[:t.blob.size]
-        tabs_b, sc = dng_ljpeg_scans(t, out_pitch, out_offset=f * ob, in_base=f * fb, tabs=tabs_b)
-        scans_b += sc
-    planb = rs.ljpeg_plan(ctx, tabs_b.tabs, scans_b)
-    d_outb = torch.zeros(NB * ob, dtype=torch.uint8, device="cuda")
-    planb.run((d_inb.data_ptr(), NB * fb), d_outb)
-    resb = planb.results()
-    gb = d_outb[(NB - 1) * ob:(NB - 1) * ob + H * out_pitch].cpu().numpy().view(np.uint16).reshape(H, out_pitch // 2)
-    exact_b = bool(np.array_equal(gb[:, :W], img)) and all(s_ == 0 for s_, _ in resb)
-    msb = time_steps(torch, lambda: planb.run((d_inb.data_ptr(), NB * fb), d_outb), steps, 3, dist)
-    in_bb, out_bb, pix_b = planb.bytes()
-    perb = msb / steps
-    label = ("configs[4]: 256-frame LJPEG batch, %d frames per GPU x %d GPUs, one launch per GPU"
-             % (NB, world)) if args.c5 else \
-        "configs[4]-style batch: %d LJPEG frames of configs[2] per GPU, one launch" % NB
-    entb = {
-        "MPixels/s_per_gpu": pix_b / (perb * 1e-3) / 1e6, "ms_per_step": perb, "bit_exact": exact_b,
-        "achieved_GBps": (in_bb + out_bb) / (perb * 1e-3) / 1e9,
-        "roofline_frac": (in_bb + out_bb) / (perb * 1e-3) / 1e9 / peak,
-        "read_only_roofline_frac": in_bb / (perb * 1e-3) / 1e9 / peak}
-    if args.c5:
-        entb["MPixels/s_all_gpus"] = world * pix_b / (perb * 1e-3) / 1e6
-        entb["frames"] = NB * world
-        entb["note"] = ("the 256 frames are copies of one synthetic frame (same statistics; generating "
-                        "256 distinct frames on the host would take minutes); ms_per_step is the max "
-                        "over ranks")
-        if dist is not None:
-            from rawspeed_b200 import shard
-            local = d_outb.view(NB, ob)
+    batches = [max(1, 256 // world)] if args.c5 else sorted({args.ljpeg_frames, args.ljpeg_big_frames})
+    for NB in batches:
+        d_inb = torch.zeros(NB * fb + 64, dtype=torch.uint8, device="cuda")
+        scans_b = []
+        for f in range(NB):
+            d_inb[f * fb:f * fb + t.blob.size] = d_in[:t.blob.size]
+            for s0 in scans:
+                s1 = rs.LJpegScan.from_buffer_copy(s0)
+                s1.in_offset = s0.in_offset + f * fb
+                s1.out_offset = s0.out_offset + f * ob
+                scans_b.append(s1)
+        planb = rs.ljpeg_plan(ctx, tabs.tabs, scans_b)
+        d_outb = torch.zeros(NB * ob, dtype=torch.uint8, device="cuda")
+        planb.run((d_inb.data_ptr(), NB * fb), d_outb)
+        resb = planb.results()
+        exact_b = all(s_ == 0 for s_, _ in resb)
+        for f in sorted({0, NB // 2, NB - 1}):
+            gb = d_outb[f * ob:f * ob + H * out_pitch].cpu().numpy().view(np.uint16).reshape(H, out_pitch // 2)
+            exact_b = exact_b and bool(np.array_equal(gb[:, :W], img))
+        nst = max(3, min(steps, 5))
+        msb = time_steps(torch, lambda: planb.run((d_inb.data_ptr(), NB * fb), d_outb), nst, 3, dist)
+        in_bb, out_bb, pix_b = planb.bytes()
+        perb = msb / nst
+        kern = "k2_fused_kernel" if planb.launches == 1 else "k2_clean_kernel + k2_thread_kernel"
+        label = ("configs[4]: 256-frame LJPEG batch, %d frames per GPU x %d GPUs, one plan per GPU"
+                 % (NB, world)) if args.c5 else \
+            "configs[4]-style batch: %d LJPEG frames of configs[2] per GPU, one plan" % NB
+        entb = {
+            "MPixels/s_per_gpu": pix_b / (perb * 1e-3) / 1e6, "ms_per_step": perb, "bit_exact": exact_b,
+            "kernels": kern, "launches_per_step": planb.launches,
+            "achieved_GBps": (in_bb + out_bb) / (perb * 1e-3) / 1e9,
+            "roofline_frac": (in_bb + out_bb) / (perb * 1e-3) / 1e9 / peak,
+            "read_only_roofline_frac": in_bb / (perb * 1e-3) / 1e9 / peak}
+        if args.c5:
+            entb["MPixels/s_all_gpus"] = world * pix_b / (perb * 1e-3) / 1e6
+            entb["frames"] = NB * world
+            entb["note"] = ("the 256 frames are copies of one synthetic frame (same statistics; generating "
+                            "256 distinct frames on the host would take minutes); ms_per_step is the max "
+                            "over ranks")
+            if dist is not None:
+                from rawspeed_b200 import shard
+                local = d_outb.view(NB, ob)
 
-            def step_g():
-                planb.run((d_inb.data_ptr(), NB * fb), d_outb)
-                shard.gather_frames(local, NB * world, dist)
-            msg = time_steps(torch, step_g, 3, 1, dist)
-            entb["decode_plus_gather_ms"] = msg / 3
-            entb["decode_plus_gather_MPixels/s"] = world * pix_b / (msg / 3 * 1e-3) / 1e6
-    out[label] = entb
-    del planb, d_inb, d_outb, d_in
+                def step_g():
+                    planb.run((d_inb.data_ptr(), NB * fb), d_outb)
+                    shard.gather_frames(local, NB * world, dist)
+                msg = time_steps(torch, step_g, 3, 1, dist)
+                entb["decode_plus_gather_ms"] = msg / 3
+                entb["decode_plus_gather_MPixels/s"] = world * pix_b / (msg / 3 * 1e-3) / 1e6
+        out[label] = entb
+        del planb, d_inb, d_outb
+    del d_in
     if not args.skip_cpu and int(os.environ.get("RANK", "0")) == 0:
         import oracle
         if oracle.HAVE_REF:

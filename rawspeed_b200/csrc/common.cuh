@@ -46,6 +46,9 @@ template <int OFF = 0> __device__ __forceinline__ uint32_t lds_u32(uint32_t sadd
   asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(OFF) : "memory");
   return v;
 }
+template <int OFF = 0> __device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(saddr), "n"(OFF), "r"(v) : "memory");
+}
 template <int OFF = 0> __device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(saddr), "n"(OFF), "h"((uint16_t)v) : "memory");
 }

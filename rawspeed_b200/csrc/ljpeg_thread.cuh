@@ -35,24 +35,26 @@ namespace rsb200 {
 constexpr int T_NT = 128;      // threads (= segments) per CTA
 constexpr int T_MAXTAB = 4;    // plan tables staged in shared memory
 
-// Per-thread ring of clean data in shared memory: T_SLOTS blocks of 16 bytes, block
-// b of the stream in slot b % T_SLOTS, slot s of thread t at ring[s][t].  A warp runs
+// Per-thread ring of clean data in shared memory (word w of the stream at
+// ring[w % T_RING][thread]: conflict free while the lanes of a warp are in step).  A warp runs
 // 32 unrelated streams, and the scoreboard that guards a load's destination register
 // is per WARP: a per-lane "load the next word when I cross into a new one" makes
 // every lane wait for whatever load another lane issued a moment ago.  So global
 // loads happen only at the start of a unit, the same instruction for all lanes,
 // land in the ring at the end of that unit, and are first needed in the next one;
 // inside a unit lanes only touch their ring.
-constexpr int T_SLOTS = 8;
+constexpr int T_RING = 32;       // words per thread (8 blocks of 16 bytes)
 constexpr uint32_t T_AHEAD = 96; // bytes kept requested ahead of the read position
+constexpr uint32_t T_WSTRIDE = 4u * T_NT;             // bytes between consecutive words of a stream
+constexpr uint32_t T_RMASK = T_RING * T_WSTRIDE - 1u; // ring size in bytes - 1
 
 struct ThreadShared {
-  uint4 ring[T_SLOTS][T_NT];
+  uint32_t ring[T_RING][T_NT]; // word w of a stream at ring[w % T_RING][thread]
   DevTable tab[T_MAXTAB];
 };
 
 __host__ __device__ inline size_t thread_smem_bytes(int ntab) {
-  return sizeof(uint4) * T_SLOTS * T_NT + sizeof(DevTable) * (size_t)ntab;
+  return sizeof(uint32_t) * T_RING * T_NT + sizeof(DevTable) * (size_t)ntab;
 }
 
 // symbols the LUT does not resolve (T.81 F.16 walk); .x = difference, .y = bits
@@ -121,7 +123,7 @@ __device__ __noinline__ uint32_t t_stream_position(const uint8_t* gbase, uint32_
   return rawp - skew;
 }
 
-// two samples (components ca, cb of the MCU) -> one output word
+// one sample of component c: Huffman code + mantissa at bit position p of the window
 #define T_SYM(c, val)                                                           \
   do {                                                                          \
     const uint32_t x_ = __funnelshift_l(nxt, cur, p);                           \
@@ -130,22 +132,12 @@ __device__ __noinline__ uint32_t t_stream_position(const uint8_t* gbase, uint32_
     if ((pn_ ^ p) & 32u) { /* into the next word (a symbol is <= 32 bits) */    \
       cur = nxt;                                                                \
       nxt = nn;                                                                 \
-      /* word wi of the stream: slot (wi / 4) % T_SLOTS, word wi % 4 */         \
-      nn = lds_u32<0>(ringb + ((wi & (4u * T_SLOTS - 4u)) * (4u * T_NT)) +      \
-                      ((wi & 3u) << 2));                                        \
-      ++wi;                                                                     \
+      nn = lds_u32<0>(ringb + (wv & T_RMASK)); /* word wv / T_WSTRIDE */        \
+      wv += T_WSTRIDE;                                                          \
     }                                                                           \
     p = pn_;                                                                    \
     pred[c] += d_;                                                              \
     val = pred[c];                                                              \
-  } while (0)
-
-#define T_PAIR(ca, cb, word)                                                    \
-  do {                                                                          \
-    uint32_t va_, vb_;                                                          \
-    T_SYM(ca, va_);                                                             \
-    T_SYM(cb, vb_);                                                             \
-    word = __byte_perm(va_, vb_, 0x5410);                                       \
   } while (0)
 
 template <int G>
@@ -160,11 +152,16 @@ thread_body(ThreadShared& sh, const DevScan* __restrict__ scp, const DevTScan& t
   // prefill: blocks 0 .. T_AHEAD/16 - 1
   uint32_t nblk = T_AHEAD / 16; // blocks requested so far
 #pragma unroll
-  for (uint32_t b = 0; b < T_AHEAD / 16; ++b)
-    sh.ring[b][threadIdx.x] = __ldg(cb + min(b, bmax));
-  uint32_t cur = sh.ring[0][threadIdx.x].x, nxt = sh.ring[0][threadIdx.x].y,
-           nn = sh.ring[0][threadIdx.x].z;
-  uint32_t wi = 3, p = 0;
+  for (uint32_t b = 0; b < T_AHEAD / 16; ++b) {
+    const uint4 q = __ldg(cb + min(b, bmax));
+    sh.ring[4 * b + 0][threadIdx.x] = q.x;
+    sh.ring[4 * b + 1][threadIdx.x] = q.y;
+    sh.ring[4 * b + 2][threadIdx.x] = q.z;
+    sh.ring[4 * b + 3][threadIdx.x] = q.w;
+  }
+  uint32_t cur = sh.ring[0][threadIdx.x], nxt = sh.ring[1][threadIdx.x],
+           nn = sh.ring[2][threadIdx.x];
+  uint32_t wv = 3u * T_WSTRIDE, p = 0; // wv: ring byte offset of the next word to fetch (unwrapped)
 
   uint32_t lutb[G];
   const DevTable* tabp[G];
@@ -208,44 +205,42 @@ thread_body(ThreadShared& sh, const DevScan* __restrict__ scp, const DevTScan& t
           }
         }
       }
-      // 8 samples = 4 words, collected in a rotating 128-bit register
-      uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-      if (G == 4) {
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          uint32_t wa, wb;
-          T_PAIR(0, 1, wa);
-          T_PAIR(2, 3, wb);
-          o0 = o2;
-          o1 = o3;
-          o2 = wa;
-          o3 = wb;
-        }
-      } else {
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          uint32_t w;
-          T_PAIR(0, G - 1, w);
-          o0 = o1;
-          o1 = o2;
-          o2 = o3;
-          o3 = w;
-        }
-      }
+      // 8 samples, straight line (component of sample k = k % G)
+      uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
+      T_SYM(0 % G, v0);
+      T_SYM(1 % G, v1);
+      T_SYM(2 % G, v2);
+      T_SYM(3 % G, v3);
+      T_SYM(4 % G, v4);
+      T_SYM(5 % G, v5);
+      T_SYM(6 % G, v6);
+      T_SYM(7 % G, v7);
+      const uint32_t o0 = __byte_perm(v0, v1, 0x5410), o1 = __byte_perm(v2, v3, 0x5410),
+                     o2 = __byte_perm(v4, v5, 0x5410), o3 = __byte_perm(v6, v7, 0x5410);
       if (u == 0) { // the first MCU of the row predicts the first MCU of the next row
-        rowstart[0] = o0 & 0xFFFFu;
+        rowstart[0] = v0;
         if (G >= 2)
-          rowstart[1] = o0 >> 16;
+          rowstart[1] = v1;
         if (G == 4) {
-          rowstart[2] = o1 & 0xFFFFu;
-          rowstart[3] = o1 >> 16;
+          rowstart[2] = v2;
+          rowstart[3] = v3;
         }
       }
       // ---- end of the unit: the blocks requested at its start go into the ring ----
-      if (pend & 1u)
-        sh.ring[qb0 & (T_SLOTS - 1)][threadIdx.x] = q0;
-      if (pend & 2u)
-        sh.ring[qb1 & (T_SLOTS - 1)][threadIdx.x] = q1;
+      if (pend & 1u) {
+        const uint32_t a = ringb + ((qb0 * (4u * T_WSTRIDE)) & T_RMASK);
+        sts_u32<0>(a, q0.x);
+        sts_u32<(int)T_WSTRIDE>(a, q0.y);
+        sts_u32<2 * (int)T_WSTRIDE>(a, q0.z);
+        sts_u32<3 * (int)T_WSTRIDE>(a, q0.w);
+      }
+      if (pend & 2u) {
+        const uint32_t a = ringb + ((qb1 * (4u * T_WSTRIDE)) & T_RMASK);
+        sts_u32<0>(a, q1.x);
+        sts_u32<(int)T_WSTRIDE>(a, q1.y);
+        sts_u32<2 * (int)T_WSTRIDE>(a, q1.z);
+        sts_u32<3 * (int)T_WSTRIDE>(a, q1.w);
+      }
       const uint32_t s = u << 3;
       if (s + 8 <= store_w) {
         stg_cs_v4(orow + 16ull * u, make_uint4(o0, o1, o2, o3));
@@ -271,7 +266,6 @@ thread_body(ThreadShared& sh, const DevScan* __restrict__ scp, const DevTScan& t
                                       anchors + ts.anchor_off, ts.n_anchor, info.clean_len);
   }
 }
-#undef T_PAIR
 #undef T_SYM
 
 #ifndef RSB200_T_LB

@@ -180,8 +180,6 @@ extern "C" int rsb200_create(int device, rsb200_ctx** out) {
                        (int)sizeof(K2Shared));
   cudaFuncSetAttribute(k2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)fused_smem_bytes(4));
-  cudaFuncSetAttribute(k2_clean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)fused_smem_bytes(4));
   cudaFuncSetAttribute(k2_range_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)fused_smem_bytes(4));
   cudaFuncSetAttribute(k2_range_diffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1230,9 +1228,9 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       ctx->launches += 1;
     }
     if (p->nthread) {
-      k2_clean_kernel<<<p->nthread, F_NT, fused_smem_bytes(0), st>>>(
-          in, (uint64_t)in_bytes, p->d_scans, p->d_thread_ids, p->d_tscans, p->d_clean,
-          p->d_anchors, p->d_tinfos);
+      k2_clean_kernel<<<(p->nthread + C_WARPS - 1) / C_WARPS, 32 * C_WARPS, 0, st>>>(
+          in, (uint64_t)in_bytes, p->d_scans, p->d_thread_ids, (uint32_t)p->nthread, p->d_tscans,
+          p->d_clean, p->d_anchors, p->d_tinfos);
       k2_thread_kernel<<<(p->nthread + T_NT - 1) / T_NT, T_NT, thread_smem_bytes(p->ntables), st>>>(
           in, p->d_scans, p->d_tables, p->ntables, outp, p->d_results, p->d_thread_ids,
           (uint32_t)p->nthread, p->d_tscans, p->d_tinfos, p->d_clean, p->d_anchors);

@@ -94,6 +94,15 @@ def one():
                         gb = d_outb[f * ob:f * ob + H * out_pitch].cpu().numpy().view(np.uint16).reshape(H, out_pitch // 2)
                         okb = okb and bool(np.array_equal(gb[:, :W], img))
                     msb = timeit(lambda: planb.run((d_inb.data_ptr(), NB * fb), d_outb), reps=3, warm=1)
+                    if os.environ.get("AB_KERNELS"):
+                        from torch.profiler import profile, ProfilerActivity
+                        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                            planb.run((d_inb.data_ptr(), NB * fb), d_outb)
+                            torch.cuda.synchronize()
+                        for ev in prof.key_averages():
+                            if "k2_" in ev.key:
+                                print("KERNEL dng%d_%s %s %.3f ms" % (NB, path, ev.key.split("(")[0],
+                                                                      ev.device_time_total / 1e3))
                     res["dng%d_%s" % (NB, path)] = {"ms": round(msb, 4), "exact": okb,
                                                     "launches": planb.launches,
                                                     "GPix/s": round(NB * W * H / msb / 1e6, 1)}
