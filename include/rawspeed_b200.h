@@ -220,6 +220,13 @@ typedef struct {
                         (BitStreamerJPEG.h:185-189): bytes from in_offset       */
 } rsb200_scan_result;
 
+/* Segments are independent (DNG tiles, restart intervals).  The plan picks the kernel:
+ * block-per-segment (K2F; multi-CTA K2R for segments > 256 KiB) or, when the plan holds
+ * >= 16384 eligible segments (e.g. a batch of >= 23 frames of 726 tiles), an unstuffing
+ * pre-pass plus one thread per segment (K2C + K2T, ljpeg_clean.cuh / ljpeg_thread.cuh).
+ * Results are identical; the environment variable RSB200_LJPEG_PATH=fused|thread, read at
+ * plan creation, forces the choice (tests).  The thread path allocates a scratch copy of
+ * the compressed bytes of its segments with the plan. */
 int rsb200_ljpeg_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables,
                              int ntables, const rsb200_ljpeg_scan* scans,
                              int nscans, rsb200_plan** plan);
