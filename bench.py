@@ -502,13 +502,18 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
             if dist is not None:
                 from rawspeed_b200 import shard
                 local = d_outb.view(NB, ob)
+                gathered = torch.empty((world, NB, ob), dtype=torch.uint8, device="cuda")
 
                 def step_g():
                     planb.run((d_inb.data_ptr(), NB * fb), d_outb)
-                    shard.gather_frames(local, NB * world, dist)
+                    shard.gather_frames(local, NB * world, dist, out=gathered, reorder=False)
                 msg = time_steps(torch, step_g, 3, 1, dist)
                 entb["decode_plus_gather_ms"] = msg / 3
                 entb["decode_plus_gather_MPixels/s"] = world * pix_b / (msg / 3 * 1e-3) / 1e6
+                entb["gather"] = ("one ncclAllGather of the uint16 outputs into a preallocated "
+                                  "[world, frames_per_gpu, frame] buffer on every rank (frame r + k*world "
+                                  "at [r, k]); %.1f GB received per GPU" % ((world - 1) * NB * ob / 1e9))
+                del gathered
         out[label] = entb
         del planb, d_inb, d_outb
     del d_in

@@ -24,11 +24,16 @@ def max_frames_per_rank(nframes: int, world: int) -> int:
     return (nframes + world - 1) // world
 
 
-def gather_frames(local_frames, nframes: int, dist=None, group=None):
-    """All ranks end up with all `nframes` decoded frames, in frame order.
+def gather_frames(local_frames, nframes: int, dist=None, group=None, out=None, reorder=True):
+    """All ranks end up with all `nframes` decoded frames.
 
     local_frames: tensor [n_local, ...] holding this rank's frames in the order of
     frames_of_rank().  Ranks with fewer frames are padded for the collective.
+    out: optional preallocated result buffer of shape [world, per, ...] (per =
+    max_frames_per_rank); without it one is allocated per call.
+    reorder=True returns the frames in frame order (one extra device copy of the whole
+    batch); reorder=False returns the collective's own layout, a [world, per, ...] view
+    in which frame r + k*world sits at [r, k] -- no copy besides the collective.
     Works with any torch.distributed backend (nccl on GPUs, gloo on CPU)."""
     import torch
     if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -37,13 +42,21 @@ def gather_frames(local_frames, nframes: int, dist=None, group=None):
     rank = dist.get_rank(group)
     per = max_frames_per_rank(nframes, world)
     shape = (per,) + tuple(local_frames.shape[1:])
-    padded = torch.zeros(shape, dtype=local_frames.dtype, device=local_frames.device)
-    padded[:local_frames.shape[0]] = local_frames
-    out = torch.empty((world,) + shape, dtype=local_frames.dtype, device=local_frames.device)
+    if local_frames.shape[0] == per and local_frames.is_contiguous():
+        padded = local_frames  # (the usual case: every rank holds `per` frames)
+    else:
+        padded = torch.zeros(shape, dtype=local_frames.dtype, device=local_frames.device)
+        padded[:local_frames.shape[0]] = local_frames
+    if out is None:
+        out = torch.empty((world,) + shape, dtype=local_frames.dtype, device=local_frames.device)
+    elif tuple(out.shape) != (world,) + shape or out.dtype != local_frames.dtype:
+        raise ValueError("gather_frames: `out` must have shape [world, per, ...] and the frames' dtype")
     # the collective moves raw bytes (uint8): every backend supports it
     dist.all_gather_into_tensor(out.view(-1).view(torch.uint8), padded.view(-1).view(torch.uint8),
                                 group=group)
+    assert frames_of_rank(nframes, rank, world) == list(range(rank, nframes, world))
+    if not reorder:
+        return out
     # out[r, k] is frame r + k*world
     full = out.permute(1, 0, *range(2, out.dim())).reshape((per * world,) + shape[1:])
-    assert frames_of_rank(nframes, rank, world) == list(range(rank, nframes, world))
     return full[:nframes]

@@ -44,6 +44,14 @@ def _worker(rank, world, port, nframes, ok):
         assert full.shape == (nframes, 4, 6)
         for i in range(nframes):
             assert int(full[i, 0, 0]) == 1000 + i and bool((full[i] == 1000 + i).all())
+        # the copy-free form bench.py times: preallocated [world, per, ...] result, the
+        # collective's own layout (frame r + k*world at [r, k])
+        per = shard.max_frames_per_rank(nframes, world)
+        buf = torch.full((world, per, 4, 6), -1, dtype=torch.int16)
+        got = shard.gather_frames(local, nframes, dist, out=buf, reorder=False)
+        assert got.data_ptr() == buf.data_ptr()
+        for i in range(nframes):
+            assert bool((got[i % world, i // world] == 1000 + i).all())
         # max-over-ranks timing reduction used by bench.py
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
