@@ -242,6 +242,24 @@ def unpack_form(data, img, w, cpp, crop, in_pitch, bps, order, form, table=None,
     return img
 
 
+def sony_arw2(img, w, data, table=None, dither=False):
+    """SonyArw2Decompressor(img, data).decompress() into img (in place); `table` = the
+    storage build_table() returns (None: the image has no table)."""
+    p, n = _u8(data)
+    im = _img(img, w, 1)
+    tp = None
+    if table is not None:
+        table = np.ascontiguousarray(table, dtype=np.uint16)
+        tp = table.ctypes.data_as(C.POINTER(C.c_uint16))
+    e = Err()
+    L = lib()
+    L.rso_sony_arw2.argtypes = [C.POINTER(Image), C.c_char_p, C.c_uint32, C.POINTER(C.c_uint16),
+                                C.c_int, C.POINTER(Err)]
+    rc = L.rso_sony_arw2(C.byref(im), p, C.c_uint32(n), tp, int(dither), C.byref(e))
+    e.check(rc)
+    return img
+
+
 def ljpeg_decompress(img, w, cpp, img_frame, mcu, frame_dim, hts, init_pred,
                      rows_per_restart, data):
     p, n = _u8(data)

@@ -198,6 +198,26 @@ def pentax_decompress(img, w, data, meta=None, meta_be=True, reps=1):
     return ms.value
 
 
+def sony_arw2(img, w, data, curve=None, dither=False, nthreads=1, reps=1):
+    """Reference SonyArw2Decompressor (ref_sony_arw2); curve: mRaw->setTable(curve, dither)."""
+    p, n = _u8(data)
+    ms = C.c_double(0)
+    e = Err()
+    cp, nc = None, 0
+    if curve is not None:
+        curve = np.ascontiguousarray(curve, dtype=np.uint16)
+        cp, nc = curve.ctypes.data_as(C.POINTER(C.c_uint16)), curve.size
+    L = lib()
+    L.ref_sony_arw2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_uint32,
+                                C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.POINTER(C.c_double), C.POINTER(Err)]
+    rc = L.ref_sony_arw2(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2, p,
+                         C.c_uint32(n), cp, nc, int(dither), nthreads, reps, C.byref(ms),
+                         C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
 def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version, nthreads=1, reps=1):
     """Reference Cr2sRawInterpolator; returns best wall ms."""
     k = (C.c_int * 3)(*coeffs)

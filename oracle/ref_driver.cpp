@@ -41,6 +41,7 @@
 #include "decompressors/UncompressedDecompressor.h"
 #include "interpolators/Cr2sRawInterpolator.h"
 #include "decompressors/PentaxDecompressor.h"
+#include "decompressors/SonyArw2Decompressor.h"
 #include "io/Buffer.h"
 #include "io/ByteStream.h"
 #include "io/Endianness.h"
@@ -296,6 +297,32 @@ int ref_unpack_form(const uint8_t* in, uint32_t in_size, void* img_data, int is_
     for (int r = 0; r < h; ++r)
       std::memcpy(static_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, rowPtr(r),
                   static_cast<size_t>(w) * bpp);
+  });
+}
+
+// SonyArw2Decompressor(mRaw, input).decompress() (SonyArw2Decompressor.h); curve !=
+// nullptr -> mRaw->setTable(curve, dither) first, as ArwDecoder does through
+// RawImageCurveGuard (decoders/ArwDecoder.cpp).
+int ref_sony_arw2(uint16_t* img_data, int w, int h, int pitch, const uint8_t* data,
+                  uint32_t size, const uint16_t* curve, int ncurve, int dither, int nthreads,
+                  int reps, double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(w, h, 1, false, 1, 1);
+    copyIn(img, img_data, pitch);
+    if (curve)
+      img->setTable(std::vector<uint16_t>(curve, curve + ncurve), dither != 0);
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      SonyArw2Decompressor a(img, ByteStream(DataBuffer(Buffer(data, size), Endianness::little)));
+      a.decompress();
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
   });
 }
 

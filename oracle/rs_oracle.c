@@ -2438,3 +2438,95 @@ int64_t rso_encode_diffs_plain(const int32_t* diffs, uint64_t n, const rso_huff*
     bw_put(&w, 0, 8);
   return w.overflow ? -1 : (int64_t)w.n;
 }
+
+/* ------------------------------------------------------------------
+ * SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp)
+ * ------------------------------------------------------------------ */
+int rso_sony_arw2(rso_image* img, const uint8_t* data, uint32_t size, const uint16_t* table,
+                  int table_dither, rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  int row, failed = 0;
+  char first[200];
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  first[0] = 0;
+  if (setjmp(c.jb))
+    return c.e->code;
+  /* ctor (:41-56) */
+  if (img->cpp != 1 || img->is_f32)
+    THROW_RDE(&c, "Unexpected component count / data type");
+  if (!(img->w > 0 && img->h > 0) || img->w % 32 != 0 || img->w > 9600 || img->h > 6376)
+    THROW_RDE(&c, "Unexpected image dimensions found: (%d; %d)", img->w, img->h);
+  /* input_.peekStream(dim.x * dim.y) (ByteStream.h) */
+  if ((uint64_t)img->w * (uint64_t)img->h > (uint64_t)size)
+    THROW_IOE(&c, "Out of bounds access in ByteStream");
+  /* decompressRow (:58-112): rows are independent (OpenMP in the reference) */
+  for (row = 0; row < img->h; row++) {
+    const uint8_t* in = data + (size_t)row * (size_t)img->w;
+    uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch);
+    /* BitStreamerLSB: bit k of the row = bit k%8 of byte k/8 */
+    uint32_t random = (uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16);
+    uint64_t bitpos = 0;
+    int col, bad = 0;
+    for (col = 0; col < img->w && !bad; col += ((col & 1) != 0) ? 31 : 1) {
+      int _max, _min, _imax, _imin, sh = 0, i;
+#define ARW2_BITS(n, dst)                                                                \
+  do {                                                                                   \
+    uint32_t v_ = 0;                                                                     \
+    int k_;                                                                              \
+    for (k_ = 0; k_ < (n); k_++, bitpos++)                                               \
+      v_ |= (uint32_t)((in[bitpos >> 3] >> (bitpos & 7)) & 1u) << k_;                    \
+    (dst) = (int)v_;                                                                     \
+  } while (0)
+      ARW2_BITS(11, _max);
+      ARW2_BITS(11, _min);
+      ARW2_BITS(4, _imax);
+      ARW2_BITS(4, _imin);
+      if (_imax == _imin) {
+        bad = 1; /* ThrowRDE inside the row; the row loop records it (:121-127) */
+        break;
+      }
+      while (sh < 4 && (0x80 << sh) <= (_max - _min))
+        sh++;
+      for (i = 0; i < 16; i++) {
+        int pv;
+        uint16_t value;
+        if (i == _imax)
+          pv = _max;
+        else if (i == _imin)
+          pv = _min;
+        else {
+          int d;
+          ARW2_BITS(7, d);
+          pv = (d << sh) + _min;
+          if (pv > 0x7ff)
+            pv = 0x7ff;
+        }
+        value = (uint16_t)(pv << 1);
+        /* setWithLookUp (RawImage.h:335-353) */
+        if (!table) {
+          o[col + i * 2] = value;
+        } else if (table_dither) {
+          uint32_t base = table[2 * value + 0], delta = table[2 * value + 1];
+          uint32_t r = random;
+          uint32_t pix = base + ((delta * (r & 2047) + 1024) >> 12);
+          random = 15700 * (r & 65535) + (r >> 16);
+          o[col + i * 2] = (uint16_t)pix;
+        } else {
+          o[col + i * 2] = table[value];
+        }
+      }
+#undef ARW2_BITS
+    }
+    if (bad && !failed) {
+      failed = 1;
+      snprintf(first, sizeof first, "ARW2 invariant failed, same pixel is both min and max");
+    }
+  }
+  /* decompress (:135-148): isTooManyErrors(1) */
+  if (failed)
+    THROW_RDE(&c, "Too many errors encountered. Giving up. First Error:\n%s", first);
+  return RSO_OK;
+}

@@ -153,6 +153,16 @@ int rso_pentax_table(const uint8_t* meta, int meta_size, int meta_be, uint8_t* n
 int64_t rso_encode_diffs_plain(const int32_t* diffs, uint64_t n, const rso_huff* ht,
                                uint8_t* out, uint64_t cap);
 
+/* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
+ * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
+ * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity
+ * pixels (the blocks of the even and the odd pixels of 32 columns alternate).  Every
+ * value goes through RawImageDataU16::setWithLookUp (common/RawImage.h:335-353) with
+ * a per-row dither state seeded from the row's first 24 bits.
+ * `table`/`table_dither` as in rso_unpack_form (NULL = image has no table). */
+int rso_sony_arw2(rso_image* img, const uint8_t* data, uint32_t size, const uint16_t* table,
+                  int table_dither, rso_err* e);
+
 /* ---- Cr2sRawInterpolator (interpolators/Cr2sRawInterpolator.cpp:32-544) ----
  * in: the subsampled image as decoded (in_w uint16 per row = 4 or 6 per MCU);
  * out: 3-component image (out->sub_x/sub_y = ImageMetaData::subsampling selects

@@ -169,3 +169,29 @@ def make_pentax(img, table):
     d[:2, :2] = a[:2, :2]
     ht = port.Huff(table[0], table[1])
     return port.encode_diffs_plain(d.reshape(-1), ht)
+
+
+def arw2_frame(w, h, seed):
+    """Random SonyArw2 payload (one byte per pixel, 128-bit blocks): LCG bytes with the
+    one invalid pattern (imax == imin, SonyArw2Decompressor.cpp:88-89) patched away."""
+    assert w % 32 == 0
+    a = lcg_bytes(w * h, seed).reshape(-1, 16).copy()
+    # bits 22..25 = imax, 26..29 = imin (LSB-first fields: max 0..10, min 11..21)
+    v = a[:, 2].astype(np.uint32) | (a[:, 3].astype(np.uint32) << 8)   # bits 16..31
+    imax = (v >> 6) & 15
+    imin = (v >> 10) & 15
+    same = imax == imin
+    imin = np.where(same, (imin + 1) & 15, imin)
+    v = (v & ~np.uint32(15 << 10)) | (imin.astype(np.uint32) << 10)
+    a[:, 2] = (v & 255).astype(np.uint8)
+    a[:, 3] = (v >> 8).astype(np.uint8)
+    return a.reshape(-1)
+
+
+def sony_curve():
+    """The curve ArwDecoder::SonyDecodeCurve-style tables look like: 0x4001 entries,
+    identity up to a knee, then steeper segments (values <= 0x3fff -> 16 bit)."""
+    x = np.arange(0x4001, dtype=np.int64)
+    y = np.where(x < 2048, x, np.where(x < 4096, 2048 + (x - 2048) * 2,
+                 np.where(x < 8192, 6144 + (x - 4096) * 3, 18432 + (x - 8192) * 4)))
+    return np.minimum(y, 65535).astype(np.uint16)
