@@ -155,6 +155,30 @@ int rsb200_raw_plan_create(rsb200_ctx* ctx, const rsb200_raw_job* jobs, int njob
                            const uint16_t* tables, int ntables, rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* K6: Sony ARW2 block codec.                            */
+/*   SonyArw2Decompressor::decompressRow / decompress                   */
+/*   decompressors/SonyArw2Decompressor.cpp:58-112, 114-148             */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t in_offset;  /* first byte of the image's data: width*height bytes       */
+  uint64_t out_offset; /* byte offset of image row 0; multiple of 16               */
+  uint32_t out_pitch;  /* bytes between output rows; multiple of 16, >= 2*width    */
+  uint32_t width;      /* multiple of 32, <= 9600                                  */
+  uint32_t height;     /* <= 6376                                                  */
+  int32_t table;       /* index into the plan's tables, -1 = image has no table    */
+} rsb200_arw2_job;
+
+/* `tables`: ntables tables in TableLookUp's storage layout (common/TableLookUp.cpp:
+ * 48-85): dither == 0 -> 65536 uint16 each, dither != 0 -> 2*65536 uint16 each
+ * (base, delta pairs).  Only entries of values <= 0xFFE are ever used (a value is
+ * an 11-bit number << 1).  A block whose imax == imin makes rsb200_plan_results
+ * report RSB200_ERR_RDE for its job (the reference throws "ARW2 invariant
+ * failed, ..." for the row and gives up on the image).                          */
+int rsb200_arw2_plan_create(rsb200_ctx* ctx, const rsb200_arw2_job* jobs, int njobs,
+                            const uint16_t* tables, int ntables, int dither,
+                            rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
 /* K5: Canon sRaw interpolation.                         */
 /*   Cr2sRawInterpolator::interpolate(version)                          */
 /*   interpolators/Cr2sRawInterpolator.cpp:96-187 (4:2:2), :189-453     */

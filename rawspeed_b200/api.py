@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -167,6 +167,20 @@ def sraw_plan(ctx, jobs):
     arr = (SrawJob * len(jobs))(*jobs)
     h = C.c_void_p()
     ctx.check(ctx._lib.rsb200_sraw_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def arw2_plan(ctx, jobs, tables=None, dither=False):
+    """Sony ARW2 images (SonyArw2Decompressor::decompress), one job per image.  tables:
+    TableLookUp storage per table (65536 uint16, or 2*65536 when dithered), or None."""
+    arr = (Arw2Job * len(jobs))(*jobs)
+    h = C.c_void_p()
+    tp, nt = None, 0
+    if tables is not None:
+        tables = np.ascontiguousarray(tables, dtype=np.uint16).reshape(-1, 131072 if dither else 65536)
+        tp, nt = tables.ctypes.data_as(C.POINTER(C.c_uint16)), tables.shape[0]
+    ctx.check(ctx._lib.rsb200_arw2_plan_create(ctx.h, arr, len(jobs), tp, nt, int(dither),
+                                               C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

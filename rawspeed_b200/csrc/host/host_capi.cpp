@@ -247,6 +247,19 @@ int rsb200h_pentax_decompress(uint16_t* img_data, int w, int h, int pitch, const
   });
 }
 
+int rsb200h_sony_arw2(uint16_t* img_data, int w, int h, int pitch, const uint8_t* data,
+                      uint32_t size, const uint16_t* curve, int ncurve, int dither,
+                      rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, 1, pitch, true, 1, 1);
+    if (curve)
+      img->setTable(std::vector<uint16_t>(curve, curve + ncurve), dither != 0);
+    SonyArw2Decompressor a(img, ByteStream(data, size));
+    a.decompress();
+    copyOut(img, img_data);
+  });
+}
+
 int rsb200h_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
                              uint16_t* out_data, int out_w, int out_h, int out_pitch, int sub_x,
                              int sub_y, const int* coeffs, int hue, int version,

@@ -532,6 +532,49 @@ void PentaxDecompressor::decompress(ByteStream data) const {
   engineCheck(rc, "rsb200_plan_results");
 }
 
+// ------------------------------------------------------------------ Sony ARW2
+// SonyArw2Decompressor ctor (decompressors/SonyArw2Decompressor.cpp:41-56)
+SonyArw2Decompressor::SonyArw2Decompressor(RawImage img, ByteStream input_)
+    : mRaw(std::move(img)), input(input_) {
+  if (mRaw->getCpp() != 1 || mRaw->getDataType() != RawImageType::UINT16 ||
+      mRaw->getBpp() != sizeof(uint16_t))
+    ThrowRDE("Unexpected component count / data type");
+  if (!(mRaw->dim.x > 0 && mRaw->dim.y > 0) || mRaw->dim.x % 32 != 0 || mRaw->dim.x > 9600 ||
+      mRaw->dim.y > 6376)
+    ThrowRDE("Unexpected image dimensions found: (%d; %d)", mRaw->dim.x, mRaw->dim.y);
+  // 1 byte per pixel: input_.peekStream(dim.x * dim.y)
+  if ((uint64_t)mRaw->dim.x * (uint64_t)mRaw->dim.y > input.getRemainSize())
+    ThrowIOE("Out of bounds access in ByteStream");
+}
+
+// SonyArw2Decompressor::decompress (:135-148); rows / blocks in parallel on the device
+void SonyArw2Decompressor::decompress() const {
+  rsb200_arw2_job job;
+  std::memset(&job, 0, sizeof job);
+  job.in_offset = 0;
+  job.out_offset = 0;
+  job.out_pitch = (uint32_t)mRaw->pitch;
+  job.width = (uint32_t)mRaw->dim.x;
+  job.height = (uint32_t)mRaw->dim.y;
+  job.table = mRaw->hasTable() ? 0 : -1;
+  PlanGuard pg;
+  engineCheck(rsb200_arw2_plan_create(engine(), &job, 1,
+                                      mRaw->hasTable() ? mRaw->tableData().data() : nullptr,
+                                      mRaw->hasTable() ? 1 : 0, mRaw->tableDither() ? 1 : 0, &pg.p),
+              "rsb200_arw2_plan_create");
+  RawImage img = mRaw;
+  const size_t bytes = (size_t)mRaw->dim.x * (size_t)mRaw->dim.y;
+  runOnImage(pg.p, input.begin() + input.getPosition(), bytes, img, /*partial=*/false);
+  rsb200_scan_result res;
+  const int rc = rsb200_plan_results(pg.p, &res, 1);
+  if (rc == RSB200_OK)
+    return;
+  if (res.status == RSB200_ERR_RDE)
+    ThrowRDE("Too many errors encountered. Giving up. First Error:\n"
+             "ARW2 invariant failed, same pixel is both min and max");
+  engineCheck(rc, "rsb200_plan_results");
+}
+
 // ------------------------------------------------------------------ sRaw
 // Cr2sRawInterpolator::interpolate (interpolators/Cr2sRawInterpolator.cpp:499-542)
 void Cr2sRawInterpolator::interpolate(int version) {

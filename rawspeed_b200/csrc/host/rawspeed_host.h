@@ -467,6 +467,21 @@ private:
   const PrefixCodeDecoder<> ht;
 };
 
+// ---------------------------------------------------------------- Sony ARW2
+// decompressors/SonyArw2Decompressor.h: same constructor (image + the byte stream,
+// one byte per pixel) and decompress().  The image's table (RawImageData::setTable,
+// set by ArwDecoder through RawImageCurveGuard) is applied on the device, including
+// the dithered form.
+class SonyArw2Decompressor final {
+public:
+  SonyArw2Decompressor(RawImage img, ByteStream input);
+  void decompress() const;
+
+private:
+  RawImage mRaw;
+  ByteStream input;
+};
+
 // ---------------------------------------------------------------- sRaw
 // adt/Array2DRef.h: non-owning 2-D view (pitch in elements)
 template <typename T> class Array2DRef {

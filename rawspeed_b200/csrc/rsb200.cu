@@ -10,6 +10,7 @@
 #include "ljpeg_thread.cuh"
 #include "rawforms.cuh"
 #include "sraw.cuh"
+#include "arw2.cuh"
 #include "pentax.cuh"
 #include "unpack.cuh"
 
@@ -92,7 +93,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -105,6 +106,13 @@ struct rsb200_plan {
   std::vector<RawGroup> raw_groups;
   uint16_t* d_raw_tables = nullptr;
   std::vector<SrawGroup> sraw_groups;
+  // Sony ARW2
+  Arw2JobDev* d_arw2_jobs = nullptr;
+  uint16_t* d_arw2_tables = nullptr;
+  uint32_t* d_arw2_bad = nullptr;
+  uint32_t* h_arw2_bad = nullptr; // pinned
+  uint32_t arw2_groups = 0;
+  int arw2_mode = 0;
   // ljpeg
   DevTable* d_tables = nullptr;
   DevScan* d_scans = nullptr;
@@ -575,6 +583,127 @@ extern "C" int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* j
   p->launches_per_run = (int)p->sraw_groups.size();
   *out = p;
   return RSB200_OK;
+}
+
+// ------------------------------------------------------------------
+// Sony ARW2 (K6)
+// ------------------------------------------------------------------
+extern "C" int rsb200_arw2_plan_create(rsb200_ctx* ctx, const rsb200_arw2_job* jobs, int njobs,
+                                       const uint16_t* tables, int ntables, int dither,
+                                       rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out || ntables < 0 || (ntables > 0 && !tables))
+    return set_err(ctx, RSB200_ERR_ARG, "arw2_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  p->kind = 4;
+  p->nunits = njobs;
+  std::vector<Arw2JobDev> dev((size_t)njobs);
+  uint64_t groups = 0;
+  bool any_table = false, any_plain = false;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_arw2_job& j = jobs[i];
+    // SonyArw2Decompressor ctor (SonyArw2Decompressor.cpp:41-56)
+    const bool ok = j.width > 0 && j.height > 0 && j.width % 32 == 0 && j.width <= 9600 &&
+                    j.height <= 6376 && (j.out_offset % 16) == 0 && (j.out_pitch % 16) == 0 &&
+                    (uint64_t)j.width * 2 <= j.out_pitch && j.table < ntables;
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "arw2 job %d: malformed descriptor", i);
+    }
+    (j.table >= 0 ? any_table : any_plain) = true;
+    Arw2JobDev& d = dev[(size_t)i];
+    d.in_offset = j.in_offset;
+    d.out_offset = j.out_offset;
+    d.out_pitch = j.out_pitch;
+    d.width = j.width;
+    d.height = j.height;
+    d.groups_per_row = j.width / 32;
+    d.group_begin = (uint32_t)groups;
+    d.table = j.table;
+    groups += (uint64_t)d.groups_per_row * j.height;
+    const uint64_t px = (uint64_t)j.width * j.height;
+    p->in_bytes += px;
+    p->out_bytes += px * 2;
+    p->pixels += px;
+    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + px);
+    p->need_out = std::max<uint64_t>(p->need_out, j.out_offset +
+                                                      (uint64_t)(j.height - 1) * j.out_pitch +
+                                                      2ull * j.width);
+  }
+  if (any_table && any_plain) {
+    delete p;
+    return set_err(ctx, RSB200_ERR_ARG, "arw2 plan: jobs with and without a table cannot be mixed");
+  }
+  if (groups >= 0xFFFF0000ull) {
+    delete p;
+    return set_err(ctx, RSB200_ERR_ARG, "arw2 plan: too many blocks");
+  }
+  p->arw2_groups = (uint32_t)groups;
+  p->arw2_mode = !any_table ? 0 : (dither ? 2 : 1);
+  // the part of the tables a value can reach: entries 0 .. 4095
+  std::vector<uint16_t> tcut;
+  if (any_table) {
+    const size_t per_in = dither ? 2u * 65536u : 65536u, per_out = dither ? 8192u : 4096u;
+    tcut.resize(per_out * (size_t)ntables);
+    for (int t = 0; t < ntables; ++t)
+      memcpy(&tcut[per_out * (size_t)t], tables + per_in * (size_t)t, per_out * sizeof(uint16_t));
+  }
+  {
+    // 15700^(32 g) mod m (one modular multiplication takes a thread to its 32 calls)
+    static uint32_t jump[ARW2_MAX_GROUPS];
+    uint64_t step = 1;
+    for (int k = 0; k < 32; ++k)
+      step = step * 15700ull % ARW2_M;
+    uint64_t v = 1;
+    for (int gq = 0; gq < ARW2_MAX_GROUPS; ++gq) {
+      jump[gq] = (uint32_t)v;
+      v = v * step % ARW2_M;
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_arw2_jump, jump, sizeof jump);
+    if (e == cudaSuccess)
+      e = cudaMalloc(&p->d_arw2_jobs, sizeof(Arw2JobDev) * dev.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->d_arw2_jobs, dev.data(), sizeof(Arw2JobDev) * dev.size(),
+                     cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMalloc(&p->d_arw2_tables, tcut.size() * sizeof(uint16_t) + 16);
+    if (e == cudaSuccess && !tcut.empty())
+      e = cudaMemcpy(p->d_arw2_tables, tcut.data(), tcut.size() * sizeof(uint16_t),
+                     cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMalloc(&p->d_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
+    if (e == cudaSuccess)
+      e = cudaMallocHost((void**)&p->h_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "arw2 plan upload failed: %s", cudaGetErrorString(e));
+    }
+  }
+  p->launches_per_run = 1;
+  *out = p;
+  return RSB200_OK;
+}
+
+static cudaError_t run_arw2(const rsb200_plan* p, const uint8_t* in, uint8_t* outp,
+                            cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(p->d_arw2_bad, 0, sizeof(uint32_t) * (size_t)p->nunits, st);
+  if (e != cudaSuccess)
+    return e;
+  const uint32_t nb = (p->arw2_groups + ARW2_NT - 1) / ARW2_NT;
+#define RSB_ARW2(M)                                                                        \
+  arw2_kernel<M><<<nb, ARW2_NT, 0, st>>>(in, outp, p->d_arw2_jobs, p->nunits, p->arw2_groups, \
+                                         p->d_arw2_tables, p->d_arw2_bad)
+  if (p->arw2_mode == 0)
+    RSB_ARW2(0);
+  else if (p->arw2_mode == 1)
+    RSB_ARW2(1);
+  else
+    RSB_ARW2(2);
+#undef RSB_ARW2
+  return cudaGetLastError();
 }
 
 static cudaError_t run_sraw_group(const SrawGroup& g, const uint8_t* in, uint8_t* outp,
@@ -1206,6 +1335,9 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->kind == 4) {
+    CUDA_TRY(ctx, run_arw2(p, in, outp, st));
+    ctx->launches++;
   } else if (p->kind == 3) {
     for (const SrawGroup& g : p->sraw_groups) {
       CUDA_TRY(ctx, run_sraw_group(g, in, outp, st));
@@ -1396,6 +1528,25 @@ extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, 
   rsb200_ctx* ctx = p->ctx;
   if (!p->ran)
     return set_err(ctx, RSB200_ERR_ARG, "plan_results: plan has not been run");
+  if (p->kind == 4) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(p->h_arw2_bad, p->d_arw2_bad, sizeof(uint32_t) * (size_t)p->nunits,
+                                  cudaMemcpyDeviceToHost, p->last_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
+    int first = RSB200_OK;
+    for (int i = 0; i < p->nunits; ++i) {
+      const bool bad = p->h_arw2_bad[i] != 0;
+      if (results && i < n) {
+        results[i].status = bad ? RSB200_ERR_RDE : RSB200_OK;
+        results[i].consumed = 0;
+      }
+      if (bad && first == RSB200_OK) {
+        first = RSB200_ERR_RDE;
+        set_err(ctx, first, "Too many errors encountered. Giving up. First Error:\n"
+                            "ARW2 invariant failed, same pixel is both min and max");
+      }
+    }
+    return first;
+  }
   if (p->kind != 1) {
     CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
     for (int i = 0; results && i < n; ++i) {
@@ -1470,6 +1621,11 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     cudaFree(g.d_jobs);
   for (RawGroup& g : p->raw_groups)
     cudaFree(g.d_jobs);
+  cudaFree(p->d_arw2_jobs);
+  cudaFree(p->d_arw2_tables);
+  cudaFree(p->d_arw2_bad);
+  if (p->h_arw2_bad)
+    cudaFreeHost(p->h_arw2_bad);
   for (SrawGroup& g : p->sraw_groups)
     cudaFree(g.d_jobs);
   cudaFree(p->d_raw_tables);

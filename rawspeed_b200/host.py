@@ -151,6 +151,23 @@ def pentax_decompress(img, w, data, meta=None, meta_be=True):
     return img
 
 
+def sony_arw2(img, w, data, curve=None, dither=False):
+    """SonyArw2Decompressor(img, data).decompress() via the host mirror; curve:
+    img->setTable(curve, dither) first."""
+    p, n = _u8(data)
+    cp, nc = None, 0
+    if curve is not None:
+        curve = np.ascontiguousarray(curve, dtype=np.uint16)
+        cp, nc = curve.ctypes.data_as(C.POINTER(C.c_uint16)), curve.size
+    e = _Err()
+    L = lib()
+    L.rsb200h_sony_arw2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_uint32,
+                                    C.POINTER(C.c_uint16), C.c_int, C.c_int, C.POINTER(_Err)]
+    e.check(L.rsb200h_sony_arw2(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
+                                p, C.c_uint32(n), cp, nc, int(dither), C.byref(e)))
+    return img
+
+
 def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version):
     """Cr2sRawInterpolator(out, inp, coeffs, hue).interpolate(version) via the host mirror."""
     k = (C.c_int * 3)(*coeffs)
