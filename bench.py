@@ -571,7 +571,7 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
 
 
 def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
-    """Canon sRaw interpolation and the Pentax PEF codec, device-timed."""
+    """Canon sRaw interpolation, the Pentax PEF codec, Sony ARW2; device-timed."""
     out = {}
     steps = max(3, min(args.steps, 10))
     rank0 = int(os.environ.get("RANK", "0")) == 0
@@ -644,6 +644,51 @@ def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
                                     "MPixels/s": w * h / (msr * 1e-3) / 1e6,
                                     "sample": "PentaxDecompressor::decompress (single threaded by design)"}
     out["8(f)2 PentaxDecompressor 6016x4000"] = ent
+    del plan, d_in, d_out
+    # ---- SonyArw2Decompressor, 9568x6376 (61 MP, A7R IV class), dithered curve, 4 frames ----
+    w, h, nf = 9568, 6376, 4
+    data = synth.arw2_frame(w, h, seed=21)
+    curve = synth.sony_curve()
+    table = port.build_table(curve, True)
+    opitch = rs.image_pitch(w)
+    fb = (data.size + 255) // 256 * 256
+    ob = (h * opitch + 255) // 256 * 256
+    jobs = []
+    for f in range(nf):
+        aj = rs.Arw2Job()
+        aj.in_offset, aj.out_offset, aj.out_pitch = f * fb, f * ob, opitch
+        aj.width, aj.height, aj.table = w, h, 0
+        jobs.append(aj)
+    plan = rs.arw2_plan(ctx, jobs, table, True)
+    d_in = torch.zeros(nf * fb + 64, dtype=torch.uint8, device="cuda")
+    for f in range(nf):
+        d_in[f * fb:f * fb + data.size] = torch.from_numpy(data)
+    d_out = torch.zeros(nf * ob, dtype=torch.uint8, device="cuda")
+    plan.run((d_in.data_ptr(), nf * fb), d_out)
+    res = plan.results()
+    want = port.new_image(w, h)
+    port.sony_arw2(want, w, data, table, True)
+    got = d_out[(nf - 1) * ob:(nf - 1) * ob + h * opitch].cpu().numpy().view(np.uint16).reshape(h, opitch // 2)
+    exact = bool(np.array_equal(got, want)) and all(s_ == 0 for s_, _ in res)
+    ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), nf * fb), d_out), steps, 3, dist)
+    in_b, out_b, pixels = plan.bytes()
+    per = ms / steps
+    ent = {"MPixels/s": pixels / (per * 1e-3) / 1e6, "ms_per_step": per, "frames_per_step": nf,
+           "bit_exact": exact, "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
+           "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak,
+           "algorithmic_bytes_per_pixel": 3.0, "kernel": "arw2_kernel<dither>"}
+    if not args.skip_cpu and rank0:
+        import oracle
+        if oracle.HAVE_REF:
+            ncores = os.cpu_count() or 1
+            tmp = port.new_image(w, h)
+            msr = min(oracle.ref.sony_arw2(tmp, w, data, curve, True, nthreads=ncores) for _ in range(3))
+            ms1 = oracle.ref.sony_arw2(tmp, w, data, curve, True, nthreads=1)
+            ent["cpu_reference"] = {"kind": "reference", "cores": ncores,
+                                    "MPixels/s": w * h / (msr * 1e-3) / 1e6,
+                                    "single_thread_MPixels/s": w * h / (ms1 * 1e-3) / 1e6,
+                                    "sample": "SonyArw2Decompressor::decompress (OpenMP over rows), 1 frame, best of 3"}
+    out["8(f)4 SonyArw2Decompressor 9568x6376 (dithered curve)"] = ent
     del plan, d_in, d_out
     return out
 
