@@ -242,6 +242,51 @@ def unpack_form(data, img, w, cpp, crop, in_pitch, bps, order, form, table=None,
     return img
 
 
+def nikon_tree(sel):
+    """NikonDecompressor::nikon_tree[sel] as (ncpl[16], values)."""
+    ncpl = (C.c_uint8 * 16)()
+    vals = (C.c_uint8 * 16)()
+    L = lib()
+    L.rso_nikon_tree.argtypes = [C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+    n = L.rso_nikon_tree(sel, ncpl, vals)
+    assert n > 0
+    return bytes(ncpl), bytes(vals[:n])
+
+
+def nikon_setup(meta, meta_be, bits, w, h):
+    """What the NikonDecompressor constructor derives from the maker note:
+    dict(curve, pup = [pUp00, pUp01, pUp10, pUp11], huff_select, split)."""
+    mp, mn = _u8(meta)
+    curve = np.zeros(32770, dtype=np.uint16)
+    nc, hs, sp = C.c_int(0), C.c_int(0), C.c_int(0)
+    pup = (C.c_int * 4)()
+    e = Err()
+    L = lib()
+    L.rso_nikon_setup.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_uint16), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(Err)]
+    rc = L.rso_nikon_setup(mp, mn, int(meta_be), bits, w, h,
+                           curve.ctypes.data_as(C.POINTER(C.c_uint16)), C.byref(nc), pup,
+                           C.byref(hs), C.byref(sp), C.byref(e))
+    e.check(rc)
+    return dict(curve=curve[:nc.value].copy(), pup=list(pup), huff_select=hs.value, split=sp.value)
+
+
+def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False):
+    """NikonDecompressor(img, meta, bits).decompress(data, uncorrected) into img (in place)."""
+    mp, mn = _u8(meta)
+    p, n = _u8(data)
+    im = _img(img, w, 1)
+    e = Err()
+    L = lib()
+    L.rso_nikon_decompress.argtypes = [C.POINTER(Image), C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_char_p, C.c_uint32, C.c_int, C.POINTER(Err)]
+    rc = L.rso_nikon_decompress(C.byref(im), mp, mn, int(meta_be), bits, p, C.c_uint32(n),
+                                int(uncorrected), C.byref(e))
+    e.check(rc)
+    return img
+
+
 def sony_arw2(img, w, data, table=None, dither=False):
     """SonyArw2Decompressor(img, data).decompress() into img (in place); `table` = the
     storage build_table() returns (None: the image has no table)."""

@@ -198,6 +198,23 @@ def pentax_decompress(img, w, data, meta=None, meta_be=True, reps=1):
     return ms.value
 
 
+def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False, reps=1):
+    """Reference NikonDecompressor (ref_nikon_decompress)."""
+    mp, mn = _u8(meta)
+    p, n = _u8(data)
+    ms = C.c_double(0)
+    e = Err()
+    L = lib()
+    L.ref_nikon_decompress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                       C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.c_uint32,
+                                       C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(Err)]
+    rc = L.ref_nikon_decompress(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
+                                mp, C.c_uint32(mn), int(meta_be), bits, p, C.c_uint32(n),
+                                int(uncorrected), reps, C.byref(ms), C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
 def sony_arw2(img, w, data, curve=None, dither=False, nthreads=1, reps=1):
     """Reference SonyArw2Decompressor (ref_sony_arw2); curve: mRaw->setTable(curve, dither)."""
     p, n = _u8(data)

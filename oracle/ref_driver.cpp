@@ -42,6 +42,7 @@
 #include "interpolators/Cr2sRawInterpolator.h"
 #include "decompressors/PentaxDecompressor.h"
 #include "decompressors/SonyArw2Decompressor.h"
+#include "decompressors/NikonDecompressor.h"
 #include "io/Buffer.h"
 #include "io/ByteStream.h"
 #include "io/Endianness.h"
@@ -297,6 +298,31 @@ int ref_unpack_form(const uint8_t* in, uint32_t in_size, void* img_data, int is_
     for (int r = 0; r < h; ++r)
       std::memcpy(static_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, rowPtr(r),
                   static_cast<size_t>(w) * bpp);
+  });
+}
+
+// NikonDecompressor(mRaw, metadata, bitsPS).decompress(input, uncorrectedRawValues)
+// (NikonDecompressor.h:51-55), as NefDecoder::DecodeNikonCompressed drives it.
+int ref_nikon_decompress(uint16_t* img_data, int w, int h, int pitch, const uint8_t* meta,
+                         uint32_t meta_size, int meta_be, int bitsPS, const uint8_t* data,
+                         uint32_t size, int uncorrected, int reps, double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, 1, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      NikonDecompressor n(img,
+                          ByteStream(DataBuffer(Buffer(meta, meta_size),
+                                                meta_be ? Endianness::big : Endianness::little)),
+                          static_cast<uint32_t>(bitsPS));
+      n.decompress(Array1DRef<const uint8_t>(data, static_cast<int>(size)), uncorrected != 0);
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
   });
 }
 

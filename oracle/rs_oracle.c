@@ -2530,3 +2530,228 @@ int rso_sony_arw2(rso_image* img, const uint8_t* data, uint32_t size, const uint
     THROW_RDE(&c, "Too many errors encountered. Giving up. First Error:\n%s", first);
   return RSO_OK;
 }
+
+/* ------------------------------------------------------------------
+ * NikonDecompressor (decompressors/NikonDecompressor.cpp)
+ * ------------------------------------------------------------------ */
+static const uint8_t nikon_tree_tab[6][2][16] = {
+    /* NikonDecompressor::nikon_tree (:47-67) */
+    {{0, 1, 5, 1, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0}, {5, 4, 3, 6, 2, 7, 1, 0, 8, 9, 11, 10, 12}},
+    {{0, 1, 5, 1, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0},
+     {0x39, 0x5a, 0x38, 0x27, 0x16, 5, 4, 3, 2, 1, 0, 11, 12, 12}},
+    {{0, 1, 4, 2, 3, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0}, {5, 4, 6, 3, 7, 2, 8, 1, 9, 0, 10, 11, 12}},
+    {{0, 1, 4, 3, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0},
+     {5, 6, 4, 7, 8, 3, 9, 2, 1, 0, 10, 11, 12, 13, 14}},
+    {{0, 1, 5, 1, 1, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0},
+     {8, 0x5c, 0x4b, 0x3a, 0x29, 7, 6, 5, 4, 3, 2, 1, 0, 13, 14}},
+    {{0, 1, 4, 2, 2, 3, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0},
+     {7, 6, 8, 5, 9, 4, 10, 3, 11, 12, 2, 0, 1, 13, 14}},
+};
+
+int rso_nikon_tree(int sel, uint8_t* ncpl, uint8_t* values) {
+  int n = 0, i;
+  if (sel < 0 || sel > 5)
+    return -1;
+  for (i = 0; i < 16; i++)
+    n += nikon_tree_tab[sel][0][i];
+  memcpy(ncpl, nikon_tree_tab[sel][0], 16);
+  memcpy(values, nikon_tree_tab[sel][1], (size_t)n);
+  return n;
+}
+
+typedef struct {
+  uint32_t huffSelect, split;
+  int pUp[2][2];
+  uint16_t curve[32770];
+  uint32_t ncurve;
+} nikon_setup;
+
+/* ctor (:478-511) + createCurve (:380-441) */
+static void nikon_setup_impl(rso_ctx* c, const uint8_t* meta, int meta_size, int meta_be,
+                             uint32_t bitsPS, int img_w, int img_h, nikon_setup* o) {
+  bstream md;
+  uint32_t v0, v1, csize, step = 0, i, n;
+  md.c = c;
+  md.data = meta;
+  md.size = (uint32_t)meta_size;
+  md.pos = 0;
+  if (!(img_w > 0 && img_h > 0) || img_w % 2 != 0 || img_w > 8288 || img_h > 5520)
+    THROW_RDE(c, "Unexpected image dimensions found: (%d; %d)", img_w, img_h);
+  if (bitsPS != 12 && bitsPS != 14)
+    THROW_RDE(c, "Invalid bpp found: %u", bitsPS);
+  v0 = bs_get_byte(&md);
+  v1 = bs_get_byte(&md);
+  if (v0 == 73 || v1 == 88)
+    bs_skip(&md, 2110);
+  o->huffSelect = 0;
+  o->split = 0;
+  if (v0 == 70)
+    o->huffSelect = 2;
+  if (bitsPS == 14)
+    o->huffSelect += 3;
+  o->pUp[0][0] = bs_get_u16e(&md, meta_be);
+  o->pUp[1][0] = bs_get_u16e(&md, meta_be);
+  o->pUp[0][1] = bs_get_u16e(&md, meta_be);
+  o->pUp[1][1] = bs_get_u16e(&md, meta_be);
+  /* createCurve */
+  if (v0 == 68 && v1 == 64)
+    bitsPS -= 2; /* Nikon Z7 12/14 bit compressed hack */
+  n = ((1u << bitsPS) & 0x7fffu) + 1u;
+  for (i = 0; i < n; i++)
+    o->curve[i] = (uint16_t)i;
+  csize = bs_get_u16e(&md, meta_be);
+  if (csize > 1)
+    step = n / (csize - 1);
+  if (v0 == 68 && (v1 == 32 || v1 == 64) && step > 0) {
+    if ((csize - 1) * step != n - 1)
+      THROW_RDE(c, "Bad curve segment count (%u)", csize);
+    for (i = 0; i < csize; i++)
+      o->curve[i * step] = bs_get_u16e(&md, meta_be);
+    for (i = 0; i < n - 1; i++) {
+      const uint32_t b_scale = i % step, a_pos = i - b_scale, b_pos = a_pos + step;
+      const uint32_t a_scale = step - b_scale;
+      o->curve[i] = (uint16_t)((a_scale * o->curve[a_pos] + b_scale * o->curve[b_pos]) / step);
+    }
+    /* metadata.setPosition(562) (ByteStream.h: check against the size) */
+    if (562 > md.size)
+      THROW_IOE(c, "Out of bounds access in ByteStream");
+    md.pos = 562;
+    o->split = bs_get_u16e(&md, meta_be);
+  } else if (v0 != 70) {
+    if (csize == 0 || csize > 0x4001)
+      THROW_RDE(c, "Don't know how to compute curve! csize = %u", csize);
+    n = csize + 1;
+    for (i = 0; i < csize; i++)
+      o->curve[i] = bs_get_u16e(&md, meta_be);
+  }
+  o->ncurve = n - 1; /* "and drop the last value" */
+  if (o->split >= (uint32_t)img_h)
+    o->split = 0;
+}
+
+int rso_nikon_setup(const uint8_t* meta, int meta_size, int meta_be, int bitsPS, int img_w,
+                    int img_h, uint16_t* curve, int* ncurve, int* pup, int* huff_select,
+                    int* split, rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  nikon_setup* volatile s = NULL;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb)) {
+    free((void*)s);
+    return c.e->code;
+  }
+  s = (nikon_setup*)malloc(sizeof(nikon_setup));
+  if (!s)
+    THROW_RDE(&c, "out of memory");
+  nikon_setup_impl(&c, meta, meta_size, meta_be, (uint32_t)bitsPS, img_w, img_h, (nikon_setup*)s);
+  if (curve)
+    memcpy(curve, ((nikon_setup*)s)->curve, ((nikon_setup*)s)->ncurve * sizeof(uint16_t));
+  if (ncurve)
+    *ncurve = (int)((nikon_setup*)s)->ncurve;
+  if (pup) {
+    pup[0] = ((nikon_setup*)s)->pUp[0][0];
+    pup[1] = ((nikon_setup*)s)->pUp[0][1];
+    pup[2] = ((nikon_setup*)s)->pUp[1][0];
+    pup[3] = ((nikon_setup*)s)->pUp[1][1];
+  }
+  if (huff_select)
+    *huff_select = (int)((nikon_setup*)s)->huffSelect;
+  if (split)
+    *split = (int)((nikon_setup*)s)->split;
+  free((void*)s);
+  return RSO_OK;
+}
+
+int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int meta_be,
+                         int bitsPS, const uint8_t* data, uint32_t size, int uncorrected,
+                         rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  nikon_setup* volatile s = NULL;
+  rso_huff* volatile h = NULL;
+  uint16_t* volatile tab = NULL; /* dithered TableLookUp storage: {base, delta} per value */
+  pump bs;
+  uint8_t ncpl[16], values[16];
+  int nv, row, col;
+  uint32_t random, i;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb)) {
+    free((void*)s);
+    free((void*)h);
+    free((void*)tab);
+    return c.e->code;
+  }
+  if (img->cpp != 1 || img->is_f32)
+    THROW_RDE(&c, "Unexpected component count / data type");
+  s = (nikon_setup*)malloc(sizeof(nikon_setup));
+  h = (rso_huff*)malloc(sizeof(rso_huff));
+  if (!s || !h)
+    THROW_RDE(&c, "out of memory");
+  nikon_setup_impl(&c, meta, meta_size, meta_be, (uint32_t)bitsPS, img->w, img->h,
+                   (nikon_setup*)s);
+  if (((nikon_setup*)s)->split != 0)
+    THROW_RDE(&c, "split"); /* (the second, "lossy after split" decoder is not restated) */
+  /* RawImageCurveGuard + TableLookUp::setTable(curve, dither = true) (TableLookUp.cpp:49-84) */
+  if (!uncorrected) {
+    const uint16_t* cv = ((nikon_setup*)s)->curve;
+    const int nf = (int)((nikon_setup*)s)->ncurve;
+    int k;
+    tab = (uint16_t*)malloc(2u * 65536u * sizeof(uint16_t));
+    if (!tab)
+      THROW_RDE(&c, "out of memory");
+    for (k = 0; k < nf; k++) {
+      int center = cv[k], lower = k > 0 ? cv[k - 1] : center,
+          upper = k < nf - 1 ? cv[k + 1] : center, v;
+      if (lower > center)
+        lower = center;
+      if (upper < center)
+        upper = center;
+      v = center - ((upper - lower + 2) / 4);
+      ((uint16_t*)tab)[2 * k] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+      ((uint16_t*)tab)[2 * k + 1] = (uint16_t)(upper - lower);
+    }
+    for (k = nf; k < 65536; k++) {
+      ((uint16_t*)tab)[2 * k] = cv[nf - 1];
+      ((uint16_t*)tab)[2 * k + 1] = 0;
+    }
+  }
+  nv = rso_nikon_tree((int)((nikon_setup*)s)->huffSelect, ncpl, values);
+  huff_build(&c, (rso_huff*)h, ncpl, values, nv, 1, 0);
+  /* decompress (:540-560, :513-538) */
+  pump_init(&bs, &c, RSO_MSB, data, (int)size);
+  pump_fill(&bs, 24);
+  random = pump_peek_nofill(&bs, 24);
+  for (row = 0; row < img->h; row++) {
+    uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch);
+    int (*pUp)[2] = ((nikon_setup*)s)->pUp;
+    int pred[2];
+    pred[0] = pUp[row & 1][0];
+    pred[1] = pUp[row & 1][1];
+    for (col = 0; col < img->w; col++) {
+      int v;
+      uint16_t value;
+      pred[col & 1] += huff_decode((const rso_huff*)h, &bs, 1);
+      if (col < 2)
+        pUp[row & 1][col & 1] = pred[col & 1];
+      v = pred[col & 1]; /* clampBits(v, 15) */
+      value = (uint16_t)(v < 0 ? 0 : (v > 32767 ? 32767 : v));
+      if (!tab) {
+        o[col] = value;
+      } else {
+        uint32_t base = ((uint16_t*)tab)[2 * value], delta = ((uint16_t*)tab)[2 * value + 1];
+        uint32_t r = random;
+        o[col] = (uint16_t)(base + ((delta * (r & 2047) + 1024) >> 12));
+        random = 15700 * (r & 65535) + (r >> 16);
+      }
+    }
+  }
+  (void)i;
+  free((void*)s);
+  free((void*)h);
+  free((void*)tab);
+  return RSO_OK;
+}

@@ -153,6 +153,27 @@ int rso_pentax_table(const uint8_t* meta, int meta_size, int meta_be, uint8_t* n
 int64_t rso_encode_diffs_plain(const int32_t* diffs, uint64_t n, const rso_huff* ht,
                                uint8_t* out, uint64_t cap);
 
+/* ---- NikonDecompressor (decompressors/NikonDecompressor.cpp:380-562) ----
+ * Constructor (meta = the maker-note ByteStream, meta_be its byte order, bitsPS 12/14):
+ * version bytes, huffSelect, the four start predictors pUp, createCurve (:380-441),
+ * split.  decompress (:513-560): plain MSB bit stream, nikon_tree[huffSelect] full-decode
+ * table, per-parity left predictor with rows starting from pUp[row & 1] (updated by
+ * the first two pixels of every row), clampBits(value, 15), setWithLookUp with the
+ * curve as a DITHERED table (RawImageCurveGuard) unless uncorrected != 0; the dither
+ * state is seeded ONCE with the first 24 bits of the stream.
+ * Restated for split == 0 (no "lossy after split" second table, NikonLASDecompressor
+ * :80-378); a non-zero split returns RSO_RDE with the message "split".
+ * Outputs (may be NULL): curve[<= 32769] + *ncurve, pup[4] = pUp[0][0], pUp[0][1],
+ * pUp[1][0], pUp[1][1], *huff_select, *split. */
+int rso_nikon_setup(const uint8_t* meta, int meta_size, int meta_be, int bitsPS, int img_w,
+                    int img_h, uint16_t* curve, int* ncurve, int* pup, int* huff_select,
+                    int* split, rso_err* e);
+int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int meta_be,
+                         int bitsPS, const uint8_t* data, uint32_t size, int uncorrected,
+                         rso_err* e);
+/* nikon_tree[sel] as (ncpl[16], values[<=16]); returns the number of codes */
+int rso_nikon_tree(int sel, uint8_t* ncpl, uint8_t* values);
+
 /* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
  * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
  * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity

@@ -195,3 +195,58 @@ def sony_curve():
     y = np.where(x < 2048, x, np.where(x < 4096, 2048 + (x - 2048) * 2,
                  np.where(x < 8192, 6144 + (x - 4096) * 3, 18432 + (x - 8192) * 4)))
     return np.minimum(y, 65535).astype(np.uint16)
+
+
+def nikon_meta(kind, bits, pup=(2048, 2050, 2040, 2046), big_endian=True, split=0):
+    """A Nikon maker-note block as NikonDecompressor's constructor reads it
+    (NikonDecompressor.cpp:478-511, createCurve :380-441).  kind:
+      "lossless"  v0=70 (identity curve, trees 2 / 5)
+      "table"     v0=68, v1=16: csize curve values follow (trees 0 / 3)
+      "segments"  v0=68, v1=32: csize knots, linear interpolation, split at offset 562
+      "z7"        v0=68, v1=64: as segments with the 2-bit shorter curve
+      "skip"      v0=73: 2110 bytes skipped first, then as "table"."""
+    u16 = (lambda v: [v >> 8, v & 255]) if big_endian else (lambda v: [v & 255, v >> 8])
+    out = bytearray()
+    v0, v1 = {"lossless": (70, 48), "table": (68, 16), "segments": (68, 32), "z7": (68, 64),
+              "skip": (73, 16)}[kind]
+    out += bytes([v0, v1])
+    if kind == "skip":
+        out += bytes(2110)
+    for v in pup:   # order in the stream: pUp[0][0], pUp[1][0], pUp[0][1], pUp[1][1]
+        out += bytes(u16(v))
+    if kind == "lossless":
+        out += bytes(u16(0))
+    elif kind in ("table", "skip"):
+        n = 1 << bits
+        xs = np.arange(n, dtype=np.int64)
+        ys = np.minimum((xs * 3) // 2 + (xs * xs) // (n * 2), 65535)
+        out += bytes(u16(n))
+        for y in ys:
+            out += bytes(u16(int(y)))
+    else:
+        cb = bits - 2 if kind == "z7" else bits
+        n = ((1 << cb) & 0x7fff) + 1
+        csize = 33     # (csize - 1) * step == n - 1 with step = (n - 1) / 32
+        out += bytes(u16(csize))
+        for k in range(csize):
+            x = k * ((n - 1) // 32)
+            out += bytes(u16(min(65535, x * 2 + (x * x) // (n // 2 + 1))))
+        out += bytes(max(0, 562 - len(out)))
+        out[562:564] = bytes(u16(split))
+    return bytes(out)
+
+
+def make_nikon(img, sel, pup):
+    """Encode a uint16 image (pre-curve values, even width) the way NikonDecompressor
+    decodes it (:513-538): per-parity left predictor, rows start from pUp[row & 1] which
+    the first two pixels of every row update.  pup = [pUp00, pUp01, pUp10, pUp11]."""
+    h, w = img.shape
+    a = img.astype(np.int32)
+    d = np.zeros((h, w), dtype=np.int32)
+    d[:, 2:] = a[:, 2:] - a[:, :-2]
+    d[2:, :2] = a[2:, :2] - a[:-2, :2]
+    d[0, 0], d[0, 1] = a[0, 0] - pup[0], a[0, 1] - pup[1]
+    if h > 1:
+        d[1, 0], d[1, 1] = a[1, 0] - pup[2], a[1, 1] - pup[3]
+    ncpl, values = port.nikon_tree(sel)
+    return port.encode_diffs_plain(d.reshape(-1), port.Huff(ncpl, values))
