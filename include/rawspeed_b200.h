@@ -305,6 +305,36 @@ typedef struct {
 int rsb200_pentax_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables, int ntables,
                               const rsb200_pentax_job* jobs, int njobs, rsb200_plan** plan);
 
+/* ------------------------------------------------------------------ */
+/* Nikon NEF Huffman codec without split.                 */
+/*   NikonDecompressor::decompress  decompressors/NikonDecompressor.cpp:513-560 */
+/*   (plain MSB bit stream, nikon_tree table, per-parity left predictor, */
+/*   rows start from pUp[row & 1], clampBits(15), dithered curve).  The  */
+/*   constructor work (:380-511: version bytes, tree selection, pUp,     */
+/*   createCurve, split) stays on the host.                              */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t in_offset;  /* first byte of the compressed stream                   */
+  uint32_t in_size;    /* bytes available (>= 4)                                */
+  uint32_t table;      /* index into the plan's Huffman tables                  */
+  int32_t width;       /* even, <= 8288                                         */
+  int32_t height;      /* <= 5520                                               */
+  uint64_t out_offset; /* byte offset of image row 0; multiple of 4             */
+  uint32_t out_pitch;  /* bytes; multiple of 4                                  */
+  int32_t lut;         /* index into the plan's curve tables, -1 = none
+                          (uncorrectedRawValues)                                */
+  uint16_t pup[4];     /* pUp[0][0], pUp[0][1], pUp[1][0], pUp[1][1]            */
+} rsb200_nikon_job;
+
+/* `luts`: nluts curve tables in TableLookUp's DITHERED storage layout (2*65536
+ * uint16 each: base, delta per value; common/TableLookUp.cpp:62-84).  Status as for
+ * the LJPEG plans: RSB200_ERR_RDE = bad Huffman code, RSB200_ERR_IOE = stream
+ * exhausted. */
+int rsb200_nikon_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables, int ntables,
+                             const rsb200_nikon_job* jobs, int njobs, const uint16_t* luts,
+                             int nluts, rsb200_plan** plan);
+
+
 
 /* ------------------------------------------------------------------ */
 /* Plan execution                                                       */

@@ -47,6 +47,12 @@ class PentaxJob(C.Structure):
                 ("out_pitch", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class NikonJob(C.Structure):
+    _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint32), ("table", C.c_uint32),
+                ("width", C.c_int32), ("height", C.c_int32), ("out_offset", C.c_uint64),
+                ("out_pitch", C.c_uint32), ("lut", C.c_int32), ("pup", C.c_uint16 * 4)]
+
+
 class Arw2Job(C.Structure):
     _fields_ = [("in_offset", C.c_uint64), ("out_offset", C.c_uint64),
                 ("out_pitch", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
@@ -90,7 +96,7 @@ EXPORTS = [
     "rsb200_abi_version", "rsb200_create", "rsb200_destroy", "rsb200_last_error",
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_raw_plan_create", "rsb200_sraw_plan_create",
-    "rsb200_pentax_plan_create", "rsb200_arw2_plan_create",
+    "rsb200_pentax_plan_create", "rsb200_arw2_plan_create", "rsb200_nikon_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",
@@ -128,6 +134,8 @@ def load():
     L.rsb200_raw_plan_create.argtypes = [vp, C.POINTER(RawJob), i32, C.POINTER(C.c_uint16),
                                          i32, C.POINTER(vp)]
     L.rsb200_sraw_plan_create.argtypes = [vp, C.POINTER(SrawJob), i32, C.POINTER(vp)]
+    L.rsb200_nikon_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32, C.POINTER(NikonJob), i32,
+                                           C.POINTER(C.c_uint16), i32, C.POINTER(vp)]
     L.rsb200_arw2_plan_create.argtypes = [vp, C.POINTER(Arw2Job), i32, C.POINTER(C.c_uint16),
                                           i32, i32, C.POINTER(vp)]
     L.rsb200_pentax_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,

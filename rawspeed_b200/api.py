@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Arw2Job, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, NikonJob, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -167,6 +167,21 @@ def sraw_plan(ctx, jobs):
     arr = (SrawJob * len(jobs))(*jobs)
     h = C.c_void_p()
     ctx.check(ctx._lib.rsb200_sraw_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def nikon_plan(ctx, tables, jobs, luts=None):
+    """Nikon NEF streams without split (NikonDecompressor::decompress), one job per image.
+    luts: dithered TableLookUp storage per curve (2*65536 uint16 each), or None."""
+    ta = (HuffTable * len(tables))(*tables)
+    ja = (NikonJob * len(jobs))(*jobs)
+    h = C.c_void_p()
+    lp, nl = None, 0
+    if luts is not None:
+        luts = np.ascontiguousarray(luts, dtype=np.uint16).reshape(-1, 131072)
+        lp, nl = luts.ctypes.data_as(C.POINTER(C.c_uint16)), luts.shape[0]
+    ctx.check(ctx._lib.rsb200_nikon_plan_create(ctx.h, ta, len(tables), ja, len(jobs), lp, nl,
+                                                C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

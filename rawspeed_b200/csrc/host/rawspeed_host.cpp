@@ -532,6 +532,146 @@ void PentaxDecompressor::decompress(ByteStream data) const {
   engineCheck(rc, "rsb200_plan_results");
 }
 
+// ------------------------------------------------------------------ Nikon
+namespace {
+// NikonDecompressor::nikon_tree (NikonDecompressor.cpp:47-67)
+const uint8_t kNikonTree[6][2][16] = {
+    {{0, 1, 5, 1, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0}, {5, 4, 3, 6, 2, 7, 1, 0, 8, 9, 11, 10, 12}},
+    {{0, 1, 5, 1, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0},
+     {0x39, 0x5a, 0x38, 0x27, 0x16, 5, 4, 3, 2, 1, 0, 11, 12, 12}},
+    {{0, 1, 4, 2, 3, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0}, {5, 4, 6, 3, 7, 2, 8, 1, 9, 0, 10, 11, 12}},
+    {{0, 1, 4, 3, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0, 0},
+     {5, 6, 4, 7, 8, 3, 9, 2, 1, 0, 10, 11, 12, 13, 14}},
+    {{0, 1, 5, 1, 1, 1, 1, 1, 1, 1, 2, 0, 0, 0, 0, 0},
+     {8, 0x5c, 0x4b, 0x3a, 0x29, 7, 6, 5, 4, 3, 2, 1, 0, 13, 14}},
+    {{0, 1, 4, 2, 2, 3, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0},
+     {7, 6, 8, 5, 9, 4, 10, 3, 11, 12, 2, 0, 1, 13, 14}},
+};
+} // namespace
+
+// createPrefixCodeDecoder<PrefixCodeDecoder<>> (:458-471)
+PrefixCodeDecoder<> NikonDecompressor::createPrefixCodeDecoder(uint32_t sel) {
+  HuffmanCode<> hc;
+  const uint32_t count = hc.setNCodesPerLength(Buffer(kNikonTree[sel][0], 16));
+  hc.setCodeValues(kNikonTree[sel][1], (int)count);
+  PrefixCodeDecoder<> ht(std::move(hc));
+  ht.setup(true, false);
+  return ht;
+}
+
+// createCurve (:380-441)
+std::vector<uint16_t> NikonDecompressor::createCurve(ByteStream& metadata, uint32_t bitsPS,
+                                                     uint32_t v0, uint32_t v1, uint32_t* split) {
+  if (v0 == 68 && v1 == 64) // Nikon Z7 12/14 bit compressed hack
+    bitsPS -= 2;
+  std::vector<uint16_t> curve(((1u << bitsPS) & 0x7fffu) + 1u);
+  for (size_t i = 0; i < curve.size(); i++)
+    curve[i] = (uint16_t)i;
+  uint32_t step = 0;
+  const uint32_t csize = metadata.getU16();
+  if (csize > 1)
+    step = (uint32_t)(curve.size() / (csize - 1));
+  if (v0 == 68 && (v1 == 32 || v1 == 64) && step > 0) {
+    if ((csize - 1) * step != curve.size() - 1)
+      ThrowRDE("Bad curve segment count (%u)", csize);
+    for (size_t i = 0; i < csize; i++)
+      curve[i * step] = metadata.getU16();
+    for (size_t i = 0; i < curve.size() - 1; i++) {
+      const uint32_t b_scale = (uint32_t)(i % step);
+      const uint32_t a_pos = (uint32_t)(i - b_scale), b_pos = a_pos + step;
+      const uint32_t a_scale = step - b_scale;
+      curve[i] = (uint16_t)((a_scale * curve[a_pos] + b_scale * curve[b_pos]) / step);
+    }
+    metadata.setPosition(562);
+    *split = metadata.getU16();
+  } else if (v0 != 70) {
+    if (csize == 0 || csize > 0x4001)
+      ThrowRDE("Don't know how to compute curve! csize = %u", csize);
+    curve.resize(csize + 1UL);
+    for (uint32_t i = 0; i < csize; i++)
+      curve[i] = metadata.getU16();
+  }
+  curve.resize(curve.size() - 1); // and drop the last value
+  return curve;
+}
+
+// ctor (:473-511)
+NikonDecompressor::NikonDecompressor(RawImage raw, ByteStream metadata, uint32_t bitsPS_)
+    : mRaw(std::move(raw)), bitsPS(bitsPS_) {
+  if (mRaw->getCpp() != 1 || mRaw->getDataType() != RawImageType::UINT16 ||
+      mRaw->getBpp() != sizeof(uint16_t))
+    ThrowRDE("Unexpected component count / data type");
+  if (!(mRaw->dim.x > 0 && mRaw->dim.y > 0) || mRaw->dim.x % 2 != 0 || mRaw->dim.x > 8288 ||
+      mRaw->dim.y > 5520)
+    ThrowRDE("Unexpected image dimensions found: (%d; %d)", mRaw->dim.x, mRaw->dim.y);
+  if (bitsPS != 12 && bitsPS != 14)
+    ThrowRDE("Invalid bpp found: %u", bitsPS);
+  const uint32_t v0 = metadata.getByte();
+  const uint32_t v1 = metadata.getByte();
+  if (v0 == 73 || v1 == 88)
+    metadata.skipBytes(2110);
+  if (v0 == 70)
+    huffSelect = 2;
+  if (bitsPS == 14)
+    huffSelect += 3;
+  pUp[0][0] = metadata.getU16();
+  pUp[1][0] = metadata.getU16();
+  pUp[0][1] = metadata.getU16();
+  pUp[1][1] = metadata.getU16();
+  curve = createCurve(metadata, bitsPS, v0, v1, &split);
+  // If the 'split' happens outside of the image, it does not actually happen.
+  if (split >= (unsigned)mRaw->dim.y)
+    split = 0;
+}
+
+// decompress (:540-560)
+void NikonDecompressor::decompress(Buffer input, bool uncorrectedRawValues) {
+  if (split != 0)
+    ThrowRDE("rawspeed_b200: Nikon streams with a split (lossy after split) are not supported yet");
+  if (input.getSize() < 4) // BitStreamerMSB ctor (BitStreamer.h:56-60)
+    ThrowIOE("Bit stream size is smaller than MaxProcessBytes");
+  // RawImageCurveGuard (common/RawImage.h): the curve is applied while decoding, dithered
+  if (!uncorrectedRawValues)
+    mRaw->setTable(curve, true);
+  const PrefixCodeDecoder<> ht = createPrefixCodeDecoder(huffSelect);
+  rsb200_huff_table t = ht.deviceTable();
+  rsb200_nikon_job job;
+  std::memset(&job, 0, sizeof job);
+  job.in_offset = 0;
+  job.in_size = input.getSize();
+  job.table = 0;
+  job.width = mRaw->dim.x;
+  job.height = mRaw->dim.y;
+  job.out_offset = 0;
+  job.out_pitch = (uint32_t)mRaw->pitch;
+  job.lut = uncorrectedRawValues ? -1 : 0;
+  job.pup[0] = (uint16_t)pUp[0][0];
+  job.pup[1] = (uint16_t)pUp[0][1];
+  job.pup[2] = (uint16_t)pUp[1][0];
+  job.pup[3] = (uint16_t)pUp[1][1];
+  PlanGuard pg;
+  engineCheck(rsb200_nikon_plan_create(engine(), &t, 1, &job, 1,
+                                       uncorrectedRawValues ? nullptr : mRaw->tableData().data(),
+                                       uncorrectedRawValues ? 0 : 1, &pg.p),
+              "rsb200_nikon_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, input.begin(), input.getSize(), img, /*partial=*/true);
+  rsb200_scan_result res;
+  const int rc = rsb200_plan_results(pg.p, &res, 1);
+  // ~RawImageCurveGuard: the table stays (plain) for the consumer only when uncorrected
+  if (uncorrectedRawValues)
+    mRaw->setTable(curve, false);
+  else
+    mRaw->clearTable();
+  if (rc == RSB200_OK)
+    return;
+  if (res.status == RSB200_ERR_RDE)
+    ThrowRDE("bad Huffman code");
+  if (res.status == RSB200_ERR_IOE)
+    ThrowIOE("Buffer overflow read in BitStreamer");
+  engineCheck(rc, "rsb200_plan_results");
+}
+
 // ------------------------------------------------------------------ Sony ARW2
 // SonyArw2Decompressor ctor (decompressors/SonyArw2Decompressor.cpp:41-56)
 SonyArw2Decompressor::SonyArw2Decompressor(RawImage img, ByteStream input_)

@@ -146,6 +146,10 @@ public:
     return v;
   }
   void skipBytes(uint64_t n) { pos += check(n); }
+  void setPosition(size_type newPos) {
+    pos = newPos;
+    check(0);
+  }
   Buffer getBuffer(size_type n) {
     Buffer b = getSubView(pos, n);
     pos += n;
@@ -465,6 +469,32 @@ private:
   static PrefixCodeDecoder<> SetupPrefixCodeDecoder(const ByteStream* metaData);
   RawImage mRaw;
   const PrefixCodeDecoder<> ht;
+};
+
+// ---------------------------------------------------------------- Nikon
+// decompressors/NikonDecompressor.h: same constructor (image, maker-note stream,
+// bits per sample) and decompress(input, uncorrectedRawValues).  The constructor work
+// (version bytes, tree selection, start predictors, createCurve, split;
+// NikonDecompressor.cpp:380-511) is host code; Huffman decode, predictor, clamp and
+// the dithered curve run on the device.  Streams with a non-zero split ("lossy after
+// split", NikonLASDecompressor) are not supported yet and throw.
+class NikonDecompressor final {
+public:
+  NikonDecompressor(RawImage raw, ByteStream metadata, uint32_t bitsPS);
+  void decompress(Buffer input, bool uncorrectedRawValues);
+  const std::vector<uint16_t>& getCurve() const { return curve; }
+  uint32_t getSplit() const { return split; }
+
+private:
+  static std::vector<uint16_t> createCurve(ByteStream& metadata, uint32_t bitsPS, uint32_t v0,
+                                           uint32_t v1, uint32_t* split);
+  static PrefixCodeDecoder<> createPrefixCodeDecoder(uint32_t huffSelect);
+  RawImage mRaw;
+  uint32_t bitsPS;
+  uint32_t huffSelect = 0;
+  uint32_t split = 0;
+  int pUp[2][2];
+  std::vector<uint16_t> curve;
 };
 
 // ---------------------------------------------------------------- Sony ARW2

@@ -12,6 +12,7 @@
 #include "sraw.cuh"
 #include "arw2.cuh"
 #include "pentax.cuh"
+#include "nikon.cuh"
 #include "unpack.cuh"
 
 #include <algorithm>
@@ -147,7 +148,8 @@ struct rsb200_plan {
   // Pentax segments (DevScan::kind == 2): first out-of-bounds pixel per segment
   uint32_t* d_oob = nullptr;
   uint32_t* h_oob = nullptr; // pinned
-  bool has_pentax = false, has_k3 = false;
+  bool has_pentax = false, has_k3 = false, has_nikon = false;
+  uint16_t* d_nikon_luts = nullptr;
   cudaStream_t last_stream = nullptr;
   bool ran = false;
 };
@@ -936,7 +938,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     DevScan& d = b.scans[i];
     const bool is_big = d.kind != 0 || d.in_size > BIG_SEGMENT_BYTES;
     if (is_big)
-      (d.kind == 2 ? p->has_pentax : p->has_k3) = true;
+      (d.kind == 2 ? p->has_pentax : (d.kind == 3 ? p->has_nikon : p->has_k3)) = true;
     if (!is_big) {
       (use_thread && thread_eligible(d) ? thread_ids : small_ids).push_back((uint32_t)i);
       continue;
@@ -1030,7 +1032,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
                    cudaGetErrorString(e));
   }
   p->launches_per_run = (p->nsmall ? 1 : 0) + (p->nthread ? 2 : 0) +
-                        (p->nbig ? 5 + (p->has_k3 ? 2 : 0) + (p->has_pentax ? 2 : 0) : 0);
+                        (p->nbig ? 5 + (p->has_k3 ? 2 : 0) + (p->has_pentax ? 2 : 0) + (p->has_nikon ? 2 : 0) : 0);
   return RSB200_OK;
 }
 
@@ -1092,6 +1094,82 @@ extern "C" int rsb200_pentax_plan_create(rsb200_ctx* ctx, const rsb200_huff_tabl
   int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/false);
   if (rc != RSB200_OK)
     return rc;
+  *out = p;
+  return RSB200_OK;
+}
+
+// ------------------------------------------------------------------
+// Nikon: one long plain-MSB Huffman stream per image (K2R + K3N)
+// ------------------------------------------------------------------
+extern "C" int rsb200_nikon_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables,
+                                        int ntables, const rsb200_nikon_job* jobs, int njobs,
+                                        const uint16_t* luts, int nluts, rsb200_plan** out) {
+  if (!ctx || !tables || ntables <= 0 || !jobs || njobs <= 0 || !out || nluts < 0 ||
+      nluts > 254 || (nluts > 0 && !luts))
+    return set_err(ctx, RSB200_ERR_ARG, "nikon_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  ScanBuild b;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_nikon_job& j = jobs[i];
+    // NikonDecompressor ctor (NikonDecompressor.cpp:478-489); BitStreamerMSB needs 4 bytes
+    const bool ok = j.width > 0 && j.height > 0 && j.width % 2 == 0 && j.width <= 8288 &&
+                    j.height <= 5520 && (int)j.table < ntables && j.in_size >= 4 &&
+                    j.in_size < (1u << 28) && (uint64_t)j.width * 2 <= j.out_pitch &&
+                    (j.out_offset % 4) == 0 && (j.out_pitch % 4) == 0 && j.lut < nluts;
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "nikon job %d: malformed descriptor", i);
+    }
+    DevScan d;
+    memset(&d, 0, sizeof d);
+    d.in_offset = j.in_offset;
+    d.in_size = j.in_size;
+    d.row_samples = (uint32_t)j.width;
+    d.rows = (uint32_t)j.height;
+    d.n_samples = (uint32_t)j.width * (uint32_t)j.height;
+    d.group = 2;
+    d.ncomp = 2;
+    d.kind = 3;
+    d.pump = 1;
+    d.pattern = PAT_PLAIN;
+    d.pad0[0] = (uint8_t)(j.lut < 0 ? 0 : j.lut + 1);
+    const uint8_t tab[4] = {(uint8_t)j.table, (uint8_t)j.table, 0, 0};
+    const uint8_t comp_of_pos[2] = {0, 1};
+    assign_tables(d, tab, 2, comp_of_pos, 2);
+    d.first_idx[0] = 0;
+    d.first_idx[1] = 1;
+    for (int k = 0; k < 4; ++k)
+      d.init_pred[k] = j.pup[k];
+    d.out_offset = j.out_offset;
+    d.out_pitch = j.out_pitch;
+    d.mcu_w = 2;
+    d.mcu_h = 1;
+    d.store_w = (uint32_t)j.width;
+    b.scans.push_back(d);
+    p->in_bytes += j.in_size;
+    p->out_bytes += (uint64_t)j.width * j.height * 2;
+    p->pixels += (uint64_t)j.width * j.height;
+    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + j.in_size);
+    p->need_out = std::max<uint64_t>(
+        p->need_out, j.out_offset + (uint64_t)(j.height - 1) * j.out_pitch + 2ull * j.width);
+  }
+  int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/false);
+  if (rc != RSB200_OK)
+    return rc;
+  {
+    const size_t bytes = (size_t)nluts * 2u * 65536u * sizeof(uint16_t);
+    cudaError_t e = cudaMalloc((void**)&p->d_nikon_luts, bytes + 16);
+    if (e == cudaSuccess && bytes)
+      e = cudaMemcpy(p->d_nikon_luts, luts, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "nikon plan upload failed: %s", cudaGetErrorString(e));
+    }
+  }
   *out = p;
   return RSB200_OK;
 }
@@ -1400,6 +1478,13 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
             p->d_scans, p->d_rows, p->nrows, p->d_diffs, p->d_colvals, outp, p->d_oob);
         nk3 += 2;
       }
+      if (p->has_nikon) {
+        k3n_column_kernel<<<(col_warps * 32 + 127) / 128, 128, 0, st>>>(
+            p->d_scans, p->d_big_ids, p->nbig, p->d_diffs, p->d_colvals);
+        k3n_row_kernel<<<(p->nrows + rows_per_block - 1) / rows_per_block, K3_THREADS, 0, st>>>(
+            in, p->d_scans, p->d_rows, p->nrows, p->d_diffs, p->d_colvals, p->d_nikon_luts, outp);
+        nk3 += 2;
+      }
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 5 + nk3;
     }
@@ -1621,6 +1706,7 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     cudaFree(g.d_jobs);
   for (RawGroup& g : p->raw_groups)
     cudaFree(g.d_jobs);
+  cudaFree(p->d_nikon_luts);
   cudaFree(p->d_arw2_jobs);
   cudaFree(p->d_arw2_tables);
   cudaFree(p->d_arw2_bad);

@@ -151,6 +151,21 @@ def pentax_decompress(img, w, data, meta=None, meta_be=True):
     return img
 
 
+def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False):
+    """NikonDecompressor(img, meta, bits).decompress(data, uncorrected) via the host mirror."""
+    mp, mn = _u8(meta)
+    p, n = _u8(data)
+    e = _Err()
+    L = lib()
+    L.rsb200h_nikon_decompress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                           C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.c_uint32,
+                                           C.c_int, C.POINTER(_Err)]
+    e.check(L.rsb200h_nikon_decompress(C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                       img.shape[1] * 2, mp, C.c_uint32(mn), int(meta_be), bits,
+                                       p, C.c_uint32(n), int(uncorrected), C.byref(e)))
+    return img
+
+
 def sony_arw2(img, w, data, curve=None, dither=False):
     """SonyArw2Decompressor(img, data).decompress() via the host mirror; curve:
     img->setTable(curve, dither) first."""
