@@ -645,6 +645,44 @@ def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
                                     "sample": "PentaxDecompressor::decompress (single threaded by design)"}
     out["8(f)2 PentaxDecompressor 6016x4000"] = ent
     del plan, d_in, d_out
+    # ---- NikonDecompressor (no split), 6032x4032 14-bit, curve + dither ----
+    w, h = 6032, 4032
+    half = 1 << 13
+    pup = [half, half + 2, half - 8, half - 2]
+    meta = synth.nikon_meta("table", 14, (pup[0], pup[2], pup[1], pup[3]), True)
+    su = port.nikon_setup(meta, True, 14, w, h)
+    img = (synth.image_model(w, h, seed=7, bits=14) & 0x3FFF).astype(np.uint16)
+    data = synth.make_nikon(img, su["huff_select"], pup)
+    ncpl, values = port.nikon_tree(su["huff_select"])
+    nj = rs.NikonJob()
+    nj.in_offset, nj.in_size, nj.table, nj.width, nj.height = 0, data.size, 0, w, h
+    nj.out_offset, nj.out_pitch, nj.lut = 0, rs.image_pitch(w), 0
+    for k in range(4):
+        nj.pup[k] = pup[k]
+    plan = rs.nikon_plan(ctx, [rs.huff_table(ncpl, values)], [nj], port.build_table(su["curve"], True))
+    d_in = torch.zeros(data.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[:data.size] = torch.from_numpy(data)
+    d_out = torch.zeros(h * rs.image_pitch(w), dtype=torch.uint8, device="cuda")
+    plan.run((d_in.data_ptr(), data.size), d_out)
+    res = plan.results()
+    want = port.new_image(w, h)
+    port.nikon_decompress(want, w, meta, True, 14, data)
+    exact = bool(np.array_equal(d_out.cpu().numpy().view(np.uint16).reshape(want.shape), want)) and res[0][0] == 0
+    ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), data.size), d_out), 3, 1, dist)
+    per = ms / 3
+    ent = {"MPixels/s": w * h / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
+           "compressed_bytes_per_pixel": data.size / (w * h),
+           "kernels": "k2_range_count/verify/diffs (plain MSB pump) + k3n_column/row (curve + dither)"}
+    if not args.skip_cpu and rank0:
+        import oracle
+        if oracle.HAVE_REF:
+            tmp = port.new_image(w, h)
+            msr = min(oracle.ref.nikon_decompress(tmp, w, meta, True, 14, data) for _ in range(2))
+            ent["cpu_reference"] = {"kind": "reference", "cores": 1,
+                                    "MPixels/s": w * h / (msr * 1e-3) / 1e6,
+                                    "sample": "NikonDecompressor::decompress (single threaded by design)"}
+    out["8(f)2 NikonDecompressor 6032x4032 14-bit (curve + dither)"] = ent
+    del plan, d_in, d_out
     # ---- SonyArw2Decompressor, 9568x6376 (61 MP, A7R IV class), dithered curve, 4 frames ----
     w, h, nf = 9568, 6376, 4
     data = synth.arw2_frame(w, h, seed=21)
