@@ -287,6 +287,19 @@ def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False):
     return img
 
 
+def panasonic(version, img, w, data, bps=14):
+    """PanasonicV{5,6,7}Decompressor(img, data[, bps]).decompress() into img (in place)."""
+    p, n = _u8(data)
+    im = _img(img, w, 1)
+    e = Err()
+    L = lib()
+    L.rso_panasonic.argtypes = [C.c_int, C.POINTER(Image), C.c_char_p, C.c_uint32, C.c_int,
+                                C.POINTER(Err)]
+    rc = L.rso_panasonic(version, C.byref(im), p, C.c_uint32(n), bps, C.byref(e))
+    e.check(rc)
+    return img
+
+
 def sony_arw2(img, w, data, table=None, dither=False):
     """SonyArw2Decompressor(img, data).decompress() into img (in place); `table` = the
     storage build_table() returns (None: the image has no table)."""

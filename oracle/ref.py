@@ -215,6 +215,21 @@ def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False, reps=
     return ms.value
 
 
+def panasonic(version, img, w, data, bps=14, nthreads=1, reps=1):
+    """Reference PanasonicV{5,6,7}Decompressor (ref_panasonic)."""
+    p, n = _u8(data)
+    ms = C.c_double(0)
+    e = Err()
+    L = lib()
+    L.ref_panasonic.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                C.POINTER(Err)]
+    rc = L.ref_panasonic(version, C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
+                         p, C.c_uint32(n), bps, nthreads, reps, C.byref(ms), C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
 def sony_arw2(img, w, data, curve=None, dither=False, nthreads=1, reps=1):
     """Reference SonyArw2Decompressor (ref_sony_arw2); curve: mRaw->setTable(curve, dither)."""
     p, n = _u8(data)

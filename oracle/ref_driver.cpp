@@ -43,6 +43,9 @@
 #include "decompressors/PentaxDecompressor.h"
 #include "decompressors/SonyArw2Decompressor.h"
 #include "decompressors/NikonDecompressor.h"
+#include "decompressors/PanasonicV5Decompressor.h"
+#include "decompressors/PanasonicV6Decompressor.h"
+#include "decompressors/PanasonicV7Decompressor.h"
 #include "io/Buffer.h"
 #include "io/ByteStream.h"
 #include "io/Endianness.h"
@@ -298,6 +301,38 @@ int ref_unpack_form(const uint8_t* in, uint32_t in_size, void* img_data, int is_
     for (int r = 0; r < h; ++r)
       std::memcpy(static_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, rowPtr(r),
                   static_cast<size_t>(w) * bpp);
+  });
+}
+
+// PanasonicV{5,6,7}Decompressor(mRaw, input[, bps]).decompress()
+int ref_panasonic(int version, uint16_t* img_data, int w, int h, int pitch, const uint8_t* data,
+                  uint32_t size, int bps, int nthreads, int reps, double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(w, h, 1, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const ByteStream in(DataBuffer(Buffer(data, size), Endianness::little));
+      const auto t0 = std::chrono::steady_clock::now();
+      if (version == 5) {
+        PanasonicV5Decompressor d(img, in, static_cast<uint32_t>(bps));
+        d.decompress();
+      } else if (version == 6) {
+        PanasonicV6Decompressor d(img, in, static_cast<uint32_t>(bps));
+        d.decompress();
+      } else if (version == 7) {
+        PanasonicV7Decompressor d(img, in);
+        d.decompress();
+      } else {
+        ThrowRDE("unknown Panasonic version");
+      }
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
   });
 }
 

@@ -2755,3 +2755,158 @@ int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int
   free((void*)tab);
   return RSO_OK;
 }
+
+/* ------------------------------------------------------------------
+ * PanasonicV5 / V6 / V7 decompressors
+ * ------------------------------------------------------------------ */
+/* n bits at bit offset `off` of a 16-byte little-endian block (BitStreamerLSB order) */
+static uint32_t pana_bits(const uint8_t* blk, uint32_t off, uint32_t n) {
+  uint32_t v = 0, k;
+  for (k = 0; k < n; k++, off++)
+    v |= (uint32_t)((blk[off >> 3] >> (off & 7)) & 1u) << k;
+  return v;
+}
+
+int rso_panasonic(int version, rso_image* img, const uint8_t* data, uint32_t size, int bps,
+                  rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  const uint64_t area = (uint64_t)(img->w > 0 ? img->w : 0) * (uint64_t)(img->h > 0 ? img->h : 0);
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb))
+    return c.e->code;
+  if (img->cpp != 1 || img->is_f32)
+    THROW_RDE(&c, "Unexpected component count / data type");
+  if (version == 5) {
+    /* ctor (PanasonicV5Decompressor.cpp:58-116) */
+    const uint32_t BlockSize = 0x4000, split = 0x1FF8;
+    uint32_t ppp;
+    uint64_t numPackets, numBlocks, b;
+    if (bps != 12 && bps != 14)
+      THROW_RDE(&c, "Unsupported bps: %u", (unsigned)bps);
+    ppp = 128u / (uint32_t)bps; /* pixels per 16-byte packet (padding bits left over) */
+    if (!(img->w > 0 && img->h > 0) || (uint32_t)img->w % ppp != 0)
+      THROW_RDE(&c, "Unexpected image dimensions found: (%i; %i)", img->w, img->h);
+    numPackets = area / ppp;
+    numBlocks = (numPackets + 1023) / 1024;
+    if ((uint64_t)size / BlockSize < numBlocks)
+      THROW_RDE(&c, "Insufficient count of input blocks for a given image");
+    /* processBlock (:206-232) with ProxyStream's section swap (:147-186) */
+    for (b = 0; b < numBlocks; b++) {
+      const uint8_t* blk = data + b * BlockSize;
+      uint32_t pk;
+      for (pk = 0; pk < 1024; pk++) {
+        uint8_t pkt[16];
+        uint64_t idx = (b * 1024 + pk) * ppp;
+        uint32_t i, j;
+        if (idx >= area)
+          break;
+        for (j = 0; j < 16; j++)
+          pkt[j] = blk[(pk * 16 + j + split) & (BlockSize - 1)];
+        for (i = 0; i < ppp; i++, idx++) {
+          uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)(idx / (uint64_t)img->w) * (size_t)img->pitch);
+          o[idx % (uint64_t)img->w] = (uint16_t)pana_bits(pkt, i * (uint32_t)bps, (uint32_t)bps);
+        }
+      }
+    }
+    return RSO_OK;
+  }
+  if (version == 7) {
+    /* PanasonicV7Decompressor.cpp:40-106: 9 pixels of 14 bits per 16-byte block */
+    uint64_t numBlocks, b;
+    if (!(img->w > 0 && img->h > 0) || img->w % 9 != 0)
+      THROW_RDE(&c, "Unexpected image dimensions found: (%i; %i)", img->w, img->h);
+    numBlocks = area / 9;
+    if ((uint64_t)size / 16 < numBlocks)
+      THROW_RDE(&c, "Insufficient count of input blocks for a given image");
+    for (b = 0; b < numBlocks; b++) {
+      const uint64_t idx = b * 9;
+      uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)(idx / (uint64_t)img->w) * (size_t)img->pitch) +
+                    idx % (uint64_t)img->w;
+      uint32_t i;
+      for (i = 0; i < 9; i++)
+        o[i] = (uint16_t)pana_bits(data + b * 16, i * 14, 14);
+    }
+    return RSO_OK;
+  }
+  if (version == 6) {
+    /* PanasonicV6Decompressor.cpp:146-239 */
+    const int is14 = bps == 14;
+    const uint32_t ppb = is14 ? 11u : 14u, PixelbaseZero = is14 ? 0x200u : 0x80u,
+                   PixelbaseCompare = is14 ? 0x2000u : 0x800u, SpixCompare = is14 ? 0xffffu : 0x3fffu,
+                   PixelMask = is14 ? 0x3fffu : 0xfffu;
+    uint64_t numBlocks, b;
+    if (bps != 12 && bps != 14)
+      THROW_RDE(&c, "Unsupported bps: %u", (unsigned)bps);
+    if (!(img->w > 0 && img->h > 0) || (uint32_t)img->w % ppb != 0)
+      THROW_RDE(&c, "Unexpected image dimensions found: (%i; %i)", img->w, img->h);
+    numBlocks = area / ppb;
+    if ((uint64_t)size / 16 < numBlocks)
+      THROW_RDE(&c, "Insufficient count of input blocks for a given image");
+    for (b = 0; b < numBlocks; b++) {
+      const uint8_t* blk = data + b * 16;
+      const uint64_t idx = b * ppb;
+      uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)(idx / (uint64_t)img->w) * (size_t)img->pitch) +
+                    idx % (uint64_t)img->w;
+      uint16_t buf[18];
+      uint32_t off = 0, k, cur = 0, pix;
+      uint32_t oddeven[2] = {0, 0}, nonzero[2] = {0, 0}, pmul = 0, pixel_base = 0;
+      /* pana_cs6_page_decoder<B>::fillBuffer (:88-142): the buffer is filled from its END */
+      if (is14) {
+        off = 4;
+        for (k = 14; k-- > 2;) {
+          const uint32_t n = (k % 4 == 2) ? 2u : 10u;
+          buf[k] = (uint16_t)pana_bits(blk, off, n);
+          off += n;
+        }
+        buf[1] = (uint16_t)pana_bits(blk, off, 14);
+        buf[0] = (uint16_t)pana_bits(blk, off + 14, 14);
+      } else {
+        for (k = 18; k-- > 2;) {
+          const uint32_t n = (k % 4 == 2) ? 2u : 8u;
+          buf[k] = (uint16_t)pana_bits(blk, off, n);
+          off += n;
+        }
+        buf[1] = (uint16_t)pana_bits(blk, off, 12);
+        buf[0] = (uint16_t)pana_bits(blk, off + 12, 12);
+      }
+      /* decompressBlock (:178-221) */
+      for (pix = 0; pix < ppb; pix++) {
+        uint16_t epixel;
+        uint32_t spix;
+        if (pix % 3 == 2) {
+          uint16_t base = buf[cur++];
+          if (base == 3)
+            base = 4;
+          pixel_base = PixelbaseZero << base;
+          pmul = 1u << base;
+        }
+        epixel = buf[cur++];
+        if (oddeven[pix % 2]) {
+          epixel = (uint16_t)(epixel * pmul);
+          if (pixel_base < PixelbaseCompare && nonzero[pix % 2] > pixel_base)
+            epixel = (uint16_t)(epixel + (nonzero[pix % 2] - pixel_base));
+          nonzero[pix % 2] = epixel;
+        } else {
+          oddeven[pix % 2] = epixel;
+          if (epixel)
+            nonzero[pix % 2] = epixel;
+          else
+            epixel = (uint16_t)nonzero[pix % 2];
+        }
+        spix = (uint32_t)((int)epixel - 0xf);
+        if (spix <= SpixCompare)
+          o[pix] = (uint16_t)(spix & SpixCompare);
+        else {
+          epixel = (uint16_t)((int)(epixel + 0x7ffffff1) >> 0x1f);
+          o[pix] = (uint16_t)(epixel & PixelMask);
+        }
+      }
+    }
+    return RSO_OK;
+  }
+  THROW_RDE(&c, "unknown Panasonic version %d", version);
+  return RSO_OK;
+}

@@ -174,6 +174,17 @@ int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int
 /* nikon_tree[sel] as (ncpl[16], values[<=16]); returns the number of codes */
 int rso_nikon_tree(int sel, uint8_t* ncpl, uint8_t* values);
 
+/* ---- PanasonicV5 / V6 / V7 Decompressor ----
+ * version 5 (decompressors/PanasonicV5Decompressor.cpp:58-266): 0x4000-byte blocks whose
+ *   two sections (split at 0x1FF8) are swapped, 16-byte packets of 10 x 12 or 9 x 14 bits
+ *   (LSB first), pixels numbered linearly over the image;
+ * version 6 (PanasonicV6Decompressor.cpp:70-263): 16-byte blocks of 14 (12 bit) or 11
+ *   (14 bit) pixels with per-triplet scale and an odd/even running reference;
+ * version 7 (PanasonicV7Decompressor.cpp:40-106): 16-byte blocks of 9 x 14 bits.
+ * bps: 12 or 14 (ignored for version 7). */
+int rso_panasonic(int version, rso_image* img, const uint8_t* data, uint32_t size, int bps,
+                  rso_err* e);
+
 /* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
  * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
  * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity
