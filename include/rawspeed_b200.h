@@ -179,6 +179,28 @@ int rsb200_arw2_plan_create(rsb200_ctx* ctx, const rsb200_arw2_job* jobs, int nj
                             rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* K7: Panasonic RW2 block codecs V5 / V6 / V7.          */
+/*   PanasonicV5Decompressor::processBlock (+ ProxyStream section swap) */
+/*       decompressors/PanasonicV5Decompressor.cpp:147-232              */
+/*   PanasonicV6Decompressor::decompressBlock  PanasonicV6Decompressor.cpp:88-221 */
+/*   PanasonicV7Decompressor::decompressBlock  PanasonicV7Decompressor.cpp:66-73  */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t in_offset;  /* first byte of the image's data                          */
+  uint64_t in_size;    /* bytes available (checked against the block count)       */
+  uint64_t out_offset; /* byte offset of image row 0; multiple of 2               */
+  uint32_t out_pitch;  /* bytes between output rows; multiple of 2, >= 2*width    */
+  uint32_t width;      /* multiple of the pixels per 16-byte unit (V5: 10 / 9,    */
+  uint32_t height;     /* V6: 14 / 11, V7: 9)                                     */
+  uint8_t version;     /* 5, 6 or 7                                               */
+  uint8_t bps;         /* 12 or 14 (V7: 14)                                       */
+  uint8_t reserved[2];
+} rsb200_pana_job;
+
+int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* jobs, int njobs,
+                            rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
 /* K5: Canon sRaw interpolation.                         */
 /*   Cr2sRawInterpolator::interpolate(version)                          */
 /*   interpolators/Cr2sRawInterpolator.cpp:96-187 (4:2:2), :189-453     */

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Arw2Job, NikonJob, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, NikonJob, PanaJob, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -182,6 +182,14 @@ def nikon_plan(ctx, tables, jobs, luts=None):
         lp, nl = luts.ctypes.data_as(C.POINTER(C.c_uint16)), luts.shape[0]
     ctx.check(ctx._lib.rsb200_nikon_plan_create(ctx.h, ta, len(tables), ja, len(jobs), lp, nl,
                                                 C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def pana_plan(ctx, jobs):
+    """Panasonic RW2 images (PanasonicV5/V6/V7Decompressor::decompress), one job per image."""
+    arr = (PanaJob * len(jobs))(*jobs)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_pana_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

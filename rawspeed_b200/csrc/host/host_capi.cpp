@@ -264,6 +264,27 @@ int rsb200h_nikon_decompress(uint16_t* img_data, int w, int h, int pitch, const 
   });
 }
 
+int rsb200h_panasonic(int version, uint16_t* img_data, int w, int h, int pitch,
+                      const uint8_t* data, uint32_t size, int bps, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, 1, pitch, true, 1, 1);
+    const ByteStream in(data, size);
+    if (version == 5) {
+      PanasonicV5Decompressor d(img, in, (uint32_t)bps);
+      d.decompress();
+    } else if (version == 6) {
+      PanasonicV6Decompressor d(img, in, (uint32_t)bps);
+      d.decompress();
+    } else if (version == 7) {
+      PanasonicV7Decompressor d(img, in);
+      d.decompress();
+    } else {
+      ThrowRDE("unknown Panasonic version");
+    }
+    copyOut(img, img_data);
+  });
+}
+
 int rsb200h_sony_arw2(uint16_t* img_data, int w, int h, int pitch, const uint8_t* data,
                       uint32_t size, const uint16_t* curve, int ncurve, int dither,
                       rsb200h_err* e) {

@@ -672,6 +672,68 @@ void NikonDecompressor::decompress(Buffer input, bool uncorrectedRawValues) {
   engineCheck(rc, "rsb200_plan_results");
 }
 
+// ------------------------------------------------------------------ Panasonic
+namespace {
+void panaCheckImage(const RawImage& mRaw) {
+  if (mRaw->getCpp() != 1 || mRaw->getDataType() != RawImageType::UINT16 ||
+      mRaw->getBpp() != sizeof(uint16_t))
+    ThrowRDE("Unexpected component count / data type");
+}
+// the constructors' block accounting (V5 :87-112, V6 :163-175, V7 :50-63)
+void panaCheckInput(const RawImage& mRaw, const ByteStream& input, int pixelsPerUnit,
+                    uint64_t unitBytes, uint64_t unitsPerBlock) {
+  if (!(mRaw->dim.x > 0 && mRaw->dim.y > 0) || mRaw->dim.x % pixelsPerUnit != 0)
+    ThrowRDE("Unexpected image dimensions found: (%i; %i)", mRaw->dim.x, mRaw->dim.y);
+  const uint64_t units = (uint64_t)mRaw->dim.x * (uint64_t)mRaw->dim.y / (uint64_t)pixelsPerUnit;
+  const uint64_t numBlocks = (units + unitsPerBlock - 1) / unitsPerBlock;
+  if ((uint64_t)input.getRemainSize() / (unitBytes * unitsPerBlock) < numBlocks)
+    ThrowRDE("Insufficient count of input blocks for a given image");
+}
+void panaRun(const RawImage& mRaw, const ByteStream& input, int version, int bps) {
+  rsb200_pana_job job;
+  std::memset(&job, 0, sizeof job);
+  job.in_offset = 0;
+  job.in_size = input.getRemainSize();
+  job.out_offset = 0;
+  job.out_pitch = (uint32_t)mRaw->pitch;
+  job.width = (uint32_t)mRaw->dim.x;
+  job.height = (uint32_t)mRaw->dim.y;
+  job.version = (uint8_t)version;
+  job.bps = (uint8_t)bps;
+  PlanGuard pg;
+  engineCheck(rsb200_pana_plan_create(engine(), &job, 1, &pg.p), "rsb200_pana_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, input.begin() + input.getPosition(), input.getRemainSize(), img,
+             /*partial=*/false);
+  engineCheck(rsb200_plan_results(pg.p, nullptr, 0), "rsb200_plan_results");
+}
+} // namespace
+
+PanasonicV5Decompressor::PanasonicV5Decompressor(RawImage img, ByteStream input_, uint32_t bps_)
+    : mRaw(std::move(img)), input(input_), bps(bps_) {
+  panaCheckImage(mRaw);
+  if (bps != 12 && bps != 14)
+    ThrowRDE("Unsupported bps: %u", bps);
+  panaCheckInput(mRaw, input, (int)(128 / bps), 16, 1024);
+}
+void PanasonicV5Decompressor::decompress() const { panaRun(mRaw, input, 5, (int)bps); }
+
+PanasonicV6Decompressor::PanasonicV6Decompressor(RawImage img, ByteStream input_, uint32_t bps_)
+    : mRaw(std::move(img)), input(input_), bps(bps_) {
+  panaCheckImage(mRaw);
+  if (bps != 12 && bps != 14)
+    ThrowRDE("Unsupported bps: %u", bps);
+  panaCheckInput(mRaw, input, bps == 14 ? 11 : 14, 16, 1);
+}
+void PanasonicV6Decompressor::decompress() const { panaRun(mRaw, input, 6, (int)bps); }
+
+PanasonicV7Decompressor::PanasonicV7Decompressor(RawImage img, ByteStream input_)
+    : mRaw(std::move(img)), input(input_) {
+  panaCheckImage(mRaw);
+  panaCheckInput(mRaw, input, 9, 16, 1);
+}
+void PanasonicV7Decompressor::decompress() const { panaRun(mRaw, input, 7, 14); }
+
 // ------------------------------------------------------------------ Sony ARW2
 // SonyArw2Decompressor ctor (decompressors/SonyArw2Decompressor.cpp:41-56)
 SonyArw2Decompressor::SonyArw2Decompressor(RawImage img, ByteStream input_)

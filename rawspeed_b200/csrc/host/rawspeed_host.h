@@ -497,6 +497,39 @@ private:
   std::vector<uint16_t> curve;
 };
 
+// ---------------------------------------------------------------- Panasonic
+// decompressors/PanasonicV{5,6,7}Decompressor.h: same constructors (image, byte
+// stream[, bps]) with the reference's validation, decompress() runs on the device.
+class PanasonicV5Decompressor final {
+public:
+  PanasonicV5Decompressor(RawImage img, ByteStream input_, uint32_t bps_);
+  void decompress() const;
+
+private:
+  RawImage mRaw;
+  ByteStream input;
+  uint32_t bps;
+};
+class PanasonicV6Decompressor final {
+public:
+  PanasonicV6Decompressor(RawImage img, ByteStream input_, uint32_t bps_);
+  void decompress() const;
+
+private:
+  RawImage mRaw;
+  ByteStream input;
+  uint32_t bps;
+};
+class PanasonicV7Decompressor final {
+public:
+  PanasonicV7Decompressor(RawImage img, ByteStream input_);
+  void decompress() const;
+
+private:
+  RawImage mRaw;
+  ByteStream input;
+};
+
 // ---------------------------------------------------------------- Sony ARW2
 // decompressors/SonyArw2Decompressor.h: same constructor (image + the byte stream,
 // one byte per pixel) and decompress().  The image's table (RawImageData::setTable,

@@ -1,0 +1,172 @@
+// pana.cuh -- K7: Panasonic RW2 block codecs V5 / V6 / V7, sm_100a.
+//
+// Replaces the bodies of
+//   PanasonicV5Decompressor::processBlock / processPixelPacket
+//       decompressors/PanasonicV5Decompressor.cpp:188-232 (+ ProxyStream :147-186)
+//   PanasonicV6Decompressor::decompressBlock  PanasonicV6Decompressor.cpp:88-221
+//   PanasonicV7Decompressor::decompressBlock  PanasonicV7Decompressor.cpp:66-73
+// and their OpenMP loops over blocks / rows.  All three cut the image into
+// independent 16-byte units read as LSB-first bit streams:
+//   V5  packets of 10 x 12 or 9 x 14 bits inside 0x4000-byte blocks whose two
+//       sections (split at 0x1FF8) are swapped; pixels numbered linearly over
+//       the image (width is a multiple of the packet size);
+//   V6  blocks of 14 (12 bit) / 11 (14 bit) pixels: 2 full-width pixels, then
+//       triplets sharing a 2-bit scale, with an odd/even running reference;
+//   V7  blocks of 9 x 14 bits.
+// One thread = one unit: 16 input bytes -> 9..14 uint16 (every field offset is a
+// compile-time constant).  HBM-bound streaming maps.
+#pragma once
+
+#include "common.cuh"
+
+namespace rsb200 {
+
+constexpr int PANA_NT = 256;
+
+struct PanaJobDev {
+  uint64_t in_offset;
+  uint64_t out_offset;
+  uint32_t out_pitch;
+  uint32_t width;
+  uint32_t height;
+  uint32_t unit_begin; // first unit of this job in the group
+  uint32_t units;      // units that carry pixels of the image
+};
+
+// n bits at compile-time bit offset OFF of the 128-bit little-endian number w[0..3]
+template <int OFF, int N>
+__device__ __forceinline__ uint32_t pana_field(const uint32_t (&w)[4]) {
+  constexpr int k = OFF >> 5, s = OFF & 31;
+  uint32_t v = w[k] >> s;
+  if (s + N > 32 && k < 3)
+    v |= w[k + 1] << (32 - s);
+  return v & ((1u << N) - 1u);
+}
+
+template <int BPS, int I, int NPIX>
+__device__ __forceinline__ void pana_unpack(const uint32_t (&w)[4], uint32_t (&px)[14]) {
+  if constexpr (I < NPIX) {
+    px[I] = pana_field<I * BPS, BPS>(w);
+    pana_unpack<BPS, I + 1, NPIX>(w, px);
+  }
+}
+
+// V6 page buffer (PanasonicV6Decompressor.cpp:88-142): entry K of the buffer; the
+// buffer is filled from its end, entry 0/1 are the two full-width pixels.
+template <int BPS, int K> __device__ __forceinline__ uint32_t pana6_entry(const uint32_t (&w)[4]) {
+  constexpr int NBUF = BPS == 14 ? 14 : 18;
+  constexpr int SMALL = BPS == 14 ? 10 : 8;
+  constexpr int LEAD = BPS == 14 ? 4 : 0;
+  if constexpr (K == 0) {
+    return pana_field<128 - BPS, BPS>(w);
+  } else if constexpr (K == 1) {
+    return pana_field<128 - 2 * BPS, BPS>(w);
+  } else {
+    // entries NBUF-1 down to 2 in stream order; widths: SMALL, except 2 bits where K % 4 == 2
+    constexpr int pos = NBUF - 1 - K; // position in stream order
+    constexpr int groups = pos / 4, rem = pos % 4; // each group of 4 = 3 SMALL + one 2-bit
+    constexpr int off = LEAD + groups * (3 * SMALL + 2) + rem * SMALL;
+    constexpr int n = (K % 4 == 2) ? 2 : SMALL;
+    return pana_field<off, n>(w);
+  }
+}
+
+template <int BPS, int PIX, int CUR>
+__device__ __forceinline__ void pana6_pixels(const uint32_t (&w)[4], uint32_t (&px)[14],
+                                             uint32_t (&oddeven)[2], uint32_t (&nonzero)[2],
+                                             uint32_t& pmul, uint32_t& pixel_base) {
+  constexpr int NPIX = BPS == 14 ? 11 : 14;
+  if constexpr (PIX < NPIX) {
+    constexpr uint32_t PixelbaseZero = BPS == 14 ? 0x200u : 0x80u;
+    constexpr uint32_t PixelbaseCompare = BPS == 14 ? 0x2000u : 0x800u;
+    constexpr uint32_t SpixCompare = BPS == 14 ? 0xffffu : 0x3fffu;
+    constexpr uint32_t PixelMask = BPS == 14 ? 0x3fffu : 0xfffu;
+    constexpr bool has_base = (PIX % 3 == 2);
+    if constexpr (has_base) {
+      uint32_t base = pana6_entry<BPS, CUR>(w);
+      if (base == 3)
+        base = 4;
+      pixel_base = PixelbaseZero << base;
+      pmul = 1u << base;
+    }
+    constexpr int E = CUR + (has_base ? 1 : 0);
+    uint32_t epixel = pana6_entry<BPS, E>(w);
+    constexpr int par = PIX % 2;
+    if (oddeven[par]) {
+      epixel = (epixel * pmul) & 0xFFFFu;
+      if (pixel_base < PixelbaseCompare && nonzero[par] > pixel_base)
+        epixel = (epixel + (nonzero[par] - pixel_base)) & 0xFFFFu;
+      nonzero[par] = epixel;
+    } else {
+      oddeven[par] = epixel;
+      if (epixel)
+        nonzero[par] = epixel;
+      else
+        epixel = nonzero[par] & 0xFFFFu;
+    }
+    const uint32_t spix = (uint32_t)((int)epixel - 0xf);
+    if (spix <= SpixCompare)
+      px[PIX] = spix & SpixCompare;
+    else
+      px[PIX] = ((uint32_t)((int)(epixel + 0x7ffffff1u) >> 0x1f) & 0xFFFFu) & PixelMask;
+    pana6_pixels<BPS, PIX + 1, E + 1>(w, px, oddeven, nonzero, pmul, pixel_base);
+  }
+}
+
+// VER 5/6/7, BPS 12/14
+template <int VER, int BPS>
+__global__ void __launch_bounds__(PANA_NT)
+    pana_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                const PanaJobDev* __restrict__ jobs, int njobs, uint32_t total_units) {
+  constexpr int NPIX = VER == 6 ? (BPS == 14 ? 11 : 14) : 128 / BPS;
+  const uint32_t u = blockIdx.x * PANA_NT + threadIdx.x;
+  if (u >= total_units)
+    return;
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].unit_begin <= u)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const PanaJobDev jb = jobs[lo];
+  const uint32_t ul = u - jb.unit_begin;
+  const uint8_t* base = in + jb.in_offset;
+  uint32_t w[4];
+  auto load8 = [&](const uint8_t* p, uint32_t& a, uint32_t& b) {
+    // 8 bytes at any alignment: three aligned words, funnel-shifted
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(p - mis);
+    const uint32_t x0 = __ldg(pw), x1 = __ldg(pw + 1), x2 = mis ? __ldg(pw + 2) : 0u;
+    a = __funnelshift_r(x0, x1, 8u * mis);
+    b = __funnelshift_r(x1, x2, 8u * mis);
+  };
+  if (VER == 5) {
+    // packet ul of the image = packet ul % 1024 of block ul / 1024, read through the
+    // section swap: rearranged byte j of a block is original byte (j + 0x1FF8) % 0x4000
+    const uint32_t blk = ul >> 10, o = (ul & 1023u) * 16u;
+    const uint8_t* bp = base + (uint64_t)blk * 0x4000u;
+    load8(bp + ((o + 0x1FF8u) & 0x3FFFu), w[0], w[1]);
+    load8(bp + ((o + 8u + 0x1FF8u) & 0x3FFFu), w[2], w[3]);
+  } else {
+    const uint8_t* p = base + (uint64_t)ul * 16u;
+    load8(p, w[0], w[1]);
+    load8(p + 8, w[2], w[3]);
+  }
+  uint32_t px[14];
+  if (VER == 6) {
+    uint32_t oddeven[2] = {0, 0}, nonzero[2] = {0, 0}, pmul = 0, pixel_base = 0;
+    pana6_pixels<BPS, 0, 0>(w, px, oddeven, nonzero, pmul, pixel_base);
+  } else {
+    pana_unpack<BPS, 0, NPIX>(w, px);
+  }
+  const uint64_t idx = (uint64_t)ul * NPIX; // linear pixel index; a unit never straddles rows
+  const uint32_t row = (uint32_t)(idx / jb.width), col = (uint32_t)(idx - (uint64_t)row * jb.width);
+  uint16_t* o16 = reinterpret_cast<uint16_t*>(out + jb.out_offset + (uint64_t)row * jb.out_pitch) + col;
+#pragma unroll
+  for (int i = 0; i < NPIX; ++i)
+    o16[i] = (uint16_t)px[i];
+}
+
+} // namespace rsb200

@@ -11,6 +11,7 @@
 #include "rawforms.cuh"
 #include "sraw.cuh"
 #include "arw2.cuh"
+#include "pana.cuh"
 #include "pentax.cuh"
 #include "nikon.cuh"
 #include "unpack.cuh"
@@ -75,6 +76,13 @@ struct RawGroup {
   uint32_t total_items = 0;
 };
 
+struct PanaGroup {
+  int version = 0, bps = 0;
+  PanaJobDev* d_jobs = nullptr;
+  int njobs = 0;
+  uint32_t total_units = 0;
+};
+
 struct SrawGroup {
   int version = 0;
   bool is420 = false;
@@ -94,7 +102,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -107,6 +115,7 @@ struct rsb200_plan {
   std::vector<RawGroup> raw_groups;
   uint16_t* d_raw_tables = nullptr;
   std::vector<SrawGroup> sraw_groups;
+  std::vector<PanaGroup> pana_groups;
   // Sony ARW2
   Arw2JobDev* d_arw2_jobs = nullptr;
   uint16_t* d_arw2_tables = nullptr;
@@ -585,6 +594,105 @@ extern "C" int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* j
   p->launches_per_run = (int)p->sraw_groups.size();
   *out = p;
   return RSB200_OK;
+}
+
+// ------------------------------------------------------------------
+// Panasonic V5 / V6 / V7 (K7)
+// ------------------------------------------------------------------
+extern "C" int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* jobs, int njobs,
+                                       rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "pana_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  p->kind = 5;
+  p->nunits = njobs;
+  std::map<std::pair<int, int>, std::vector<PanaJobDev>> buckets;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_pana_job& j = jobs[i];
+    const int bps = j.version == 7 ? 14 : j.bps;
+    const bool vok = (j.version == 5 || j.version == 6 || j.version == 7) && (bps == 12 || bps == 14);
+    const uint32_t npix = !vok ? 1u : (j.version == 6 ? (bps == 14 ? 11u : 14u) : 128u / (uint32_t)bps);
+    const uint64_t area = (uint64_t)j.width * j.height;
+    const uint64_t units = area / npix;
+    // the constructors' checks (PanasonicV5Decompressor.cpp:58-116, V6 :146-176, V7 :40-64)
+    uint64_t need = units * 16;
+    if (j.version == 5)
+      need = ((units + 1023) / 1024) * 0x4000ull;
+    const bool ok = vok && j.width > 0 && j.height > 0 && j.width % npix == 0 &&
+                    j.in_size >= need && (j.out_offset % 2) == 0 && (j.out_pitch % 2) == 0 &&
+                    (uint64_t)j.width * 2 <= j.out_pitch && units < 0xFFFF0000ull;
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "pana job %d: malformed descriptor", i);
+    }
+    PanaJobDev d;
+    memset(&d, 0, sizeof d);
+    d.in_offset = j.in_offset;
+    d.out_offset = j.out_offset;
+    d.out_pitch = j.out_pitch;
+    d.width = j.width;
+    d.height = j.height;
+    d.units = (uint32_t)units;
+    buckets[{(int)j.version, bps}].push_back(d);
+    p->in_bytes += units * 16;
+    p->out_bytes += area * 2;
+    p->pixels += area;
+    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + need);
+    p->need_out = std::max<uint64_t>(p->need_out, j.out_offset +
+                                                      (uint64_t)(j.height - 1) * j.out_pitch +
+                                                      2ull * j.width);
+  }
+  for (auto& kv : buckets) {
+    PanaGroup g;
+    g.version = kv.first.first;
+    g.bps = kv.first.second;
+    uint64_t n = 0;
+    for (auto& d : kv.second) {
+      d.unit_begin = (uint32_t)n;
+      n += d.units;
+    }
+    if (n >= 0xFFFF0000ull) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_ARG, "pana plan: too many blocks");
+    }
+    g.total_units = (uint32_t)n;
+    g.njobs = (int)kv.second.size();
+    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(PanaJobDev) * kv.second.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(PanaJobDev) * kv.second.size(),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "pana plan upload failed: %s", cudaGetErrorString(e));
+    }
+    p->pana_groups.push_back(g);
+  }
+  p->launches_per_run = (int)p->pana_groups.size();
+  *out = p;
+  return RSB200_OK;
+}
+
+static cudaError_t run_pana_group(const PanaGroup& g, const uint8_t* in, uint8_t* outp,
+                                  cudaStream_t st) {
+  const uint32_t nb = (g.total_units + PANA_NT - 1) / PANA_NT;
+#define RSB_PANA(V, B)                                                                     \
+  pana_kernel<V, B><<<nb, PANA_NT, 0, st>>>(in, outp, g.d_jobs, g.njobs, g.total_units)
+  if (g.version == 5 && g.bps == 12)
+    RSB_PANA(5, 12);
+  else if (g.version == 5)
+    RSB_PANA(5, 14);
+  else if (g.version == 6 && g.bps == 12)
+    RSB_PANA(6, 12);
+  else if (g.version == 6)
+    RSB_PANA(6, 14);
+  else
+    RSB_PANA(7, 14);
+#undef RSB_PANA
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------
@@ -1413,6 +1521,11 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->kind == 5) {
+    for (const PanaGroup& g : p->pana_groups) {
+      CUDA_TRY(ctx, run_pana_group(g, in, outp, st));
+      ctx->launches++;
+    }
   } else if (p->kind == 4) {
     CUDA_TRY(ctx, run_arw2(p, in, outp, st));
     ctx->launches++;
@@ -1705,6 +1818,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   for (UnpackFastGroup& g : p->fast_groups)
     cudaFree(g.d_jobs);
   for (RawGroup& g : p->raw_groups)
+    cudaFree(g.d_jobs);
+  for (PanaGroup& g : p->pana_groups)
     cudaFree(g.d_jobs);
   cudaFree(p->d_nikon_luts);
   cudaFree(p->d_arw2_jobs);

@@ -166,6 +166,18 @@ def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False):
     return img
 
 
+def panasonic(version, img, w, data, bps=14):
+    """PanasonicV{5,6,7}Decompressor(img, data[, bps]).decompress() via the host mirror."""
+    p, n = _u8(data)
+    e = _Err()
+    L = lib()
+    L.rsb200h_panasonic.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                    C.c_uint32, C.c_int, C.POINTER(_Err)]
+    e.check(L.rsb200h_panasonic(version, C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                img.shape[1] * 2, p, C.c_uint32(n), bps, C.byref(e)))
+    return img
+
+
 def sony_arw2(img, w, data, curve=None, dither=False):
     """SonyArw2Decompressor(img, data).decompress() via the host mirror; curve:
     img->setTable(curve, dither) first."""
