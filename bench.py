@@ -683,6 +683,51 @@ def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
                                     "sample": "NikonDecompressor::decompress (single threaded by design)"}
     out["8(f)2 NikonDecompressor 6032x4032 14-bit (curve + dither)"] = ent
     del plan, d_in, d_out
+    # ---- PanasonicV5 (14 bit) / V6 (14 bit) / V7, 5184x3888-class frames, 4 frames per launch ----
+    for ver, bps, w, h in ((5, 14, 5184, 3888), (6, 14, 5181, 3888), (7, 14, 5184, 3888)):
+        npix = (11 if ver == 6 else 128 // bps)
+        nunits = w * h // npix
+        nbytes = ((nunits + 1023) // 1024) * 0x4000 if ver == 5 else nunits * 16
+        data = synth.lcg_bytes(nbytes, 40 + ver)
+        opitch = rs.image_pitch(w)
+        nf = 4
+        fb = (nbytes + 255) // 256 * 256
+        ob = (h * opitch + 255) // 256 * 256
+        jobs = []
+        for f in range(nf):
+            pj = rs.PanaJob()
+            pj.in_offset, pj.in_size, pj.out_offset, pj.out_pitch = f * fb, nbytes, f * ob, opitch
+            pj.width, pj.height, pj.version, pj.bps = w, h, ver, bps
+            jobs.append(pj)
+        plan = rs.pana_plan(ctx, jobs)
+        d_in = torch.zeros(nf * fb + 64, dtype=torch.uint8, device="cuda")
+        for f in range(nf):
+            d_in[f * fb:f * fb + nbytes] = torch.from_numpy(data)
+        d_out = torch.zeros(nf * ob, dtype=torch.uint8, device="cuda")
+        plan.run((d_in.data_ptr(), nf * fb), d_out)
+        torch.cuda.synchronize()
+        want = port.new_image(w, h)
+        port.panasonic(ver, want, w, data, bps)
+        got = d_out[(nf - 1) * ob:(nf - 1) * ob + h * opitch].cpu().numpy().view(np.uint16).reshape(h, opitch // 2)
+        exact = bool(np.array_equal(got[:, :w], want[:, :w]))
+        ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), nf * fb), d_out), steps, 3, dist)
+        in_b, out_b, pixels = plan.bytes()
+        per = ms / steps
+        ent = {"MPixels/s": pixels / (per * 1e-3) / 1e6, "ms_per_step": per, "frames_per_step": nf,
+               "bit_exact": exact, "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
+               "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak,
+               "kernel": "pana_kernel<%d,%d>" % (ver, bps)}
+        if not args.skip_cpu and rank0:
+            import oracle
+            if oracle.HAVE_REF:
+                ncores = os.cpu_count() or 1
+                tmp = port.new_image(w, h)
+                msr = min(oracle.ref.panasonic(ver, tmp, w, data, bps, nthreads=ncores) for _ in range(3))
+                ent["cpu_reference"] = {"kind": "reference", "cores": ncores,
+                                        "MPixels/s": w * h / (msr * 1e-3) / 1e6,
+                                        "sample": "PanasonicV%dDecompressor::decompress (OpenMP), 1 frame, best of 3" % ver}
+        out["8(f)4 PanasonicV%dDecompressor %dx%d %d-bit" % (ver, w, h, bps)] = ent
+        del plan, d_in, d_out
     # ---- SonyArw2Decompressor, 9568x6376 (61 MP, A7R IV class), dithered curve, 4 frames ----
     w, h, nf = 9568, 6376, 4
     data = synth.arw2_frame(w, h, seed=21)

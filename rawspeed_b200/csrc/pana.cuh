@@ -38,7 +38,7 @@ template <int OFF, int N>
 __device__ __forceinline__ uint32_t pana_field(const uint32_t (&w)[4]) {
   constexpr int k = OFF >> 5, s = OFF & 31;
   uint32_t v = w[k] >> s;
-  if (s + N > 32 && k < 3)
+  if constexpr (s + N > 32 && k < 3)
     v |= w[k + 1] << (32 - s);
   return v & ((1u << N) - 1u);
 }
