@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(PANA_NT)
     pana_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                 const PanaJobDev* __restrict__ jobs, int njobs, uint32_t total_units) {
   constexpr int NPIX = VER == 6 ? (BPS == 14 ? 11 : 14) : 128 / BPS;
-  const uint32_t u = blockIdx.x * PANA_NT + threadIdx.x;
-  if (u >= total_units)
-    return;
+  const uint32_t u_raw = blockIdx.x * PANA_NT + threadIdx.x;
+  const bool live = u_raw < total_units;
+  const uint32_t u = live ? u_raw : total_units - 1u; // (idle threads of the last CTA mirror the last unit)
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -161,12 +161,65 @@ __global__ void __launch_bounds__(PANA_NT)
   } else {
     pana_unpack<BPS, 0, NPIX>(w, px);
   }
-  const uint64_t idx = (uint64_t)ul * NPIX; // linear pixel index; a unit never straddles rows
-  const uint32_t row = (uint32_t)(idx / jb.width), col = (uint32_t)(idx - (uint64_t)row * jb.width);
-  uint16_t* o16 = reinterpret_cast<uint16_t*>(out + jb.out_offset + (uint64_t)row * jb.out_pitch) + col;
+  // ---- pixels -> image, coalesced: the CTA's units are consecutive pixels of the image
+  //      (consecutive units of one job; a job change inside the CTA falls back to direct
+  //      stores), so they are staged in shared memory and written out as aligned 32-bit
+  //      words, 128 contiguous bytes per warp instruction instead of 32 scattered uint16 ----
+  __shared__ uint16_t stage[PANA_NT * 14];
+  __shared__ int same_job;
+  const uint32_t u0 = blockIdx.x * PANA_NT; // first unit of the CTA
+  if (threadIdx.x == 0) {
+    const uint32_t ulast = min(u0 + PANA_NT, total_units) - 1u;
+    same_job = (jobs[lo].unit_begin <= u0 && ulast - jb.unit_begin < jb.units) ? 1 : 0;
+  }
+  if (live) {
 #pragma unroll
-  for (int i = 0; i < NPIX; ++i)
-    o16[i] = (uint16_t)px[i];
+    for (int i = 0; i < NPIX; ++i)
+      stage[threadIdx.x * NPIX + i] = (uint16_t)px[i];
+  }
+  __syncthreads();
+  if (!same_job) {
+    if (!live)
+      return;
+    const uint64_t idx = (uint64_t)ul * NPIX; // a unit never straddles rows
+    const uint32_t row = (uint32_t)(idx / jb.width), col = (uint32_t)(idx - (uint64_t)row * jb.width);
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(out + jb.out_offset + (uint64_t)row * jb.out_pitch) + col;
+#pragma unroll
+    for (int i = 0; i < NPIX; ++i)
+      o16[i] = (uint16_t)px[i];
+    return;
+  }
+  {
+    const uint32_t nunits = min((uint32_t)PANA_NT, total_units - u0);
+    const uint32_t npx = nunits * NPIX;
+    const uint64_t p0 = (uint64_t)(u0 - jb.unit_begin) * NPIX; // first pixel of the CTA in the image
+    uint8_t* obase = out + jb.out_offset;
+    // pixel k of the CTA -> byte address; rows are out_pitch apart
+    uint32_t row = (uint32_t)(p0 / jb.width);
+    uint32_t col = (uint32_t)(p0 - (uint64_t)row * jb.width);
+    // walk the CTA's pixels row by row: segment [k0, k1) lies in `row` starting at `col`
+    uint32_t k0 = 0;
+    while (k0 < npx) {
+      const uint32_t k1 = min(npx, k0 + (jb.width - col));
+      uint8_t* rowp = obase + (uint64_t)row * jb.out_pitch + 2ull * col;
+      const uint32_t n = k1 - k0;
+      // leading pixel to reach 4-byte alignment, then pairs, then a trailing pixel
+      const uint32_t lead = ((reinterpret_cast<uintptr_t>(rowp) & 2u) && n) ? 1u : 0u;
+      if (lead && threadIdx.x == 0)
+        *reinterpret_cast<uint16_t*>(rowp) = stage[k0];
+      const uint32_t npairs = (n - lead) >> 1;
+      uint32_t* o32 = reinterpret_cast<uint32_t*>(rowp + 2u * lead);
+      for (uint32_t q = threadIdx.x; q < npairs; q += PANA_NT) {
+        const uint32_t a = stage[k0 + lead + 2 * q], b = stage[k0 + lead + 2 * q + 1];
+        o32[q] = a | (b << 16);
+      }
+      if (((n - lead) & 1u) && threadIdx.x == 1)
+        reinterpret_cast<uint16_t*>(rowp)[n - 1] = stage[k1 - 1];
+      k0 = k1;
+      ++row;
+      col = 0;
+    }
+  }
 }
 
 } // namespace rsb200

@@ -62,8 +62,9 @@ def test_panasonic_batch_mixed_versions_unaligned(ctx):
         buf[o:o + d.size] = d
     plan = rs.pana_plan(ctx, jobs)
     got, _ = gpu_run(plan, buf, np.zeros(opos // 2, dtype=np.uint16))
-    for o, want in wants:
-        assert np.array_equal(got.reshape(-1)[o // 2:o // 2 + want.size].reshape(want.shape), want)
+    for (o, want), (v, bps, w, h) in zip(wants, specs):
+        g = got.reshape(-1)[o // 2:o // 2 + want.size].reshape(want.shape)
+        assert np.array_equal(g[:, :w], want[:, :w])
 
 
 @pytest.mark.parametrize("version,bps,w,h", [(5, 12, 400, 33), (6, 14, 1100, 13), (7, 14, 1809, 10)])
