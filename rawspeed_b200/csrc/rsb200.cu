@@ -122,7 +122,7 @@ struct rsb200_plan {
   uint32_t* d_arw2_bad = nullptr;
   uint32_t* h_arw2_bad = nullptr; // pinned
   uint32_t arw2_groups = 0;
-  int arw2_mode = 0;
+  int arw2_mode = 0, arw2_ntables = 0;
   // ljpeg
   DevTable* d_tables = nullptr;
   DevScan* d_scans = nullptr;
@@ -753,6 +753,7 @@ extern "C" int rsb200_arw2_plan_create(rsb200_ctx* ctx, const rsb200_arw2_job* j
   }
   p->arw2_groups = (uint32_t)groups;
   p->arw2_mode = !any_table ? 0 : (dither ? 2 : 1);
+  p->arw2_ntables = any_table ? ntables : 0;
   // the part of the tables a value can reach: entries 0 .. 4095
   std::vector<uint16_t> tcut;
   if (any_table) {
@@ -802,16 +803,25 @@ static cudaError_t run_arw2(const rsb200_plan* p, const uint8_t* in, uint8_t* ou
   cudaError_t e = cudaMemsetAsync(p->d_arw2_bad, 0, sizeof(uint32_t) * (size_t)p->nunits, st);
   if (e != cudaSuccess)
     return e;
-  const uint32_t nb = (p->arw2_groups + ARW2_NT - 1) / ARW2_NT;
-#define RSB_ARW2(M)                                                                        \
-  arw2_kernel<M><<<nb, ARW2_NT, 0, st>>>(in, outp, p->d_arw2_jobs, p->nunits, p->arw2_groups, \
-                                         p->d_arw2_tables, p->d_arw2_bad)
+  const uint32_t per_cta = ARW2_NT * ARW2_GPT;
+  const uint32_t nb = (p->arw2_groups + per_cta - 1) / per_cta;
+  const bool sm = p->arw2_ntables == 1; // one table: staged in shared memory
+#define RSB_ARW2(M, S)                                                                     \
+  arw2_kernel<M, S><<<nb, ARW2_NT, 0, st>>>(in, outp, p->d_arw2_jobs, p->nunits,           \
+                                            p->arw2_groups, p->d_arw2_tables, p->d_arw2_bad)
   if (p->arw2_mode == 0)
-    RSB_ARW2(0);
-  else if (p->arw2_mode == 1)
-    RSB_ARW2(1);
-  else
-    RSB_ARW2(2);
+    RSB_ARW2(0, false);
+  else if (p->arw2_mode == 1) {
+    if (sm)
+      RSB_ARW2(1, true);
+    else
+      RSB_ARW2(1, false);
+  } else {
+    if (sm)
+      RSB_ARW2(2, true);
+    else
+      RSB_ARW2(2, false);
+  }
 #undef RSB_ARW2
   return cudaGetLastError();
 }
