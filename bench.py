@@ -411,10 +411,12 @@ def bench_gather(torch, dist, d_out, world, rank, plan, d_in, args, frames, out_
     = one NCCL all_gather on the decode stream."""
     from rawspeed_b200 import shard
     local = d_out.view(frames, out_fb)
+    gathered = torch.empty((world, frames, out_fb), dtype=torch.uint8, device="cuda")
 
     def step():
         plan.run(d_in, d_out)
-        shard.gather_frames(local, frames * world, dist)
+        # copy-free form: preallocated result, the collective's own layout (frame r + k*world at [r, k])
+        shard.gather_frames(local, frames * world, dist, out=gathered, reorder=False)
     n = max(2, min(args.steps, 5))
     ms = time_steps(torch, step, n, 1, dist)
     total = frames * world * out_fb
