@@ -39,7 +39,7 @@ struct DevTInfo {
 constexpr uint32_t T_ANCHOR_SHIFT = 8; // one anchor per 256 raw bytes
 constexpr uint32_t T_PAD_WORDS = 8;    // zero words behind the data
 constexpr int C_WARPS = 4;             // segments per CTA
-constexpr int C_STAGE = 136;           // staging words per warp (3 + 512 bytes, rounded up)
+constexpr int C_STAGE = 160;           // staging words per warp (3 + 512 bytes + padding, 5 x 32)
 
 // bit i (0..3) = byte i of w is 0xFF / 0x00 (exact per byte: no carries between bytes)
 __device__ __forceinline__ uint32_t c_ff_mask4(uint32_t w) {
@@ -63,12 +63,10 @@ __device__ __forceinline__ uint32_t c_zero_mask16(const uint4& q) {
 // over the pair (q[k], q[k+1]))
 __device__ __forceinline__ void c_remove_byte(uint4& q, uint32_t i) {
   auto sel = [&](int k) -> uint32_t {
-    const int r = (int)i - 4 * k; // position of the removed byte relative to word k
-    if (r >= 4)
-      return 0x3210u; // entirely below: unchanged
-    if (r <= 0)
-      return 0x4321u; // entirely above: shifted by one byte
-    return r == 1 ? 0x4320u : (r == 2 ? 0x4310u : 0x4210u);
+    // byte j of word k comes from position j (below the removed byte) or j + 1 (at / above
+    // it): selector 0x3210 with 1 added to the nibbles j >= r, r = i - 4k clamped to 0..4
+    const int r = min(max((int)i - 4 * k, 0), 4);
+    return 0x3210u + (0x1111u & ((0xFFFFu << (4 * r)) & 0xFFFFu));
   };
   const uint32_t a = __byte_perm(q.x, q.y, sel(0)), b = __byte_perm(q.y, q.z, sel(1)),
                  c = __byte_perm(q.z, q.w, sel(2)), d = __byte_perm(q.w, 0u, sel(3));
@@ -230,14 +228,17 @@ __global__ void __launch_bounds__(32 * C_WARPS)
       nw = ((have + 3u) >> 2) + T_PAD_WORDS;
     const uint32_t part = (have & 3u) && !ended ? stage[have >> 2] : 0u; // carried to the next piece
     __syncwarp();
-    for (uint32_t i = lane; i < max(nw, (have >> 2) + 1u); i += 32) {
-      uint32_t w = 0;
-      if (i < (uint32_t)C_STAGE) {
-        w = stage[i];
-        stage[i] = (i == 0) ? part : 0u; // (the buffer is clean again for the next piece)
+    {
+      // (nw <= 129 + T_PAD_WORDS < C_STAGE = 5 x 32; the segment's capacity covers data + padding)
+      uint32_t* cwp = cw + wout + lane;
+#pragma unroll
+      for (int it = 0; it < C_STAGE / 32; ++it) {
+        const uint32_t i = lane + 32u * it;
+        const uint32_t w = stage[i];
+        stage[i] = (it == 0 && lane == 0) ? part : 0u; // clean again for the next piece
+        if (i < nw)
+          cwp[32 * it] = w;
       }
-      if (i < nw && wout + i < ts.cap_words)
-        cw[wout + i] = w;
     }
     __syncwarp();
     wout += have >> 2;
