@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(PANA_NT)
   if (!same_job) {
     if (!live)
       return;
-    const uint64_t idx = (uint64_t)ul * NPIX; // a unit never straddles rows
-    const uint32_t row = (uint32_t)(idx / jb.width), col = (uint32_t)(idx - (uint64_t)row * jb.width);
+    const uint32_t idx = ul * NPIX; // (< 2^32: checked at plan creation) a unit never straddles rows
+    const uint32_t row = idx / jb.width, col = idx - row * jb.width;
     uint16_t* o16 = reinterpret_cast<uint16_t*>(out + jb.out_offset + (uint64_t)row * jb.out_pitch) + col;
 #pragma unroll
     for (int i = 0; i < NPIX; ++i)
@@ -192,11 +192,11 @@ __global__ void __launch_bounds__(PANA_NT)
   {
     const uint32_t nunits = min((uint32_t)PANA_NT, total_units - u0);
     const uint32_t npx = nunits * NPIX;
-    const uint64_t p0 = (uint64_t)(u0 - jb.unit_begin) * NPIX; // first pixel of the CTA in the image
+    const uint32_t p0 = (u0 - jb.unit_begin) * NPIX; // first pixel of the CTA in the image (< 2^32)
     uint8_t* obase = out + jb.out_offset;
     // pixel k of the CTA -> byte address; rows are out_pitch apart
-    uint32_t row = (uint32_t)(p0 / jb.width);
-    uint32_t col = (uint32_t)(p0 - (uint64_t)row * jb.width);
+    uint32_t row = p0 / jb.width;
+    uint32_t col = p0 - row * jb.width;
     // walk the CTA's pixels row by row: segment [k0, k1) lies in `row` starting at `col`
     uint32_t k0 = 0;
     while (k0 < npx) {

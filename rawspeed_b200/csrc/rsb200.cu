@@ -624,7 +624,7 @@ extern "C" int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* j
       need = ((units + 1023) / 1024) * 0x4000ull;
     const bool ok = vok && j.width > 0 && j.height > 0 && j.width % npix == 0 &&
                     j.in_size >= need && (j.out_offset % 2) == 0 && (j.out_pitch % 2) == 0 &&
-                    (uint64_t)j.width * 2 <= j.out_pitch && units < 0xFFFF0000ull;
+                    (uint64_t)j.width * 2 <= j.out_pitch && area < 0xFFFF0000ull;
     if (!ok) {
       delete p;
       return set_err(ctx, RSB200_ERR_ARG, "pana job %d: malformed descriptor", i);
