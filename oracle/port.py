@@ -287,6 +287,29 @@ def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False):
     return img
 
 
+def _strips(strips):
+    n = len(strips)
+    off = (C.c_uint64 * n)(*[s[0] for s in strips])
+    ln = (C.c_uint32 * n)(*[s[1] for s in strips])
+    rown = (C.c_int32 * n)(*[s[2] for s in strips])
+    return off, ln, rown, n
+
+
+def phaseone(img, w, file, strips):
+    """PhaseOneDecompressor(img, strips).decompress(); strips: [(offset, size, row)]."""
+    p, n = _u8(file)
+    im = _img(img, w, 1)
+    off, ln, rown, ns = _strips(strips)
+    e = Err()
+    L = lib()
+    L.rso_phaseone.argtypes = [C.POINTER(Image), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64),
+                               C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_int,
+                               C.POINTER(Err)]
+    rc = L.rso_phaseone(C.byref(im), p, C.c_uint64(n), off, ln, rown, ns, C.byref(e))
+    e.check(rc)
+    return img
+
+
 def panasonic(version, img, w, data, bps=14):
     """PanasonicV{5,6,7}Decompressor(img, data[, bps]).decompress() into img (in place)."""
     p, n = _u8(data)

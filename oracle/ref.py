@@ -215,6 +215,23 @@ def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False, reps=
     return ms.value
 
 
+def phaseone(img, w, file, strips, nthreads=1, reps=1):
+    """Reference PhaseOneDecompressor (ref_phaseone); strips: [(offset, size, row)]."""
+    from .port import _strips
+    p, n = _u8(file)
+    off, ln, rown, ns = _strips(strips)
+    ms = C.c_double(0)
+    e = Err()
+    L = lib()
+    L.ref_phaseone.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_uint64,
+                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_int32),
+                               C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(Err)]
+    rc = L.ref_phaseone(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2, p,
+                        C.c_uint64(n), off, ln, rown, ns, nthreads, reps, C.byref(ms), C.byref(e))
+    e.check(rc)
+    return ms.value
+
+
 def panasonic(version, img, w, data, bps=14, nthreads=1, reps=1):
     """Reference PanasonicV{5,6,7}Decompressor (ref_panasonic)."""
     p, n = _u8(data)

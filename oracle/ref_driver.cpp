@@ -43,6 +43,7 @@
 #include "decompressors/PentaxDecompressor.h"
 #include "decompressors/SonyArw2Decompressor.h"
 #include "decompressors/NikonDecompressor.h"
+#include "decompressors/PhaseOneDecompressor.h"
 #include "decompressors/PanasonicV5Decompressor.h"
 #include "decompressors/PanasonicV6Decompressor.h"
 #include "decompressors/PanasonicV7Decompressor.h"
@@ -301,6 +302,37 @@ int ref_unpack_form(const uint8_t* in, uint32_t in_size, void* img_data, int is_
     for (int r = 0; r < h; ++r)
       std::memcpy(static_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, rowPtr(r),
                   static_cast<size_t>(w) * bpp);
+  });
+}
+
+// PhaseOneDecompressor(mRaw, strips).decompress(): strip k = (row rown[k], bytes
+// [off[k], off[k]+len[k]) of `file`), as IiqDecoder::DecodePhaseOneC builds them.
+int ref_phaseone(uint16_t* img_data, int w, int h, int pitch, const uint8_t* file,
+                 uint64_t file_size, const uint64_t* off, const uint32_t* len, const int32_t* rown,
+                 int nstrips, int nthreads, int reps, double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(w, h, 1, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      std::vector<PhaseOneStrip> strips;
+      strips.reserve(static_cast<size_t>(nstrips));
+      for (int k = 0; k < nstrips; ++k) {
+        if (off[k] + len[k] > file_size)
+          ThrowIOE("Out of bounds access in ByteStream");
+        strips.emplace_back(rown[k], ByteStream(DataBuffer(Buffer(file + off[k], len[k]),
+                                                          Endianness::little)));
+      }
+      const auto t0 = std::chrono::steady_clock::now();
+      PhaseOneDecompressor d(img, std::move(strips));
+      d.decompress();
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
   });
 }
 

@@ -2910,3 +2910,108 @@ int rso_panasonic(int version, rso_image* img, const uint8_t* data, uint32_t siz
   THROW_RDE(&c, "unknown Panasonic version %d", version);
   return RSO_OK;
 }
+
+/* ------------------------------------------------------------------
+ * PhaseOneDecompressor (decompressors/PhaseOneDecompressor.cpp)
+ * ------------------------------------------------------------------ */
+typedef struct {
+  jmp_buf* outer;
+} p1_dummy;
+
+int rso_phaseone(rso_image* img, const uint8_t* file, uint64_t file_size, const uint64_t* off,
+                 const uint32_t* len, const int32_t* rown, int nstrips, rso_err* e) {
+  static const int length[10] = {8, 7, 6, 9, 11, 10, 5, 12, 14, 13};
+  rso_ctx c;
+  rso_err le;
+  int* volatile order = NULL;
+  volatile int failed = 0;
+  char first[320];
+  int k;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  first[0] = 0;
+  if (setjmp(c.jb)) {
+    free((void*)order);
+    return c.e->code;
+  }
+  /* ctor (:42-59) */
+  if (img->is_f32)
+    THROW_RDE(&c, "Unexpected data type");
+  if (img->cpp != 1)
+    THROW_RDE(&c, "Unexpected cpp: %u", (unsigned)img->cpp);
+  if (!(img->w > 0 && img->h > 0) || img->w % 2 != 0 || img->w > 11976 || img->h > 8854)
+    THROW_RDE(&c, "Unexpected image dimensions found: (%d; %d)", img->w, img->h);
+  /* prepareStrips (:61-83): exactly one strip per row */
+  if (nstrips != img->h)
+    THROW_RDE(&c, "Height (%d) vs strip count %zu mismatch", img->h, (size_t)nstrips);
+  order = (int*)malloc(sizeof(int) * (size_t)img->h);
+  if (!order)
+    THROW_RDE(&c, "out of memory");
+  for (k = 0; k < img->h; k++)
+    ((int*)order)[k] = -1;
+  for (k = 0; k < nstrips; k++) {
+    if (rown[k] < 0 || rown[k] >= img->h || ((int*)order)[rown[k]] != -1)
+      THROW_RDE(&c, "Strips validation issue.");
+    if (off[k] + len[k] > file_size)
+      THROW_IOE(&c, "Out of bounds access in ByteStream");
+    ((int*)order)[rown[k]] = k;
+  }
+  /* decompressStrip (:85-135), one row at a time; a throwing row is recorded (:137-150) */
+  for (k = 0; k < img->h; k++) {
+    const int s = ((int*)order)[k];
+    rso_ctx rc;
+    rso_err re;
+    rc.e = &re;
+    re.code = RSO_OK;
+    re.msg[0] = 0;
+    if (setjmp(rc.jb)) {
+      if (!failed) {
+        failed = 1;
+        snprintf(first, sizeof first, "%s", re.msg);
+      }
+      continue;
+    }
+    {
+      pump bs;
+      int32_t pred[2] = {0, 0};
+      int ln[2] = {0, 0}, col;
+      uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)k * (size_t)img->pitch);
+      pump_init(&bs, &rc, RSO_MSB32, file + off[s], (int)len[s]);
+      for (col = 0; col < img->w; col++) {
+        int i;
+        pump_fill(&bs, 32);
+        if ((unsigned)col >= ((unsigned)img->w & ~7u)) {
+          ln[0] = ln[1] = 14;
+        } else if ((col & 7) == 0) {
+          int t;
+          for (t = 0; t < 2; t++) {
+            int j = 0;
+            for (; j < 5; j++) {
+              if (pump_get_nofill(&bs, 1) != 0) {
+                if (col == 0)
+                  THROW_RDE(&rc, "Can not initialize lengths. Data is corrupt.");
+                break;
+              }
+            }
+            if (j > 0)
+              ln[t] = length[2 * (j - 1) + (int)pump_get_nofill(&bs, 1)];
+          }
+        }
+        i = ln[col & 1];
+        if (i == 14) {
+          pred[col & 1] = (int32_t)pump_get_nofill(&bs, 16);
+          o[col] = (uint16_t)pred[col & 1];
+        } else {
+          pred[col & 1] += (int32_t)pump_get_nofill(&bs, i) + 1 - (1 << (i - 1));
+          o[col] = (uint16_t)pred[col & 1];
+        }
+      }
+    }
+  }
+  free((void*)order);
+  order = NULL;
+  if (failed)
+    THROW_RDE(&c, "Too many errors encountered. Giving up. First Error:\n%s", first);
+  return RSO_OK;
+}

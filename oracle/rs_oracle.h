@@ -185,6 +185,14 @@ int rso_nikon_tree(int sel, uint8_t* ncpl, uint8_t* values);
 int rso_panasonic(int version, rso_image* img, const uint8_t* data, uint32_t size, int bps,
                   rso_err* e);
 
+/* ---- PhaseOneDecompressor (decompressors/PhaseOneDecompressor.cpp:42-168) ----
+ * One strip per image row (any order; strip k = bytes [off[k], off[k]+len[k]) of `file`,
+ * decoding row rown[k]); a row is an MSB32 bit stream: every 8 pixels two code lengths
+ * (unary prefix + 1 bit into {8,7,6,9,11,10,5,12,14,13}), then per pixel either a raw
+ * 16-bit value (length 14) or a difference to the same-parity predecessor. */
+int rso_phaseone(rso_image* img, const uint8_t* file, uint64_t file_size, const uint64_t* off,
+                 const uint32_t* len, const int32_t* rown, int nstrips, rso_err* e);
+
 /* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
  * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
  * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity

@@ -250,3 +250,76 @@ def make_nikon(img, sel, pup):
         d[1, 0], d[1, 1] = a[1, 0] - pup[2], a[1, 1] - pup[3]
     ncpl, values = port.nikon_tree(sel)
     return port.encode_diffs_plain(d.reshape(-1), port.Huff(ncpl, values))
+
+
+_P1_LENGTH = [8, 7, 6, 9, 11, 10, 5, 12, 14, 13]
+
+
+def phaseone_row(vals):
+    """Encode one image row the way PhaseOneDecompressor::decompressStrip reads it
+    (PhaseOneDecompressor.cpp:85-135): an MSB32 bit stream (32-bit little-endian chunks
+    consumed MSB first); per 8 pixels two code lengths, chosen as the smallest that holds
+    the 4 differences of that parity.  Returns bytes (multiple of 4, + 8 bytes slack)."""
+    w = len(vals)
+    bits = []
+
+    def put(v, n):
+        for k in range(n - 1, -1, -1):
+            bits.append((v >> k) & 1)
+
+    pred = [0, 0]
+    ln = [0, 0]
+    lim = w & ~7
+    for col in range(w):
+        if col >= lim:
+            ln = [14, 14]
+        elif col % 8 == 0:
+            for t in (0, 1):
+                p = pred[t]
+                need = 5
+                for c in range(col + t, col + 8, 2):
+                    d = int(vals[c]) - p
+                    p = int(vals[c])
+                    n = 5
+                    while n < 14 and not (0 <= d - 1 + (1 << (n - 1)) < (1 << n)):
+                        n += 1
+                    need = max(need, n)
+                if col == 0:
+                    need = max(need, 13)   # at column 0 a 1 bit in the prefix is an error: only 5 zeros
+                idx = _P1_LENGTH.index(need)
+                j, b = idx // 2 + 1, idx % 2
+                put(0, j)
+                if j < 5:
+                    put(1, 1)
+                put(b, 1)
+                ln[t] = need
+        i = ln[col & 1]
+        v = int(vals[col])
+        if i == 14:
+            put(v & 0xFFFF, 16)
+        else:
+            put(v - pred[col & 1] - 1 + (1 << (i - 1)), i)
+        pred[col & 1] = v
+    while len(bits) % 32:
+        bits.append(0)
+    a = np.array(bits, dtype=np.uint8).reshape(-1, 32)
+    words = (a.astype(np.uint64) << np.arange(31, -1, -1, dtype=np.uint64)).sum(axis=1).astype("<u4")
+    return words.tobytes() + bytes(8)
+
+
+def make_phaseone(img, shuffle_seed=None, gap=0):
+    """file bytes + strips [(offset, size, row)] for PhaseOneDecompressor: one strip per
+    row, stored in shuffled order with `gap` unused bytes between them."""
+    h, w = img.shape
+    rows = [phaseone_row(img[r]) for r in range(h)]
+    order = list(range(h))
+    if shuffle_seed is not None:
+        rng = np.random.default_rng(shuffle_seed)
+        rng.shuffle(order)
+    blob = bytearray()
+    strips = []
+    for r in order:
+        blob += bytes(gap)
+        strips.append((len(blob), len(rows[r]), r))
+        blob += rows[r]
+    return np.frombuffer(bytes(blob), dtype=np.uint8).copy(), strips
