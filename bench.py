@@ -730,6 +730,47 @@ def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
                                         "sample": "PanasonicV%dDecompressor::decompress (OpenMP), 1 frame, best of 3" % ver}
         out["8(f)4 PanasonicV%dDecompressor %dx%d %d-bit" % (ver, w, h, bps)] = ent
         del plan, d_in, d_out
+    # ---- PhaseOneDecompressor, 11608x8708 (IQ3 100MP class): one thread per row ----
+    w, h = 11608, 8708
+    rowimg = (synth.image_model(w, 4, seed=31, bits=14)).astype(np.uint16)
+    rows4 = [np.frombuffer(synth.phaseone_row(rowimg[k]), dtype=np.uint8) for k in range(4)]
+    offs, blobs, pos = [], [], 0
+    for r in range(h):   # the four encoded rows repeat down the image (rows are independent streams)
+        offs.append((pos, rows4[r % 4].size, r))
+        blobs.append(rows4[r % 4])
+        pos += rows4[r % 4].size
+    blob = np.concatenate(blobs)
+    pj = rs.PhaseOneJob()
+    pj.out_offset, pj.out_pitch, pj.width, pj.height, pj.first_strip = 0, rs.image_pitch(w), w, h, 0
+    pstrips = []
+    for off, size, row in offs:
+        ps = rs.PhaseOneStrip()
+        ps.in_offset, ps.in_size, ps.row = off, size, row
+        pstrips.append(ps)
+    plan = rs.phaseone_plan(ctx, [pj], pstrips)
+    d_in = torch.zeros(blob.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[:blob.size] = torch.from_numpy(blob)
+    d_out = torch.zeros(h * rs.image_pitch(w), dtype=torch.uint8, device="cuda")
+    plan.run((d_in.data_ptr(), blob.size), d_out)
+    res = plan.results()
+    got = d_out.cpu().numpy().view(np.uint16).reshape(h, rs.image_pitch(w) // 2)
+    exact = res[0][0] == 0 and all(bool(np.array_equal(got[r, :w], rowimg[r % 4])) for r in (0, 1, 2, 3, h - 1))
+    ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), blob.size), d_out), 3, 1, dist)
+    per = ms / 3
+    ent = {"MPixels/s": w * h / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": bool(exact),
+           "compressed_bytes_per_pixel": blob.size / (w * h),
+           "kernel": "p1_kernel (one thread per row: 8708 threads, latency bound)"}
+    if not args.skip_cpu and rank0:
+        import oracle
+        if oracle.HAVE_REF:
+            ncores = os.cpu_count() or 1
+            tmp = port.new_image(w, h)
+            msr = min(oracle.ref.phaseone(tmp, w, blob, offs, nthreads=ncores) for _ in range(2))
+            ent["cpu_reference"] = {"kind": "reference", "cores": ncores,
+                                    "MPixels/s": w * h / (msr * 1e-3) / 1e6,
+                                    "sample": "PhaseOneDecompressor::decompress (OpenMP over rows), best of 2"}
+    out["8(f)4 PhaseOneDecompressor 11608x8708"] = ent
+    del plan, d_in, d_out
     # ---- SonyArw2Decompressor, 9568x6376 (61 MP, A7R IV class), dithered curve, 4 frames ----
     w, h, nf = 9568, 6376, 4
     data = synth.arw2_frame(w, h, seed=21)

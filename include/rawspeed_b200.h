@@ -201,6 +201,34 @@ int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* jobs, int nj
                             rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* K8: Phase One IIQ row codec.                          */
+/*   PhaseOneDecompressor::decompressStrip / decompress                 */
+/*   decompressors/PhaseOneDecompressor.cpp:85-168                      */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t in_offset; /* first byte of the strip (one image row)                  */
+  uint32_t in_size;   /* bytes of the strip                                       */
+  uint32_t row;       /* image row it decodes (PhaseOneStrip::n)                  */
+} rsb200_phaseone_strip;
+
+typedef struct {
+  uint64_t out_offset;  /* byte offset of image row 0; multiple of 4              */
+  uint32_t out_pitch;   /* bytes between output rows; multiple of 4, >= 2*width   */
+  uint32_t width;       /* even, <= 11976                                         */
+  uint32_t height;      /* <= 8854; the job owns `height` strips                  */
+  uint32_t first_strip; /* index of its first strip in the plan's strip array; the
+                           strips of a job may be in any order but must name every
+                           row exactly once (prepareStrips, :61-83)               */
+} rsb200_phaseone_job;
+
+/* rsb200_plan_results: RSB200_ERR_RDE for a job with a row that cannot be decoded
+ * (lengths not initialised at column 0, bit stream over-read) -- the reference's
+ * "Too many errors encountered. Giving up." */
+int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseone_job* jobs, int njobs,
+                                const rsb200_phaseone_strip* strips, int nstrips,
+                                rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
 /* K5: Canon sRaw interpolation.                         */
 /*   Cr2sRawInterpolator::interpolate(version)                          */
 /*   interpolators/Cr2sRawInterpolator.cpp:96-187 (4:2:2), :189-453     */

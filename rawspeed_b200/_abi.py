@@ -59,6 +59,15 @@ class PanaJob(C.Structure):
                 ("version", C.c_uint8), ("bps", C.c_uint8), ("reserved", C.c_uint8 * 2)]
 
 
+class PhaseOneStrip(C.Structure):
+    _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint32), ("row", C.c_uint32)]
+
+
+class PhaseOneJob(C.Structure):
+    _fields_ = [("out_offset", C.c_uint64), ("out_pitch", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("first_strip", C.c_uint32)]
+
+
 class Arw2Job(C.Structure):
     _fields_ = [("in_offset", C.c_uint64), ("out_offset", C.c_uint64),
                 ("out_pitch", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
@@ -103,7 +112,7 @@ EXPORTS = [
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_raw_plan_create", "rsb200_sraw_plan_create",
     "rsb200_pentax_plan_create", "rsb200_arw2_plan_create", "rsb200_nikon_plan_create",
-    "rsb200_pana_plan_create",
+    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",
@@ -144,6 +153,8 @@ def load():
     L.rsb200_nikon_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32, C.POINTER(NikonJob), i32,
                                            C.POINTER(C.c_uint16), i32, C.POINTER(vp)]
     L.rsb200_pana_plan_create.argtypes = [vp, C.POINTER(PanaJob), i32, C.POINTER(vp)]
+    L.rsb200_phaseone_plan_create.argtypes = [vp, C.POINTER(PhaseOneJob), i32,
+                                              C.POINTER(PhaseOneStrip), i32, C.POINTER(vp)]
     L.rsb200_arw2_plan_create.argtypes = [vp, C.POINTER(Arw2Job), i32, C.POINTER(C.c_uint16),
                                           i32, i32, C.POINTER(vp)]
     L.rsb200_pentax_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32,

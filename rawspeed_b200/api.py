@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Arw2Job, NikonJob, PanaJob, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, NikonJob, PanaJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -190,6 +190,16 @@ def pana_plan(ctx, jobs):
     arr = (PanaJob * len(jobs))(*jobs)
     h = C.c_void_p()
     ctx.check(ctx._lib.rsb200_pana_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def phaseone_plan(ctx, jobs, strips):
+    """Phase One IIQ images (PhaseOneDecompressor::decompress): one strip per image row."""
+    ja = (PhaseOneJob * len(jobs))(*jobs)
+    sa = (PhaseOneStrip * len(strips))(*strips)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_phaseone_plan_create(ctx.h, ja, len(jobs), sa, len(strips),
+                                                   C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

@@ -285,6 +285,28 @@ int rsb200h_panasonic(int version, uint16_t* img_data, int w, int h, int pitch,
   });
 }
 
+int rsb200h_phaseone(uint16_t* img_data, int w, int h, int pitch, const uint8_t* file,
+                     uint64_t file_size, const uint64_t* off, const uint32_t* len,
+                     const int32_t* rown, int nstrips, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, 1, pitch, true, 1, 1);
+    std::vector<PhaseOneStrip> strips;
+    for (int k = 0; k < nstrips; ++k) {
+      if (off[k] + len[k] > file_size)
+        ThrowIOE("Out of bounds access in ByteStream");
+      strips.emplace_back(rown[k], ByteStream(file + off[k], len[k]));
+    }
+    PhaseOneDecompressor d(img, std::move(strips));
+    try {
+      d.decompress();
+    } catch (...) {
+      copyOut(img, img_data);
+      throw;
+    }
+    copyOut(img, img_data);
+  });
+}
+
 int rsb200h_sony_arw2(uint16_t* img_data, int w, int h, int pitch, const uint8_t* data,
                       uint32_t size, const uint16_t* curve, int ncurve, int dither,
                       rsb200h_err* e) {

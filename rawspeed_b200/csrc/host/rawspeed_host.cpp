@@ -734,6 +734,71 @@ PanasonicV7Decompressor::PanasonicV7Decompressor(RawImage img, ByteStream input_
 }
 void PanasonicV7Decompressor::decompress() const { panaRun(mRaw, input, 7, 14); }
 
+// ------------------------------------------------------------------ Phase One
+// ctor (decompressors/PhaseOneDecompressor.cpp:42-59)
+PhaseOneDecompressor::PhaseOneDecompressor(RawImage img, std::vector<PhaseOneStrip>&& strips_)
+    : mRaw(std::move(img)), strips(std::move(strips_)) {
+  if (mRaw->getDataType() != RawImageType::UINT16)
+    ThrowRDE("Unexpected data type");
+  if (mRaw->getCpp() != 1 || mRaw->getBpp() != sizeof(uint16_t))
+    ThrowRDE("Unexpected cpp: %u", mRaw->getCpp());
+  if (!(mRaw->dim.x > 0 && mRaw->dim.y > 0) || mRaw->dim.x % 2 != 0 || mRaw->dim.x > 11976 ||
+      mRaw->dim.y > 8854)
+    ThrowRDE("Unexpected image dimensions found: (%d; %d)", mRaw->dim.x, mRaw->dim.y);
+  prepareStrips();
+}
+
+// prepareStrips (:61-83): every row exactly once
+void PhaseOneDecompressor::prepareStrips() {
+  if (strips.size() != (size_t)mRaw->dim.y)
+    ThrowRDE("Height (%d) vs strip count %zu mismatch", mRaw->dim.y, strips.size());
+  std::sort(strips.begin(), strips.end(),
+            [](const PhaseOneStrip& a, const PhaseOneStrip& b) { return a.n < b.n; });
+  for (size_t i = 0; i < strips.size(); ++i)
+    if ((size_t)strips[i].n != i)
+      ThrowRDE("Strips validation issue.");
+}
+
+// decompress (:152-168): rows in parallel on the device
+void PhaseOneDecompressor::decompress() const {
+  // one contiguous input window that covers every strip
+  const uint8_t* lo = nullptr;
+  const uint8_t* hi = nullptr;
+  for (const PhaseOneStrip& s : strips) {
+    const uint8_t* b = s.bs.begin() + s.bs.getPosition();
+    const uint8_t* e = b + s.bs.getRemainSize();
+    lo = (!lo || b < lo) ? b : lo;
+    hi = (!hi || e > hi) ? e : hi;
+  }
+  std::vector<rsb200_phaseone_strip> st(strips.size());
+  for (size_t i = 0; i < strips.size(); ++i) {
+    const uint8_t* b = strips[i].bs.begin() + strips[i].bs.getPosition();
+    st[i].in_offset = (uint64_t)(b - lo);
+    st[i].in_size = strips[i].bs.getRemainSize();
+    st[i].row = (uint32_t)strips[i].n;
+  }
+  rsb200_phaseone_job job;
+  std::memset(&job, 0, sizeof job);
+  job.out_offset = 0;
+  job.out_pitch = (uint32_t)mRaw->pitch;
+  job.width = (uint32_t)mRaw->dim.x;
+  job.height = (uint32_t)mRaw->dim.y;
+  job.first_strip = 0;
+  PlanGuard pg;
+  engineCheck(rsb200_phaseone_plan_create(engine(), &job, 1, st.data(), (int)st.size(), &pg.p),
+              "rsb200_phaseone_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, lo, (size_t)(hi - lo), img, /*partial=*/true);
+  rsb200_scan_result res;
+  const int rc = rsb200_plan_results(pg.p, &res, 1);
+  if (rc == RSB200_OK)
+    return;
+  if (res.status == RSB200_ERR_RDE)
+    ThrowRDE("Too many errors encountered. Giving up. First Error:\n"
+             "a Phase One row cannot be decoded (lengths / bit stream)");
+  engineCheck(rc, "rsb200_plan_results");
+}
+
 // ------------------------------------------------------------------ Sony ARW2
 // SonyArw2Decompressor ctor (decompressors/SonyArw2Decompressor.cpp:41-56)
 SonyArw2Decompressor::SonyArw2Decompressor(RawImage img, ByteStream input_)

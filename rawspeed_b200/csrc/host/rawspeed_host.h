@@ -530,6 +530,26 @@ private:
   ByteStream input;
 };
 
+// ---------------------------------------------------------------- Phase One
+// decompressors/PhaseOneDecompressor.h: one strip per image row.
+struct PhaseOneStrip final {
+  int n = 0;
+  ByteStream bs;
+  PhaseOneStrip() = default;
+  PhaseOneStrip(int block, ByteStream bs_) : n(block), bs(bs_) {}
+};
+
+class PhaseOneDecompressor final {
+public:
+  PhaseOneDecompressor(RawImage img, std::vector<PhaseOneStrip>&& strips_);
+  void decompress() const;
+
+private:
+  void prepareStrips();
+  RawImage mRaw;
+  std::vector<PhaseOneStrip> strips;
+};
+
 // ---------------------------------------------------------------- Sony ARW2
 // decompressors/SonyArw2Decompressor.h: same constructor (image + the byte stream,
 // one byte per pixel) and decompress().  The image's table (RawImageData::setTable,

@@ -12,6 +12,7 @@
 #include "sraw.cuh"
 #include "arw2.cuh"
 #include "pana.cuh"
+#include "phaseone.cuh"
 #include "pentax.cuh"
 #include "nikon.cuh"
 #include "unpack.cuh"
@@ -102,7 +103,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -116,6 +117,10 @@ struct rsb200_plan {
   uint16_t* d_raw_tables = nullptr;
   std::vector<SrawGroup> sraw_groups;
   std::vector<PanaGroup> pana_groups;
+  // Phase One (shares d_arw2_bad / h_arw2_bad as the per-job error flags)
+  P1StripDev* d_p1_strips = nullptr;
+  P1JobDev* d_p1_jobs = nullptr;
+  uint32_t p1_nstrips = 0;
   // Sony ARW2
   Arw2JobDev* d_arw2_jobs = nullptr;
   uint16_t* d_arw2_tables = nullptr;
@@ -594,6 +599,91 @@ extern "C" int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* j
   p->launches_per_run = (int)p->sraw_groups.size();
   *out = p;
   return RSB200_OK;
+}
+
+// ------------------------------------------------------------------
+// Phase One (K8)
+// ------------------------------------------------------------------
+extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseone_job* jobs,
+                                           int njobs, const rsb200_phaseone_strip* strips,
+                                           int nstrips, rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !strips || nstrips <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "phaseone_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  p->kind = 6;
+  p->nunits = njobs;
+  std::vector<P1JobDev> dj((size_t)njobs);
+  std::vector<P1StripDev> ds;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_phaseone_job& j = jobs[i];
+    // PhaseOneDecompressor ctor + prepareStrips (PhaseOneDecompressor.cpp:42-83)
+    bool ok = j.width > 0 && j.height > 0 && j.width % 2 == 0 && j.width <= 11976 &&
+              j.height <= 8854 && (j.out_offset % 4) == 0 && (j.out_pitch % 4) == 0 &&
+              (uint64_t)j.width * 2 <= j.out_pitch &&
+              (uint64_t)j.first_strip + j.height <= (uint64_t)nstrips;
+    std::vector<uint8_t> seen(ok ? j.height : 0, 0);
+    for (uint32_t k = 0; ok && k < j.height; ++k) {
+      const rsb200_phaseone_strip& st = strips[j.first_strip + k];
+      ok = st.row < j.height && !seen[st.row];
+      if (ok) {
+        seen[st.row] = 1;
+        P1StripDev d;
+        d.in_offset = st.in_offset;
+        d.in_size = st.in_size;
+        d.row = st.row;
+        d.job = (uint32_t)i;
+        d.pad = 0;
+        ds.push_back(d);
+        p->in_bytes += st.in_size;
+        p->need_in = std::max<uint64_t>(p->need_in, st.in_offset + st.in_size);
+      }
+    }
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "phaseone job %d: malformed descriptor or strips", i);
+    }
+    dj[(size_t)i].out_offset = j.out_offset;
+    dj[(size_t)i].out_pitch = j.out_pitch;
+    dj[(size_t)i].width = j.width;
+    p->out_bytes += (uint64_t)j.width * j.height * 2;
+    p->pixels += (uint64_t)j.width * j.height;
+    p->need_out = std::max<uint64_t>(p->need_out, j.out_offset +
+                                                      (uint64_t)(j.height - 1) * j.out_pitch +
+                                                      2ull * j.width);
+  }
+  p->p1_nstrips = (uint32_t)ds.size();
+  cudaError_t e = cudaMalloc((void**)&p->d_p1_strips, sizeof(P1StripDev) * ds.size());
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->d_p1_strips, ds.data(), sizeof(P1StripDev) * ds.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMalloc((void**)&p->d_p1_jobs, sizeof(P1JobDev) * dj.size());
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->d_p1_jobs, dj.data(), sizeof(P1JobDev) * dj.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMalloc((void**)&p->d_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
+  if (e == cudaSuccess)
+    e = cudaMallocHost((void**)&p->h_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
+  if (e != cudaSuccess) {
+    rsb200_plan_destroy(p);
+    return set_err(ctx, RSB200_ERR_CUDA, "phaseone plan upload failed: %s", cudaGetErrorString(e));
+  }
+  p->launches_per_run = 1;
+  *out = p;
+  return RSB200_OK;
+}
+
+static cudaError_t run_phaseone(const rsb200_plan* p, const uint8_t* in, uint8_t* outp,
+                                cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(p->d_arw2_bad, 0, sizeof(uint32_t) * (size_t)p->nunits, st);
+  if (e != cudaSuccess)
+    return e;
+  p1_kernel<<<(p->p1_nstrips + P1_NT - 1) / P1_NT, P1_NT, 0, st>>>(
+      in, outp, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs, p->d_arw2_bad);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------
@@ -1531,6 +1621,9 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->kind == 6) {
+    CUDA_TRY(ctx, run_phaseone(p, in, outp, st));
+    ctx->launches++;
   } else if (p->kind == 5) {
     for (const PanaGroup& g : p->pana_groups) {
       CUDA_TRY(ctx, run_pana_group(g, in, outp, st));
@@ -1736,7 +1829,7 @@ extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, 
   rsb200_ctx* ctx = p->ctx;
   if (!p->ran)
     return set_err(ctx, RSB200_ERR_ARG, "plan_results: plan has not been run");
-  if (p->kind == 4) {
+  if (p->kind == 4 || p->kind == 6) {
     CUDA_TRY(ctx, cudaMemcpyAsync(p->h_arw2_bad, p->d_arw2_bad, sizeof(uint32_t) * (size_t)p->nunits,
                                   cudaMemcpyDeviceToHost, p->last_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
@@ -1749,8 +1842,11 @@ extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, 
       }
       if (bad && first == RSB200_OK) {
         first = RSB200_ERR_RDE;
-        set_err(ctx, first, "Too many errors encountered. Giving up. First Error:\n"
-                            "ARW2 invariant failed, same pixel is both min and max");
+        set_err(ctx, first, p->kind == 4
+                                ? "Too many errors encountered. Giving up. First Error:\n"
+                                  "ARW2 invariant failed, same pixel is both min and max"
+                                : "Too many errors encountered. Giving up. First Error:\n"
+                                  "a Phase One row cannot be decoded (lengths / bit stream)");
       }
     }
     return first;
@@ -1831,6 +1927,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     cudaFree(g.d_jobs);
   for (PanaGroup& g : p->pana_groups)
     cudaFree(g.d_jobs);
+  cudaFree(p->d_p1_strips);
+  cudaFree(p->d_p1_jobs);
   cudaFree(p->d_nikon_luts);
   cudaFree(p->d_arw2_jobs);
   cudaFree(p->d_arw2_tables);

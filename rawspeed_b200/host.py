@@ -178,6 +178,24 @@ def panasonic(version, img, w, data, bps=14):
     return img
 
 
+def phaseone(img, w, file, strips):
+    """PhaseOneDecompressor(img, strips).decompress() via the host mirror; strips:
+    [(offset, size, row)] into `file`."""
+    p, n = _u8(file)
+    ns = len(strips)
+    off = (C.c_uint64 * ns)(*[s[0] for s in strips])
+    ln = (C.c_uint32 * ns)(*[s[1] for s in strips])
+    rown = (C.c_int32 * ns)(*[s[2] for s in strips])
+    e = _Err()
+    L = lib()
+    L.rsb200h_phaseone.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_uint64,
+                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_int32), C.c_int, C.POINTER(_Err)]
+    e.check(L.rsb200h_phaseone(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2, p,
+                               C.c_uint64(n), off, ln, rown, ns, C.byref(e)))
+    return img
+
+
 def sony_arw2(img, w, data, curve=None, dither=False):
     """SonyArw2Decompressor(img, data).decompress() via the host mirror; curve:
     img->setTable(curve, dither) first."""
