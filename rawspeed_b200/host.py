@@ -28,7 +28,9 @@ class _Huff(C.Structure):
 
 EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_dng_decompress", "rsb200h_cr2_decompress", "rsb200h_cr2_ljpeg_decode",
-           "rsb200h_huff_check"]
+           "rsb200h_huff_check", "rsb200h_unpack_form", "rsb200h_pentax_decompress",
+           "rsb200h_sraw_interpolate", "rsb200h_nikon_decompress", "rsb200h_sony_arw2",
+           "rsb200h_panasonic", "rsb200h_phaseone"]
 
 _lib = None
 

@@ -85,3 +85,39 @@ def test_cr2_ctor_errors_same_class():
     for slicing in [(2, 31, 33), (2, 32, 16), (2, 32, 48), (1, 0, 62)]:
         _same_class(lambda: port.cr2_ljpeg_decode(blob, port.new_image(w, h), w, slicing),
                     lambda: host.cr2_ljpeg_decode(blob, port.new_image(w, h), w, slicing))
+
+
+def test_vendor_codec_ctor_errors_same_class():
+    """Constructors of the vendor codec mirrors (Nikon, Sony ARW2, Panasonic V5/V6/V7, Phase
+    One) reject what the reference rejects, with the same exception class, before any GPU work."""
+    # Nikon: odd width, bad bit depth, truncated maker note, bad curve segment count
+    w, h = 64, 8
+    meta = synth.nikon_meta("table", 12)
+    data = synth.lcg_bytes(256, 3)
+    for args in [(63, h, meta, 12), (w, h, meta, 13), (w, h, meta[:9], 12)]:
+        ww, hh, m, bits = args
+        _same_class(lambda: port.nikon_decompress(port.new_image(ww, hh), ww, m, True, bits, data),
+                    lambda: host.nikon_decompress(port.new_image(ww, hh), ww, m, True, bits, data))
+    bad = bytearray(synth.nikon_meta("segments", 12))
+    bad[10:12] = bytes([0, 30])
+    _same_class(lambda: port.nikon_decompress(port.new_image(w, h), w, bytes(bad), True, 12, data),
+                lambda: host.nikon_decompress(port.new_image(w, h), w, bytes(bad), True, 12, data))
+    # Sony ARW2: width not a multiple of 32, not enough data
+    a = synth.arw2_frame(64, 4, seed=1)
+    _same_class(lambda: port.sony_arw2(port.new_image(48, 2), 48, a),
+                lambda: host.sony_arw2(port.new_image(48, 2), 48, a))
+    _same_class(lambda: port.sony_arw2(port.new_image(64, 4), 64, a[:-1]),
+                lambda: host.sony_arw2(port.new_image(64, 4), 64, a[:-1]))
+    # Panasonic: width not a multiple of the unit, unsupported bps, too few blocks
+    blob = synth.lcg_bytes(0x8000, 1)
+    for ver, bps, ww in [(5, 12, 41), (5, 13, 40), (6, 12, 27), (6, 16, 28), (7, 14, 20)]:
+        _same_class(lambda: port.panasonic(ver, port.new_image(ww, 2), ww, blob, bps),
+                    lambda: host.panasonic(ver, port.new_image(ww, 2), ww, blob, bps))
+    _same_class(lambda: port.panasonic(7, port.new_image(18, 2), 18, blob[:63], 14),
+                lambda: host.panasonic(7, port.new_image(18, 2), 18, blob[:63], 14))
+    # Phase One: strip count, a row twice, odd width
+    img = synth.image_model(16, 4, seed=2)
+    pb, strips = synth.make_phaseone(img)
+    for ww, st in [(16, strips[:-1]), (16, strips[:-1] + [strips[0]]), (15, strips)]:
+        _same_class(lambda: port.phaseone(port.new_image(ww, 4), ww, pb, st),
+                    lambda: host.phaseone(port.new_image(ww, 4), ww, pb, st))
