@@ -681,8 +681,18 @@ static cudaError_t run_phaseone(const rsb200_plan* p, const uint8_t* in, uint8_t
   cudaError_t e = cudaMemsetAsync(p->d_arw2_bad, 0, sizeof(uint32_t) * (size_t)p->nunits, st);
   if (e != cudaSuccess)
     return e;
-  p1_kernel<<<(p->p1_nstrips + P1_NT - 1) / P1_NT, P1_NT, 0, st>>>(
-      in, outp, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs, p->d_arw2_bad);
+  // RSB200_P1=1 selects the first version (per-lane refills) for A/B runs
+  static const bool v1 = [] {
+    const char* e = getenv("RSB200_P1");
+    return e && e[0] == '1';
+  }();
+  const uint32_t nb = (p->p1_nstrips + P1_NT - 1) / P1_NT;
+  if (v1)
+    p1_kernel<<<nb, P1_NT, 0, st>>>(in, outp, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs,
+                                    p->d_arw2_bad);
+  else
+    p1_kernel_v2<<<nb, P1_NT, 0, st>>>(in, outp, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs,
+                                       p->d_arw2_bad);
   return cudaGetLastError();
 }
 
