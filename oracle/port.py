@@ -295,6 +295,22 @@ def _strips(strips):
     return off, ln, rown, n
 
 
+def hasselblad_decompress(img, w, ht, init_pred, data):
+    """HasselbladDecompressor(img, {ht, init_pred}, data).decompress() into img; returns the
+    stream position.  ht: Huff(ncpl, values, full=False)."""
+    p, n = _u8(data)
+    im = _img(img, w, 1)
+    consumed = C.c_uint32(0)
+    e = Err()
+    L = lib()
+    L.rso_hasselblad_decompress.argtypes = [C.POINTER(Image), C.c_void_p, C.c_uint16, C.c_char_p,
+                                            C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(Err)]
+    rc = L.rso_hasselblad_decompress(C.byref(im), ht.h, init_pred, p, C.c_uint32(n),
+                                     C.byref(consumed), C.byref(e))
+    e.check(rc)
+    return consumed.value
+
+
 def phaseone(img, w, file, strips):
     """PhaseOneDecompressor(img, strips).decompress(); strips: [(offset, size, row)]."""
     p, n = _u8(file)

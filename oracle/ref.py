@@ -215,6 +215,25 @@ def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False, reps=
     return ms.value
 
 
+def hasselblad_decompress(img, w, ncpl, values, full, init_pred, data):
+    """Reference HasselbladDecompressor (ref_hasselblad_decompress); returns the stream position."""
+    p, n = _u8(data)
+    consumed = C.c_uint32(0)
+    ms = C.c_double(0)
+    e = Err()
+    L = lib()
+    L.ref_hasselblad_decompress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                            C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                            C.c_uint32, C.POINTER(C.c_uint32), C.c_int,
+                                            C.POINTER(C.c_double), C.POINTER(Err)]
+    rc = L.ref_hasselblad_decompress(C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                     img.shape[1] * 2, bytes(ncpl), bytes(values), len(values),
+                                     int(full), init_pred, p, C.c_uint32(n), C.byref(consumed), 1,
+                                     C.byref(ms), C.byref(e))
+    e.check(rc)
+    return consumed.value
+
+
 def phaseone(img, w, file, strips, nthreads=1, reps=1):
     """Reference PhaseOneDecompressor (ref_phaseone); strips: [(offset, size, row)]."""
     from .port import _strips

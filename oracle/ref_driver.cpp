@@ -43,6 +43,7 @@
 #include "decompressors/PentaxDecompressor.h"
 #include "decompressors/SonyArw2Decompressor.h"
 #include "decompressors/NikonDecompressor.h"
+#include "decompressors/HasselbladDecompressor.h"
 #include "decompressors/PhaseOneDecompressor.h"
 #include "decompressors/PanasonicV5Decompressor.h"
 #include "decompressors/PanasonicV6Decompressor.h"
@@ -302,6 +303,33 @@ int ref_unpack_form(const uint8_t* in, uint32_t in_size, void* img_data, int is_
     for (int r = 0; r < h; ++r)
       std::memcpy(static_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, rowPtr(r),
                   static_cast<size_t>(w) * bpp);
+  });
+}
+
+// HasselbladDecompressor(mRaw, {ht, initPred}, input).decompress(); the table is set up
+// as a code-value table (full = false), as HasselbladLJpegDecoder::decode arranges.
+int ref_hasselblad_decompress(uint16_t* img_data, int w, int h, int pitch, const uint8_t* ncpl,
+                              const uint8_t* values, int nvalues, int full, int init_pred,
+                              const uint8_t* data, uint32_t size, uint32_t* consumed, int reps,
+                              double* best_ms, RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, 1, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    const PrefixCodeDecoder<> ht = makeHT(ncpl, values, nvalues, full, 0);
+    const HasselbladDecompressor::PerComponentRecipe rec = {ht, static_cast<uint16_t>(init_pred)};
+    double best = 1e30;
+    for (int r = 0; r < (reps < 1 ? 1 : reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      HasselbladDecompressor d(img, rec, Array1DRef<const uint8_t>(data, static_cast<int>(size)));
+      const auto c = d.decompress();
+      const auto t1 = std::chrono::steady_clock::now();
+      best = std::min(best, std::chrono::duration<double, std::milli>(t1 - t0).count());
+      if (consumed)
+        *consumed = c;
+    }
+    if (best_ms)
+      *best_ms = best;
+    copyOut(img, img_data, pitch);
   });
 }
 

@@ -3015,3 +3015,62 @@ int rso_phaseone(rso_image* img, const uint8_t* file, uint64_t file_size, const 
     THROW_RDE(&c, "Too many errors encountered. Giving up. First Error:\n%s", first);
   return RSO_OK;
 }
+
+/* ------------------------------------------------------------------
+ * HasselbladDecompressor (decompressors/HasselbladDecompressor.cpp)
+ * ------------------------------------------------------------------ */
+/* HasselbladDecompressor::getBits (:60-70) */
+static int hassel_bits(pump* bs, int len) {
+  int diff;
+  if (!len)
+    return 0;
+  diff = (int)pump_get_bits(bs, len);
+  diff = rso_huff_extend((uint32_t)diff, (uint32_t)len);
+  if (diff == 65535)
+    return -32768;
+  return diff;
+}
+
+int rso_hasselblad_decompress(rso_image* img, const rso_huff* ht, uint16_t init_pred,
+                              const uint8_t* in, uint32_t in_size, uint32_t* consumed,
+                              rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  pump bs;
+  int row, col, k;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb))
+    return c.e->code;
+  /* ctor (:39-58) */
+  if (img->is_f32)
+    THROW_RDE(&c, "Unexpected data type");
+  if (img->cpp != 1)
+    THROW_RDE(&c, "Unexpected cpp: %u", (unsigned)img->cpp);
+  if (!(img->w > 0 && img->h > 0) || img->w % 2 != 0 || img->w > 12000 || img->h > 8842)
+    THROW_RDE(&c, "Unexpected image dimensions found: (%d; %d)", img->w, img->h);
+  if (ht->full)
+    THROW_RDE(&c, "Huffman table is of a full decoding variety");
+  /* ht.verifyCodeValuesAsDiffLengths() (codes/AbstractPrefixCode.h): every value <= 16 */
+  for (k = 0; k < ht->nsym; k++)
+    if (ht->val[k] > 16)
+      THROW_RDE(&c, "Corrupt Huffman code: difference length %u longer than 16", (unsigned)ht->val[k]);
+  /* decompress (:72-100) */
+  pump_init(&bs, &c, RSO_MSB32, in, (int)in_size);
+  for (row = 0; row < img->h; row++) {
+    uint16_t* o = (uint16_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch);
+    int p1 = init_pred, p2 = init_pred;
+    for (col = 0; col < img->w; col += 2) {
+      const int len1 = huff_decode(ht, &bs, 0);
+      const int len2 = huff_decode(ht, &bs, 0);
+      p1 += hassel_bits(&bs, len1);
+      p2 += hassel_bits(&bs, len2);
+      o[col] = (uint16_t)p1;
+      o[col + 1] = (uint16_t)p2;
+    }
+  }
+  if (consumed)
+    *consumed = (uint32_t)pump_stream_position(&bs);
+  return RSO_OK;
+}

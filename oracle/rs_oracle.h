@@ -185,6 +185,16 @@ int rso_nikon_tree(int sel, uint8_t* ncpl, uint8_t* values);
 int rso_panasonic(int version, rso_image* img, const uint8_t* data, uint32_t size, int bps,
                   rso_err* e);
 
+/* ---- HasselbladDecompressor (decompressors/HasselbladDecompressor.cpp:39-100) ----
+ * (groundwork for the next "next" row: restated and pinned, no device kernel yet)
+ * One MSB32 bit stream per image; pixels are packed two at a time:
+ * [len1 code][len2 code][len1 bits][len2 bits]; `ht` must be a code-value table (built with
+ * full = 0); each row starts from init_pred for both pixels of a pair; values are stored
+ * truncated to 16 bits.  *consumed = BitStreamerMSB32::getStreamPosition(). */
+int rso_hasselblad_decompress(rso_image* img, const rso_huff* ht, uint16_t init_pred,
+                              const uint8_t* in, uint32_t in_size, uint32_t* consumed,
+                              rso_err* e);
+
 /* ---- PhaseOneDecompressor (decompressors/PhaseOneDecompressor.cpp:42-168) ----
  * One strip per image row (any order; strip k = bytes [off[k], off[k]+len[k]) of `file`,
  * decoding row rown[k]); a row is an MSB32 bit stream: every 8 pixels two code lengths

@@ -323,3 +323,47 @@ def make_phaseone(img, shuffle_seed=None, gap=0):
         strips.append((len(blob), len(rows[r]), r))
         blob += rows[r]
     return np.frombuffer(bytes(blob), dtype=np.uint8).copy(), strips
+
+
+def make_hasselblad(img, ht, init_pred):
+    """Encode a uint16 image (even width) the way HasselbladDecompressor reads it
+    (HasselbladDecompressor.cpp:72-100): one MSB32 bit stream, per pixel pair
+    [len1 code][len2 code][len1 bits][len2 bits], both predictors reset to init_pred at
+    every row.  ht: port.Huff over difference lengths 0..16 (any mode; only its codes are
+    used).  Returns bytes (multiple of 4, + 16 bytes slack)."""
+    codes = {v: cl for v, cl in zip(ht.values, ht.symbols())}
+    bits = []
+
+    def put(v, n):
+        for k in range(n - 1, -1, -1):
+            bits.append((v >> k) & 1)
+
+    def cat(d):
+        """(length, bits) of difference d (T.81 F.12 inverse; -32768 = length 16, all ones)"""
+        if d == 0:
+            return 0, 0
+        if d == -32768:
+            return 16, 0xFFFF
+        n = abs(d).bit_length()
+        return n, (d if d > 0 else d + (1 << n) - 1)
+
+    h, w = img.shape
+    for r in range(h):
+        p = [init_pred, init_pred]
+        for c in range(0, w, 2):
+            enc = []
+            for t in (0, 1):
+                d = (int(img[r, c + t]) - p[t] + 32768) % 65536 - 32768   # difference mod 2^16
+                enc.append(cat(d))
+                p[t] = int(img[r, c + t])
+            for n, _ in enc:
+                code, cl = codes[n]
+                put(code, cl)
+            for n, b in enc:
+                if n:
+                    put(b, n)
+    while len(bits) % 32:
+        bits.append(0)
+    a = np.array(bits, dtype=np.uint8).reshape(-1, 32)
+    words = (a.astype(np.uint64) << np.arange(31, -1, -1, dtype=np.uint64)).sum(axis=1).astype("<u4")
+    return np.frombuffer(words.tobytes() + bytes(16), dtype=np.uint8).copy()
