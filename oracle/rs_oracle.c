@@ -2664,6 +2664,168 @@ int rso_nikon_setup(const uint8_t* meta, int meta_size, int meta_be, int bitsPS,
   return RSO_OK;
 }
 
+/* NikonLASDecompressor (NikonDecompressor.cpp:80-378): the "lossy after split" decoder.
+ * Its own table builder (T.81 C.1/C.2/F.15 without HuffmanCode's validation), an 8-bit and a
+ * 14-bit lookup, and a difference format where a code value packs (len | shl << 4). */
+typedef struct {
+  uint32_t bits[17];
+  uint32_t huffval[256];
+  uint16_t mincode[17];
+  int maxcode[18];
+  int16_t valptr[17];
+  uint32_t numbits[256];
+  int bigTable[1 << 14];
+} nikon_las;
+
+static void las_create(rso_ctx* c, nikon_las* t, const uint8_t* ncpl, const uint8_t* values,
+                       int nvalues) {
+  int p, i, l, lastp, si, size, value, ll, ul;
+  int8_t huffsize[257];
+  uint16_t huffcode[257], code;
+  memset(t, 0, sizeof *t);
+  for (i = 0; i < 16; i++)
+    t->bits[i + 1] = ncpl[i];
+  for (i = 0; i < nvalues; i++)
+    t->huffval[i] = values[i];
+  /* createPrefixCodeDecoder (:112-210) */
+  p = 0;
+  for (l = 1; l <= 16; l++)
+    for (i = 1; i <= (int)t->bits[l]; i++) {
+      huffsize[p++] = (int8_t)l;
+      if (p > 256)
+        THROW_RDE(c, "LJpegDecoder::createPrefixCodeDecoder: Code length too long. Corrupt data.");
+    }
+  huffsize[p] = 0;
+  lastp = p;
+  code = 0;
+  si = huffsize[0];
+  p = 0;
+  while (huffsize[p]) {
+    while ((int)huffsize[p] == si) {
+      huffcode[p++] = code;
+      code++;
+    }
+    code = (uint16_t)(code << 1);
+    si++;
+    if (p > 256)
+      THROW_RDE(c, "createPrefixCodeDecoder: Code length too long. Corrupt data.");
+  }
+  t->mincode[0] = 0;
+  t->maxcode[0] = 0;
+  p = 0;
+  for (l = 1; l <= 16; l++) {
+    if (t->bits[l]) {
+      t->valptr[l] = (int16_t)p;
+      t->mincode[l] = huffcode[p];
+      p += (int)t->bits[l];
+      t->maxcode[l] = huffcode[p - 1];
+    } else {
+      t->valptr[l] = 0xff;
+      t->maxcode[l] = -1;
+    }
+    if (p > 256)
+      THROW_RDE(c, "createPrefixCodeDecoder: Code length too long. Corrupt data.");
+  }
+  t->maxcode[17] = 0xFFFFF;
+  for (p = 0; p < lastp; p++) {
+    size = huffsize[p];
+    if (size <= 8) {
+      value = (int)t->huffval[p];
+      code = huffcode[p];
+      ll = code << (8 - size);
+      ul = size < 8 ? (ll | (int)(0xffffffffu >> (24 + size))) : ll; /* bitMask[24 + size] */
+      if (ul > 256 || ll > ul)
+        THROW_RDE(c, "createPrefixCodeDecoder: Code length too long. Corrupt data.");
+      for (i = ll; i <= ul; i++)
+        t->numbits[i] = (uint32_t)(size | (value << 4));
+    }
+  }
+  /* createBigTable (:224-283), bits = 14 */
+  for (i = 0; i < (1 << 14); i++) {
+    const uint16_t input = (uint16_t)(i << 2);
+    int cd = input >> 8, rv, x;
+    uint32_t val = t->numbits[cd];
+    uint32_t ln = val & 15;
+    if (ln) {
+      rv = (int)(val >> 4);
+    } else {
+      ln = 8;
+      while (cd > t->maxcode[ln]) {
+        /* extractHighBits(input, ln, effectiveBitwidth = 15) & 1 */
+        const int temp = (input >> (15 - ln)) & 1;
+        cd = (cd << 1) | temp;
+        ln++;
+      }
+      if (ln > 16 || t->valptr[ln] == 0xff) {
+        t->bigTable[i] = 0xff;
+        continue;
+      }
+      rv = (int)t->huffval[t->valptr[ln] + (cd - t->mincode[ln])];
+    }
+    if (rv == 16) {
+      t->bigTable[i] = (-(32768 << 8)) | (int)ln;
+      continue;
+    }
+    if (rv + (int)ln > 14) {
+      t->bigTable[i] = 0xff;
+      continue;
+    }
+    if (rv) {
+      /* extractHighBits(input, ln + rv) of the 16-bit input */
+      x = (input >> (16 - (ln + (uint32_t)rv))) & ((1 << rv) - 1);
+      if ((x & (1 << (rv - 1))) == 0)
+        x -= (1 << rv) - 1;
+      t->bigTable[i] = (int)(((unsigned)x << 8) | (ln + (uint32_t)rv));
+    } else {
+      t->bigTable[i] = (int)ln;
+    }
+  }
+}
+
+/* NikonLASDecompressor::decodeDifference (:315-377) */
+static int las_decode(const nikon_las* t, pump* bs) {
+  int rv, l, code;
+  unsigned val;
+  uint32_t len, shl, nb;
+  int diff;
+  pump_fill(bs, 32);
+  code = (int)pump_peek_nofill(bs, 14);
+  val = (unsigned)t->bigTable[code];
+  if ((val & 0xff) != 0xff) {
+    pump_skip_nofill(bs, (int)(val & 0xff));
+    return (int)val >> 8;
+  }
+  rv = 0;
+  code = (int)pump_peek_nofill(bs, 8);
+  val = t->numbits[code];
+  l = (int)(val & 15);
+  if (l) {
+    pump_skip_nofill(bs, l);
+    rv = (int)val >> 4;
+  } else {
+    pump_skip_nofill(bs, 8);
+    l = 8;
+    while (code > t->maxcode[l]) {
+      const int temp = (int)pump_get_nofill(bs, 1);
+      code = (code << 1) | temp;
+      l++;
+    }
+    if (l > 16)
+      THROW_RDE(bs->c, "Corrupt JPEG data: bad Huffman code:%d\n", l);
+    rv = (int)t->huffval[t->valptr[l] + (code - t->mincode[l])];
+  }
+  if (rv == 16)
+    return -32768;
+  len = (uint32_t)rv & 15;
+  shl = (uint32_t)rv >> 4;
+  nb = len - shl;
+  /* (bits.getBits(0) is not defined in the reference; real tables never get here with nb == 0) */
+  diff = (int)(((((nb ? pump_get_bits(bs, (int)nb) : 0u) << 1) + 1) << shl) >> 1);
+  if ((diff & (1 << (len - 1))) == 0)
+    diff -= (1 << len) - !shl;
+  return diff;
+}
+
 int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int meta_be,
                          int bitsPS, const uint8_t* data, uint32_t size, int uncorrected,
                          rso_err* e) {
@@ -2672,9 +2834,10 @@ int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int
   nikon_setup* volatile s = NULL;
   rso_huff* volatile h = NULL;
   uint16_t* volatile tab = NULL; /* dithered TableLookUp storage: {base, delta} per value */
+  nikon_las* volatile las = NULL;
   pump bs;
   uint8_t ncpl[16], values[16];
-  int nv, row, col;
+  int nv, row, col, split;
   uint32_t random, i;
   c.e = e ? e : &le;
   c.e->code = RSO_OK;
@@ -2683,6 +2846,7 @@ int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int
     free((void*)s);
     free((void*)h);
     free((void*)tab);
+    free((void*)las);
     return c.e->code;
   }
   if (img->cpp != 1 || img->is_f32)
@@ -2693,8 +2857,6 @@ int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int
     THROW_RDE(&c, "out of memory");
   nikon_setup_impl(&c, meta, meta_size, meta_be, (uint32_t)bitsPS, img->w, img->h,
                    (nikon_setup*)s);
-  if (((nikon_setup*)s)->split != 0)
-    THROW_RDE(&c, "split"); /* (the second, "lossy after split" decoder is not restated) */
   /* RawImageCurveGuard + TableLookUp::setTable(curve, dither = true) (TableLookUp.cpp:49-84) */
   if (!uncorrected) {
     const uint16_t* cv = ((nikon_setup*)s)->curve;
@@ -2721,6 +2883,15 @@ int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int
   }
   nv = rso_nikon_tree((int)((nikon_setup*)s)->huffSelect, ncpl, values);
   huff_build(&c, (rso_huff*)h, ncpl, values, nv, 1, 0);
+  split = (int)((nikon_setup*)s)->split;
+  if (split) {
+    uint8_t n2[16], v2[16];
+    const int nv2 = rso_nikon_tree((int)((nikon_setup*)s)->huffSelect + 1, n2, v2);
+    las = (nikon_las*)malloc(sizeof(nikon_las));
+    if (!las || nv2 < 0)
+      THROW_RDE(&c, "out of memory");
+    las_create(&c, (nikon_las*)las, n2, v2, nv2);
+  }
   /* decompress (:540-560, :513-538) */
   pump_init(&bs, &c, RSO_MSB, data, (int)size);
   pump_fill(&bs, 24);
@@ -2734,7 +2905,10 @@ int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int
     for (col = 0; col < img->w; col++) {
       int v;
       uint16_t value;
-      pred[col & 1] += huff_decode((const rso_huff*)h, &bs, 1);
+      /* rows below the split: nikon_tree[huffSelect] through PrefixCodeDecoder<>; from the
+       * split on: nikon_tree[huffSelect + 1] through NikonLASDecompressor (:549-556) */
+      pred[col & 1] += (split == 0 || row < split) ? huff_decode((const rso_huff*)h, &bs, 1)
+                                                   : las_decode((const nikon_las*)las, &bs);
       if (col < 2)
         pUp[row & 1][col & 1] = pred[col & 1];
       v = pred[col & 1]; /* clampBits(v, 15) */
@@ -2753,6 +2927,7 @@ int rso_nikon_decompress(rso_image* img, const uint8_t* meta, int meta_size, int
   free((void*)s);
   free((void*)h);
   free((void*)tab);
+  free((void*)las);
   return RSO_OK;
 }
 

@@ -161,8 +161,9 @@ int64_t rso_encode_diffs_plain(const int32_t* diffs, uint64_t n, const rso_huff*
  * the first two pixels of every row), clampBits(value, 15), setWithLookUp with the
  * curve as a DITHERED table (RawImageCurveGuard) unless uncorrected != 0; the dither
  * state is seeded ONCE with the first 24 bits of the stream.
- * Restated for split == 0 (no "lossy after split" second table, NikonLASDecompressor
- * :80-378); a non-zero split returns RSO_RDE with the message "split".
+ * With a non-zero split the rows from `split` on are decoded with nikon_tree[huffSelect+1]
+ * through the restated NikonLASDecompressor (:80-378: own table builder, 8/14-bit lookups,
+ * (len | shl << 4) difference format).
  * Outputs (may be NULL): curve[<= 32769] + *ncurve, pup[4] = pUp[0][0], pUp[0][1],
  * pUp[1][0], pUp[1][1], *huff_select, *split. */
 int rso_nikon_setup(const uint8_t* meta, int meta_size, int meta_be, int bitsPS, int img_w,

@@ -367,3 +367,61 @@ def make_hasselblad(img, ht, init_pred):
     a = np.array(bits, dtype=np.uint8).reshape(-1, 32)
     words = (a.astype(np.uint64) << np.arange(31, -1, -1, dtype=np.uint64)).sum(axis=1).astype("<u4")
     return np.frombuffer(words.tobytes() + bytes(16), dtype=np.uint8).copy()
+
+
+def _canonical(ncpl, values):
+    """value -> (code, length) by T.81 C.1/C.2 (the first occurrence of a value wins)."""
+    out, code, k = {}, 0, 0
+    for ln in range(1, 17):
+        for _ in range(ncpl[ln - 1]):
+            out.setdefault(values[k], (code, ln))
+            code += 1
+            k += 1
+        code <<= 1
+    return out
+
+
+def make_nikon_split(img_top, sel, pup, rows_after, seed):
+    """A Nikon stream WITH a split: rows of `img_top` coded with nikon_tree[sel] like
+    make_nikon, then `rows_after` rows of random symbols of nikon_tree[sel + 1] in the
+    NikonLASDecompressor format (code, then len - shl bits; NikonDecompressor.cpp:315-377).
+    Differential-fuzz input: the second part is not the encoding of a chosen image."""
+    h, w = img_top.shape
+    t1 = _canonical(*port.nikon_tree(sel))
+    n2, v2 = port.nikon_tree(sel + 1)
+    t2 = _canonical(n2, v2)
+    bits = []
+
+    def put(v, n):
+        for k in range(n - 1, -1, -1):
+            bits.append((v >> k) & 1)
+
+    a = img_top.astype(np.int64)
+    for r in range(h):
+        for c in range(w):
+            if c >= 2:
+                p = a[r, c - 2]
+            elif r >= 2:
+                p = a[r - 2, c]
+            else:
+                p = pup[2 * r + c]
+            d = int(a[r, c] - p)
+            n = 0 if d == 0 else abs(d).bit_length()
+            code, cl = t1[n]
+            put(code, cl)
+            if n:
+                put(d if d > 0 else d + (1 << n) - 1, n)
+    rng = np.random.default_rng(seed)
+    vals = sorted(t2)
+    for _ in range(rows_after * w):
+        rv = vals[int(rng.integers(0, len(vals)))]
+        code, cl = t2[rv]
+        put(code, cl)
+        if rv != 16:
+            nb = (rv & 15) - (rv >> 4)
+            if nb > 0:
+                put(int(rng.integers(0, 1 << nb)), nb)
+    while len(bits) % 8:
+        bits.append(0)
+    by = np.packbits(np.array(bits, dtype=np.uint8))
+    return np.concatenate([by, np.zeros(16, dtype=np.uint8)])

@@ -62,3 +62,31 @@ def test_nikon_error_classes():
     for f in (port.nikon_decompress, oracle.ref.nikon_decompress):
         with pytest.raises(port.RawDecoderException):
             f(port.new_image(w, h), w, bytes(bad), True, 12, data)
+
+
+@pytest.mark.parametrize("bits", [12, 14])
+@pytest.mark.parametrize("uncorrected", [False, True])
+def test_nikon_split_streams_match_reference(bits, uncorrected):
+    """Streams with a split: the rows from `split` on go through the restated
+    NikonLASDecompressor ("lossy after split" tree, (len | shl << 4) differences)."""
+    w, h, split = 66, 24, 10
+    half = 1 << (bits - 1)
+    pup = [half, half + 2, half - 8, half - 2]
+    meta = synth.nikon_meta("segments", bits, (pup[0], pup[2], pup[1], pup[3]), True, split=split)
+    su = port.nikon_setup(meta, True, bits, w, h)
+    assert su["split"] == split and su["huff_select"] in (0, 3)
+    top = (synth.image_model(w, split, seed=bits, bits=bits) & ((1 << bits) - 1)).astype(np.uint16)
+    data = synth.make_nikon_split(top, su["huff_select"], pup, h - split, seed=bits)
+    a = port.new_image(w, h)
+    b = a.copy()
+    port.nikon_decompress(a, w, meta, True, bits, data, uncorrected)
+    oracle.ref.nikon_decompress(b, w, meta, True, bits, data, uncorrected)
+    assert np.array_equal(a, b)
+    if uncorrected:
+        assert np.array_equal(a[:split, :w], top)
+
+
+def test_nikon_split_outside_the_image_is_ignored():
+    w, h = 34, 6
+    meta = synth.nikon_meta("segments", 12, split=h)     # split >= height: no split
+    assert port.nikon_setup(meta, True, 12, w, h)["split"] == 0
