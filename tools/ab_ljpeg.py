@@ -6,8 +6,12 @@ the benchmark).
     python tools/ab_ljpeg.py one                       # (internal) time the library in RSB200_LIB
 
 Each variant is timed on: one 8256x5504 DNG frame (726 LJPEG tiles), the same frame
-with two Huffman tables (phase-carrying synchronisation), an 8-frame batch, and the
+with two Huffman tables (phase-carrying synchronisation), LJPEG batches and the
 6720x4480 CR2 stream; every output is checked bit for bit against the encoder's input.
+
+Environment: AB_FRAMES=8,32,128   batch sizes (frames of the 45 MP DNG in one plan)
+             AB_PATHS=fused,thread|auto   kernel path(s) per batch (RSB200_LJPEG_PATH)
+             AB_KERNELS=1         per-kernel durations of one run (torch profiler / CUPTI)
 """
 import json
 import os
