@@ -326,6 +326,24 @@ def phaseone(img, w, file, strips):
     return img
 
 
+def panasonic_v4(img, w, data, zero_is_not_bad=True, split=0, cap=1 << 16):
+    """PanasonicV4Decompressor(img, data, zero_is_not_bad, split).decompress(); returns the
+    sorted list of bad (zero) pixel positions (row << 16 | col)."""
+    p, n = _u8(data)
+    im = _img(img, w, 1)
+    z = (C.c_uint32 * cap)()
+    nz = C.c_uint32(0)
+    e = Err()
+    L = lib()
+    L.rso_panasonic_v4.argtypes = [C.POINTER(Image), C.c_char_p, C.c_uint32, C.c_int, C.c_uint32,
+                                   C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32),
+                                   C.POINTER(Err)]
+    rc = L.rso_panasonic_v4(C.byref(im), p, C.c_uint32(n), int(zero_is_not_bad), split, z, cap,
+                            C.byref(nz), C.byref(e))
+    e.check(rc)
+    return sorted(z[:min(nz.value, cap)])
+
+
 def panasonic(version, img, w, data, bps=14):
     """PanasonicV{5,6,7}Decompressor(img, data[, bps]).decompress() into img (in place)."""
     p, n = _u8(data)

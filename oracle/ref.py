@@ -251,6 +251,23 @@ def phaseone(img, w, file, strips, nthreads=1, reps=1):
     return ms.value
 
 
+def panasonic_v4(img, w, data, zero_is_not_bad=True, split=0, cap=1 << 16, nthreads=1):
+    """Reference PanasonicV4Decompressor (ref_panasonic_v4); returns the sorted bad-pixel list."""
+    p, n = _u8(data)
+    z = (C.c_uint32 * cap)()
+    nz = C.c_uint32(0)
+    e = Err()
+    L = lib()
+    L.ref_panasonic_v4.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_uint32,
+                                   C.c_int, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+                                   C.POINTER(C.c_uint32), C.c_int, C.POINTER(Err)]
+    rc = L.ref_panasonic_v4(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2, p,
+                            C.c_uint32(n), int(zero_is_not_bad), split, z, cap, C.byref(nz),
+                            nthreads, C.byref(e))
+    e.check(rc)
+    return list(z[:min(nz.value, cap)])
+
+
 def panasonic(version, img, w, data, bps=14, nthreads=1, reps=1):
     """Reference PanasonicV{5,6,7}Decompressor (ref_panasonic)."""
     p, n = _u8(data)

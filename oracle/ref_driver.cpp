@@ -45,6 +45,7 @@
 #include "decompressors/NikonDecompressor.h"
 #include "decompressors/HasselbladDecompressor.h"
 #include "decompressors/PhaseOneDecompressor.h"
+#include "decompressors/PanasonicV4Decompressor.h"
 #include "decompressors/PanasonicV5Decompressor.h"
 #include "decompressors/PanasonicV6Decompressor.h"
 #include "decompressors/PanasonicV7Decompressor.h"
@@ -360,6 +361,29 @@ int ref_phaseone(uint16_t* img_data, int w, int h, int pitch, const uint8_t* fil
     }
     if (best_ms)
       *best_ms = best;
+    copyOut(img, img_data, pitch);
+  });
+}
+
+// PanasonicV4Decompressor(mRaw, input, zero_is_not_bad, section_split_offset).decompress();
+// zero_pos receives mRaw->mBadPixelPositions (sorted: the threads append in any order).
+int ref_panasonic_v4(uint16_t* img_data, int w, int h, int pitch, const uint8_t* data,
+                     uint32_t size, int zero_is_not_bad, uint32_t section_split_offset,
+                     uint32_t* zero_pos, uint32_t cap, uint32_t* nzero, int nthreads,
+                     RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(w, h, 1, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    PanasonicV4Decompressor d(img, ByteStream(DataBuffer(Buffer(data, size), Endianness::little)),
+                              zero_is_not_bad != 0, section_split_offset);
+    d.decompress();
+    std::vector<uint32_t> z(img->mBadPixelPositions.begin(), img->mBadPixelPositions.end());
+    std::sort(z.begin(), z.end());
+    if (nzero)
+      *nzero = static_cast<uint32_t>(z.size());
+    for (size_t i = 0; i < z.size() && i < cap && zero_pos; ++i)
+      zero_pos[i] = z[i];
     copyOut(img, img_data, pitch);
   });
 }

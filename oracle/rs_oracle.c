@@ -3249,3 +3249,112 @@ int rso_hasselblad_decompress(rso_image* img, const rso_huff* ht, uint16_t init_
     *consumed = (uint32_t)pump_stream_position(&bs);
   return RSO_OK;
 }
+
+/* ------------------------------------------------------------------
+ * PanasonicV4Decompressor (decompressors/PanasonicV4Decompressor.cpp)
+ * ------------------------------------------------------------------ */
+typedef struct {
+  const uint8_t* buf; /* the block with its sections swapped back + one zero byte */
+  int vbits;
+} pana4_stream;
+
+/* ProxyStream::getBits (:164-168) */
+static uint32_t pana4_bits(pana4_stream* s, int nbits) {
+  int byte;
+  s->vbits = (s->vbits - nbits) & 0x1ffff;
+  byte = (s->vbits >> 3) ^ 0x3ff0;
+  return (uint32_t)((s->buf[byte] | s->buf[byte + 1] << 8) >> (s->vbits & 7)) & ~(uint32_t)(-(1 << nbits));
+}
+
+int rso_panasonic_v4(rso_image* img, const uint8_t* data, uint32_t size, int zero_is_not_bad,
+                     uint32_t section_split_offset, uint32_t* zero_pos, uint32_t cap,
+                     uint32_t* nzero, rso_err* e) {
+  enum { BlockSize = 0x4000, PixelsPerPacket = 14, BytesPerPacket = 16 };
+  rso_ctx c;
+  rso_err le;
+  uint8_t* volatile buf = NULL;
+  uint64_t area, bytesTotal, bufSize, blocksTotal, b, pixel = 0;
+  uint32_t nz = 0;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb)) {
+    free((void*)buf);
+    return c.e->code;
+  }
+  /* ctor (:49-90) */
+  if (img->cpp != 1 || img->is_f32)
+    THROW_RDE(&c, "Unexpected component count / data type");
+  if (!(img->w > 0 && img->h > 0) || img->w % PixelsPerPacket != 0)
+    THROW_RDE(&c, "Unexpected image dimensions found: (%i; %i)", img->w, img->h);
+  if (BlockSize < section_split_offset)
+    THROW_RDE(&c, "Bad section_split_offset: %u, less than BlockSize (%u)", section_split_offset,
+              (unsigned)BlockSize);
+  area = (uint64_t)img->w * (uint64_t)img->h;
+  bytesTotal = area / PixelsPerPacket * BytesPerPacket;
+  bufSize = section_split_offset == 0 ? bytesTotal
+                                      : (bytesTotal + BlockSize - 1) / BlockSize * BlockSize;
+  if (bufSize > 0xFFFFFFFFull)
+    THROW_RDE(&c, "Raw dimensions require input buffer larger than supported");
+  if (bufSize > size) /* input_.peekStream(bufSize) */
+    THROW_IOE(&c, "Out of bounds access in ByteStream");
+  buf = (uint8_t*)malloc(BlockSize + 2);
+  if (!buf)
+    THROW_RDE(&c, "out of memory");
+  /* chopInputIntoBlocks (:92-127) + processBlock (:216-236) */
+  blocksTotal = (bufSize + BlockSize - 1) / BlockSize;
+  for (b = 0; b < blocksTotal; b++) {
+    const uint64_t off = b * BlockSize;
+    const uint32_t blockSize = (uint32_t)(bufSize - off < BlockSize ? bufSize - off : BlockSize);
+    const uint32_t packets = blockSize / BytesPerPacket;
+    pana4_stream st;
+    uint32_t k;
+    /* ProxyStream::parseBlock (:136-159): second section first */
+    {
+      const uint32_t first = section_split_offset < blockSize ? section_split_offset : blockSize;
+      memcpy((uint8_t*)buf, data + off + first, blockSize - first);
+      memcpy((uint8_t*)buf + (blockSize - first), data + off, first);
+      ((uint8_t*)buf)[blockSize] = 0;
+    }
+    st.buf = (const uint8_t*)buf;
+    st.vbits = 0;
+    for (k = 0; k < packets && pixel < area; k++) {
+      /* processPixelPacket (:171-214) */
+      int sh = 0, u = 0, p;
+      int pred[2] = {0, 0}, nonz[2] = {0, 0};
+      for (p = 0; p < PixelsPerPacket; p++, pixel++) {
+        const int cc = p & 1;
+        const uint32_t row = (uint32_t)(pixel / (uint64_t)img->w), col = (uint32_t)(pixel % (uint64_t)img->w);
+        if (u == 2) {
+          /* extractHighBits(4U, bits.getBits(2), effectiveBitwidth = 3) = 4 >> (3 - n) */
+          sh = 4 >> (3 - (int)pana4_bits(&st, 2));
+          u = -1;
+        }
+        if (nonz[cc]) {
+          const int j = (int)pana4_bits(&st, 8);
+          if (j) {
+            pred[cc] -= 0x80 << sh;
+            if (pred[cc] < 0 || sh == 4)
+              pred[cc] &= ~(-(1 << sh));
+            pred[cc] += j << sh;
+          }
+        } else {
+          nonz[cc] = (int)pana4_bits(&st, 8);
+          if (nonz[cc] || p > 11)
+            pred[cc] = nonz[cc] << 4 | (int)pana4_bits(&st, 4);
+        }
+        ((uint16_t*)((uint8_t*)img->data + (size_t)row * (size_t)img->pitch))[col] = (uint16_t)pred[cc];
+        if (!zero_is_not_bad && pred[cc] == 0) {
+          if (zero_pos && nz < cap)
+            zero_pos[nz] = (row << 16) | col;
+          nz++;
+        }
+        u++;
+      }
+    }
+  }
+  if (nzero)
+    *nzero = nz;
+  free((void*)buf);
+  return RSO_OK;
+}

@@ -204,6 +204,17 @@ int rso_hasselblad_decompress(rso_image* img, const rso_huff* ht, uint16_t init_
 int rso_phaseone(rso_image* img, const uint8_t* file, uint64_t file_size, const uint64_t* off,
                  const uint32_t* len, const int32_t* rown, int nstrips, rso_err* e);
 
+/* ---- PanasonicV4Decompressor (decompressors/PanasonicV4Decompressor.cpp:49-277) ----
+ * (groundwork: restated and pinned, no device kernel yet)
+ * 0x4000-byte blocks whose two sections (split at section_split_offset) are swapped; every
+ * 16-byte packet is read from its top bit down and holds 14 pixels: 8-bit steps scaled by a
+ * 2-bit shift per triplet, per-parity predictor, 12-bit restarts.  zero_pos (may be NULL):
+ * (row << 16 | col) of every zero pixel when !zero_is_not_bad, in pixel order; *nzero = how
+ * many there are (only the first `cap` are stored). */
+int rso_panasonic_v4(rso_image* img, const uint8_t* data, uint32_t size, int zero_is_not_bad,
+                     uint32_t section_split_offset, uint32_t* zero_pos, uint32_t cap,
+                     uint32_t* nzero, rso_err* e);
+
 /* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
  * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
  * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity

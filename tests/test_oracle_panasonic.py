@@ -63,3 +63,33 @@ def test_panasonic_truncated_input(version, bps, w, h):
               lambda: oracle.ref.panasonic(version, port.new_image(w, h), w, data, bps)):
         with pytest.raises(port.RawDecoderException):
             f()
+
+
+@pytest.mark.parametrize("w,h,split,zero_ok", [(14, 1, 0, True), (28, 3, 0, False), (1400, 25, 0x1FF8, True),
+                                               (2800, 13, 0x1FF8, False), (1414, 9, 0, False),
+                                               (4200, 6, 0x2008, True)])
+def test_panasonic_v4_matches_reference(w, h, split, zero_ok):
+    """V4 (groundwork, no device kernel yet): random payloads are valid streams; with a
+    section split the input is whole 0x4000-byte blocks, without one the last block is short."""
+    nbytes = w * h // 14 * 16
+    if split:
+        nbytes = (nbytes + 0x3FFF) // 0x4000 * 0x4000
+    data = synth.lcg_bytes(nbytes, seed=w + h)
+    data[::7] = 0     # plenty of zero steps: the zero-reference and bad-pixel branches
+    a = port.new_image(w, h)
+    b = a.copy()
+    za = port.panasonic_v4(a, w, data, zero_ok, split)
+    zb = oracle.ref.panasonic_v4(b, w, data, zero_ok, split, nthreads=3)
+    assert np.array_equal(a, b)
+    assert za == zb and (zero_ok is False or za == [])
+
+
+def test_panasonic_v4_error_classes():
+    data = synth.lcg_bytes(0x8000, 2)
+    for f in (port.panasonic_v4, oracle.ref.panasonic_v4):
+        with pytest.raises(port.RawDecoderException):       # width not a multiple of 14
+            f(port.new_image(15, 2), 15, data)
+        with pytest.raises(port.RawDecoderException):       # split beyond the block
+            f(port.new_image(14, 2), 14, data, True, 0x4001)
+        with pytest.raises(port.IOException):               # not enough data
+            f(port.new_image(1400, 40), 1400, data)
