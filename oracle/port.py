@@ -357,6 +357,58 @@ def panasonic(version, img, w, data, bps=14):
     return img
 
 
+def scale_uses_sse2(black_sep, white):
+    """RawImageDataU16::scaleValues' path choice on x86 (app_scale < 63 -> SSE2)."""
+    b = (C.c_int * 4)(*[int(v) for v in black_sep])
+    L = lib()
+    L.rso_scale_uses_sse2.argtypes = [C.POINTER(C.c_int), C.c_int]
+    return bool(L.rso_scale_uses_sse2(b, int(white)))
+
+
+def scale_values(img, w, crop, black_sep, white, dither=True, sse2=None):
+    """RawImageDataU16::scaleValues over crop = (off_x, off_y, crop_w, crop_h), in place;
+    sse2=None picks the path the reference picks on x86."""
+    if sse2 is None:
+        sse2 = scale_uses_sse2(black_sep, white)
+    im = _img(img, w, 1)
+    b = (C.c_int * 4)(*[int(v) for v in black_sep])
+    e = Err()
+    L = lib()
+    L.rso_scale_values.argtypes = [C.POINTER(Image)] + [C.c_int] * 4 + [C.POINTER(C.c_int)] + \
+        [C.c_int] * 3 + [C.POINTER(Err)]
+    rc = L.rso_scale_values(C.byref(im), crop[0], crop[1], crop[2], crop[3], b, int(white),
+                            int(dither), int(sse2), C.byref(e))
+    e.check(rc)
+    return img
+
+
+class BlackArea(C.Structure):
+    _fields_ = [("offset", C.c_uint32), ("size", C.c_uint32), ("is_vertical", C.c_int)]
+
+
+def scale_black_white(img, w, crop, black_level=-1, black_sep=None, white=None, areas=(),
+                      dither=True, is_cfa=True, sse2=None):
+    """RawImageDataU16::scaleBlackWhite() in place; areas: [(is_vertical, offset, size)].
+    Returns (black_sep or None when no scaling happened, white)."""
+    im = _img(img, w, 1)
+    im.is_cfa = int(is_cfa)
+    b = (C.c_int * 4)(*([int(v) for v in black_sep] if black_sep is not None else [-7] * 4))
+    wh = C.c_int(int(white) if white is not None else 0)
+    ar = (BlackArea * max(1, len(areas)))(*[BlackArea(o, s, int(v)) for v, o, s in areas])
+    e = Err()
+    L = lib()
+    L.rso_scale_black_white.argtypes = [C.POINTER(Image)] + [C.c_int] * 5 + [C.POINTER(C.c_int), C.c_int,
+                                        C.POINTER(C.c_int), C.c_int, C.POINTER(BlackArea)] + \
+        [C.c_int] * 3 + [C.POINTER(Err)]
+    rc = L.rso_scale_black_white(C.byref(im), crop[0], crop[1], crop[2], crop[3], int(black_level),
+                                 b, int(black_sep is not None), C.byref(wh), int(white is not None),
+                                 ar, len(areas), int(dither), -1 if sse2 is None else int(sse2),
+                                 C.byref(e))
+    e.check(rc)
+    sep = list(b)
+    return (None if sep == [-7] * 4 else sep), wh.value
+
+
 def sony_arw2(img, w, data, table=None, dither=False):
     """SonyArw2Decompressor(img, data).decompress() into img (in place); `table` = the
     storage build_table() returns (None: the image has no table)."""

@@ -283,6 +283,44 @@ def panasonic(version, img, w, data, bps=14, nthreads=1, reps=1):
     return ms.value
 
 
+def scale_values(img, w, crop, black_sep, white, dither=True, nthreads=1):
+    """Reference RawImageData::scaleBlackWhite() with blackLevelSeparate / whitePoint given
+    (ref_scale_values); crop = (off_x, off_y, crop_w, crop_h)."""
+    b = (C.c_int * 4)(*[int(v) for v in black_sep])
+    e = Err()
+    L = lib()
+    L.ref_scale_values.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.POINTER(C.c_int)] + \
+        [C.c_int] * 3 + [C.POINTER(Err)]
+    rc = L.ref_scale_values(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
+                            crop[0], crop[1], crop[2], crop[3], b, int(white), int(dither),
+                            nthreads, C.byref(e))
+    e.check(rc)
+    return img
+
+
+def scale_black_white(img, w, crop, black_level=-1, black_sep=None, white=None, areas=(),
+                      dither=True, is_cfa=True, nthreads=1):
+    """Reference RawImageData::scaleBlackWhite() (ref_scale_black_white); areas:
+    [(is_vertical, offset, size)].  Returns (blackLevelSeparate or None, whitePoint)."""
+    b = (C.c_int * 4)(*([int(v) for v in black_sep] if black_sep is not None else [-7] * 4))
+    wh = C.c_int(int(white) if white is not None else 0)
+    flat = [int(x) for a in areas for x in a] or [0]
+    ar = (C.c_int * len(flat))(*flat)
+    sep_set = C.c_int(0)
+    e = Err()
+    L = lib()
+    L.ref_scale_black_white.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.POINTER(C.c_int), C.c_int,
+                                        C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)] + \
+        [C.c_int] * 3 + [C.POINTER(C.c_int), C.POINTER(Err)]
+    rc = L.ref_scale_black_white(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
+                                 int(is_cfa), crop[0], crop[1], crop[2], crop[3], int(black_level),
+                                 b, int(black_sep is not None), C.byref(wh), int(white is not None),
+                                 ar, len(areas), int(dither), nthreads, C.byref(sep_set),
+                                 C.byref(e))
+    e.check(rc)
+    return (list(b) if sep_set.value else None), wh.value
+
+
 def sony_arw2(img, w, data, curve=None, dither=False, nthreads=1, reps=1):
     """Reference SonyArw2Decompressor (ref_sony_arw2); curve: mRaw->setTable(curve, dither)."""
     p, n = _u8(data)

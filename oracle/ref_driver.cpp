@@ -334,6 +334,62 @@ int ref_hasselblad_decompress(uint16_t* img_data, int w, int h, int pitch, const
   });
 }
 
+// RawImageDataU16::scaleBlackWhite() with blackLevelSeparate and whitePoint given (no
+// estimation, no black areas): the SCALE_VALUES worker over the cropped rows.
+int ref_scale_values(uint16_t* img_data, int w, int h, int pitch, int off_x, int off_y,
+                     int crop_w, int crop_h, const int* black_sep, int white, int dither,
+                     int nthreads, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(w, h, 1, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    img->subFrame(iRectangle2D(iPoint2D(off_x, off_y), iPoint2D(crop_w, crop_h)));
+    img->blackLevelSeparate = Array2DRef<int>(img->blackLevelSeparateStorage.data(), 2, 2);
+    for (int i = 0; i < 4; ++i)
+      img->blackLevelSeparateStorage[i] = black_sep[i];
+    img->whitePoint = white;
+    img->mDitherScale = dither != 0;
+    img->scaleBlackWhite();
+    // copy out the whole uncropped buffer
+    const auto a = img->getU16DataAsUncroppedArray2DRef();
+    for (int r = 0; r < a.height(); ++r)
+      std::memcpy(reinterpret_cast<uint8_t*>(img_data) + static_cast<size_t>(r) * pitch, &a(r, 0),
+                  sizeof(uint16_t) * a.width());
+  });
+}
+
+// RawImageDataU16::scaleBlackWhite() in full: blackLevel, optional blackLevelSeparate /
+// whitePoint, blackAreas (triples is_vertical, offset, size); reports what it settled on.
+int ref_scale_black_white(uint16_t* img_data, int w, int h, int pitch, int is_cfa, int off_x,
+                          int off_y, int crop_w, int crop_h, int black_level, int* black_sep,
+                          int has_sep, int* white, int has_white, const int* areas, int n_areas,
+                          int dither, int nthreads, int* sep_set, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(w, h, 1, is_cfa != 0, 1, 1);
+    copyIn(img, img_data, pitch);
+    img->subFrame(iRectangle2D(iPoint2D(off_x, off_y), iPoint2D(crop_w, crop_h)));
+    img->blackLevel = black_level;
+    if (has_sep) {
+      img->blackLevelSeparate = Array2DRef<int>(img->blackLevelSeparateStorage.data(), 2, 2);
+      for (int i = 0; i < 4; ++i)
+        img->blackLevelSeparateStorage[i] = black_sep[i];
+    }
+    if (has_white)
+      img->whitePoint = *white;
+    for (int i = 0; i < n_areas; ++i)
+      img->blackAreas.emplace_back(areas[3 * i + 1], areas[3 * i + 2], areas[3 * i] != 0);
+    img->mDitherScale = dither != 0;
+    img->scaleBlackWhite();
+    copyOut(img, img_data, pitch);
+    *sep_set = img->blackLevelSeparate.has_value();
+    if (img->blackLevelSeparate)
+      for (int i = 0; i < 4; ++i)
+        black_sep[i] = img->blackLevelSeparateStorage[i];
+    *white = img->whitePoint.has_value() ? *img->whitePoint : -1;
+  });
+}
+
 // PhaseOneDecompressor(mRaw, strips).decompress(): strip k = (row rown[k], bytes
 // [off[k], off[k]+len[k]) of `file`), as IiqDecoder::DecodePhaseOneC builds them.
 int ref_phaseone(uint16_t* img_data, int w, int h, int pitch, const uint8_t* file,

@@ -3358,3 +3358,225 @@ int rso_panasonic_v4(rso_image* img, const uint8_t* data, uint32_t size, int zer
   free((void*)buf);
   return RSO_OK;
 }
+
+/* ------------------------------------------------------------------
+ * RawImageDataU16::scaleValues (common/RawImageDataU16.cpp)
+ * ------------------------------------------------------------------ */
+int rso_scale_uses_sse2(const int* black_sep, int white) {
+  /* scaleValues (:185-202): Cpuid::SSE2() && app_scale < 63 */
+  const int depth_values = white - black_sep[0];
+  const float app_scale = 65535.0F / (float)depth_values;
+  return app_scale < 63;
+}
+
+int rso_scale_values(rso_image* img, int off_x, int off_y, int crop_w, int crop_h,
+                     const int* black_sep, int white, int dither, int sse2, rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  const int depth_values = white - black_sep[0];
+  const float app_scale = 65535.0F / (float)depth_values;
+  const int full_scale_fp = (int)(app_scale * 4.0F);    /* 30.2 fixed point */
+  const int half_scale_fp = (int)(app_scale * 4095.0F); /* 18.14 fixed point */
+  int y;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb))
+    return c.e->code;
+  if (img->is_f32)
+    THROW_RDE(&c, "Unexpected data type");
+  if (off_x < 0 || off_y < 0 || crop_w <= 0 || crop_h <= 0 || off_x + crop_w > img->w ||
+      off_y + crop_h > img->h)
+    THROW_RDE(&c, "bad crop");
+  if (!sse2) {
+    /* scaleValues_plain (:343-399) */
+    const int gw = crop_w * img->cpp;
+    int mul[4], sub[4], i;
+    for (i = 0; i < 4; i++) {
+      int v = i;
+      if (off_x & 1)
+        v ^= 1;
+      if (off_y & 1)
+        v ^= 2;
+      mul[i] = (int)(16384.0F * 65535.0F / (float)(white - black_sep[v]));
+      sub[i] = black_sep[v];
+    }
+    for (y = 0; y < crop_h; y++) {
+      uint16_t* row = (uint16_t*)((uint8_t*)img->data + (size_t)(off_y + y) * (size_t)img->pitch) +
+                      off_x * img->cpp;
+      int v = crop_w + y * 36969, x;
+      for (x = 0; x < gw; x++) {
+        int rnd = 0, val;
+        if (dither) {
+          v = 18000 * (v & 65535) + (v >> 16);
+          rnd = half_scale_fp - (full_scale_fp * (v & 2047));
+        }
+        val = ((row[x] - sub[(2 * (y & 1)) + (x & 1)]) * mul[(2 * (y & 1)) + (x & 1)] + 8192 + rnd) >> 14;
+        row[x] = (uint16_t)(val < 0 ? 0 : (val > 65535 ? 65535 : val)); /* clampBits(.., 16) */
+      }
+    }
+    return RSO_OK;
+  }
+  /* scaleValues_SSE2 (:204-341), lane by lane */
+  {
+    uint32_t sub_even, mul_even, sub_odd, mul_odd;
+    const int xend = (img->w * img->cpp) / 8 * 8; /* roundDown(uncropped_dim.x, 8) (cpp == 1 images) */
+    /* 10 bit fraction; the pair (column parity 0, 1) packed into one 32-bit lane */
+    mul_even = (uint32_t)(int)(1024.0F * 65535.0F / (float)(white - black_sep[off_x & 1]));
+    mul_even |= (uint32_t)(int)(1024.0F * 65535.0F / (float)(white - black_sep[(off_x + 1) & 1])) << 16;
+    sub_even = (uint32_t)black_sep[off_x & 1] | ((uint32_t)black_sep[(off_x + 1) & 1] << 16);
+    mul_odd = (uint32_t)(int)(1024.0F * 65535.0F / (float)(white - black_sep[2 + (off_x & 1)]));
+    mul_odd |= (uint32_t)(int)(1024.0F * 65535.0F / (float)(white - black_sep[2 + ((off_x + 1) & 1)])) << 16;
+    sub_odd = (uint32_t)black_sep[2 + (off_x & 1)] | ((uint32_t)black_sep[2 + ((off_x + 1) & 1)] << 16);
+    for (y = 0; y < crop_h; y++) {
+      uint16_t* row = (uint16_t*)((uint8_t*)img->data + (size_t)(off_y + y) * (size_t)img->pitch);
+      const uint32_t subv = ((y + off_y) & 1) == 0 ? sub_even : sub_odd;
+      const uint32_t mulv = ((y + off_y) & 1) == 0 ? mul_even : mul_odd;
+      uint16_t rnd[8];
+      int x, k;
+      if (dither) {
+        /* _mm_set_epi32(e3, e2, e1, e0): 32-bit lane 0 = e0 */
+        const uint32_t l0 = (uint32_t)(crop_w * 1234 + y * 23464), l1 = (uint32_t)(crop_w * 4272 + y * 12123),
+                       l2 = (uint32_t)(crop_w * 2342 + y * 34311), l3 = (uint32_t)(crop_w * 1676 + y * 18000);
+        rnd[0] = (uint16_t)l0; rnd[1] = (uint16_t)(l0 >> 16);
+        rnd[2] = (uint16_t)l1; rnd[3] = (uint16_t)(l1 >> 16);
+        rnd[4] = (uint16_t)l2; rnd[5] = (uint16_t)(l2 >> 16);
+        rnd[6] = (uint16_t)l3; rnd[7] = (uint16_t)(l3 >> 16);
+      } else {
+        memset(rnd, 0, sizeof rnd);
+      }
+      for (x = 0; x < xend; x += 8) {
+        for (k = 0; k < 8; k++) {
+          /* sserandom = mulhi_epi16(r, m) ^ mullo_epi16(r, m), m = 0x1d32 / 0x4d9f (0 without dither) */
+          const int16_t m = dither ? (int16_t)((k & 1) ? 0x4d9f : 0x1d32) : 0;
+          const int32_t prod = (int32_t)(int16_t)rnd[k] * (int32_t)m;
+          rnd[k] = (uint16_t)((uint32_t)prod >> 16) ^ (uint16_t)prod;
+        }
+        for (k = 0; k < 8; k++) {
+          const uint16_t sub16 = (uint16_t)((k & 1) ? subv >> 16 : subv);
+          const uint16_t mul16 = (uint16_t)((k & 1) ? mulv >> 16 : mulv);
+          const uint16_t pix = row[x + k] > sub16 ? (uint16_t)(row[x + k] - sub16) : 0; /* subs_epu16 */
+          const uint32_t p32 = (uint32_t)pix * (uint32_t)mul16;      /* mulhi:mullo */
+          const uint16_t r16 = (uint16_t)((rnd[k] & 0x00ff) * (uint16_t)full_scale_fp); /* mullo_epi16 */
+          const uint32_t radd = (uint32_t)(half_scale_fp >> 4) - (uint32_t)r16;
+          int32_t v = (int32_t)(p32 + 512u + radd); /* epi32 adds wrap */
+          v >>= 10;                                  /* srai */
+          v = (int32_t)((uint32_t)v - 32768u);       /* sub_epi32 */
+          if (v < -32768)                            /* packs_epi32: signed saturation */
+            v = -32768;
+          if (v > 32767)
+            v = 32767;
+          row[x + k] = (uint16_t)((uint16_t)(int16_t)v ^ 0x8000u);
+        }
+      }
+    }
+  }
+  return RSO_OK;
+}
+
+int rso_scale_black_white(rso_image* img, int off_x, int off_y, int crop_w, int crop_h,
+                          int black_level, int* black_sep, int has_sep, int* white, int has_white,
+                          const rso_black_area* areas, int n_areas, int dither, int force_sse2,
+                          rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  uint16_t* hist = NULL;
+  const int skip = 250;
+  int rc, i;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb)) {
+    free(hist);
+    return c.e->code;
+  }
+  if (img->is_f32)
+    THROW_RDE(&c, "Unexpected data type");
+  if (off_x < 0 || off_y < 0 || crop_w < 0 || crop_h < 0 || off_x + crop_w > img->w ||
+      off_y + crop_h > img->h)
+    THROW_RDE(&c, "bad crop");
+  /* scaleBlackWhite (:147-171): estimate from the crop minus a 250 pixel border */
+  if ((n_areas == 0 && !has_sep && black_level < 0) || !has_white) {
+    const int gw = (crop_w - skip) * img->cpp;
+    int b = 65536, m = 0, row, col;
+    for (row = skip; row < crop_h - skip; row++) {
+      const uint16_t* p = (const uint16_t*)((const uint8_t*)img->data + (size_t)(off_y + row) * (size_t)img->pitch) +
+                          off_x * img->cpp;
+      for (col = skip; col < gw; col++) {
+        const int pixel = p[skip + col];
+        b = pixel < b ? pixel : b;
+        m = pixel > m ? pixel : m;
+      }
+    }
+    if (black_level < 0)
+      black_level = b;
+    if (!has_white) {
+      *white = m;
+      has_white = 1;
+    }
+  }
+  /* (:173-177) nothing to do */
+  if ((n_areas == 0 && black_level == 0 && *white == 65535 && !has_sep) || crop_w <= 0 || crop_h <= 0)
+    return RSO_OK;
+  if (!has_sep) {
+    /* calculateBlackAreas (:60-145) */
+    int totalpixels = 0;
+    hist = (uint16_t*)calloc(4 * 65536, sizeof(uint16_t));
+    if (!hist)
+      THROW_RDE(&c, "out of memory");
+    for (i = 0; i < n_areas; i++) {
+      const uint32_t offset = areas[i].offset;
+      const uint32_t size = areas[i].size - (areas[i].size & 1);
+      if (!areas[i].is_vertical) {
+        uint32_t y;
+        int x;
+        if ((int)offset + (int)size > img->h)
+          THROW_RDE(&c, "Offset + size is larger than height of image");
+        for (y = offset; y < offset + size; y++) {
+          const uint16_t* p = (const uint16_t*)((const uint8_t*)img->data + (size_t)y * (size_t)img->pitch);
+          for (x = off_x; x < crop_w + off_x; x++)
+            hist[(size_t)((2 * (y & 1)) + (x & 1)) * 65536 + p[off_x]]++; /* one sampled column (:87-91) */
+        }
+        totalpixels += (int)(size * (uint32_t)crop_w);
+      } else {
+        int y;
+        uint32_t x;
+        if ((int)offset + (int)size > img->w)
+          THROW_RDE(&c, "Offset + size is larger than width of image");
+        for (y = off_y; y < crop_h + off_y; y++) {
+          const uint16_t* p = (const uint16_t*)((const uint8_t*)img->data + (size_t)y * (size_t)img->pitch);
+          for (x = offset; x < size + offset; x++)
+            hist[(size_t)((2 * (y & 1)) + (x & 1)) * 65536 + p[offset]]++;
+        }
+        totalpixels += (int)(size * (uint32_t)crop_h);
+      }
+    }
+    if (!totalpixels) {
+      for (i = 0; i < 4; i++)
+        black_sep[i] = black_level;
+    } else {
+      totalpixels /= 4 * 2;
+      for (i = 0; i < 4; i++) {
+        const uint16_t* h = hist + (size_t)i * 65536;
+        int acc = h[0], v = 0;
+        while (acc <= totalpixels && v < 65535) {
+          v++;
+          acc += h[v];
+        }
+        black_sep[i] = v;
+      }
+      if (!img->is_cfa) {
+        int total = 0;
+        for (i = 0; i < 4; i++)
+          total += black_sep[i];
+        for (i = 0; i < 4; i++)
+          black_sep[i] = (total + 2) >> 2;
+      }
+    }
+    free(hist);
+    hist = NULL;
+  }
+  rc = rso_scale_values(img, off_x, off_y, crop_w, crop_h, black_sep, *white, dither,
+                        force_sse2 < 0 ? rso_scale_uses_sse2(black_sep, *white) : force_sse2, c.e);
+  return rc;
+}

@@ -215,6 +215,35 @@ int rso_panasonic_v4(rso_image* img, const uint8_t* data, uint32_t size, int zer
                      uint32_t section_split_offset, uint32_t* zero_pos, uint32_t cap,
                      uint32_t* nzero, rso_err* e);
 
+/* ---- RawImageDataU16::scaleValues (common/RawImageDataU16.cpp:185-399) ----
+ * (groundwork for SURVEY 8(f)3: restated and pinned, no device kernel yet)
+ * The black/white scaling of scaleBlackWhite() once black_sep[4] (blackLevelSeparate, index
+ * 2*(row&1) + (col&1) in crop coordinates) and white are known.  img = the UNCROPPED buffer,
+ * (off_x, off_y, crop_w, crop_h) = mOffset / dim.  sse2 != 0 restates scaleValues_SSE2
+ * (:204-341, what x86 builds run when app_scale < 63: 10-bit fixed point, eight 16-bit
+ * multiplicative dither states per row, whole uncropped rows in groups of 8 columns);
+ * sse2 == 0 restates scaleValues_plain (:343-399: 14-bit fixed point, one
+ * multiply-with-carry dither state per row, cropped columns only).  The reference picks:
+ * SSE2 iff 65535 / (white - black_sep[0]) < 63 (rso_scale_uses_sse2). */
+/* RawImageDataU16::scaleBlackWhite (:147-183) + calculateBlackAreas (:60-145): black_level =
+ * RawImageData::blackLevel (-1 unset); has_sep / black_sep[4] = blackLevelSeparate (in when
+ * has_sep, always out); has_white / *white = whitePoint (in when has_white, always out);
+ * areas = blackAreas.  Estimates black/white from the crop's centre when they are unknown,
+ * takes the per-CFA-position median of the masked areas (16-bit histogram counters and the
+ * single sampled column / row of the FIXMEs included), then scales (force_sse2: -1 = the
+ * reference's choice).  Returns RSO_OK also when the reference returns without scaling. */
+typedef struct {
+  uint32_t offset, size; /* BlackArea (metadata/BlackArea.h:27-34) */
+  int is_vertical;
+} rso_black_area;
+int rso_scale_black_white(rso_image* img, int off_x, int off_y, int crop_w, int crop_h,
+                          int black_level, int* black_sep, int has_sep, int* white, int has_white,
+                          const rso_black_area* areas, int n_areas, int dither, int force_sse2,
+                          rso_err* e);
+int rso_scale_uses_sse2(const int* black_sep, int white);
+int rso_scale_values(rso_image* img, int off_x, int off_y, int crop_w, int crop_h,
+                     const int* black_sep, int white, int dither, int sse2, rso_err* e);
+
 /* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
  * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
  * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity
