@@ -387,10 +387,10 @@ class BlackArea(C.Structure):
 
 
 def scale_black_white(img, w, crop, black_level=-1, black_sep=None, white=None, areas=(),
-                      dither=True, is_cfa=True, sse2=None):
+                      dither=True, is_cfa=True, sse2=None, cpp=1):
     """RawImageDataU16::scaleBlackWhite() in place; areas: [(is_vertical, offset, size)].
     Returns (black_sep or None when no scaling happened, white)."""
-    im = _img(img, w, 1)
+    im = _img(img, w, cpp)
     im.is_cfa = int(is_cfa)
     b = (C.c_int * 4)(*([int(v) for v in black_sep] if black_sep is not None else [-7] * 4))
     wh = C.c_int(int(white) if white is not None else 0)

@@ -299,7 +299,7 @@ def scale_values(img, w, crop, black_sep, white, dither=True, nthreads=1):
 
 
 def scale_black_white(img, w, crop, black_level=-1, black_sep=None, white=None, areas=(),
-                      dither=True, is_cfa=True, nthreads=1):
+                      dither=True, is_cfa=True, nthreads=1, cpp=1):
     """Reference RawImageData::scaleBlackWhite() (ref_scale_black_white); areas:
     [(is_vertical, offset, size)].  Returns (blackLevelSeparate or None, whitePoint)."""
     b = (C.c_int * 4)(*([int(v) for v in black_sep] if black_sep is not None else [-7] * 4))
@@ -309,10 +309,10 @@ def scale_black_white(img, w, crop, black_level=-1, black_sep=None, white=None, 
     sep_set = C.c_int(0)
     e = Err()
     L = lib()
-    L.ref_scale_black_white.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.POINTER(C.c_int), C.c_int,
+    L.ref_scale_black_white.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.POINTER(C.c_int), C.c_int,
                                         C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)] + \
         [C.c_int] * 3 + [C.POINTER(C.c_int), C.POINTER(Err)]
-    rc = L.ref_scale_black_white(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
+    rc = L.ref_scale_black_white(C.c_void_p(img.ctypes.data), w, img.shape[0], cpp, img.shape[1] * 2,
                                  int(is_cfa), crop[0], crop[1], crop[2], crop[3], int(black_level),
                                  b, int(black_sep is not None), C.byref(wh), int(white is not None),
                                  ar, len(areas), int(dither), nthreads, C.byref(sep_set),

@@ -360,13 +360,13 @@ int ref_scale_values(uint16_t* img_data, int w, int h, int pitch, int off_x, int
 
 // RawImageDataU16::scaleBlackWhite() in full: blackLevel, optional blackLevelSeparate /
 // whitePoint, blackAreas (triples is_vertical, offset, size); reports what it settled on.
-int ref_scale_black_white(uint16_t* img_data, int w, int h, int pitch, int is_cfa, int off_x,
+int ref_scale_black_white(uint16_t* img_data, int w, int h, int cpp, int pitch, int is_cfa, int off_x,
                           int off_y, int crop_w, int crop_h, int black_level, int* black_sep,
                           int has_sep, int* white, int has_white, const int* areas, int n_areas,
                           int dither, int nthreads, int* sep_set, RefErr* e) {
   return guarded(e, [&] {
     ref_set_threads(nthreads);
-    RawImage img = makeImage(w, h, 1, is_cfa != 0, 1, 1);
+    RawImage img = makeImage(w, h, cpp, is_cfa != 0, 1, 1);
     copyIn(img, img_data, pitch);
     img->subFrame(iRectangle2D(iPoint2D(off_x, off_y), iPoint2D(crop_w, crop_h)));
     img->blackLevel = black_level;

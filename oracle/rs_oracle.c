@@ -3420,7 +3420,7 @@ int rso_scale_values(rso_image* img, int off_x, int off_y, int crop_w, int crop_
   /* scaleValues_SSE2 (:204-341), lane by lane */
   {
     uint32_t sub_even, mul_even, sub_odd, mul_odd;
-    const int xend = (img->w * img->cpp) / 8 * 8; /* roundDown(uncropped_dim.x, 8) (cpp == 1 images) */
+    const int xend = img->w / 8 * 8; /* x < roundDown(uncropped_dim.x, 8): PIXELS, also when cpp > 1 (:309) */
     /* 10 bit fraction; the pair (column parity 0, 1) packed into one 32-bit lane */
     mul_even = (uint32_t)(int)(1024.0F * 65535.0F / (float)(white - black_sep[off_x & 1]));
     mul_even |= (uint32_t)(int)(1024.0F * 65535.0F / (float)(white - black_sep[(off_x + 1) & 1])) << 16;

@@ -146,3 +146,19 @@ def test_histogram_counters_are_16_bit():
                                         areas=[(1, 0, 512)], dither=False)
     # 512 rows * 512 columns / 4 positions = 65536 hits per histogram -> all counters wrapped to 0
     assert sep == [65535] * 4
+
+
+@needs_ref
+@pytest.mark.parametrize("white", [15000, 900])     # SSE2 path / plain path
+def test_three_components_per_pixel(white):
+    # cpp = 3 (not CFA): the SSE2 loop still bounds x by the PIXEL width (only the first
+    # roundDown(w, 8) of the 3*w samples of a row are scaled); the plain loop covers dim.x*cpp
+    w, h, cpp = 40, 10, 3
+    rng = np.random.default_rng(white)
+    a = port.new_image(w, h, cpp)
+    a[:, :] = rng.integers(100, white, size=a.shape, dtype=np.uint16)
+    b = a.copy()
+    kw = dict(black_sep=[100, 100, 100, 100], white=white, is_cfa=False, cpp=cpp)
+    ra = ref.scale_black_white(a, w, (2, 1, 30, 8), **kw)
+    rb = port.scale_black_white(b, w, (2, 1, 30, 8), **kw)
+    assert ra == rb and np.array_equal(a, b)
