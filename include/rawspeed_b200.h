@@ -229,6 +229,40 @@ int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseone_job* jobs
                                 rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* K9: black / white level scaling, in place.            */
+/*   RawImageDataU16::scaleValues  common/RawImageDataU16.cpp:185-399   */
+/*   (the SCALE_VALUES worker of scaleBlackWhite(), :147-183)           */
+/* The job scales the crop rows of one uint16 image that already lives  */
+/* in the plan's OUTPUT buffer (a decode plan's output): run it with     */
+/* rsb200_plan_run(plan, NULL, 0, d_image, bytes, stream).              */
+/* NOT YET VALIDATED ON A B200.                     */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t offset;     /* byte offset of row 0 of the UNCROPPED image; multiple of 16 */
+  uint32_t pitch;      /* bytes between rows; multiple of 16 (RawImageData::pitch)    */
+  uint32_t width;      /* uncropped_dim.x (pixels)                                    */
+  uint32_t height;     /* uncropped_dim.y                                             */
+  uint32_t cpp;        /* components per pixel                                        */
+  uint32_t crop_x;     /* mOffset.x                                                   */
+  uint32_t crop_y;     /* mOffset.y                                                   */
+  uint32_t crop_w;     /* dim.x                                                       */
+  uint32_t crop_h;     /* dim.y                                                       */
+  int32_t black_separate[4]; /* blackLevelSeparate, index 2*row + col                 */
+  int32_t white_point;       /* whitePoint; must differ from black_separate[0]        */
+  uint8_t dither;      /* mDitherScale                                                */
+  uint8_t path;        /* RSB200_SCALE_AUTO: what an x86 build of the reference runs
+                          (SSE2 loop iff 65535 / (white - black[0]) < 63, :185-202);
+                          RSB200_SCALE_SSE2 / RSB200_SCALE_PLAIN force one            */
+  uint8_t reserved[2];
+} rsb200_scale_job;
+#define RSB200_SCALE_AUTO 0
+#define RSB200_SCALE_SSE2 1
+#define RSB200_SCALE_PLAIN 2
+
+int rsb200_scale_plan_create(rsb200_ctx* ctx, const rsb200_scale_job* jobs, int njobs,
+                             rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
 /* K5: Canon sRaw interpolation.                         */
 /*   Cr2sRawInterpolator::interpolate(version)                          */
 /*   interpolators/Cr2sRawInterpolator.cpp:96-187 (4:2:2), :189-453     */

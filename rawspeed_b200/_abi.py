@@ -59,6 +59,17 @@ class PanaJob(C.Structure):
                 ("version", C.c_uint8), ("bps", C.c_uint8), ("reserved", C.c_uint8 * 2)]
 
 
+class ScaleJob(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("pitch", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("cpp", C.c_uint32), ("crop_x", C.c_uint32),
+                ("crop_y", C.c_uint32), ("crop_w", C.c_uint32), ("crop_h", C.c_uint32),
+                ("black_separate", C.c_int32 * 4), ("white_point", C.c_int32),
+                ("dither", C.c_uint8), ("path", C.c_uint8), ("reserved", C.c_uint8 * 2)]
+
+
+SCALE_AUTO, SCALE_SSE2, SCALE_PLAIN = 0, 1, 2
+
+
 class PhaseOneStrip(C.Structure):
     _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint32), ("row", C.c_uint32)]
 
@@ -112,7 +123,7 @@ EXPORTS = [
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_raw_plan_create", "rsb200_sraw_plan_create",
     "rsb200_pentax_plan_create", "rsb200_arw2_plan_create", "rsb200_nikon_plan_create",
-    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create",
+    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_scale_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",

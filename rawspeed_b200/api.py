@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Arw2Job, NikonJob, PanaJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, NikonJob, PanaJob, ScaleJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -83,7 +83,10 @@ def huff_table(ncpl, values, fix16=False):
 
 
 def _ptr_bytes(x):
-    """(device pointer, nbytes) of a torch CUDA tensor or (ptr, nbytes) tuple."""
+    """(device pointer, nbytes) of a torch CUDA tensor or (ptr, nbytes) tuple; None = no
+    buffer (plans that work in place on the output)."""
+    if x is None:
+        return 0, 0
     if isinstance(x, tuple):
         return int(x[0]), int(x[1])
     return int(x.data_ptr()), int(x.numel() * x.element_size())
@@ -190,6 +193,15 @@ def pana_plan(ctx, jobs):
     arr = (PanaJob * len(jobs))(*jobs)
     h = C.c_void_p()
     ctx.check(ctx._lib.rsb200_pana_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def scale_plan(ctx, jobs):
+    """Black / white scaling of decoded images in place (RawImageDataU16::scaleValues); run
+    with d_in=None: plan.run(None, d_image)."""
+    arr = (ScaleJob * len(jobs))(*jobs)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_scale_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

@@ -320,6 +320,42 @@ int rsb200h_sony_arw2(uint16_t* img_data, int w, int h, int pitch, const uint8_t
   });
 }
 
+// RawImageData::scaleBlackWhite(): blackLevel, optional blackLevelSeparate / whitePoint,
+// blackAreas as triples (is_vertical, offset, size); reports what it settled on.
+// stage: 0 = everything (device pass included), 1 = host part only (estimate + black areas;
+// needs no GPU).
+int rsb200h_scale_black_white(uint16_t* img_data, int w, int h, int cpp, int pitch, int is_cfa,
+                              int off_x, int off_y, int crop_w, int crop_h, int black_level,
+                              int* black_sep, int has_sep, int* white, int has_white,
+                              const int* areas, int n_areas, int dither, int path, int stage,
+                              int* sep_set, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, cpp, pitch, is_cfa != 0, 1, 1);
+    img->subFrame(iRectangle2D(off_x, off_y, crop_w, crop_h));
+    img->blackLevel = black_level;
+    if (has_sep) {
+      img->blackLevelSeparate = Array2DRef<int>(img->blackLevelSeparateStorage.data(), 2, 2);
+      for (int i = 0; i < 4; ++i)
+        img->blackLevelSeparateStorage[i] = black_sep[i];
+    }
+    if (has_white)
+      img->whitePoint = *white;
+    for (int i = 0; i < n_areas; ++i)
+      img->blackAreas.emplace_back(areas[3 * i + 1], areas[3 * i + 2], areas[3 * i] != 0);
+    img->mDitherScale = dither != 0;
+    if (stage == 0)
+      img->scaleBlackWhite(path);
+    else
+      img->prepareScaleBlackWhite();
+    copyOut(img, img_data);
+    *sep_set = img->blackLevelSeparate.has_value();
+    if (img->blackLevelSeparate)
+      for (int i = 0; i < 4; ++i)
+        black_sep[i] = img->blackLevelSeparateStorage[i];
+    *white = img->whitePoint.has_value() ? *img->whitePoint : -1;
+  });
+}
+
 int rsb200h_sraw_interpolate(const uint16_t* in, int in_w, int in_h, int in_pitch,
                              uint16_t* out_data, int out_w, int out_h, int out_pitch, int sub_x,
                              int sub_y, const int* coeffs, int hue, int version,

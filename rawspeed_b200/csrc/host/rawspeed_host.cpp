@@ -99,6 +99,136 @@ void RawImageData::createData() {
   pitch = (int)(((size_t)dim.x * bpp + 15) / 16 * 16);
   data.resize((size_t)pitch * dim.y + 16);
   storage = reinterpret_cast<uint8_t*>(((uintptr_t)data.data() + 15) & ~(uintptr_t)15);
+  uncropped_dim = dim;
+}
+
+// RawImageData::subFrame (common/RawImage.cpp:175-199); the CFA shift is metadata outside
+// this path
+void RawImageData::subFrame(iRectangle2D crop) {
+  if (!crop.hasPositiveArea())
+    ThrowRDE("No positive crop area");
+  if (!(crop.dim.x <= dim.x - crop.pos.x && crop.dim.y <= dim.y - crop.pos.y))
+    return; // "Attempted to create new subframe larger than original size. Crop skipped."
+  if (crop.pos.x < 0 || crop.pos.y < 0 || crop.dim.x < 0 || crop.dim.y < 0)
+    return; // "Negative crop offset. Crop skipped."
+  mOffset.x += crop.pos.x;
+  mOffset.y += crop.pos.y;
+  dim = crop.dim;
+}
+
+// RawImageDataU16::calculateBlackAreas (common/RawImageDataU16.cpp:60-145): per CFA position,
+// the median of the masked areas -- 16-bit histogram counters and the one sampled column / row
+// (the FIXMEs at :87, :103) as the reference has them.  Host work: the areas are a few rows.
+void RawImageData::calculateBlackAreas() {
+  const uint16_t* img = reinterpret_cast<const uint16_t*>(storage);
+  const size_t pitchElts = (size_t)pitch / 2;
+  std::vector<uint16_t> histogram(4 * 65536, 0);
+  int totalpixels = 0;
+  for (BlackArea area : blackAreas) {
+    area.size = area.size - (area.size & 1);
+    if (!area.isVertical) {
+      if ((int)area.offset + (int)area.size > uncropped_dim.y)
+        ThrowRDE("Offset + size is larger than height of image");
+      for (uint32_t y = area.offset; y < area.offset + area.size; y++)
+        for (int x = mOffset.x; x < dim.x + mOffset.x; x++)
+          histogram[(size_t)((2 * (y & 1)) + (x & 1)) * 65536 + img[y * pitchElts + mOffset.x]]++;
+      totalpixels += area.size * dim.x;
+    } else {
+      if ((int)area.offset + (int)area.size > uncropped_dim.x)
+        ThrowRDE("Offset + size is larger than width of image");
+      for (int y = mOffset.y; y < dim.y + mOffset.y; y++)
+        for (uint32_t x = area.offset; x < area.size + area.offset; x++)
+          histogram[(size_t)((2 * (y & 1)) + (x & 1)) * 65536 + img[(size_t)y * pitchElts + area.offset]]++;
+      totalpixels += area.size * dim.y;
+    }
+  }
+  blackLevelSeparate = Array2DRef<int>(blackLevelSeparateStorage.data(), 2, 2);
+  if (!totalpixels) {
+    for (int& i : blackLevelSeparateStorage)
+      i = blackLevel;
+    return;
+  }
+  totalpixels /= 4 * 2;
+  for (int i = 0; i < 4; i++) {
+    const uint16_t* localhist = &histogram[(size_t)i * 65536];
+    int acc_pixels = localhist[0];
+    int pixel_value = 0;
+    while (acc_pixels <= totalpixels && pixel_value < 65535) {
+      pixel_value++;
+      acc_pixels += localhist[pixel_value];
+    }
+    blackLevelSeparateStorage[i] = pixel_value;
+  }
+  if (!isCFA) {
+    int total = 0;
+    for (int i : blackLevelSeparateStorage)
+      total += i;
+    for (int& i : blackLevelSeparateStorage)
+      i = (total + 2) >> 2;
+  }
+}
+
+// RawImageDataU16::scaleBlackWhite (common/RawImageDataU16.cpp:147-183) up to the worker
+// launch: false = the reference returns without scaling
+bool RawImageData::prepareScaleBlackWhite() {
+  if (dataType != RawImageType::UINT16)
+    ThrowRDE("rawspeed_b200: scaleBlackWhite is implemented for UINT16 images");
+  if (!isAllocated())
+    ThrowRDE("scaleBlackWhite: image has no data");
+  const int skipBorder = 250;
+  const int gw = (dim.x - skipBorder) * (int)cpp;
+  if ((blackAreas.empty() && !blackLevelSeparate && blackLevel < 0) || !whitePoint) { // estimate
+    int b = 65536;
+    int m = 0;
+    const uint16_t* img = reinterpret_cast<const uint16_t*>(storage);
+    for (int row = skipBorder; row < (dim.y - skipBorder); row++) {
+      const uint16_t* p = img + (size_t)(mOffset.y + row) * ((size_t)pitch / 2) + (size_t)mOffset.x * cpp;
+      for (int col = skipBorder; col < gw; col++) {
+        const int pixel = p[skipBorder + col];
+        b = std::min(pixel, b);
+        m = std::max(pixel, m);
+      }
+    }
+    if (blackLevel < 0)
+      blackLevel = b;
+    if (!whitePoint)
+      whitePoint = m;
+  }
+  // nothing to do (:173-177)
+  if ((blackAreas.empty() && blackLevel == 0 && whitePoint == 65535 && !blackLevelSeparate) ||
+      dim.area() <= 0)
+    return false;
+  if (!blackLevelSeparate)
+    calculateBlackAreas();
+  return true;
+}
+
+void RawImageData::scaleBlackWhite(int path) {
+  if (!prepareScaleBlackWhite())
+    return;
+  // startWorker(SCALE_VALUES): the per-sample pass, on the device
+  rsb200_scale_job job;
+  std::memset(&job, 0, sizeof job);
+  job.offset = 0;
+  job.pitch = (uint32_t)pitch;
+  job.width = (uint32_t)uncropped_dim.x;
+  job.height = (uint32_t)uncropped_dim.y;
+  job.cpp = cpp;
+  job.crop_x = (uint32_t)mOffset.x;
+  job.crop_y = (uint32_t)mOffset.y;
+  job.crop_w = (uint32_t)dim.x;
+  job.crop_h = (uint32_t)dim.y;
+  for (int i = 0; i < 4; ++i)
+    job.black_separate[i] = blackLevelSeparateStorage[i];
+  job.white_point = *whitePoint;
+  job.dither = mDitherScale ? 1 : 0;
+  job.path = (uint8_t)path;
+  PlanGuard pg;
+  engineCheck(rsb200_scale_plan_create(engine(), &job, 1, &pg.p), "rsb200_scale_plan_create");
+  engineCheck(rsb200_plan_run_host_image(pg.p, nullptr, 0, storage, (uint32_t)pitch,
+                                         (uint32_t)(uncropped_dim.x * (int)bpp),
+                                         (uint32_t)uncropped_dim.y, /*partial=*/1),
+              "rsb200_plan_run_host_image");
 }
 
 void RawImageData::setError(const std::string& err) {

@@ -30,6 +30,7 @@
 #include <cstdio>
 #include <memory>
 #include <mutex>
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -173,6 +174,36 @@ private:
 };
 
 // ---------------------------------------------------------------- RawImage
+// adt/Array2DRef.h: non-owning 2-D view (pitch in elements)
+template <typename T> class Array2DRef {
+public:
+  Array2DRef(T* data_, int width_, int height_, int pitch_)
+      : data(data_), w(width_), h(height_), pitchElts(pitch_) {}
+  Array2DRef(T* data_, int width_, int height_)
+      : data(data_), w(width_), h(height_), pitchElts(width_) {}
+  int width() const { return w; }
+  int height() const { return h; }
+  int pitch() const { return pitchElts; }
+  T* begin() const { return data; }
+  T& operator()(int row, int col) const { return data[(size_t)row * pitchElts + col]; }
+
+private:
+  T* data;
+  int w, h, pitchElts;
+};
+
+template <typename T> using Optional = std::optional<T>; // adt/Optional.h
+
+// metadata/BlackArea.h:27-34
+class BlackArea final {
+public:
+  BlackArea(int offset_, int size_, bool isVertical_)
+      : offset(offset_), size(size_), isVertical(isVertical_) {}
+  uint32_t offset; // in bayer pixels
+  uint32_t size;
+  bool isVertical; // otherwise horizontal
+};
+
 enum class RawImageType { UINT16, F32 };
 
 class RawImageData {
@@ -181,6 +212,24 @@ public:
   int pitch = 0;
   bool isCFA = true;
   iPoint2D subsampling{1, 1}; // ImageMetaData::subsampling
+  // black / white levels (common/RawImage.h:163-174) and the scaling they drive
+  int blackLevel = -1;
+  std::array<int, 4> blackLevelSeparateStorage{};
+  Optional<Array2DRef<int>> blackLevelSeparate;
+  Optional<int> whitePoint;
+  std::vector<BlackArea> blackAreas;
+  bool mDitherScale = true; // common/RawImage.h:205
+  // RawImageData::subFrame (common/RawImage.cpp:175-199): dim becomes the crop, the data and
+  // pitch stay those of the uncropped image
+  void subFrame(iRectangle2D crop);
+  iPoint2D getUncroppedDim() const { return uncropped_dim; }
+  iPoint2D getCropOffset() const { return mOffset; }
+  // RawImageDataU16::scaleBlackWhite (common/RawImageDataU16.cpp:147-183): the estimate and the
+  // masked-area medians (calculateBlackAreas :60-145) on the host, the SCALE_VALUES pass over
+  // the image on the device (K9).  `path`: RSB200_SCALE_AUTO = what an x86 build runs.
+  void scaleBlackWhite(int path = RSB200_SCALE_AUTO);
+  // its host half alone (estimate + calculateBlackAreas); false: nothing to scale
+  bool prepareScaleBlackWhite();
   uint32_t getCpp() const { return cpp; }
   uint32_t getBpp() const { return bpp; }
   RawImageType getDataType() const { return dataType; }
@@ -196,7 +245,7 @@ public:
   bool isAllocated() const { return !data.empty(); }
   uint16_t* getData() { return reinterpret_cast<uint16_t*>(storage); }
   uint8_t* getByteData() { return storage; }
-  size_t getByteSize() const { return (size_t)pitch * (size_t)dim.y; }
+  size_t getByteSize() const { return (size_t)pitch * (size_t)uncropped_dim.y; }
   // ErrorLog (common/ErrorLog.h)
   void setError(const std::string& err);
   bool isTooManyErrors(unsigned many, std::string* firstErr = nullptr);
@@ -204,6 +253,8 @@ public:
 
 private:
   friend class RawImage;
+  void calculateBlackAreas();
+  iPoint2D uncropped_dim, mOffset;
   uint32_t cpp = 1, bpp = 2;
   RawImageType dataType = RawImageType::UINT16;
   std::vector<uint16_t> tableStorage;
@@ -566,22 +617,6 @@ private:
 };
 
 // ---------------------------------------------------------------- sRaw
-// adt/Array2DRef.h: non-owning 2-D view (pitch in elements)
-template <typename T> class Array2DRef {
-public:
-  Array2DRef(T* data_, int width_, int height_, int pitch_)
-      : data(data_), w(width_), h(height_), pitchElts(pitch_) {}
-  int width() const { return w; }
-  int height() const { return h; }
-  int pitch() const { return pitchElts; }
-  T* begin() const { return data; }
-  T& operator()(int row, int col) const { return data[(size_t)row * pitchElts + col]; }
-
-private:
-  T* data;
-  int w, h, pitchElts;
-};
-
 // interpolators/Cr2sRawInterpolator.h:36-60 -- same constructor and interpolate();
 // the per-pixel work (chroma interpolation + YCbCr->RGB) runs on the device.
 class Cr2sRawInterpolator final {

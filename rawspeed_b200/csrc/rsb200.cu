@@ -9,6 +9,8 @@
 #include "ljpeg_ranges.cuh"
 #include "ljpeg_thread.cuh"
 #include "rawforms.cuh"
+#include "scale.cuh"
+#include "scale_host.h"
 #include "sraw.cuh"
 #include "arw2.cuh"
 #include "pana.cuh"
@@ -23,6 +25,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -92,6 +95,13 @@ struct SrawGroup {
   uint32_t total_mcus = 0;
 };
 
+struct ScaleGroup {
+  int mode = 0; // 0: SSE2 loop semantics, 1: plain loop semantics
+  ScaleJobDev* d_jobs = nullptr;
+  int njobs = 0;
+  uint32_t total_quads = 0;
+};
+
 struct UnpackFastGroup {
   int bps;
   bool lsb;
@@ -103,7 +113,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place)
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -117,6 +127,7 @@ struct rsb200_plan {
   uint16_t* d_raw_tables = nullptr;
   std::vector<SrawGroup> sraw_groups;
   std::vector<PanaGroup> pana_groups;
+  std::vector<ScaleGroup> scale_groups;
   // Phase One (shares d_arw2_bad / h_arw2_bad as the per-job error flags)
   P1StripDev* d_p1_strips = nullptr;
   P1JobDev* d_p1_jobs = nullptr;
@@ -523,6 +534,55 @@ static cudaError_t run_raw_group(const RawGroup& g, const uint8_t* in, uint64_t 
 // ------------------------------------------------------------------
 // sRaw interpolation (K5)
 // ------------------------------------------------------------------
+// K9: black / white scaling in place (RawImageDataU16::scaleValues)
+extern "C" int rsb200_scale_plan_create(rsb200_ctx* ctx, const rsb200_scale_job* jobs, int njobs,
+                                        rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "scale_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<rsb200_plan, void (*)(rsb200_plan*)> holder(new rsb200_plan, rsb200_plan_destroy);
+  rsb200_plan* p = holder.get();
+  p->ctx = ctx;
+  p->kind = 7;
+  p->nunits = njobs;
+  std::vector<ScaleJobDev> dev[2];
+  uint32_t quads[2] = {0, 0};
+  for (int i = 0; i < njobs; ++i) {
+    ScaleJobDev d;
+    int mode = 0;
+    if (const char* why = scale_build_job(jobs[i], 0, &d, &mode))
+      return set_err(ctx, RSB200_ERR_ARG, "scale job %d: %s", i, why);
+    d.quad_begin = quads[mode];
+    const uint64_t q = (uint64_t)quads[mode] + scale_job_quads(jobs[i]);
+    if (q > 0x7FFFFFFFull)
+      return set_err(ctx, RSB200_ERR_ARG, "scale plan: too many rows");
+    quads[mode] = (uint32_t)q;
+    dev[mode].push_back(d);
+    // what one run reads and writes: the samples of the rows it walks
+    const uint64_t samples = (uint64_t)d.ncols * jobs[i].crop_h;
+    p->in_bytes += samples * 2;
+    p->out_bytes += samples * 2;
+    p->pixels += (uint64_t)jobs[i].crop_w * jobs[i].crop_h;
+    p->need_out = std::max<uint64_t>(p->need_out,
+                                     jobs[i].offset + (uint64_t)jobs[i].height * jobs[i].pitch);
+  }
+  for (int mode = 0; mode < 2; ++mode) {
+    if (dev[mode].empty())
+      continue;
+    ScaleGroup g;
+    g.mode = mode;
+    g.njobs = (int)dev[mode].size();
+    g.total_quads = quads[mode];
+    CUDA_TRY(ctx, cudaMalloc((void**)&g.d_jobs, sizeof(ScaleJobDev) * dev[mode].size()));
+    p->scale_groups.push_back(g); // owned by the plan from here on
+    CUDA_TRY(ctx, cudaMemcpy(g.d_jobs, dev[mode].data(), sizeof(ScaleJobDev) * dev[mode].size(),
+                             cudaMemcpyHostToDevice));
+  }
+  p->launches_per_run = (int)p->scale_groups.size();
+  *out = holder.release();
+  return RSB200_OK;
+}
+
 extern "C" int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* jobs, int njobs,
                                        rsb200_plan** out) {
   if (!ctx || !jobs || njobs <= 0 || !out)
@@ -1605,7 +1665,7 @@ extern "C" int rsb200_cr2_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* 
 // ------------------------------------------------------------------
 extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes,
                                void* d_out, size_t out_bytes, void* stream) {
-  if (!p || !d_in || !d_out)
+  if (!p || !d_out || (!d_in && p->need_in))
     return RSB200_ERR_ARG;
   rsb200_ctx* ctx = p->ctx;
   if (in_bytes < p->need_in || out_bytes < p->need_out)
@@ -1629,6 +1689,16 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       if (!g.nblocks)
         continue;
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
+      ctx->launches++;
+    }
+  } else if (p->kind == 7) {
+    for (const ScaleGroup& g : p->scale_groups) {
+      const uint32_t nb = (g.total_quads + SCALE_WARPS - 1) / SCALE_WARPS;
+      if (g.mode == 0)
+        scale_kernel<0><<<nb, SCALE_NT, 0, st>>>(outp, g.d_jobs, g.njobs, g.total_quads);
+      else
+        scale_kernel<1><<<nb, SCALE_NT, 0, st>>>(outp, g.d_jobs, g.njobs, g.total_quads);
+      CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches++;
     }
   } else if (p->kind == 6) {
@@ -1780,7 +1850,7 @@ static int run_host_unpack_pipelined(rsb200_plan* p, const uint8_t* in, size_t i
 
 extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
                                     uint8_t* out, size_t out_bytes, int partial) {
-  if (!p || !in || !out)
+  if (!p || !out || (!in && in_bytes))
     return RSB200_ERR_ARG;
   rsb200_ctx* ctx = p->ctx;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1795,7 +1865,8 @@ extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in
   if (!partial && unpack_pipeline_ok(p))
     return run_host_unpack_pipelined(p, in, in_bytes, out, out_bytes);
   cudaStream_t st = ctx->stream;
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (in_bytes)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
   if (partial)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_out, out, out_bytes, cudaMemcpyHostToDevice, st));
   rc = rsb200_plan_run(p, ctx->d_in, in_bytes, ctx->d_out, out_bytes, (void*)st);
@@ -1809,7 +1880,7 @@ extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in
 extern "C" int rsb200_plan_run_host_image(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
                                           uint8_t* out, uint32_t pitch, uint32_t row_bytes,
                                           uint32_t rows, int partial) {
-  if (!p || !in || !out || row_bytes > pitch)
+  if (!p || !out || (!in && in_bytes) || row_bytes > pitch)
     return RSB200_ERR_ARG;
   rsb200_ctx* ctx = p->ctx;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1821,7 +1892,8 @@ extern "C" int rsb200_plan_run_host_image(rsb200_plan* p, const uint8_t* in, siz
   if (rc)
     return rc;
   cudaStream_t st = ctx->stream;
-  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (in_bytes)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
   if (partial)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_out, out, out_bytes, cudaMemcpyHostToDevice, st));
   rc = rsb200_plan_run(p, ctx->d_in, in_bytes, ctx->d_out, out_bytes, (void*)st);
@@ -1936,6 +2008,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   for (RawGroup& g : p->raw_groups)
     cudaFree(g.d_jobs);
   for (PanaGroup& g : p->pana_groups)
+    cudaFree(g.d_jobs);
+  for (ScaleGroup& g : p->scale_groups)
     cudaFree(g.d_jobs);
   cudaFree(p->d_p1_strips);
   cudaFree(p->d_p1_jobs);

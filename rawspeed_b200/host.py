@@ -30,7 +30,7 @@ EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_dng_decompress", "rsb200h_cr2_decompress", "rsb200h_cr2_ljpeg_decode",
            "rsb200h_huff_check", "rsb200h_unpack_form", "rsb200h_pentax_decompress",
            "rsb200h_sraw_interpolate", "rsb200h_nikon_decompress", "rsb200h_sony_arw2",
-           "rsb200h_panasonic", "rsb200h_phaseone"]
+           "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white"]
 
 _lib = None
 
@@ -213,6 +213,30 @@ def sony_arw2(img, w, data, curve=None, dither=False):
     e.check(L.rsb200h_sony_arw2(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
                                 p, C.c_uint32(n), cp, nc, int(dither), C.byref(e)))
     return img
+
+
+def scale_black_white(img, w, crop, black_level=-1, black_sep=None, white=None, areas=(),
+                      dither=True, is_cfa=True, cpp=1, path=0, host_part_only=False):
+    """RawImageData::scaleBlackWhite() via the host mirror, in place; crop = (off_x, off_y,
+    crop_w, crop_h) applied with subFrame(); areas: [(is_vertical, offset, size)].  Returns
+    (blackLevelSeparate or None, whitePoint).  host_part_only: the estimate and the black-area
+    medians without the device pass (needs no GPU)."""
+    b = (C.c_int * 4)(*([int(v) for v in black_sep] if black_sep is not None else [-7] * 4))
+    wh = C.c_int(int(white) if white is not None else 0)
+    flat = [int(x) for a in areas for x in a] or [0]
+    ar = (C.c_int * len(flat))(*flat)
+    sep_set = C.c_int(0)
+    e = _Err()
+    L = lib()
+    L.rsb200h_scale_black_white.argtypes = [C.c_void_p] + [C.c_int] * 10 + [
+        C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)] + \
+        [C.c_int] * 4 + [C.POINTER(C.c_int), C.POINTER(_Err)]
+    e.check(L.rsb200h_scale_black_white(
+        C.c_void_p(img.ctypes.data), w, img.shape[0], cpp, img.shape[1] * 2, int(is_cfa),
+        crop[0], crop[1], crop[2], crop[3], int(black_level), b, int(black_sep is not None),
+        C.byref(wh), int(white is not None), ar, len(areas), int(dither), int(path),
+        1 if host_part_only else 0, C.byref(sep_set), C.byref(e)))
+    return (list(b) if sep_set.value else None), wh.value
 
 
 def sraw_interpolate(inp, in_w, out, out_w, sub, coeffs, hue, version):

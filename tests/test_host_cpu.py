@@ -121,3 +121,51 @@ def test_vendor_codec_ctor_errors_same_class():
     for ww, st in [(16, strips[:-1]), (16, strips[:-1] + [strips[0]]), (15, strips)]:
         _same_class(lambda: port.phaseone(port.new_image(ww, 4), ww, pb, st),
                     lambda: host.phaseone(port.new_image(ww, 4), ww, pb, st))
+
+
+# ---- RawImageData::scaleBlackWhite: the host half (estimate + calculateBlackAreas) -----------
+
+def _sensor(w, h, seed, black=512, white=15000):
+    rng = np.random.default_rng(seed)
+    img = port.new_image(w, h)
+    img[:, :] = rng.integers(black, white, size=img.shape, dtype=np.uint16)
+    img[:, :16] = (black + rng.integers(-6, 7, size=(h, 16))).astype(np.uint16)
+    img[:8, :] = (black + 3 + rng.integers(-6, 7, size=(8, img.shape[1]))).astype(np.uint16)
+    return img
+
+
+@pytest.mark.parametrize("name,w,h,crop,kw", [
+    ("vertical_area", 96, 40, (16, 8, 80, 32), dict(white=15000, areas=[(1, 0, 16)])),
+    ("horizontal_area", 96, 40, (16, 8, 80, 32), dict(white=15000, areas=[(0, 0, 8)])),
+    ("both_odd_sizes", 97, 41, (17, 9, 80, 32), dict(white=15000, areas=[(1, 1, 15), (0, 1, 7)])),
+    ("not_cfa_average", 96, 40, (16, 8, 80, 32), dict(white=15000, areas=[(1, 0, 16)], is_cfa=False)),
+    ("black_level_only", 64, 24, (0, 0, 64, 24), dict(black_level=500, white=15000)),
+    ("nothing_to_do", 64, 24, (0, 0, 64, 24), dict(black_level=0, white=65535)),
+    ("estimate_both", 640, 560, (4, 4, 620, 540), dict()),
+    ("estimate_white", 640, 560, (4, 4, 620, 540), dict(black_level=600)),
+])
+def test_scale_black_white_host_half_matches_oracle(name, w, h, crop, kw):
+    a = _sensor(w, h, len(name))
+    keep = a.copy()
+    got = host.scale_black_white(a, w, crop, host_part_only=True, **kw)
+    assert np.array_equal(a, keep)          # the host half does not touch the pixels
+    b = keep.copy()
+    want = port.scale_black_white(b, w, crop, **kw)
+    assert got == want
+
+
+def test_scale_black_white_area_errors_same_class():
+    a = _sensor(64, 24, 5)
+    for areas in ([(0, 20, 8)], [(1, 60, 8)]):
+        kw = dict(white=15000, areas=areas)
+        _same_class(lambda: port.scale_black_white(a.copy(), 64, (0, 0, 64, 24), **kw),
+                    lambda: host.scale_black_white(a.copy(), 64, (0, 0, 64, 24), host_part_only=True, **kw))
+
+
+def test_scale_black_white_needs_the_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the device pass runs (tests/test_gpu_scale.py)")
+    a = _sensor(64, 24, 6)
+    with pytest.raises(Exception):
+        host.scale_black_white(a, 64, (0, 0, 64, 24), black_level=500, white=15000)
