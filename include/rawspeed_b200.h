@@ -179,7 +179,10 @@ int rsb200_arw2_plan_create(rsb200_ctx* ctx, const rsb200_arw2_job* jobs, int nj
                             rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
-/* K7: Panasonic RW2 block codecs V5 / V6 / V7.          */
+/* K7: Panasonic RW2 block codecs V4 / V5 / V6 / V7.     */
+/*   PanasonicV4Decompressor::processBlock (+ ProxyStream section swap) */
+/*       decompressors/PanasonicV4Decompressor.cpp:129-236  (V4: written */
+/*       and CPU-replayed, NOT YET RUN ON A B200 -- DESIGN.md K7)        */
 /*   PanasonicV5Decompressor::processBlock (+ ProxyStream section swap) */
 /*       decompressors/PanasonicV5Decompressor.cpp:147-232              */
 /*   PanasonicV6Decompressor::decompressBlock  PanasonicV6Decompressor.cpp:88-221 */
@@ -190,15 +193,27 @@ typedef struct {
   uint64_t in_size;    /* bytes available (checked against the block count)       */
   uint64_t out_offset; /* byte offset of image row 0; multiple of 2               */
   uint32_t out_pitch;  /* bytes between output rows; multiple of 2, >= 2*width    */
-  uint32_t width;      /* multiple of the pixels per 16-byte unit (V5: 10 / 9,    */
-  uint32_t height;     /* V6: 14 / 11, V7: 9)                                     */
-  uint8_t version;     /* 5, 6 or 7                                               */
-  uint8_t bps;         /* 12 or 14 (V7: 14)                                       */
-  uint8_t reserved[2];
+  uint32_t width;      /* multiple of the pixels per 16-byte unit (V4: 14,        */
+  uint32_t height;     /* V5: 10 / 9, V6: 14 / 11, V7: 9)                         */
+  uint8_t version;     /* 4, 5, 6 or 7                                            */
+  uint8_t bps;         /* 12 or 14 (V7: 14; V4: ignored)                          */
+  uint8_t zero_is_not_bad; /* V4: 0 = positions of pixels decoded as 0 are kept
+                              for rsb200_plan_bad_pixels()                        */
+  uint8_t reserved;
+  uint32_t section_split_offset; /* V4: 0 .. 0x4000 (0 = blocks are not swapped)  */
+  uint32_t reserved1;
 } rsb200_pana_job;
 
 int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* jobs, int njobs,
                             rsb200_plan** plan);
+/* V4 jobs with zero_is_not_bad == 0: the positions ((row << 16) | col) of the pixels the
+ * plan's last run decoded as 0 -- what the reference appends to mRaw->mBadPixelPositions
+ * (PanasonicV4Decompressor.cpp:206-207, :228-235), in no particular order (the reference's
+ * order depends on its thread schedule).  *count = how many there were; at most `cap` (and at
+ * most RSB200_PANA_BAD_CAP) are stored.  Waits for the run. */
+#define RSB200_PANA_BAD_CAP (1u << 22)
+int rsb200_plan_bad_pixels(rsb200_plan* plan, int job, uint32_t* positions, uint32_t cap,
+                           uint32_t* count);
 
 /* ------------------------------------------------------------------ */
 /* K8: Phase One IIQ row codec.                          */

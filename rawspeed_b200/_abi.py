@@ -56,7 +56,12 @@ class NikonJob(C.Structure):
 class PanaJob(C.Structure):
     _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint64), ("out_offset", C.c_uint64),
                 ("out_pitch", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
-                ("version", C.c_uint8), ("bps", C.c_uint8), ("reserved", C.c_uint8 * 2)]
+                ("version", C.c_uint8), ("bps", C.c_uint8), ("zero_is_not_bad", C.c_uint8),
+                ("reserved", C.c_uint8), ("section_split_offset", C.c_uint32),
+                ("reserved1", C.c_uint32)]
+
+
+PANA_BAD_CAP = 1 << 22
 
 
 class ScaleJob(C.Structure):
@@ -123,7 +128,7 @@ EXPORTS = [
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_raw_plan_create", "rsb200_sraw_plan_create",
     "rsb200_pentax_plan_create", "rsb200_arw2_plan_create", "rsb200_nikon_plan_create",
-    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_scale_plan_create",
+    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_scale_plan_create", "rsb200_plan_bad_pixels",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",

@@ -140,6 +140,14 @@ class Plan:
         self.ctx._lib.rsb200_plan_bytes(self.h, C.byref(a), C.byref(b), C.byref(p))
         return a.value, b.value, p.value
 
+    def bad_pixels(self, job=0, cap=1 << 20):
+        """Panasonic V4 job with zero_is_not_bad == 0: (count, positions[:min(count, cap)]) of
+        the pixels the last run decoded as 0, positions = (row << 16) | col, unordered."""
+        buf = (C.c_uint32 * cap)()
+        n = C.c_uint32(0)
+        self.ctx.check(self.ctx._lib.rsb200_plan_bad_pixels(self.h, job, buf, cap, C.byref(n)))
+        return n.value, list(buf[:min(n.value, cap)])
+
     @property
     def launches(self):
         return int(self.ctx._lib.rsb200_plan_launches(self.h))

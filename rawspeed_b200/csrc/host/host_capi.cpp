@@ -285,6 +285,26 @@ int rsb200h_panasonic(int version, uint16_t* img_data, int w, int h, int pitch,
   });
 }
 
+// PanasonicV4Decompressor(img, data, zero_is_not_bad, split).decompress(); the bad-pixel
+// positions it appended to mRaw->mBadPixelPositions come back in zero_pos (at most cap) / nzero.
+// construct_only != 0: the constructor's checks alone (no GPU needed).
+int rsb200h_panasonic_v4(uint16_t* img_data, int w, int h, int pitch, const uint8_t* data,
+                         uint32_t size, int zero_is_not_bad, uint32_t split, uint32_t* zero_pos,
+                         uint32_t cap, uint32_t* nzero, int construct_only, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, 1, pitch, true, 1, 1);
+    PanasonicV4Decompressor d(img, ByteStream(data, size), zero_is_not_bad != 0, split);
+    if (construct_only)
+      return;
+    d.decompress();
+    copyOut(img, img_data);
+    const auto& z = img->mBadPixelPositions;
+    *nzero = (uint32_t)z.size();
+    for (size_t i = 0; i < z.size() && i < cap; ++i)
+      zero_pos[i] = z[i];
+  });
+}
+
 int rsb200h_phaseone(uint16_t* img_data, int w, int h, int pitch, const uint8_t* file,
                      uint64_t file_size, const uint64_t* off, const uint32_t* len,
                      const int32_t* rown, int nstrips, rsb200h_err* e) {

@@ -839,6 +839,65 @@ void panaRun(const RawImage& mRaw, const ByteStream& input, int version, int bps
 }
 } // namespace
 
+// ctor (decompressors/PanasonicV4Decompressor.cpp:49-90)
+PanasonicV4Decompressor::PanasonicV4Decompressor(RawImage img, ByteStream input_,
+                                                 bool zero_is_not_bad,
+                                                 uint32_t section_split_offset_)
+    : mRaw(std::move(img)), input(input_), zero_is_bad(!zero_is_not_bad),
+      section_split_offset(section_split_offset_) {
+  constexpr uint32_t BlockSize = 0x4000, PixelsPerPacket = 14, BytesPerPacket = 16;
+  panaCheckImage(mRaw);
+  if (!(mRaw->dim.x > 0 && mRaw->dim.y > 0) || mRaw->dim.x % (int)PixelsPerPacket != 0)
+    ThrowRDE("Unexpected image dimensions found: (%i; %i)", mRaw->dim.x, mRaw->dim.y);
+  if (BlockSize < section_split_offset)
+    ThrowRDE("Bad section_split_offset: %u, less than BlockSize (%u)", section_split_offset,
+             BlockSize);
+  const uint64_t bytesTotal = mRaw->dim.area() / PixelsPerPacket * BytesPerPacket;
+  const uint64_t bufSize = section_split_offset == 0
+                               ? bytesTotal
+                               : (bytesTotal + BlockSize - 1) / BlockSize * BlockSize;
+  if (bufSize > 0xFFFFFFFFull)
+    ThrowRDE("Raw dimensions require input buffer larger than supported");
+  if (bufSize > input.getRemainSize()) // input_.peekStream(bufSize)
+    ThrowIOE("Out of bounds access in ByteStream");
+}
+
+// decompress (:238-266): blocks / packets in parallel on the device
+void PanasonicV4Decompressor::decompress() const {
+  rsb200_pana_job job;
+  std::memset(&job, 0, sizeof job);
+  job.in_offset = 0;
+  job.in_size = input.getRemainSize();
+  job.out_offset = 0;
+  job.out_pitch = (uint32_t)mRaw->pitch;
+  job.width = (uint32_t)mRaw->dim.x;
+  job.height = (uint32_t)mRaw->dim.y;
+  job.version = 4;
+  job.bps = 12;
+  job.zero_is_not_bad = zero_is_bad ? 0 : 1;
+  job.section_split_offset = section_split_offset;
+  PlanGuard pg;
+  engineCheck(rsb200_pana_plan_create(engine(), &job, 1, &pg.p), "rsb200_pana_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, input.begin() + input.getPosition(), input.getRemainSize(), img,
+             /*partial=*/false);
+  engineCheck(rsb200_plan_results(pg.p, nullptr, 0), "rsb200_plan_results");
+  if (!zero_is_bad)
+    return;
+  uint32_t count = 0;
+  engineCheck(rsb200_plan_bad_pixels(pg.p, 0, nullptr, 0, &count), "rsb200_plan_bad_pixels");
+  if (!count)
+    return;
+  if (count > RSB200_PANA_BAD_CAP)
+    ThrowRDE("rawspeed_b200: %u bad pixels, more than the device list holds (%u)", count,
+             RSB200_PANA_BAD_CAP);
+  std::vector<uint32_t> zero_pos(count);
+  engineCheck(rsb200_plan_bad_pixels(pg.p, 0, zero_pos.data(), count, &count),
+              "rsb200_plan_bad_pixels");
+  std::lock_guard<std::mutex> guard(mRaw->mBadPixelMutex);
+  mRaw->mBadPixelPositions.insert(mRaw->mBadPixelPositions.end(), zero_pos.begin(), zero_pos.end());
+}
+
 PanasonicV5Decompressor::PanasonicV5Decompressor(RawImage img, ByteStream input_, uint32_t bps_)
     : mRaw(std::move(img)), input(input_), bps(bps_) {
   panaCheckImage(mRaw);

@@ -219,6 +219,9 @@ public:
   Optional<int> whitePoint;
   std::vector<BlackArea> blackAreas;
   bool mDitherScale = true; // common/RawImage.h:205
+  // (y << 16) | x of pixels a decoder marked bad (common/RawImage.h:179-186)
+  std::vector<uint32_t> mBadPixelPositions;
+  std::mutex mBadPixelMutex;
   // RawImageData::subFrame (common/RawImage.cpp:175-199): dim becomes the crop, the data and
   // pitch stay those of the uncropped image
   void subFrame(iRectangle2D crop);
@@ -551,6 +554,21 @@ private:
 // ---------------------------------------------------------------- Panasonic
 // decompressors/PanasonicV{5,6,7}Decompressor.h: same constructors (image, byte
 // stream[, bps]) with the reference's validation, decompress() runs on the device.
+// decompressors/PanasonicV4Decompressor.h:37-98: zero_is_not_bad = false makes decompress()
+// append the positions of the pixels decoded as 0 to mRaw->mBadPixelPositions (unordered, as
+// the reference's thread schedule leaves them)
+class PanasonicV4Decompressor final {
+public:
+  PanasonicV4Decompressor(RawImage img, ByteStream input_, bool zero_is_not_bad,
+                          uint32_t section_split_offset_);
+  void decompress() const;
+
+private:
+  RawImage mRaw;
+  ByteStream input;
+  bool zero_is_bad;
+  uint32_t section_split_offset;
+};
 class PanasonicV5Decompressor final {
 public:
   PanasonicV5Decompressor(RawImage img, ByteStream input_, uint32_t bps_);

@@ -1,12 +1,19 @@
-// pana.cuh -- K7: Panasonic RW2 block codecs V5 / V6 / V7, sm_100a.
+// pana.cuh -- K7: Panasonic RW2 block codecs V4 / V5 / V6 / V7, sm_100a.
 //
 // Replaces the bodies of
+//   PanasonicV4Decompressor::processBlock / processPixelPacket
+//       decompressors/PanasonicV4Decompressor.cpp:171-236 (+ ProxyStream :129-168); the
+//       packet arithmetic is in pana4_core.h.  (VER == 4 has NOT YET RUN ON A B200: it is
+//       checked by a CPU replay, tests/test_pana4_emu.py; V5 / V6 / V7 are GPU-validated.)
 //   PanasonicV5Decompressor::processBlock / processPixelPacket
 //       decompressors/PanasonicV5Decompressor.cpp:188-232 (+ ProxyStream :147-186)
 //   PanasonicV6Decompressor::decompressBlock  PanasonicV6Decompressor.cpp:88-221
 //   PanasonicV7Decompressor::decompressBlock  PanasonicV7Decompressor.cpp:66-73
 // and their OpenMP loops over blocks / rows.  All three cut the image into
 // independent 16-byte units read as LSB-first bit streams:
+//   V4  packets of 14 pixels (8-bit differences with a per-triplet shift, one 12-bit start
+//       value per colour) inside 0x4000-byte blocks whose two sections (split at
+//       section_split_offset) are swapped; pixels decoded as 0 can be reported as bad;
 //   V5  packets of 10 x 12 or 9 x 14 bits inside 0x4000-byte blocks whose two
 //       sections (split at 0x1FF8) are swapped; pixels numbered linearly over
 //       the image (width is a multiple of the packet size);
@@ -18,6 +25,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "pana4_core.h"
 
 namespace rsb200 {
 
@@ -31,7 +39,11 @@ struct PanaJobDev {
   uint32_t height;
   uint32_t unit_begin; // first unit of this job in the group
   uint32_t units;      // units that carry pixels of the image
+  uint32_t split;      // V4: section_split_offset
+  uint32_t zero_slot;  // V4: 1 + index of the job's bad-pixel list, 0 = zeros are not bad
 };
+
+constexpr uint32_t PANA_ZERO_CAP = 1u << 22; // bad-pixel positions kept per job and run
 
 // n bits at compile-time bit offset OFF of the 128-bit little-endian number w[0..3]
 template <int OFF, int N>
@@ -113,12 +125,14 @@ __device__ __forceinline__ void pana6_pixels(const uint32_t (&w)[4], uint32_t (&
   }
 }
 
-// VER 5/6/7, BPS 12/14
+// VER 4 (BPS 12) / 5 / 6 / 7, BPS 12 / 14.  zero_count / zero_list: V4 bad-pixel lists
+// (PANA_ZERO_CAP positions per list), unused otherwise.
 template <int VER, int BPS>
 __global__ void __launch_bounds__(PANA_NT)
     pana_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                const PanaJobDev* __restrict__ jobs, int njobs, uint32_t total_units) {
-  constexpr int NPIX = VER == 6 ? (BPS == 14 ? 11 : 14) : 128 / BPS;
+                const PanaJobDev* __restrict__ jobs, int njobs, uint32_t total_units,
+                uint32_t* __restrict__ zero_count, uint32_t* __restrict__ zero_list) {
+  constexpr int NPIX = VER == 4 ? 14 : (VER == 6 ? (BPS == 14 ? 11 : 14) : 128 / BPS);
   const uint32_t u_raw = blockIdx.x * PANA_NT + threadIdx.x;
   const bool live = u_raw < total_units;
   const uint32_t u = live ? u_raw : total_units - 1u; // (idle threads of the last CTA mirror the last unit)
@@ -142,7 +156,19 @@ __global__ void __launch_bounds__(PANA_NT)
     a = __funnelshift_r(x0, x1, 8u * mis);
     b = __funnelshift_r(x1, x2, 8u * mis);
   };
-  if (VER == 5) {
+  if (VER == 4) {
+    // packet ul of the image = packet ul % 1024 of block ul / 1024, through the section swap
+    const uint32_t blk = ul >> 10, o = (ul & 1023u) * 16u;
+    if ((jb.split & 7u) == 0) { // (the decoder's 0x2008 / 0): an 8-byte half never wraps
+      load8(base + pana4_src(blk, o, jb.split), w[0], w[1]);
+      load8(base + pana4_src(blk, o + 8u, jb.split), w[2], w[3]);
+    } else {
+      w[0] = w[1] = w[2] = w[3] = 0u;
+#pragma unroll
+      for (uint32_t i = 0; i < 16; ++i)
+        w[i >> 2] |= (uint32_t)__ldg(base + pana4_src(blk, o + i, jb.split)) << (8u * (i & 3u));
+    }
+  } else if (VER == 5) {
     // packet ul of the image = packet ul % 1024 of block ul / 1024, read through the
     // section swap: rearranged byte j of a block is original byte (j + 0x1FF8) % 0x4000
     const uint32_t blk = ul >> 10, o = (ul & 1023u) * 16u;
@@ -155,7 +181,20 @@ __global__ void __launch_bounds__(PANA_NT)
     load8(p + 8, w[2], w[3]);
   }
   uint32_t px[14];
-  if (VER == 6) {
+  if (VER == 4) {
+    const uint32_t zeros = pana4_packet(w, px);
+    if (live && zeros && jb.zero_slot) {
+      // mRaw->mBadPixelPositions (PanasonicV4Decompressor.cpp:206-207, :228-235): (y << 16) | x
+      const uint32_t idx0 = ul * 14u;
+      const uint32_t row = idx0 / jb.width, col0 = idx0 - row * jb.width;
+      for (uint32_t z = zeros; z; z &= z - 1u) {
+        const uint32_t i = (uint32_t)__ffs((int)z) - 1u;
+        const uint32_t at = atomicAdd(zero_count + (jb.zero_slot - 1u), 1u);
+        if (at < PANA_ZERO_CAP)
+          zero_list[(uint64_t)(jb.zero_slot - 1u) * PANA_ZERO_CAP + at] = (row << 16) | (col0 + i);
+      }
+    }
+  } else if (VER == 6) {
     uint32_t oddeven[2] = {0, 0}, nonzero[2] = {0, 0}, pmul = 0, pixel_base = 0;
     pana6_pixels<BPS, 0, 0>(w, px, oddeven, nonzero, pmul, pixel_base);
   } else {

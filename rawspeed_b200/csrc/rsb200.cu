@@ -127,6 +127,11 @@ struct rsb200_plan {
   uint16_t* d_raw_tables = nullptr;
   std::vector<SrawGroup> sraw_groups;
   std::vector<PanaGroup> pana_groups;
+  // Panasonic V4 bad-pixel lists: slot per job that asked for them (-1 otherwise)
+  std::vector<int> pana_zero_slot;
+  uint32_t* d_pana_zero_count = nullptr;
+  uint32_t* d_pana_zero_list = nullptr;
+  int pana_zero_slots = 0;
   std::vector<ScaleGroup> scale_groups;
   // Phase One (shares d_arw2_bad / h_arw2_bad as the per-job error flags)
   P1StripDev* d_p1_strips = nullptr;
@@ -773,18 +778,25 @@ extern "C" int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* j
   std::map<std::pair<int, int>, std::vector<PanaJobDev>> buckets;
   for (int i = 0; i < njobs; ++i) {
     const rsb200_pana_job& j = jobs[i];
-    const int bps = j.version == 7 ? 14 : j.bps;
-    const bool vok = (j.version == 5 || j.version == 6 || j.version == 7) && (bps == 12 || bps == 14);
-    const uint32_t npix = !vok ? 1u : (j.version == 6 ? (bps == 14 ? 11u : 14u) : 128u / (uint32_t)bps);
+    const int bps = j.version == 7 ? 14 : (j.version == 4 ? 12 : j.bps);
+    const bool vok = (j.version == 4 || j.version == 5 || j.version == 6 || j.version == 7) &&
+                     (bps == 12 || bps == 14);
+    const uint32_t npix = !vok ? 1u
+                               : (j.version == 4 ? 14u
+                                                 : (j.version == 6 ? (bps == 14 ? 11u : 14u)
+                                                                   : 128u / (uint32_t)bps));
     const uint64_t area = (uint64_t)j.width * j.height;
     const uint64_t units = area / npix;
-    // the constructors' checks (PanasonicV5Decompressor.cpp:58-116, V6 :146-176, V7 :40-64)
+    // the constructors' checks (PanasonicV4Decompressor.cpp:49-90, V5 :58-116, V6 :146-176,
+    // V7 :40-64)
     uint64_t need = units * 16;
-    if (j.version == 5)
+    if (j.version == 5 || (j.version == 4 && j.section_split_offset != 0))
       need = ((units + 1023) / 1024) * 0x4000ull;
     const bool ok = vok && j.width > 0 && j.height > 0 && j.width % npix == 0 &&
                     j.in_size >= need && (j.out_offset % 2) == 0 && (j.out_pitch % 2) == 0 &&
-                    (uint64_t)j.width * 2 <= j.out_pitch && area < 0xFFFF0000ull;
+                    (uint64_t)j.width * 2 <= j.out_pitch && area < 0xFFFF0000ull &&
+                    (j.version != 4 || (j.section_split_offset <= 0x4000u && j.width <= 0xFFFFu &&
+                                        j.height <= 0xFFFFu));
     if (!ok) {
       delete p;
       return set_err(ctx, RSB200_ERR_ARG, "pana job %d: malformed descriptor", i);
@@ -797,6 +809,14 @@ extern "C" int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* j
     d.width = j.width;
     d.height = j.height;
     d.units = (uint32_t)units;
+    p->pana_zero_slot.push_back(-1);
+    if (j.version == 4) {
+      d.split = j.section_split_offset;
+      if (!j.zero_is_not_bad) {
+        p->pana_zero_slot.back() = p->pana_zero_slots;
+        d.zero_slot = (uint32_t)++p->pana_zero_slots;
+      }
+    }
     buckets[{(int)j.version, bps}].push_back(d);
     p->in_bytes += units * 16;
     p->out_bytes += area * 2;
@@ -831,17 +851,38 @@ extern "C" int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* j
     }
     p->pana_groups.push_back(g);
   }
+  if (p->pana_zero_slots) {
+    cudaError_t e = cudaMalloc(&p->d_pana_zero_count, sizeof(uint32_t) * (size_t)p->pana_zero_slots);
+    if (e == cudaSuccess)
+      e = cudaMalloc(&p->d_pana_zero_list,
+                     sizeof(uint32_t) * (size_t)PANA_ZERO_CAP * (size_t)p->pana_zero_slots);
+    if (e != cudaSuccess) {
+      rsb200_plan_destroy(p);
+      return set_err(ctx, RSB200_ERR_CUDA, "pana plan: bad-pixel lists: %s", cudaGetErrorString(e));
+    }
+  }
   p->launches_per_run = (int)p->pana_groups.size();
   *out = p;
   return RSB200_OK;
 }
 
-static cudaError_t run_pana_group(const PanaGroup& g, const uint8_t* in, uint8_t* outp,
-                                  cudaStream_t st) {
+static_assert(PANA_ZERO_CAP == RSB200_PANA_BAD_CAP, "header and kernel disagree");
+
+static cudaError_t run_pana_group(const rsb200_plan* p, const PanaGroup& g, const uint8_t* in,
+                                  uint8_t* outp, cudaStream_t st) {
   const uint32_t nb = (g.total_units + PANA_NT - 1) / PANA_NT;
 #define RSB_PANA(V, B)                                                                     \
-  pana_kernel<V, B><<<nb, PANA_NT, 0, st>>>(in, outp, g.d_jobs, g.njobs, g.total_units)
-  if (g.version == 5 && g.bps == 12)
+  pana_kernel<V, B><<<nb, PANA_NT, 0, st>>>(in, outp, g.d_jobs, g.njobs, g.total_units,    \
+                                            p->d_pana_zero_count, p->d_pana_zero_list)
+  if (g.version == 4) {
+    if (p->pana_zero_slots) {
+      const cudaError_t e = cudaMemsetAsync(p->d_pana_zero_count, 0,
+                                            sizeof(uint32_t) * (size_t)p->pana_zero_slots, st);
+      if (e != cudaSuccess)
+        return e;
+    }
+    RSB_PANA(4, 12);
+  } else if (g.version == 5 && g.bps == 12)
     RSB_PANA(5, 12);
   else if (g.version == 5)
     RSB_PANA(5, 14);
@@ -1706,7 +1747,7 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
     ctx->launches++;
   } else if (p->kind == 5) {
     for (const PanaGroup& g : p->pana_groups) {
-      CUDA_TRY(ctx, run_pana_group(g, in, outp, st));
+      CUDA_TRY(ctx, run_pana_group(p, g, in, outp, st));
       ctx->launches++;
     }
   } else if (p->kind == 4) {
@@ -1979,6 +2020,31 @@ extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, 
   return first;
 }
 
+extern "C" int rsb200_plan_bad_pixels(rsb200_plan* p, int job, uint32_t* positions, uint32_t cap,
+                                      uint32_t* count) {
+  if (!p || !count)
+    return RSB200_ERR_ARG;
+  rsb200_ctx* ctx = p->ctx;
+  *count = 0;
+  if (p->kind != 5 || job < 0 || job >= (int)p->pana_zero_slot.size())
+    return set_err(ctx, RSB200_ERR_ARG, "plan_bad_pixels: not a job of a Panasonic plan");
+  if (!p->ran)
+    return set_err(ctx, RSB200_ERR_ARG, "plan_bad_pixels: plan has not been run");
+  const int slot = p->pana_zero_slot[job];
+  if (slot < 0)
+    return RSB200_OK; // zero_is_not_bad (or not V4): the reference collects nothing
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
+  uint32_t n = 0;
+  CUDA_TRY(ctx, cudaMemcpy(&n, p->d_pana_zero_count + slot, sizeof n, cudaMemcpyDeviceToHost));
+  *count = n;
+  const uint32_t take = std::min(std::min(n, cap), (uint32_t)PANA_ZERO_CAP);
+  if (take && positions)
+    CUDA_TRY(ctx, cudaMemcpy(positions, p->d_pana_zero_list + (size_t)slot * PANA_ZERO_CAP,
+                             sizeof(uint32_t) * take, cudaMemcpyDeviceToHost));
+  return RSB200_OK;
+}
+
 extern "C" int rsb200_plan_bytes(const rsb200_plan* p, uint64_t* in_bytes,
                                  uint64_t* out_bytes, uint64_t* pixels) {
   if (!p)
@@ -2011,6 +2077,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     cudaFree(g.d_jobs);
   for (ScaleGroup& g : p->scale_groups)
     cudaFree(g.d_jobs);
+  cudaFree(p->d_pana_zero_count);
+  cudaFree(p->d_pana_zero_list);
   cudaFree(p->d_p1_strips);
   cudaFree(p->d_p1_jobs);
   cudaFree(p->d_nikon_luts);

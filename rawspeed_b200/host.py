@@ -30,7 +30,8 @@ EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_dng_decompress", "rsb200h_cr2_decompress", "rsb200h_cr2_ljpeg_decode",
            "rsb200h_huff_check", "rsb200h_unpack_form", "rsb200h_pentax_decompress",
            "rsb200h_sraw_interpolate", "rsb200h_nikon_decompress", "rsb200h_sony_arw2",
-           "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white"]
+           "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white",
+           "rsb200h_panasonic_v4"]
 
 _lib = None
 
@@ -178,6 +179,23 @@ def panasonic(version, img, w, data, bps=14):
     e.check(L.rsb200h_panasonic(version, C.c_void_p(img.ctypes.data), w, img.shape[0],
                                 img.shape[1] * 2, p, C.c_uint32(n), bps, C.byref(e)))
     return img
+
+
+def panasonic_v4(img, w, data, zero_is_not_bad=True, split=0, cap=1 << 20, construct_only=False):
+    """PanasonicV4Decompressor(img, data, zero_is_not_bad, split).decompress() via the host
+    mirror; returns the sorted bad (zero) pixel positions (row << 16 | col)."""
+    p, n = _u8(data)
+    z = (C.c_uint32 * cap)()
+    nz = C.c_uint32(0)
+    e = _Err()
+    L = lib()
+    L.rsb200h_panasonic_v4.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_uint32,
+                                       C.c_int, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+                                       C.POINTER(C.c_uint32), C.c_int, C.POINTER(_Err)]
+    e.check(L.rsb200h_panasonic_v4(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
+                                   p, C.c_uint32(n), int(zero_is_not_bad), split, z, cap,
+                                   C.byref(nz), int(construct_only), C.byref(e)))
+    return sorted(z[:min(nz.value, cap)])
 
 
 def phaseone(img, w, file, strips):

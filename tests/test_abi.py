@@ -43,6 +43,12 @@ int main(void){
   printf("%zu %zu %zu\n", sizeof(rsb200_raw_job), offsetof(rsb200_raw_job, format), offsetof(rsb200_raw_job, table));
   printf("%zu %zu %zu %zu\n", offsetof(rsb200_ljpeg_scan, init_pred), offsetof(rsb200_ljpeg_scan, out_offset),
          offsetof(rsb200_cr2_job, frame_w), offsetof(rsb200_cr2_job, out_offset));
+  printf("%zu %zu %zu %zu\n", sizeof(rsb200_pana_job), offsetof(rsb200_pana_job, version),
+         offsetof(rsb200_pana_job, zero_is_not_bad), offsetof(rsb200_pana_job, section_split_offset));
+  printf("%zu %zu %zu %zu\n", sizeof(rsb200_scale_job), offsetof(rsb200_scale_job, black_separate),
+         offsetof(rsb200_scale_job, white_point), offsetof(rsb200_scale_job, path));
+  printf("%zu %zu %zu %zu %zu\n", sizeof(rsb200_arw2_job), sizeof(rsb200_nikon_job),
+         sizeof(rsb200_phaseone_job), sizeof(rsb200_phaseone_strip), offsetof(rsb200_nikon_job, pup));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
@@ -55,7 +61,13 @@ int main(void){
             _abi.SrawJob.out_offset.offset, _abi.SrawJob.out_pitch.offset,
             C.sizeof(_abi.RawJob), _abi.RawJob.format.offset, _abi.RawJob.table.offset,
             _abi.LJpegScan.init_pred.offset, _abi.LJpegScan.out_offset.offset,
-            _abi.Cr2Job.frame_w.offset, _abi.Cr2Job.out_offset.offset]
+            _abi.Cr2Job.frame_w.offset, _abi.Cr2Job.out_offset.offset,
+            C.sizeof(_abi.PanaJob), _abi.PanaJob.version.offset, _abi.PanaJob.zero_is_not_bad.offset,
+            _abi.PanaJob.section_split_offset.offset,
+            C.sizeof(_abi.ScaleJob), _abi.ScaleJob.black_separate.offset,
+            _abi.ScaleJob.white_point.offset, _abi.ScaleJob.path.offset,
+            C.sizeof(_abi.Arw2Job), C.sizeof(_abi.NikonJob), C.sizeof(_abi.PhaseOneJob),
+            C.sizeof(_abi.PhaseOneStrip), _abi.NikonJob.pup.offset]
     assert got == want
 
 

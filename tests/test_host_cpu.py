@@ -169,3 +169,15 @@ def test_scale_black_white_needs_the_device():
     a = _sensor(64, 24, 6)
     with pytest.raises(Exception):
         host.scale_black_white(a, 64, (0, 0, 64, 24), black_level=500, white=15000)
+
+
+def test_panasonic_v4_ctor_errors_same_class():
+    data = synth.lcg_bytes(0x8000, 2)
+    for args in ((port.new_image(15, 2), 15, data),                     # width % 14
+                 (port.new_image(14, 2), 14, data, True, 0x4001),       # split beyond the block
+                 (port.new_image(1400, 40), 1400, data),                # not enough data
+                 (port.new_image(1400, 40), 1400, data, True, 0x2008)):
+        _same_class(lambda: port.panasonic_v4(*args),
+                    lambda: host.panasonic_v4(*args, construct_only=True))
+    # a well-formed descriptor constructs (nothing runs)
+    host.panasonic_v4(port.new_image(28, 2), 28, data, True, 0x2008, construct_only=True)
