@@ -382,6 +382,28 @@ def scale_values(img, w, crop, black_sep, white, dither=True, sse2=None):
     return img
 
 
+def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
+    """DngOpcodes(ri, data) + applyOpCodes(ri) in place; img: uint16 image or uint32 array of
+    an F32 image; crop = [off_x, off_y, crop_w, crop_h].  Returns (crop after TrimBounds,
+    mBadPixelPositions).  On an exception `dng_opcodes.partial` holds (crop, list, applied)."""
+    p, n = _u8(data)
+    im = _img(img, w, cpp)
+    cr = (C.c_int * 4)(*[int(v) for v in crop])
+    bad = (C.c_uint32 * cap)()
+    nbad = C.c_uint32(0)
+    applied = C.c_int(0)
+    e = Err()
+    L = lib()
+    L.rso_dng_opcodes.argtypes = [C.POINTER(Image), C.POINTER(C.c_int), C.c_char_p, C.c_uint32,
+                                  C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32),
+                                  C.POINTER(C.c_int), C.POINTER(Err)]
+    rc = L.rso_dng_opcodes(C.byref(im), cr, p, C.c_uint32(n), bad, cap, C.byref(nbad),
+                           C.byref(applied), C.byref(e))
+    dng_opcodes.partial = (list(cr), list(bad[:min(nbad.value, cap)]), applied.value)
+    e.check(rc)
+    return list(cr), list(bad[:min(nbad.value, cap)])
+
+
 class BlackArea(C.Structure):
     _fields_ = [("offset", C.c_uint32), ("size", C.c_uint32), ("is_vertical", C.c_int)]
 

@@ -283,6 +283,30 @@ def panasonic(version, img, w, data, bps=14, nthreads=1, reps=1):
     return ms.value
 
 
+def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
+    """Reference DngOpcodes(ri, data) + applyOpCodes(ri) (ref_dng_opcodes); img: uint16 image or
+    uint32 array holding an F32 image.  Returns (crop, mBadPixelPositions); `dng_opcodes.stage`
+    = which half threw (1 constructor, 2 apply, 0 none)."""
+    p, n = _u8(data)
+    cr = (C.c_int * 4)(*[int(v) for v in crop])
+    bad = (C.c_uint32 * cap)()
+    nbad = C.c_uint32(0)
+    stage = C.c_int(0)
+    e = Err()
+    L = lib()
+    is_f32 = img.dtype == np.uint32
+    L.ref_dng_opcodes.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.POINTER(C.c_int), C.c_char_p,
+                                  C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+                                  C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(Err)]
+    rc = L.ref_dng_opcodes(C.c_void_p(img.ctypes.data), int(is_f32), w, img.shape[0], cpp,
+                           img.shape[1] * (4 if is_f32 else 2), cr, p, C.c_uint32(n), bad, cap,
+                           C.byref(nbad), C.byref(stage), C.byref(e))
+    dng_opcodes.stage = stage.value
+    dng_opcodes.partial = (list(cr), list(bad[:min(nbad.value, cap)]))
+    e.check(rc)
+    return list(cr), list(bad[:min(nbad.value, cap)])
+
+
 def scale_values(img, w, crop, black_sep, white, dither=True, nthreads=1):
     """Reference RawImageData::scaleBlackWhite() with blackLevelSeparate / whitePoint given
     (ref_scale_values); crop = (off_x, off_y, crop_w, crop_h)."""

@@ -30,6 +30,7 @@
 #include "codes/HuffmanCode.h"
 #include "codes/PrefixCodeDecoder.h"
 #include "codes/PrefixCodeVectorEncoder.h"
+#include "common/DngOpcodes.h"
 #include "common/RawImage.h"
 #include "common/RawspeedException.h"
 #include "decoders/RawDecoderException.h"
@@ -387,6 +388,48 @@ int ref_scale_black_white(uint16_t* img_data, int w, int h, int cpp, int pitch, 
       for (int i = 0; i < 4; ++i)
         black_sep[i] = img->blackLevelSeparateStorage[i];
     *white = img->whitePoint.has_value() ? *img->whitePoint : -1;
+  });
+}
+
+// DngOpcodes(ri, bs) + applyOpCodes(ri) on a uint16 (is_f32 == 0) or float image with the crop
+// crop[4] = (mOffset.x, mOffset.y, dim.x, dim.y); reports the crop and mBadPixelPositions
+// afterwards.  stage: which half threw (1 constructor, 2 applyOpCodes), 0 if none.
+int ref_dng_opcodes(void* img_data, int is_f32, int w, int h, int cpp, int pitch, int* crop,
+                    const uint8_t* data, uint32_t size, uint32_t* bad, uint32_t bad_cap,
+                    uint32_t* nbad, int* stage, RefErr* e) {
+  *stage = 0;
+  return guarded(e, [&] {
+    RawImage img = RawImage::create(iPoint2D(w, h),
+                                    is_f32 ? RawImageType::F32 : RawImageType::UINT16, cpp);
+    if (img->pitch != pitch)
+      ThrowRDE("driver: pitch mismatch (%d vs %d)", img->pitch, pitch);
+    uint8_t* base = is_f32 ? reinterpret_cast<uint8_t*>(&img->getF32DataAsUncroppedArray2DRef()(0, 0))
+                           : reinterpret_cast<uint8_t*>(&img->getU16DataAsUncroppedArray2DRef()(0, 0));
+    std::memcpy(base, img_data, static_cast<size_t>(pitch) * h);
+    if (crop[0] || crop[1] || crop[2] != w || crop[3] != h)
+      img->subFrame(iRectangle2D(iPoint2D(crop[0], crop[1]), iPoint2D(crop[2], crop[3])));
+    auto copyBack = [&] {
+      std::memcpy(img_data, base, static_cast<size_t>(pitch) * h);
+      const iPoint2D o = img->getCropOffset();
+      crop[0] = o.x;
+      crop[1] = o.y;
+      crop[2] = img->dim.x;
+      crop[3] = img->dim.y;
+      *nbad = static_cast<uint32_t>(img->mBadPixelPositions.size());
+      for (uint32_t i = 0; i < *nbad && i < bad_cap; ++i)
+        bad[i] = img->mBadPixelPositions[i];
+    };
+    *stage = 1;
+    DngOpcodes codes(img, ByteStream(DataBuffer(Buffer(data, size), Endianness::little)));
+    *stage = 2;
+    try {
+      codes.applyOpCodes(img);
+    } catch (...) {
+      copyBack();
+      throw;
+    }
+    *stage = 0;
+    copyBack();
   });
 }
 

@@ -17,6 +17,7 @@
 
 #include <limits.h>
 #include <setjmp.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -3579,4 +3580,422 @@ int rso_scale_black_white(rso_image* img, int off_x, int off_y, int crop_w, int 
   rc = rso_scale_values(img, off_x, off_y, crop_w, crop_h, black_sep, *white, dither,
                         force_sse2 < 0 ? rso_scale_uses_sse2(black_sep, *white) : force_sse2, c.e);
   return rc;
+}
+
+/* ------------------------------------------------------------------
+ * DngOpcodes (common/DngOpcodes.cpp)
+ * ------------------------------------------------------------------ */
+typedef struct {
+  int code;
+  uint32_t value;            /* FixBadPixelsConstant */
+  uint32_t* bad;             /* FixBadPixelsList */
+  uint32_t nbad;
+  int top, left, w, h;       /* ROI (pos, dim) */
+  uint32_t firstPlane, planes, rowPitch, colPitch;
+  uint16_t* lookup;          /* MapTable / MapPolynomial: 65536 entries */
+  float* deltaF;             /* Delta / Scale per row / column */
+  uint32_t ndelta;
+} dng_op;
+
+typedef struct {
+  dng_op* ops;
+  uint32_t nops;
+  uint32_t* list; /* mBadPixelPositions */
+  uint32_t nlist, caplist;
+} dng_state;
+
+static void dng_free(dng_state* st) {
+  uint32_t i;
+  for (i = 0; i < st->nops; i++) {
+    free(st->ops[i].bad);
+    free(st->ops[i].lookup);
+    free(st->ops[i].deltaF);
+  }
+  free(st->ops);
+  free(st->list);
+  st->ops = NULL;
+  st->list = NULL;
+}
+
+static uint32_t bs_get_u32be(bstream* s) {
+  uint32_t v;
+  bs_check(s, 4);
+  v = ld_be32(s->data + s->pos);
+  s->pos += 4;
+  return v;
+}
+/* ByteStream::check(nmemb, size) / skipBytes(nmemb, size) (io/ByteStream.h:71-75, :130-132) */
+static uint32_t bs_check2(const bstream* s, uint32_t nmemb, uint32_t size) {
+  if (size && nmemb > 0xFFFFFFFFu / size)
+    THROW_IOE(s->c, "Integer overflow when calculating stream length");
+  bs_check(s, (uint64_t)nmemb * size);
+  return nmemb * size;
+}
+static uint64_t dng_round_up_div(uint64_t a, uint64_t b) { return a ? 1 + (a - 1) / b : 0; }
+
+/* ROIOpcode ctor (:193-226): rectangle inside {0, 0, dim} (inclusive), bottomRight >= topLeft */
+static void dng_read_roi(rso_ctx* c, bstream* bs, int dim_x, int dim_y, dng_op* op) {
+  const uint32_t top = bs_get_u32be(bs), left = bs_get_u32be(bs), bottom = bs_get_u32be(bs),
+                 right = bs_get_u32be(bs);
+  const int tx = (int)left, ty = (int)top, bx = (int)right, by = (int)bottom;
+  const int ok = tx >= 0 && ty >= 0 && tx <= dim_x && ty <= dim_y && bx >= 0 && by >= 0 &&
+                 bx <= dim_x && by <= dim_y && bx >= tx && by >= ty;
+  if (!ok)
+    THROW_RDE(c, "Rectangle (%d, %d, %d, %d) not inside image (%d, %d, %d, %d).", tx, ty, bx, by, 0,
+              0, dim_x, dim_y);
+  op->left = tx;
+  op->top = ty;
+  op->w = bx - tx;
+  op->h = by - ty;
+}
+
+/* PixelOpcode ctor (:353-381) */
+static void dng_read_pixel_op(rso_ctx* c, bstream* bs, int cpp, int dim_x, int dim_y, dng_op* op) {
+  dng_read_roi(c, bs, dim_x, dim_y, op);
+  op->firstPlane = bs_get_u32be(bs);
+  op->planes = bs_get_u32be(bs);
+  if (op->planes == 0 || op->firstPlane > (uint32_t)cpp || op->planes > (uint32_t)cpp ||
+      op->firstPlane + op->planes > (uint32_t)cpp)
+    THROW_RDE(c, "Bad plane params (first %u, num %u), got planes = %u", op->firstPlane, op->planes,
+              (unsigned)cpp);
+  op->rowPitch = bs_get_u32be(bs);
+  op->colPitch = bs_get_u32be(bs);
+  if (op->rowPitch < 1 || op->rowPitch > (uint32_t)op->h || op->colPitch < 1 ||
+      op->colPitch > (uint32_t)op->w)
+    THROW_RDE(c, "Invalid pitch");
+}
+
+static void dng_list_reserve(rso_ctx* c, dng_state* st, uint64_t extra) {
+  if ((uint64_t)st->nlist + extra > st->caplist) {
+    uint64_t ncap = ((uint64_t)st->nlist + extra) * 2 + 16;
+    uint32_t* n = (uint32_t*)realloc(st->list, ncap * sizeof(uint32_t));
+    if (!n || ncap > 0xFFFFFFFFull)
+      THROW_RDE(c, "out of memory");
+    st->list = n;
+    st->caplist = (uint32_t)ncap;
+  }
+}
+
+int rso_dng_opcodes(rso_image* img, int* crop, const uint8_t* data, uint32_t size, uint32_t* bad,
+                    uint32_t bad_cap, uint32_t* nbad, int* applied, rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  dng_state* volatile stp;
+  dng_state st;
+  bstream bs;
+  uint32_t opcode_count, i;
+  int int_x, int_y, int_w, int_h; /* integrated_subimg */
+  const int cpp = img->cpp;
+  volatile int done = 0;
+  memset(&st, 0, sizeof st);
+  stp = &st;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (applied)
+    *applied = 0;
+  if (nbad)
+    *nbad = 0;
+  if (setjmp(c.jb)) {
+    if (applied)
+      *applied = done;
+    dng_free((dng_state*)stp);
+    return c.e->code;
+  }
+  /* DngOpcodes::DngOpcodes (:666-726), big endian */
+  bs.c = &c;
+  bs.data = data;
+  bs.size = size;
+  bs.pos = 0;
+  opcode_count = bs_get_u32be(&bs);
+  {
+    const uint32_t orig = bs.pos;
+    for (i = 0; i < opcode_count; i++) {
+      uint32_t opcode_size;
+      bs_skip(&bs, 4);
+      bs_skip(&bs, 4);
+      bs_skip(&bs, 4);
+      opcode_size = bs_get_u32be(&bs);
+      bs_skip(&bs, opcode_size);
+    }
+    bs.pos = orig;
+  }
+  st.ops = (dng_op*)calloc(opcode_count ? opcode_count : 1, sizeof(dng_op));
+  if (!st.ops)
+    THROW_RDE(&c, "out of memory");
+  int_x = crop[0];
+  int_y = crop[1];
+  int_w = crop[2];
+  int_h = crop[3];
+  for (i = 0; i < opcode_count; i++) {
+    const uint32_t code = bs_get_u32be(&bs);
+    uint32_t flags, opcode_size;
+    bstream ob;
+    dng_op* op = &st.ops[st.nops];
+    bs_skip(&bs, 4); /* version */
+    flags = bs_get_u32be(&bs);
+    opcode_size = bs_get_u32be(&bs);
+    ob = bs_get_stream(&bs, opcode_size);
+    memset(op, 0, sizeof *op);
+    op->code = (int)code;
+    switch (code) {
+    case 1:
+    case 2:
+    case 3:
+    case 9:
+      /* known, not implemented (:751-757, :776): an error unless flagged optional */
+      if (!(flags & 1)) {
+        static const char* const names[] = {"", "WarpRectilinear", "WarpFisheye", "FixVignetteRadial",
+                                            "", "", "", "", "", "GainMap"};
+        THROW_RDE(&c, "Unsupported Opcode: %u (%s)", code, names[code]);
+      }
+      op = NULL;
+      break;
+    case 4: /* FixBadPixelsConstant (:149-185) */
+      st.nops++;
+      op->value = bs_get_u32be(&ob);
+      (void)bs_get_u32be(&ob); /* Bayer phase */
+      break;
+    case 5: { /* FixBadPixelsList (:263-325): coordinates of the uncropped image */
+      uint32_t npts, nrect, k;
+      uint64_t n = 0, capn;
+      st.nops++;
+      (void)bs_get_u32be(&ob); /* phase */
+      npts = bs_get_u32be(&ob);
+      nrect = bs_get_u32be(&ob);
+      {
+        const uint32_t orig = ob.pos;
+        bs_check(&ob, 0);
+        ob.pos += bs_check2(&ob, npts, 8);
+        ob.pos += bs_check2(&ob, nrect, 16);
+        ob.pos = orig;
+        bs_check(&ob, 0);
+      }
+      capn = (uint64_t)npts + 16;
+      op->bad = (uint32_t*)malloc(capn * sizeof(uint32_t));
+      if (!op->bad)
+        THROW_RDE(&c, "out of memory");
+      for (k = 0; k < npts; k++) {
+        const uint32_t y = bs_get_u32be(&ob), x = bs_get_u32be(&ob);
+        const int px = (int)x, py = (int)y;
+        if (!(px >= 0 && py >= 0 && px < img->w && py < img->h))
+          THROW_RDE(&c, "Bad point not inside image.");
+        op->bad[n++] = y << 16 | x;
+        op->nbad = (uint32_t)n;
+      }
+      for (k = 0; k < nrect; k++) {
+        dng_op r;
+        int y, x;
+        memset(&r, 0, sizeof r);
+        dng_read_roi(&c, &ob, img->w, img->h, &r);
+        if (n + (uint64_t)r.w * r.h > capn) {
+          uint32_t* nb;
+          capn = (n + (uint64_t)r.w * r.h) * 2;
+          nb = (uint32_t*)realloc(op->bad, capn * sizeof(uint32_t));
+          if (!nb)
+            THROW_RDE(&c, "out of memory");
+          op->bad = nb;
+        }
+        for (y = 0; y < r.h; y++)
+          for (x = 0; x < r.w; x++)
+            op->bad[n++] = (uint32_t)(r.top + y) << 16 | (uint32_t)(r.left + x);
+        op->nbad = (uint32_t)n;
+      }
+      break;
+    }
+    case 6: /* TrimBounds (:332-346) */
+      st.nops++;
+      dng_read_roi(&c, &ob, int_w, int_h, op);
+      int_x += op->left;
+      int_y += op->top;
+      int_w = op->w;
+      int_h = op->h;
+      break;
+    case 7: { /* MapTable (:446-466) */
+      uint32_t count, k;
+      st.nops++;
+      dng_read_pixel_op(&c, &ob, cpp, int_w, int_h, op);
+      count = bs_get_u32be(&ob);
+      if (count == 0 || count > 65536)
+        THROW_RDE(&c, "Invalid size of lookup table");
+      op->lookup = (uint16_t*)calloc(65536, sizeof(uint16_t));
+      if (!op->lookup)
+        THROW_RDE(&c, "out of memory");
+      for (k = 0; k < count; k++)
+        op->lookup[k] = bs_get_u16be(&ob);
+      for (k = count; k < 65536; k++)
+        op->lookup[k] = op->lookup[count - 1];
+      break;
+    }
+    case 8: { /* MapPolynomial (:473-505) */
+      double poly[9];
+      uint64_t psize;
+      uint32_t k, j;
+      st.nops++;
+      dng_read_pixel_op(&c, &ob, cpp, int_w, int_h, op);
+      psize = (uint64_t)bs_get_u32be(&ob) + 1;
+      bs_check(&ob, (uint32_t)(8 * psize)); /* implicit_cast<size_type>(8UL * polynomial_size) */
+      if (psize > 9)
+        THROW_RDE(&c, "A polynomial with more than 8 degrees not allowed");
+      for (k = 0; k < psize; k++) {
+        uint64_t bits;
+        bs_check(&ob, 8);
+        bits = ((uint64_t)ld_be32(ob.data + ob.pos) << 32) | ld_be32(ob.data + ob.pos + 4);
+        ob.pos += 8;
+        memcpy(&poly[k], &bits, 8);
+      }
+      op->lookup = (uint16_t*)calloc(65536, sizeof(uint16_t));
+      if (!op->lookup)
+        THROW_RDE(&c, "out of memory");
+      for (k = 0; k < 65536; k++) {
+        double val = poly[0], t;
+        for (j = 1; j < psize; j++)
+          val += poly[j] * pow((double)k / 65536.0, (double)j);
+        t = val * 65535.5;
+        t = t < 0.0 ? 0.0 : (t > 65535.0 ? 65535.0 : t); /* std::clamp<double>(.., 0, 65535) */
+        op->lookup[k] = (uint16_t)t;
+      }
+      break;
+    }
+    case 10:
+    case 11:
+    case 12:
+    case 13: { /* DeltaRowOrCol (:535-589): 10 / 12 select the row index, 11 / 13 the column */
+      uint32_t count, k;
+      uint64_t expected;
+      st.nops++;
+      dng_read_pixel_op(&c, &ob, cpp, int_w, int_h, op);
+      count = bs_get_u32be(&ob);
+      (void)bs_check2(&ob, count, 4);
+      expected = (code == 10 || code == 12) ? dng_round_up_div((uint64_t)op->h, op->rowPitch)
+                                            : dng_round_up_div((uint64_t)op->w, op->colPitch);
+      if (expected != count)
+        THROW_RDE(&c, "Got unexpected number of elements (%llu), expected %u.",
+                  (unsigned long long)expected, count);
+      op->deltaF = (float*)malloc(((size_t)count + 1) * sizeof(float));
+      if (!op->deltaF)
+        THROW_RDE(&c, "out of memory");
+      for (k = 0; k < count; k++) {
+        const uint32_t bits = bs_get_u32be(&ob);
+        float f;
+        memcpy(&f, &bits, 4);
+        if (!isfinite(f))
+          THROW_RDE(&c, "Got bad float %f.", (double)f);
+        op->deltaF[k] = f;
+      }
+      op->ndelta = count;
+      break;
+    }
+    default:
+      THROW_RDE(&c, "Unknown unhandled Opcode: %u", code);
+    }
+    if (ob.size - ob.pos != 0)
+      THROW_RDE(&c, "Inconsistent length of opcode");
+    (void)op;
+  }
+
+  /* applyOpCodes (:730-735): setup() then apply(), in order */
+  for (i = 0; i < st.nops; i++) {
+    const dng_op* op = &st.ops[i];
+    const int ox = crop[0], oy = crop[1], dw = crop[2], dh = crop[3];
+    switch (op->code) {
+    case 4: {
+      int row, col;
+      if (img->is_f32)
+        THROW_RDE(&c, "Only 16 bit images supported");
+      if (cpp > 1)
+        THROW_RDE(&c, "Only 1 component images supported");
+      for (row = 0; row < dh; row++) {
+        const uint16_t* p = (const uint16_t*)((const uint8_t*)img->data + (size_t)(oy + row) * (size_t)img->pitch) + ox;
+        for (col = 0; col < dw; col++)
+          if (p[col] == op->value) {
+            dng_list_reserve(&c, &st, 1);
+            st.list[st.nlist++] = ((uint32_t)ox | ((uint32_t)oy << 16)) + ((uint32_t)row << 16 | (uint32_t)col);
+          }
+      }
+      break;
+    }
+    case 5: /* inserted at the BEGINNING of the list (:319-321) */
+      dng_list_reserve(&c, &st, op->nbad);
+      memmove(st.list + op->nbad, st.list, (size_t)st.nlist * sizeof(uint32_t));
+      memcpy(st.list, op->bad, (size_t)op->nbad * sizeof(uint32_t));
+      st.nlist += op->nbad;
+      break;
+    case 6: /* ri->subFrame(roi) (common/RawImage.cpp:175-199) */
+      if (!(op->w > 0 && op->h > 0))
+        THROW_RDE(&c, "No positive crop area");
+      if (!(op->w <= dw - op->left && op->h <= dh - op->top))
+        break; /* "Crop skipped." */
+      crop[0] = ox + op->left;
+      crop[1] = oy + op->top;
+      crop[2] = op->w;
+      crop[3] = op->h;
+      break;
+    default: {
+      const uint64_t nax = dng_round_up_div((uint64_t)op->w, op->colPitch),
+                     nay = dng_round_up_div((uint64_t)op->h, op->rowPitch);
+      const int is_scale = op->code == 12 || op->code == 13;
+      const int by_row = op->code == 10 || op->code == 12;
+      int* deltaI = NULL;
+      uint64_t y, x;
+      uint32_t p;
+      if (op->lookup) {
+        if (img->is_f32)
+          THROW_RDE(&c, "Only 16 bit images supported");
+      } else if (!img->is_f32) {
+        /* DeltaRowOrCol::setup (:538-552) */
+        uint32_t k;
+        const double absLimit = 65535.0 / (double)65535.0F;
+        const double maxLimit = ((double)(2147483647 - 512) / 65535.0) / (double)1024.0F;
+        deltaI = (int*)malloc(((size_t)op->ndelta + 1) * sizeof(int));
+        if (!deltaI)
+          THROW_RDE(&c, "out of memory");
+        for (k = 0; k < op->ndelta; k++) {
+          const float f = op->deltaF[k];
+          const int ok = is_scale ? (f >= 0.0F && (double)f <= maxLimit) : ((double)fabsf(f) <= absLimit);
+          if (!ok) {
+            free(deltaI);
+            THROW_RDE(&c, "Got float %f which is unacceptable.", (double)f);
+          }
+          deltaI[k] = (int)((is_scale ? 1024.0F : 65535.0F) * f);
+        }
+      }
+      /* PixelOpcode::applyOP (:390-409) */
+      for (y = 0; y < nay; y++) {
+        uint8_t* rowp = (uint8_t*)img->data + (size_t)(oy + op->top + (int)(op->rowPitch * y)) * (size_t)img->pitch;
+        for (x = 0; x < nax; x++) {
+          for (p = 0; p < op->planes; p++) {
+            const size_t s = (size_t)ox * cpp + op->firstPlane + (size_t)(op->left + (int)(op->colPitch * x)) * cpp + p;
+            const uint64_t sel = by_row ? y : x;
+            if (img->is_f32) {
+              float* px = (float*)rowp + s;
+              *px = is_scale ? op->deltaF[sel] * *px : op->deltaF[sel] + *px;
+            } else {
+              uint16_t* px = (uint16_t*)rowp + s;
+              int v;
+              if (op->lookup)
+                v = op->lookup[*px];
+              else if (is_scale)
+                v = (deltaI[sel] * (int)*px + 512) >> 10;
+              else
+                v = deltaI[sel] + (int)*px;
+              *px = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+            }
+          }
+        }
+      }
+      free(deltaI);
+      break;
+    }
+    }
+    done = (int)i + 1;
+  }
+  if (applied)
+    *applied = done;
+  if (nbad)
+    *nbad = st.nlist;
+  for (i = 0; i < st.nlist && i < bad_cap && bad; i++)
+    bad[i] = st.list[i];
+  dng_free(&st);
+  return RSO_OK;
 }

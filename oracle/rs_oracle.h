@@ -244,6 +244,21 @@ int rso_scale_uses_sse2(const int* black_sep, int white);
 int rso_scale_values(rso_image* img, int off_x, int off_y, int crop_w, int crop_h,
                      const int* black_sep, int white, int dither, int sse2, rso_err* e);
 
+/* ---- DngOpcodes (common/DngOpcodes.cpp:62-798) ----
+ * (restated and pinned; device pass = K10)
+ * DngOpcodes(ri, bs) -- parse and validate the big-endian opcode list against the image and
+ * its current crop -- then applyOpCodes(ri): FixBadPixelsConstant (4), FixBadPixelsList (5),
+ * TrimBounds (6), MapTable (7), MapPolynomial (8), DeltaPerRow / Column (10 / 11),
+ * ScalePerRow / Column (12 / 13) on uint16 or float images; 1, 2, 3, 9 are known but
+ * unsupported (an error unless flagged optional).  img = the UNCROPPED buffer (uint16, or
+ * 32-bit samples holding floats when is_f32); crop[4] = mOffset.x, mOffset.y, dim.x, dim.y,
+ * updated by TrimBounds.  bad / *nbad: mRaw->mBadPixelPositions afterwards, in the reference's
+ * order (starts empty; at most bad_cap entries are stored, *nbad is the full count).
+ * An error raised by an opcode's setup()/apply() leaves the earlier opcodes applied, as in the
+ * reference; *applied (may be NULL) = opcodes fully applied. */
+int rso_dng_opcodes(rso_image* img, int* crop, const uint8_t* data, uint32_t size, uint32_t* bad,
+                    uint32_t bad_cap, uint32_t* nbad, int* applied, rso_err* e);
+
 /* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
  * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
  * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity

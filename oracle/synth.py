@@ -3,6 +3,8 @@ TEST INFRASTRUCTURE ONLY -- inputs for tests and bench, never product code."""
 from concurrent.futures import ThreadPoolExecutor
 import os
 
+import struct
+
 import numpy as np
 
 from . import port
@@ -425,3 +427,60 @@ def make_nikon_split(img_top, sel, pup, rows_after, seed):
         bits.append(0)
     by = np.packbits(np.array(bits, dtype=np.uint8))
     return np.concatenate([by, np.zeros(16, dtype=np.uint8)])
+
+
+# ---- DNG opcode lists (common/DngOpcodes.cpp:666-726; big endian) -----------------------------
+
+def _be32(*v):
+    return b"".join(struct.pack(">I", int(x) & 0xFFFFFFFF) for x in v)
+
+
+def dng_opcode_list(ops):
+    """ops: [(code, payload bytes[, flags])] -> the OpcodeList blob."""
+    out = _be32(len(ops))
+    for op in ops:
+        code, payload = op[0], op[1]
+        flags = op[2] if len(op) > 2 else 0
+        out += _be32(code, 0x01030000, flags, len(payload)) + payload
+    return np.frombuffer(out, dtype=np.uint8).copy()
+
+
+def dng_roi(top, left, bottom, right):
+    return _be32(top, left, bottom, right)
+
+
+def dng_pixel_area(roi, first_plane=0, planes=1, row_pitch=1, col_pitch=1):
+    return dng_roi(*roi) + _be32(first_plane, planes, row_pitch, col_pitch)
+
+
+def dng_fix_bad_constant(value, phase=0):
+    return (4, _be32(value, phase))
+
+
+def dng_fix_bad_list(points=(), rects=(), phase=0):
+    """points: [(y, x)], rects: [(top, left, bottom, right)] in uncropped coordinates."""
+    b = _be32(phase, len(points), len(rects))
+    for y, x in points:
+        b += _be32(y, x)
+    for r in rects:
+        b += dng_roi(*r)
+    return (5, b)
+
+
+def dng_trim_bounds(top, left, bottom, right):
+    return (6, dng_roi(top, left, bottom, right))
+
+
+def dng_map_table(area, table):
+    t = np.asarray(table, dtype=">u2")
+    return (7, area + _be32(t.size) + t.tobytes())
+
+
+def dng_map_polynomial(area, coeffs):
+    return (8, area + _be32(len(coeffs) - 1) + b"".join(struct.pack(">d", float(c)) for c in coeffs))
+
+
+def dng_delta(code, area, values):
+    """code 10 DeltaPerRow, 11 DeltaPerColumn, 12 ScalePerRow, 13 ScalePerColumn."""
+    v = np.asarray(values, dtype=">f4")
+    return (code, area + _be32(v.size) + v.tobytes())
