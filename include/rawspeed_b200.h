@@ -212,6 +212,7 @@ int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* jobs, int nj
  * order depends on its thread schedule).  *count = how many there were; at most `cap` (and at
  * most RSB200_PANA_BAD_CAP) are stored.  Waits for the run. */
 #define RSB200_PANA_BAD_CAP (1u << 22)
+/* (For a DNG opcode plan `job` is the index of a BAD_CONSTANT opcode, see K10.) */
 int rsb200_plan_bad_pixels(rsb200_plan* plan, int job, uint32_t* positions, uint32_t cap,
                            uint32_t* count);
 
@@ -275,6 +276,56 @@ typedef struct {
 #define RSB200_SCALE_PLAIN 2
 
 int rsb200_scale_plan_create(rsb200_ctx* ctx, const rsb200_scale_job* jobs, int njobs,
+                             rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
+/* K10: a DNG opcode list applied in one pass, in place. */
+/*   DngOpcodes::applyOpCodes            common/DngOpcodes.cpp:730-735  */
+/*   PixelOpcode::applyOP (lattice walk) :390-409, LookupOpcode :417-438,*/
+/*   OffsetPerRowOrCol :591-623, ScalePerRowOrCol :625-662,              */
+/*   FixBadPixelsConstant::apply :172-183                                */
+/* The list is parsed and validated on the host (the mirror's DngOpcodes */
+/* class does what the reference's constructor and setup() do); what     */
+/* reaches the device are the per-sample maps, with their ROI in         */
+/* UNCROPPED pixel coordinates.  Run with rsb200_plan_run(plan, NULL, 0, */
+/* d_image, bytes, stream).  NOT YET VALIDATED ON A B200.*/
+/* ------------------------------------------------------------------ */
+#define RSB200_DNGOP_LOOKUP 0       /* MapTable / MapPolynomial: v = table[v] (uint16)       */
+#define RSB200_DNGOP_OFFSET_ROW 1   /* DeltaPerRow: clampBits(delta[y] + v, 16) | d[y] + v    */
+#define RSB200_DNGOP_OFFSET_COL 2   /* DeltaPerColumn                                        */
+#define RSB200_DNGOP_SCALE_ROW 3    /* ScalePerRow: clampBits((d[y]*v + 512) >> 10, 16) | d*v */
+#define RSB200_DNGOP_SCALE_COL 4    /* ScalePerColumn                                        */
+#define RSB200_DNGOP_BAD_CONSTANT 5 /* FixBadPixelsConstant: collect samples == value        */
+typedef struct {
+  uint32_t kind;
+  uint32_t top, left, bottom, right; /* pixels top..bottom-1 x left..right-1 (uncropped)     */
+  uint32_t first_plane, planes;      /* components first_plane .. first_plane+planes-1       */
+  uint32_t row_pitch, col_pitch;     /* every row_pitch-th row / col_pitch-th column of the ROI */
+  uint32_t table;  /* LOOKUP: index into `tables`; OFFSET / SCALE: first element in `deltas`
+                      (one per affected row resp. column: int32 = (int)(f2iScale * f) for
+                      uint16 images, the float itself for float images)                      */
+  uint32_t value;  /* BAD_CONSTANT                                                           */
+  uint32_t reserved;
+} rsb200_dng_op;
+
+typedef struct {
+  uint64_t offset;   /* byte offset of row 0 of the uncropped image; multiple of 16          */
+  uint32_t pitch;    /* bytes between rows; multiple of 16                                   */
+  uint32_t width;    /* uncropped pixels per row                                             */
+  uint32_t height;
+  uint32_t cpp;      /* 1 .. 4                                                               */
+  uint32_t is_f32;   /* samples are 32-bit floats instead of uint16                          */
+  uint32_t first_op; /* this image's opcodes: ops[first_op .. first_op + num_ops)            */
+  uint32_t num_ops;
+  uint32_t reserved;
+} rsb200_dngop_job;
+
+/* tables: ntables x 65536 uint16; deltas: ndeltas 32-bit words.  The positions a
+ * BAD_CONSTANT opcode collected ((row << 16) | col, uncropped coordinates, unordered) are
+ * read with rsb200_plan_bad_pixels(plan, index of the opcode in `ops`, ...). */
+int rsb200_dngop_plan_create(rsb200_ctx* ctx, const rsb200_dngop_job* jobs, int njobs,
+                             const rsb200_dng_op* ops, int nops, const uint16_t* tables,
+                             int ntables, const uint32_t* deltas, int ndeltas,
                              rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */

@@ -3697,9 +3697,15 @@ int rso_dng_opcodes(rso_image* img, int* crop, const uint8_t* data, uint32_t siz
   if (nbad)
     *nbad = 0;
   if (setjmp(c.jb)) {
+    dng_state* sp = (dng_state*)stp;
     if (applied)
       *applied = done;
-    dng_free((dng_state*)stp);
+    /* an apply-time error leaves the earlier opcodes' list entries in place */
+    if (nbad)
+      *nbad = sp->nlist;
+    for (i = 0; i < sp->nlist && i < bad_cap && bad; i++)
+      bad[i] = sp->list[i];
+    dng_free(sp);
     return c.e->code;
   }
   /* DngOpcodes::DngOpcodes (:666-726), big endian */

@@ -75,6 +75,23 @@ class ScaleJob(C.Structure):
 SCALE_AUTO, SCALE_SSE2, SCALE_PLAIN = 0, 1, 2
 
 
+class DngOp(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("top", C.c_uint32), ("left", C.c_uint32),
+                ("bottom", C.c_uint32), ("right", C.c_uint32), ("first_plane", C.c_uint32),
+                ("planes", C.c_uint32), ("row_pitch", C.c_uint32), ("col_pitch", C.c_uint32),
+                ("table", C.c_uint32), ("value", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class DngOpJob(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("pitch", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("cpp", C.c_uint32), ("is_f32", C.c_uint32),
+                ("first_op", C.c_uint32), ("num_ops", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+(DNGOP_LOOKUP, DNGOP_OFFSET_ROW, DNGOP_OFFSET_COL, DNGOP_SCALE_ROW, DNGOP_SCALE_COL,
+ DNGOP_BAD_CONSTANT) = range(6)
+
+
 class PhaseOneStrip(C.Structure):
     _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint32), ("row", C.c_uint32)]
 
@@ -128,7 +145,7 @@ EXPORTS = [
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_raw_plan_create", "rsb200_sraw_plan_create",
     "rsb200_pentax_plan_create", "rsb200_arw2_plan_create", "rsb200_nikon_plan_create",
-    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_scale_plan_create", "rsb200_plan_bad_pixels",
+    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_scale_plan_create", "rsb200_plan_bad_pixels", "rsb200_dngop_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",

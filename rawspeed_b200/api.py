@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Arw2Job, NikonJob, PanaJob, ScaleJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, NikonJob, PanaJob, ScaleJob, DngOp, DngOpJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -211,6 +211,27 @@ def scale_plan(ctx, jobs):
     h = C.c_void_p()
     ctx.check(ctx._lib.rsb200_scale_plan_create(ctx.h, arr, len(jobs), C.byref(h)))
     return Plan(ctx, h, len(jobs))
+
+
+def dngop_plan(ctx, jobs, ops, tables=None, deltas=None):
+    """A DNG opcode list per image, applied in one pass in place (DngOpcodes::applyOpCodes);
+    tables: (n, 65536) uint16, deltas: uint32 words; run with plan.run(None, d_image).
+    plan.bad_pixels(k) reads the positions BAD_CONSTANT opcode k collected."""
+    ja = (DngOpJob * len(jobs))(*jobs)
+    oa = (DngOp * max(1, len(ops)))(*ops)
+    tp, nt, dp, nd = None, 0, None, 0
+    if tables is not None and len(tables):
+        tables = np.ascontiguousarray(tables, dtype=np.uint16).reshape(-1, 65536)
+        tp, nt = tables.ctypes.data_as(C.POINTER(C.c_uint16)), tables.shape[0]
+    if deltas is not None and len(deltas):
+        deltas = np.ascontiguousarray(deltas, dtype=np.uint32)
+        dp, nd = deltas.ctypes.data_as(C.POINTER(C.c_uint32)), deltas.size
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_dngop_plan_create(ctx.h, ja, len(jobs), oa, len(ops), tp, nt, dp, nd,
+                                                C.byref(h)))
+    plan = Plan(ctx, h, len(jobs))
+    plan._keep = (tables, deltas)
+    return plan
 
 
 def phaseone_plan(ctx, jobs, strips):

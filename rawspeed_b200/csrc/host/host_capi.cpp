@@ -305,6 +305,105 @@ int rsb200h_panasonic_v4(uint16_t* img_data, int w, int h, int pitch, const uint
   });
 }
 
+namespace {
+RawImage makeAnyImage(const void* src, int is_f32, int w, int h, int cpp, int pitch, const int* crop) {
+  RawImage img = RawImage::create(iPoint2D(w, h), is_f32 ? RawImageType::F32 : RawImageType::UINT16,
+                                  (uint32_t)cpp);
+  if (img->pitch != pitch)
+    ThrowRDE("test harness: pitch mismatch (%d vs %d)", img->pitch, pitch);
+  std::memcpy(img->getByteData(), src, (size_t)pitch * h);
+  if (crop[0] || crop[1] || crop[2] != w || crop[3] != h)
+    img->subFrame(iRectangle2D(crop[0], crop[1], crop[2], crop[3]));
+  return img;
+}
+} // namespace
+
+// DngOpcodes(ri, data) + applyOpCodes(ri) on a uint16 / float image with the crop crop[4] =
+// (mOffset.x, mOffset.y, dim.x, dim.y); reports crop and mBadPixelPositions afterwards (also
+// when applyOpCodes throws: the opcodes before the failing one stay applied).  stage: which
+// half threw (1 constructor, 2 applyOpCodes), 0 if none.
+int rsb200h_dng_opcodes(void* img_data, int is_f32, int w, int h, int cpp, int pitch, int* crop,
+                        const uint8_t* data, uint32_t size, uint32_t* bad, uint32_t bad_cap,
+                        uint32_t* nbad, int* stage, rsb200h_err* e) {
+  *stage = 0;
+  return guarded(e, [&] {
+    RawImage img = makeAnyImage(img_data, is_f32, w, h, cpp, pitch, crop);
+    auto copyBack = [&] {
+      std::memcpy(img_data, img->getByteData(), img->getByteSize());
+      const iPoint2D o = img->getCropOffset();
+      crop[0] = o.x;
+      crop[1] = o.y;
+      crop[2] = img->dim.x;
+      crop[3] = img->dim.y;
+      *nbad = (uint32_t)img->mBadPixelPositions.size();
+      for (uint32_t i = 0; i < *nbad && i < bad_cap; ++i)
+        bad[i] = img->mBadPixelPositions[i];
+    };
+    *stage = 1;
+    DngOpcodes codes(img, ByteStream(data, size));
+    *stage = 2;
+    try {
+      codes.applyOpCodes(img);
+    } catch (...) {
+      copyBack();
+      throw;
+    }
+    *stage = 0;
+    copyBack();
+  });
+}
+
+// The list in device form (DngOpcodes::lower) without running anything: what applyOpCodes would
+// upload.  Buffers are caller-allocated (capacities in elements); counts come back in n[4] =
+// {ops, tables, deltas, actions}; actions as pairs (kind: 0 list / 1 constant / 2 trim, index),
+// followed for a list action by nothing -- the lists themselves are read with list_of.
+// has_error: the first failing opcode's setup()/apply() error is in *e (class code returned).
+int rsb200h_dngop_lower(const void* img_data, int is_f32, int w, int h, int cpp, int pitch,
+                        const int* crop, const uint8_t* data, uint32_t size, rsb200_dng_op* ops,
+                        uint32_t ops_cap, uint16_t* tables, uint32_t tables_cap, uint32_t* deltas,
+                        uint32_t deltas_cap, uint32_t* actions, uint32_t actions_cap, uint32_t* n,
+                        uint32_t* lists, uint32_t lists_cap, uint32_t* rois, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeAnyImage(img_data, is_f32, w, h, cpp, pitch, crop);
+    DngOpcodes codes(img, ByteStream(data, size));
+    const DngOpcodes::Lowered L = codes.lower(img);
+    n[0] = (uint32_t)L.ops.size();
+    n[1] = (uint32_t)(L.tables.size() / 65536);
+    n[2] = (uint32_t)L.deltas.size();
+    n[3] = (uint32_t)L.actions.size();
+    if (n[0] > ops_cap || n[1] > tables_cap || n[2] > deltas_cap || n[3] > actions_cap)
+      ThrowRDE("test harness: buffers too small");
+    std::copy(L.ops.begin(), L.ops.end(), ops);
+    std::copy(L.tables.begin(), L.tables.end(), tables);
+    std::copy(L.deltas.begin(), L.deltas.end(), deltas);
+    // per action: kind, index, then (list: count + offset into `lists`) / (trim: roi x, y, w, h in rois)
+    uint32_t lpos = 0;
+    for (size_t i = 0; i < L.actions.size(); ++i) {
+      const auto& a = L.actions[i];
+      actions[4 * i] = (uint32_t)a.kind;
+      actions[4 * i + 1] = a.index;
+      actions[4 * i + 2] = actions[4 * i + 3] = 0;
+      if (a.kind == DngOpcodes::Action::BadList) {
+        const auto& b = codes.badPixels(a.index);
+        if (lpos + b.size() > lists_cap)
+          ThrowRDE("test harness: buffers too small");
+        actions[4 * i + 2] = (uint32_t)b.size();
+        actions[4 * i + 3] = lpos;
+        std::copy(b.begin(), b.end(), lists + lpos);
+        lpos += (uint32_t)b.size();
+      } else if (a.kind == DngOpcodes::Action::Trim) {
+        const iRectangle2D r = codes.roi(a.index);
+        rois[4 * i] = (uint32_t)r.pos.x;
+        rois[4 * i + 1] = (uint32_t)r.pos.y;
+        rois[4 * i + 2] = (uint32_t)r.dim.x;
+        rois[4 * i + 3] = (uint32_t)r.dim.y;
+      }
+    }
+    if (L.error)
+      std::rethrow_exception(L.error);
+  });
+}
+
 int rsb200h_phaseone(uint16_t* img_data, int w, int h, int pitch, const uint8_t* file,
                      uint64_t file_size, const uint64_t* off, const uint32_t* len,
                      const int32_t* rown, int nstrips, rsb200h_err* e) {

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <limits>
 
@@ -1029,6 +1030,342 @@ void SonyArw2Decompressor::decompress() const {
     ThrowRDE("Too many errors encountered. Giving up. First Error:\n"
              "ARW2 invariant failed, same pixel is both min and max");
   engineCheck(rc, "rsb200_plan_results");
+}
+
+// ------------------------------------------------------------------ DngOpcodes
+// ROIOpcode ctor (common/DngOpcodes.cpp:193-226): inside {0, 0, dim}, inclusive
+void DngOpcodes::readRoi(ByteStream& bs, const iPoint2D& dim, Op& op) {
+  const uint32_t top = bs.getU32(), left = bs.getU32(), bottom = bs.getU32(), right = bs.getU32();
+  const int tx = (int)left, ty = (int)top, bx = (int)right, by = (int)bottom;
+  const bool ok = tx >= 0 && ty >= 0 && tx <= dim.x && ty <= dim.y && bx >= 0 && by >= 0 &&
+                  bx <= dim.x && by <= dim.y && bx >= tx && by >= ty;
+  if (!ok)
+    ThrowRDE("Rectangle (%d, %d, %d, %d) not inside image (%d, %d, %d, %d).", tx, ty, bx, by, 0, 0,
+             dim.x, dim.y);
+  op.roi = iRectangle2D(tx, ty, bx - tx, by - ty);
+}
+
+// PixelOpcode ctor (:353-381)
+void DngOpcodes::readPixelOpcode(const RawImage& ri, ByteStream& bs, const iPoint2D& dim, Op& op) {
+  readRoi(bs, dim, op);
+  op.firstPlane = bs.getU32();
+  op.planes = bs.getU32();
+  if (op.planes == 0 || op.firstPlane > ri->getCpp() || op.planes > ri->getCpp() ||
+      op.firstPlane + op.planes > ri->getCpp())
+    ThrowRDE("Bad plane params (first %u, num %u), got planes = %u", op.firstPlane, op.planes,
+             ri->getCpp());
+  op.rowPitch = bs.getU32();
+  op.colPitch = bs.getU32();
+  if (op.rowPitch < 1 || op.rowPitch > (uint32_t)op.roi.dim.y || op.colPitch < 1 ||
+      op.colPitch > (uint32_t)op.roi.dim.x)
+    ThrowRDE("Invalid pitch");
+}
+
+namespace {
+uint64_t roundUpDivisionSafe(uint64_t a, uint64_t b) { return a ? 1 + (a - 1) / b : 0; }
+} // namespace
+
+// DngOpcodes::DngOpcodes (:666-726) and the opcode constructors it dispatches to
+DngOpcodes::DngOpcodes(const RawImage& ri, ByteStream bs) {
+  bs.setByteOrder(Endianness::big);
+  const uint32_t opcode_count = bs.getU32();
+  const auto origPos = bs.getPosition();
+  for (uint32_t i = 0; i < opcode_count; i++) {
+    bs.skipBytes(4);
+    bs.skipBytes(4);
+    bs.skipBytes(4);
+    const uint32_t opcode_size = bs.getU32();
+    bs.skipBytes(opcode_size);
+  }
+  bs.setPosition(origPos);
+  opcodes.reserve(opcode_count);
+  // integrated_subimg: the crop the list will see as TrimBounds opcodes narrow it
+  iPoint2D subDim = ri->dim;
+  const iPoint2D fullDim = ri->getUncroppedDim();
+  for (uint32_t i = 0; i < opcode_count; i++) {
+    const uint32_t code = bs.getU32();
+    bs.skipBytes(4); // version
+    const uint32_t flags = bs.getU32();
+    const uint32_t opcode_size = bs.getU32();
+    ByteStream ob = bs.getStream(opcode_size);
+    Op op;
+    op.code = code;
+    bool keep = true;
+    switch (code) {
+    case 1:
+    case 2:
+    case 3:
+    case 9: { // known, not implemented (:751-757, :776)
+      static const char* const names[] = {"", "WarpRectilinear", "WarpFisheye", "FixVignetteRadial",
+                                          "", "", "", "", "", "GainMap"};
+      if (!(flags & 1))
+        ThrowRDE("Unsupported Opcode: %u (%s)", code, names[code]);
+      keep = false;
+      break;
+    }
+    case 4: // FixBadPixelsConstant (:149-160)
+      op.value = ob.getU32();
+      ob.getU32(); // Bayer phase
+      break;
+    case 5: { // FixBadPixelsList (:263-317): uncropped coordinates
+      ob.getU32(); // phase
+      const uint32_t badPointCount = ob.getU32();
+      const uint32_t badRectCount = ob.getU32();
+      const auto pos0 = ob.getPosition();
+      ob.skipBytes(badPointCount, 2 * 4);
+      ob.skipBytes(badRectCount, 4 * 4);
+      ob.setPosition(pos0);
+      op.badPixels.reserve(badPointCount);
+      for (uint32_t k = 0; k < badPointCount; ++k) {
+        const uint32_t y = ob.getU32(), x = ob.getU32();
+        const int px = (int)x, py = (int)y;
+        if (!(px >= 0 && py >= 0 && px < fullDim.x && py < fullDim.y))
+          ThrowRDE("Bad point not inside image.");
+        op.badPixels.emplace_back(y << 16 | x);
+      }
+      for (uint32_t k = 0; k < badRectCount; ++k) {
+        Op r;
+        readRoi(ob, fullDim, r);
+        for (int y = 0; y < r.roi.dim.y; ++y)
+          for (int x = 0; x < r.roi.dim.x; ++x)
+            op.badPixels.emplace_back((uint32_t)(r.roi.pos.y + y) << 16 | (uint32_t)(r.roi.pos.x + x));
+      }
+      break;
+    }
+    case 6: // TrimBounds (:332-346)
+      readRoi(ob, subDim, op);
+      subDim = op.roi.dim;
+      break;
+    case 7: { // MapTable (:446-466)
+      readPixelOpcode(ri, ob, subDim, op);
+      const uint32_t count = ob.getU32();
+      if (count == 0 || count > 65536)
+        ThrowRDE("Invalid size of lookup table");
+      op.lookup.assign(65536, 0);
+      for (uint32_t k = 0; k < count; ++k)
+        op.lookup[k] = ob.getU16();
+      for (uint32_t k = count; k < 65536; ++k)
+        op.lookup[k] = op.lookup[count - 1];
+      break;
+    }
+    case 8: { // MapPolynomial (:473-505)
+      readPixelOpcode(ri, ob, subDim, op);
+      const uint64_t polynomial_size = (uint64_t)ob.getU32() + 1;
+      (void)ob.check((uint64_t)(uint32_t)(8 * polynomial_size)); // implicit_cast<size_type>(8UL * n)
+      if (polynomial_size > 9)
+        ThrowRDE("A polynomial with more than 8 degrees not allowed");
+      std::vector<double> polynomial;
+      for (uint64_t k = 0; k < polynomial_size; ++k) {
+        const uint64_t hi = ob.getU32(), lo = ob.getU32();
+        const uint64_t bits = (hi << 32) | lo;
+        double d;
+        std::memcpy(&d, &bits, 8);
+        polynomial.push_back(d);
+      }
+      op.lookup.assign(65536, 0);
+      for (size_t k = 0; k < op.lookup.size(); ++k) {
+        double val = polynomial[0];
+        for (size_t j = 1; j < polynomial.size(); ++j)
+          val += polynomial[j] * std::pow((double)k / 65536.0, (double)j);
+        op.lookup[k] = (uint16_t)std::clamp<double>(val * 65535.5, 0.0, 65535.0);
+      }
+      break;
+    }
+    case 10:
+    case 11:
+    case 12:
+    case 13: { // DeltaRowOrCol (:535-589): 10 / 12 index by row, 11 / 13 by column
+      readPixelOpcode(ri, ob, subDim, op);
+      const uint32_t deltaF_count = ob.getU32();
+      (void)ob.check(deltaF_count, 4);
+      const bool byRow = code == 10 || code == 12;
+      const uint64_t expectedSize = byRow ? roundUpDivisionSafe((uint64_t)op.roi.dim.y, op.rowPitch)
+                                          : roundUpDivisionSafe((uint64_t)op.roi.dim.x, op.colPitch);
+      if (expectedSize != deltaF_count)
+        ThrowRDE("Got unexpected number of elements (%llu), expected %u.",
+                 (unsigned long long)expectedSize, deltaF_count);
+      op.deltaF.reserve(deltaF_count);
+      for (uint32_t k = 0; k < deltaF_count; ++k) {
+        const uint32_t bits = ob.getU32();
+        float f;
+        std::memcpy(&f, &bits, 4);
+        if (!std::isfinite(f))
+          ThrowRDE("Got bad float %f.", (double)f);
+        op.deltaF.push_back(f);
+      }
+      break;
+    }
+    default:
+      ThrowRDE("Unknown unhandled Opcode: %u", code);
+    }
+    if (ob.getRemainSize() != 0)
+      ThrowRDE("Inconsistent length of opcode");
+    if (keep)
+      opcodes.push_back(std::move(op));
+  }
+}
+
+DngOpcodes::~DngOpcodes() = default;
+
+// setup() of every opcode in list order (:160-170, :425-430, :538-552) and the device form of
+// its apply(); the first failing opcode ends the list and its exception is kept
+DngOpcodes::Lowered DngOpcodes::lower(const RawImage& ri) const {
+  Lowered L;
+  iPoint2D off = ri->getCropOffset(), dim = ri->dim; // the crop as the list narrows it
+  const bool isU16 = ri->getDataType() == RawImageType::UINT16;
+  try {
+    for (uint32_t i = 0; i < opcodes.size(); ++i) {
+      const Op& op = opcodes[i];
+      rsb200_dng_op d;
+      std::memset(&d, 0, sizeof d);
+      switch (op.code) {
+      case 4:
+        if (!isU16)
+          ThrowRDE("Only 16 bit images supported");
+        if (ri->getCpp() > 1)
+          ThrowRDE("Only 1 component images supported");
+        d.kind = RSB200_DNGOP_BAD_CONSTANT;
+        d.top = (uint32_t)off.y;
+        d.left = (uint32_t)off.x;
+        d.bottom = (uint32_t)(off.y + dim.y);
+        d.right = (uint32_t)(off.x + dim.x);
+        d.first_plane = 0;
+        d.planes = 1;
+        d.row_pitch = d.col_pitch = 1;
+        d.value = op.value;
+        L.actions.push_back({Action::BadConstant, (uint32_t)L.ops.size()});
+        L.ops.push_back(d);
+        break;
+      case 5:
+        L.actions.push_back({Action::BadList, i});
+        break;
+      case 6: // ri->subFrame(roi) (common/RawImage.cpp:175-199)
+        if (!op.roi.hasPositiveArea())
+          ThrowRDE("No positive crop area");
+        L.actions.push_back({Action::Trim, i});
+        if (op.roi.dim.x <= dim.x - op.roi.pos.x && op.roi.dim.y <= dim.y - op.roi.pos.y) {
+          off.x += op.roi.pos.x;
+          off.y += op.roi.pos.y;
+          dim = op.roi.dim;
+        }
+        break;
+      default: {
+        d.top = (uint32_t)(off.y + op.roi.pos.y);
+        d.left = (uint32_t)(off.x + op.roi.pos.x);
+        d.bottom = d.top + (uint32_t)op.roi.dim.y;
+        d.right = d.left + (uint32_t)op.roi.dim.x;
+        d.first_plane = op.firstPlane;
+        d.planes = op.planes;
+        d.row_pitch = op.rowPitch;
+        d.col_pitch = op.colPitch;
+        if (op.code == 7 || op.code == 8) {
+          if (!isU16)
+            ThrowRDE("Only 16 bit images supported");
+          d.kind = RSB200_DNGOP_LOOKUP;
+          d.table = (uint32_t)(L.tables.size() / 65536);
+          L.tables.insert(L.tables.end(), op.lookup.begin(), op.lookup.end());
+        } else {
+          const bool scale = op.code == 12 || op.code == 13;
+          d.kind = op.code == 10   ? RSB200_DNGOP_OFFSET_ROW
+                   : op.code == 11 ? RSB200_DNGOP_OFFSET_COL
+                   : op.code == 12 ? RSB200_DNGOP_SCALE_ROW
+                                   : RSB200_DNGOP_SCALE_COL;
+          d.table = (uint32_t)L.deltas.size();
+          if (isU16) {
+            // DeltaRowOrCol::setup (:538-552) with valueIsOk of Offset (:598-600) / Scale (:636-638)
+            const float f2iScale = scale ? 1024.0F : 65535.0F;
+            const double absLimit = 65535.0 / (double)65535.0F;
+            const double maxLimit = ((double)(2147483647 - 512) / 65535.0) / (double)1024.0F;
+            std::vector<uint32_t> conv;
+            conv.reserve(op.deltaF.size());
+            for (const float f : op.deltaF) {
+              const bool ok = scale ? (f >= 0.0F && (double)f <= maxLimit)
+                                    : ((double)std::abs(f) <= absLimit);
+              if (!ok)
+                ThrowRDE("Got float %f which is unacceptable.", (double)f);
+              conv.push_back((uint32_t)static_cast<int>(f2iScale * f));
+            }
+            L.deltas.insert(L.deltas.end(), conv.begin(), conv.end());
+          } else {
+            for (const float f : op.deltaF) {
+              uint32_t bits;
+              std::memcpy(&bits, &f, 4);
+              L.deltas.push_back(bits);
+            }
+          }
+        }
+        L.ops.push_back(d);
+        break;
+      }
+      }
+    }
+  } catch (...) {
+    L.error = std::current_exception();
+  }
+  return L;
+}
+
+// DngOpcodes::applyOpCodes (:730-735): the opcodes that set up run as one pass over the image;
+// then the crop and mBadPixelPositions are brought to the state the reference's sequential walk
+// leaves them in, and the error of the opcode that failed (if any) is rethrown
+void DngOpcodes::applyOpCodes(const RawImage& ri) const {
+  const Lowered L = lower(ri);
+  std::vector<std::vector<uint32_t>> constant(L.ops.size());
+  if (!L.ops.empty()) {
+    if (!ri->isAllocated())
+      ThrowRDE("applyOpCodes: image has no data");
+    const iPoint2D full = ri->getUncroppedDim();
+    rsb200_dngop_job job;
+    std::memset(&job, 0, sizeof job);
+    job.offset = 0;
+    job.pitch = (uint32_t)ri->pitch;
+    job.width = (uint32_t)full.x;
+    job.height = (uint32_t)full.y;
+    job.cpp = ri->getCpp();
+    job.is_f32 = ri->getDataType() == RawImageType::F32 ? 1u : 0u;
+    job.first_op = 0;
+    job.num_ops = (uint32_t)L.ops.size();
+    PlanGuard pg;
+    engineCheck(rsb200_dngop_plan_create(engine(), &job, 1, L.ops.data(), (int)L.ops.size(),
+                                         L.tables.data(), (int)(L.tables.size() / 65536),
+                                         L.deltas.data(), (int)L.deltas.size(), &pg.p),
+                "rsb200_dngop_plan_create");
+    engineCheck(rsb200_plan_run_host_image(pg.p, nullptr, 0, ri->getByteData(), (uint32_t)ri->pitch,
+                                           (uint32_t)(full.x * (int)ri->getBpp()), (uint32_t)full.y,
+                                           /*partial=*/1),
+                "rsb200_plan_run_host_image");
+    for (size_t k = 0; k < L.ops.size(); ++k) {
+      if (L.ops[k].kind != RSB200_DNGOP_BAD_CONSTANT)
+        continue;
+      uint32_t count = 0;
+      engineCheck(rsb200_plan_bad_pixels(pg.p, (int)k, nullptr, 0, &count), "rsb200_plan_bad_pixels");
+      if (count > RSB200_PANA_BAD_CAP)
+        ThrowRDE("rawspeed_b200: %u bad pixels, more than the device list holds (%u)", count,
+                 RSB200_PANA_BAD_CAP);
+      constant[k].resize(count);
+      if (count)
+        engineCheck(rsb200_plan_bad_pixels(pg.p, (int)k, constant[k].data(), count, &count),
+                    "rsb200_plan_bad_pixels");
+      // the reference walks the crop row by row (:175-182): ascending (row << 16 | col)
+      std::sort(constant[k].begin(), constant[k].end());
+    }
+  }
+  {
+    std::lock_guard<std::mutex> guard(ri->mBadPixelMutex);
+    for (const Action& a : L.actions) {
+      if (a.kind == Action::BadList) {
+        const auto& b = opcodes[a.index].badPixels;
+        ri->mBadPixelPositions.insert(ri->mBadPixelPositions.begin(), b.begin(), b.end());
+      } else if (a.kind == Action::BadConstant) {
+        ri->mBadPixelPositions.insert(ri->mBadPixelPositions.end(), constant[a.index].begin(),
+                                      constant[a.index].end());
+      } else {
+        ri->subFrame(opcodes[a.index].roi);
+      }
+    }
+  }
+  if (L.error)
+    std::rethrow_exception(L.error);
 }
 
 // ------------------------------------------------------------------ sRaw

@@ -28,6 +28,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <optional>
@@ -147,6 +148,21 @@ public:
     return v;
   }
   void skipBytes(uint64_t n) { pos += check(n); }
+  // check(nmemb, size) / skipBytes(nmemb, size) (io/ByteStream.h:71-75, :130-132)
+  size_type check(size_type nmemb, size_type size) const {
+    if (size && nmemb > UINT32_MAX / size)
+      ThrowIOE("Integer overflow when calculating stream length");
+    return check((uint64_t)nmemb * size);
+  }
+  void skipBytes(size_type nmemb, size_type size) { pos += check(nmemb, size); }
+  uint32_t getU32() {
+    check(4);
+    const uint8_t* p = data_ + pos;
+    pos += 4;
+    return order == Endianness::big
+               ? ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]
+               : ((uint32_t)p[3] << 24) | ((uint32_t)p[2] << 16) | ((uint32_t)p[1] << 8) | p[0];
+  }
   void setPosition(size_type newPos) {
     pos = newPos;
     check(0);
@@ -635,6 +651,50 @@ private:
 };
 
 // ---------------------------------------------------------------- sRaw
+// ---------------------------------------------------------------- DngOpcodes
+// common/DngOpcodes.h:41-88 -- same constructor (parses and validates the big-endian list
+// against the image and its crop, common/DngOpcodes.cpp:666-726) and applyOpCodes(); the
+// per-sample work of all opcodes runs as ONE pass on the device (K10), the bad-pixel list and
+// crop bookkeeping on the host in the reference's order.
+class DngOpcodes final {
+public:
+  DngOpcodes(const RawImage& ri, ByteStream bs);
+  ~DngOpcodes();
+  void applyOpCodes(const RawImage& ri) const;
+
+  // The list in device form for `ri` in its current state (setup() of every opcode done, in
+  // order; ROIs in uncropped coordinates) + the host-side actions, in list order.
+  struct Action {
+    enum Kind { BadList, BadConstant, Trim } kind;
+    uint32_t index; // BadList: opcode; BadConstant: index into Lowered::ops; Trim: opcode
+  };
+  struct Lowered {
+    std::vector<rsb200_dng_op> ops;
+    std::vector<uint16_t> tables; // 65536 per table
+    std::vector<uint32_t> deltas;
+    std::vector<Action> actions;
+    std::exception_ptr error; // setup()/apply() error of the first opcode that failed, if any
+  };
+  Lowered lower(const RawImage& ri) const;
+  // opcode `i`: its bad-pixel list (FixBadPixelsList) / ROI (TrimBounds)
+  const std::vector<uint32_t>& badPixels(uint32_t i) const { return opcodes[i].badPixels; }
+  iRectangle2D roi(uint32_t i) const { return opcodes[i].roi; }
+
+private:
+  struct Op {
+    uint32_t code = 0;
+    uint32_t value = 0;
+    std::vector<uint32_t> badPixels;
+    iRectangle2D roi;
+    uint32_t firstPlane = 0, planes = 0, rowPitch = 0, colPitch = 0;
+    std::vector<uint16_t> lookup;
+    std::vector<float> deltaF;
+  };
+  std::vector<Op> opcodes;
+  static void readRoi(ByteStream& bs, const iPoint2D& dim, Op& op);
+  static void readPixelOpcode(const RawImage& ri, ByteStream& bs, const iPoint2D& dim, Op& op);
+};
+
 // interpolators/Cr2sRawInterpolator.h:36-60 -- same constructor and interpolate();
 // the per-pixel work (chroma interpolation + YCbCr->RGB) runs on the device.
 class Cr2sRawInterpolator final {

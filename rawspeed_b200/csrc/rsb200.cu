@@ -13,6 +13,8 @@
 #include "scale_host.h"
 #include "sraw.cuh"
 #include "arw2.cuh"
+#include "dngop.cuh"
+#include "dngop_host.h"
 #include "pana.cuh"
 #include "phaseone.cuh"
 #include "pentax.cuh"
@@ -113,7 +115,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place)
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place), 8 DNG opcode list (in place)
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -133,6 +135,14 @@ struct rsb200_plan {
   uint32_t* d_pana_zero_list = nullptr;
   int pana_zero_slots = 0;
   std::vector<ScaleGroup> scale_groups;
+  // DNG opcode pass (K10); bad-pixel lists share pana_zero_slot / d_pana_zero_* (slot per
+  // BAD_CONSTANT opcode, indexed by opcode)
+  DngOpJobDev* d_dngop_jobs = nullptr;
+  DngOpDev* d_dngop_ops = nullptr;
+  uint16_t* d_dngop_tables = nullptr;
+  uint32_t* d_dngop_deltas = nullptr;
+  int dngop_njobs = 0;
+  uint32_t dngop_units = 0;
   // Phase One (shares d_arw2_bad / h_arw2_bad as the per-job error flags)
   P1StripDev* d_p1_strips = nullptr;
   P1JobDev* d_p1_jobs = nullptr;
@@ -539,6 +549,62 @@ static cudaError_t run_raw_group(const RawGroup& g, const uint8_t* in, uint64_t 
 // ------------------------------------------------------------------
 // sRaw interpolation (K5)
 // ------------------------------------------------------------------
+// K10: a DNG opcode list in one pass (DngOpcodes::applyOpCodes)
+static_assert(DNGOP_BAD_CAP == RSB200_PANA_BAD_CAP, "one list capacity for both users");
+extern "C" int rsb200_dngop_plan_create(rsb200_ctx* ctx, const rsb200_dngop_job* jobs, int njobs,
+                                        const rsb200_dng_op* ops, int nops, const uint16_t* tables,
+                                        int ntables, const uint32_t* deltas, int ndeltas,
+                                        rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out || nops < 0 || (nops > 0 && !ops) || ntables < 0 ||
+      (ntables > 0 && !tables) || ndeltas < 0 || (ndeltas > 0 && !deltas))
+    return set_err(ctx, RSB200_ERR_ARG, "dngop_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<rsb200_plan, void (*)(rsb200_plan*)> holder(new rsb200_plan, rsb200_plan_destroy);
+  rsb200_plan* p = holder.get();
+  p->ctx = ctx;
+  p->kind = 8;
+  p->nunits = njobs;
+  std::vector<DngOpJobDev> hj((size_t)njobs);
+  std::vector<DngOpDev> ho((size_t)nops);
+  p->pana_zero_slot.assign((size_t)nops, -1);
+  uint64_t units = 0;
+  if (const char* why = dngop_build(jobs, njobs, ops, nops, ntables, ndeltas, hj.data(), ho.data(),
+                                    p->pana_zero_slot.data(), &p->pana_zero_slots, &units))
+    return set_err(ctx, RSB200_ERR_ARG, "dngop plan: %s", why);
+  for (int i = 0; i < njobs; ++i) {
+    const uint64_t bytes = (uint64_t)(hj[i].row1 - hj[i].row0) * hj[i].samples * (jobs[i].is_f32 ? 4u : 2u);
+    p->in_bytes += bytes;
+    p->out_bytes += bytes;
+    p->pixels += (uint64_t)(hj[i].row1 - hj[i].row0) * jobs[i].width;
+    p->need_out = std::max<uint64_t>(p->need_out, jobs[i].offset + (uint64_t)jobs[i].height * jobs[i].pitch);
+  }
+  p->dngop_njobs = njobs;
+  p->dngop_units = (uint32_t)units;
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_dngop_jobs, sizeof(DngOpJobDev) * hj.size()));
+  CUDA_TRY(ctx, cudaMemcpy(p->d_dngop_jobs, hj.data(), sizeof(DngOpJobDev) * hj.size(),
+                           cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_dngop_ops, sizeof(DngOpDev) * (ho.size() + 1)));
+  if (!ho.empty())
+    CUDA_TRY(ctx, cudaMemcpy(p->d_dngop_ops, ho.data(), sizeof(DngOpDev) * ho.size(),
+                             cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_dngop_tables, sizeof(uint16_t) * 65536 * (size_t)(ntables + 1)));
+  if (ntables)
+    CUDA_TRY(ctx, cudaMemcpy(p->d_dngop_tables, tables, sizeof(uint16_t) * 65536 * (size_t)ntables,
+                             cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_dngop_deltas, sizeof(uint32_t) * (size_t)(ndeltas + 1)));
+  if (ndeltas)
+    CUDA_TRY(ctx, cudaMemcpy(p->d_dngop_deltas, deltas, sizeof(uint32_t) * (size_t)ndeltas,
+                             cudaMemcpyHostToDevice));
+  if (p->pana_zero_slots) {
+    CUDA_TRY(ctx, cudaMalloc((void**)&p->d_pana_zero_count, sizeof(uint32_t) * (size_t)p->pana_zero_slots));
+    CUDA_TRY(ctx, cudaMalloc((void**)&p->d_pana_zero_list,
+                             sizeof(uint32_t) * (size_t)DNGOP_BAD_CAP * (size_t)p->pana_zero_slots));
+  }
+  p->launches_per_run = units ? 1 : 0;
+  *out = holder.release();
+  return RSB200_OK;
+}
+
 // K9: black / white scaling in place (RawImageDataU16::scaleValues)
 extern "C" int rsb200_scale_plan_create(rsb200_ctx* ctx, const rsb200_scale_job* jobs, int njobs,
                                         rsb200_plan** out) {
@@ -1732,6 +1798,17 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->kind == 8) {
+    if (p->pana_zero_slots)
+      CUDA_TRY(ctx, cudaMemsetAsync(p->d_pana_zero_count, 0,
+                                    sizeof(uint32_t) * (size_t)p->pana_zero_slots, st));
+    if (p->dngop_units) {
+      dngop_kernel<<<(p->dngop_units + DNGOP_NT - 1) / DNGOP_NT, DNGOP_NT, 0, st>>>(
+          outp, p->d_dngop_jobs, p->dngop_njobs, p->dngop_units, p->d_dngop_ops, p->d_dngop_tables,
+          p->d_dngop_deltas, p->d_pana_zero_count, p->d_pana_zero_list);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches++;
+    }
   } else if (p->kind == 7) {
     for (const ScaleGroup& g : p->scale_groups) {
       const uint32_t nb = (g.total_quads + SCALE_WARPS - 1) / SCALE_WARPS;
@@ -2026,8 +2103,9 @@ extern "C" int rsb200_plan_bad_pixels(rsb200_plan* p, int job, uint32_t* positio
     return RSB200_ERR_ARG;
   rsb200_ctx* ctx = p->ctx;
   *count = 0;
-  if (p->kind != 5 || job < 0 || job >= (int)p->pana_zero_slot.size())
-    return set_err(ctx, RSB200_ERR_ARG, "plan_bad_pixels: not a job of a Panasonic plan");
+  if ((p->kind != 5 && p->kind != 8) || job < 0 || job >= (int)p->pana_zero_slot.size())
+    return set_err(ctx, RSB200_ERR_ARG,
+                   "plan_bad_pixels: not a job of a Panasonic plan / an opcode of a DNG opcode plan");
   if (!p->ran)
     return set_err(ctx, RSB200_ERR_ARG, "plan_bad_pixels: plan has not been run");
   const int slot = p->pana_zero_slot[job];
@@ -2079,6 +2157,10 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     cudaFree(g.d_jobs);
   cudaFree(p->d_pana_zero_count);
   cudaFree(p->d_pana_zero_list);
+  cudaFree(p->d_dngop_jobs);
+  cudaFree(p->d_dngop_ops);
+  cudaFree(p->d_dngop_tables);
+  cudaFree(p->d_dngop_deltas);
   cudaFree(p->d_p1_strips);
   cudaFree(p->d_p1_jobs);
   cudaFree(p->d_nikon_luts);

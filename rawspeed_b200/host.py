@@ -31,7 +31,7 @@ EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_huff_check", "rsb200h_unpack_form", "rsb200h_pentax_decompress",
            "rsb200h_sraw_interpolate", "rsb200h_nikon_decompress", "rsb200h_sony_arw2",
            "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white",
-           "rsb200h_panasonic_v4"]
+           "rsb200h_panasonic_v4", "rsb200h_dng_opcodes", "rsb200h_dngop_lower"]
 
 _lib = None
 
@@ -231,6 +231,76 @@ def sony_arw2(img, w, data, curve=None, dither=False):
     e.check(L.rsb200h_sony_arw2(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
                                 p, C.c_uint32(n), cp, nc, int(dither), C.byref(e)))
     return img
+
+
+def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
+    """DngOpcodes(ri, data) + applyOpCodes(ri) via the host mirror, in place; img: uint16 image or
+    uint32 array holding an F32 image; crop = [off_x, off_y, crop_w, crop_h].  Returns (crop,
+    mBadPixelPositions); dng_opcodes.stage = which half threw (1 constructor, 2 apply, 0 none)."""
+    p, n = _u8(data)
+    cr = (C.c_int * 4)(*[int(v) for v in crop])
+    bad = (C.c_uint32 * cap)()
+    nbad = C.c_uint32(0)
+    stage = C.c_int(0)
+    e = _Err()
+    L = lib()
+    is_f32 = img.dtype == np.uint32
+    L.rsb200h_dng_opcodes.argtypes = [C.c_void_p] + [C.c_int] * 5 + [
+        C.POINTER(C.c_int), C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+        C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(_Err)]
+    rc = L.rsb200h_dng_opcodes(C.c_void_p(img.ctypes.data), int(is_f32), w, img.shape[0], cpp,
+                               img.shape[1] * img.itemsize, cr, p, C.c_uint32(n), bad, cap,
+                               C.byref(nbad), C.byref(stage), C.byref(e))
+    dng_opcodes.stage = stage.value
+    dng_opcodes.partial = (list(cr), list(bad[:min(nbad.value, cap)]))
+    e.check(rc)
+    return list(cr), list(bad[:min(nbad.value, cap)])
+
+
+def dngop_lower(img, w, cpp, crop, data):
+    """DngOpcodes(ri, data).lower(ri): the device form of the list (no GPU needed).  Returns a
+    dict(ops=[DngOp], tables=(n,65536) uint16, deltas=uint32[], actions=[(kind, index, list or
+    roi)], error=exception or None); a constructor error raises."""
+    from ._abi import DngOp
+    p, n = _u8(data)
+    cr = (C.c_int * 4)(*[int(v) for v in crop])
+    ops = (DngOp * 64)()
+    tables = np.zeros((16, 65536), dtype=np.uint16)
+    deltas = np.zeros(1 << 18, dtype=np.uint32)
+    actions = (C.c_uint32 * (4 * 64))()
+    rois = (C.c_uint32 * (4 * 64))()
+    lists = np.zeros(1 << 20, dtype=np.uint32)
+    cnt = (C.c_uint32 * 4)(*([0xFFFFFFFF] * 4))   # still the sentinel = the constructor threw
+    e = _Err()
+    L = lib()
+    L.rsb200h_dngop_lower.argtypes = [C.c_void_p] + [C.c_int] * 5 + [
+        C.POINTER(C.c_int), C.c_char_p, C.c_uint32, C.POINTER(DngOp), C.c_uint32, C.c_void_p,
+        C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+        C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(_Err)]
+    rc = L.rsb200h_dngop_lower(C.c_void_p(img.ctypes.data), int(img.dtype == np.uint32), w,
+                               img.shape[0], cpp, img.shape[1] * img.itemsize, cr, p, C.c_uint32(n),
+                               ops, 64, tables.ctypes.data, 16, deltas.ctypes.data, deltas.size,
+                               actions, 64, cnt, lists.ctypes.data, lists.size, rois, C.byref(e))
+    err = None
+    if rc != 0:
+        if cnt[0] == 0xFFFFFFFF:
+            e.check(rc)
+        try:
+            e.check(rc)
+        except Exception as ex:   # noqa: BLE001
+            err = ex
+    acts = []
+    for i in range(cnt[3]):
+        kind, index, a, b = actions[4 * i:4 * i + 4]
+        if kind == 0:
+            acts.append((0, index, lists[b:b + a].tolist()))
+        elif kind == 2:
+            acts.append((2, index, tuple(rois[4 * i:4 * i + 4])))
+        else:
+            acts.append((1, index, None))
+    return dict(ops=[DngOp.from_buffer_copy(ops[i]) for i in range(cnt[0])],
+                tables=tables[:cnt[1]].copy(), deltas=deltas[:cnt[2]].copy(), actions=acts,
+                error=err)
 
 
 def scale_black_white(img, w, crop, black_level=-1, black_sep=None, white=None, areas=(),

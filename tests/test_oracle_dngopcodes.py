@@ -35,6 +35,58 @@ def both(img, w, cpp, crop, blob):
 FULL = lambda w, h: (0, 0, h, w)   # noqa: E731  (top, left, bottom, right)
 
 
+def scenarios():
+    """(name, image, w, cpp, crop, opcode list) -- shared with the CPU replay of the kernel
+    (tests/test_dngop_emu.py) and the GPU tests (tests/test_gpu_dngopcodes.py)."""
+    out = []
+    rng = np.random.default_rng(77)
+    small = lambda n: (rng.random(n, dtype=np.float32) * 2 - 1) * 0.01     # noqa: E731
+    w, h = 64, 20
+    table = (np.arange(1000, dtype=np.uint32) * 37 % 65536).astype(np.uint16)
+    out.append(("lookup", u16_image(w, h, 1, 1), w, 1, [0, 0, w, h], S.dng_opcode_list([
+        S.dng_map_table(S.dng_pixel_area((2, 4, 18, 60), 0, 1, 2, 2), table),
+        S.dng_map_polynomial(S.dng_pixel_area(FULL(w, h)), [0.01, 0.9, 0.2, -0.1]),
+        S.dng_map_polynomial(S.dng_pixel_area((1, 1, 19, 63), 0, 1, 3, 5), [0.0] * 8 + [1.0])])))
+    for cpp in (1, 3):
+        w, h = 60, 24
+        out.append(("delta_u16_cpp%d" % cpp, u16_image(w, h, cpp, 2), w, cpp, [3, 2, 50, 20], S.dng_opcode_list([
+            S.dng_delta(10, S.dng_pixel_area((0, 0, 20, 50), 0, cpp, 1, 1), small(20)),
+            S.dng_delta(11, S.dng_pixel_area((1, 2, 19, 47), cpp - 1, 1, 2, 3), small(15)),
+            S.dng_delta(12, S.dng_pixel_area((2, 0, 20, 50), 0, 1, 4, 1), np.abs(small(5)) * 150),
+            S.dng_delta(13, S.dng_pixel_area((0, 5, 20, 45), 0, cpp, 1, 7), np.abs(small(6)) * 90 + 0.5)])))
+    for cpp in (1, 2):
+        w, h = 36, 10
+        out.append(("delta_f32_cpp%d" % cpp, f32_image(w, h, cpp, 3), w, cpp, [0, 0, w, h], S.dng_opcode_list([
+            S.dng_delta(10, S.dng_pixel_area((1, 0, 9, 36), 0, cpp, 2, 1), rng.random(4, dtype=np.float32)),
+            S.dng_delta(13, S.dng_pixel_area((0, 3, 10, 33), 0, 1, 1, 4), rng.random(8, dtype=np.float32) * 3),
+            S.dng_delta(11, S.dng_pixel_area(FULL(36, 10), cpp - 1, 1, 1, 1), -rng.random(36, dtype=np.float32)),
+            S.dng_delta(12, S.dng_pixel_area(FULL(36, 10), 0, cpp, 3, 2), rng.random(4, dtype=np.float32) + 1e30)])))
+    w, h = 48, 16
+    out.append(("bad_lists_trim", u16_image(w, h, 1, 4, 0, 8), w, 1, [0, 0, w, h], S.dng_opcode_list([
+        S.dng_fix_bad_constant(3),
+        S.dng_fix_bad_list(points=[(2, 5), (15, 47)], rects=[(1, 1, 3, 4), (0, 0, 0, 9)]),
+        S.dng_trim_bounds(2, 4, 14, 40),
+        S.dng_fix_bad_constant(5),
+        S.dng_delta(10, S.dng_pixel_area((0, 0, 12, 36)), np.full(12, 0.001, np.float32)),
+        S.dng_fix_bad_list(points=[(0, 0)]),
+        S.dng_trim_bounds(1, 1, 11, 35)])))
+    w, h = 300, 9
+    out.append(("wide_mixed", u16_image(w, h, 1, 12), w, 1, [4, 1, 290, 7], S.dng_opcode_list([
+        S.dng_delta(11, S.dng_pixel_area((0, 0, 7, 290), 0, 1, 1, 1), small(290)),
+        S.dng_map_table(S.dng_pixel_area((1, 3, 6, 287), 0, 1, 1, 2), (65535 - np.arange(65536)).astype(np.uint16)),
+        S.dng_fix_bad_constant(65535),
+        S.dng_delta(12, S.dng_pixel_area((0, 1, 7, 289), 0, 1, 3, 16), np.array([0.5, 1.5, 31.9], np.float32))])))
+    # setup() errors after opcodes that did run
+    w, h = 32, 8
+    area = S.dng_pixel_area(FULL(w, h))
+    out.append(("error_after_prefix", u16_image(w, h, 1, 9), w, 1, [0, 0, w, h], S.dng_opcode_list([
+        S.dng_delta(11, area, np.full(w, 0.25, np.float32)), S.dng_fix_bad_list(points=[(1, 1)]),
+        S.dng_delta(12, area, np.full(8, -0.5, np.float32)), S.dng_delta(10, area, np.zeros(8, np.float32))])))
+    out.append(("empty_trim_after_prefix", u16_image(w, h, 1, 9), w, 1, [0, 0, w, h], S.dng_opcode_list([
+        S.dng_delta(11, area, np.full(w, 0.25, np.float32)), S.dng_trim_bounds(3, 3, 3, 9)])))
+    return out
+
+
 @needs_ref
 def test_map_table_and_polynomial_u16():
     w, h = 64, 20
@@ -175,3 +227,14 @@ def test_setup_errors_on_wrong_image_type():
     u3 = u16_image(w, h, 3, 2)
     assert _err_both(u3, w, 3, [0, 0, w, h], S.dng_opcode_list([S.dng_fix_bad_constant(0)])) == \
         ("RawDecoderException", 2)
+
+
+@needs_ref
+@pytest.mark.parametrize("k", range(9))
+def test_shared_scenarios_match_reference(k):
+    name, img, w, cpp, crop, blob = scenarios()[k]
+    if "error" in name or "empty_trim" in name:
+        assert _err_both(img, w, cpp, crop, blob)[1] == 2
+        assert ref.dng_opcodes.partial == port.dng_opcodes.partial[:2]
+    else:
+        both(img, w, cpp, crop, blob)
