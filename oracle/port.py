@@ -404,6 +404,17 @@ def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
     return list(cr), list(bad[:min(nbad.value, cap)])
 
 
+def fix_bad_pixels(img, w, cpp, positions, is_cfa=True):
+    """RawImageData::fixBadPixels() with mBadPixelPositions = positions, in place."""
+    im = _img(img, w, cpp, is_cfa)
+    pos = np.ascontiguousarray(positions, dtype=np.uint32)
+    e = Err()
+    L = lib()
+    L.rso_fix_bad_pixels.argtypes = [C.POINTER(Image), C.c_void_p, C.c_uint32, C.POINTER(Err)]
+    e.check(L.rso_fix_bad_pixels(C.byref(im), pos.ctypes.data, pos.size, C.byref(e)))
+    return img
+
+
 class BlackArea(C.Structure):
     _fields_ = [("offset", C.c_uint32), ("size", C.c_uint32), ("is_vertical", C.c_int)]
 

@@ -307,6 +307,18 @@ def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
     return list(cr), list(bad[:min(nbad.value, cap)])
 
 
+def fix_bad_pixels(img, w, cpp, positions, is_cfa=True, nthreads=1):
+    """Reference RawImageData::fixBadPixels() (ref_fix_bad_pixels)."""
+    pos = np.ascontiguousarray(positions, dtype=np.uint32)
+    e = Err()
+    L = lib()
+    L.ref_fix_bad_pixels.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint32, C.c_int,
+                                                                    C.POINTER(Err)]
+    e.check(L.ref_fix_bad_pixels(C.c_void_p(img.ctypes.data), w, img.shape[0], cpp, img.shape[1] * 2,
+                                 int(is_cfa), pos.ctypes.data, pos.size, nthreads, C.byref(e)))
+    return img
+
+
 def scale_values(img, w, crop, black_sep, white, dither=True, nthreads=1):
     """Reference RawImageData::scaleBlackWhite() with blackLevelSeparate / whitePoint given
     (ref_scale_values); crop = (off_x, off_y, crop_w, crop_h)."""

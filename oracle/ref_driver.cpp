@@ -433,6 +433,19 @@ int ref_dng_opcodes(void* img_data, int is_f32, int w, int h, int cpp, int pitch
   });
 }
 
+// RawImageData::fixBadPixels() with mBadPixelPositions = positions[0..n)
+int ref_fix_bad_pixels(uint16_t* img_data, int w, int h, int cpp, int pitch, int is_cfa,
+                       const uint32_t* positions, uint32_t n, int nthreads, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(w, h, cpp, is_cfa != 0, 1, 1);
+    copyIn(img, img_data, pitch);
+    img->mBadPixelPositions.assign(positions, positions + n);
+    img->fixBadPixels();
+    copyOut(img, img_data, pitch);
+  });
+}
+
 // PhaseOneDecompressor(mRaw, strips).decompress(): strip k = (row rown[k], bytes
 // [off[k], off[k]+len[k]) of `file`), as IiqDecoder::DecodePhaseOneC builds them.
 int ref_phaseone(uint16_t* img_data, int w, int h, int pitch, const uint8_t* file,

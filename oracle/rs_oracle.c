@@ -4005,3 +4005,116 @@ int rso_dng_opcodes(rso_image* img, int* crop, const uint8_t* data, uint32_t siz
   dng_free(&st);
   return RSO_OK;
 }
+
+/* ------------------------------------------------------------------
+ * RawImageData::fixBadPixels (common/RawImage.cpp, common/RawImageDataU16.cpp)
+ * ------------------------------------------------------------------ */
+static void fix_bad_pixel(rso_image* img, const uint8_t* bad, uint32_t bpitch, uint32_t x, uint32_t y,
+                          int component) {
+  /* RawImageDataU16::fixBadPixel (:399-485) */
+  int values[4] = {-1, -1, -1, -1}, dist[4] = {0, 0, 0, 0}, weight[4] = {0, 0, 0, 0};
+  const int step = img->is_cfa ? 2 : 1;
+  int x_find, y_find, total_dist_x, total_dist_y, total_shifts = 7, total_pixel = 0, i;
+#define PIX(r, c) (((uint16_t*)((uint8_t*)img->data + (size_t)(r) * (size_t)img->pitch))[(c)])
+#define ISBAD(r, c) ((bad[(size_t)bpitch * (size_t)(r) + ((c) >> 3)] >> ((c)&7)) & 1)
+  x_find = (int)x - step;
+  while (x_find >= 0 && values[0] < 0) {
+    if (!ISBAD(y, x_find)) {
+      values[0] = PIX(y, x_find + component);
+      dist[0] = (int)x - x_find;
+    }
+    x_find -= step;
+  }
+  x_find = (int)x + step;
+  while (x_find < img->w && values[1] < 0) {
+    if (!ISBAD(y, x_find)) {
+      values[1] = PIX(y, x_find + component);
+      dist[1] = x_find - (int)x;
+    }
+    x_find += step;
+  }
+  y_find = (int)y - step;
+  while (y_find >= 0 && values[2] < 0) {
+    if (!ISBAD(y_find, x)) {
+      values[2] = PIX(y_find, x + component);
+      dist[2] = (int)y - y_find;
+    }
+    y_find -= step;
+  }
+  y_find = (int)y + step;
+  while (y_find < img->h && values[3] < 0) {
+    if (!ISBAD(y_find, x)) {
+      values[3] = PIX(y_find, x + component);
+      dist[3] = y_find - (int)y;
+    }
+    y_find += step;
+  }
+  total_dist_x = dist[0] + dist[1];
+  if (total_dist_x) {
+    weight[0] = dist[0] ? (total_dist_x - dist[0]) * 256 / total_dist_x : 0;
+    weight[1] = 256 - weight[0];
+    total_shifts++;
+  }
+  total_dist_y = dist[2] + dist[3];
+  if (total_dist_y) {
+    weight[2] = dist[2] ? (total_dist_y - dist[2]) * 256 / total_dist_y : 0;
+    weight[3] = 256 - weight[2];
+    total_shifts++;
+  }
+  for (i = 0; i < 4; i++)
+    if (values[i] >= 0)
+      total_pixel += values[i] * weight[i];
+  total_pixel >>= total_shifts;
+  PIX(y, x + component) = (uint16_t)(total_pixel < 0 ? 0 : (total_pixel > 65535 ? 65535 : total_pixel));
+  if (img->cpp > 1 && component == 0)
+    for (i = 1; i < img->cpp; i++)
+      fix_bad_pixel(img, bad, bpitch, x, y, i);
+#undef PIX
+#undef ISBAD
+}
+
+int rso_fix_bad_pixels(rso_image* img, const uint32_t* positions, uint32_t npositions, rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  uint8_t* volatile map = NULL;
+  uint32_t bpitch, i;
+  int y, x, gw;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb)) {
+    free((void*)map);
+    return c.e->code;
+  }
+  if (img->is_f32)
+    THROW_RDE(&c, "restated for UINT16 images");
+  /* transferBadPixelsToMap (:211-229) */
+  if (!npositions)
+    return RSO_OK;
+  bpitch = (uint32_t)((((img->w + 7) / 8) + 15) / 16 * 16); /* createBadPixelMap (:201-209) */
+  map = (uint8_t*)calloc((size_t)bpitch * (size_t)img->h, 1);
+  if (!map)
+    THROW_RDE(&c, "out of memory");
+  for (i = 0; i < npositions; i++) {
+    const uint32_t px = positions[i] & 0xffff, py = positions[i] >> 16;
+    if ((int)px >= img->w || (int)py >= img->h) /* (assert in the reference) */
+      THROW_RDE(&c, "bad pixel position outside the image");
+    ((uint8_t*)map)[(size_t)bpitch * py + (px >> 3)] |= (uint8_t)(1 << (px & 7));
+  }
+  /* fixBadPixelsThread (:297-323): blocks of 32 pixels, (w + 15) / 32 of them per row */
+  gw = (img->w + 15) / 32;
+  for (y = 0; y < img->h; y++) {
+    for (x = 0; x < gw; x++) {
+      const uint8_t* block = (const uint8_t*)map + (size_t)bpitch * (size_t)y + (size_t)x * 4;
+      int bi, bj;
+      if (!(block[0] | block[1] | block[2] | block[3]))
+        continue;
+      for (bi = 0; bi < 4; bi++)
+        for (bj = 0; bj < 8; bj++)
+          if ((block[bi] >> bj) & 1)
+            fix_bad_pixel(img, (const uint8_t*)map, bpitch, (uint32_t)(x * 32 + bi * 8 + bj), (uint32_t)y, 0);
+    }
+  }
+  free((void*)map);
+  return RSO_OK;
+}

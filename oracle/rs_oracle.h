@@ -259,6 +259,16 @@ int rso_scale_values(rso_image* img, int off_x, int off_y, int crop_w, int crop_
 int rso_dng_opcodes(rso_image* img, int* crop, const uint8_t* data, uint32_t size, uint32_t* bad,
                     uint32_t bad_cap, uint32_t* nbad, int* applied, rso_err* e);
 
+/* ---- RawImageData::fixBadPixels (common/RawImage.cpp:201-239, :297-323;
+ *      RawImageDataU16::fixBadPixel common/RawImageDataU16.cpp:399-485) ----
+ * (restated and pinned; device pass = K11)
+ * positions = mBadPixelPositions ((y << 16) | x, uncropped coordinates).  Every bad pixel in
+ * the first ((w + 15) / 32) * 32 columns is replaced by the distance-weighted mean of the
+ * nearest good pixels to the left / right / above / below, at step 2 for CFA images and 1
+ * otherwise; for cpp > 1 the components are read at column x + component (not x * cpp +
+ * component), as the reference does. */
+int rso_fix_bad_pixels(rso_image* img, const uint32_t* positions, uint32_t npositions, rso_err* e);
+
 /* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
  * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
  * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity
