@@ -329,6 +329,32 @@ int rsb200_dngop_plan_create(rsb200_ctx* ctx, const rsb200_dngop_job* jobs, int 
                              rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* K11: bad-pixel interpolation, in place.               */
+/*   RawImageData::fixBadPixels / transferBadPixelsToMap /               */
+/*   fixBadPixelsThread       common/RawImage.cpp:201-239, :297-323      */
+/*   RawImageDataU16::fixBadPixel  common/RawImageDataU16.cpp:399-485    */
+/* uint16 images with one component per pixel (the reference's indexing  */
+/* for cpp > 1 makes the result depend on its visiting order; refused).  */
+/* Run with rsb200_plan_run(plan, NULL, 0, d_image, bytes, stream).      */
+/* NOT YET VALIDATED ON A B200.                          */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t offset;         /* byte offset of row 0 of the uncropped image; multiple of 2   */
+  uint32_t pitch;          /* bytes between rows; multiple of 2                            */
+  uint32_t width;          /* uncropped_dim                                                */
+  uint32_t height;
+  uint32_t is_cfa;         /* RawImageData::isCFA: neighbours at distance 2, else 1        */
+  uint32_t first_position; /* mBadPixelPositions of this image: positions[first ..         */
+  uint32_t num_positions;  /* first + num), each (y << 16) | x in uncropped coordinates    */
+  const uint8_t* prior_map; /* an existing mBadPixelMap (map pitch roundUp(ceil(width/8),  */
+                            /* 16) x height bytes) to OR the positions into, or NULL       */
+} rsb200_badpix_job;
+
+int rsb200_badpix_plan_create(rsb200_ctx* ctx, const rsb200_badpix_job* jobs, int njobs,
+                              const uint32_t* positions, uint32_t npositions,
+                              rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
 /* K5: Canon sRaw interpolation.                         */
 /*   Cr2sRawInterpolator::interpolate(version)                          */
 /*   interpolators/Cr2sRawInterpolator.cpp:96-187 (4:2:2), :189-453     */

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Arw2Job, NikonJob, PanaJob, ScaleJob, DngOp, DngOpJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, NikonJob, PanaJob, ScaleJob, DngOp, DngOpJob, BadPixJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -232,6 +232,17 @@ def dngop_plan(ctx, jobs, ops, tables=None, deltas=None):
     plan = Plan(ctx, h, len(jobs))
     plan._keep = (tables, deltas)
     return plan
+
+
+def badpix_plan(ctx, jobs, positions):
+    """Bad-pixel interpolation in place (RawImageData::fixBadPixels); positions: uint32
+    (y << 16) | x, each job names its slice; run with plan.run(None, d_image)."""
+    ja = (BadPixJob * len(jobs))(*jobs)
+    pos = np.ascontiguousarray(positions, dtype=np.uint32)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_badpix_plan_create(ctx.h, ja, len(jobs), pos.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                 pos.size, C.byref(h)))
+    return Plan(ctx, h, len(jobs))
 
 
 def phaseone_plan(ctx, jobs, strips):

@@ -305,6 +305,26 @@ int rsb200h_panasonic_v4(uint16_t* img_data, int w, int h, int pitch, const uint
   });
 }
 
+// RawImageData::fixBadPixels() with mBadPixelPositions = positions[0..n); map_only != 0: stop
+// after transferBadPixelsToMap() and return the bitmap (no GPU needed): map_out must hold
+// roundUp(ceil(w / 8), 16) * h bytes.
+int rsb200h_fix_bad_pixels(uint16_t* img_data, int w, int h, int cpp, int pitch, int is_cfa,
+                           const uint32_t* positions, uint32_t n, int map_only, uint8_t* map_out,
+                           rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, cpp, pitch, is_cfa != 0, 1, 1);
+    img->mBadPixelPositions.assign(positions, positions + n);
+    if (map_only) {
+      img->transferBadPixelsToMap();
+      if (map_out && !img->mBadPixelMap.empty())
+        std::memcpy(map_out, img->mBadPixelMap.data(), img->mBadPixelMap.size());
+      return;
+    }
+    img->fixBadPixels();
+    copyOut(img, img_data);
+  });
+}
+
 namespace {
 RawImage makeAnyImage(const void* src, int is_f32, int w, int h, int cpp, int pitch, const int* crop) {
   RawImage img = RawImage::create(iPoint2D(w, h), is_f32 ? RawImageType::F32 : RawImageType::UINT16,

@@ -117,6 +117,55 @@ void RawImageData::subFrame(iRectangle2D crop) {
   dim = crop.dim;
 }
 
+// RawImageData::createBadPixelMap + transferBadPixelsToMap (common/RawImage.cpp:201-229)
+void RawImageData::transferBadPixelsToMap() {
+  std::lock_guard<std::mutex> guard(mBadPixelMutex);
+  if (mBadPixelPositions.empty())
+    return;
+  if (mBadPixelMap.empty()) {
+    if (!isAllocated())
+      ThrowRDE("(internal) Bad pixel map cannot be allocated before image.");
+    mBadPixelMapPitch = (uint32_t)((((uint32_t)uncropped_dim.x + 7) / 8 + 15) / 16 * 16);
+    mBadPixelMap.assign((size_t)mBadPixelMapPitch * (size_t)uncropped_dim.y, 0);
+  }
+  for (const uint32_t pos : mBadPixelPositions) {
+    const uint32_t pos_x = pos & 0xffff, pos_y = pos >> 16;
+    if ((int)pos_x >= uncropped_dim.x || (int)pos_y >= uncropped_dim.y) // (an assert in the reference)
+      ThrowRDE("Bad pixel position (%u, %u) outside the image", pos_x, pos_y);
+    mBadPixelMap[(size_t)mBadPixelMapPitch * pos_y + (pos_x >> 3)] |= (uint8_t)(1 << (pos_x & 7));
+  }
+  mBadPixelPositions.clear();
+}
+
+// RawImageData::fixBadPixels (:231-239): FIX_BAD_PIXELS over the whole map, on the device
+void RawImageData::fixBadPixels() {
+  transferBadPixelsToMap();
+  if (mBadPixelMap.empty())
+    return;
+  if (dataType != RawImageType::UINT16)
+    ThrowRDE("rawspeed_b200: fixBadPixels is implemented for UINT16 images");
+  if (cpp != 1)
+    ThrowRDE("rawspeed_b200: fixBadPixels is implemented for 1 component per pixel (the "
+             "reference's result for %u depends on its visiting order)", cpp);
+  rsb200_badpix_job job;
+  std::memset(&job, 0, sizeof job);
+  job.offset = 0;
+  job.pitch = (uint32_t)pitch;
+  job.width = (uint32_t)uncropped_dim.x;
+  job.height = (uint32_t)uncropped_dim.y;
+  job.is_cfa = isCFA ? 1u : 0u;
+  job.first_position = 0;
+  job.num_positions = 0;
+  job.prior_map = mBadPixelMap.data();
+  PlanGuard pg;
+  engineCheck(rsb200_badpix_plan_create(engine(), &job, 1, nullptr, 0, &pg.p),
+              "rsb200_badpix_plan_create");
+  engineCheck(rsb200_plan_run_host_image(pg.p, nullptr, 0, storage, (uint32_t)pitch,
+                                         (uint32_t)(uncropped_dim.x * (int)bpp),
+                                         (uint32_t)uncropped_dim.y, /*partial=*/1),
+              "rsb200_plan_run_host_image");
+}
+
 // RawImageDataU16::calculateBlackAreas (common/RawImageDataU16.cpp:60-145): per CFA position,
 // the median of the masked areas -- 16-bit histogram counters and the one sampled column / row
 // (the FIXMEs at :87, :103) as the reference has them.  Host work: the areas are a few rows.

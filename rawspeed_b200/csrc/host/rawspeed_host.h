@@ -238,6 +238,13 @@ public:
   // (y << 16) | x of pixels a decoder marked bad (common/RawImage.h:179-186)
   std::vector<uint32_t> mBadPixelPositions;
   std::mutex mBadPixelMutex;
+  // bitmap of bad pixels, mBadPixelMapPitch bytes per row (common/RawImage.h:190-197)
+  std::vector<uint8_t> mBadPixelMap;
+  uint32_t mBadPixelMapPitch = 0;
+  // RawImageData::transferBadPixelsToMap / fixBadPixels (common/RawImage.cpp:211-239): the
+  // positions move into the bitmap on the host, the interpolation runs on the device (K11)
+  void transferBadPixelsToMap();
+  void fixBadPixels();
   // RawImageData::subFrame (common/RawImage.cpp:175-199): dim becomes the crop, the data and
   // pitch stay those of the uncropped image
   void subFrame(iRectangle2D crop);

@@ -13,6 +13,8 @@
 #include "scale_host.h"
 #include "sraw.cuh"
 #include "arw2.cuh"
+#include "badpix.cuh"
+#include "badpix_host.h"
 #include "dngop.cuh"
 #include "dngop_host.h"
 #include "pana.cuh"
@@ -115,7 +117,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place), 8 DNG opcode list (in place)
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place), 8 DNG opcode list (in place), 9 bad-pixel interpolation (in place)
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -143,6 +145,12 @@ struct rsb200_plan {
   uint32_t* d_dngop_deltas = nullptr;
   int dngop_njobs = 0;
   uint32_t dngop_units = 0;
+  // bad-pixel interpolation (K11)
+  BadPixJobDev* d_badpix_jobs = nullptr;
+  uint32_t* d_badpix_list = nullptr;
+  uint8_t* d_badpix_maps = nullptr;
+  int badpix_njobs = 0;
+  uint32_t badpix_total = 0;
   // Phase One (shares d_arw2_bad / h_arw2_bad as the per-job error flags)
   P1StripDev* d_p1_strips = nullptr;
   P1JobDev* d_p1_jobs = nullptr;
@@ -549,6 +557,49 @@ static cudaError_t run_raw_group(const RawGroup& g, const uint8_t* in, uint64_t 
 // ------------------------------------------------------------------
 // sRaw interpolation (K5)
 // ------------------------------------------------------------------
+// K11: bad-pixel interpolation (RawImageData::fixBadPixels)
+extern "C" int rsb200_badpix_plan_create(rsb200_ctx* ctx, const rsb200_badpix_job* jobs, int njobs,
+                                         const uint32_t* positions, uint32_t npositions,
+                                         rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out || (npositions && !positions))
+    return set_err(ctx, RSB200_ERR_ARG, "badpix_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<rsb200_plan, void (*)(rsb200_plan*)> holder(new rsb200_plan, rsb200_plan_destroy);
+  rsb200_plan* p = holder.get();
+  p->ctx = ctx;
+  p->kind = 9;
+  p->nunits = njobs;
+  std::vector<BadPixJobDev> hj((size_t)njobs);
+  std::vector<uint8_t> maps;
+  std::vector<uint32_t> list;
+  for (int i = 0; i < njobs; ++i) {
+    if (const char* why = badpix_build(jobs[i], positions, npositions, jobs[i].prior_map, &hj[i],
+                                       &maps, &list))
+      return set_err(ctx, RSB200_ERR_ARG, "badpix job %d: %s", i, why);
+    p->pixels += hj[i].count;
+    p->in_bytes += (uint64_t)hj[i].count * 2 * 4; // up to four neighbours read per bad pixel
+    p->out_bytes += (uint64_t)hj[i].count * 2;
+    p->need_out = std::max<uint64_t>(p->need_out, jobs[i].offset + (uint64_t)jobs[i].height * jobs[i].pitch);
+  }
+  if (list.size() > 0x7FFFFFFFull)
+    return set_err(ctx, RSB200_ERR_ARG, "badpix plan: too many bad pixels");
+  p->badpix_njobs = njobs;
+  p->badpix_total = (uint32_t)list.size();
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_badpix_jobs, sizeof(BadPixJobDev) * hj.size()));
+  CUDA_TRY(ctx, cudaMemcpy(p->d_badpix_jobs, hj.data(), sizeof(BadPixJobDev) * hj.size(),
+                           cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_badpix_list, sizeof(uint32_t) * (list.size() + 1)));
+  if (!list.empty())
+    CUDA_TRY(ctx, cudaMemcpy(p->d_badpix_list, list.data(), sizeof(uint32_t) * list.size(),
+                             cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_badpix_maps, maps.size() + 16));
+  if (!maps.empty())
+    CUDA_TRY(ctx, cudaMemcpy(p->d_badpix_maps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+  p->launches_per_run = p->badpix_total ? 1 : 0;
+  *out = holder.release();
+  return RSB200_OK;
+}
+
 // K10: a DNG opcode list in one pass (DngOpcodes::applyOpCodes)
 static_assert(DNGOP_BAD_CAP == RSB200_PANA_BAD_CAP, "one list capacity for both users");
 extern "C" int rsb200_dngop_plan_create(rsb200_ctx* ctx, const rsb200_dngop_job* jobs, int njobs,
@@ -1798,6 +1849,13 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->kind == 9) {
+    if (p->badpix_total) {
+      badpix_kernel<<<(p->badpix_total + BADPIX_NT - 1) / BADPIX_NT, BADPIX_NT, 0, st>>>(
+          outp, p->d_badpix_jobs, p->badpix_njobs, p->d_badpix_list, p->badpix_total, p->d_badpix_maps);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches++;
+    }
   } else if (p->kind == 8) {
     if (p->pana_zero_slots)
       CUDA_TRY(ctx, cudaMemsetAsync(p->d_pana_zero_count, 0,
@@ -2157,6 +2215,9 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     cudaFree(g.d_jobs);
   cudaFree(p->d_pana_zero_count);
   cudaFree(p->d_pana_zero_list);
+  cudaFree(p->d_badpix_jobs);
+  cudaFree(p->d_badpix_list);
+  cudaFree(p->d_badpix_maps);
   cudaFree(p->d_dngop_jobs);
   cudaFree(p->d_dngop_ops);
   cudaFree(p->d_dngop_tables);

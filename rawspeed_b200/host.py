@@ -31,7 +31,8 @@ EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_huff_check", "rsb200h_unpack_form", "rsb200h_pentax_decompress",
            "rsb200h_sraw_interpolate", "rsb200h_nikon_decompress", "rsb200h_sony_arw2",
            "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white",
-           "rsb200h_panasonic_v4", "rsb200h_dng_opcodes", "rsb200h_dngop_lower"]
+           "rsb200h_panasonic_v4", "rsb200h_dng_opcodes", "rsb200h_dngop_lower",
+           "rsb200h_fix_bad_pixels"]
 
 _lib = None
 
@@ -231,6 +232,22 @@ def sony_arw2(img, w, data, curve=None, dither=False):
     e.check(L.rsb200h_sony_arw2(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
                                 p, C.c_uint32(n), cp, nc, int(dither), C.byref(e)))
     return img
+
+
+def fix_bad_pixels(img, w, cpp, positions, is_cfa=True, map_only=False):
+    """RawImageData::fixBadPixels() via the host mirror, in place; map_only: only
+    transferBadPixelsToMap(), returns the bitmap (rows of roundUp(ceil(w / 8), 16) bytes)."""
+    pos = np.ascontiguousarray(positions, dtype=np.uint32)
+    mp = ((w + 7) // 8 + 15) // 16 * 16
+    m = np.zeros((img.shape[0], mp), dtype=np.uint8)
+    e = _Err()
+    L = lib()
+    L.rsb200h_fix_bad_pixels.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint32, C.c_int,
+                                                                        C.c_void_p, C.POINTER(_Err)]
+    e.check(L.rsb200h_fix_bad_pixels(C.c_void_p(img.ctypes.data), w, img.shape[0], cpp,
+                                     img.shape[1] * 2, int(is_cfa), pos.ctypes.data, pos.size,
+                                     int(map_only), m.ctypes.data, C.byref(e)))
+    return m if map_only else img
 
 
 def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
