@@ -262,6 +262,10 @@ def main():
                     help="run BASELINE configs[4]: the 256-frame LJPEG batch sharded over the "
                          "ranks (256/N frames per GPU, strong scaling) + NCCL gather of the outputs")
     ap.add_argument("--skip-others", action="store_true")
+    ap.add_argument("--unvalidated", action="store_true",
+                    help="also time the kernels that have not passed their first GPU parity run yet "
+                         "(K9 scaling, K10 DNG opcodes, K11 bad pixels, Panasonic V4); each leg "
+                         "checks bit-exactness against the oracle before timing")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -569,6 +573,8 @@ def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
         del plan, d_in, d_out
     out.update(bench_forms(torch, rs, ctx, port, synth, args, dist, peak))
     out.update(bench_codecs(torch, rs, ctx, port, synth, args, dist, peak))
+    if args.unvalidated:
+        out.update(bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak))
     return out
 
 
@@ -816,6 +822,114 @@ def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
                                     "sample": "SonyArw2Decompressor::decompress (OpenMP over rows), 1 frame, best of 3"}
     out["8(f)4 SonyArw2Decompressor 9568x6376 (dithered curve)"] = ent
     del plan, d_in, d_out
+    return out
+
+
+def bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak):
+    """SURVEY 8(f)3 (+ Panasonic V4): kernels written after round 1's GPU budget was spent.  Off by
+    default (--unvalidated); every leg first checks the result against the oracle."""
+    out = {}
+    steps = max(3, min(args.steps, 10))
+    W, H = 8256, 5504
+    pitch = rs.image_pitch(W)
+    rng = np.random.default_rng(9)
+    base = port.new_image(W, H)
+    base[:, :] = rng.integers(0, 16384, size=base.shape, dtype=np.uint16)
+
+    def leg(name, plan, want, kernel, restore=True):
+        d = torch.from_numpy(base.view(np.int16).copy()).cuda()
+        src = d.clone()
+        plan.run(None, d)
+        torch.cuda.synchronize()
+        exact = bool(np.array_equal(d.cpu().numpy().view(np.uint16), want))
+
+        def step():
+            if restore:
+                d.copy_(src)        # in-place kernels: every timed run starts from the same pixels
+            plan.run(None, d)
+        ms = time_steps(torch, step, steps, 3, dist)
+        ms_copy = time_steps(torch, lambda: d.copy_(src), steps, 3, dist) if restore else 0.0
+        in_b, out_b, pixels = plan.bytes()
+        per = (ms - ms_copy) / steps
+        out[name] = {"MPixels/s": pixels / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": exact,
+                     "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
+                     "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak, "kernel": kernel,
+                     "timing": "in-place kernel + restoring copy, minus the copy alone"}
+
+    # K9: black / white scaling, both loops
+    for label, black, white in (("SSE2 loop", (1008, 1010, 1009, 1011), 16383), ("plain loop", (64,) * 4, 1000)):
+        j = rs.ScaleJob()
+        j.offset, j.pitch, j.width, j.height, j.cpp = 0, pitch, W, H, 1
+        j.crop_x, j.crop_y, j.crop_w, j.crop_h = 8, 8, W - 16, H - 16
+        for i in range(4):
+            j.black_separate[i] = black[i]
+        j.white_point, j.dither, j.path = white, 1, 0
+        want = base.copy()
+        port.scale_values(want, W, (8, 8, W - 16, H - 16), black, white)
+        leg("8(f)3 scaleBlackWhite 8256x5504 (%s, dither)" % label, rs.scale_plan(ctx, [j]), want,
+            "scale_kernel<%d>" % (0 if "SSE2" in label else 1))
+    # K10: eight opcodes in one pass
+    from rawspeed_b200 import host
+    area = synth.dng_pixel_area((0, 0, H, W))
+    blob = synth.dng_opcode_list([
+        synth.dng_delta(12, area, rng.random(H, dtype=np.float32) + 0.5),
+        synth.dng_delta(13, synth.dng_pixel_area((0, 0, H, W), 0, 1, 1, 2), rng.random(W // 2, dtype=np.float32) + 0.5),
+        synth.dng_delta(10, synth.dng_pixel_area((1, 1, H, W), 0, 1, 2, 2), (rng.random(H // 2, dtype=np.float32) - 0.5) * 0.01),
+        synth.dng_delta(11, area, (rng.random(W, dtype=np.float32) - 0.5) * 0.01),
+        synth.dng_map_polynomial(area, [0.0, 0.8, 0.3, -0.1]),
+        synth.dng_map_table(synth.dng_pixel_area((0, 1, H, W), 0, 1, 2, 2), (np.arange(65536) ^ 1).astype(np.uint16)),
+        synth.dng_delta(13, synth.dng_pixel_area((8, 8, H - 8, W - 8), 0, 1, 1, 16), rng.random((W - 16 + 15) // 16, dtype=np.float32) + 0.25),
+        synth.dng_delta(12, synth.dng_pixel_area((0, 0, H, W), 0, 1, 4, 1), rng.random(H // 4, dtype=np.float32) + 0.75)])
+    low = host.dngop_lower(base, W, 1, [0, 0, W, H], blob)
+    dj = rs.DngOpJob()
+    dj.offset, dj.pitch, dj.width, dj.height, dj.cpp, dj.is_f32 = 0, pitch, W, H, 1, 0
+    dj.first_op, dj.num_ops = 0, len(low["ops"])
+    want = base.copy()
+    port.dng_opcodes(want, W, 1, [0, 0, W, H], blob)
+    leg("8(f)3 DngOpcodes 8256x5504, 8 opcodes in one pass", rs.dngop_plan(ctx, [dj], low["ops"], low["tables"], low["deltas"]),
+        want, "dngop_kernel")
+    # K11: 20 000 defects
+    n = 20000
+    p = ((rng.integers(0, H, n).astype(np.uint32) << 16) | rng.integers(0, W, n).astype(np.uint32))
+    bj = rs.BadPixJob()
+    bj.offset, bj.pitch, bj.width, bj.height, bj.is_cfa = 0, pitch, W, H, 1
+    bj.first_position, bj.num_positions, bj.prior_map = 0, n, None
+    want = base.copy()
+    port.fix_bad_pixels(want, W, 1, p, True)
+    leg("8(f)3 fixBadPixels 8256x5504, 20000 defects", rs.badpix_plan(ctx, [bj], p), want, "badpix_kernel",
+        restore=False)     # idempotent: good pixels are never written
+    # Panasonic V4, 4592x3448-class frames, 4 per launch
+    w, h, split = 4592 // 14 * 14, 3448, 0x2008
+    nbytes = (w * h // 14 * 16 + 0x3FFF) // 0x4000 * 0x4000
+    data = synth.lcg_bytes(nbytes, 44)
+    opitch = rs.image_pitch(w)
+    nf, fb, ob = 4, (nbytes + 255) // 256 * 256, (h * opitch + 255) // 256 * 256
+    jobs = []
+    for f in range(nf):
+        pj = rs.PanaJob()
+        pj.in_offset, pj.in_size, pj.out_offset, pj.out_pitch = f * fb, nbytes, f * ob, opitch
+        pj.width, pj.height, pj.version, pj.bps = w, h, 4, 12
+        pj.zero_is_not_bad, pj.section_split_offset = 0, split
+        jobs.append(pj)
+    plan = rs.pana_plan(ctx, jobs)
+    d_in = torch.zeros(nf * fb + 64, dtype=torch.uint8, device="cuda")
+    for f in range(nf):
+        d_in[f * fb:f * fb + nbytes] = torch.from_numpy(data)
+    d_out = torch.zeros(nf * ob, dtype=torch.uint8, device="cuda")
+    plan.run((d_in.data_ptr(), nf * fb), d_out)
+    torch.cuda.synchronize()
+    want = port.new_image(w, h)
+    zwant = port.panasonic_v4(want, w, data, False, split, cap=1 << 22)
+    got = d_out[(nf - 1) * ob:(nf - 1) * ob + h * opitch].cpu().numpy().view(np.uint16).reshape(h, opitch // 2)
+    nz, zl = plan.bad_pixels(nf - 1, cap=1 << 22)
+    exact = bool(np.array_equal(got[:, :w], want[:, :w])) and sorted(zl) == zwant
+    ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), nf * fb), d_out), steps, 3, dist)
+    in_b, out_b, pixels = plan.bytes()
+    per = ms / steps
+    out["8(f)4 PanasonicV4Decompressor %dx%d" % (w, h)] = {
+        "MPixels/s": pixels / (per * 1e-3) / 1e6, "ms_per_step": per, "frames_per_step": nf, "bit_exact": exact,
+        "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
+        "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak, "kernel": "pana_kernel<4,12>"}
     return out
 
 
