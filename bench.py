@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--skip-others", action="store_true")
     ap.add_argument("--unvalidated", action="store_true",
                     help="also time the kernels that have not passed their first GPU parity run yet "
-                         "(K9 scaling, K10 DNG opcodes, K11 bad pixels, Panasonic V4); each leg "
+                         "(K9 scaling, K10 DNG opcodes, K11 bad pixels, K12 table lookup, Panasonic V4); each leg "
                          "checks bit-exactness against the oracle before timing")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
@@ -868,6 +868,15 @@ def bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak):
         port.scale_values(want, W, (8, 8, W - 16, H - 16), black, white)
         leg("8(f)3 scaleBlackWhite 8256x5504 (%s, dither)" % label, rs.scale_plan(ctx, [j]), want,
             "scale_kernel<%d>" % (0 if "SSE2" in label else 1))
+    # K12: whole-image table lookup, Sony curve, plain and dithered
+    for dither in (False, True):
+        lj = rs.LookupJob()
+        lj.offset, lj.pitch, lj.width, lj.height, lj.cpp, lj.table = 0, pitch, W, H, 1, 0
+        t = port.build_table(synth.sony_curve(), dither)
+        want = base.copy()
+        port.sixteen_bit_lookup(want, W, 1, t, dither)
+        leg("8(f)3 sixteenBitLookup 8256x5504 (%s)" % ("dithered" if dither else "plain"),
+            rs.lookup_plan(ctx, [lj], t, dither), want, "lookup_kernel<%s>" % ("true" if dither else "false"))
     # K10: eight opcodes in one pass
     from rawspeed_b200 import host
     area = synth.dng_pixel_area((0, 0, H, W))

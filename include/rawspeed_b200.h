@@ -355,6 +355,32 @@ int rsb200_badpix_plan_create(rsb200_ctx* ctx, const rsb200_badpix_job* jobs, in
                               rsb200_plan** plan);
 
 /* ------------------------------------------------------------------ */
+/* K12: 16-bit table lookup of a whole image, in place.  */
+/*   RawImageData::sixteenBitLookup        common/RawImage.cpp:373-378  */
+/*   RawImageDataU16::doLookup      common/RawImageDataU16.cpp:487-520  */
+/* (what DngDecoder does with a LinearizationTable, DngDecoder.cpp:614,  */
+/* and Cr2Decoder with its curve, Cr2Decoder.cpp:117).  Every sample of  */
+/* every row of the uncropped buffer; run with rsb200_plan_run(plan,     */
+/* NULL, 0, d_image, bytes, stream).  NOT YET VALIDATED ON A B200        */
+/* (DESIGN.md K12).                                                      */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  uint64_t offset;  /* byte offset of row 0 of the uncropped image; multiple of 16 */
+  uint32_t pitch;   /* bytes between rows; multiple of 16                          */
+  uint32_t width;   /* uncropped_dim.x (pixels)                                    */
+  uint32_t height;
+  uint32_t cpp;
+  uint32_t table;   /* index into the plan's tables                                */
+  uint32_t reserved;
+} rsb200_lookup_job;
+
+/* tables: ntables tables in TableLookUp's storage layout (common/TableLookUp.cpp:48-85):
+ * dither == 0 -> 65536 uint16 each, dither != 0 -> 2*65536 uint16 each ({base, delta}). */
+int rsb200_lookup_plan_create(rsb200_ctx* ctx, const rsb200_lookup_job* jobs, int njobs,
+                              const uint16_t* tables, int ntables, int dither,
+                              rsb200_plan** plan);
+
+/* ------------------------------------------------------------------ */
 /* K5: Canon sRaw interpolation.                         */
 /*   Cr2sRawInterpolator::interpolate(version)                          */
 /*   interpolators/Cr2sRawInterpolator.cpp:96-187 (4:2:2), :189-453     */

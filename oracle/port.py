@@ -404,6 +404,20 @@ def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
     return list(cr), list(bad[:min(nbad.value, cap)])
 
 
+def sixteen_bit_lookup(img, w, cpp, table, dither):
+    """RawImageData::sixteenBitLookup() in place; table = build_table(curve, dither) storage."""
+    im = _img(img, w, cpp)
+    tp = None
+    if table is not None:
+        table = np.ascontiguousarray(table, dtype=np.uint16)
+        tp = table.ctypes.data_as(C.POINTER(C.c_uint16))
+    e = Err()
+    L = lib()
+    L.rso_sixteen_bit_lookup.argtypes = [C.POINTER(Image), C.POINTER(C.c_uint16), C.c_int, C.POINTER(Err)]
+    e.check(L.rso_sixteen_bit_lookup(C.byref(im), tp, int(dither), C.byref(e)))
+    return img
+
+
 def fix_bad_pixels(img, w, cpp, positions, is_cfa=True):
     """RawImageData::fixBadPixels() with mBadPixelPositions = positions, in place."""
     im = _img(img, w, cpp, is_cfa)

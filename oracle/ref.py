@@ -307,6 +307,22 @@ def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
     return list(cr), list(bad[:min(nbad.value, cap)])
 
 
+def sixteen_bit_lookup(img, w, cpp, crop, curve, dither, nthreads=1):
+    """Reference setTable(curve, dither) + sixteenBitLookup() (ref_sixteen_bit_lookup)."""
+    cr = (C.c_int * 4)(*[int(v) for v in crop])
+    cp, nc = None, 0
+    if curve is not None:
+        curve = np.ascontiguousarray(curve, dtype=np.uint16)
+        cp, nc = curve.ctypes.data_as(C.POINTER(C.c_uint16)), curve.size
+    e = Err()
+    L = lib()
+    L.ref_sixteen_bit_lookup.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.POINTER(C.c_int),
+                                         C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int, C.POINTER(Err)]
+    e.check(L.ref_sixteen_bit_lookup(C.c_void_p(img.ctypes.data), w, img.shape[0], cpp, img.shape[1] * 2,
+                                     cr, cp, nc, int(dither), nthreads, C.byref(e)))
+    return img
+
+
 def fix_bad_pixels(img, w, cpp, positions, is_cfa=True, nthreads=1):
     """Reference RawImageData::fixBadPixels() (ref_fix_bad_pixels)."""
     pos = np.ascontiguousarray(positions, dtype=np.uint32)

@@ -433,6 +433,22 @@ int ref_dng_opcodes(void* img_data, int is_f32, int w, int h, int cpp, int pitch
   });
 }
 
+// mRaw->setTable(curve, dither); mRaw->sixteenBitLookup() on an image cropped to crop[4]
+int ref_sixteen_bit_lookup(uint16_t* img_data, int w, int h, int cpp, int pitch, const int* crop,
+                           const uint16_t* curve, int ncurve, int dither, int nthreads, RefErr* e) {
+  return guarded(e, [&] {
+    ref_set_threads(nthreads);
+    RawImage img = makeImage(w, h, cpp, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    if (crop[0] || crop[1] || crop[2] != w || crop[3] != h)
+      img->subFrame(iRectangle2D(iPoint2D(crop[0], crop[1]), iPoint2D(crop[2], crop[3])));
+    if (curve)
+      img->setTable(std::vector<uint16_t>(curve, curve + ncurve), dither != 0);
+    img->sixteenBitLookup();
+    copyOut(img, img_data, pitch);
+  });
+}
+
 // RawImageData::fixBadPixels() with mBadPixelPositions = positions[0..n)
 int ref_fix_bad_pixels(uint16_t* img_data, int w, int h, int cpp, int pitch, int is_cfa,
                        const uint32_t* positions, uint32_t n, int nthreads, RefErr* e) {

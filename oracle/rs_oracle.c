@@ -4118,3 +4118,40 @@ int rso_fix_bad_pixels(rso_image* img, const uint32_t* positions, uint32_t nposi
   free((void*)map);
   return RSO_OK;
 }
+
+/* ------------------------------------------------------------------
+ * RawImageData::sixteenBitLookup / RawImageDataU16::doLookup
+ * ------------------------------------------------------------------ */
+int rso_sixteen_bit_lookup(rso_image* img, const uint16_t* table, int dither, rso_err* e) {
+  rso_ctx c;
+  rso_err le;
+  const int gw = img->w * img->cpp;
+  int y, x;
+  c.e = e ? e : &le;
+  c.e->code = RSO_OK;
+  c.e->msg[0] = 0;
+  if (setjmp(c.jb))
+    return c.e->code;
+  if (img->is_f32)
+    THROW_RDE(&c, "Unexpected data type");
+  if (!table) /* sixteenBitLookup (:373-376): no table, nothing to do */
+    return RSO_OK;
+  for (y = 0; y < img->h; y++) { /* FULL_IMAGE: uncropped_dim.y rows */
+    uint16_t* row = (uint16_t*)((uint8_t*)img->data + (size_t)y * (size_t)img->pitch);
+    if (dither) {
+      uint32_t v = (uint32_t)(img->w + y * 13) ^ 0x45694584u;
+      for (x = 0; x < gw; x++) {
+        const uint16_t p = row[x];
+        const uint32_t base = table[2 * p + 0], delta = table[2 * p + 1];
+        uint32_t pix;
+        v = 15700u * (v & 65535u) + (v >> 16);
+        pix = base + ((delta * (v & 2047u) + 1024u) >> 12);
+        row[x] = (uint16_t)(pix > 65535u ? 65535u : pix); /* clampBits(pix, 16) */
+      }
+    } else {
+      for (x = 0; x < gw; x++)
+        row[x] = table[row[x]];
+    }
+  }
+  return RSO_OK;
+}

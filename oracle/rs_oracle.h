@@ -269,6 +269,16 @@ int rso_dng_opcodes(rso_image* img, int* crop, const uint8_t* data, uint32_t siz
  * component), as the reference does. */
 int rso_fix_bad_pixels(rso_image* img, const uint32_t* positions, uint32_t npositions, rso_err* e);
 
+/* ---- RawImageData::sixteenBitLookup (common/RawImage.cpp:373-378) + RawImageDataU16::doLookup
+ *      (common/RawImageDataU16.cpp:487-520) ----
+ * (restated and pinned; device pass = K12)
+ * The APPLY_LOOKUP worker carries the FULL_IMAGE flag (common/RawImage.h:58-63, RawImage.cpp:
+ * 272-279): every row of the UNCROPPED buffer, all w * cpp samples of each; `table` = the
+ * storage build_table() / TableLookUp::setTable makes (65536 entries, or 2 * 65536 {base,
+ * delta} when dithered: v = 15700 * (v & 65535) + (v >> 16) seeded (w + 13 y) ^ 0x45694584 per
+ * row, pix = base + ((delta * (v & 2047) + 1024) >> 12)). */
+int rso_sixteen_bit_lookup(rso_image* img, const uint16_t* table, int dither, rso_err* e);
+
 /* ---- SonyArw2Decompressor (decompressors/SonyArw2Decompressor.cpp:41-150) ----
  * One byte per pixel: every row is an LSB-first bit stream of 128-bit blocks; a block
  * carries max(11) min(11) imax(4) imin(4) + 14 x 7-bit deltas for 16 same-parity

@@ -92,6 +92,12 @@ class DngOpJob(C.Structure):
  DNGOP_BAD_CONSTANT) = range(6)
 
 
+class LookupJob(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("pitch", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("cpp", C.c_uint32), ("table", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
 class BadPixJob(C.Structure):
     _fields_ = [("offset", C.c_uint64), ("pitch", C.c_uint32), ("width", C.c_uint32),
                 ("height", C.c_uint32), ("is_cfa", C.c_uint32), ("first_position", C.c_uint32),
@@ -151,7 +157,7 @@ EXPORTS = [
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_raw_plan_create", "rsb200_sraw_plan_create",
     "rsb200_pentax_plan_create", "rsb200_arw2_plan_create", "rsb200_nikon_plan_create",
-    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_scale_plan_create", "rsb200_plan_bad_pixels", "rsb200_dngop_plan_create", "rsb200_badpix_plan_create",
+    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_scale_plan_create", "rsb200_plan_bad_pixels", "rsb200_dngop_plan_create", "rsb200_badpix_plan_create", "rsb200_lookup_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Arw2Job, NikonJob, PanaJob, ScaleJob, DngOp, DngOpJob, BadPixJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, NikonJob, PanaJob, ScaleJob, DngOp, DngOpJob, BadPixJob, LookupJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -232,6 +232,18 @@ def dngop_plan(ctx, jobs, ops, tables=None, deltas=None):
     plan = Plan(ctx, h, len(jobs))
     plan._keep = (tables, deltas)
     return plan
+
+
+def lookup_plan(ctx, jobs, tables, dither=False):
+    """Whole-image table lookup in place (RawImageData::sixteenBitLookup); tables: TableLookUp
+    storage per table (65536 uint16, or 2*65536 when dithered); run with plan.run(None, d_image)."""
+    ja = (LookupJob * len(jobs))(*jobs)
+    tables = np.ascontiguousarray(tables, dtype=np.uint16).reshape(-1, 131072 if dither else 65536)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_lookup_plan_create(ctx.h, ja, len(jobs),
+                                                 tables.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                                 tables.shape[0], int(dither), C.byref(h)))
+    return Plan(ctx, h, len(jobs))
 
 
 def badpix_plan(ctx, jobs, positions):

@@ -305,6 +305,18 @@ int rsb200h_panasonic_v4(uint16_t* img_data, int w, int h, int pitch, const uint
   });
 }
 
+// mRaw->setTable(curve, dither); mRaw->sixteenBitLookup()
+int rsb200h_sixteen_bit_lookup(uint16_t* img_data, int w, int h, int cpp, int pitch,
+                               const uint16_t* curve, int ncurve, int dither, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, cpp, pitch, true, 1, 1);
+    if (curve)
+      img->setTable(std::vector<uint16_t>(curve, curve + ncurve), dither != 0);
+    img->sixteenBitLookup();
+    copyOut(img, img_data);
+  });
+}
+
 // RawImageData::fixBadPixels() with mBadPixelPositions = positions[0..n); map_only != 0: stop
 // after transferBadPixelsToMap() and return the bitmap (no GPU needed): map_out must hold
 // roundUp(ceil(w / 8), 16) * h bytes.

@@ -117,6 +117,32 @@ void RawImageData::subFrame(iRectangle2D crop) {
   dim = crop.dim;
 }
 
+// RawImageData::sixteenBitLookup (common/RawImage.cpp:373-378) -> doLookup over the full image
+void RawImageData::sixteenBitLookup() {
+  if (!hasTable())
+    return;
+  if (dataType != RawImageType::UINT16)
+    ThrowRDE("rawspeed_b200: sixteenBitLookup is implemented for UINT16 images");
+  if (!isAllocated())
+    ThrowRDE("sixteenBitLookup: image has no data");
+  rsb200_lookup_job job;
+  std::memset(&job, 0, sizeof job);
+  job.offset = 0;
+  job.pitch = (uint32_t)pitch;
+  job.width = (uint32_t)uncropped_dim.x;
+  job.height = (uint32_t)uncropped_dim.y;
+  job.cpp = cpp;
+  job.table = 0;
+  PlanGuard pg;
+  engineCheck(rsb200_lookup_plan_create(engine(), &job, 1, tableStorage.data(), 1, ditherTable ? 1 : 0,
+                                        &pg.p),
+              "rsb200_lookup_plan_create");
+  engineCheck(rsb200_plan_run_host_image(pg.p, nullptr, 0, storage, (uint32_t)pitch,
+                                         (uint32_t)(uncropped_dim.x * (int)bpp),
+                                         (uint32_t)uncropped_dim.y, /*partial=*/1),
+              "rsb200_plan_run_host_image");
+}
+
 // RawImageData::createBadPixelMap + transferBadPixelsToMap (common/RawImage.cpp:201-229)
 void RawImageData::transferBadPixelsToMap() {
   std::lock_guard<std::mutex> guard(mBadPixelMutex);

@@ -245,6 +245,9 @@ public:
   // positions move into the bitmap on the host, the interpolation runs on the device (K11)
   void transferBadPixelsToMap();
   void fixBadPixels();
+  // RawImageData::sixteenBitLookup (common/RawImage.cpp:373-378): the table set with
+  // setTable() applied to every sample of the uncropped buffer, on the device (K12)
+  void sixteenBitLookup();
   // RawImageData::subFrame (common/RawImage.cpp:175-199): dim becomes the crop, the data and
   // pitch stay those of the uncropped image
   void subFrame(iRectangle2D crop);

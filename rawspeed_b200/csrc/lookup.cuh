@@ -1,0 +1,70 @@
+// lookup.cuh -- K12: 16-bit table lookup (curve, optionally dithered) of a whole image, in
+// place (sm_100a).  Reference: RawImageDataU16::doLookup (common/RawImageDataU16.cpp:487-520);
+// the per-lane arithmetic is in lookup_core.h (shared with the CPU replay in tests/emu).
+//
+// A streaming map, 2 B read + 2 B written per sample; the 128 KB (256 KB dithered) table is read
+// through L1/L2.  Same decomposition as K9: one warp = four rows, a lane owns one aligned group
+// of eight samples per row and iteration (4 x LDG.128 issued before the arithmetic), and jumps
+// the 248 samples to its next group with one modular multiplication.
+//
+// NOT YET RUN ON A B200 (round 1 ended without GPU time for it): checked by replaying this loop
+// on the CPU against the oracle (tests/test_lookup_emu.py).
+#pragma once
+
+#include "common.cuh"
+#include "lookup_core.h"
+#include "scale.cuh" // scale_ld / scale_st, SCALE_ROWS
+
+namespace rsb200 {
+
+constexpr int LUT_WARPS = 8;
+constexpr int LUT_NT = 32 * LUT_WARPS;
+
+template <bool DITHER>
+__global__ void __launch_bounds__(LUT_NT)
+    lookup_kernel(uint8_t* __restrict__ img, const LookupJobDev* __restrict__ jobs, int njobs,
+                  uint32_t total_quads, const uint16_t* __restrict__ tables) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t quad = blockIdx.x * LUT_WARPS + warp;
+  if (quad >= total_quads)
+    return;
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].quad_begin <= quad)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const LookupJobDev j = jobs[lo];
+  const uint32_t y0 = (quad - j.quad_begin) * SCALE_ROWS;
+  uint8_t* const base = img + j.offset + (uint64_t)y0 * j.pitch;
+  const uint16_t* const table = tables + (size_t)j.table * (DITHER ? 131072u : 65536u);
+  const uint32_t iters = (j.ngroups + 31) / 32;
+  const uint32_t jump = DITHER ? lut_powmod(248u) : 0u;
+  uint32_t st[SCALE_ROWS];
+#pragma unroll
+  for (int r = 0; r < SCALE_ROWS; ++r)
+    st[r] = DITHER ? lut_mwc_state(j.width, y0 + r, 8u * (uint32_t)lane) : 0u;
+  for (uint32_t it = 0; it < iters; ++it) {
+    const uint32_t g = it * 32 + lane;
+    if (g < j.ngroups) {
+      ScaleVec v[SCALE_ROWS];
+#pragma unroll
+      for (int r = 0; r < SCALE_ROWS; ++r)
+        if (y0 + r < j.height)
+          v[r] = scale_ld(base + (uint64_t)r * j.pitch + (uint64_t)g * 16);
+#pragma unroll
+      for (int r = 0; r < SCALE_ROWS; ++r) {
+        if (y0 + r < j.height) {
+          const ScaleVec o = lut_group<DITHER>(v[r], table, j.ncols, 8u * g, st[r]);
+          scale_st(base + (uint64_t)r * j.pitch + (uint64_t)g * 16, o);
+          if (DITHER)
+            st[r] = lut_mwc_jump(st[r], 248u, jump);
+        }
+      }
+    }
+  }
+}
+
+} // namespace rsb200

@@ -9,6 +9,8 @@
 #include "ljpeg_ranges.cuh"
 #include "ljpeg_thread.cuh"
 #include "rawforms.cuh"
+#include "lookup.cuh"
+#include "lookup_host.h"
 #include "scale.cuh"
 #include "scale_host.h"
 #include "sraw.cuh"
@@ -117,7 +119,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place), 8 DNG opcode list (in place), 9 bad-pixel interpolation (in place)
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place), 8 DNG opcode list (in place), 9 bad-pixel interpolation (in place), 10 whole-image table lookup (in place)
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -145,6 +147,12 @@ struct rsb200_plan {
   uint32_t* d_dngop_deltas = nullptr;
   int dngop_njobs = 0;
   uint32_t dngop_units = 0;
+  // whole-image table lookup (K12)
+  LookupJobDev* d_lookup_jobs = nullptr;
+  uint16_t* d_lookup_tables = nullptr;
+  int lookup_njobs = 0;
+  uint32_t lookup_quads = 0;
+  bool lookup_dither = false;
   // bad-pixel interpolation (K11)
   BadPixJobDev* d_badpix_jobs = nullptr;
   uint32_t* d_badpix_list = nullptr;
@@ -557,6 +565,46 @@ static cudaError_t run_raw_group(const RawGroup& g, const uint8_t* in, uint64_t 
 // ------------------------------------------------------------------
 // sRaw interpolation (K5)
 // ------------------------------------------------------------------
+// K12: whole-image table lookup (RawImageData::sixteenBitLookup)
+extern "C" int rsb200_lookup_plan_create(rsb200_ctx* ctx, const rsb200_lookup_job* jobs, int njobs,
+                                         const uint16_t* tables, int ntables, int dither,
+                                         rsb200_plan** out) {
+  if (!ctx || !jobs || njobs <= 0 || !out || !tables || ntables <= 0)
+    return set_err(ctx, RSB200_ERR_ARG, "lookup_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<rsb200_plan, void (*)(rsb200_plan*)> holder(new rsb200_plan, rsb200_plan_destroy);
+  rsb200_plan* p = holder.get();
+  p->ctx = ctx;
+  p->kind = 10;
+  p->nunits = njobs;
+  p->lookup_dither = dither != 0;
+  std::vector<LookupJobDev> hj((size_t)njobs);
+  uint64_t quads = 0;
+  for (int i = 0; i < njobs; ++i) {
+    if (const char* why = lookup_build_job(jobs[i], ntables, (uint32_t)quads, &hj[i]))
+      return set_err(ctx, RSB200_ERR_ARG, "lookup job %d: %s", i, why);
+    quads += lookup_job_quads(jobs[i]);
+    if (quads > 0x7FFFFFFFull)
+      return set_err(ctx, RSB200_ERR_ARG, "lookup plan: too many rows");
+    const uint64_t bytes = (uint64_t)hj[i].ncols * jobs[i].height * 2;
+    p->in_bytes += bytes;
+    p->out_bytes += bytes;
+    p->pixels += (uint64_t)jobs[i].width * jobs[i].height;
+    p->need_out = std::max<uint64_t>(p->need_out, jobs[i].offset + (uint64_t)jobs[i].height * jobs[i].pitch);
+  }
+  p->lookup_njobs = njobs;
+  p->lookup_quads = (uint32_t)quads;
+  const size_t tbytes = sizeof(uint16_t) * (size_t)ntables * (dither ? 131072u : 65536u);
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_lookup_jobs, sizeof(LookupJobDev) * hj.size()));
+  CUDA_TRY(ctx, cudaMemcpy(p->d_lookup_jobs, hj.data(), sizeof(LookupJobDev) * hj.size(),
+                           cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_lookup_tables, tbytes));
+  CUDA_TRY(ctx, cudaMemcpy(p->d_lookup_tables, tables, tbytes, cudaMemcpyHostToDevice));
+  p->launches_per_run = 1;
+  *out = holder.release();
+  return RSB200_OK;
+}
+
 // K11: bad-pixel interpolation (RawImageData::fixBadPixels)
 extern "C" int rsb200_badpix_plan_create(rsb200_ctx* ctx, const rsb200_badpix_job* jobs, int njobs,
                                          const uint32_t* positions, uint32_t npositions,
@@ -1849,6 +1897,16 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, run_unpack_group(g, in, (uint64_t)in_bytes, outp, st));
       ctx->launches++;
     }
+  } else if (p->kind == 10) {
+    const uint32_t nb = (p->lookup_quads + LUT_WARPS - 1) / LUT_WARPS;
+    if (p->lookup_dither)
+      lookup_kernel<true><<<nb, LUT_NT, 0, st>>>(outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads,
+                                                 p->d_lookup_tables);
+    else
+      lookup_kernel<false><<<nb, LUT_NT, 0, st>>>(outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads,
+                                                  p->d_lookup_tables);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
   } else if (p->kind == 9) {
     if (p->badpix_total) {
       badpix_kernel<<<(p->badpix_total + BADPIX_NT - 1) / BADPIX_NT, BADPIX_NT, 0, st>>>(
@@ -2215,6 +2273,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     cudaFree(g.d_jobs);
   cudaFree(p->d_pana_zero_count);
   cudaFree(p->d_pana_zero_list);
+  cudaFree(p->d_lookup_jobs);
+  cudaFree(p->d_lookup_tables);
   cudaFree(p->d_badpix_jobs);
   cudaFree(p->d_badpix_list);
   cudaFree(p->d_badpix_maps);

@@ -32,7 +32,7 @@ EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_sraw_interpolate", "rsb200h_nikon_decompress", "rsb200h_sony_arw2",
            "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white",
            "rsb200h_panasonic_v4", "rsb200h_dng_opcodes", "rsb200h_dngop_lower",
-           "rsb200h_fix_bad_pixels"]
+           "rsb200h_fix_bad_pixels", "rsb200h_sixteen_bit_lookup"]
 
 _lib = None
 
@@ -231,6 +231,21 @@ def sony_arw2(img, w, data, curve=None, dither=False):
                                     C.POINTER(C.c_uint16), C.c_int, C.c_int, C.POINTER(_Err)]
     e.check(L.rsb200h_sony_arw2(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
                                 p, C.c_uint32(n), cp, nc, int(dither), C.byref(e)))
+    return img
+
+
+def sixteen_bit_lookup(img, w, cpp, curve, dither):
+    """mRaw->setTable(curve, dither); mRaw->sixteenBitLookup() via the host mirror, in place."""
+    cp, nc = None, 0
+    if curve is not None:
+        curve = np.ascontiguousarray(curve, dtype=np.uint16)
+        cp, nc = curve.ctypes.data_as(C.POINTER(C.c_uint16)), curve.size
+    e = _Err()
+    L = lib()
+    L.rsb200h_sixteen_bit_lookup.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.POINTER(C.c_uint16), C.c_int,
+                                                                            C.c_int, C.POINTER(_Err)]
+    e.check(L.rsb200h_sixteen_bit_lookup(C.c_void_p(img.ctypes.data), w, img.shape[0], cpp,
+                                         img.shape[1] * 2, cp, nc, int(dither), C.byref(e)))
     return img
 
 

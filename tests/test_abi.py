@@ -49,6 +49,7 @@ int main(void){
          offsetof(rsb200_scale_job, white_point), offsetof(rsb200_scale_job, path));
   printf("%zu %zu %zu %zu %zu\n", sizeof(rsb200_arw2_job), sizeof(rsb200_nikon_job),
          sizeof(rsb200_phaseone_job), sizeof(rsb200_phaseone_strip), offsetof(rsb200_nikon_job, pup));
+  printf("%zu %zu\n", sizeof(rsb200_lookup_job), offsetof(rsb200_lookup_job, table));
   printf("%zu %zu %zu %zu %zu\n", sizeof(rsb200_dng_op), sizeof(rsb200_dngop_job), sizeof(rsb200_badpix_job),
          offsetof(rsb200_badpix_job, prior_map), offsetof(rsb200_dng_op, value));
   return 0; }''')
@@ -70,6 +71,7 @@ int main(void){
             _abi.ScaleJob.white_point.offset, _abi.ScaleJob.path.offset,
             C.sizeof(_abi.Arw2Job), C.sizeof(_abi.NikonJob), C.sizeof(_abi.PhaseOneJob),
             C.sizeof(_abi.PhaseOneStrip), _abi.NikonJob.pup.offset,
+            C.sizeof(_abi.LookupJob), _abi.LookupJob.table.offset,
             C.sizeof(_abi.DngOp), C.sizeof(_abi.DngOpJob), C.sizeof(_abi.BadPixJob),
             _abi.BadPixJob.prior_map.offset, _abi.DngOp.value.offset]
     assert got == want

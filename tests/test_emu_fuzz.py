@@ -13,6 +13,8 @@ from test_scale_emu import emu as scale_emu, job as scale_job, run as scale_run 
 from test_dngop_emu import emu as dngop_emu, replay as dngop_replay               # noqa: F401
 from test_badpix_emu import emu as badpix_emu, job as badpix_job                  # noqa: F401
 from test_pana4_emu import emu as pana4_emu, v4_payload                           # noqa: F401
+from test_lookup_emu import emu as lookup_emu, job as lookup_job                  # noqa: F401
+from rawspeed_b200._abi import LookupJob
 
 HAVE_REF = ref.available()
 
@@ -149,3 +151,24 @@ def test_panasonic_v4_fuzz(pana4_emu, seed):
                             int(zero_ok), zl.ctypes.data, zl.size, C.byref(nz))
     assert np.array_equal(got, want)
     assert sorted(zl[:nz.value].tolist()) == zwant
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_lookup_fuzz(lookup_emu, seed):
+    rng = np.random.default_rng(5000 + seed)
+    cpp = int(rng.integers(1, 4))
+    w, h = int(rng.integers(1, 700)), int(rng.integers(1, 14))
+    dither = bool(seed & 1)
+    cv = np.sort(rng.integers(0, 65536, int(rng.integers(1, 5000)))).astype(np.uint16)
+    a = rnd_image(rng, w, h, cpp)
+    want = a.copy()
+    t = port.build_table(cv, dither)
+    port.sixteen_bit_lookup(want, w, cpp, t, dither)
+    if HAVE_REF:
+        r = a.copy()
+        ref.sixteen_bit_lookup(r, w, cpp, [0, 0, w, h], cv, dither, nthreads=2)
+        assert np.array_equal(r, want)
+    err = C.create_string_buffer(256)
+    assert lookup_emu.lookup_emu_run(a.ctypes.data, (LookupJob * 1)(lookup_job(0, a, w, cpp)), 1,
+                                     t.ctypes.data, 1, int(dither), err, 256) == 0, err.value
+    assert np.array_equal(a, want)
