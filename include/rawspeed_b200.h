@@ -548,7 +548,8 @@ int rsb200_plan_run(rsb200_plan* plan, const void* d_in, size_t in_bytes,
                     void* d_out, size_t out_bytes, void* stream);
 /* Host buffers: H2D copy of `in`, kernels, D2H copy of `out` (pinned staging is
  * the library's), then waits.  `out` must hold the current image contents for
- * bytes the decode does not write (it is uploaded first when partial != 0). */
+ * bytes the decode does not write (it is uploaded first when partial != 0; always
+ * for the in-place plans K9 - K12, which take in == NULL, in_bytes == 0). */
 int rsb200_plan_run_host(rsb200_plan* plan, const uint8_t* in, size_t in_bytes,
                          uint8_t* out, size_t out_bytes, int partial);
 /* Same, for a plan whose output is ONE RawImage (pitch bytes between rows): only

@@ -2096,6 +2096,8 @@ extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in
     return rc;
   if (in_bytes < p->need_in || out_bytes < p->need_out)
     return set_err(ctx, RSB200_ERR_ARG, "plan_run_host: buffers too small");
+  if (p->kind >= 7)
+    partial = 1; // in-place plans work on the image the caller holds: it always goes up first
   if (!partial && unpack_pipeline_ok(p))
     return run_host_unpack_pipelined(p, in, in_bytes, out, out_bytes);
   cudaStream_t st = ctx->stream;
@@ -2119,6 +2121,8 @@ extern "C" int rsb200_plan_run_host_image(rsb200_plan* p, const uint8_t* in, siz
   rsb200_ctx* ctx = p->ctx;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t out_bytes = (size_t)pitch * rows;
+  if (p->kind >= 7)
+    partial = 1; // in-place plans: the image always goes up first
   int rc = ensure_cap(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes + 16);
   if (rc)
     return rc;
