@@ -262,6 +262,8 @@ def main():
                     help="run BASELINE configs[4]: the 256-frame LJPEG batch sharded over the "
                          "ranks (256/N frames per GPU, strong scaling) + NCCL gather of the outputs")
     ap.add_argument("--skip-others", action="store_true")
+    ap.add_argument("--only-unvalidated", action="store_true",
+                    help="with --unvalidated: skip the other (validated) secondary legs (short runs under ncu)")
     ap.add_argument("--unvalidated", action="store_true",
                     help="also time the kernels that have not passed their first GPU parity run yet "
                          "(K9 scaling, K10 DNG opcodes, K11 bad pixels, K12 table lookup, Panasonic V4); each leg "
@@ -433,6 +435,8 @@ def bench_gather(torch, dist, d_out, world, rank, plan, d_in, args, frames, out_
 def bench_others(torch, rs, ctx, port, synth, args, dist, peak):
     """configs[2] (DNG LJPEG tiles) and configs[3] (CR2): device-timed decode."""
     from helpers import dng_ljpeg_scans, parse_ljpeg, TableSet
+    if args.unvalidated and args.only_unvalidated:
+        return bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak)
     out = {}
     steps = max(3, min(args.steps, 10))
     # ---- C3: 8256x5504 DNG, 726 LJPEG tiles of 256x256, 2 components ----
