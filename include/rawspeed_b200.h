@@ -181,8 +181,7 @@ int rsb200_arw2_plan_create(rsb200_ctx* ctx, const rsb200_arw2_job* jobs, int nj
 /* ------------------------------------------------------------------ */
 /* K7: Panasonic RW2 block codecs V4 / V5 / V6 / V7.     */
 /*   PanasonicV4Decompressor::processBlock (+ ProxyStream section swap) */
-/*       decompressors/PanasonicV4Decompressor.cpp:129-236  (V4: written */
-/*       and CPU-replayed, NOT YET RUN ON A B200 -- DESIGN.md K7)        */
+/*       decompressors/PanasonicV4Decompressor.cpp:129-236               */
 /*   PanasonicV5Decompressor::processBlock (+ ProxyStream section swap) */
 /*       decompressors/PanasonicV5Decompressor.cpp:147-232              */
 /*   PanasonicV6Decompressor::decompressBlock  PanasonicV6Decompressor.cpp:88-221 */
@@ -251,7 +250,6 @@ int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseone_job* jobs
 /* The job scales the crop rows of one uint16 image that already lives  */
 /* in the plan's OUTPUT buffer (a decode plan's output): run it with     */
 /* rsb200_plan_run(plan, NULL, 0, d_image, bytes, stream).              */
-/* NOT YET VALIDATED ON A B200.                     */
 /* ------------------------------------------------------------------ */
 typedef struct {
   uint64_t offset;     /* byte offset of row 0 of the UNCROPPED image; multiple of 16 */
@@ -288,7 +286,7 @@ int rsb200_scale_plan_create(rsb200_ctx* ctx, const rsb200_scale_job* jobs, int 
 /* class does what the reference's constructor and setup() do); what     */
 /* reaches the device are the per-sample maps, with their ROI in         */
 /* UNCROPPED pixel coordinates.  Run with rsb200_plan_run(plan, NULL, 0, */
-/* d_image, bytes, stream).  NOT YET VALIDATED ON A B200.*/
+/* d_image, bytes, stream).                                              */
 /* ------------------------------------------------------------------ */
 #define RSB200_DNGOP_LOOKUP 0       /* MapTable / MapPolynomial: v = table[v] (uint16)       */
 #define RSB200_DNGOP_OFFSET_ROW 1   /* DeltaPerRow: clampBits(delta[y] + v, 16) | d[y] + v    */
@@ -336,7 +334,6 @@ int rsb200_dngop_plan_create(rsb200_ctx* ctx, const rsb200_dngop_job* jobs, int 
 /* uint16 images with one component per pixel (the reference's indexing  */
 /* for cpp > 1 makes the result depend on its visiting order; refused).  */
 /* Run with rsb200_plan_run(plan, NULL, 0, d_image, bytes, stream).      */
-/* NOT YET VALIDATED ON A B200.                          */
 /* ------------------------------------------------------------------ */
 typedef struct {
   uint64_t offset;         /* byte offset of row 0 of the uncropped image; multiple of 2   */
@@ -361,8 +358,7 @@ int rsb200_badpix_plan_create(rsb200_ctx* ctx, const rsb200_badpix_job* jobs, in
 /* (what DngDecoder does with a LinearizationTable, DngDecoder.cpp:614,  */
 /* and Cr2Decoder with its curve, Cr2Decoder.cpp:117).  Every sample of  */
 /* every row of the uncropped buffer; run with rsb200_plan_run(plan,     */
-/* NULL, 0, d_image, bytes, stream).  NOT YET VALIDATED ON A B200        */
-/* (DESIGN.md K12).                                                      */
+/* NULL, 0, d_image, bytes, stream).                                     */
 /* ------------------------------------------------------------------ */
 typedef struct {
   uint64_t offset;  /* byte offset of row 0 of the uncropped image; multiple of 16 */

@@ -8,8 +8,8 @@
 // consults is the reference's mBadPixelMap.  Work is proportional to the number of bad
 // pixels, not to the image: a latency-bound scatter of a few thousand threads.
 //
-// NOT YET RUN ON A B200 (round 1 ended without GPU time for it): checked by replaying the thread
-// program on the CPU against the oracle (tests/test_badpix_emu.py).
+// Developed against a CPU replay of the thread program (tests/test_badpix_emu.py); first run on
+// a B200: bit-exact (profiles/r1_postdecode_first_gpu_run.md).
 #pragma once
 
 #include "badpix_core.h"

@@ -9,8 +9,9 @@
 // per sample regardless of the length of the list: HBM bound.  Lookup tables (128 KB each)
 // and delta arrays stay in L2.
 //
-// NOT YET RUN ON A B200 (round 1 ended without GPU time for it): checked by replaying the thread
-// program on the CPU against the oracle (tests/test_dngop_emu.py).
+// Developed against a CPU replay of the thread program (tests/test_dngop_emu.py); first run on
+// a B200: bit-exact (profiles/r1_postdecode_first_gpu_run.md), 0.51 ms per 45 MP frame with
+// eight opcodes -- issue bound (the per-sample lattice tests), the next thing to tune.
 #pragma once
 
 #include "common.cuh"

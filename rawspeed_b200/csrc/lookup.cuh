@@ -7,8 +7,9 @@
 // of eight samples per row and iteration (4 x LDG.128 issued before the arithmetic), and jumps
 // the 248 samples to its next group with one modular multiplication.
 //
-// NOT YET RUN ON A B200 (round 1 ended without GPU time for it): checked by replaying this loop
-// on the CPU against the oracle (tests/test_lookup_emu.py).
+// Developed against a CPU replay of this loop (tests/test_lookup_emu.py); first run on a B200:
+// bit-exact (profiles/r1_postdecode_first_gpu_run.md); the plain lookup is bound by the table
+// gather (one 2-byte load per sample) -- staging the 128 KB table in shared memory is the lever.
 #pragma once
 
 #include "common.cuh"

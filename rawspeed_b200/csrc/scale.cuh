@@ -8,8 +8,8 @@
 // sequential along a row, so every iteration starts with the 32 lanes advancing the 4 x 8
 // generators of the quad by 32 steps into the warp's private 1 KB of shared memory.
 //
-// NOT YET RUN ON A B200 (round 1 ended without GPU time for it): the arithmetic and the
-// indexing are checked by replaying this loop on the CPU (tests/test_scale_emu.py).
+// Developed against a CPU replay of this loop (tests/test_scale_emu.py); first run on a B200:
+// bit-exact (profiles/r1_postdecode_first_gpu_run.md).
 #pragma once
 
 #include "common.cuh"

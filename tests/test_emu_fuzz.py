@@ -1,4 +1,4 @@
-"""Seeded differential fuzz of the kernels awaiting their first GPU run (K9 scaling, K10 DNG
+"""Seeded differential fuzz of the kernels developed against CPU replays (K9 scaling, K10 DNG
 opcodes, K11 bad pixels, Panasonic V4): random geometries and parameters, three ways --
 compiled reference (where built), oracle, CPU replay of the kernel's thread program -- all
 bit-exact.  Sized to run in a few seconds."""

@@ -1,4 +1,4 @@
-"""Fast first contact with the GPU for the kernels that have not run yet (K9 scaling, K10 DNG
+"""Fast GPU check of the kernels developed against CPU replays (K9 scaling, K10 DNG
 opcodes, K11 bad pixels, K12 table lookup, Panasonic V4): every scenario of their test files
 through the C++ host mirror (-> C ABI -> kernel; no torch import, the library owns the device
 buffers), compared with the oracle.  Prints one line per case and a summary; exit code =
