@@ -59,7 +59,7 @@ RSD_HD uint32_t dngop_clamp16(int32_t v) { return (uint32_t)(v < 0 ? 0 : (v > 65
 // v[8]: samples s0 .. s0+7 of row r (uint16 values, or float bit patterns); Sink::hit(slot,
 // row, col) receives FixBadPixelsConstant matches.
 template <class Sink>
-RSD_HD void dngop_apply_group(const DngOpDev* ops, uint32_t nops, const uint16_t* tables,
+RSD_HD void dngop_apply_group_v1(const DngOpDev* ops, uint32_t nops, const uint16_t* tables,
                               const uint32_t* deltas, const DngOpJobDev& jb, uint32_t r,
                               uint32_t s0, uint32_t (&v)[8], Sink& sink) {
   for (uint32_t k = 0; k < nops; ++k) {
@@ -124,6 +124,119 @@ RSD_HD void dngop_apply_group(const DngOpDev* ops, uint32_t nops, const uint16_t
       }
     }
   }
+}
+
+// ---- second version of the walk (RSB200_DNGOP_V2; same results, fewer instructions) ----------
+// The first version pays, per opcode and SAMPLE, a division by the run-time column pitch and a
+// switch on the opcode kind.  Here the lattice position of the group's first column is computed
+// once per opcode (one division) and stepped incrementally as the column advances, and the
+// kind is dispatched once per opcode, outside the sample loop.  First measured on a B200 the
+// first version was issue bound (0.51 ms per 45 MP frame with eight opcodes); this one is the
+// candidate to A/B against it (tools/ab_ljpeg.py build NAME -DRSB200_DNGOP_V2).
+template <class Sink>
+RSD_HD void dngop_apply_group_v2(const DngOpDev* ops, uint32_t nops, const uint16_t* tables,
+                                 const uint32_t* deltas, const DngOpJobDev& jb, uint32_t r,
+                                 uint32_t s0, uint32_t (&v)[8], Sink& sink) {
+  const uint32_t col0 = s0 / jb.cpp, plane0 = s0 - col0 * jb.cpp;
+  const uint32_t nvalid = jb.samples - s0 < 8u ? jb.samples - s0 : 8u;
+  for (uint32_t k = 0; k < nops; ++k) {
+    const DngOpDev op = ops[k];
+    if (r < op.top || r >= op.bottom)
+      continue;
+    const uint32_t ry = r - op.top;
+    const uint32_t yi = op.row_pitch == 1 ? ry : ry / op.row_pitch;
+    if (yi * op.row_pitch != ry)
+      continue;
+    // the group's columns: col0 .. col0 + 7 / cpp; nothing to do if they miss [left, right)
+    if (col0 >= op.right || col0 + 8u <= op.left)
+      continue;
+    // lattice phase of col0 relative to `left`: d = col0 - left (may be negative),
+    // xi = floor(d / pitch), rem = d mod pitch in [0, pitch)
+    const int32_t d = (int32_t)col0 - (int32_t)op.left, pit = (int32_t)op.col_pitch;
+    int32_t xi, rem;
+    if (d >= 0) {
+      xi = pit == 1 ? d : d / pit;
+      rem = d - xi * pit;
+    } else {
+      const int32_t q = (-d + pit - 1) / pit; // ceil(-d / pit)
+      xi = -q;
+      rem = d + q * pit;
+    }
+    const bool by_row = op.kind == DNGOP_OFFSET_ROW || op.kind == DNGOP_SCALE_ROW;
+    // which of the eight samples this opcode touches, and with which delta index
+    uint32_t hit = 0;
+    uint32_t col = col0, plane = plane0;
+    int32_t sel[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 8; ++i) {
+      const bool in = (uint32_t)i < nvalid && rem == 0 && col >= op.left && col < op.right &&
+                      plane - op.first_plane < op.planes;
+      hit |= (in ? 1u : 0u) << i;
+      sel[i] = by_row ? (int32_t)yi : xi;
+      if (++plane == jb.cpp) {
+        plane = 0;
+        ++col;
+        if (++rem == pit) {
+          rem = 0;
+          ++xi;
+        }
+      }
+    }
+    if (!hit)
+      continue;
+    if (op.kind == DNGOP_LOOKUP) {
+      const uint16_t* t = tables + (size_t)op.table * 65536u;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; ++i)
+        if ((hit >> i) & 1u)
+          v[i] = t[v[i]];
+    } else if (op.kind == DNGOP_BAD_CONSTANT) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; ++i)
+        if (((hit >> i) & 1u) && v[i] == op.value)
+          sink.hit(op.slot, r, (s0 + (uint32_t)i) / jb.cpp);
+    } else {
+      const bool scale = op.kind == DNGOP_SCALE_ROW || op.kind == DNGOP_SCALE_COL;
+      const uint32_t* dl = deltas + op.table;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; ++i) {
+        if (!((hit >> i) & 1u))
+          continue;
+        const uint32_t dv = dl[sel[i]];
+        if (jb.is_f32) {
+          union { uint32_t u; float f; } a, dd;
+          a.u = v[i];
+          dd.u = dv;
+          a.f = scale ? dd.f * a.f : dd.f + a.f;
+          v[i] = a.u;
+        } else if (scale) {
+          v[i] = dngop_clamp16(((int32_t)dv * (int32_t)v[i] + 512) >> 10);
+        } else {
+          v[i] = dngop_clamp16((int32_t)dv + (int32_t)v[i]);
+        }
+      }
+    }
+  }
+}
+
+// the walk the kernel (and its CPU replay) uses
+template <class Sink>
+RSD_HD void dngop_apply_group(const DngOpDev* ops, uint32_t nops, const uint16_t* tables,
+                              const uint32_t* deltas, const DngOpJobDev& jb, uint32_t r,
+                              uint32_t s0, uint32_t (&v)[8], Sink& sink) {
+#if defined(RSB200_DNGOP_V2)
+  dngop_apply_group_v2(ops, nops, tables, deltas, jb, r, s0, v, sink);
+#else
+  dngop_apply_group_v1(ops, nops, tables, deltas, jb, r, s0, v, sink);
+#endif
 }
 
 } // namespace rsb200

@@ -19,17 +19,21 @@ from test_oracle_dngopcodes import scenarios
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "dngop_emu.cpp")
-OUT = os.path.join(HERE, "emu", "_build", "libdngop_emu.so")
+OUT = os.path.join(HERE, "emu", "_build", "libdngop_emu%s.so")
 DEPS = [SRC] + [os.path.join(HERE, "..", "rawspeed_b200", "csrc", f)
                 for f in ("dngop_core.h", "dngop_host.h")]
 
 
-@pytest.fixture(scope="module")
-def emu():
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
-        os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-o", OUT, SRC])
-    lib = C.CDLL(OUT)
+@pytest.fixture(scope="module", params=["", "_v2"])
+def emu(request):
+    """Both versions of the opcode walk: the one the library ships (validated on the GPU) and the
+    A/B candidate behind -DRSB200_DNGOP_V2."""
+    out = OUT % request.param
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        flags = ["-DRSB200_DNGOP_V2"] if request.param else []
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared"] + flags + ["-o", out, SRC])
+    lib = C.CDLL(out)
     lib.dngop_emu_run.argtypes = [C.c_void_p, C.POINTER(DngOpJob), C.c_int, C.POINTER(DngOp), C.c_int,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32,
                                   C.c_char_p, C.c_int]

@@ -33,6 +33,13 @@ try:
 except Exception as ex:   # noqa: BLE001
     print("bench line unreadable:", ex)
 PY
+# A/B of the second opcode walk (build it here first: python tools/ab_ljpeg.py build dngop_v2 -DRSB200_DNGOP_V2)
+python tools/quick_time.py > "$OUT/quick_time_v1.log" 2>&1
+grep "K10" "$OUT/quick_time_v1.log" | sed 's/^/shipped  /' | tee -a "$OUT/summary.txt"
+if [ -f tools/_ab/dngop_v2.so ]; then
+  RSB200_LIB=tools/_ab/dngop_v2.so python tools/quick_time.py > "$OUT/quick_time_v2.log" 2>&1
+  grep "K10" "$OUT/quick_time_v2.log" | sed 's/^/DNGOP_V2 /' | tee -a "$OUT/summary.txt"
+fi
 if command -v ncu > /dev/null; then
   for k in scale_kernel lookup_kernel dngop_kernel badpix_kernel "pana_kernel<4"; do
     f=$(echo "$k" | tr -cd 'a-z0-9_')
