@@ -15,7 +15,7 @@ OUT=gpurun_out/first_run
 mkdir -p "$OUT"
 export RSB200_UNVALIDATED=1
 python -m pytest tests/test_gpu_scale.py tests/test_gpu_lookup.py tests/test_gpu_dngopcodes.py \
-       tests/test_gpu_badpixels.py tests/test_gpu_panasonic_v4.py -m gpu -x -q > "$OUT/gated_tests.log" 2>&1
+       tests/test_gpu_badpixels.py tests/test_gpu_panasonic_v4.py tests/test_examples.py -m gpu -x -q > "$OUT/gated_tests.log" 2>&1
 echo "gated tests exit $?" | tee -a "$OUT/summary.txt"
 tail -5 "$OUT/gated_tests.log"
 python -m pytest tests -m gpu -q > "$OUT/all_gpu_tests.log" 2>&1
