@@ -172,3 +172,50 @@ def test_lookup_fuzz(lookup_emu, seed):
     assert lookup_emu.lookup_emu_run(a.ctypes.data, (LookupJob * 1)(lookup_job(0, a, w, cpp)), 1,
                                      t.ctypes.data, 1, int(dither), err, 256) == 0, err.value
     assert np.array_equal(a, want)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libref.so not built")
+@pytest.mark.parametrize("seed", range(250))
+def test_mutated_opcode_lists_fail_alike(seed):
+    """Byte-level mutations of valid opcode lists (what fuzz/librawspeed/common/DngOpcodes.cpp
+    feeds the reference): the compiled reference, the oracle and the host mirror's parser agree
+    on success / exception class / stage, and reference and oracle on the image and the lists."""
+    from rawspeed_b200 import host
+    rng = np.random.default_rng(6000 + seed)
+    cpp = int(rng.integers(1, 3))
+    w, h = int(rng.integers(8, 40)), int(rng.integers(4, 12))
+    a = rnd_image(rng, w, h, cpp, 64)
+    blob = _random_opcode_list(rng, w, h, cpp, False).copy()
+    for _ in range(int(rng.integers(1, 4))):
+        kind = int(rng.integers(0, 4))
+        i = int(rng.integers(0, blob.size))
+        if kind == 0:
+            blob[i] = rng.integers(0, 256)
+        elif kind == 1:
+            blob[i] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2 and blob.size > 8:
+            blob = blob[:int(rng.integers(4, blob.size))].copy()
+        else:
+            blob = np.concatenate([blob, rng.integers(0, 256, int(rng.integers(1, 6))).astype(np.uint8)])
+    crop = [0, 0, w, h]
+    res = {}
+    for name, mod in (("ref", ref), ("port", port)):
+        im = a.copy()
+        try:
+            out = mod.dng_opcodes(im, w, cpp, crop, blob)
+            res[name] = ("ok", out, im)
+        except Exception as ex:   # noqa: BLE001
+            res[name] = (type(ex).__name__, tuple(mod.dng_opcodes.partial[:2]), im)
+    assert res["ref"][0] == res["port"][0], (res["ref"][0], res["port"][0])
+    assert tuple(res["ref"][1]) == tuple(res["port"][1])
+    assert np.array_equal(res["ref"][2], res["port"][2])
+    # the mirror: constructor errors raise from dngop_lower; setup()/apply() errors come back in "error"
+    stage = ref.dng_opcodes.stage
+    try:
+        low = host.dngop_lower(a, w, cpp, crop, blob)
+        got = "ok" if low["error"] is None else type(low["error"]).__name__
+        assert stage != 1, "the reference's constructor threw, the mirror's did not"
+    except Exception as ex:   # noqa: BLE001
+        got = type(ex).__name__
+        assert stage == 1, "the mirror's constructor threw (%s), the reference's did not" % ex
+    assert got == res["ref"][0]
