@@ -80,3 +80,76 @@ def test_truncated_or_short_packed_strips(seed):
     assert ra == rb, (ra, rb)
     if ra == "ok":
         assert np.array_equal(ia, ib)
+
+
+def _classes(fa, fb, w, h):
+    a, b = port.new_image(w, h), port.new_image(w, h)
+    out = []
+    for fn, im in ((fa, a), (fb, b)):
+        try:
+            fn(im)
+            out.append("ok")
+        except Exception as ex:   # noqa: BLE001
+            out.append(type(ex).__name__)
+    assert out[0] == out[1], out
+    if out[0] == "ok":
+        assert np.array_equal(a, b)
+    return out[0]
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_mutated_pentax(seed):
+    rng = np.random.default_rng(9000 + seed)
+    modern = bool(rng.integers(0, 2))
+    be = bool(rng.integers(0, 2)) if modern else True
+    meta = synth.pentax_modern_meta(be) if modern else None
+    w, h = 2 * int(rng.integers(1, 40)), int(rng.integers(1, 12))
+    img = (synth.image_model(w, h, seed=seed, bits=12) & 0x0FFF).astype(np.uint16)
+    data = np.frombuffer(bytes(synth.make_pentax(img, port.pentax_table(meta, be))), dtype=np.uint8).copy()
+    if modern and rng.integers(0, 2):
+        meta = _mutate(rng, np.frombuffer(bytes(meta), dtype=np.uint8).copy())
+    else:
+        data = _mutate(rng, data)
+    _classes(lambda im: ref.pentax_decompress(im, w, data, meta, be),
+             lambda im: port.pentax_decompress(im, w, data, meta, be), w, h)
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_mutated_nikon(seed):
+    rng = np.random.default_rng(9500 + seed)
+    kind = str(rng.choice(["lossless", "table", "segments", "z7", "skip"]))
+    bits = int(rng.choice([12, 14]))
+    be = bool(rng.integers(0, 2))
+    w, h = 2 * int(rng.integers(1, 40)), int(rng.integers(1, 12))
+    half = 1 << (bits - 1)
+    pup = [half, half + 2, half - 8, half - 2]
+    meta = np.frombuffer(bytes(synth.nikon_meta(kind, bits, (pup[0], pup[2], pup[1], pup[3]), be)), dtype=np.uint8).copy()
+    su = port.nikon_setup(meta, be, bits, w, h)
+    img = (synth.image_model(w, h, seed=seed, bits=bits) & ((1 << bits) - 1)).astype(np.uint16)
+    data = np.frombuffer(bytes(synth.make_nikon(img, su["huff_select"], pup)), dtype=np.uint8).copy()
+    if rng.integers(0, 2):
+        meta = _mutate(rng, meta)
+    else:
+        data = _mutate(rng, data)
+    unc = bool(rng.integers(0, 2))
+    _classes(lambda im: ref.nikon_decompress(im, w, meta, be, bits, data, unc),
+             lambda im: port.nikon_decompress(im, w, meta, be, bits, data, unc), w, h)
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_mutated_cr2(seed):
+    rng = np.random.default_rng(9800 + seed)
+    ncomp = int(rng.choice([2, 4]))
+    nslices = int(rng.integers(0, 3))
+    sw = ncomp * int(rng.integers(2, 10))                   # slice width in samples
+    w = sw * (nslices + 1)
+    h = int(rng.integers(2, 10))
+    slicing = (nslices, sw, sw)
+    img = port.new_image(w, h)
+    img[:, :w] = synth.image_model(w, h, seed, bits=14)
+    two = bool(rng.integers(0, 2))
+    blob = port.cr2_encode(img, w, (ncomp, 1, 1), (w // ncomp, h), slicing, 14,
+                           synth.default_tables(2 if two else 1), [c % 2 if two else 0 for c in range(ncomp)])
+    blob = _mutate(rng, np.ascontiguousarray(blob))
+    _classes(lambda im: ref.cr2_ljpeg_decode(blob, im, w, slicing),
+             lambda im: port.cr2_ljpeg_decode(blob, im, w, slicing), w, h)
