@@ -1,6 +1,8 @@
 #!/usr/bin/env bash
-# First GPU run of the kernels written after round 1's GPU budget was spent (K9 scaling, K10 DNG
-# opcodes, K11 bad pixels, K12 table lookup, Panasonic V4).  One gpurun call:
+# Follow-up GPU run for the kernels written at the end of round 1 (K9 scaling, K10 DNG opcodes,
+# K11 bad pixels, K12 table lookup, Panasonic V4).  They passed their first contact with a B200
+# bit for bit (profiles/r1_postdecode_first_gpu_run.md, tools/quick_validate.py + quick_time.py);
+# what is still owed: their torch-based pytest files, the bench numbers of record, ncu.  One call:
 #
 #   gpurun --timeout 1500 -- 'bash tools/first_gpu_run.sh'
 #
