@@ -4,6 +4,7 @@
 // (fuzz/librawspeed/decompressors/*.cpp), exceptions reported as codes.
 #include "rawspeed_host.h"
 
+#include <chrono>
 #include <cstring>
 
 using namespace rawspeed_b200;
@@ -184,6 +185,64 @@ int rsb200h_dng_decompress(const uint8_t* file, uint64_t file_size, const uint64
       throw;
     }
     std::memcpy(img_data, img->getByteData(), img->getByteSize());
+  });
+}
+
+// The host half of AbstractDngDecompressor::decompress() for LJPEG tiles, alone
+// (AbstractDngDecompressor::prepareLJpeg: per tile LJpegDecoder::prepare() -- marker walk, SOF3 /
+// DHT / SOS validation, restart-marker scan -- then scan descriptors and table de-duplication):
+// everything that happens before rsb200_ljpeg_plan_create.  No GPU involved: a measurement and
+// test hook (best wall ms of `reps`; a digest of the descriptors so that thread counts can be
+// compared); the image is only a shape here.
+int rsb200h_dng_ljpeg_host_half(const uint8_t* file, uint64_t file_size, const uint64_t* tile_off,
+                                const uint32_t* tile_len, int ntiles, int w, int h, int cpp,
+                                int tile_w, int tile_h, int fix_ljpeg, int threads, int reps,
+                                double* best_ms, uint32_t* nscans, uint32_t* ntables,
+                                uint32_t* nerrors, uint64_t* digest, rsb200_ljpeg_scan* scans_out,
+                                uint32_t scans_cap, rsb200h_err* e) {
+  return guarded(e, [&] {
+    const iPoint2D dim(w, h); // (DngTilingDescription keeps a reference to it)
+    RawImage img = RawImage::create(dim, RawImageType::UINT16, (uint32_t)cpp);
+    DngTilingDescription dsc(dim, (uint32_t)tile_w, (uint32_t)tile_h);
+    AbstractDngDecompressor d(img, dsc, 7, fix_ljpeg != 0, 16, 1);
+    const Buffer whole(file, (Buffer::size_type)file_size);
+    d.slices.reserve((size_t)ntiles);
+    for (int n = 0; n < ntiles; ++n)
+      d.slices.emplace_back(d.dsc, (unsigned)n,
+                            ByteStream(whole.getSubView((Buffer::size_type)tile_off[n], tile_len[n]),
+                                       Endianness::little));
+    *best_ms = 1e30;
+    for (int r = 0; r < std::max(1, reps); ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      const AbstractDngDecompressor::PreparedLJpeg pl = d.prepareLJpeg((unsigned)threads);
+      const double ms =
+          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      *best_ms = std::min(*best_ms, ms);
+      *nscans = (uint32_t)pl.scans.size();
+      *ntables = (uint32_t)pl.tables.size();
+      *nerrors = (uint32_t)pl.errors.size();
+      // FNV-1a over the descriptors, the tables and the error texts, in order
+      uint64_t hsh = 1469598103934665603ull;
+      auto mix = [&](const void* p, size_t nb) {
+        const uint8_t* b = static_cast<const uint8_t*>(p);
+        for (size_t i = 0; i < nb; ++i)
+          hsh = (hsh ^ b[i]) * 1099511628211ull;
+      };
+      if (!pl.scans.empty())
+        mix(pl.scans.data(), sizeof(rsb200_ljpeg_scan) * pl.scans.size());
+      if (!pl.tables.empty())
+        mix(pl.tables.data(), sizeof(rsb200_huff_table) * pl.tables.size());
+      for (const std::string& er : pl.errors)
+        mix(er.data(), er.size());
+      for (const auto& t : pl.tiles)
+        mix(&t.firstScan, sizeof t.firstScan);
+      *digest = hsh;
+      // the descriptors themselves (offsets relative to `file`), for comparison in tests
+      for (size_t i = 0; scans_out && i < pl.scans.size() && i < scans_cap; ++i) {
+        scans_out[i] = pl.scans[i];
+        scans_out[i].in_offset += (uint64_t)(pl.base - file);
+      }
+    }
   });
 }
 

@@ -6,6 +6,8 @@
 #include "rawspeed_host.h"
 
 #include <algorithm>
+#include <thread>
+#include <atomic>
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
@@ -2242,52 +2244,114 @@ void AbstractDngDecompressor::decompressUncompressed() const {
   runOnImage(pg.p, base, span, img, /*partial=*/true);
 }
 
-void AbstractDngDecompressor::decompressLJpeg() const {
-  const uint8_t* base;
-  size_t span;
-  tileSpan(slices, &base, &span);
-  struct Tile {
+AbstractDngDecompressor::PreparedLJpeg AbstractDngDecompressor::prepareLJpeg(unsigned threads) const {
+  PreparedLJpeg out;
+  tileSpan(slices, &out.base, &out.span);
+  struct One {
     std::unique_ptr<LJpegDecoder> dec;
-    int firstScan = 0, nScans = 0;
+    bool use = false;
+    std::string err;
+    std::vector<rsb200_huff_table> tables; // this tile's tables and scans (table indices local)
+    std::vector<rsb200_ljpeg_scan> scans;
   };
-  std::vector<Tile> tiles;
-  std::vector<rsb200_huff_table> tables;
-  std::vector<rsb200_ljpeg_scan> scans;
-  for (const auto& e : slices) {
+  std::vector<One> one(slices.size());
+  const uint8_t* const base = out.base;
+  auto work = [&](size_t i) {
+    const DngSliceElement& e = slices[i];
+    One& o = one[i];
     try {
       auto dec = std::make_unique<LJpegDecoder>(e.bs, mRaw);
-      if (!dec->prepare(e.offX, e.offY, e.width, e.height,
-                        iPoint2D((int)e.dsc.tileW, (int)e.dsc.tileH), mFixLjpeg))
-        continue;
-      const size_t before = scans.size();
-      try {
-        dec->scan()->describe(base, tables, scans);
-      } catch (...) {
-        scans.resize(before);
-        throw;
-      }
-      Tile t;
-      t.firstScan = (int)before;
-      t.nScans = (int)(scans.size() - before);
-      t.dec = std::move(dec);
-      tiles.push_back(std::move(t));
+      o.use = dec->prepare(e.offX, e.offY, e.width, e.height,
+                           iPoint2D((int)e.dsc.tileW, (int)e.dsc.tileH), mFixLjpeg);
+      if (o.use) // restart-marker scan (a memchr walk over the tile's entropy data) + descriptors
+        dec->scan()->describe(base, o.tables, o.scans);
+      o.dec = std::move(dec);
     } catch (const RawDecoderException& err) {
-      mRaw->setError(err.what());
+      o.err = err.what();
+      o.scans.clear();
     } catch (const IOException& err) {
-      mRaw->setError(err.what());
+      o.err = err.what();
+      o.scans.clear();
     }
+  };
+  if (threads == 0) {
+    threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* env = std::getenv("RSB200_HOST_THREADS"))
+      threads = (unsigned)std::max(1, std::atoi(env));
   }
-  if (scans.empty())
+  // worth a thread: >= 16 tiles and >= 1 MiB of tile data each
+  threads = (unsigned)std::min<size_t>(threads, std::min((slices.size() + 15) / 16, out.span / (1u << 20) + 1));
+  if (threads <= 1) {
+    for (size_t i = 0; i < slices.size(); ++i)
+      work(i);
+  } else {
+    // tiles are independent (each decoder only reads the image's shape): a shared counter
+    // hands them out; results land in per-tile slots, so the order of the outcome is fixed
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    pool.reserve(threads);
+    for (unsigned t = 0; t < threads; ++t)
+      pool.emplace_back([&] {
+        for (size_t i = next.fetch_add(1); i < slices.size(); i = next.fetch_add(1))
+          work(i);
+      });
+    for (auto& th : pool)
+      th.join();
+  }
+  // merge in tile order: de-duplicate the tables across tiles, re-index the scans
+  {
+    size_t total = 0;
+    for (const One& o : one)
+      total += o.scans.size();
+    out.scans.reserve(total);
+    out.tiles.reserve(slices.size());
+  }
+  for (size_t i = 0; i < slices.size(); ++i) {
+    One& o = one[i];
+    if (!o.err.empty()) {
+      out.errors.push_back(o.err);
+      continue;
+    }
+    if (!o.use)
+      continue;
+    uint8_t remap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    try {
+      for (size_t t = 0; t < o.tables.size() && t < 8; ++t)
+        remap[t] = tableIndex(out.tables, o.tables[t]);
+    } catch (const RawDecoderException& err) { // more than 255 distinct tables in the batch
+      out.errors.emplace_back(err.what());
+      continue;
+    }
+    PreparedLJpeg::Tile t;
+    t.firstScan = (int)out.scans.size();
+    t.nScans = (int)o.scans.size();
+    for (rsb200_ljpeg_scan sc : o.scans) {
+      const size_t ncomp = std::min<size_t>((size_t)sc.mcu_w * sc.mcu_h, sizeof sc.table / sizeof sc.table[0]);
+      for (size_t c = 0; c < ncomp; ++c)
+        sc.table[c] = remap[sc.table[c] & 7];
+      out.scans.push_back(sc);
+    }
+    t.dec = std::move(o.dec);
+    out.tiles.push_back(std::move(t));
+  }
+  return out;
+}
+
+void AbstractDngDecompressor::decompressLJpeg() const {
+  PreparedLJpeg pl = prepareLJpeg();
+  for (const std::string& err : pl.errors)
+    mRaw->setError(err);
+  if (pl.scans.empty())
     return;
   PlanGuard pg;
-  engineCheck(rsb200_ljpeg_plan_create(engine(), tables.data(), (int)tables.size(), scans.data(),
-                                       (int)scans.size(), &pg.p),
+  engineCheck(rsb200_ljpeg_plan_create(engine(), pl.tables.data(), (int)pl.tables.size(),
+                                       pl.scans.data(), (int)pl.scans.size(), &pg.p),
               "rsb200_ljpeg_plan_create");
   RawImage img = mRaw;
-  runOnImage(pg.p, base, span, img, /*partial=*/true);
-  std::vector<rsb200_scan_result> res(scans.size());
+  runOnImage(pg.p, pl.base, pl.span, img, /*partial=*/true);
+  std::vector<rsb200_scan_result> res(pl.scans.size());
   (void)rsb200_plan_results(pg.p, res.data(), (int)res.size());
-  for (auto& t : tiles) {
+  for (auto& t : pl.tiles) {
     try {
       const uint32_t consumed = t.dec->scan()->finish(res.data() + t.firstScan, t.nScans);
       t.dec->decodeSOIAfterScan(consumed);

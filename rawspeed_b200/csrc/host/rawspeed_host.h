@@ -755,6 +755,24 @@ public:
   // all tiles of the frame go to the device in ONE plan (the reference fans them
   // out over OpenMP threads, AbstractDngDecompressor.cpp:54-131,240-252)
   void decompress() const;
+  // The host half of the LJPEG path: per tile the marker walk / validation / restart-marker
+  // scan (LJpegDecoder::prepare, on `threads` host threads: 0 = min(16, hardware threads),
+  // RSB200_HOST_THREADS overrides) and, in tile order, the scan descriptors and de-duplicated
+  // tables the device plan is made of.  Tile errors come back in tile order, as the serial walk
+  // of the reference's single-threaded build reports them.
+  struct PreparedLJpeg {
+    struct Tile {
+      std::unique_ptr<LJpegDecoder> dec;
+      int firstScan = 0, nScans = 0;
+    };
+    std::vector<Tile> tiles;
+    std::vector<rsb200_huff_table> tables;
+    std::vector<rsb200_ljpeg_scan> scans;
+    std::vector<std::string> errors;
+    const uint8_t* base = nullptr; // the file span the scans' offsets refer to
+    size_t span = 0;
+  };
+  PreparedLJpeg prepareLJpeg(unsigned threads = 0) const;
   const DngTilingDescription dsc;
   std::vector<DngSliceElement> slices;
   const int compression;

@@ -32,7 +32,8 @@ EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_sraw_interpolate", "rsb200h_nikon_decompress", "rsb200h_sony_arw2",
            "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white",
            "rsb200h_panasonic_v4", "rsb200h_dng_opcodes", "rsb200h_dngop_lower",
-           "rsb200h_fix_bad_pixels", "rsb200h_sixteen_bit_lookup"]
+           "rsb200h_fix_bad_pixels", "rsb200h_sixteen_bit_lookup",
+           "rsb200h_dng_ljpeg_host_half"]
 
 _lib = None
 
@@ -232,6 +233,34 @@ def sony_arw2(img, w, data, curve=None, dither=False):
     e.check(L.rsb200h_sony_arw2(C.c_void_p(img.ctypes.data), w, img.shape[0], img.shape[1] * 2,
                                 p, C.c_uint32(n), cp, nc, int(dither), C.byref(e)))
     return img
+
+
+def dng_ljpeg_host_half(file_bytes, tile_off, tile_len, w, h, cpp, tile_w, tile_h, fix_ljpeg=False,
+                        threads=0, reps=3, want_scans=False):
+    """AbstractDngDecompressor::prepareLJpeg alone (header walk, validation, restart scan, scan
+    descriptors; no GPU): dict(ms=best wall ms, scans, tables, errors, digest of everything it
+    produced).  threads: 0 = the library's default."""
+    p, n = _u8(file_bytes)
+    offs = (C.c_uint64 * len(tile_off))(*tile_off)
+    lens = (C.c_uint32 * len(tile_len))(*tile_len)
+    ms, ns, nt, ne, dg = C.c_double(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+    e = _Err()
+    L = lib()
+    L.rsb200h_dng_ljpeg_host_half.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                              C.POINTER(C.c_uint32)] + [C.c_int] * 9 + [
+        C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+        C.POINTER(C.c_uint64), C.c_void_p, C.c_uint32, C.POINTER(_Err)]
+    from ._abi import LJpegScan
+    cap = 1 << 18 if want_scans else 0
+    buf = (LJpegScan * cap)() if want_scans else None
+    e.check(L.rsb200h_dng_ljpeg_host_half(p, C.c_uint64(n), offs, lens, len(tile_off), w, h, cpp,
+                                          tile_w, tile_h, int(fix_ljpeg), int(threads), reps,
+                                          C.byref(ms), C.byref(ns), C.byref(nt), C.byref(ne),
+                                          C.byref(dg), buf, cap, C.byref(e)))
+    out = dict(ms=ms.value, scans=ns.value, tables=nt.value, errors=ne.value, digest=dg.value)
+    if want_scans:
+        out["scan_list"] = [buf[i] for i in range(min(ns.value, cap))]
+    return out
 
 
 def sixteen_bit_lookup(img, w, cpp, curve, dither):

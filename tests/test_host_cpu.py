@@ -181,3 +181,66 @@ def test_panasonic_v4_ctor_errors_same_class():
                     lambda: host.panasonic_v4(*args, construct_only=True))
     # a well-formed descriptor constructs (nothing runs)
     host.panasonic_v4(port.new_image(28, 2), 28, data, True, 0x2008, construct_only=True)
+
+
+# ---- AbstractDngDecompressor::prepareLJpeg (the host half of the DNG LJPEG path) ---------------
+
+def _dng(w, h, tile, **kw):
+    img = synth.image_model(w, h, 3)
+    t = synth.make_dng_ljpeg(img, tile, tile, **kw)
+    return t, [int(o) for o in t.offsets], [int(n) for n in t.lengths]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(restart_rows=1), dict(restart_rows=4),
+                                dict(tabs=synth.default_tables(2), tab_of_comp=[0, 1])])
+def test_prepare_ljpeg_is_the_same_on_any_number_of_threads(kw):
+    w, h, tile = 1024, 768, 64
+    t, offs, lens = _dng(w, h, tile, **kw)
+    runs = [host.dng_ljpeg_host_half(t.blob, offs, lens, w, h, 1, tile, tile, False, th, 1) for th in (1, 2, 5, 16, 0)]
+    assert len({r["digest"] for r in runs}) == 1
+    assert runs[0]["errors"] == 0 and runs[0]["tables"] == len(kw.get("tabs", [0]))
+    rows = kw.get("restart_rows", 0)
+    per_tile = 1 if not rows else -(-tile // rows)
+    assert runs[0]["scans"] == len(offs) * per_tile
+
+
+def test_prepare_ljpeg_reports_tile_errors_in_tile_order_on_any_number_of_threads():
+    w, h, tile = 1024, 768, 64
+    t, offs, lens = _dng(w, h, tile, restart_rows=2)
+    blob = t.blob.copy()
+    rng = np.random.default_rng(4)
+    bad = sorted(rng.choice(len(offs), 9, replace=False).tolist())
+    for k, i in enumerate(bad):
+        o = offs[i]
+        if k % 3 == 0:
+            blob[o + 3] = 0x00                     # SOF marker destroyed
+        elif k % 3 == 1:
+            blob[o + lens[i] // 2:o + lens[i]] = 0  # restart markers gone: "Jpeg marker not encountered"
+        else:
+            lens[i] = 20                            # tile cut inside its headers
+    runs = [host.dng_ljpeg_host_half(blob, offs, lens, w, h, 1, tile, tile, False, th, 1) for th in (1, 3, 16)]
+    assert len({r["digest"] for r in runs}) == 1    # the digest covers the error texts, in order
+    assert runs[0]["errors"] == len(bad)
+    assert runs[0]["scans"] == (len(offs) - len(bad)) * (tile // 2)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(restart_rows=2), dict(tabs=synth.default_tables(2), tab_of_comp=[0, 1]),
+                                dict(ncomp=4, restart_rows=8)])
+def test_prepare_ljpeg_descriptors_equal_the_test_suite_s_own_scan_builder(kw):
+    """The C++ host half against tests/helpers.dng_ljpeg_scans (the Python builder every GPU
+    parity test of the C ABI feeds the device with): same scans, field by field."""
+    from helpers import dng_ljpeg_scans
+    w, h, tile = 520, 300, 64            # ragged right and bottom tiles
+    t, offs, lens = _dng(w, h, tile, **kw)
+    pitch = port.image_pitch(w)
+    tabs, want = dng_ljpeg_scans(t, pitch)
+    got = host.dng_ljpeg_host_half(t.blob, offs, lens, w, h, 1, tile, tile, False, 3, 1, want_scans=True)
+    assert got["errors"] == 0 and got["scans"] == len(want) and got["tables"] == len(tabs.tabs)
+    for a, b in zip(got["scan_list"], want):
+        ncomp = b.mcu_w * b.mcu_h
+        assert (a.in_offset, a.in_size, a.rows, a.frame_w, a.mcu_w, a.mcu_h) == \
+               (b.in_offset, b.in_size, b.rows, b.frame_w, b.mcu_w, b.mcu_h)
+        assert list(a.table)[:ncomp] == list(b.table)[:ncomp]
+        assert list(a.init_pred)[:ncomp] == list(b.init_pred)[:ncomp]
+        assert (a.out_offset, a.out_pitch, a.out_x, a.out_y, a.store_w) == \
+               (b.out_offset, b.out_pitch, b.out_x, b.out_y, b.store_w)
