@@ -555,6 +555,8 @@ def encode_diffs_plain(diffs, ht):
     out = np.empty(cap, dtype=np.uint8)
     L = lib()
     L.rso_encode_diffs_plain.restype = C.c_int64
+    # (the handle is a pointer: without argtypes ctypes would pass a Python int as a C int)
+    L.rso_encode_diffs_plain.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
     n = L.rso_encode_diffs_plain(d.ctypes.data_as(C.c_void_p), C.c_uint64(d.size), ht.h,
                                  out.ctypes.data_as(C.c_void_p), C.c_uint64(cap))
     if n < 0:
