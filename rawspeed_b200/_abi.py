@@ -213,6 +213,14 @@ def load():
     L.rsb200_plan_run_host_image.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, C.c_uint32,
                                              C.c_uint32, i32]
     L.rsb200_plan_results.argtypes = [vp, C.POINTER(ScanResult), i32]
+    u32p = C.POINTER(C.c_uint32)
+    L.rsb200_scale_plan_create.argtypes = [vp, C.POINTER(ScaleJob), i32, C.POINTER(vp)]
+    L.rsb200_lookup_plan_create.argtypes = [vp, C.POINTER(LookupJob), i32, C.POINTER(C.c_uint16), i32, i32,
+                                            C.POINTER(vp)]
+    L.rsb200_dngop_plan_create.argtypes = [vp, C.POINTER(DngOpJob), i32, C.POINTER(DngOp), i32,
+                                           C.POINTER(C.c_uint16), i32, u32p, i32, C.POINTER(vp)]
+    L.rsb200_badpix_plan_create.argtypes = [vp, C.POINTER(BadPixJob), i32, u32p, C.c_uint32, C.POINTER(vp)]
+    L.rsb200_plan_bad_pixels.argtypes = [vp, i32, u32p, C.c_uint32, u32p]
     L.rsb200_plan_bytes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.rsb200_plan_launches.argtypes = [vp]
     L.rsb200_plan_destroy.argtypes = [vp]
