@@ -840,7 +840,10 @@ def bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak):
     base = port.new_image(W, H)
     base[:, :] = rng.integers(0, 16384, size=base.shape, dtype=np.uint16)
 
-    def leg(name, plan, want, kernel, restore=True):
+    rank0 = int(os.environ.get("RANK", "0")) == 0
+    ncores = os.cpu_count() or 1
+
+    def leg(name, plan, want, kernel, restore=True, cpu=None, cpu_threads=None):
         d = torch.from_numpy(base.view(np.int16).copy()).cuda()
         src = d.clone()
         plan.run(None, d)
@@ -859,6 +862,16 @@ def bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak):
                      "achieved_GBps": (in_b + out_b) / (per * 1e-3) / 1e9,
                      "roofline_frac": (in_b + out_b) / (per * 1e-3) / 1e9 / peak, "kernel": kernel,
                      "timing": "in-place kernel + restoring copy, minus the copy alone"}
+        if cpu is not None and not args.skip_cpu and rank0:
+            import oracle
+            if oracle.HAVE_REF:
+                best = 1e30
+                for _ in range(3):
+                    cpu(base.copy())
+                    best = min(best, oracle.ref.last_ms())
+                out[name]["cpu_reference"] = {"kind": "reference", "cores": cpu_threads or ncores,
+                                              "MPixels/s": W * H / (best * 1e-3) / 1e6, "ms": best,
+                                              "sample": "the reference's own member on 1 frame, best of 3 (driver copies excluded)"}
 
     # K9: black / white scaling, both loops
     for label, black, white in (("SSE2 loop", (1008, 1010, 1009, 1011), 16383), ("plain loop", (64,) * 4, 1000)):
@@ -871,7 +884,9 @@ def bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak):
         want = base.copy()
         port.scale_values(want, W, (8, 8, W - 16, H - 16), black, white)
         leg("8(f)3 scaleBlackWhite 8256x5504 (%s, dither)" % label, rs.scale_plan(ctx, [j]), want,
-            "scale_kernel<%d>" % (0 if "SSE2" in label else 1))
+            "scale_kernel<%d>" % (0 if "SSE2" in label else 1),
+            cpu=lambda im, black=black, white=white: __import__("oracle").ref.scale_values(
+                im, W, (8, 8, W - 16, H - 16), black, white, nthreads=ncores))
     # K12: whole-image table lookup, Sony curve, plain and dithered
     for dither in (False, True):
         lj = rs.LookupJob()
@@ -880,7 +895,9 @@ def bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak):
         want = base.copy()
         port.sixteen_bit_lookup(want, W, 1, t, dither)
         leg("8(f)3 sixteenBitLookup 8256x5504 (%s)" % ("dithered" if dither else "plain"),
-            rs.lookup_plan(ctx, [lj], t, dither), want, "lookup_kernel<%s>" % ("true" if dither else "false"))
+            rs.lookup_plan(ctx, [lj], t, dither), want, "lookup_kernel<%s>" % ("true" if dither else "false"),
+            cpu=lambda im, dither=dither: __import__("oracle").ref.sixteen_bit_lookup(
+                im, W, 1, [0, 0, W, H], synth.sony_curve(), dither, nthreads=ncores))
     # K10: eight opcodes in one pass
     from rawspeed_b200 import host
     area = synth.dng_pixel_area((0, 0, H, W))
@@ -900,7 +917,8 @@ def bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak):
     want = base.copy()
     port.dng_opcodes(want, W, 1, [0, 0, W, H], blob)
     leg("8(f)3 DngOpcodes 8256x5504, 8 opcodes in one pass", rs.dngop_plan(ctx, [dj], low["ops"], low["tables"], low["deltas"]),
-        want, "dngop_kernel")
+        want, "dngop_kernel", cpu=lambda im: __import__("oracle").ref.dng_opcodes(im, W, 1, [0, 0, W, H], blob),
+        cpu_threads=1)   # applyOpCodes is single threaded in the reference
     # K11: 20 000 defects
     n = 20000
     p = ((rng.integers(0, H, n).astype(np.uint32) << 16) | rng.integers(0, W, n).astype(np.uint32))
@@ -910,7 +928,8 @@ def bench_unvalidated(torch, rs, ctx, port, synth, args, dist, peak):
     want = base.copy()
     port.fix_bad_pixels(want, W, 1, p, True)
     leg("8(f)3 fixBadPixels 8256x5504, 20000 defects", rs.badpix_plan(ctx, [bj], p), want, "badpix_kernel",
-        restore=False)     # idempotent: good pixels are never written
+        restore=False,     # idempotent: good pixels are never written
+        cpu=lambda im: __import__("oracle").ref.fix_bad_pixels(im, W, 1, p, True, nthreads=ncores))
     # Panasonic V4, 4592x3448-class frames, 4 per launch
     w, h, split = 4592 // 14 * 14, 3448, 0x2008
     nbytes = (w * h // 14 * 16 + 0x3FFF) // 0x4000 * 0x4000

@@ -283,6 +283,14 @@ def panasonic(version, img, w, data, bps=14, nthreads=1, reps=1):
     return ms.value
 
 
+def last_ms():
+    """Wall ms of the reference call inside the last post-decode driver (scale_values,
+    scale_black_white, sixteen_bit_lookup, fix_bad_pixels, dng_opcodes); driver copies excluded."""
+    L = lib()
+    L.ref_last_ms.restype = C.c_double
+    return float(L.ref_last_ms())
+
+
 def dng_opcodes(img, w, cpp, crop, data, cap=1 << 20):
     """Reference DngOpcodes(ri, data) + applyOpCodes(ri) (ref_dng_opcodes); img: uint16 image or
     uint32 array holding an F32 image.  Returns (crop, mBadPixelPositions); `dng_opcodes.stage`

@@ -104,6 +104,17 @@ template <typename F> int guarded(RefErr* e, F&& f) {
   }
 }
 
+// wall time of the reference call inside the last post-decode driver (ref_scale_values,
+// ref_scale_black_white, ref_sixteen_bit_lookup, ref_fix_bad_pixels, ref_dng_opcodes), copies
+// in and out of the driver's image excluded
+double g_last_ms = 0.0;
+struct StageTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~StageTimer() {
+    g_last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+
 RawImage makeImage(int w, int h, int cpp, bool isCfa, int subX, int subY) {
   RawImage img = RawImage::create(iPoint2D(w, h), RawImageType::UINT16, cpp);
   img->isCFA = isCfa;
@@ -151,6 +162,9 @@ void pumpGet(const uint8_t* data, int size, const int* lens, int n,
 } // namespace
 
 extern "C" {
+
+double ref_last_ms(void) { return g_last_ms; }
+
 
 int ref_image_pitch(int w, int h, int cpp) {
   RawImage img = RawImage::create(iPoint2D(w, h), RawImageType::UINT16, cpp);
@@ -350,7 +364,10 @@ int ref_scale_values(uint16_t* img_data, int w, int h, int pitch, int off_x, int
       img->blackLevelSeparateStorage[i] = black_sep[i];
     img->whitePoint = white;
     img->mDitherScale = dither != 0;
-    img->scaleBlackWhite();
+    {
+      StageTimer tm;
+      img->scaleBlackWhite();
+    }
     // copy out the whole uncropped buffer
     const auto a = img->getU16DataAsUncroppedArray2DRef();
     for (int r = 0; r < a.height(); ++r)
@@ -381,7 +398,10 @@ int ref_scale_black_white(uint16_t* img_data, int w, int h, int cpp, int pitch, 
     for (int i = 0; i < n_areas; ++i)
       img->blackAreas.emplace_back(areas[3 * i + 1], areas[3 * i + 2], areas[3 * i] != 0);
     img->mDitherScale = dither != 0;
-    img->scaleBlackWhite();
+    {
+      StageTimer tm;
+      img->scaleBlackWhite();
+    }
     copyOut(img, img_data, pitch);
     *sep_set = img->blackLevelSeparate.has_value();
     if (img->blackLevelSeparate)
@@ -423,6 +443,7 @@ int ref_dng_opcodes(void* img_data, int is_f32, int w, int h, int cpp, int pitch
     DngOpcodes codes(img, ByteStream(DataBuffer(Buffer(data, size), Endianness::little)));
     *stage = 2;
     try {
+      StageTimer tm;
       codes.applyOpCodes(img);
     } catch (...) {
       copyBack();
@@ -444,7 +465,10 @@ int ref_sixteen_bit_lookup(uint16_t* img_data, int w, int h, int cpp, int pitch,
       img->subFrame(iRectangle2D(iPoint2D(crop[0], crop[1]), iPoint2D(crop[2], crop[3])));
     if (curve)
       img->setTable(std::vector<uint16_t>(curve, curve + ncurve), dither != 0);
-    img->sixteenBitLookup();
+    {
+      StageTimer tm;
+      img->sixteenBitLookup();
+    }
     copyOut(img, img_data, pitch);
   });
 }
@@ -457,7 +481,10 @@ int ref_fix_bad_pixels(uint16_t* img_data, int w, int h, int cpp, int pitch, int
     RawImage img = makeImage(w, h, cpp, is_cfa != 0, 1, 1);
     copyIn(img, img_data, pitch);
     img->mBadPixelPositions.assign(positions, positions + n);
-    img->fixBadPixels();
+    {
+      StageTimer tm;
+      img->fixBadPixels();
+    }
     copyOut(img, img_data, pitch);
   });
 }
