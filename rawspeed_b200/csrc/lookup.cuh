@@ -68,4 +68,60 @@ __global__ void __launch_bounds__(LUT_NT)
   }
 }
 
+// ---- A/B candidate (RSB200_LUT_SMEM=1; plain lookup, plans with ONE table) -------------------
+// The first GPU run put the plain lookup at 0.100 ms per 45 MP frame against 0.055 ms for a
+// copy of the same bytes: the random 2-byte table reads go through L1 one sector per lane.
+// Here the 128 KB table is staged once per CTA in shared memory (opt-in dynamic size) and the
+// CTAs are persistent (one per SM, 32 warps), walking the row quads with a grid stride.  Same
+// per-lane arithmetic (lut_group<false>), not yet run on a GPU, hence not the default.
+constexpr int LUT_SMEM_NT = 1024;
+constexpr int LUT_SMEM_BYTES = 65536 * 2;
+
+__global__ void __launch_bounds__(LUT_SMEM_NT, 1)
+    lookup_smem_kernel(uint8_t* __restrict__ img, const LookupJobDev* __restrict__ jobs, int njobs,
+                       uint32_t total_quads, const uint16_t* __restrict__ tables) {
+  extern __shared__ __align__(16) uint8_t s_lut_raw[];
+  uint16_t* const s_table = reinterpret_cast<uint16_t*>(s_lut_raw);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(tables);
+    uint4* dst = reinterpret_cast<uint4*>(s_lut_raw);
+    for (uint32_t i = threadIdx.x; i < LUT_SMEM_BYTES / 16; i += LUT_SMEM_NT)
+      dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t warps_per_cta = LUT_SMEM_NT / 32;
+  for (uint32_t quad = blockIdx.x * warps_per_cta + warp; quad < total_quads;
+       quad += gridDim.x * warps_per_cta) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].quad_begin <= quad)
+        lo = mid;
+      else
+        hi = mid - 1;
+    }
+    const LookupJobDev j = jobs[lo];
+    const uint32_t y0 = (quad - j.quad_begin) * SCALE_ROWS;
+    uint8_t* const base = img + j.offset + (uint64_t)y0 * j.pitch;
+    const uint32_t iters = (j.ngroups + 31) / 32;
+    uint32_t unused = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+      const uint32_t g = it * 32 + lane;
+      if (g < j.ngroups) {
+        ScaleVec v[SCALE_ROWS];
+#pragma unroll
+        for (int r = 0; r < SCALE_ROWS; ++r)
+          if (y0 + r < j.height)
+            v[r] = scale_ld(base + (uint64_t)r * j.pitch + (uint64_t)g * 16);
+#pragma unroll
+        for (int r = 0; r < SCALE_ROWS; ++r)
+          if (y0 + r < j.height)
+            scale_st(base + (uint64_t)r * j.pitch + (uint64_t)g * 16,
+                     lut_group<false>(v[r], s_table, j.ncols, 8u * g, unused));
+      }
+    }
+  }
+}
+
 } // namespace rsb200

@@ -153,6 +153,7 @@ struct rsb200_plan {
   int lookup_njobs = 0;
   uint32_t lookup_quads = 0;
   bool lookup_dither = false;
+  int lookup_ntables = 0;
   // bad-pixel interpolation (K11)
   BadPixJobDev* d_badpix_jobs = nullptr;
   uint32_t* d_badpix_list = nullptr;
@@ -578,6 +579,7 @@ extern "C" int rsb200_lookup_plan_create(rsb200_ctx* ctx, const rsb200_lookup_jo
   p->kind = 10;
   p->nunits = njobs;
   p->lookup_dither = dither != 0;
+  p->lookup_ntables = ntables;
   std::vector<LookupJobDev> hj((size_t)njobs);
   uint64_t quads = 0;
   for (int i = 0; i < njobs; ++i) {
@@ -1899,7 +1901,15 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
     }
   } else if (p->kind == 10) {
     const uint32_t nb = (p->lookup_quads + LUT_WARPS - 1) / LUT_WARPS;
-    if (p->lookup_dither)
+    const char* smem_env = getenv("RSB200_LUT_SMEM"); // A/B candidate, see lookup.cuh
+    if (smem_env && smem_env[0] == '1' && !p->lookup_dither && p->lookup_ntables == 1) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(lookup_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         LUT_SMEM_BYTES));
+      int sms = 0;
+      CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      lookup_smem_kernel<<<(unsigned)std::max(1, sms), LUT_SMEM_NT, LUT_SMEM_BYTES, st>>>(
+          outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads, p->d_lookup_tables);
+    } else if (p->lookup_dither)
       lookup_kernel<true><<<nb, LUT_NT, 0, st>>>(outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads,
                                                  p->d_lookup_tables);
     else

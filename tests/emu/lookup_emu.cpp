@@ -69,6 +69,44 @@ extern "C" int lookup_emu_run(uint8_t* img, const rsb200_lookup_job* jobs, int n
   return 0;
 }
 
+// the RSB200_LUT_SMEM=1 candidate (lookup_smem_kernel): persistent CTAs of 32 warps walking the
+// quads with a grid stride, table staged once (here: used in place); plain lookup, one table
+extern "C" int lookup_emu_run_smem(uint8_t* img, const rsb200_lookup_job* jobs, int njobs,
+                                   const uint16_t* tables, int grid, char* err, int errlen) {
+  std::vector<LookupJobDev> hj((size_t)njobs);
+  uint64_t quads = 0;
+  for (int i = 0; i < njobs; ++i) {
+    if (const char* why = lookup_build_job(jobs[i], 1, (uint32_t)quads, &hj[i])) {
+      std::strncpy(err, why, (size_t)errlen - 1);
+      err[errlen - 1] = 0;
+      return -1;
+    }
+    quads += lookup_job_quads(jobs[i]);
+  }
+  const uint32_t warps_per_cta = 32;
+  std::vector<char> seen((size_t)quads, 0);
+  for (int block = 0; block < grid; ++block)
+    for (uint32_t warp = 0; warp < warps_per_cta; ++warp)
+      for (uint32_t quad = (uint32_t)block * warps_per_cta + warp; quad < (uint32_t)quads;
+           quad += (uint32_t)grid * warps_per_cta) {
+        if (seen[quad]++)
+          return -2; // a quad visited twice would be looked up twice
+        int lo = 0, hi = njobs - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (hj[mid].quad_begin <= quad)
+            lo = mid;
+          else
+            hi = mid - 1;
+        }
+        replay_quad<false>(img, hj[lo], quad, tables);
+      }
+  for (char c : seen)
+    if (!c)
+      return -3;
+  return 0;
+}
+
 extern "C" uint32_t lookup_emu_mwc_direct(uint32_t width, uint32_t y, uint32_t x) {
   uint32_t v = (width + y * 13u) ^ 0x45694584u;
   while (x--)

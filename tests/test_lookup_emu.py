@@ -28,6 +28,8 @@ def emu():
     lib = C.CDLL(OUT)
     lib.lookup_emu_run.argtypes = [C.c_void_p, C.POINTER(LookupJob), C.c_int, C.c_void_p, C.c_int, C.c_int,
                                    C.c_char_p, C.c_int]
+    lib.lookup_emu_run_smem.argtypes = [C.c_void_p, C.POINTER(LookupJob), C.c_int, C.c_void_p, C.c_int,
+                                        C.c_char_p, C.c_int]
     lib.lookup_emu_mwc_direct.argtypes = lib.lookup_emu_mwc_state.argtypes = [C.c_uint32] * 3
     lib.lookup_emu_mwc_direct.restype = lib.lookup_emu_mwc_state.restype = C.c_uint32
     return lib
@@ -82,3 +84,26 @@ def test_jump_ahead_equals_stepping(emu):
     for w, y in [(8256, 0), (8256, 5503), (40, 3669), (47739, 0), (0xBA7B - 13 * 7, 7), (65535, 65535)]:
         for x in [0, 1, 2, 7, 8, 248, 249, 1000, 24767]:
             assert emu.lookup_emu_mwc_state(w, y, x) == emu.lookup_emu_mwc_direct(w, y, x)
+
+
+@pytest.mark.parametrize("grid", [1, 3, 148])
+def test_persistent_grid_variant_covers_every_quad_once(emu, grid):
+    """The RSB200_LUT_SMEM=1 candidate (lookup_smem_kernel): grid-stride walk of the quads."""
+    specs = [(2100, 7, 1), (300, 9, 3), (64, 130, 1)]
+    imgs = [image(w, h, cpp, 60 + i) for i, (w, h, cpp) in enumerate(specs)]
+    t = port.build_table(curve(4096, 3), False)
+    sizes = [(im.nbytes + 255) // 256 * 256 for im in imgs]
+    buf = np.zeros(sum(sizes), dtype=np.uint8)
+    jobs, o = [], 0
+    for im, sz, (w, h, cpp) in zip(imgs, sizes, specs):
+        buf[o:o + im.nbytes] = im.reshape(-1).view(np.uint8)
+        jobs.append(job(o, im, w, cpp, 0))
+        o += sz
+    err = C.create_string_buffer(256)
+    assert emu.lookup_emu_run_smem(buf.ctypes.data, (LookupJob * 3)(*jobs), 3, t.ctypes.data, grid, err, 256) == 0
+    o = 0
+    for im, sz, (w, h, cpp) in zip(imgs, sizes, specs):
+        want = im.copy()
+        port.sixteen_bit_lookup(want, w, cpp, t, False)
+        assert np.array_equal(buf[o:o + im.nbytes].view(np.uint16).reshape(im.shape), want)
+        o += sz

@@ -42,6 +42,10 @@ if [ -f tools/_ab/dngop_v2.so ]; then
   RSB200_LIB=tools/_ab/dngop_v2.so python tools/quick_time.py > "$OUT/quick_time_v2.log" 2>&1
   grep "K10" "$OUT/quick_time_v2.log" | sed 's/^/DNGOP_V2 /' | tee -a "$OUT/summary.txt"
 fi
+# A/B of the shared-memory-table lookup (run-time switch, same library)
+RSB200_LUT_SMEM=1 python tools/quick_time.py > "$OUT/quick_time_lut_smem.log" 2>&1
+grep "K12 sixteenBitLookup, plain" "$OUT/quick_time_v1.log" | sed 's/^/shipped   /' | tee -a "$OUT/summary.txt"
+grep "K12 sixteenBitLookup, plain" "$OUT/quick_time_lut_smem.log" | sed 's/^/LUT_SMEM  /' | tee -a "$OUT/summary.txt"
 if command -v ncu > /dev/null; then
   for k in scale_kernel lookup_kernel dngop_kernel badpix_kernel "pana_kernel<4"; do
     f=$(echo "$k" | tr -cd 'a-z0-9_')
