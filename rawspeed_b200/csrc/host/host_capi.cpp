@@ -199,7 +199,8 @@ int rsb200h_dng_ljpeg_host_half(const uint8_t* file, uint64_t file_size, const u
                                 int tile_w, int tile_h, int fix_ljpeg, int threads, int reps,
                                 double* best_ms, uint32_t* nscans, uint32_t* ntables,
                                 uint32_t* nerrors, uint64_t* digest, rsb200_ljpeg_scan* scans_out,
-                                uint32_t scans_cap, rsb200h_err* e) {
+                                uint32_t scans_cap, char* first_error, int first_error_cap,
+                                rsb200h_err* e) {
   return guarded(e, [&] {
     const iPoint2D dim(w, h); // (DngTilingDescription keeps a reference to it)
     RawImage img = RawImage::create(dim, RawImageType::UINT16, (uint32_t)cpp);
@@ -237,6 +238,14 @@ int rsb200h_dng_ljpeg_host_half(const uint8_t* file, uint64_t file_size, const u
       for (const auto& t : pl.tiles)
         mix(&t.firstScan, sizeof t.firstScan);
       *digest = hsh;
+      if (first_error && first_error_cap > 0) {
+        first_error[0] = 0;
+        if (!pl.errors.empty()) { // "IOE: ..." / "RDE: ..."
+          const std::string tagged = std::string(pl.errorIsIOE[0] ? "IOE: " : "RDE: ") + pl.errors[0];
+          std::strncpy(first_error, tagged.c_str(), (size_t)first_error_cap - 1);
+          first_error[first_error_cap - 1] = 0;
+        }
+      }
       // the descriptors themselves (offsets relative to `file`), for comparison in tests
       for (size_t i = 0; scans_out && i < pl.scans.size() && i < scans_cap; ++i) {
         scans_out[i] = pl.scans[i];

@@ -2250,6 +2250,7 @@ AbstractDngDecompressor::PreparedLJpeg AbstractDngDecompressor::prepareLJpeg(uns
   struct One {
     std::unique_ptr<LJpegDecoder> dec;
     bool use = false;
+    bool ioe = false;
     std::string err;
     std::vector<rsb200_huff_table> tables; // this tile's tables and scans (table indices local)
     std::vector<rsb200_ljpeg_scan> scans;
@@ -2271,6 +2272,7 @@ AbstractDngDecompressor::PreparedLJpeg AbstractDngDecompressor::prepareLJpeg(uns
       o.scans.clear();
     } catch (const IOException& err) {
       o.err = err.what();
+      o.ioe = true;
       o.scans.clear();
     }
   };
@@ -2310,6 +2312,7 @@ AbstractDngDecompressor::PreparedLJpeg AbstractDngDecompressor::prepareLJpeg(uns
     One& o = one[i];
     if (!o.err.empty()) {
       out.errors.push_back(o.err);
+      out.errorIsIOE.push_back(o.ioe ? 1 : 0);
       continue;
     }
     if (!o.use)
@@ -2320,6 +2323,7 @@ AbstractDngDecompressor::PreparedLJpeg AbstractDngDecompressor::prepareLJpeg(uns
         remap[t] = tableIndex(out.tables, o.tables[t]);
     } catch (const RawDecoderException& err) { // more than 255 distinct tables in the batch
       out.errors.emplace_back(err.what());
+      out.errorIsIOE.push_back(0);
       continue;
     }
     PreparedLJpeg::Tile t;

@@ -769,6 +769,7 @@ public:
     std::vector<rsb200_huff_table> tables;
     std::vector<rsb200_ljpeg_scan> scans;
     std::vector<std::string> errors;
+    std::vector<uint8_t> errorIsIOE; // per entry of `errors`: IOException (1) or RawDecoderException (0)
     const uint8_t* base = nullptr; // the file span the scans' offsets refer to
     size_t span = 0;
   };

@@ -249,15 +249,17 @@ def dng_ljpeg_host_half(file_bytes, tile_off, tile_len, w, h, cpp, tile_w, tile_
     L.rsb200h_dng_ljpeg_host_half.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64),
                                               C.POINTER(C.c_uint32)] + [C.c_int] * 9 + [
         C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
-        C.POINTER(C.c_uint64), C.c_void_p, C.c_uint32, C.POINTER(_Err)]
+        C.POINTER(C.c_uint64), C.c_void_p, C.c_uint32, C.c_char_p, C.c_int, C.POINTER(_Err)]
     from ._abi import LJpegScan
+    first = C.create_string_buffer(512)
     cap = 1 << 18 if want_scans else 0
     buf = (LJpegScan * cap)() if want_scans else None
     e.check(L.rsb200h_dng_ljpeg_host_half(p, C.c_uint64(n), offs, lens, len(tile_off), w, h, cpp,
                                           tile_w, tile_h, int(fix_ljpeg), int(threads), reps,
                                           C.byref(ms), C.byref(ns), C.byref(nt), C.byref(ne),
-                                          C.byref(dg), buf, cap, C.byref(e)))
-    out = dict(ms=ms.value, scans=ns.value, tables=nt.value, errors=ne.value, digest=dg.value)
+                                          C.byref(dg), buf, cap, first, 512, C.byref(e)))
+    out = dict(ms=ms.value, scans=ns.value, tables=nt.value, errors=ne.value, digest=dg.value,
+               first_error=first.value.decode("utf-8", "replace"))
     if want_scans:
         out["scan_list"] = [buf[i] for i in range(min(ns.value, cap))]
     return out

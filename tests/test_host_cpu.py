@@ -244,3 +244,39 @@ def test_prepare_ljpeg_descriptors_equal_the_test_suite_s_own_scan_builder(kw):
         assert list(a.init_pred)[:ncomp] == list(b.init_pred)[:ncomp]
         assert (a.out_offset, a.out_pitch, a.out_x, a.out_y, a.store_w) == \
                (b.out_offset, b.out_pitch, b.out_x, b.out_y, b.store_w)
+
+
+@pytest.mark.parametrize("seed", range(200))
+def test_host_half_against_the_oracle_on_mutated_tiles(seed):
+    """What the mirror decides about a tile BEFORE anything reaches the device, against the
+    oracle's verdict on the whole tile (byte-mutated LJPEG tiles as in
+    tests/test_oracle_mutation_fuzz.py): a tile the oracle decodes is never refused; a tile the
+    host half refuses fails in the oracle too, with the same exception class -- except for the
+    documented deviation: restart markers are validated up front, so a tile whose entropy data
+    is ALSO corrupt before a bad marker reports the marker (known deviations)."""
+    from test_oracle_mutation_fuzz import _mutate
+    rng = np.random.default_rng(7000 + seed)
+    ncomp = int(rng.choice([1, 2, 3, 4]))
+    tw, th = 8 * ncomp * int(rng.integers(1, 5)), int(rng.integers(2, 12))
+    img = synth.image_model(tw, th, seed, bits=14)
+    two = ncomp >= 2 and bool(rng.integers(0, 2))
+    t = synth.make_dng_ljpeg(img, tw, th, ncomp=ncomp, tabs=synth.default_tables(2 if two else 1),
+                             tab_of_comp=[c % 2 if two else 0 for c in range(ncomp)],
+                             restart_rows=int(rng.choice([0, 0, 1, 2])))
+    blob = _mutate(rng, t.blob)
+    try:
+        port.ljpeg_decode(blob, port.new_image(tw, th), tw, 1, (0, 0), (tw, th), (tw, th))
+        want = "ok"
+    except port.IOException:
+        want = "IOE"
+    except port.RawDecoderException:
+        want = "RDE"
+    r = host.dng_ljpeg_host_half(blob, [0], [blob.size], tw, th, 1, tw, th, False, 1, 1)
+    if want == "ok":
+        assert r["errors"] == 0, r["first_error"]
+    if r["errors"]:
+        assert want != "ok"
+        marker_first = any(m in r["first_error"] for m in ("Not a restart marker!", "Jpeg marker not encountered",
+                                                           "Unexpected restart marker found"))
+        if not marker_first:
+            assert r["first_error"].startswith(want + ": "), (want, r["first_error"])
