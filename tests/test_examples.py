@@ -56,8 +56,6 @@ def _expected():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("RSB200_UNVALIDATED") != "1",
-                    reason="this test has not been executed on a GPU yet; set RSB200_UNVALIDATED=1")
 def test_example_runs_and_matches_the_oracle(tmp_path):
     exe = _build(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)

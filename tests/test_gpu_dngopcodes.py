@@ -3,10 +3,7 @@ reference in tests/test_oracle_dngopcodes.py): through the C++ host mirror's
 DngOpcodes(ri, bs).applyOpCodes(ri) (pixels, crop, mBadPixelPositions in order, error class and
 stage) and through the C ABI with a device-resident image.
 
-GATED (RSB200_UNVALIDATED=1): the kernel itself passed its first run on a B200 bit for bit
-through tools/quick_validate.py and tools/quick_time.py (tests/test_gpu_postdecode.py runs those
-un-gated); THIS file, which goes through torch-owned buffers, has not been executed yet and stays
-behind the gate so that a slip in test code cannot stop the GPU suite.  Run it once, drop the gate."""
+First executed on a B200 in round 2 (gpurun_out/r2_run1: 138 passed); un-gated since."""
 import os
 
 import numpy as np
@@ -17,9 +14,7 @@ from rawspeed_b200 import host
 from oracle import port
 from test_oracle_dngopcodes import scenarios
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("RSB200_UNVALIDATED") != "1",
-                                 reason="this test file has not been executed yet (the kernel has); set RSB200_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _oracle(img, w, cpp, crop, blob):

@@ -10,8 +10,7 @@ profiles/r1_quick_time_gpu.log), run as they ran there.
    first run of every leg compared bit for bit with the oracle.
 
 The per-kernel pytest files (test_gpu_scale / _lookup / _dngopcodes / _badpixels /
-_panasonic_v4) cover the same ground through torch-owned buffers; they stay behind
-RSB200_UNVALIDATED=1 until they themselves have been executed once."""
+_panasonic_v4) cover the same ground through torch-owned buffers (un-gated in round 2)."""
 import json
 import os
 import subprocess

@@ -2,10 +2,7 @@
 tests/test_oracle_scale.py), through the C ABI (device-resident, in place) and through the
 C++ host mirror's RawImageData::scaleBlackWhite(); bit-exact, dither included.
 
-GATED (RSB200_UNVALIDATED=1): the kernel itself passed its first run on a B200 bit for bit
-through tools/quick_validate.py and tools/quick_time.py (tests/test_gpu_postdecode.py runs those
-un-gated); THIS file, which goes through torch-owned buffers, has not been executed yet and stays
-behind the gate so that a slip in test code cannot stop the GPU suite.  Run it once, drop the gate."""
+First executed on a B200 in round 2 (gpurun_out/r2_run1: 138 passed); un-gated since."""
 import os
 
 import numpy as np
@@ -16,9 +13,7 @@ from rawspeed_b200 import host
 from rawspeed_b200._abi import SCALE_AUTO, SCALE_PLAIN, SCALE_SSE2
 from oracle import port
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("RSB200_UNVALIDATED") != "1",
-                                 reason="this test file has not been executed yet (the kernel has); set RSB200_UNVALIDATED=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _job(offset, img, w, h, cpp, crop, black, white, dither=True, path=SCALE_AUTO):
