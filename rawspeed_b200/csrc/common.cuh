@@ -52,6 +52,35 @@ template <int OFF = 0> __device__ __forceinline__ void sts_u32(uint32_t saddr, u
 template <int OFF = 0> __device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(saddr), "n"(OFF), "h"((uint16_t)v) : "memory");
 }
+template <int OFF = 0> __device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(saddr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF = 0> __device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(saddr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF = 0> __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(saddr), "n"(OFF)
+               : "memory");
+  return v;
+}
+template <int OFF = 0> __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0+%1], %2;" ::"r"(saddr), "n"(OFF), "r"(v) : "memory");
+}
+template <int OFF = 0> __device__ __forceinline__ void sts_v2(uint32_t saddr, const uint2& v) {
+  asm volatile("st.shared.v2.u32 [%0+%1], {%2,%3};" ::"r"(saddr), "n"(OFF), "r"(v.x), "r"(v.y) : "memory");
+}
+template <int OFF = 0> __device__ __forceinline__ void sts_v4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0+%1], {%2,%3,%4,%5};" ::"r"(saddr), "n"(OFF), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
 // c + (a * b >> 32): with b a power of two this is "c + (a >> k)" on the FMA
 // pipe (IMAD.HI), which the decode loops use to off-load the busier ALU pipe
 __device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {

@@ -8,6 +8,8 @@
 #include "ljpeg_fused.cuh"
 #include "ljpeg_ranges.cuh"
 #include "ljpeg_thread.cuh"
+#include "ljpeg_tile.cuh"
+#include "ljpeg_host.h"
 #include "rawforms.cuh"
 #include "lookup.cuh"
 #include "lookup_host.h"
@@ -62,6 +64,11 @@ static int set_err(rsb200_ctx* c, int code, const char* fmt, ...) {
   }
   return code;
 }
+
+
+// offset + extent without wrap-around: a sum that does not fit saturates, so the plan asks for
+// more bytes than any caller has and rsb200_plan_run refuses it
+static inline uint64_t sat_add(uint64_t a, uint64_t b) { return a + b < a ? ~0ull : a + b; }
 
 #define CUDA_TRY(ctx, expr)                                                    \
   do {                                                                         \
@@ -187,6 +194,10 @@ struct rsb200_plan {
   // untiled strips): multi-CTA count/verify/diffs + K3
   uint32_t* d_small_ids = nullptr;
   int nsmall = 0;
+  uint32_t* d_tile_ids = nullptr; // segments decoded by k2_tile_kernel<R> (ljpeg_tile.cuh)
+  DevTileParam* d_tile_params = nullptr;
+  int ntile = 0;
+  int tile_r = 1;
   uint32_t* d_thread_ids = nullptr; // segments decoded one per thread (K2C + K2T)
   DevTScan* d_tscans = nullptr;
   DevTInfo* d_tinfos = nullptr;
@@ -247,6 +258,12 @@ extern "C" int rsb200_create(int device, rsb200_ctx** out) {
                        (int)sizeof(K2Shared));
   cudaFuncSetAttribute(k2_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)fused_smem_bytes(4));
+  cudaFuncSetAttribute(lookup_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES);
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaFuncSetAttribute(k2_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)tile_smem_bytes<1>());
+  cudaFuncSetAttribute(k2_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)tile_smem_bytes<2>());
   cudaFuncSetAttribute(k2_range_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)fused_smem_bytes(4));
   cudaFuncSetAttribute(k2_range_diffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -286,6 +303,17 @@ extern "C" int rsb200_debug_phase_cycles(unsigned long long* out16, int reset) {
   }
   return RSB200_OK;
 }
+extern "C" int rsb200_debug_tile_phase_cycles(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  if (out16 && cudaMemcpyFromSymbol(out16, rsb200::g_tile_phase_cycles, 16 * sizeof(unsigned long long)) != cudaSuccess)
+    return RSB200_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(rsb200::g_tile_phase_cycles, z, sizeof z) != cudaSuccess)
+      return RSB200_ERR_CUDA;
+  }
+  return RSB200_OK;
+}
 #endif
 
 // ------------------------------------------------------------------
@@ -316,7 +344,7 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
         ((uint64_t)j.samples * (uint64_t)j.bps) % 8 != 0 ||
         (uint64_t)j.in_pitch < ((uint64_t)j.samples * j.bps) / 8 ||
         (uint64_t)j.rows * (uint64_t)j.in_pitch > j.in_size ||
-        (uint64_t)(j.out_col0 + j.samples) * 2 > (uint64_t)j.out_pitch) {
+        ((uint64_t)j.out_col0 + j.samples) * 2 > (uint64_t)j.out_pitch) {
       delete p;
       return set_err(ctx, RSB200_ERR_ARG, "unpack job %d: malformed descriptor", i);
     }
@@ -369,10 +397,9 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
     p->in_bytes += (uint64_t)j.rows * ((uint64_t)j.samples * j.bps / 8);
     p->out_bytes += (uint64_t)j.rows * (uint64_t)j.samples * 2;
     p->pixels += (uint64_t)j.rows * (uint64_t)j.samples;
-    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + (uint64_t)j.rows * j.in_pitch);
-    p->need_out = std::max<uint64_t>(
-        p->need_out, j.out_offset + (uint64_t)(j.row0 + j.rows - 1) * j.out_pitch +
-                         2ull * (uint64_t)(j.out_col0 + j.samples));
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, (uint64_t)j.rows * j.in_pitch));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.row0 + j.rows - 1) * j.out_pitch +
+                         2ull * ((uint64_t)j.out_col0 + j.samples)));
   }
   for (auto& kv : buckets) {
     UnpackGroup g;
@@ -446,7 +473,7 @@ extern "C" int rsb200_raw_plan_create(rsb200_ctx* ctx, const rsb200_raw_job* job
     bool ok = fmt_ok && j.rows >= 0 && j.samples > 0 && j.in_pitch > 0 && j.out_pitch > 0 &&
               j.row0 >= 0 && j.out_col0 >= 0 && (j.out_offset % ob) == 0 &&
               ((uint32_t)j.out_pitch % ob) == 0 &&
-              (uint64_t)(j.out_col0 + j.samples) * ob <= (uint64_t)j.out_pitch &&
+              ((uint64_t)j.out_col0 + j.samples) * ob <= (uint64_t)j.out_pitch &&
               (uint64_t)j.rows * (uint64_t)j.in_pitch <= j.in_size;
     if (ok) {
       // bytes one row really occupies
@@ -487,10 +514,9 @@ extern "C" int rsb200_raw_plan_create(rsb200_ctx* ctx, const rsb200_raw_job* job
     p->in_bytes += (uint64_t)j.rows * raw_in_bytes(j.format, (uint32_t)j.samples);
     p->out_bytes += (uint64_t)j.rows * (uint64_t)j.samples * ob;
     p->pixels += (uint64_t)j.rows * (uint64_t)j.samples;
-    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + (uint64_t)j.rows * j.in_pitch);
-    p->need_out = std::max<uint64_t>(
-        p->need_out, j.out_offset + (uint64_t)(j.row0 + j.rows - 1) * j.out_pitch +
-                         (uint64_t)ob * (uint64_t)(j.out_col0 + j.samples));
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, (uint64_t)j.rows * j.in_pitch));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.row0 + j.rows - 1) * j.out_pitch +
+                         (uint64_t)ob * ((uint64_t)j.out_col0 + j.samples)));
   }
   if (ntables > 0) {
     const size_t tb = (size_t)ntables * 65536u * sizeof(uint16_t);
@@ -592,7 +618,7 @@ extern "C" int rsb200_lookup_plan_create(rsb200_ctx* ctx, const rsb200_lookup_jo
     p->in_bytes += bytes;
     p->out_bytes += bytes;
     p->pixels += (uint64_t)jobs[i].width * jobs[i].height;
-    p->need_out = std::max<uint64_t>(p->need_out, jobs[i].offset + (uint64_t)jobs[i].height * jobs[i].pitch);
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(jobs[i].offset, (uint64_t)jobs[i].height * jobs[i].pitch));
   }
   p->lookup_njobs = njobs;
   p->lookup_quads = (uint32_t)quads;
@@ -629,7 +655,7 @@ extern "C" int rsb200_badpix_plan_create(rsb200_ctx* ctx, const rsb200_badpix_jo
     p->pixels += hj[i].count;
     p->in_bytes += (uint64_t)hj[i].count * 2 * 4; // up to four neighbours read per bad pixel
     p->out_bytes += (uint64_t)hj[i].count * 2;
-    p->need_out = std::max<uint64_t>(p->need_out, jobs[i].offset + (uint64_t)jobs[i].height * jobs[i].pitch);
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(jobs[i].offset, (uint64_t)jobs[i].height * jobs[i].pitch));
   }
   if (list.size() > 0x7FFFFFFFull)
     return set_err(ctx, RSB200_ERR_ARG, "badpix plan: too many bad pixels");
@@ -677,7 +703,7 @@ extern "C" int rsb200_dngop_plan_create(rsb200_ctx* ctx, const rsb200_dngop_job*
     p->in_bytes += bytes;
     p->out_bytes += bytes;
     p->pixels += (uint64_t)(hj[i].row1 - hj[i].row0) * jobs[i].width;
-    p->need_out = std::max<uint64_t>(p->need_out, jobs[i].offset + (uint64_t)jobs[i].height * jobs[i].pitch);
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(jobs[i].offset, (uint64_t)jobs[i].height * jobs[i].pitch));
   }
   p->dngop_njobs = njobs;
   p->dngop_units = (uint32_t)units;
@@ -735,8 +761,7 @@ extern "C" int rsb200_scale_plan_create(rsb200_ctx* ctx, const rsb200_scale_job*
     p->in_bytes += samples * 2;
     p->out_bytes += samples * 2;
     p->pixels += (uint64_t)jobs[i].crop_w * jobs[i].crop_h;
-    p->need_out = std::max<uint64_t>(p->need_out,
-                                     jobs[i].offset + (uint64_t)jobs[i].height * jobs[i].pitch);
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(jobs[i].offset, (uint64_t)jobs[i].height * jobs[i].pitch));
   }
   for (int mode = 0; mode < 2; ++mode) {
     if (dev[mode].empty())
@@ -798,10 +823,10 @@ extern "C" int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* j
     p->in_bytes += (uint64_t)j.in_rows * j.num_mcus * per * 2;
     p->out_bytes += out_rows * j.num_mcus * 12;
     p->pixels += out_rows * j.num_mcus * 2;
-    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + (uint64_t)(j.in_rows - 1) * j.in_pitch +
-                                                    (uint64_t)j.num_mcus * per * 2);
-    p->need_out = std::max<uint64_t>(p->need_out, j.out_offset + (out_rows - 1) * j.out_pitch +
-                                                      (uint64_t)j.num_mcus * 12);
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, ((uint64_t)j.in_rows - 1) * j.in_pitch +
+                                                    (uint64_t)j.num_mcus * per * 2));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, (out_rows - 1) * j.out_pitch +
+                                                      (uint64_t)j.num_mcus * 12));
   }
   for (auto& kv : buckets) {
     SrawGroup g;
@@ -871,7 +896,7 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
         d.pad = 0;
         ds.push_back(d);
         p->in_bytes += st.in_size;
-        p->need_in = std::max<uint64_t>(p->need_in, st.in_offset + st.in_size);
+        p->need_in = std::max<uint64_t>(p->need_in, sat_add(st.in_offset, st.in_size));
       }
     }
     if (!ok) {
@@ -883,9 +908,8 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
     dj[(size_t)i].width = j.width;
     p->out_bytes += (uint64_t)j.width * j.height * 2;
     p->pixels += (uint64_t)j.width * j.height;
-    p->need_out = std::max<uint64_t>(p->need_out, j.out_offset +
-                                                      (uint64_t)(j.height - 1) * j.out_pitch +
-                                                      2ull * j.width);
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.height - 1) * j.out_pitch +
+                                                      2ull * j.width));
   }
   p->p1_nstrips = (uint32_t)ds.size();
   cudaError_t e = cudaMalloc((void**)&p->d_p1_strips, sizeof(P1StripDev) * ds.size());
@@ -988,10 +1012,9 @@ extern "C" int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* j
     p->in_bytes += units * 16;
     p->out_bytes += area * 2;
     p->pixels += area;
-    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + need);
-    p->need_out = std::max<uint64_t>(p->need_out, j.out_offset +
-                                                      (uint64_t)(j.height - 1) * j.out_pitch +
-                                                      2ull * j.width);
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, need));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.height - 1) * j.out_pitch +
+                                                      2ull * j.width));
   }
   for (auto& kv : buckets) {
     PanaGroup g;
@@ -1106,10 +1129,9 @@ extern "C" int rsb200_arw2_plan_create(rsb200_ctx* ctx, const rsb200_arw2_job* j
     p->in_bytes += px;
     p->out_bytes += px * 2;
     p->pixels += px;
-    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + px);
-    p->need_out = std::max<uint64_t>(p->need_out, j.out_offset +
-                                                      (uint64_t)(j.height - 1) * j.out_pitch +
-                                                      2ull * j.width);
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, px));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.height - 1) * j.out_pitch +
+                                                      2ull * j.width));
   }
   if (any_table && any_plain) {
     delete p;
@@ -1283,60 +1305,6 @@ static cudaError_t run_unpack_fast_group(const UnpackFastGroup& g, const uint8_t
 #undef RSB_CASE
 }
 
-// ------------------------------------------------------------------
-// Huffman table -> device table (HuffmanCode.h:66-93 code assignment,
-// PrefixCodeLookupDecoder.h:97-113 maxcode/offset, LUT as documented in ljpeg.cuh)
-// ------------------------------------------------------------------
-static bool build_dev_table(const rsb200_huff_table& h, DevTable& t) {
-  memset(&t, 0, sizeof t);
-  unsigned count = 0, maxlen = 0;
-  for (unsigned l = 1; l <= 16; ++l) {
-    count += h.ncodes_per_len[l - 1];
-    if (h.ncodes_per_len[l - 1])
-      maxlen = l;
-  }
-  if (maxlen == 0 || count > 162 || count != h.nvalues)
-    return false;
-  // Kraft / canonical assignment
-  unsigned maxCodes = 2;
-  uint32_t code = 0;
-  unsigned n = 0;
-  for (unsigned l = 0; l < 18; ++l) {
-    t.maxcode[l] = -1;
-    t.valoff[l] = 0;
-  }
-  for (unsigned l = 1; l <= maxlen; ++l) {
-    const unsigned nc = h.ncodes_per_len[l - 1];
-    if (nc > maxCodes)
-      return false;
-    maxCodes = (maxCodes - nc) * 2;
-    if (nc) {
-      t.valoff[l] = (int32_t)code - (int32_t)n;
-      for (unsigned i = 0; i < nc; ++i, ++n, ++code) {
-        const unsigned ssss = h.values[n];
-        if (ssss > 16)
-          return false;
-        // SSSS = 16 stays out of the LUT: the decode loops resolve LUT hits with a
-        // branch-free extend() that only covers SSSS <= 15; the rare 16 takes the walk
-        if (l <= (unsigned)LUT_BITS && ssss != 16) {
-          const unsigned total = l + (ssss == 16 ? (h.fix_dng16 ? 16u : 0u) : ssss);
-          const uint16_t e = (uint16_t)(l | (ssss << 5) | (total << 10));
-          const uint32_t lo = code << (LUT_BITS - l);
-          const uint32_t hi = lo | ((1u << (LUT_BITS - l)) - 1u);
-          for (uint32_t c = lo; c <= hi; ++c)
-            t.lut[c] = e;
-        }
-      }
-      t.maxcode[l] = (int32_t)code - 1;
-    }
-    code <<= 1;
-  }
-  memcpy(t.values, h.values, count);
-  t.maxlen = (int32_t)maxlen;
-  t.fix16 = h.fix_dng16 ? 1 : 0;
-  return true;
-}
-
 struct ScanBuild {
   std::vector<DevScan> scans;
   std::vector<DevStrip> strips;
@@ -1344,29 +1312,6 @@ struct ScanBuild {
   uint64_t diff_elems = 0;
   uint64_t col_elems = 0;
 };
-
-static void assign_tables(DevScan& d, const uint8_t* table, int ncomp,
-                          const uint8_t* comp_of_pos, int group) {
-  // block-local slots: slot of component c
-  int slot_of_comp[4] = {0, 0, 0, 0};
-  int nslots = 0;
-  for (int s = 0; s < 4; ++s)
-    d.table_idx[s] = -1;
-  for (int c = 0; c < ncomp; ++c) {
-    int found = -1;
-    for (int s = 0; s < nslots; ++s)
-      if (d.table_idx[s] == (int)table[c])
-        found = s;
-    if (found < 0) {
-      found = nslots++;
-      d.table_idx[found] = table[c];
-    }
-    slot_of_comp[c] = found;
-  }
-  d.multi_table = nslots > 1;
-  for (int p = 0; p < group && p < 12; ++p)
-    d.table_of[p] = (uint8_t)slot_of_comp[comp_of_pos[p] & 3];
-}
 
 constexpr uint32_t BIG_SEGMENT_BYTES = 256u << 10; // above this a segment gets several CTAs
 
@@ -1397,7 +1342,8 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   p->nscans = (int)b.scans.size();
   p->nunits = p->nscans;
   // classify the segments and lay out the scratch of the multi-CTA path
-  std::vector<uint32_t> small_ids, big_ids, thread_ids;
+  std::vector<uint32_t> small_ids, big_ids, thread_ids, tile_ids;
+  std::vector<DevTileParam> tile_prm;
   // K2T (one thread per segment) pays off once the launch holds enough independent
   // segments to fill the machine with serial decoders; RSB200_LJPEG_PATH=thread|fused
   // forces the choice (tests exercise both kernels on the same inputs).
@@ -1411,10 +1357,28 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     if (const char* e = getenv("RSB200_LJPEG_PATH")) {
       if (!strcmp(e, "thread"))
         use_thread = true;
-      else if (!strcmp(e, "fused"))
+      else if (!strcmp(e, "fused") || !strcmp(e, "tile"))
         use_thread = false;
     }
   }
+  // k2_tile_kernel<R> takes the plain single-table tiles; RSB200_LJPEG_PATH=fused keeps them on
+  // k2_fused_kernel (tests run both), RSB200_TILE_R=1|2 picks the geometry, RSB200_TILE_PREROLL /
+  // RSB200_TILE_NPIECES override the plan-time parameters (A/B runs)
+  bool use_tile = true;
+  int tile_r = 1, preroll_override = -1, npieces_override = 0;
+  if (const char* e = getenv("RSB200_LJPEG_PATH"))
+    if (!strcmp(e, "fused"))
+      use_tile = false;
+  if (const char* e = getenv("RSB200_TILE_R"))
+    tile_r = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("RSB200_TILE_PREROLL"))
+    preroll_override = atoi(e);
+  if (const char* e = getenv("RSB200_TILE_NPIECES"))
+    npieces_override = atoi(e);
+  p->tile_r = tile_r;
+  const int tile_min_rs = tile_r == 2 ? TileGeom<2>::MIN_RS : TileGeom<1>::MIN_RS;
+  const int tile_npiece = tile_r == 2 ? TileGeom<2>::NPIECE : TileGeom<1>::NPIECE;
+  const int tile_dcap = tile_r == 2 ? TileGeom<2>::DCAP : TileGeom<1>::DCAP;
   std::vector<BigScanInfo> big;
   std::vector<DevRange> ranges;
   b.rows.clear();
@@ -1426,7 +1390,18 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     if (is_big)
       (d.kind == 2 ? p->has_pentax : (d.kind == 3 ? p->has_nikon : p->has_k3)) = true;
     if (!is_big) {
-      (use_thread && thread_eligible(d) ? thread_ids : small_ids).push_back((uint32_t)i);
+      if (use_thread && thread_eligible(d)) {
+        thread_ids.push_back((uint32_t)i);
+      } else if (use_tile && tile_eligible(d, tile_min_rs)) {
+        DevTileParam tp;
+        tile_params(d, tile_npiece, tile_dcap, preroll_override, tp.npieces, tp.preroll);
+        if (npieces_override > 0)
+          tp.npieces = (uint32_t)std::min(npieces_override, tile_npiece);
+        tile_ids.push_back((uint32_t)i);
+        tile_prm.push_back(tp);
+      } else {
+        small_ids.push_back((uint32_t)i);
+      }
       continue;
     }
     big_ids.push_back((uint32_t)i);
@@ -1450,6 +1425,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
       ranges.push_back(DevRange{(uint32_t)i, r});
   }
   p->nsmall = (int)small_ids.size();
+  p->ntile = (int)tile_ids.size();
   p->nthread = (int)thread_ids.size();
   p->ntables = ntables;
   p->nbig = (int)big_ids.size();
@@ -1473,6 +1449,8 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   up((void**)&p->d_rows, b.rows.data(), sizeof(K3RowRef) * b.rows.size());
   up((void**)&p->d_small_ids, small_ids.data(), sizeof(uint32_t) * small_ids.size());
   up((void**)&p->d_thread_ids, thread_ids.data(), sizeof(uint32_t) * thread_ids.size());
+  up((void**)&p->d_tile_ids, tile_ids.data(), sizeof(uint32_t) * tile_ids.size());
+  up((void**)&p->d_tile_params, tile_prm.data(), sizeof(DevTileParam) * tile_prm.size());
   if (!thread_ids.empty()) {
     std::vector<DevTScan> tsc(thread_ids.size());
     uint64_t clean_words = 0, n_anchor = 0;
@@ -1517,7 +1495,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
                    cudaGetErrorString(e));
   }
-  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->nthread ? 2 : 0) +
+  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->ntile ? 1 : 0) + (p->nthread ? 2 : 0) +
                         (p->nbig ? 5 + (p->has_k3 ? 2 : 0) + (p->has_pentax ? 2 : 0) + (p->has_nikon ? 2 : 0) : 0);
   return RSB200_OK;
 }
@@ -1573,9 +1551,8 @@ extern "C" int rsb200_pentax_plan_create(rsb200_ctx* ctx, const rsb200_huff_tabl
     p->in_bytes += j.in_size;
     p->out_bytes += (uint64_t)j.width * j.height * 2;
     p->pixels += (uint64_t)j.width * j.height;
-    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + j.in_size);
-    p->need_out = std::max<uint64_t>(
-        p->need_out, j.out_offset + (uint64_t)(j.height - 1) * j.out_pitch + 2ull * j.width);
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, j.in_size));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.height - 1) * j.out_pitch + 2ull * j.width));
   }
   int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/false);
   if (rc != RSB200_OK)
@@ -1639,9 +1616,8 @@ extern "C" int rsb200_nikon_plan_create(rsb200_ctx* ctx, const rsb200_huff_table
     p->in_bytes += j.in_size;
     p->out_bytes += (uint64_t)j.width * j.height * 2;
     p->pixels += (uint64_t)j.width * j.height;
-    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + j.in_size);
-    p->need_out = std::max<uint64_t>(
-        p->need_out, j.out_offset + (uint64_t)(j.height - 1) * j.out_pitch + 2ull * j.width);
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, j.in_size));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.height - 1) * j.out_pitch + 2ull * j.width));
   }
   int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/false);
   if (rc != RSB200_OK)
@@ -1672,48 +1648,16 @@ extern "C" int rsb200_ljpeg_plan_create(rsb200_ctx* ctx, const rsb200_huff_table
   p->ctx = ctx;
   ScanBuild b;
   b.scans.reserve((size_t)nscans);
-  static const uint8_t ident[12] = {0, 1, 2, 3, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < nscans; ++i) {
     const rsb200_ljpeg_scan& s = scans[i];
     const int group = s.mcu_w * s.mcu_h;
-    const bool mcu_ok = (s.mcu_h == 1 && s.mcu_w >= 1 && s.mcu_w <= 4) ||
-                        (s.mcu_w == 2 && s.mcu_h == 2);
-    bool ok = mcu_ok && s.rows > 0 && s.frame_w > 0 && s.store_w > 0 &&
-              (uint64_t)s.frame_w * s.mcu_w >= s.store_w &&
-              (uint64_t)(s.out_x + s.store_w) * 2 <= s.out_pitch &&
-              (uint64_t)s.rows * s.frame_w * group < (1ull << 32) &&
-              s.in_size < (1u << 28);
-    for (int c = 0; ok && c < group; ++c)
-      ok = s.table[c] < ntables;
-    if (!ok) {
+    DevScan d;
+    // validation (every sum in 64 bits, out_offset 2-byte aligned) + descriptor: ljpeg_host.h
+    if (!ljpeg_scan_to_dev(s, ntables, d)) {
       delete p;
       return set_err(ctx, RSB200_ERR_ARG, "ljpeg scan %d: malformed descriptor", i);
     }
-    DevScan d;
-    memset(&d, 0, sizeof d);
-    d.in_offset = s.in_offset;
-    d.in_size = s.in_size;
-    d.rows = s.rows;
-    d.row_samples = s.frame_w * (uint32_t)group;
-    d.n_samples = d.rows * d.row_samples;
-    d.rs_inv = d.row_samples <= 1 ? 0xFFFFFFFFu
-                                  : (uint32_t)(((1ull << 32) + d.row_samples - 1) / d.row_samples);
-    d.group = (uint8_t)group;
-    d.ncomp = (uint8_t)group;
-    d.kind = 0;
-    d.pattern = PAT_PLAIN;
-    assign_tables(d, s.table, group, ident, group);
-    for (int c = 0; c < group; ++c) {
-      d.first_idx[c] = (uint8_t)c;
-      d.init_pred[c] = s.init_pred[c];
-    }
-    d.out_offset = s.out_offset;
-    d.out_pitch = s.out_pitch;
-    d.out_x = s.out_x;
-    d.out_y = s.out_y;
-    d.store_w = s.store_w;
-    d.mcu_w = s.mcu_w;
-    d.mcu_h = s.mcu_h;
+    (void)group;
     d.diff_offset = b.diff_elems;
     b.diff_elems += ((uint64_t)d.n_samples + 7) & ~7ull;
     d.col_offset = b.col_elems;
@@ -1725,11 +1669,14 @@ extern "C" int rsb200_ljpeg_plan_create(rsb200_ctx* ctx, const rsb200_huff_table
     p->in_bytes += s.in_size;
     p->out_bytes += (uint64_t)s.rows * s.mcu_h * s.store_w * 2;
     p->pixels += (uint64_t)s.rows * s.mcu_h * s.store_w;
-    p->need_in = std::max<uint64_t>(p->need_in, s.in_offset + s.in_size);
-    p->need_out = std::max<uint64_t>(
-        p->need_out, s.out_offset +
-                         (uint64_t)(s.out_y + s.rows * s.mcu_h - 1) * s.out_pitch +
-                         2ull * (s.out_x + s.store_w));
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(s.in_offset, s.in_size));
+    const uint64_t last_row = (uint64_t)s.out_y + (uint64_t)s.rows * s.mcu_h - 1;
+    const uint64_t extent = last_row * s.out_pitch + 2ull * ((uint64_t)s.out_x + s.store_w);
+    if (s.out_offset + extent < s.out_offset || s.in_offset + (uint64_t)s.in_size < s.in_offset) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "ljpeg scan %d: offset + extent overflows", i);
+    }
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(s.out_offset, extent));
   }
   int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/true);
   if (rc != RSB200_OK)
@@ -1857,9 +1804,8 @@ extern "C" int rsb200_cr2_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* 
     p->in_bytes += j.in_size;
     p->out_bytes += (uint64_t)j.img_w * j.img_h * 2;
     p->pixels += (uint64_t)j.img_w * j.img_h;
-    p->need_in = std::max<uint64_t>(p->need_in, j.in_offset + j.in_size);
-    p->need_out = std::max<uint64_t>(
-        p->need_out, j.out_offset + (uint64_t)(j.img_h - 1) * j.out_pitch + 2ull * j.img_w);
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, j.in_size));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.img_h - 1) * j.out_pitch + 2ull * j.img_w));
   }
   int rc = finish_ljpeg_plan(ctx, p, tables, ntables, b, /*fused=*/false);
   if (rc != RSB200_OK)
@@ -1871,6 +1817,25 @@ extern "C" int rsb200_cr2_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* 
 // ------------------------------------------------------------------
 // execution
 // ------------------------------------------------------------------
+namespace {
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false, ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess)
+      prev = -1;
+    if (prev != dev) {
+      ok = cudaSetDevice(dev) == cudaSuccess;
+      changed = ok;
+    }
+  }
+  ~DeviceGuard() {
+    if (changed && prev >= 0)
+      cudaSetDevice(prev);
+  }
+};
+} // namespace
+
 extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes,
                                void* d_out, size_t out_bytes, void* stream) {
   if (!p || !d_out || (!d_in && p->need_in))
@@ -1883,6 +1848,10 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
                    (unsigned long long)p->need_out);
   if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
     return set_err(ctx, RSB200_ERR_ARG, "plan_run: device pointers must be 16-byte aligned");
+  // launches go to the plan's device whatever the caller's current device is (restored on return)
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok)
+    return set_err(ctx, RSB200_ERR_CUDA, "plan_run: cannot select device %d", ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   const uint8_t* in = (const uint8_t*)d_in;
   uint8_t* outp = (uint8_t*)d_out;
@@ -1903,10 +1872,7 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
     const uint32_t nb = (p->lookup_quads + LUT_WARPS - 1) / LUT_WARPS;
     const char* smem_env = getenv("RSB200_LUT_SMEM"); // A/B candidate, see lookup.cuh
     if (smem_env && smem_env[0] == '1' && !p->lookup_dither && p->lookup_ntables == 1) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(lookup_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         LUT_SMEM_BYTES));
-      int sms = 0;
-      CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      const int sms = ctx->sm_count;
       lookup_smem_kernel<<<(unsigned)std::max(1, sms), LUT_SMEM_NT, LUT_SMEM_BYTES, st>>>(
           outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads, p->d_lookup_tables);
     } else if (p->lookup_dither)
@@ -1970,6 +1936,18 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
     }
   } else {
     const size_t fsm = fused_smem_bytes(p->ntab_slots);
+    if (p->ntile) {
+      if (p->tile_r == 2)
+        k2_tile_kernel<2><<<p->ntile, TL_NT, tile_smem_bytes<2>(), st>>>(
+            in, (uint64_t)in_bytes, p->d_scans, p->d_tables, outp, p->d_results, p->d_tile_ids,
+            p->d_tile_params);
+      else
+        k2_tile_kernel<1><<<p->ntile, TL_NT, tile_smem_bytes<1>(), st>>>(
+            in, (uint64_t)in_bytes, p->d_scans, p->d_tables, outp, p->d_results, p->d_tile_ids,
+            p->d_tile_params);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    }
     if (p->nsmall) {
       k2_fused_kernel<<<p->nsmall, F_NT, fsm, st>>>(in, (uint64_t)in_bytes, p->d_scans,
                                                      p->d_tables, outp, p->d_results,
@@ -2315,6 +2293,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   cudaFree(p->d_colvals);
   cudaFree(p->d_results);
   cudaFree(p->d_small_ids);
+  cudaFree(p->d_tile_ids);
+  cudaFree(p->d_tile_params);
   cudaFree(p->d_thread_ids);
   cudaFree(p->d_tscans);
   cudaFree(p->d_tinfos);

@@ -9,14 +9,18 @@ from helpers import dng_ljpeg_scans, gpu_run
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["auto", "thread"])
+@pytest.fixture(autouse=True, params=["auto", "tile2", "fused", "thread"])
 def ljpeg_path(request, monkeypatch):
-    """Every case runs twice: with the plan's own choice of kernel (block per segment for
-    these sizes) and with the one-thread-per-segment path (K2C + K2T) forced."""
-    if request.param != "auto":
+    """Every case runs four times: with the plan's own choice of kernel (k2_tile_kernel<1> for
+    plain single-table tiles, k2_fused_kernel for the rest, at these sizes), with the second
+    geometry of the tile kernel (RSB200_TILE_R=2), with the round-1 block-per-segment kernel for
+    everything (RSB200_LJPEG_PATH=fused) and with the one-thread-per-segment path (K2C + K2T)."""
+    monkeypatch.delenv("RSB200_LJPEG_PATH", raising=False)
+    monkeypatch.delenv("RSB200_TILE_R", raising=False)
+    if request.param == "tile2":
+        monkeypatch.setenv("RSB200_TILE_R", "2")
+    elif request.param != "auto":
         monkeypatch.setenv("RSB200_LJPEG_PATH", request.param)
-    else:
-        monkeypatch.delenv("RSB200_LJPEG_PATH", raising=False)
     return request.param
 
 
