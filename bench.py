@@ -4,16 +4,22 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 Metric (BASELINE.json): MPixels/s decoded (bit-exact); achieved HBM GB/s vs roofline.
-Headline workload (configs[1]): 14-bit packed unpack, 8256x5504 (45 MP) frames,
-a batch of --frames frames per step, inputs resident in HBM (`value`) and through
-the host-buffer C-ABI call with H2D/D2H inside the timed region (`e2e`).
-`others` carries the same device-timed measurement for the LJPEG configs
-(configs[2] DNG tiles, configs[3] CR2).
 
-One JSON line on stdout (rank 0).  A "step" = one pass of the hot path over one
-batch of synthetic input.  Under torchrun each rank decodes its own batch (the
-path shards by frame with no data-path collective -> weak scaling); the optional
-NVLink output gather is timed separately (`gather`).
+Headline workload at every N: BASELINE configs[4] -- a 256-frame batch of configs[2] frames
+(DNG lossless-JPEG predictor 1, 14-bit 8256x5504 = 45 MP, 726 tiles of 256x256 each; 256
+DISTINCT synthetic frames, seeds 12345+i), sharded 256/N frames per GPU: strong scaling, the
+configuration north_star's target is quoted on ("45 MP 14-bit LJPEG decode ... with >= 6x
+scaling at 8 GPUs on a 256-frame batch").  `value` = device-timed decode with inputs resident
+in HBM (CUDA events, W warm-up + K timed steps, max over ranks); `roofline` for the decode
+kernel in SURVEY 8(d)'s in+out bytes (and the read-only variant); `e2e` = the same batch through
+the host-buffer C-ABI call (H2D + decode + D2H inside the timed region); `cpu_baseline` = the
+reference's AbstractDngDecompressor::decompress() on the box's host cores (bounded sample);
+`gather` (N > 1) = decode + NVLink output gather through the C ABI, both to every rank and to
+the consumer GPU.  `single_frame` carries configs[2] proper (ONE frame per launch: decode,
+roofline, pinned / pageable host runs, the host mirror's drop-in call), `others` configs[0],
+[1] and [3] (and, with --all-legs, every secondary kernel).
+
+One JSON line on stdout (rank 0).  A "step" = one pass of the hot path over the batch.
 """
 import argparse
 import json
@@ -26,6 +32,9 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# the reference arm / cpu_baseline: stable thread placement for the reference's OpenMP loops
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -218,56 +227,260 @@ def cpu_reference_unpack(sample_frames=1, reps=3):
             "unit": "MPixels/s", "sample": "1 frame 8256x5504 14-bit MSB, oracle C port"}
 
 
+# ------------------------------------------------------------------
+# LJPEG workloads (BASELINE configs[2] / configs[4])
+# ------------------------------------------------------------------
+FRAMES_TOTAL = 256      # configs[4]: 256-frame batch, sharded 256/N per GPU (strong scaling)
+SEED0 = 12345           # frame i is synth.image_model(W, H, SEED0 + i)
+
+
+def _weights():
+    """Per-pixel weights of the second checksum (uint64 wrap-around arithmetic)."""
+    y, x = np.mgrid[0:H, 0:W].astype(np.uint64)
+    return ((x * np.uint64(31) + y * np.uint64(17)) & np.uint64(0xFFFF)) | np.uint64(1)
+
+
+def _gen_frame(job):
+    """Worker (no CUDA): synthesise frame `seed`, encode it as a tiled LJPEG DNG payload, put the
+    bytes into the shared block and return the scan descriptors + two checksums of the image."""
+    seed, shm_name, off, cap = job
+    from multiprocessing import shared_memory
+    from oracle import synth
+    import rawspeed_b200 as rs
+    from helpers import dng_ljpeg_scans
+    img = synth.image_model(W, H, seed)
+    t = synth.make_dng_ljpeg(img, 256, 256)
+    assert t.blob.size <= cap, (t.blob.size, cap)
+    shm = shared_memory.SharedMemory(name=shm_name)
+    try:
+        np.frombuffer(shm.buf, dtype=np.uint8, count=t.blob.size, offset=off)[:] = t.blob
+    finally:
+        shm.close()
+    tabs, scans = dng_ljpeg_scans(t, rs.image_pitch(W))
+    keys = list(tabs.keys.keys())
+    v = img.astype(np.uint64)
+    s0 = int(v.sum(dtype=np.uint64))
+    with np.errstate(over="ignore"):
+        s1 = int((v * _weights()).sum(dtype=np.uint64))
+    return (seed, int(t.blob.size), b"".join(bytes(s_) for s_ in scans), keys, s0, s1,
+            [int(o) for o in t.offsets], [int(n) for n in t.lengths])
+
+
+def gen_frames(seeds, procs):
+    """Distinct synthetic frames, generated on the host cores in parallel (before CUDA is
+    touched).  Returns (shared block, per-frame capacity, per-frame records)."""
+    from multiprocessing import shared_memory, get_context
+    cap = align(int(PIX * 1.25) + 4096)  # the synthetic frames compress to ~1.01 byte/pixel
+    shm = shared_memory.SharedMemory(create=True, size=max(1, len(seeds)) * cap)
+    jobs = [(sd, shm.name, k * cap, cap) for k, sd in enumerate(seeds)]
+    if procs > 1 and len(seeds) > 1:
+        with get_context("fork").Pool(min(procs, len(seeds))) as pool:
+            recs = pool.map(_gen_frame, jobs, chunksize=1)
+    else:
+        recs = [_gen_frame(j) for j in jobs]
+    return shm, cap, recs
+
+
+class LJpegBatch:
+    """Frames of one rank laid out in one input / one output buffer + the plan over all tiles."""
+
+    def __init__(self, torch, rs, ctx, shm, cap, recs, pinned=True):
+        from helpers import TableSet
+        self.n = len(recs)
+        self.out_pitch = rs.image_pitch(W)
+        self.ob = align(H * self.out_pitch)
+        self.in_off = []
+        off = 0
+        for r in recs:
+            self.in_off.append(off)
+            off += align(r[1])
+        self.in_bytes = off
+        self.h_in = torch.empty(self.in_bytes + 64, dtype=torch.uint8, pin_memory=pinned)
+        hv = self.h_in.numpy()
+        src = np.frombuffer(shm.buf, dtype=np.uint8)
+        tabs = TableSet()
+        scans = []
+        ssz = C_sizeof_scan(rs)
+        for k, r in enumerate(recs):
+            hv[self.in_off[k]:self.in_off[k] + r[1]] = src[k * cap:k * cap + r[1]]
+            tid = [tabs.add(*key) for key in r[3]]
+            for j in range(len(r[2]) // ssz):
+                s1 = rs.LJpegScan.from_buffer_copy(r[2][j * ssz:(j + 1) * ssz])
+                s1.in_offset += self.in_off[k]
+                s1.out_offset += k * self.ob
+                for c in range(4):
+                    s1.table[c] = tid[s1.table[c]] if s1.table[c] < len(tid) else 0
+                scans.append(s1)
+        del src
+        self.recs = recs
+        self.tabs = tabs
+        self.scans = scans
+        self.plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
+        self.d_in = self.h_in.cuda()
+        self.out_bytes = self.n * self.ob
+
+    def check(self, torch, d_out, wts, full_frames=()):
+        """All frames by two checksums (uint64 wrap-around) against the generator's image; the
+        frames listed in full_frames bit for bit against a regenerated image."""
+        from oracle import synth
+        ok = True
+        for k, r in enumerate(self.recs):
+            fr = d_out[k * self.ob:k * self.ob + H * self.out_pitch].view(torch.int16).view(H, self.out_pitch // 2)
+            v = (fr[:, :W].to(torch.int64) & 0xFFFF)
+            s0 = int(v.sum().item()) & 0xFFFFFFFFFFFFFFFF
+            s1 = int((v * wts).sum().item()) & 0xFFFFFFFFFFFFFFFF
+            ok = ok and s0 == r[4] and s1 == r[5]
+        for k in full_frames:
+            img = synth.image_model(W, H, self.recs[k][0])
+            g = d_out[k * self.ob:k * self.ob + H * self.out_pitch].cpu().numpy().view(np.uint16).reshape(H, self.out_pitch // 2)
+            ok = ok and bool(np.array_equal(g[:, :W], img))
+        return ok
+
+
+def C_sizeof_scan(rs):
+    import ctypes
+    return ctypes.sizeof(rs.LJpegScan)
+
+
+def cpu_reference_ljpeg(shm, cap, recs, reps=5, warm=1):
+    """The reference's own CPU path for this workload on the box's host cores:
+    AbstractDngDecompressor::decompress() (OpenMP over the tiles) on a bounded sample of frames,
+    median of `reps` passes after `warm` warm-up passes."""
+    import oracle
+    from oracle import port
+    ncores = os.cpu_count() or 1
+    src = np.frombuffer(shm.buf, dtype=np.uint8)
+    frames = [(src[k * cap:k * cap + r[1]].copy(), r[6], r[7]) for k, r in enumerate(recs)]
+    del src
+    img = port.new_image(W, H)
+    if oracle.HAVE_REF:
+        def one_pass(nt):
+            return sum(oracle.ref.dng_decompress(b, o, l, img, W, 1, 256, 256, 7, nthreads=nt, reps=1)
+                       for b, o, l in frames)
+        for _ in range(warm):
+            one_pass(ncores)
+        ts = sorted(one_pass(ncores) for _ in range(reps))
+        ms = ts[len(ts) // 2]
+        ms1 = oracle.ref.dng_decompress(frames[0][0], frames[0][1], frames[0][2], img, W, 1, 256, 256, 7,
+                                        nthreads=1, reps=1)
+        return {"kind": "reference", "cores": ncores, "unit": "MPixels/s",
+                "value": len(frames) * PIX / (ms * 1e-3) / 1e6,
+                "best": len(frames) * PIX / (ts[0] * 1e-3) / 1e6,
+                "worst": len(frames) * PIX / (ts[-1] * 1e-3) / 1e6,
+                "single_thread_value": PIX / (ms1 * 1e-3) / 1e6,
+                "sample": "%d frame(s) 8256x5504 DNG LJPEG (726 tiles each), "
+                          "AbstractDngDecompressor::decompress() with %d OpenMP threads "
+                          "(OMP_PROC_BIND=close, OMP_PLACES=cores), median of %d passes after %d warm-up; "
+                          "single_thread_value = the same with 1 thread" % (len(frames), ncores, reps, warm)}
+    t0 = time.perf_counter()
+    for b, o, l in frames:
+        port.dng_decompress(b, o, l, img, W, 1, 256, 256, 7, nthreads=ncores)
+    ms = (time.perf_counter() - t0) * 1e3
+    return {"kind": "port", "cores": ncores, "unit": "MPixels/s", "value": len(frames) * PIX / (ms * 1e-3) / 1e6,
+            "sample": "%d frame(s), oracle C port with %d OpenMP threads" % (len(frames), ncores)}
+
+
+def cpu_reference_c1():
+    """BASELINE configs[0]: UncompressedDecompressor 12-bit packed, 4000x3000, CPU only --
+    the reference's own accounting (items = pixels, bytes = bps*pixels/8,
+    bench/librawspeed/decompressors/UncompressedDecompressorBenchmark.cpp:80-82)."""
+    import oracle
+    from oracle import port, synth
+    if not oracle.HAVE_REF:
+        return None
+    w, h, bps = 4000, 3000, 12
+    out = {}
+    for name, order in (("MSB", port.MSB), ("LSB", port.LSB)):
+        data, pitch = synth.packed_frame(w, h, bps, seed=1)
+        img = port.new_image(w, h)
+        ts = sorted(oracle.ref.unpack(data, img, w, 1, (0, 0, w, h), pitch, bps, order, reps=1) for _ in range(7))
+        ms = ts[len(ts) // 2]
+        out[name] = {"ms": ms, "MPixels/s": w * h / (ms * 1e-3) / 1e6,
+                     "input_MB/s": w * h * bps / 8 / (ms * 1e-3) / 1e6}
+    out["what"] = ("configs[0]: UncompressedDecompressor::readUncompressedRaw 12-bit 4000x3000 on the host, "
+                   "1 thread as shipped, median of 7")
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation, rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the headline workload (DNG LJPEG
+    frames through AbstractDngDecompressor::decompress, all host cores), rank 0 only; one step =
+    a bounded sample of the batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = None
-    ms_tot = 0.0
-    vals = []
-    for i in range(args.warmup + args.steps):
-        cb = cpu_reference_unpack(reps=1)
-        if i >= args.warmup:
-            vals.append(cb["value"])
-    v = float(np.mean(vals))
-    cb["value"] = v
-    line = {
-        "impl": "reference", "metric": "MPixels/s decoded (bit-exact)", "value": v,
-        "unit": "MPixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": PIX / v / 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": "configs[1]: 14-bit packed unpack 8256x5504 (45 MP), 1 frame per "
-                               "step (bounded sample of the GPU arm's batch)"},
-        "cpu_baseline": cb,
-        "e2e": {"value": v, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
+    nsample = max(1, args.ref_frames)
+    shm, cap, recs = gen_frames([SEED0 + i for i in range(nsample)], procs=min(nsample, os.cpu_count() or 1))
+    try:
+        import oracle
+        from oracle import port
+        ncores = os.cpu_count() or 1
+        src = np.frombuffer(shm.buf, dtype=np.uint8)
+        frames = [(src[k * cap:k * cap + r[1]].copy(), r[6], r[7]) for k, r in enumerate(recs)]
+        del src
+        img = port.new_image(W, H)
+        dec = oracle.ref.dng_decompress if oracle.HAVE_REF else None
+
+        def step():
+            if dec:
+                return sum(dec(b, o, l, img, W, 1, 256, 256, 7, nthreads=ncores, reps=1) for b, o, l in frames)
+            t0 = time.perf_counter()
+            for b, o, l in frames:
+                port.dng_decompress(b, o, l, img, W, 1, 256, 256, 7, nthreads=ncores)
+            return (time.perf_counter() - t0) * 1e3
+        for _ in range(args.warmup):
+            step()
+        ts = [step() for _ in range(args.steps)]
+        ms = float(np.median(ts))
+        v = nsample * PIX / (ms * 1e-3) / 1e6
+        cb = {"kind": "reference" if dec else "port", "cores": ncores, "value": v, "unit": "MPixels/s",
+              "best": nsample * PIX / (min(ts) * 1e-3) / 1e6, "worst": nsample * PIX / (max(ts) * 1e-3) / 1e6,
+              "sample": "%d distinct frame(s) 8256x5504 DNG LJPEG per step, AbstractDngDecompressor::decompress() "
+                        "with %d OpenMP threads (OMP_PROC_BIND=close, OMP_PLACES=cores); value = median of the "
+                        "%d timed steps" % (nsample, ncores, args.steps)}
+        line = {
+            "impl": "reference", "metric": "MPixels/s decoded (bit-exact)", "value": v,
+            "unit": "MPixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": {"workload": "configs[4]: batch of configs[2] frames (DNG lossless-JPEG predictor 1, "
+                                   "8256x5504, 726 tiles of 256x256); %d frames per step = a bounded sample "
+                                   "of the GPU arm's 256-frame batch" % nsample},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+    finally:
+        shm.close()
+        shm.unlink()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--frames", type=int, default=8, help="frames per step per GPU")
-    ap.add_argument("--ljpeg-frames", type=int, default=8, help="frames in the small LJPEG batch leg")
-    ap.add_argument("--ljpeg-big-frames", type=int, default=64,
-                    help="frames in the large LJPEG batch leg (one-thread-per-segment path)")
+    ap.add_argument("--total-frames", type=int, default=FRAMES_TOTAL,
+                    help="frames of the batch over all GPUs (configs[4]: 256)")
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of --impl reference")
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the cpu_baseline sample")
+    ap.add_argument("--gen-procs", type=int, default=0, help="host processes that synthesise the frames")
+    ap.add_argument("--frames", type=int, default=8, help="frames per step of the configs[1] unpack leg")
+    ap.add_argument("--ljpeg-frames", type=int, default=8)
+    ap.add_argument("--ljpeg-big-frames", type=int, default=64)
     ap.add_argument("--sustain-s", type=float, default=1.0,
                     help="seconds of the same step back to back after the timed steps "
                          "(clock sampling + sustained figure)")
-    ap.add_argument("--c5", action="store_true",
-                    help="run BASELINE configs[4]: the 256-frame LJPEG batch sharded over the "
-                         "ranks (256/N frames per GPU, strong scaling) + NCCL gather of the outputs")
+    ap.add_argument("--c5", action="store_true", help="(kept for compatibility: the headline IS configs[4] now)")
+    ap.add_argument("--all-legs", action="store_true",
+                    help="also time every secondary kernel (UncompressedDecompressor forms, vendor codecs, "
+                         "post-decode stages): several minutes")
     ap.add_argument("--skip-others", action="store_true")
-    ap.add_argument("--only-unvalidated", action="store_true",
-                    help="with --unvalidated: skip the other (validated) secondary legs (short runs under ncu)")
+    ap.add_argument("--skip-single", action="store_true")
+    ap.add_argument("--only-unvalidated", action="store_true")
     ap.add_argument("--unvalidated", action="store_true",
-                    help="also time the kernels that have not passed their first GPU parity run yet "
-                         "(K9 scaling, K10 DNG opcodes, K11 bad pixels, K12 table lookup, Panasonic V4); each leg "
-                         "checks bit-exactness against the oracle before timing")
+                    help="with --all-legs: include the post-decode kernels K9-K12 and Panasonic V4")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -276,10 +489,22 @@ def main():
         run_reference(args)
         return
 
-    import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    pin_rank_to_numa(local)
+
+    # ---------------- synthetic frames: this rank's share of the 256-frame batch ----------------
+    FT = args.total_frames
+    per = (FT + world - 1) // world
+    mine = list(range(rank * per, min(FT, (rank + 1) * per)))  # contiguous blocks of 256/N frames
+    ncpu = os.cpu_count() or 1
+    procs = args.gen_procs or max(1, min(len(mine), (ncpu - 2 * world) // world))
+    t_gen = time.perf_counter()
+    shm, cap, recs = gen_frames([SEED0 + i for i in mine], procs)
+    t_gen = time.perf_counter() - t_gen
+
+    import torch
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -290,125 +515,325 @@ def main():
     import rawspeed_b200 as rs
     from oracle import port, synth  # checker + synthetic inputs only
     ctx = rs.Context(local)
-
-    F = args.frames
     peak, peak_src = measured_peaks()
+    try:
+        batch = LJpegBatch(torch, rs, ctx, shm, cap, recs)
+        d_out = torch.zeros(batch.out_bytes, dtype=torch.uint8, device="cuda")
+        plan = batch.plan
+        in_b, out_b, pixels = plan.bytes()
+        run = lambda: plan.run((batch.d_in.data_ptr(), batch.in_bytes), d_out)  # noqa: E731
 
-    # ---------------- headline: 14-bit packed unpack ----------------
-    data, pitch = synth.packed_frame(W, H, BPS, seed=2 + rank)
+        # parity gate (not timed): every frame by checksum, first / last frame bit for bit
+        run()
+        st = plan.results()
+        wts = torch.from_numpy(_weights().view(np.int64)).cuda()
+        bit_exact = all(s == 0 for s, _ in st) and batch.check(torch, d_out, wts, sorted({0, batch.n - 1}))
+        if dist is not None:
+            t = torch.tensor([1 if bit_exact else 0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            bit_exact = bool(t.item())
+        if not bit_exact:
+            if rank == 0:
+                print(json.dumps({"error": "GPU output differs from the encoder's input; no number reported"}))
+            sys.exit(1)
+
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = ctx.launches
+        ms = time_steps(torch, run, args.steps, args.warmup, dist)
+        launches = ctx.launches - l0 - args.warmup * plan.launches
+        sus_n, sus_ms = 0, 0.0
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < args.sustain_s:
+            sus_ms += time_steps(torch, run, 10, 0, None)
+            sus_n += 10
+        clocks = sampler.stop() if rank == 0 else None
+        ms_per_step = ms / args.steps
+        total_pixels = FT * PIX
+        if dist is not None:
+            tp = torch.tensor([pixels], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tp)
+            total_pixels = float(tp.item())
+        value = total_pixels / (ms_per_step * 1e-3) / 1e6
+        kern = kernel_name(plan, batch.n)
+        ach = (in_b + out_b) / (ms_per_step * 1e-3) / 1e9  # this GPU; one plan run per step
+        roofline = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": in_b + out_b,
+                    "algorithmic_bytes_per_pixel": (in_b + out_b) / pixels,
+                    "read_only_frac": (in_b / (ms_per_step * 1e-3) / 1e9) / peak,
+                    "launches_per_step": plan.launches,
+                    "note": "in+out accounting of SURVEY 8(d): compressed bytes read once + 2 B/pixel written "
+                            "once; read_only_frac = compressed bytes only (north_star's wording) -- the 2 B/pixel "
+                            "of output cap it at ~0.34 when the in+out fraction is 1"}
+        tr = ncu_traffic(kern.split(" ")[0])
+        if tr:
+            roofline["traffic"] = tr["dram_bytes_per_frame"] * batch.n
+            roofline["traffic_source"] = tr["source"]
+        sustained = None
+        if sus_n:
+            sp = sus_ms / sus_n
+            sustained = {"ms_per_step": sp, "steps": sus_n, "value_this_gpu": pixels / (sp * 1e-3) / 1e6,
+                         "frac": (in_b + out_b) / (sp * 1e-3) / 1e9 / peak,
+                         "note": "same step back to back for %.1f s after the timed steps (rank-local)" % args.sustain_s}
+
+        # ---------------- e2e: host buffers through the C-ABI call ----------------
+        h_out = torch.empty(batch.out_bytes, dtype=torch.uint8, pin_memory=True)
+
+        def e2e_step():
+            plan.run_host(batch.h_in.numpy()[:batch.in_bytes], h_out.numpy())
+        e2e_steps = 3
+        ms_e = wall_steps(torch, e2e_step, e2e_steps, 1, dist)
+        e2e = {"value": total_pixels * e2e_steps / (ms_e * 1e-3) / 1e6, "unit": "MPixels/s",
+               "h2d_bytes_per_step": int(batch.in_bytes), "d2h_bytes_per_step": int(batch.out_bytes),
+               "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
+               "api": "rsb200_plan_run_host: pinned host buffers; upload, decode and download of consecutive "
+                      "groups of tiles (~8 MB of pixels) overlap on three streams"}
+        got = d_out.cpu().numpy()
+        e2e["bit_exact"] = bool(np.array_equal(h_out.numpy()[:H * batch.out_pitch], got[:H * batch.out_pitch])) and \
+            bool(np.array_equal(h_out.numpy()[(batch.n - 1) * batch.ob:(batch.n - 1) * batch.ob + H * batch.out_pitch],
+                                got[(batch.n - 1) * batch.ob:(batch.n - 1) * batch.ob + H * batch.out_pitch]))
+        del got
+
+        gather = None
+        if dist is not None:
+            gather = bench_gather_abi(torch, dist, rs, ctx, batch, world, rank, args, total_pixels)
+        del h_out
+
+        single = None
+        others = {}
+        if rank == 0 and not args.skip_single:
+            single = bench_single_frame(torch, rs, ctx, port, synth, args, shm, cap, recs, peak, peak_src)
+        if not args.skip_others:
+            if args.all_legs:
+                others = bench_others(torch, rs, ctx, port, synth, args, dist, peak)
+            elif rank == 0 or dist is not None:
+                others = bench_core_others(torch, rs, ctx, port, synth, args, dist, peak)
+
+        if rank == 0:
+            cpu = None
+            if not args.skip_cpu:
+                nc = max(1, min(args.cpu_frames, len(recs)))
+                cpu = cpu_reference_ljpeg(shm, cap, recs[:nc])
+                c1 = cpu_reference_c1()
+                if c1:
+                    others["configs[0] 12-bit packed 4000x3000, CPU only"] = c1
+            line = {
+                "metric": "MPixels/s decoded (bit-exact)", "value": value, "unit": "MPixels/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+                "config": {"workload": "configs[4]: %d-frame batch of configs[2] frames (DNG lossless-JPEG predictor 1, "
+                                       "14-bit 8256x5504 = 45 MP, 726 tiles of 256x256 each, distinct frames "
+                                       "seeds %d..%d), sharded %d frames per GPU over %d GPU(s), one plan run per step"
+                                       % (FT, SEED0, SEED0 + FT - 1, per, world),
+                           "frames_total": FT, "frames_per_gpu": per,
+                           "bytes_per_step_per_gpu": in_b + out_b,
+                           "compressed_bytes_per_pixel": in_b / pixels,
+                           "l2": "inputs+outputs of one step (%.1f GB per GPU) exceed the 126 MB L2; no flush needed"
+                                 % ((in_b + out_b) / 1e9),
+                           "parallelism": "frames sharded across ranks (contiguous blocks of 256/N), no data-path "
+                                          "collective in `value`; the NVLink output gather is `gather`",
+                           "frame_synthesis_s": round(t_gen, 1)},
+                "bit_exact": bit_exact, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks, "sustained": sustained,
+                "single_frame": single, "others": others,
+            }
+            if gather:
+                line["gather"] = gather
+            print(json.dumps(line))
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+    finally:
+        shm.close()
+        shm.unlink()
+
+
+def kernel_name(plan, nframes):
+    if plan.launches == 1:
+        return "k2_tile_kernel<%s> (one CTA per tile)" % os.environ.get("RSB200_TILE_R", "1")
+    return "k2_clean_kernel + k2_thread_kernel (one thread per tile)"
+
+
+def pin_rank_to_numa(local):
+    """GPUs 0-3 hang off NUMA node 0, GPUs 4-7 off node 1 on the 8-GPU boxes (SCALE_r01.json
+    topology): keep this rank's threads, and therefore its pinned staging buffers (first touch), on
+    the cores of its GPU's node."""
+    try:
+        ncpu = os.cpu_count() or 1
+        if ncpu < 64 or not hasattr(os, "sched_setaffinity"):
+            return
+        half, q = ncpu // 2, ncpu // 4
+        node = 0 if local < 4 else 1
+        cores = list(range(node * q, (node + 1) * q)) + list(range(half + node * q, half + (node + 1) * q))
+        os.sched_setaffinity(0, cores)
+    except Exception:
+        pass
+
+
+def bench_gather_abi(torch, dist, rs, ctx, batch, world, rank, args, total_pixels):
+    """north_star's NVLink output gather through the C ABI (rsb200_plan_run_gather): the slab of a
+    group of tiles travels on the communicator's stream while the next groups decode.  Two
+    modes: every rank gets everything / only the consumer GPU (rank 0) does."""
+    uid = [rs.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    comm = rs.Comm(ctx, uid[0], world, rank)
+    slab = batch.out_bytes
+    d_all = torch.zeros(world * slab, dtype=torch.uint8, device="cuda")
+    out = {"what": "decode + gather of the uint16 images over NVLink (rsb200_plan_run_gather: per group of "
+                   "tiles, grouped ncclBroadcast / ncclSend+ncclRecv on a side stream, overlapping the decode)",
+           "gathered_bytes_total": int(world * slab)}
+    for name, mode in (("to_all_ranks", rs.GATHER_ALL), ("to_rank0", rs.GATHER_ROOT)):
+        def step():
+            batch.plan.run_gather(comm, (batch.d_in.data_ptr(), batch.in_bytes), d_all, slab, mode, 0)
+        n = 3
+        ms = time_steps(torch, step, n, 1, dist) / n
+        recv = (world - 1) * slab
+        out[name] = {"ms_per_step": ms, "MPixels/s": total_pixels / (ms * 1e-3) / 1e6,
+                     "received_bytes_busiest_gpu": int(recv),
+                     "ingress_GBps_busiest_gpu": recv / (ms * 1e-3) / 1e9}
+    # parity of the gathered data: slab r of rank 0 == what rank r decoded (checksum of the first frame)
+    torch.cuda.synchronize()
+    mine = d_all[rank * slab:rank * slab + 1024 * 1024].to(torch.int64).sum()
+    sums = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(sums, mine)
+    ok = True
+    if rank == 0:
+        for r in range(world):
+            ok = ok and int(d_all[r * slab:r * slab + 1024 * 1024].to(torch.int64).sum().item()) == int(sums[r].item())
+    out["gathered_matches_the_owners"] = bool(ok)
+    out["bound"] = ("the consumer GPU receives (N-1)/N of %.1f GB; at the 900 GB/s per direction of NVLink 5 that "
+                    "alone is %.1f ms" % (world * slab / 1e9, (world - 1) * slab / 900e9 * 1e3))
+    comm.close()
+    del d_all
+    return out
+
+
+def bench_single_frame(torch, rs, ctx, port, synth, args, shm, cap, recs, peak, peak_src):
+    """BASELINE configs[2]: ONE 8256x5504 DNG LJPEG frame (726 tiles): device-timed decode,
+    roofline, host-buffer runs (pinned / pageable) and the drop-in call of the host mirror."""
+    from rawspeed_b200 import host
+    b1 = LJpegBatch(torch, rs, ctx, shm, cap, recs[:1])
+    d_out = torch.zeros(b1.out_bytes, dtype=torch.uint8, device="cuda")
+    plan = b1.plan
+    plan.run((b1.d_in.data_ptr(), b1.in_bytes), d_out)
+    st = plan.results()
+    img = synth.image_model(W, H, recs[0][0])
+    got = d_out.cpu().numpy().view(np.uint16).reshape(H, b1.out_pitch // 2)
+    exact = bool(np.array_equal(got[:, :W], img)) and all(s == 0 for s, _ in st)
+    # the launch is shorter than the L2 flush would be meaningful for: flush L2 between runs by
+    # writing a 256 MB buffer (not timed: CUDA events around the decode only)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for i in range(3 + 20):
+        flush.fill_(i & 0xFF)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.run((b1.d_in.data_ptr(), b1.in_bytes), d_out)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    ms_warm = time_steps(torch, lambda: plan.run((b1.d_in.data_ptr(), b1.in_bytes), d_out), 20, 3, None) / 20
+    in_b, out_b, pixels = plan.bytes()
+    ent = {"workload": "configs[2]: DNG lossless-JPEG predictor 1, 8256x5504, 726 tiles 256x256, ONE frame per launch",
+           "MPixels/s": pixels / (ms * 1e-3) / 1e6, "ms_per_frame": ms, "bit_exact": exact,
+           "timing": "CUDA events around each launch, L2 flushed (256 MB write) between launches, mean of 20",
+           "ms_per_frame_back_to_back": ms_warm,
+           "kernel": kernel_name(plan, 1), "launches_per_frame": plan.launches,
+           "compressed_bytes_per_pixel": in_b / pixels,
+           "roofline": {"bound": "hbm", "achieved": (in_b + out_b) / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": (in_b + out_b) / (ms * 1e-3) / 1e9 / peak,
+                        "read_only_frac": in_b / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src}}
+    del flush
+    # host buffers through the C ABI: pinned and pageable
+    h_out = torch.empty(b1.out_bytes, dtype=torch.uint8, pin_memory=True)
+    n = 5
+    ms_p = wall_steps(torch, lambda: plan.run_host(b1.h_in.numpy()[:b1.in_bytes], h_out.numpy()), n, 2) / n
+    ok_p = bool(np.array_equal(h_out.numpy()[:H * b1.out_pitch].view(np.uint16).reshape(H, -1)[:, :W], img))
+    pg_in = np.array(b1.h_in.numpy()[:b1.in_bytes])
+    pg_out = np.zeros(b1.out_bytes, dtype=np.uint8)
+    ms_g = wall_steps(torch, lambda: plan.run_host(pg_in, pg_out), n, 2) / n
+    ent["e2e"] = {"value": pixels / (ms_p * 1e-3) / 1e6, "unit": "MPixels/s", "ms_per_frame": ms_p,
+                  "h2d_bytes_per_step": int(b1.in_bytes), "d2h_bytes_per_step": int(b1.out_bytes),
+                  "bit_exact": ok_p, "api": "rsb200_plan_run_host, pinned host buffers, pipelined groups",
+                  "pageable": {"value": pixels / (ms_g * 1e-3) / 1e6, "ms_per_frame": ms_g}}
+    # the drop-in call: the host mirror's AbstractDngDecompressor::decompress() -- marker walk of
+    # every tile, table validation, plan, upload, decode, download, per-tile results
+    r = recs[0]
+    blob = np.array(b1.h_in.numpy()[:r[1]])
+    himg = port.new_image(W, H)
+    host.dng_decompress(blob, r[6], r[7], himg, W, 1, 256, 256, 7)
+    ok_m = bool(np.array_equal(himg[:, :W], img))
+    ms_m = wall_steps(torch, lambda: host.dng_decompress(blob, r[6], r[7], himg, W, 1, 256, 256, 7), n, 1) / n
+    ent["e2e_host_mirror"] = {"value": PIX / (ms_m * 1e-3) / 1e6, "unit": "MPixels/s", "ms_per_frame": ms_m,
+                              "bit_exact": ok_m,
+                              "api": "rawspeed_b200::AbstractDngDecompressor::decompress() (C++ host mirror, pageable "
+                                     "RawImage): parse + plan + H2D + decode + D2H + results, per call"}
+    return ent
+
+
+def bench_core_others(torch, rs, ctx, port, synth, args, dist, peak):
+    """The other BASELINE configs, short: configs[1] (14-bit packed unpack, 8 frames per launch)
+    and configs[3] (CR2 6720x4480, 3 slices)."""
+    out = {}
+    F = args.frames
+    data, pitch = synth.packed_frame(W, H, BPS, seed=2)
     out_pitch = rs.image_pitch(W)
-    in_fb = align(pitch * H)
-    out_fb = align(out_pitch * H)
-    h_in = torch.empty(F * in_fb, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(F * out_fb, dtype=torch.uint8).pin_memory()
-    hv = h_in.numpy()
+    in_fb, out_fb = align(pitch * H), align(out_pitch * H)
+    d_in = torch.zeros(F * in_fb, dtype=torch.uint8, device="cuda")
+    base = torch.from_numpy(data).cuda()
     for f in range(F):
-        # distinct frames: frame f = frame 0 with its bytes rotated by f
-        hv[f * in_fb:f * in_fb + pitch * H] = np.roll(data, f * 7919)
-    d_in = h_in.cuda()
+        d_in[f * in_fb:f * in_fb + pitch * H] = torch.roll(base, f * 7919)
     d_out = torch.zeros(F * out_fb, dtype=torch.uint8, device="cuda")
     plan = rs.unpack_plan(ctx, unpack_jobs(rs, F, in_fb, out_fb, pitch, out_pitch, rs.MSB))
-    in_b, out_b, pixels = plan.bytes()
-
-    # parity gate (not timed): frame 0 and the last frame against the oracle
     plan.run(d_in, d_out)
-    torch.cuda.synchronize()
-    got = d_out.cpu().numpy()
-    bit_exact = True
-    for f in (0, F - 1):
-        want = port.new_image(W, H)
-        port.unpack(hv[f * in_fb:f * in_fb + pitch * H], want, W, 1, (0, 0, W, H), pitch, BPS, port.MSB)
-        g = got[f * out_fb:f * out_fb + out_pitch * H].view(np.uint16).reshape(H, out_pitch // 2)
-        bit_exact &= bool(np.array_equal(g[:, :W], want[:, :W]))
-    if not bit_exact:
-        print(json.dumps({"error": "GPU output differs from the oracle; no number reported"}))
-        sys.exit(1)
-
-    # Timed region first: W warm-up + K timed steps straight away (the kernel timed
-    # alone -> compared with the burst peak).  nvidia-smi (100 ms period) cannot
-    # resolve a few-ms region, so the sampler runs from before the warm-up until
-    # the end of a follow-on sustained loop of the SAME step (--sustain-s seconds,
-    # timed separately and reported as `sustained`); only samples taken under load
-    # count for the median.
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = ctx.launches
-    ms = time_steps(torch, lambda: plan.run(d_in, d_out), args.steps, args.warmup, dist)
-    launches = ctx.launches - l0 - args.warmup * plan.launches
-    sus_n, sus_ms = 0, 0.0
-    t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < args.sustain_s:
-        sus_ms += time_steps(torch, lambda: plan.run(d_in, d_out), 100, 0, None)
-        sus_n += 100
-    clocks = sampler.stop() if rank == 0 else None
-
-    ms_per_step = ms / args.steps
-    value = world * pixels * args.steps / (ms * 1e-3) / 1e6
-    ach = (in_b + out_b) / (ms_per_step * 1e-3) / 1e9  # per GPU, one launch per step
-    roofline = {"bound": "hbm", "kernel": "unpack_fast_kernel<14,MSB>", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": in_b + out_b,
-                "read_only_frac": (in_b / (ms_per_step * 1e-3) / 1e9) / peak,
-                "launches_per_step": plan.launches}
-    tr = ncu_traffic("unpack_fast_kernel<14,MSB>")
-    if tr:
-        roofline["traffic"] = tr["dram_bytes_per_frame"] * F
-        roofline["traffic_source"] = tr["source"]
-    sustained = None
-    if sus_n:
-        sp = sus_ms / sus_n
-        sustained = {"ms_per_step": sp, "steps": sus_n,
-                     "value": world * pixels / (sp * 1e-3) / 1e6,
-                     "achieved": (in_b + out_b) / (sp * 1e-3) / 1e9,
-                     "frac": (in_b + out_b) / (sp * 1e-3) / 1e9 / peak,
-                     "note": "same step back to back for %.1f s after the timed steps (rank-local "
-                             "timing); the board reaches its power cap here, so this is the "
-                             "sustained figure against the same burst peak" % args.sustain_s}
-
-    # ---------------- e2e: host buffers through the C-ABI call ----------------
-    def e2e_step():
-        plan.run_host(h_in.numpy(), h_out.numpy())
-    e2e_steps = max(3, min(args.steps, 5))
-    ms_e = wall_steps(torch, e2e_step, e2e_steps, 1, dist)
-    e2e = {"value": world * pixels * e2e_steps / (ms_e * 1e-3) / 1e6, "unit": "MPixels/s",
-           "h2d_bytes_per_step": int(F * in_fb), "d2h_bytes_per_step": int(F * out_fb),
-           "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
-           "api": "rsb200_plan_run_host (pinned host buffers, H2D + kernel + D2H per step)"}
-    ok = np.array_equal(h_out.numpy()[:out_pitch * H], got[:out_pitch * H])
-    e2e["bit_exact"] = bool(ok)
-
-    others = {}
-    if not args.skip_others:
-        others = bench_others(torch, rs, ctx, port, synth, args, dist, peak)
-
-    gather = None
-    if dist is not None:
-        gather = bench_gather(torch, dist, d_out, world, rank, plan, d_in, args, F, out_fb)
-
-    if rank == 0:
-        cpu = None if args.skip_cpu else cpu_reference_unpack()
-        line = {
-            "metric": "MPixels/s decoded (bit-exact)", "value": value, "unit": "MPixels/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": "configs[1]: 14-bit packed (MSB) unpack, 8256x5504 (45 MP), "
-                                   "%d frames per step per GPU" % F,
-                       "frames_per_step_per_gpu": F, "bytes_per_step_per_gpu": in_b + out_b,
-                       "l2": "inputs+outputs of one step (%.2f GB) exceed the 126 MB L2; no flush "
-                             "needed" % ((in_b + out_b) / 1e9),
-                       "parallelism": "frames sharded across ranks, no data-path collective"},
-            "bit_exact": bit_exact, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "sustained": sustained,
-            "others": others,
-        }
-        if gather:
-            line["gather"] = gather
-        print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    want = port.new_image(W, H)
+    port.unpack(data, want, W, 1, (0, 0, W, H), pitch, BPS, port.MSB)
+    got = d_out[:out_pitch * H].cpu().numpy().view(np.uint16).reshape(H, out_pitch // 2)
+    exact = bool(np.array_equal(got[:, :W], want[:, :W]))
+    n = max(5, min(args.steps, 20))
+    ms = time_steps(torch, lambda: plan.run(d_in, d_out), n, 3, dist) / n
+    in_b, out_b, pixels = plan.bytes()
+    out["configs[1] 14-bit packed (MSB) unpack 8256x5504, %d frames per launch" % F] = {
+        "MPixels/s": pixels / (ms * 1e-3) / 1e6, "ms_per_step": ms, "bit_exact": exact,
+        "kernel": "unpack_fast_kernel<14,MSB>", "achieved_GBps": (in_b + out_b) / (ms * 1e-3) / 1e9,
+        "roofline_frac": (in_b + out_b) / (ms * 1e-3) / 1e9 / peak}
+    del plan, d_in, d_out, base
+    from helpers import TableSet
+    from test_gpu_cr2 import cr2_job
+    cw, ch = 6720, 4480
+    cimg = port.new_image(cw, ch)
+    cimg[:, :cw] = synth.image_model(cw, ch, 4)
+    hts = synth.default_tables(2)
+    fmt, frame = (2, 1, 1), (3360, 4480)
+    blob = port.cr2_encode(cimg, cw, fmt, frame, (3, 2240, 2240), 14, hts, [0, 1])
+    ts = TableSet()
+    job = cr2_job(blob, cw, ch, fmt, (3, 2240, 2240), cimg.shape[1] * 2, ts)
+    plan = rs.cr2_plan(ctx, ts.tabs, [job])
+    d_in = torch.zeros(blob.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[:blob.size] = torch.from_numpy(blob)
+    d_out = torch.zeros(cimg.size * 2, dtype=torch.uint8, device="cuda")
+    plan.run((d_in.data_ptr(), blob.size), d_out)
+    res = plan.results()
+    got = d_out.cpu().numpy().view(np.uint16).reshape(cimg.shape)
+    exact = bool(np.array_equal(got[:, :cw], cimg[:, :cw])) and res[0][0] == 0
+    ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), blob.size), d_out), 5, 2, dist) / 5
+    ent = {"MPixels/s": cw * ch / (ms * 1e-3) / 1e6, "ms_per_frame": ms, "bit_exact": exact,
+           "kernels": "k2_range_count/verify/diffs + k3_column/row"}
+    if not args.skip_cpu and int(os.environ.get("RANK", "0")) == 0:
+        import oracle
+        if oracle.HAVE_REF:
+            tmp = port.new_image(cw, ch)
+            msr = min(oracle.ref.cr2_ljpeg_decode(blob, tmp, cw, (3, 2240, 2240), reps=1) for _ in range(2))
+            ent["cpu_reference"] = {"kind": "reference", "cores": 1, "MPixels/s": cw * ch / (msr * 1e-3) / 1e6,
+                                    "sample": "Cr2LJpegDecoder::decode (single threaded by design)"}
+    out["configs[3] CR2 6720x4480 3 slices <2,1,1>"] = ent
+    return out
 
 
 def bench_gather(torch, dist, d_out, world, rank, plan, d_in, args, frames, out_fb):

@@ -567,6 +567,38 @@ int rsb200_plan_bytes(const rsb200_plan* plan, uint64_t* in_bytes,
 int rsb200_plan_launches(const rsb200_plan* plan);
 void rsb200_plan_destroy(rsb200_plan* plan);
 
+/* ------------------------------------------------------------------ */
+/* Multi-GPU: frames are sharded across the GPUs of one box, one process */
+/* per GPU; the only exchange is the gather of the decoded   */
+/* uint16 images over NVLink.  The reference has no counterpart (its     */
+/* fan-out is OpenMP over tiles, AbstractDngDecompressor.cpp:240-252);   */
+/* this is the `rsgpu_gather` of SURVEY 8b.  NCCL is taken from the      */
+/* process at run time (dlopen of libnccl.so.2, the copy that is already  */
+/* loaded if there is one); without it these calls return RSB200_ERR_CUDA.*/
+/* ------------------------------------------------------------------ */
+typedef struct rsb200_comm rsb200_comm;
+enum {
+  RSB200_GATHER_NONE = 0, /* decode only: every rank keeps its slab               */
+  RSB200_GATHER_ALL = 1,  /* every rank ends up with every slab                   */
+  RSB200_GATHER_ROOT = 2  /* only `root` does (the consumer GPU)                  */
+};
+/* Rank 0 makes the 128-byte id, the caller ships it to the other ranks (any
+ * side channel), then every rank creates its communicator. */
+int rsb200_comm_unique_id(uint8_t id[128]);
+int rsb200_comm_create(rsb200_ctx* ctx, const uint8_t id[128], int world, int rank,
+                       rsb200_comm** comm);
+void rsb200_comm_destroy(rsb200_comm* comm);
+/* Decode + gather.  d_out_all holds `world` slabs of slab_bytes each; this rank
+ * decodes into slab `rank` (the plan's output offsets are relative to the slab)
+ * and, as soon as a group of segments (~8 MB of pixels) has been decoded, that
+ * part of the slab travels on the communicator's own stream, so the transfer
+ * overlaps the decode of the following groups.  Every rank must run a plan of
+ * the same geometry (same output spans).  `stream` orders the whole call: when
+ * work queued behind it on `stream` runs, decode and gather are complete. */
+int rsb200_plan_run_gather(rsb200_plan* plan, rsb200_comm* comm, const void* d_in,
+                           size_t in_bytes, void* d_out_all, size_t slab_bytes, int mode,
+                           int root, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

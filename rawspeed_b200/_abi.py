@@ -161,6 +161,7 @@ EXPORTS = [
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
     "rsb200_plan_launches", "rsb200_plan_destroy",
+    "rsb200_comm_unique_id", "rsb200_comm_create", "rsb200_comm_destroy", "rsb200_plan_run_gather",
 ]
 
 _lib = None
@@ -225,5 +226,10 @@ def load():
     L.rsb200_plan_launches.argtypes = [vp]
     L.rsb200_plan_destroy.argtypes = [vp]
     L.rsb200_plan_destroy.restype = None
+    L.rsb200_comm_unique_id.argtypes = [vp]
+    L.rsb200_comm_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+    L.rsb200_comm_destroy.argtypes = [vp]
+    L.rsb200_comm_destroy.restype = None
+    L.rsb200_plan_run_gather.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, i32, i32, vp]
     _lib = L
     return L

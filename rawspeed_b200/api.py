@@ -119,6 +119,21 @@ class Plan:
         rc = self.ctx._lib.rsb200_plan_run(self.h, ip, ib, op, ob, C.c_void_p(stream))
         self.ctx.check(rc)
 
+    def run_gather(self, comm, d_in, d_out_all, slab_bytes, mode, root=0, stream=None):
+        """Decode into this rank's slab of d_out_all and gather the slabs over NVLink
+        (rsb200_plan_run_gather: the transfer of a group of segments overlaps the decode of the
+        following ones).  mode: GATHER_NONE / GATHER_ALL / GATHER_ROOT.  Asynchronous."""
+        ip, ib = _ptr_bytes(d_in)
+        op, _ = _ptr_bytes(d_out_all)
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        elif hasattr(stream, "cuda_stream"):
+            stream = stream.cuda_stream
+        rc = self.ctx._lib.rsb200_plan_run_gather(self.h, comm.h, ip, ib, op, slab_bytes, mode, root,
+                                                  C.c_void_p(stream))
+        self.ctx.check(rc)
+
     def run_host(self, in_np, out_np, partial=False):
         """Host buffers in, host buffers out (H2D + kernels + D2H, synchronous)."""
         assert in_np.flags.c_contiguous and out_np.flags.c_contiguous
@@ -151,6 +166,37 @@ class Plan:
     @property
     def launches(self):
         return int(self.ctx._lib.rsb200_plan_launches(self.h))
+
+
+GATHER_NONE, GATHER_ALL, GATHER_ROOT = 0, 1, 2
+
+
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 makes it, the caller ships it to the other ranks)."""
+    from . import _abi
+    buf = (C.c_uint8 * 128)()
+    if _abi.load().rsb200_comm_unique_id(buf) != 0:
+        raise RuntimeError("rsb200_comm_unique_id failed: NCCL (libnccl.so.2) not available")
+    return bytes(buf)
+
+
+class Comm:
+    """One rank's communicator for the output gather (rsb200_comm_create)."""
+
+    def __init__(self, ctx, uid, world, rank):
+        self.ctx = ctx
+        self.world, self.rank = world, rank
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        ctx.check(ctx._lib.rsb200_comm_create(ctx.h, buf, world, rank, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx._lib.rsb200_comm_destroy(self.h)
+        self.h = None
+
+    __del__ = close
 
 
 def unpack_plan(ctx, jobs):

@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     dev_src = _sources("", (".cu", ".cuh")) + [hdr]
     if force or _newer(LIB, dev_src):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            "-o", LIB, os.path.join(HERE, "csrc", "rsb200.cu")]
+            "-o", LIB, os.path.join(HERE, "csrc", "rsb200.cu"), "-ldl"]
         subprocess.check_call(cmd, cwd=ROOT)
     host_src = _sources("host", (".cpp", ".h"))
     if host_src and (force or _newer(HOST_LIB, host_src + [hdr, LIB])):

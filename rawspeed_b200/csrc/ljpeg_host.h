@@ -106,10 +106,16 @@ inline bool tile_eligible(const DevScan& d, int min_rs) {
 inline void tile_params(const DevScan& d, int npiece_max, int dcap, int preroll_override,
                         uint32_t& npieces, uint32_t& preroll) {
   const double bits = d.n_samples ? 8.0 * (double)d.in_size / (double)d.n_samples : 8.0;
-  double np = 0.85 * (double)dcap * bits / 8.0 / 64.0;
+  double np = 0.90 * (double)dcap * bits / 8.0 / 64.0;
   np = std::min(np, (double)npiece_max);
   np = std::max(np, 16.0);
   npieces = (uint32_t)np;
+  // equal chunks: the same number of chunks, none of them nearly empty
+  {
+    const uint32_t total = ((uint32_t)(d.in_offset & 15ull) + d.in_size + 63u) / 64u;
+    const uint32_t nch = std::max(1u, (total + npieces - 1) / npieces);
+    npieces = std::max(16u, (total + nch - 1) / nch);
+  }
   const uint32_t sub_bits = std::max(288u, npieces * 512u / 256u);
   uint32_t pre = (uint32_t)std::min(1024.0, std::max(128.0, 44.0 * bits));
   pre = (pre + 31u) & ~31u;

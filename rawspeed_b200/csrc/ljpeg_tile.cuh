@@ -51,10 +51,19 @@ constexpr int TL_RBMAX = 128;  // row starts per predictor batch
 constexpr uint32_t TL_NOPOS = 0xFFFFFFFFu;
 
 template <int R> struct TileGeom {
-  static constexpr int NPIECE = 224 * R;             // pieces per chunk (at most)
+#ifndef RSB200_TILE_NPIECE1
+#define RSB200_TILE_NPIECE1 208
+#endif
+#ifndef RSB200_TILE_DCAP1
+#define RSB200_TILE_DCAP1 15360
+#endif
+  // R = 1: 55 KB of shared memory -> four CTAs per SM (measured best: r2_run4; 168 / 11520 / 5 CTAs
+  // keeps all 726 tiles of a 45 MP frame resident at once but is slower); R = 2: 105 KB -> two
+  // CTAs per SM with subsequences twice as long
+  static constexpr int NPIECE = R == 1 ? RSB200_TILE_NPIECE1 : 448; // pieces per chunk (at most)
   static constexpr int RAWMAX = NPIECE * TL_PIECE;   // raw bytes per chunk (at most)
   static constexpr int UBBYTES = RAWMAX + 128;       // carried tail + chunk + zero extension + slack
-  static constexpr int DCAP = 16000 * R;             // samples per predictor batch (at most)
+  static constexpr int DCAP = R == 1 ? RSB200_TILE_DCAP1 : 32000; // samples per predictor batch (at most)
   static constexpr int UPT = ((DCAP / 8 + TL_NT - 1) / TL_NT) | 1; // units per thread (odd), at most
   static constexpr int MIN_RS = 8 * UPT;             // a thread's units hold at most one row start
 };
@@ -90,6 +99,9 @@ template <int R> struct alignas(128) TileShared {
   uint32_t mpos;
   uint32_t bad_code;
   uint32_t nlist;
+  uint32_t tail_raw_next; // B: raw offset of the source of the next chunk's ub byte 0
+  uint32_t prev_ff_next;  // B: the chunk's last raw byte is an FF inside the segment
+  uint32_t coop_n[3];     // B: byte counts of the edge pieces / the piece the marker cuts
   uint32_t rstat;   // result of tl_replay: 0 fine, 2 the reference would have thrown
   uint32_t rcons;   // ... and its getStreamPosition()
   uint32_t exitpos[TL_NT];         // C/D: exit positions of the subsequences
@@ -99,6 +111,7 @@ template <int R> struct alignas(128) TileShared {
   uint32_t rowbase[TL_RBMAX + 1][2];
   alignas(16) uint32_t ub[G::UBBYTES / 4];    // clean big-endian words
   alignas(16) uint16_t dbuf[G::DCAP + 16];    // differences; A/B: raw staging (RAWMAX + 16 bytes)
+  alignas(16) uint8_t len8[1 << LUT_BITS];    // bits consumed by the symbol at the top of an 11-bit window (0: slow path)
   DevTable tab;
 };
 
@@ -216,12 +229,94 @@ __device__ __forceinline__ bool tl_marker2(const TileStream& st, uint32_t r) {
   return r > st.skew && r < st.limit && st.gbase[r] != 0u && st.gbase[r - 1] == 0xFFu;
 }
 
+// Optional per-phase cycle accounting (profiling builds only: -DRSB200_PHASE_TIMING).
+#if defined(RSB200_PHASE_TIMING) && !defined(RSB200_EMU)
+__device__ unsigned long long g_tile_phase_cycles[16];
+#define TL_TICK(i)                                                                 \
+  do {                                                                             \
+    if (threadIdx.x == 0) {                                                        \
+      const long long t_now = clock64();                                           \
+      atomicAdd(&g_tile_phase_cycles[i], (unsigned long long)(t_now - t_phase));   \
+      t_phase = t_now;                                                             \
+    }                                                                              \
+  } while (0)
+#define TL_TICK_INIT long long t_phase = clock64()
+#define TL_TICK_ARG , long long& t_phase
+#define TL_TICK_PASS , t_phase
+#else
+#define TL_TICK(i) do { } while (0)
+#define TL_TICK_INIT do { } while (0)
+#define TL_TICK_ARG
+#define TL_TICK_PASS
+#endif
+
 // ================= B: unstuff one raw chunk (staged in sh.dbuf) into sh.ub =================
+// Byte q of the chunk (raw offset cbase + q from gbase), read from the staging buffer; the byte in
+// front of the chunk is only known as "was it FF" (carry).
+template <int R>
+__device__ __forceinline__ uint32_t tl_stage_byte(uint32_t sb_raw, uint32_t q) {
+  return lds_u8<0>(sb_raw + q);
+}
+
+// One warp looks at one 64-byte piece, two bytes per lane: which bytes are data (w.r.t. the end
+// `lim`, a raw offset from gbase), and where does a marker start (first FF followed by a non-zero
+// byte inside the segment; the chunk's last piece also answers for the look-ahead byte).
+// Returns the two keep flags of this lane; *mk = chunk-relative offset of the first marker whose
+// second byte lies in [p0, p0 + 64 (+1)) or TL_NOPOS.
+template <int R>
+__device__ __forceinline__ uint32_t tl_piece_flags(const TileStream& st, uint32_t sb_raw,
+                                                   uint32_t cbase, uint32_t pi, uint32_t prev_ff,
+                                                   uint32_t lim, uint32_t* mk) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t q0 = pi * TL_PIECE + 2u * lane;
+  const uint32_t pm = q0 > 0 ? tl_stage_byte<R>(sb_raw, q0 - 1) : (prev_ff ? 0xFFu : 0u);
+  const uint32_t c0 = tl_stage_byte<R>(sb_raw, q0), c1 = tl_stage_byte<R>(sb_raw, q0 + 1);
+  const uint32_t r0 = cbase + q0, r1 = r0 + 1;
+  // pairing needs the FF inside the segment: r - 1 >= skew
+  const bool k0 = r0 >= st.skew && r0 < lim && !(c0 == 0u && pm == 0xFFu && r0 > st.skew);
+  const bool k1 = r1 >= st.skew && r1 < lim && !(c1 == 0u && c0 == 0xFFu && r1 > st.skew);
+  bool m0 = r0 > st.skew && r0 < st.limit && c0 != 0u && pm == 0xFFu; // marker at q0 - 1
+  bool m1 = r1 > st.skew && r1 < st.limit && c1 != 0u && c0 == 0xFFu; // marker at q0
+  uint32_t first = TL_NOPOS;
+  const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, m0), b1 = __ballot_sync(0xFFFFFFFFu, m1);
+  if (b0 | b1) {
+    const uint32_t l0 = b0 ? (uint32_t)__ffs(b0) - 1u : 64u, l1 = b1 ? (uint32_t)__ffs(b1) - 1u : 64u;
+    // marker offsets: from m0 of lane l -> piece byte 2l - 1; from m1 of lane l -> 2l
+    const uint32_t o0 = b0 ? 2u * l0 : 0xFFFFu, o1 = b1 ? 2u * l1 + 1u : 0xFFFFu; // (+1 biased)
+    first = pi * TL_PIECE + min(o0, o1) - 1u; // chunk relative (wraps to -1 only for q = 0: see caller)
+  } else if (pi + 1 == st.npieces) {
+    // look-ahead byte behind the chunk
+    const uint32_t qa = st.npieces * TL_PIECE, ra = cbase + qa;
+    if (ra > st.skew && ra < st.limit && tl_stage_byte<R>(sb_raw, qa) != 0u &&
+        tl_stage_byte<R>(sb_raw, qa - 1) == 0xFFu)
+      first = qa - 1u;
+  }
+  *mk = first;
+  return (k0 ? 1u : 0u) | (k1 ? 2u : 0u);
+}
+
+// keep flags only (pass 2b)
+template <int R>
+__device__ __forceinline__ uint32_t tl_piece_keep(const TileStream& st, uint32_t sb_raw,
+                                                  uint32_t cbase, uint32_t pi, uint32_t prev_ff,
+                                                  uint32_t lim, uint32_t* c01) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t q0 = pi * TL_PIECE + 2u * lane;
+  const uint32_t pm = q0 > 0 ? tl_stage_byte<R>(sb_raw, q0 - 1) : (prev_ff ? 0xFFu : 0u);
+  const uint32_t c0 = tl_stage_byte<R>(sb_raw, q0), c1 = tl_stage_byte<R>(sb_raw, q0 + 1);
+  const uint32_t r0 = cbase + q0, r1 = r0 + 1;
+  const bool k0 = r0 >= st.skew && r0 < lim && !(c0 == 0u && pm == 0xFFu && r0 > st.skew);
+  const bool k1 = r1 >= st.skew && r1 < lim && !(c1 == 0u && c0 == 0xFFu && r1 > st.skew);
+  *c01 = c0 | (c1 << 8);
+  return (k0 ? 1u : 0u) | (k1 ? 2u : 0u);
+}
+
 template <int R>
 __device__ __forceinline__ TileChunk tl_unstuff(TileShared<R>& sh, const TileStream& st,
-                                                const TileCarry& cy, uint32_t chunk) {
+                                                const TileCarry& cy, uint32_t chunk TL_TICK_ARG) {
   using G = TileGeom<R>;
   const int tid = threadIdx.x;
+  const uint32_t lane = (uint32_t)tid & 31u, wid = (uint32_t)tid >> 5;
   const uint32_t sb_raw = smem_u32(sh.dbuf);
   const uint32_t sb_ub = smem_u32(sh.ub);
   const uint32_t cbase = chunk * st.chunk_raw; // raw offset (from gbase) of the chunk
@@ -229,23 +324,28 @@ __device__ __forceinline__ TileChunk tl_unstuff(TileShared<R>& sh, const TileStr
   if (tid == 0) {
     sh.mpos = TL_NOPOS;
     sh.nlist = 0;
+    sh.tail_raw_next = TL_NOPOS;
   }
+  // pieces that are not fully inside the segment (its first and its last one): at most two per
+  // chunk, known from the geometry alone
+  const bool has_edge = chunk == 0 || cbase + st.chunk_raw + 1u > st.limit;
   // ---- pass 1: classify my pieces; regular = 64 data bytes, nothing dropped ----
   uint32_t w[R][16];
   uint32_t n_emit[R];
-  bool regular[R], active[R];
-  uint32_t m2any = 0;
+  bool regular[R], active[R], edge[R];
+  uint32_t mk_mine = TL_NOPOS; // chunk-relative offset of the first marker my pieces see
 #pragma unroll
   for (int rr = 0; rr < R; ++rr) {
     const uint32_t pi = (uint32_t)rr * TL_NT + (uint32_t)tid;
-    const uint32_t r0 = cbase + pi * TL_PIECE;
+    const uint32_t p0 = pi * TL_PIECE, r0 = cbase + p0;
     active[rr] = pi < st.npieces && r0 < st.limit;
     regular[rr] = false;
     n_emit[rr] = 0;
     // fully inside the segment, previous byte included (its FF would pair with my first byte)
     const bool inside = active[rr] && r0 > st.skew && r0 + TL_PIECE <= st.limit;
+    edge[rr] = active[rr] && !inside;
     if (inside) {
-      const uint32_t pa = sb_raw + pi * TL_PIECE;
+      const uint32_t pa = sb_raw + p0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint4 v = lds_v4<0>(pa + 16 * q);
@@ -259,7 +359,7 @@ __device__ __forceinline__ TileChunk tl_unstuff(TileShared<R>& sh, const TileStr
         ffp = cy.prev_ff ? 0x80000000u : 0u; // (chunk > 0 here: piece 0 of chunk 0 is never `inside`)
       else
         ffp = tl_ff_flags(lds_u32<0>(pa - 4));
-      uint32_t zs_cnt = 0, m2acc = 0;
+      uint32_t zs_cnt = 0, mk_local = TL_NOPOS; // mk_local: piece-relative index of a marker's SECOND byte
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const uint32_t ffk = tl_ff_flags(w[rr][k]);
@@ -267,75 +367,90 @@ __device__ __forceinline__ TileChunk tl_unstuff(TileShared<R>& sh, const TileStr
         if (pf) {
           const uint32_t zf = tl_zero_flags(w[rr][k]);
           zs_cnt += (uint32_t)__popc(pf & zf);
-          m2acc |= pf & ~zf;
+          const uint32_t m2 = pf & ~zf; // second byte of a marker
+          if (m2 && mk_local == TL_NOPOS)
+            mk_local = 4u * k + (((uint32_t)__ffs(m2) - 1u) >> 3);
         }
         ffp = ffk;
       }
-      // the chunk's last piece also answers for the byte behind the chunk: an FF in my last
-      // byte followed by a non-zero look-ahead byte is the end marker
-      if (pi + 1 == st.npieces && tl_marker2(st, r0 + TL_PIECE))
-        m2acc |= 1u;
+      // the chunk's last piece also answers for the byte behind the chunk
+      if (mk_local == TL_NOPOS && pi + 1 == st.npieces && (w[rr][15] >> 24) == 0xFFu &&
+          r0 + TL_PIECE < st.limit && tl_stage_byte<R>(sb_raw, p0 + TL_PIECE) != 0u)
+        mk_local = TL_PIECE;
       n_emit[rr] = TL_PIECE - zs_cnt;
-      regular[rr] = zs_cnt == 0 && m2acc == 0;
-      m2any |= m2acc;
-    } else if (active[rr]) {
-      // first / last piece of the segment: scalar count and marker search
-      uint32_t n = 0;
-      for (uint32_t b = 0; b < (uint32_t)TL_PIECE; ++b) {
-        n += tl_keep(st, r0 + b, st.limit) ? 1u : 0u;
-        m2any |= tl_marker2(st, r0 + b) ? 1u : 0u;
-      }
-      if (pi + 1 == st.npieces && tl_marker2(st, r0 + TL_PIECE))
-        m2any |= 1u;
-      n_emit[rr] = n;
+      regular[rr] = zs_cnt == 0 && mk_local == TL_NOPOS;
+      if (mk_local != TL_NOPOS && p0 + mk_local > 0) // the marker's FF sits one byte earlier
+        mk_mine = min(mk_mine, p0 + mk_local - 1u);
     }
   }
-  const int any_mk = __syncthreads_or(m2any != 0u);
+  TL_TICK(9);
+  const int any_mk = __syncthreads_or(mk_mine != TL_NOPOS || has_edge);
   uint32_t mpos = TL_NOPOS;
   if (any_mk) {
-    // exact position of the first marker: scalar search in the pieces that saw one.  (A marker
-    // whose FF is the last byte of the previous chunk gives position -1 = 0xFFFFFFFF + ... : it
-    // cannot happen, that chunk sees the FF followed by a non-zero look-ahead byte itself.)
-    if (m2any) {
-#pragma unroll
-      for (int rr = 0; rr < R; ++rr) {
-        const uint32_t pi = (uint32_t)rr * TL_NT + (uint32_t)tid;
-        if (!active[rr])
-          continue;
-        const uint32_t nb = (pi + 1 == st.npieces) ? TL_PIECE + 1u : (uint32_t)TL_PIECE;
-        for (uint32_t b = 0; b < nb; ++b) {
-          const uint32_t r = cbase + pi * TL_PIECE + b;
-          if (tl_marker2(st, r)) {
-            atomicMin(&sh.mpos, r - 1u - cbase);
-            break;
-          }
-        }
+    // (a) markers: flagged pieces of pass 1 and, cooperatively, the edge pieces
+    if (mk_mine != TL_NOPOS)
+      atomicMin(&sh.mpos, mk_mine);
+    const uint32_t e1 = min((st.limit - 1u - cbase) / TL_PIECE, st.npieces - 1u); // holds the last byte
+    auto is_edge_piece = [&](uint32_t pi) {
+      const uint32_t r0 = cbase + pi * TL_PIECE;
+      return pi < st.npieces && r0 < st.limit && !(r0 > st.skew && r0 + TL_PIECE <= st.limit);
+    };
+    if (has_edge && wid < 2) {
+      const uint32_t pi = wid == 0 ? 0u : e1;
+      if (is_edge_piece(pi) && !(wid == 1 && e1 == 0u)) {
+        uint32_t mk;
+        tl_piece_flags<R>(st, sb_raw, cbase, pi, cy.prev_ff, st.limit, &mk);
+        if (lane == 0 && mk != TL_NOPOS)
+          atomicMin(&sh.mpos, mk);
       }
     }
     __syncthreads();
-    mpos = sh.mpos;
-    // pieces at / behind the marker hold no data; the piece that contains it is cut
+    mpos = sh.mpos; // chunk relative
+    // (b) byte counts of the edge pieces and of the piece the marker cuts, w.r.t. the real end
+    const uint32_t lim = mpos == TL_NOPOS ? st.limit : min(st.limit, cbase + mpos);
+    const uint32_t pm = mpos == TL_NOPOS ? TL_NOPOS : mpos / TL_PIECE;
+    if (has_edge || mpos != TL_NOPOS) {
+      if (wid < 3) {
+        const uint32_t pi = wid == 0 ? 0u : (wid == 1 ? e1 : pm);
+        const bool wanted = wid == 2 ? (pm != TL_NOPOS && pm < st.npieces)
+                                     : (has_edge && is_edge_piece(pi) && !(wid == 1 && e1 == 0u));
+        if (wanted) {
+          uint32_t mk;
+          const uint32_t kf = tl_piece_flags<R>(st, sb_raw, cbase, pi, cy.prev_ff, lim, &mk);
+          const uint32_t n = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, kf & 1u)) +
+                             (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, kf & 2u));
+          if (lane == 0)
+            sh.coop_n[wid] = n;
+        }
+      }
+      __syncthreads();
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      const uint32_t pi = (uint32_t)rr * TL_NT + (uint32_t)tid;
-      const uint32_t p0 = pi * TL_PIECE;
-      if (!active[rr] || mpos == TL_NOPOS)
-        continue;
-      if (p0 >= mpos) {
-        n_emit[rr] = 0;
-        regular[rr] = false;
-        active[rr] = false;
-      } else if (mpos < p0 + TL_PIECE) {
-        uint32_t n = 0;
-        for (uint32_t b = 0; b < mpos - p0; ++b)
-          n += tl_keep(st, cbase + p0 + b, cbase + mpos) ? 1u : 0u;
-        n_emit[rr] = n;
-        regular[rr] = false;
+      for (int rr = 0; rr < R; ++rr) {
+        const uint32_t pi = (uint32_t)rr * TL_NT + (uint32_t)tid;
+        const uint32_t p0 = pi * TL_PIECE;
+        if (!active[rr])
+          continue;
+        if (mpos != TL_NOPOS && p0 >= mpos) { // at / behind the marker: no data
+          n_emit[rr] = 0;
+          regular[rr] = false;
+          active[rr] = false;
+        } else if (pi == pm) {
+          n_emit[rr] = sh.coop_n[2];
+          regular[rr] = false;
+        } else if (edge[rr]) {
+          n_emit[rr] = sh.coop_n[pi == 0 ? 0 : 1];
+          regular[rr] = false;
+        }
       }
     }
   }
   const uint32_t limit_eff = mpos == TL_NOPOS ? st.limit : min(st.limit, cbase + mpos);
-  // ---- positions ----
+  TL_TICK(10);
+  // ---- positions; the list of the pieces that need byte-wise treatment ----
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr)
+    if (active[rr] && !regular[rr] && n_emit[rr])
+      sh.list[atomicAdd(&sh.nlist, 1u)] = (uint32_t)rr * TL_NT + (uint32_t)tid;
   uint32_t dst0[R];
   uint32_t run = cy.tail_len;
 #pragma unroll
@@ -347,17 +462,23 @@ __device__ __forceinline__ TileChunk tl_unstuff(TileShared<R>& sh, const TileStr
     const uint32_t pi = (uint32_t)rr * TL_NT + (uint32_t)tid;
     if (pi <= (uint32_t)G::NPIECE)
       sh.anchor[pi] = dst0[rr];
-    if (active[rr] && !regular[rr] && n_emit[rr])
-      sh.list[atomicAdd(&sh.nlist, 1u)] = pi;
   }
   const uint32_t total_emit = run - cy.tail_len;
-  co.len = run;
+  const uint32_t len = run;
+  const bool final_chunk = (mpos != TL_NOPOS) || (cbase + st.chunk_raw >= st.limit);
+  co.len = len;
+  co.Lc = final_chunk ? len + TL_ZEXT : (len > (uint32_t)TL_LA ? len - TL_LA : 0u);
+  const uint32_t Lc = co.Lc;
+  TL_TICK(11);
   // ---- pass 2a: regular pieces, whole words (byte i of the clean stream lives at ub8[i ^ 3]) ----
 #pragma unroll
   for (int rr = 0; rr < R; ++rr) {
     if (!regular[rr])
       continue;
     const uint32_t d0 = dst0[rr];
+    // the source of clean byte Lc becomes the source of ub byte 0 of the next chunk
+    if (!final_chunk && Lc - d0 < (uint32_t)TL_PIECE)
+      sh.tail_raw_next = cbase + ((uint32_t)rr * TL_NT + (uint32_t)tid) * TL_PIECE + (Lc - d0);
     const uint32_t head = (4u - (d0 & 3u)) & 3u; // bytes up to the next word boundary
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -379,38 +500,50 @@ __device__ __forceinline__ TileChunk tl_unstuff(TileShared<R>& sh, const TileStr
           sts_u8<0>(sb_ub + ((d0 + 60 + k) ^ 3u), (w[rr][15] >> (8 * k)) & 0xFFu);
     }
   }
-  __syncthreads(); // list complete
-  // ---- pass 2b: irregular pieces, byte by byte, one thread per piece ----
-  {
-    const uint32_t nl = sh.nlist;
-    for (uint32_t j = tid; j < nl; j += TL_NT) {
-      const uint32_t pi = sh.list[j];
-      uint32_t d = sh.anchor[pi];
-      const uint32_t r0 = cbase + pi * TL_PIECE;
-      for (uint32_t b = 0; b < (uint32_t)TL_PIECE; ++b) {
-        const uint32_t r = r0 + b;
-        if (tl_keep(st, r, limit_eff)) {
-          sts_u8<0>(sb_ub + (d ^ 3u), st.gbase[r]);
-          ++d;
-        }
-      }
-    }
-  }
-  const bool final_chunk = (mpos != TL_NOPOS) || (cbase + st.chunk_raw >= st.limit);
-  const uint32_t len = co.len;
-  __syncthreads();
   // zero padding behind the data (look-ahead loads; zero extension at the end of the segment)
   if (tid < 64) {
     const uint32_t i = len + tid;
     if (i < (uint32_t)G::UBBYTES)
       sts_u8<0>(sb_ub + (i ^ 3u), 0u);
   }
-  co.Lc = final_chunk ? len + TL_ZEXT : (len > (uint32_t)TL_LA ? len - TL_LA : 0u);
+  if (tid == 64) { // was the last raw byte of this chunk an FF inside the segment?
+    const uint32_t lastr = cbase + st.chunk_raw - 1u;
+    sh.prev_ff_next = (lastr >= st.skew && lastr < st.limit &&
+                       tl_stage_byte<R>(sb_raw, st.chunk_raw - 1u) == 0xFFu) ? 1u : 0u;
+  }
+  TL_TICK(12);
+  __syncthreads(); // list + anchors complete
+  // ---- pass 2b: the other pieces, one warp per piece, two bytes per lane, from the staging ----
+  {
+    const uint32_t nl = sh.nlist;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t j = wid; j < nl; j += TL_NT / 32) {
+      const uint32_t pi = sh.list[j];
+      uint32_t c01;
+      const uint32_t kf = tl_piece_keep<R>(st, sb_raw, cbase, pi, cy.prev_ff, limit_eff, &c01);
+      const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, kf & 1u), b1 = __ballot_sync(0xFFFFFFFFu, kf & 2u);
+      uint32_t d = sh.anchor[pi] + (uint32_t)__popc(b0 & lt) + (uint32_t)__popc(b1 & lt);
+      const uint32_t q0 = pi * TL_PIECE + 2u * lane;
+      if (kf & 1u) {
+        if (!final_chunk && d == Lc)
+          sh.tail_raw_next = cbase + q0;
+        sts_u8<0>(sb_ub + (d ^ 3u), c01 & 0xFFu);
+        ++d;
+      }
+      if (kf & 2u) {
+        if (!final_chunk && d == Lc)
+          sh.tail_raw_next = cbase + q0 + 1u;
+        sts_u8<0>(sb_ub + (d ^ 3u), c01 >> 8);
+      }
+    }
+  }
+  TL_TICK(13);
   co.end_all = co.Lc * 8;
   co.mpos = mpos;
   co.total_emit = total_emit;
   co.final_chunk = final_chunk;
   __syncthreads();
+  TL_TICK(14);
   return co;
 }
 
@@ -420,28 +553,40 @@ template <int R> struct TileOff {
   static constexpr int UB = (int)offsetof(S, ub);
   static constexpr int DBUF = (int)offsetof(S, dbuf);
   static constexpr int LUT = (int)(offsetof(S, tab) + offsetof(DevTable, lut));
+  static constexpr int LEN8 = (int)offsetof(S, len8);
 };
 constexpr uint32_t TL_LUT_TOPMASK = ~((1u << (32 - LUT_BITS)) - 1u);
 
 template <int R> struct TileBits {
   uint32_t p;        // bit position in ub
   uint32_t cur, nxt; // words p/32 and p/32+1
+  uint32_t wa;       // shared address (relative to sb + UB) of word p/32+2
   __device__ __forceinline__ void open(uint32_t sb, uint32_t start) {
     p = start;
-    const uint32_t wa = sb + ((start >> 3) & ~3u);
+    wa = sb + ((start >> 3) & ~3u);
     cur = lds_u32<TileOff<R>::UB>(wa);
     nxt = lds_u32<TileOff<R>::UB + 4>(wa);
   }
   __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, p); }
-  __device__ __forceinline__ void skip(uint32_t sb, uint32_t n) {
+  __device__ __forceinline__ void skip(uint32_t n) { // n <= 32: at most one word boundary
     const uint32_t pn = p + n;
-    if ((pn ^ p) & ~31u) { // crossed into the next word (n <= 32)
+    if ((pn ^ p) & 32u) {
       cur = nxt;
-      nxt = lds_u32<TileOff<R>::UB + 4>(mad_hi(pn & ~31u, 1u << 29, sb)); // sb + 4*(pn/32)
+      nxt = lds_u32<TileOff<R>::UB + 8>(wa);
+      wa += 4;
     }
     p = pn;
   }
 };
+
+// keeps a loop-invariant value in its register (ptxas otherwise re-derives it from
+// threadIdx.x inside the hot loops when registers are short)
+__device__ __forceinline__ uint32_t tl_opaque(uint32_t v) {
+#ifndef RSB200_EMU
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+#endif
+  return v;
+}
 
 template <int R> __device__ __forceinline__ uint32_t tl_lut(uint32_t sb, uint32_t x) {
   return lds_u16<TileOff<R>::LUT>(mad_hi(x & TL_LUT_TOPMASK, 1u << (LUT_BITS + 1), sb));
@@ -454,6 +599,10 @@ __device__ __noinline__ uint32_t tl_long_symbol(const DevTable* t, uint32_t x) {
 
 // lengths-only parse from `start` up to (not including) the first symbol that starts at or
 // behind end_bit; returns the position reached and counts the symbols
+template <int R> __device__ __forceinline__ uint32_t tl_len8(uint32_t sb, uint32_t x) {
+  return lds_u8<TileOff<R>::LEN8>(mad_hi(x, 1u << LUT_BITS, sb)); // sb + (x >> 21)
+}
+
 template <int R>
 __device__ __forceinline__ uint32_t tl_scan(const TileShared<R>& sh, uint32_t sb, uint32_t start,
                                             uint32_t end_bit, uint32_t& count) {
@@ -462,15 +611,16 @@ __device__ __forceinline__ uint32_t tl_scan(const TileShared<R>& sh, uint32_t sb
     count = 0;
     return start;
   }
+  end_bit = tl_opaque(end_bit);
   TileBits<R> b;
   b.open(sb, start);
   do {
     const uint32_t x = b.peek();
-    uint32_t len = tl_lut<R>(sb, x) >> 10;
+    uint32_t len = tl_len8<R>(sb, x);
     if (len == 0)
       len = tl_long_symbol(&sh.tab, x);
     ++cnt;
-    b.skip(sb, len);
+    b.skip(len);
   } while (b.p < end_bit);
   count = cnt;
   return b.p;
@@ -679,10 +829,10 @@ __device__ __noinline__ void tl_replay(TileShared<R>& sh, const TileStream& st, 
     }
     const uint32_t at = b.p;
     const uint32_t x = b.peek();
-    uint32_t len = tl_lut<R>(sb, x) >> 10;
+    uint32_t len = tl_len8<R>(sb, x);
     if (len == 0)
       len = tl_long_symbol(&sh.tab, x);
-    b.skip(sb, len);
+    b.skip(len);
     fill -= len;
     if (at >= p_last)
       break;
@@ -693,23 +843,6 @@ __device__ __noinline__ void tl_replay(TileShared<R>& sh, const TileStream& st, 
   sh.rstat = threw ? 2u : 0u;
   sh.rcons = end_pos != TL_NOPOS ? end_pos : rp;
 }
-
-// Optional per-phase cycle accounting (profiling builds only: -DRSB200_PHASE_TIMING).
-#if defined(RSB200_PHASE_TIMING) && !defined(RSB200_EMU)
-__device__ unsigned long long g_tile_phase_cycles[16];
-#define TL_TICK(i)                                                                 \
-  do {                                                                             \
-    if (threadIdx.x == 0) {                                                        \
-      const long long t_now = clock64();                                           \
-      atomicAdd(&g_tile_phase_cycles[i], (unsigned long long)(t_now - t_phase));   \
-      t_phase = t_now;                                                             \
-    }                                                                              \
-  } while (0)
-#define TL_TICK_INIT long long t_phase = clock64()
-#else
-#define TL_TICK(i) do { } while (0)
-#define TL_TICK_INIT do { } while (0)
-#endif
 
 // ================= the kernel body =================
 template <int R, int GG>
@@ -758,7 +891,7 @@ __device__ __forceinline__ void tile_body(TileShared<R>& sh, const uint8_t* __re
     TL_TICK(0);
 
     // ================= B: unstuff =================
-    const TileChunk co = tl_unstuff<R>(sh, st, cy, chunk);
+    const TileChunk co = tl_unstuff<R>(sh, st, cy, chunk TL_TICK_PASS);
     const uint32_t len = co.len, Lc = co.Lc;
     TL_TICK(1);
 
@@ -793,10 +926,10 @@ __device__ __forceinline__ void tile_body(TileShared<R>& sh, const uint8_t* __re
           b.open(sb, my_start);
           for (uint32_t k = rel0; k < lo; ++k) { // symbols of earlier batches: lengths only
             const uint32_t x = b.peek();
-            uint32_t tl = tl_lut<R>(sb, x) >> 10;
+            uint32_t tl = tl_len8<R>(sb, x);
             if (tl == 0)
               tl = tl_long_symbol(&sh.tab, x);
-            b.skip(sb, tl);
+            b.skip(tl);
           }
           uint32_t dst = sb + 2u * (cb.leftover + (lo - done));
           const uint32_t dst_end = dst + 2u * (hi - lo);
@@ -810,7 +943,7 @@ __device__ __forceinline__ void tile_body(TileShared<R>& sh, const uint8_t* __re
               const uint32_t diff = tl_decode_diff<R>(sh, sb, x, tl);
               sts_u16<TileOff<R>::DBUF>(dst, diff);
               dst += 2;
-              b.skip(sb, tl);
+              b.skip(tl);
             }
             if (stop == dst_end)
               break;
@@ -973,11 +1106,8 @@ __device__ __forceinline__ void tile_body(TileShared<R>& sh, const uint8_t* __re
       else
         tl_store_units<R, 1>(sh, sb, sc, out, S0, n, upt, base01, base23, r_first, cb.rb01, cb.rb23);
       TL_TICK(6);
-      // E4: carry; the unfinished differences (< 8) travel in the carry
-      uint32_t keep = 0;
-      if ((uint32_t)tid < have - n)
-        keep = sh.dbuf[n + tid];
-      __syncthreads();
+      // E4: carry; the unfinished differences (< 8) travel in the carry (dbuf is the staging of
+      //     the next chunk's raw bytes)
       if (tid == 0) {
         TileCarry& c2 = sh.cy;
         c2.pc01 = __vadd2(cb.pc01, ta);
@@ -988,11 +1118,13 @@ __device__ __forceinline__ void tile_body(TileShared<R>& sh, const uint8_t* __re
         }
         c2.proc = S0 + n;
         c2.leftover = have - n;
-        c2.left[0] = c2.left[1] = c2.left[2] = c2.left[3] = 0;
       }
-      __syncthreads();
-      if ((uint32_t)tid < have - n)
-        atomicOr(&sh.cy.left[tid >> 1], keep << (16 * (tid & 1)));
+      if (tid >= 32 && tid < 36) {
+        const uint32_t k = 2u * (uint32_t)(tid - 32);
+        const uint32_t lo = (k < have - n) ? sh.dbuf[n + k] : 0u;
+        const uint32_t hi = (k + 1 < have - n) ? sh.dbuf[n + k + 1] : 0u;
+        sh.cy.left[tid - 32] = lo | (hi << 16);
+      }
       __syncthreads();
       done += take;
       if (done >= chunk_syms)
@@ -1002,29 +1134,31 @@ __device__ __forceinline__ void tile_body(TileShared<R>& sh, const uint8_t* __re
     TL_TICK(7);
     // ================= carry to the next chunk =================
     {
-      // deferred tail: clean bytes [Lc, len) move to the front of ub
+      // deferred tail: clean bytes [Lc, len) move to the front of ub (nobody reads ub any more)
       const uint32_t tail = co.final_chunk ? 0u : len - Lc;
       uint32_t tailbyte = 0;
       if ((uint32_t)tid < tail)
         tailbyte = reinterpret_cast<uint8_t*>(sh.ub)[(Lc + tid) ^ 3u];
-      __syncthreads();
-      if ((uint32_t)tid < tail)
-        reinterpret_cast<uint8_t*>(sh.ub)[tid ^ 3u] = (uint8_t)tailbyte;
-      if (tid == 0) {
+      if (tid == 32) {
         TileCarry& c2 = sh.cy;
         c2.sym = cy.sym + total_syms;
         c2.pos = exit_all - Lc * 8u;
         c2.tail_len = tail;
         c2.ubytes = cy.ubytes + Lc;
         if (!co.final_chunk) {
-          // raw offset of the clean byte that becomes ub byte 0 (clean index Lc of this chunk)
-          c2.tail_raw = tl_raw_of_clean<R>(sh, st, cy, chunk, Lc) + st.skew;
-          const uint32_t lastr = (chunk + 1) * st.chunk_raw - 1;
-          c2.prev_ff = (lastr >= st.skew && lastr < st.limit && st.gbase[lastr] == 0xFFu) ? 1u : 0u;
+          // raw offset of the clean byte that becomes ub byte 0 (clean index Lc of this chunk):
+          // recorded by the piece that holds it; it lies in the carried tail only when this chunk
+          // produced fewer than TL_LA bytes
+          c2.tail_raw = sh.tail_raw_next != TL_NOPOS
+                            ? sh.tail_raw_next
+                            : tl_raw_of_clean<R>(sh, st, cy, chunk, Lc) + st.skew;
+          c2.prev_ff = sh.prev_ff_next;
         }
         c2.ended = co.final_chunk ? 1u : 0u;
       }
       __syncthreads();
+      if ((uint32_t)tid < tail)
+        reinterpret_cast<uint8_t*>(sh.ub)[tid ^ 3u] = (uint8_t)tailbyte;
       // the raw staging of the next chunk lands in dbuf: everything above has left it
       const bool more = !co.final_chunk && sh.cy.sym < sc.n_samples;
       if (more) {
@@ -1155,6 +1289,9 @@ __device__ __forceinline__ void tile_entry(TileShared<R>& sh, const uint8_t* __r
     for (int i = tid; i < (int)(sizeof(DevTable) / 16); i += TL_NT)
       dst[i] = src[i];
   }
+  __syncthreads();
+  for (int i = tid; i < (1 << LUT_BITS); i += TL_NT)
+    sh.len8[i] = (uint8_t)(sh.tab.lut[i] >> 10);
   if (tid == 0) {
     res->consumed = 0;
     sh.bad_code = 0;
@@ -1187,8 +1324,11 @@ __device__ __forceinline__ void tile_entry(TileShared<R>& sh, const uint8_t* __r
 }
 
 #ifndef RSB200_EMU
+#ifndef RSB200_TILE_CTAS1
+#define RSB200_TILE_CTAS1 4
+#endif
 template <int R>
-__global__ void __launch_bounds__(TL_NT, (R == 1 ? 4 : 2))
+__global__ void __launch_bounds__(TL_NT, (R == 1 ? RSB200_TILE_CTAS1 : 2))
     k2_tile_kernel(const uint8_t* __restrict__ in, uint64_t in_total,
                    const DevScan* __restrict__ scans, const DevTable* __restrict__ tables,
                    uint8_t* __restrict__ out, DevResult* __restrict__ results_all,

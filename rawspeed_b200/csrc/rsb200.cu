@@ -195,6 +195,13 @@ struct rsb200_plan {
   uint32_t* d_small_ids = nullptr;
   int nsmall = 0;
   uint32_t* d_tile_ids = nullptr; // segments decoded by k2_tile_kernel<R> (ljpeg_tile.cuh)
+  // host-buffer runs of a plan that holds only such segments are pipelined group by group
+  // (upload / decode / download of consecutive groups overlap on three streams)
+  struct TileGroup {
+    uint32_t first, count;
+    uint64_t in_lo, in_hi, out_lo, out_hi;
+  };
+  std::vector<TileGroup> tile_groups;
   DevTileParam* d_tile_params = nullptr;
   int ntile = 0;
   int tile_r = 1;
@@ -1426,6 +1433,30 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   }
   p->nsmall = (int)small_ids.size();
   p->ntile = (int)tile_ids.size();
+  if (!tile_ids.empty() && small_ids.empty() && thread_ids.empty() && big_ids.empty()) {
+    // groups of consecutive segments worth ~8 MB of output each
+    const uint64_t kGroupOut = 8ull << 20;
+    rsb200_plan::TileGroup g{0, 0, ~0ull, 0, ~0ull, 0};
+    uint64_t acc = 0;
+    for (size_t k = 0; k < tile_ids.size(); ++k) {
+      const DevScan& d = b.scans[tile_ids[k]];
+      const uint64_t i0 = d.in_offset & ~15ull, i1 = (d.in_offset + d.in_size + 15) & ~15ull;
+      const uint64_t o0 = d.out_offset + (uint64_t)d.out_y * d.out_pitch + 2ull * d.out_x;
+      const uint64_t o1 = d.out_offset + ((uint64_t)d.out_y + d.rows - 1) * d.out_pitch +
+                          2ull * ((uint64_t)d.out_x + d.store_w);
+      g.in_lo = std::min(g.in_lo, i0);
+      g.in_hi = std::max(g.in_hi, i1);
+      g.out_lo = std::min(g.out_lo, o0);
+      g.out_hi = std::max(g.out_hi, o1);
+      ++g.count;
+      acc += (uint64_t)d.rows * d.store_w * 2;
+      if (acc >= kGroupOut || k + 1 == tile_ids.size()) {
+        p->tile_groups.push_back(g);
+        g = rsb200_plan::TileGroup{(uint32_t)(k + 1), 0, ~0ull, 0, ~0ull, 0};
+        acc = 0;
+      }
+    }
+  }
   p->nthread = (int)thread_ids.size();
   p->ntables = ntables;
   p->nbig = (int)big_ids.size();
@@ -2070,6 +2101,49 @@ static int run_host_unpack_pipelined(rsb200_plan* p, const uint8_t* in, size_t i
   return RSB200_OK;
 }
 
+static cudaError_t launch_tile_range(const rsb200_plan* p, const uint8_t* d_in, uint64_t in_bytes,
+                                     uint8_t* d_out, uint32_t first, uint32_t count,
+                                     cudaStream_t st) {
+  if (p->tile_r == 2)
+    k2_tile_kernel<2><<<count, TL_NT, tile_smem_bytes<2>(), st>>>(
+        d_in, in_bytes, p->d_scans, p->d_tables, d_out, p->d_results, p->d_tile_ids + first,
+        p->d_tile_params + first);
+  else
+    k2_tile_kernel<1><<<count, TL_NT, tile_smem_bytes<1>(), st>>>(
+        d_in, in_bytes, p->d_scans, p->d_tables, d_out, p->d_results, p->d_tile_ids + first,
+        p->d_tile_params + first);
+  return cudaGetLastError();
+}
+
+// LJPEG plan made of tile-kernel segments only: group g's upload, kernel and download are chained
+// on stream g % 3, so the upload of the next group and the download of the previous one overlap
+// the decode of the current one.  Spans of neighbouring groups may overlap (tiles of one tile row
+// in two groups): every byte's last download happens after its last write, whatever the order.
+static int run_host_tile_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
+                                   uint8_t* out, size_t out_bytes) {
+  rsb200_ctx* ctx = p->ctx;
+  for (size_t gi = 0; gi < p->tile_groups.size(); ++gi) {
+    const rsb200_plan::TileGroup& g = p->tile_groups[gi];
+    cudaStream_t st = ctx->pipe[gi % 3];
+    const uint64_t i1 = std::min<uint64_t>(g.in_hi, (in_bytes + 15) & ~15ull);
+    const uint64_t i1c = std::min<uint64_t>(i1, in_bytes);
+    const uint64_t o1 = std::min<uint64_t>(g.out_hi, out_bytes);
+    if (i1c > g.in_lo)
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in + g.in_lo, in + g.in_lo, i1c - g.in_lo,
+                                    cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, launch_tile_range(p, ctx->d_in, (uint64_t)in_bytes, ctx->d_out, g.first, g.count, st));
+    ctx->launches++;
+    if (o1 > g.out_lo)
+      CUDA_TRY(ctx, cudaMemcpyAsync(out + g.out_lo, ctx->d_out + g.out_lo, o1 - g.out_lo,
+                                    cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < 3; ++i)
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+  p->last_stream = ctx->pipe[0];
+  p->ran = true;
+  return RSB200_OK;
+}
+
 extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
                                     uint8_t* out, size_t out_bytes, int partial) {
   if (!p || !out || (!in && in_bytes))
@@ -2088,6 +2162,8 @@ extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in
     partial = 1; // in-place plans work on the image the caller holds: it always goes up first
   if (!partial && unpack_pipeline_ok(p))
     return run_host_unpack_pipelined(p, in, in_bytes, out, out_bytes);
+  if (!partial && p->kind == 1 && p->tile_groups.size() >= 2 && !getenv("RSB200_NO_PIPELINE"))
+    return run_host_tile_pipelined(p, in, in_bytes, out, out_bytes);
   cudaStream_t st = ctx->stream;
   if (in_bytes)
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
@@ -2128,6 +2204,208 @@ extern "C" int rsb200_plan_run_host_image(rsb200_plan* p, const uint8_t* in, siz
   CUDA_TRY(ctx, cudaMemcpy2DAsync(out, pitch, ctx->d_out, pitch, row_bytes, rows,
                                   cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return RSB200_OK;
+}
+
+// ------------------------------------------------------------------
+// Multi-GPU output gather over NCCL (resolved at run time)
+// ------------------------------------------------------------------
+#include <dlfcn.h>
+struct Id128 { // ncclUniqueId: 128 opaque bytes, passed by value
+  char internal[128];
+};
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+} // namespace
+static NcclApi& nccl_api() {
+  static NcclApi a;
+  static bool tried = false;
+  if (tried)
+    return a;
+  tried = true;
+  // the copy the process already has (e.g. the one PyTorch brought), else the system's
+  a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!a.lib)
+    a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!a.lib)
+    a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!a.lib)
+    return a;
+#define RSB_SYM(field, name) *(void**)(&a.field) = dlsym(a.lib, name)
+  RSB_SYM(GetUniqueId, "ncclGetUniqueId");
+  RSB_SYM(CommInitRank, "ncclCommInitRank");
+  RSB_SYM(CommDestroy, "ncclCommDestroy");
+  RSB_SYM(GroupStart, "ncclGroupStart");
+  RSB_SYM(GroupEnd, "ncclGroupEnd");
+  RSB_SYM(Broadcast, "ncclBroadcast");
+  RSB_SYM(Send, "ncclSend");
+  RSB_SYM(Recv, "ncclRecv");
+  RSB_SYM(GetErrorString, "ncclGetErrorString");
+#undef RSB_SYM
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd &&
+         a.Broadcast && a.Send && a.Recv;
+  return a;
+}
+
+struct rsb200_comm {
+  rsb200_ctx* ctx = nullptr;
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+  cudaStream_t stream = nullptr; // the transfers run here, beside the decode stream
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t done = nullptr;
+};
+
+#define NCCL_TRY(ctx, expr)                                                                \
+  do {                                                                                     \
+    const int rc_ = (expr);                                                                \
+    if (rc_ != 0)                                                                          \
+      return set_err(ctx, RSB200_ERR_CUDA, "%s failed: %s", #expr,                         \
+                     nccl_api().GetErrorString ? nccl_api().GetErrorString(rc_) : "?");    \
+  } while (0)
+
+extern "C" int rsb200_comm_unique_id(uint8_t id[128]) {
+  NcclApi& a = nccl_api();
+  if (!a.ok || !id)
+    return RSB200_ERR_CUDA;
+  return a.GetUniqueId(id) == 0 ? RSB200_OK : RSB200_ERR_CUDA;
+}
+
+extern "C" int rsb200_comm_create(rsb200_ctx* ctx, const uint8_t id[128], int world, int rank,
+                                  rsb200_comm** out) {
+  if (!ctx || !id || !out || world < 1 || rank < 0 || rank >= world)
+    return set_err(ctx, RSB200_ERR_ARG, "comm_create: bad arguments");
+  NcclApi& a = nccl_api();
+  if (!a.ok)
+    return set_err(ctx, RSB200_ERR_CUDA, "comm_create: NCCL (libnccl.so.2) is not available");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  rsb200_comm* c = new (std::nothrow) rsb200_comm();
+  if (!c)
+    return RSB200_ERR_CUDA;
+  c->ctx = ctx;
+  c->world = world;
+  c->rank = rank;
+  Id128 uid;
+  memcpy(uid.internal, id, 128);
+  const int rc = a.CommInitRank(&c->comm, world, uid, rank);
+  if (rc != 0) {
+    delete c;
+    return set_err(ctx, RSB200_ERR_CUDA, "ncclCommInitRank failed: %s",
+                   a.GetErrorString ? a.GetErrorString(rc) : "?");
+  }
+  cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
+  *out = c;
+  return RSB200_OK;
+}
+
+extern "C" void rsb200_comm_destroy(rsb200_comm* c) {
+  if (!c)
+    return;
+  cudaSetDevice(c->ctx->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  if (c->comm)
+    nccl_api().CommDestroy(c->comm);
+  for (cudaEvent_t e : c->events)
+    cudaEventDestroy(e);
+  if (c->done)
+    cudaEventDestroy(c->done);
+  if (c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// one span [lo, hi) of every rank's slab, on the communicator's stream
+static int gather_span(rsb200_comm* c, uint8_t* all, size_t slab, uint64_t lo, uint64_t hi, int mode,
+                       int root) {
+  NcclApi& a = nccl_api();
+  rsb200_ctx* ctx = c->ctx;
+  const size_t n = (size_t)(hi - lo);
+  if (!n || c->world == 1 || mode == RSB200_GATHER_NONE)
+    return RSB200_OK;
+  NCCL_TRY(ctx, a.GroupStart());
+  if (mode == RSB200_GATHER_ALL) {
+    for (int r = 0; r < c->world; ++r) {
+      uint8_t* ptr = all + (size_t)r * slab + lo;
+      NCCL_TRY(ctx, a.Broadcast(ptr, ptr, n, /*ncclUint8*/ 1, r, c->comm, c->stream));
+    }
+  } else {
+    if (c->rank == root) {
+      for (int r = 0; r < c->world; ++r)
+        if (r != root)
+          NCCL_TRY(ctx, a.Recv(all + (size_t)r * slab + lo, n, 1, r, c->comm, c->stream));
+    } else {
+      NCCL_TRY(ctx, a.Send(all + (size_t)c->rank * slab + lo, n, 1, root, c->comm, c->stream));
+    }
+  }
+  NCCL_TRY(ctx, a.GroupEnd());
+  return RSB200_OK;
+}
+
+extern "C" int rsb200_plan_run_gather(rsb200_plan* p, rsb200_comm* c, const void* d_in,
+                                      size_t in_bytes, void* d_out_all, size_t slab_bytes, int mode,
+                                      int root, void* stream) {
+  if (!p || !c || !d_out_all || root < 0 || root >= c->world || mode < 0 || mode > 2)
+    return RSB200_ERR_ARG;
+  rsb200_ctx* ctx = p->ctx;
+  if (slab_bytes < p->need_out || (slab_bytes & 15))
+    return set_err(ctx, RSB200_ERR_ARG, "plan_run_gather: slab smaller than the plan's output or not a multiple of 16");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok)
+    return set_err(ctx, RSB200_ERR_CUDA, "plan_run_gather: cannot select device %d", ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* all = (uint8_t*)d_out_all;
+  uint8_t* mine = all + (size_t)c->rank * slab_bytes;
+  // the transfers start behind whatever the caller queued on `stream` so far
+  CUDA_TRY(ctx, cudaEventRecord(c->done, st));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(c->stream, c->done, 0));
+  if (p->kind == 1 && !p->tile_groups.empty()) {
+    if (in_bytes < p->need_in)
+      return set_err(ctx, RSB200_ERR_ARG, "plan_run_gather: input too small");
+    while (c->events.size() < p->tile_groups.size()) {
+      cudaEvent_t e;
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->events.push_back(e);
+    }
+    for (size_t gi = 0; gi < p->tile_groups.size(); ++gi) {
+      const rsb200_plan::TileGroup& g = p->tile_groups[gi];
+      CUDA_TRY(ctx, launch_tile_range(p, (const uint8_t*)d_in, (uint64_t)in_bytes, mine, g.first, g.count, st));
+      ctx->launches++;
+      CUDA_TRY(ctx, cudaEventRecord(c->events[gi], st));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(c->stream, c->events[gi], 0));
+      const int rc = gather_span(c, all, slab_bytes, g.out_lo & ~15ull,
+                                 std::min<uint64_t>((g.out_hi + 15) & ~15ull, slab_bytes), mode, root);
+      if (rc)
+        return rc;
+    }
+    p->last_stream = st;
+    p->ran = true;
+  } else {
+    const int rc0 = rsb200_plan_run(p, d_in, in_bytes, mine, slab_bytes, stream);
+    if (rc0)
+      return rc0;
+    CUDA_TRY(ctx, cudaEventRecord(c->done, st));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(c->stream, c->done, 0));
+    const int rc = gather_span(c, all, slab_bytes, 0, p->need_out, mode, root);
+    if (rc)
+      return rc;
+  }
+  // `stream` continues only when the transfers are done
+  CUDA_TRY(ctx, cudaEventRecord(c->done, c->stream));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(st, c->done, 0));
   return RSB200_OK;
 }
 

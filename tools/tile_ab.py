@@ -28,8 +28,8 @@ VARIANTS = [
     ("tile_r2_np320", dict(RSB200_TILE_R="2", RSB200_TILE_NPIECES="320")),
 ]
 KEYS = ("RSB200_LJPEG_PATH", "RSB200_TILE_R", "RSB200_TILE_PREROLL", "RSB200_TILE_NPIECES")
-PHASES = ["wait TMA", "B unstuff", "C sync", "D decode", "finish", "E1/E2 sums", "E3 stores",
-          "E4 carry", "chunk carry"]
+PHASES = ["wait TMA", "B unstuff(rest)", "C sync", "D decode", "finish", "E1/E2 sums", "E3 stores",
+          "E4 carry", "chunk carry", "B1 pass1", "B2 vote/marker", "B3 scan", "B4 pass2a", "B5 pass2b", "B6 barrier"]
 
 
 def main():
