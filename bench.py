@@ -234,10 +234,31 @@ FRAMES_TOTAL = 256      # configs[4]: 256-frame batch, sharded 256/N per GPU (st
 SEED0 = 12345           # frame i is synth.image_model(W, H, SEED0 + i)
 
 
-def _weights():
+_WTS = {}
+
+
+def _weights(w=W, h=H):
     """Per-pixel weights of the second checksum (uint64 wrap-around arithmetic)."""
-    y, x = np.mgrid[0:H, 0:W].astype(np.uint64)
-    return ((x * np.uint64(31) + y * np.uint64(17)) & np.uint64(0xFFFF)) | np.uint64(1)
+    if (w, h) not in _WTS:
+        x = np.arange(w, dtype=np.uint64)[None, :]
+        y = np.arange(h, dtype=np.uint64)[:, None]
+        _WTS[(w, h)] = ((x * np.uint64(31) + y * np.uint64(17)) & np.uint64(0xFFFF)) | np.uint64(1)
+    return _WTS[(w, h)]
+
+
+def frame_image(w, h, seed):
+    """Same pixels as oracle.synth.image_model(w, h, seed) (px = (2000 + ((7x+3y)&1023)
+    + noise6 - 32) & 0x3FFF), without the full-size coordinate grids (tests/test_bench_synth.py
+    pins the equality)."""
+    from oracle import synth
+    r = synth.lcg_u32(w * h, seed).reshape(h, w)
+    x = np.arange(w, dtype=np.uint32)[None, :]
+    y = np.arange(h, dtype=np.uint32)[:, None]
+    v = (np.uint32(7) * x + np.uint32(3) * y) & np.uint32(1023)
+    v += np.uint32(2000 - 32)
+    v += r >> np.uint32(26)
+    v &= np.uint32(0x3FFF)
+    return v.astype(np.uint16)
 
 
 def _gen_frame(job):
@@ -248,7 +269,7 @@ def _gen_frame(job):
     from oracle import synth
     import rawspeed_b200 as rs
     from helpers import dng_ljpeg_scans
-    img = synth.image_model(W, H, seed)
+    img = frame_image(W, H, seed)
     t = synth.make_dng_ljpeg(img, 256, 256)
     assert t.blob.size <= cap, (t.blob.size, cap)
     shm = shared_memory.SharedMemory(name=shm_name)
@@ -331,7 +352,7 @@ class LJpegBatch:
             s1 = int((v * wts).sum().item()) & 0xFFFFFFFFFFFFFFFF
             ok = ok and s0 == r[4] and s1 == r[5]
         for k in full_frames:
-            img = synth.image_model(W, H, self.recs[k][0])
+            img = synth.image_model(W, H, self.recs[k][0])  # (the oracle's generator, not the fast copy)
             g = d_out[k * self.ob:k * self.ob + H * self.out_pitch].cpu().numpy().view(np.uint16).reshape(H, self.out_pitch // 2)
             ok = ok and bool(np.array_equal(g[:, :W], img))
         return ok

@@ -53,7 +53,9 @@ inline const char* badpix_build(const rsb200_badpix_job& j, const uint32_t* posi
         continue;
       for (uint32_t bi = 0; bi < 4; ++bi)
         for (uint32_t bj = 0; bj < 8; ++bj)
-          if ((block[bi] >> bj) & 1)
+          if (((block[bi] >> bj) & 1) && x * 32 + bi * 8 + bj < j.width)
+            // (a bit of a caller-supplied prior_map behind the last column is not a pixel: the
+            //  kernel stores to the column unconditionally)
             list->push_back((y << 16) | (x * 32 + bi * 8 + bj));
     }
   o.count = (uint32_t)list->size() - o.first;

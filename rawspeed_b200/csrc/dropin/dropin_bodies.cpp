@@ -270,6 +270,9 @@ void AbstractDngDecompressor::decompress() const {
                 [](const TileJob& a, const TileJob& b) { return a.data < b.data; });
       std::vector<rsb200_huff_table> tabs;
       std::vector<rsb200_ljpeg_scan> scans;
+      // every tile was recorded: together they cover the whole image (DngTilingDescription), so the
+      // current image contents need not travel to the device first
+      const bool covers_image = batch.jobs.size() == slices.size() && slices.size() == dsc.numTiles;
       try {
         for (const TileJob& j : batch.jobs)
           append_scans(j, lo, mRaw->getCpp(), 0, pitch, tabs, scans, nullptr);
@@ -282,7 +285,8 @@ void AbstractDngDecompressor::decompress() const {
         rc = rsb200_plan_run_host_image(pg.p, lo, static_cast<size_t>(hi - lo),
                                         reinterpret_cast<uint8_t*>(&img(0, 0)), pitch,
                                         static_cast<uint32_t>(img.width()) * 2u,
-                                        static_cast<uint32_t>(img.height()), /*partial=*/1);
+                                        static_cast<uint32_t>(img.height()),
+                                        /*partial=*/covers_image ? 0 : 1);
         if (rc != RSB200_OK)
           throw_status(rc, "AbstractDngDecompressor");
         std::vector<rsb200_scan_result> res(scans.size());

@@ -2274,15 +2274,27 @@ AbstractDngDecompressor::PreparedLJpeg AbstractDngDecompressor::prepareLJpeg(uns
       o.err = err.what();
       o.ioe = true;
       o.scans.clear();
+    } catch (const std::exception& err) {
+      // (bad_alloc, system_error ...: must not escape a std::thread; reported like a tile error)
+      o.err = std::string("rawspeed_b200 host half: ") + err.what();
+      o.scans.clear();
+    } catch (...) {
+      o.err = "rawspeed_b200 host half: unknown exception";
+      o.scans.clear();
     }
   };
+  bool forced = false;
   if (threads == 0) {
     threads = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    if (const char* env = std::getenv("RSB200_HOST_THREADS"))
+    if (const char* env = std::getenv("RSB200_HOST_THREADS")) {
       threads = (unsigned)std::max(1, std::atoi(env));
+      forced = true; // the override is taken as is (it may raise the count above the default clamp)
+    }
   }
   // worth a thread: >= 16 tiles and >= 1 MiB of tile data each
-  threads = (unsigned)std::min<size_t>(threads, std::min((slices.size() + 15) / 16, out.span / (1u << 20) + 1));
+  if (!forced)
+    threads = (unsigned)std::min<size_t>(threads, std::min((slices.size() + 15) / 16, out.span / (1u << 20) + 1));
+  threads = (unsigned)std::min<size_t>(threads, std::max<size_t>(1, slices.size()));
   if (threads <= 1) {
     for (size_t i = 0; i < slices.size(); ++i)
       work(i);
@@ -2352,9 +2364,15 @@ void AbstractDngDecompressor::decompressLJpeg() const {
                                        pl.scans.data(), (int)pl.scans.size(), &pg.p),
               "rsb200_ljpeg_plan_create");
   RawImage img = mRaw;
-  runOnImage(pg.p, pl.base, pl.span, img, /*partial=*/true);
+  // every tile was prepared: together they cover the whole image (DngTilingDescription), so its
+  // current contents need not travel to the device first
+  const bool covers = pl.errors.empty() && pl.tiles.size() == slices.size() && slices.size() == dsc.numTiles;
+  runOnImage(pg.p, pl.base, pl.span, img, /*partial=*/!covers);
   std::vector<rsb200_scan_result> res(pl.scans.size());
-  (void)rsb200_plan_results(pg.p, res.data(), (int)res.size());
+  // (a CUDA / argument failure must not read as "every tile decoded")
+  const int rrc = rsb200_plan_results(pg.p, res.data(), (int)res.size());
+  if (rrc != RSB200_OK && rrc != RSB200_ERR_RDE && rrc != RSB200_ERR_IOE)
+    engineCheck(rrc, "rsb200_plan_results");
   for (auto& t : pl.tiles) {
     try {
       const uint32_t consumed = t.dec->scan()->finish(res.data() + t.firstScan, t.nScans);

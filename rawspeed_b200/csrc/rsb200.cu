@@ -36,6 +36,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace rsb200;
@@ -53,6 +54,12 @@ struct rsb200_ctx {
   size_t d_out_cap = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr}; // H2D / kernel / D2H overlap
+  // pinned staging for callers whose buffers are pageable (a RawImage is): grow only
+  uint8_t* h_in = nullptr;
+  size_t h_in_cap = 0;
+  uint8_t* h_out = nullptr;
+  size_t h_out_cap = 0;
+  std::vector<cudaEvent_t> stage_events;
 };
 
 static int set_err(rsb200_ctx* c, int code, const char* fmt, ...) {
@@ -285,6 +292,12 @@ extern "C" void rsb200_destroy(rsb200_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_in);
   cudaFree(c->d_out);
+  if (c->h_in)
+    cudaFreeHost(c->h_in);
+  if (c->h_out)
+    cudaFreeHost(c->h_out);
+  for (cudaEvent_t e : c->stage_events)
+    cudaEventDestroy(e);
   if (c->stream)
     cudaStreamDestroy(c->stream);
   for (int i = 0; i < 3; ++i)
@@ -2101,6 +2114,79 @@ static int run_host_unpack_pipelined(rsb200_plan* p, const uint8_t* in, size_t i
   return RSB200_OK;
 }
 
+// ---- host buffers that are not page-locked ----
+// cudaMemcpyAsync from / to pageable memory is staged by the driver on one thread (~9 GB/s
+// measured: 15 ms for the 137 MB of a 45 MP frame).  The library stages such buffers itself
+// through its own pinned memory with several copying threads, slice by slice, overlapped with the
+// transfers and the kernels.
+constexpr size_t STAGE_LIMIT = 768ull << 20; // beyond this the driver's path is used
+static bool host_is_pageable(const void* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+static void parallel_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+  const size_t kSlice = 2ull << 20;
+  unsigned nt = (unsigned)std::min<size_t>(12, n / kSlice);
+  if (const char* e = getenv("RSB200_COPY_THREADS"))
+    nt = (unsigned)std::max(1, atoi(e));
+  if (nt <= 1) {
+    memcpy(dst, src, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+  for (unsigned t = 1; t < nt; ++t) {
+    const size_t a = std::min(n, per * t), b = std::min(n, per * (t + 1));
+    if (b > a)
+      th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+  }
+  memcpy(dst, src, std::min(n, per));
+  for (std::thread& t : th)
+    t.join();
+}
+// rows of row_bytes out of a pitch-strided source into a pitch-strided destination
+static void parallel_copy_rows(uint8_t* dst, const uint8_t* src, size_t pitch, size_t row_bytes,
+                               size_t rows) {
+  if (row_bytes == pitch) {
+    parallel_copy(dst, src, pitch * rows);
+    return;
+  }
+  unsigned nt = (unsigned)std::min<size_t>(12, (row_bytes * rows) / (2ull << 20));
+  if (nt <= 1) {
+    for (size_t r = 0; r < rows; ++r)
+      memcpy(dst + r * pitch, src + r * pitch, row_bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (rows + nt - 1) / nt;
+  auto work = [=](size_t r0, size_t r1) {
+    for (size_t r = r0; r < r1; ++r)
+      memcpy(dst + r * pitch, src + r * pitch, row_bytes);
+  };
+  for (unsigned t = 1; t < nt; ++t)
+    if (std::min(rows, per * t) < std::min(rows, per * (t + 1)))
+      th.emplace_back(work, std::min(rows, per * t), std::min(rows, per * (t + 1)));
+  work(0, std::min(rows, per));
+  for (std::thread& t : th)
+    t.join();
+}
+static int ensure_host_cap(rsb200_ctx* ctx, uint8_t** buf, size_t* cap, size_t need) {
+  need = (need + 4095) & ~(size_t)4095;
+  if (*cap >= need)
+    return RSB200_OK;
+  if (*buf)
+    cudaFreeHost(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  CUDA_TRY(ctx, cudaHostAlloc((void**)buf, need + 4096, cudaHostAllocDefault));
+  *cap = need;
+  return RSB200_OK;
+}
+
 static cudaError_t launch_tile_range(const rsb200_plan* p, const uint8_t* d_in, uint64_t in_bytes,
                                      uint8_t* d_out, uint32_t first, uint32_t count,
                                      cudaStream_t st) {
@@ -2120,22 +2206,73 @@ static cudaError_t launch_tile_range(const rsb200_plan* p, const uint8_t* d_in, 
 // the decode of the current one.  Spans of neighbouring groups may overlap (tiles of one tile row
 // in two groups): every byte's last download happens after its last write, whatever the order.
 static int run_host_tile_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_bytes,
-                                   uint8_t* out, size_t out_bytes) {
+                                   uint8_t* out, size_t out_bytes, uint32_t pitch = 0,
+                                   uint32_t row_bytes = 0) {
   rsb200_ctx* ctx = p->ctx;
+  const bool stage_in = in_bytes <= STAGE_LIMIT && host_is_pageable(in);
+  const bool stage_out = out_bytes <= STAGE_LIMIT && host_is_pageable(out);
+  if (stage_in) {
+    const int rc = ensure_host_cap(ctx, &ctx->h_in, &ctx->h_in_cap, in_bytes + 16);
+    if (rc)
+      return rc;
+  }
+  if (stage_out) {
+    const int rc = ensure_host_cap(ctx, &ctx->h_out, &ctx->h_out_cap, out_bytes);
+    if (rc)
+      return rc;
+    while (ctx->stage_events.size() < p->tile_groups.size()) {
+      cudaEvent_t e;
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->stage_events.push_back(e);
+    }
+  }
+  const bool rows2d = pitch && row_bytes && row_bytes < pitch;
   for (size_t gi = 0; gi < p->tile_groups.size(); ++gi) {
     const rsb200_plan::TileGroup& g = p->tile_groups[gi];
     cudaStream_t st = ctx->pipe[gi % 3];
-    const uint64_t i1 = std::min<uint64_t>(g.in_hi, (in_bytes + 15) & ~15ull);
-    const uint64_t i1c = std::min<uint64_t>(i1, in_bytes);
+    const uint64_t i1c = std::min<uint64_t>(g.in_hi, in_bytes);
     const uint64_t o1 = std::min<uint64_t>(g.out_hi, out_bytes);
-    if (i1c > g.in_lo)
-      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in + g.in_lo, in + g.in_lo, i1c - g.in_lo,
-                                    cudaMemcpyHostToDevice, st));
+    if (i1c > g.in_lo) {
+      const uint8_t* src = in + g.in_lo;
+      if (stage_in) {
+        parallel_copy(ctx->h_in + g.in_lo, src, i1c - g.in_lo);
+        src = ctx->h_in + g.in_lo;
+      }
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in + g.in_lo, src, i1c - g.in_lo, cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(ctx, launch_tile_range(p, ctx->d_in, (uint64_t)in_bytes, ctx->d_out, g.first, g.count, st));
     ctx->launches++;
-    if (o1 > g.out_lo)
-      CUDA_TRY(ctx, cudaMemcpyAsync(out + g.out_lo, ctx->d_out + g.out_lo, o1 - g.out_lo,
-                                    cudaMemcpyDeviceToHost, st));
+    if (o1 > g.out_lo) {
+      uint8_t* dst = (stage_out ? ctx->h_out : out) + g.out_lo;
+      if (rows2d && !stage_out) {
+        // whole rows of the span, only row_bytes of each (the caller's row padding stays untouched)
+        const uint64_t r0 = g.out_lo / pitch, r1 = (o1 + pitch - 1) / pitch;
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(out + r0 * pitch, pitch, ctx->d_out + r0 * pitch, pitch, row_bytes,
+                                        r1 - r0, cudaMemcpyDeviceToHost, st));
+      } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, ctx->d_out + g.out_lo, o1 - g.out_lo, cudaMemcpyDeviceToHost, st));
+      }
+      if (stage_out)
+        CUDA_TRY(ctx, cudaEventRecord(ctx->stage_events[gi], st));
+    }
+  }
+  if (stage_out) {
+    // copy every group out of the staging as soon as its download has landed
+    for (size_t gi = 0; gi < p->tile_groups.size(); ++gi) {
+      const rsb200_plan::TileGroup& g = p->tile_groups[gi];
+      const uint64_t o1 = std::min<uint64_t>(g.out_hi, out_bytes);
+      if (o1 <= g.out_lo)
+        continue;
+      CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_events[gi]));
+      if (rows2d) {
+        const uint64_t r0 = g.out_lo / pitch, r1 = (o1 + pitch - 1) / pitch;
+        // (rows shared with a neighbouring group are copied by both, after both downloads: the
+        //  later copy carries the final bytes, see above)
+        parallel_copy_rows(out + r0 * pitch, ctx->h_out + r0 * pitch, pitch, row_bytes, r1 - r0);
+      } else {
+        parallel_copy(out + g.out_lo, ctx->h_out + g.out_lo, o1 - g.out_lo);
+      }
+    }
   }
   for (int i = 0; i < 3; ++i)
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->pipe[i]));
@@ -2165,15 +2302,38 @@ extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in
   if (!partial && p->kind == 1 && p->tile_groups.size() >= 2 && !getenv("RSB200_NO_PIPELINE"))
     return run_host_tile_pipelined(p, in, in_bytes, out, out_bytes);
   cudaStream_t st = ctx->stream;
+  const bool stage_in = in_bytes && in_bytes <= STAGE_LIMIT && host_is_pageable(in);
+  const bool stage_out = out_bytes <= STAGE_LIMIT && host_is_pageable(out);
+  const uint8_t* hin = in;
+  if (stage_in) {
+    rc = ensure_host_cap(ctx, &ctx->h_in, &ctx->h_in_cap, in_bytes + 16);
+    if (rc)
+      return rc;
+    parallel_copy(ctx->h_in, in, in_bytes);
+    hin = ctx->h_in;
+  }
+  if (stage_out) {
+    rc = ensure_host_cap(ctx, &ctx->h_out, &ctx->h_out_cap, out_bytes);
+    if (rc)
+      return rc;
+  }
   if (in_bytes)
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
-  if (partial)
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_out, out, out_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, hin, in_bytes, cudaMemcpyHostToDevice, st));
+  if (partial) {
+    const uint8_t* hout = out;
+    if (stage_out) {
+      parallel_copy(ctx->h_out, out, out_bytes);
+      hout = ctx->h_out;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_out, hout, out_bytes, cudaMemcpyHostToDevice, st));
+  }
   rc = rsb200_plan_run(p, ctx->d_in, in_bytes, ctx->d_out, out_bytes, (void*)st);
   if (rc)
     return rc;
-  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(stage_out ? ctx->h_out : out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (stage_out)
+    parallel_copy(out, ctx->h_out, out_bytes);
   return RSB200_OK;
 }
 
@@ -2193,17 +2353,49 @@ extern "C" int rsb200_plan_run_host_image(rsb200_plan* p, const uint8_t* in, siz
   rc = ensure_cap(ctx, &ctx->d_out, &ctx->d_out_cap, out_bytes);
   if (rc)
     return rc;
+  if (in_bytes < p->need_in || out_bytes < p->need_out)
+    return set_err(ctx, RSB200_ERR_ARG, "plan_run_host_image: buffers too small");
+  if (!partial && p->kind == 1 && p->tile_groups.size() >= 2 && !getenv("RSB200_NO_PIPELINE"))
+    return run_host_tile_pipelined(p, in, in_bytes, out, out_bytes, pitch, row_bytes);
   cudaStream_t st = ctx->stream;
+  // pageable buffers go through the library's pinned staging (several copying threads)
+  const bool stage_in = in_bytes && in_bytes <= STAGE_LIMIT && host_is_pageable(in);
+  const bool stage_out = out_bytes <= STAGE_LIMIT && host_is_pageable(out);
+  const uint8_t* hin = in;
+  if (stage_in) {
+    rc = ensure_host_cap(ctx, &ctx->h_in, &ctx->h_in_cap, in_bytes + 16);
+    if (rc)
+      return rc;
+    parallel_copy(ctx->h_in, in, in_bytes);
+    hin = ctx->h_in;
+  }
+  if (stage_out) {
+    rc = ensure_host_cap(ctx, &ctx->h_out, &ctx->h_out_cap, out_bytes);
+    if (rc)
+      return rc;
+  }
   if (in_bytes)
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, in, in_bytes, cudaMemcpyHostToDevice, st));
-  if (partial)
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_out, out, out_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in, hin, in_bytes, cudaMemcpyHostToDevice, st));
+  if (partial) {
+    const uint8_t* hout = out;
+    if (stage_out) {
+      parallel_copy(ctx->h_out, out, out_bytes);
+      hout = ctx->h_out;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_out, hout, out_bytes, cudaMemcpyHostToDevice, st));
+  }
   rc = rsb200_plan_run(p, ctx->d_in, in_bytes, ctx->d_out, out_bytes, (void*)st);
   if (rc)
     return rc;
-  CUDA_TRY(ctx, cudaMemcpy2DAsync(out, pitch, ctx->d_out, pitch, row_bytes, rows,
-                                  cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  if (stage_out) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    parallel_copy_rows(out, ctx->h_out, pitch, row_bytes, rows);
+  } else {
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(out, pitch, ctx->d_out, pitch, row_bytes, rows,
+                                    cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  }
   return RSB200_OK;
 }
 
