@@ -4155,3 +4155,23 @@ int rso_sixteen_bit_lookup(rso_image* img, const uint16_t* table, int dither, rs
   }
   return RSO_OK;
 }
+
+/* ---- synthetic frame generator (see rs_oracle.h) ---- */
+void rso_image_model(uint32_t w, uint32_t h, uint32_t seed, uint16_t* out, uint64_t sums[2]) {
+  uint32_t s = seed;
+  uint64_t s0 = 0, s1 = 0;
+  for (uint32_t y = 0; y < h; ++y) {
+    uint16_t* row = out + (size_t)y * w;
+    for (uint32_t x = 0; x < w; ++x) {
+      s = s * 1664525u + 1013904223u;
+      const uint32_t v = (2000u + ((7u * x + 3u * y) & 1023u) + (s >> 26) - 32u) & 0x3FFFu;
+      row[x] = (uint16_t)v;
+      s0 += v;
+      s1 += (uint64_t)v * ((((uint64_t)31 * x + (uint64_t)17 * y) & 0xFFFFu) | 1u);
+    }
+  }
+  if (sums) {
+    sums[0] = s0;
+    sums[1] = s1;
+  }
+}

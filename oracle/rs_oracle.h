@@ -345,6 +345,13 @@ int64_t rso_cr2_encode(const rso_image* img, int n_comp, int x_s_f, int y_s_f,
                        int last_slice_w, int prec, const rso_dht* tabs, int ntab,
                        const uint8_t* tab_of_comp, uint8_t* out, uint64_t cap);
 
+
+/* Synthetic frame of SURVEY 8(d) C3 (test inputs; same pixels as synth.image_model):
+ * px(x,y) = (2000 + ((7x+3y)&1023) + noise6 - 32) & 0x3FFF, noise6 = bits 31..26 of the LCG
+ * s' = s*1664525 + 1013904223 stepped once per pixel in raster order from `seed`.
+ * sums[0] = sum of the pixels, sums[1] = sum of pixel * (((31x + 17y) & 0xFFFF) | 1), both mod 2^64. */
+void rso_image_model(uint32_t w, uint32_t h, uint32_t seed, uint16_t* out, uint64_t sums[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,19 @@ def lcg_u32(n, seed):
     return out
 
 
+def image_model_c(w, h, seed):
+    """image_model(w, h, seed) (non-wild, 14 bit) by the C oracle library, with the two checksums
+    bench.py compares on the GPU: (image, sum, weighted sum)."""
+    import ctypes as C
+    L = port.lib()
+    L.rso_image_model.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.rso_image_model.restype = None
+    img = np.empty((h, w), dtype=np.uint16)
+    sums = (C.c_uint64 * 2)()
+    L.rso_image_model(w, h, seed, img.ctypes.data, sums)
+    return img, int(sums[0]), int(sums[1])
+
+
 def lcg_bytes(n, seed):
     """byte_k = s_k >> 24 (SURVEY 8d C1/C2 input)."""
     return (lcg_u32(n, seed) >> np.uint32(24)).astype(np.uint8)

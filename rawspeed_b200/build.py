@@ -14,7 +14,7 @@ HOST_LIB = os.path.join(HERE, "librawspeed_b200_host.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-    "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+    "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared",
 ]
 
 
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     dev_src = _sources("", (".cu", ".cuh")) + [hdr]
     if force or _newer(LIB, dev_src):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-            "-o", LIB, os.path.join(HERE, "csrc", "rsb200.cu"), "-ldl"]
+            "-o", LIB, os.path.join(HERE, "csrc", "rsb200.cu"), "-ldl", "-lgomp"]
         subprocess.check_call(cmd, cwd=ROOT)
     host_src = _sources("host", (".cpp", ".h"))
     if host_src and (force or _newer(HOST_LIB, host_src + [hdr, LIB])):

@@ -1339,4 +1339,110 @@ __global__ void __launch_bounds__(TL_NT, (R == 1 ? RSB200_TILE_CTAS1 : 2))
 }
 #endif
 
+
+#ifndef RSB200_EMU
+// ------------------------------------------------------------------
+// K2C2 `k2_clean2_kernel`: the unstuffing pre-pass of the one-thread-per-segment path (K2T,
+// ljpeg_thread.cuh) built from this file's stage B: one CTA per segment, 64-byte pieces in
+// registers, whole-word writes for the pieces without a stuffing byte.  Same outputs as
+// k2_clean_kernel (ljpeg_clean.cuh): clean big-endian words, one anchor per 256 raw bytes, the
+// clean length / marker flag -- at ~1/4 of its instructions per byte for DNG-size tiles.
+// ------------------------------------------------------------------
+__global__ void __launch_bounds__(TL_NT, 4)
+    k2_clean2_kernel(const uint8_t* __restrict__ in, uint64_t in_total,
+                     const DevScan* __restrict__ scans, const uint32_t* __restrict__ scan_ids,
+                     uint32_t nids, const DevTScan* __restrict__ tscans,
+                     uint32_t* __restrict__ clean, uint32_t* __restrict__ anchors,
+                     DevTInfo* __restrict__ infos) {
+  extern __shared__ __align__(128) uint8_t tl_smem_raw[];
+  TileShared<1>& sh = *reinterpret_cast<TileShared<1>*>(tl_smem_raw);
+  using G = TileGeom<1>;
+  const int tid = threadIdx.x;
+  const uint32_t id = blockIdx.x;
+  if (id >= nids)
+    return;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[scan_ids[id]]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.sc);
+    for (int i = tid; i < (int)(sizeof(DevScan) / 4); i += TL_NT)
+      dst[i] = src[i];
+  }
+  if (tid == 0) {
+    mbar_init(&sh.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const DevScan& sc = sh.sc;
+  const DevTScan ts = tscans[id];
+  const uint64_t abase = sc.in_offset & ~15ull;
+  TileStream st;
+  st.skew = (uint32_t)(sc.in_offset - abase);
+  st.gbase = in + abase;
+  st.limit = st.skew + sc.in_size;
+  st.readable = ((in_total + 15) & ~15ull) - abase;
+  st.npieces = (uint32_t)G::NPIECE & ~3u; // chunk bases are multiples of 256 raw bytes (anchors)
+  st.chunk_raw = st.npieces * TL_PIECE;
+  uint32_t* cw = clean + ts.clean_off;
+  uint32_t* anc = anchors + ts.anchor_off;
+  if (tid == 0)
+    tl_issue_chunk<1>(sh, st, 0);
+  TileCarry cy;
+  cy.tail_len = 0;
+  cy.prev_ff = 0;
+  uint32_t emitted = 0; // clean bytes produced by the chunks so far
+  uint32_t wout = 0;    // words written so far (emitted - 4 * wout bytes wait at the front of ub)
+  const uint32_t sb_ub = smem_u32(sh.ub);
+  TL_TICK_INIT;
+  for (uint32_t chunk = 0;; ++chunk) {
+    mbar_wait(&sh.bar, chunk & 1);
+    const TileChunk co = tl_unstuff<1>(sh, st, cy, chunk TL_TICK_PASS);
+    const uint32_t cbase = chunk * st.chunk_raw;
+    // the staging is free again: fetch the next chunk while this one is written out
+    const bool more = !co.final_chunk;
+    if (more && tid == 0) {
+      fence_proxy_async();
+      tl_issue_chunk<1>(sh, st, chunk + 1);
+    }
+    // anchors: clean bytes in front of every 256-byte raw offset of this chunk
+    for (uint32_t pi = 4u * (uint32_t)tid; pi < st.npieces; pi += 4u * TL_NT) {
+      const uint32_t a = (cbase + pi * TL_PIECE) >> T_ANCHOR_SHIFT;
+      if (a < ts.n_anchor)
+        anc[a] = emitted + sh.anchor[pi] - cy.tail_len;
+    }
+    const uint32_t len = co.len; // carried bytes + this chunk's
+    const uint32_t nw = co.final_chunk ? (len + 3u) / 4u + T_PAD_WORDS : len / 4u;
+    if (co.final_chunk) { // zero words behind the data (tl_unstuff zeroed 64 bytes behind len)
+      __syncthreads();
+    }
+    for (uint32_t w = tid; w < nw; w += TL_NT)
+      if (wout + w < ts.cap_words)
+        cw[wout + w] = lds_u32<0>(sb_ub + 4u * w);
+    emitted += co.total_emit;
+    if (co.final_chunk) {
+      if (tid == 0) {
+        infos[id].clean_len = emitted;
+        infos[id].marker = co.mpos != TL_NOPOS ? 1u : 0u;
+      }
+      // the anchors behind the end of the data
+      const uint32_t a0 = ((cbase + st.chunk_raw) >> T_ANCHOR_SHIFT);
+      for (uint32_t a = a0 + tid; a < ts.n_anchor; a += TL_NT)
+        anc[a] = emitted;
+      break;
+    }
+    // the bytes of the last, incomplete word stay at the front of ub
+    const uint32_t keep = len & 3u;
+    uint32_t kb = 0;
+    if ((uint32_t)tid < keep)
+      kb = reinterpret_cast<uint8_t*>(sh.ub)[((len & ~3u) + tid) ^ 3u];
+    __syncthreads();
+    if ((uint32_t)tid < keep)
+      reinterpret_cast<uint8_t*>(sh.ub)[tid ^ 3u] = (uint8_t)kb;
+    wout += len / 4u;
+    cy.tail_len = keep;
+    cy.prev_ff = sh.prev_ff_next;
+    __syncthreads();
+  }
+}
+#endif
+
 } // namespace rsb200

@@ -41,6 +41,85 @@
 
 using namespace rsb200;
 
+// ---- allocation: plans are created and destroyed per frame by the drop-in callers (one
+// AbstractDngDecompressor::decompress() = one plan), so their device memory comes from the
+// device's stream-ordered pool (kept, not returned to the driver) and their small pinned result
+// buffers from a process-wide cache; cudaMalloc / cudaFree (which synchronises the device) and
+// cudaMallocHost (milliseconds) are off that path.  The big grow-only staging buffers of a
+// context (ensure_cap / ensure_host_cap) keep using the plain calls. ----
+#include <mutex>
+static cudaError_t rsb_dev_alloc(void** p, size_t n) {
+  cudaError_t e = cudaMallocAsync(p, n, (cudaStream_t)0);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize((cudaStream_t)0);
+  if (e != cudaSuccess) { // (no pool support: fall back to the plain allocator)
+    cudaGetLastError();
+    e = cudaMalloc(p, n);
+  }
+  return e;
+}
+template <typename T> static cudaError_t rsb_dev_alloc(T** p, size_t n) {
+  return rsb_dev_alloc(reinterpret_cast<void**>(p), n);
+}
+static cudaError_t rsb_dev_free(void* p) {
+  if (!p)
+    return cudaSuccess;
+  cudaError_t e = cudaFreeAsync(p, (cudaStream_t)0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    e = cudaFree(p);
+  }
+  return e;
+}
+namespace {
+struct HostCache {
+  std::mutex m;
+  std::multimap<size_t, void*> free_blocks;
+  std::map<void*, size_t> live;
+};
+HostCache& host_cache() {
+  static HostCache* c = new HostCache(); // (never destroyed: pinned blocks live as long as the process)
+  return *c;
+}
+} // namespace
+static cudaError_t rsb_host_alloc(void** p, size_t n) {
+  size_t cap = 256;
+  while (cap < n)
+    cap <<= 1;
+  HostCache& c = host_cache();
+  {
+    std::lock_guard<std::mutex> g(c.m);
+    auto it = c.free_blocks.find(cap);
+    if (it != c.free_blocks.end()) {
+      *p = it->second;
+      c.free_blocks.erase(it);
+      c.live[*p] = cap;
+      return cudaSuccess;
+    }
+  }
+  const cudaError_t e = cudaMallocHost(p, cap);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> g(c.m);
+    c.live[*p] = cap;
+  }
+  return e;
+}
+template <typename T> static cudaError_t rsb_host_alloc(T** p, size_t n) {
+  return rsb_host_alloc(reinterpret_cast<void**>(p), n);
+}
+static cudaError_t rsb_host_free(void* p) {
+  if (!p)
+    return cudaSuccess;
+  HostCache& c = host_cache();
+  std::lock_guard<std::mutex> g(c.m);
+  auto it = c.live.find(p);
+  if (it == c.live.end())
+    return cudaFreeHost(p);
+  c.free_blocks.emplace(it->second, p);
+  c.live.erase(it);
+  return cudaSuccess;
+}
+
 // ------------------------------------------------------------------
 struct rsb200_ctx {
   int device = 0;
@@ -212,6 +291,7 @@ struct rsb200_plan {
   DevTileParam* d_tile_params = nullptr;
   int ntile = 0;
   int tile_r = 1;
+  bool clean2 = false; // thread path: k2_clean2_kernel instead of k2_clean_kernel
   uint32_t* d_thread_ids = nullptr; // segments decoded one per thread (K2C + K2T)
   DevTScan* d_tscans = nullptr;
   DevTInfo* d_tinfos = nullptr;
@@ -274,7 +354,18 @@ extern "C" int rsb200_create(int device, rsb200_ctx** out) {
                        (int)fused_smem_bytes(4));
   cudaFuncSetAttribute(lookup_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES);
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      cudaGetLastError();
+    }
+  }
   cudaFuncSetAttribute(k2_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)tile_smem_bytes<1>());
+  cudaFuncSetAttribute(k2_clean2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)tile_smem_bytes<1>());
   cudaFuncSetAttribute(k2_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)tile_smem_bytes<2>());
@@ -432,7 +523,7 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
     }
     g.njobs = (int)kv.second.size();
     g.nblocks = nb;
-    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(UnpackJobDev) * kv.second.size());
+    cudaError_t e = rsb_dev_alloc(&g.d_jobs, sizeof(UnpackJobDev) * kv.second.size());
     if (e == cudaSuccess)
       e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(UnpackJobDev) * kv.second.size(),
                      cudaMemcpyHostToDevice);
@@ -455,7 +546,7 @@ extern "C" int rsb200_unpack_plan_create(rsb200_ctx* ctx, const rsb200_unpack_jo
     g.njobs = (int)kv.second.size();
     g.nblocks = nb;
     g.h_jobs = kv.second;
-    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(UnpackFastJobDev) * kv.second.size());
+    cudaError_t e = rsb_dev_alloc(&g.d_jobs, sizeof(UnpackFastJobDev) * kv.second.size());
     if (e == cudaSuccess)
       e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(UnpackFastJobDev) * kv.second.size(),
                      cudaMemcpyHostToDevice);
@@ -540,7 +631,7 @@ extern "C" int rsb200_raw_plan_create(rsb200_ctx* ctx, const rsb200_raw_job* job
   }
   if (ntables > 0) {
     const size_t tb = (size_t)ntables * 65536u * sizeof(uint16_t);
-    cudaError_t e = cudaMalloc(&p->d_raw_tables, tb);
+    cudaError_t e = rsb_dev_alloc(&p->d_raw_tables, tb);
     if (e == cudaSuccess)
       e = cudaMemcpy(p->d_raw_tables, tables, tb, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -562,7 +653,7 @@ extern "C" int rsb200_raw_plan_create(rsb200_ctx* ctx, const rsb200_raw_job* job
     }
     g.total_items = (uint32_t)items;
     g.njobs = (int)kv.second.size();
-    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(RawJobDev) * kv.second.size());
+    cudaError_t e = rsb_dev_alloc(&g.d_jobs, sizeof(RawJobDev) * kv.second.size());
     if (e == cudaSuccess)
       e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(RawJobDev) * kv.second.size(),
                      cudaMemcpyHostToDevice);
@@ -643,10 +734,10 @@ extern "C" int rsb200_lookup_plan_create(rsb200_ctx* ctx, const rsb200_lookup_jo
   p->lookup_njobs = njobs;
   p->lookup_quads = (uint32_t)quads;
   const size_t tbytes = sizeof(uint16_t) * (size_t)ntables * (dither ? 131072u : 65536u);
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_lookup_jobs, sizeof(LookupJobDev) * hj.size()));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_lookup_jobs, sizeof(LookupJobDev) * hj.size()));
   CUDA_TRY(ctx, cudaMemcpy(p->d_lookup_jobs, hj.data(), sizeof(LookupJobDev) * hj.size(),
                            cudaMemcpyHostToDevice));
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_lookup_tables, tbytes));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_lookup_tables, tbytes));
   CUDA_TRY(ctx, cudaMemcpy(p->d_lookup_tables, tables, tbytes, cudaMemcpyHostToDevice));
   p->launches_per_run = 1;
   *out = holder.release();
@@ -681,14 +772,14 @@ extern "C" int rsb200_badpix_plan_create(rsb200_ctx* ctx, const rsb200_badpix_jo
     return set_err(ctx, RSB200_ERR_ARG, "badpix plan: too many bad pixels");
   p->badpix_njobs = njobs;
   p->badpix_total = (uint32_t)list.size();
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_badpix_jobs, sizeof(BadPixJobDev) * hj.size()));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_badpix_jobs, sizeof(BadPixJobDev) * hj.size()));
   CUDA_TRY(ctx, cudaMemcpy(p->d_badpix_jobs, hj.data(), sizeof(BadPixJobDev) * hj.size(),
                            cudaMemcpyHostToDevice));
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_badpix_list, sizeof(uint32_t) * (list.size() + 1)));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_badpix_list, sizeof(uint32_t) * (list.size() + 1)));
   if (!list.empty())
     CUDA_TRY(ctx, cudaMemcpy(p->d_badpix_list, list.data(), sizeof(uint32_t) * list.size(),
                              cudaMemcpyHostToDevice));
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_badpix_maps, maps.size() + 16));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_badpix_maps, maps.size() + 16));
   if (!maps.empty())
     CUDA_TRY(ctx, cudaMemcpy(p->d_badpix_maps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
   p->launches_per_run = p->badpix_total ? 1 : 0;
@@ -727,24 +818,24 @@ extern "C" int rsb200_dngop_plan_create(rsb200_ctx* ctx, const rsb200_dngop_job*
   }
   p->dngop_njobs = njobs;
   p->dngop_units = (uint32_t)units;
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_dngop_jobs, sizeof(DngOpJobDev) * hj.size()));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_dngop_jobs, sizeof(DngOpJobDev) * hj.size()));
   CUDA_TRY(ctx, cudaMemcpy(p->d_dngop_jobs, hj.data(), sizeof(DngOpJobDev) * hj.size(),
                            cudaMemcpyHostToDevice));
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_dngop_ops, sizeof(DngOpDev) * (ho.size() + 1)));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_dngop_ops, sizeof(DngOpDev) * (ho.size() + 1)));
   if (!ho.empty())
     CUDA_TRY(ctx, cudaMemcpy(p->d_dngop_ops, ho.data(), sizeof(DngOpDev) * ho.size(),
                              cudaMemcpyHostToDevice));
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_dngop_tables, sizeof(uint16_t) * 65536 * (size_t)(ntables + 1)));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_dngop_tables, sizeof(uint16_t) * 65536 * (size_t)(ntables + 1)));
   if (ntables)
     CUDA_TRY(ctx, cudaMemcpy(p->d_dngop_tables, tables, sizeof(uint16_t) * 65536 * (size_t)ntables,
                              cudaMemcpyHostToDevice));
-  CUDA_TRY(ctx, cudaMalloc((void**)&p->d_dngop_deltas, sizeof(uint32_t) * (size_t)(ndeltas + 1)));
+  CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_dngop_deltas, sizeof(uint32_t) * (size_t)(ndeltas + 1)));
   if (ndeltas)
     CUDA_TRY(ctx, cudaMemcpy(p->d_dngop_deltas, deltas, sizeof(uint32_t) * (size_t)ndeltas,
                              cudaMemcpyHostToDevice));
   if (p->pana_zero_slots) {
-    CUDA_TRY(ctx, cudaMalloc((void**)&p->d_pana_zero_count, sizeof(uint32_t) * (size_t)p->pana_zero_slots));
-    CUDA_TRY(ctx, cudaMalloc((void**)&p->d_pana_zero_list,
+    CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_pana_zero_count, sizeof(uint32_t) * (size_t)p->pana_zero_slots));
+    CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_pana_zero_list,
                              sizeof(uint32_t) * (size_t)DNGOP_BAD_CAP * (size_t)p->pana_zero_slots));
   }
   p->launches_per_run = units ? 1 : 0;
@@ -790,7 +881,7 @@ extern "C" int rsb200_scale_plan_create(rsb200_ctx* ctx, const rsb200_scale_job*
     g.mode = mode;
     g.njobs = (int)dev[mode].size();
     g.total_quads = quads[mode];
-    CUDA_TRY(ctx, cudaMalloc((void**)&g.d_jobs, sizeof(ScaleJobDev) * dev[mode].size()));
+    CUDA_TRY(ctx, rsb_dev_alloc((void**)&g.d_jobs, sizeof(ScaleJobDev) * dev[mode].size()));
     p->scale_groups.push_back(g); // owned by the plan from here on
     CUDA_TRY(ctx, cudaMemcpy(g.d_jobs, dev[mode].data(), sizeof(ScaleJobDev) * dev[mode].size(),
                              cudaMemcpyHostToDevice));
@@ -863,7 +954,7 @@ extern "C" int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* j
     }
     g.total_mcus = (uint32_t)n;
     g.njobs = (int)kv.second.size();
-    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(SrawJobDev) * kv.second.size());
+    cudaError_t e = rsb_dev_alloc(&g.d_jobs, sizeof(SrawJobDev) * kv.second.size());
     if (e == cudaSuccess)
       e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(SrawJobDev) * kv.second.size(),
                      cudaMemcpyHostToDevice);
@@ -932,17 +1023,17 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
                                                       2ull * j.width));
   }
   p->p1_nstrips = (uint32_t)ds.size();
-  cudaError_t e = cudaMalloc((void**)&p->d_p1_strips, sizeof(P1StripDev) * ds.size());
+  cudaError_t e = rsb_dev_alloc((void**)&p->d_p1_strips, sizeof(P1StripDev) * ds.size());
   if (e == cudaSuccess)
     e = cudaMemcpy(p->d_p1_strips, ds.data(), sizeof(P1StripDev) * ds.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaMalloc((void**)&p->d_p1_jobs, sizeof(P1JobDev) * dj.size());
+    e = rsb_dev_alloc((void**)&p->d_p1_jobs, sizeof(P1JobDev) * dj.size());
   if (e == cudaSuccess)
     e = cudaMemcpy(p->d_p1_jobs, dj.data(), sizeof(P1JobDev) * dj.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaMalloc((void**)&p->d_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
+    e = rsb_dev_alloc((void**)&p->d_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
   if (e == cudaSuccess)
-    e = cudaMallocHost((void**)&p->h_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
+    e = rsb_host_alloc((void**)&p->h_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
   if (e != cudaSuccess) {
     rsb200_plan_destroy(p);
     return set_err(ctx, RSB200_ERR_CUDA, "phaseone plan upload failed: %s", cudaGetErrorString(e));
@@ -1051,7 +1142,7 @@ extern "C" int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* j
     }
     g.total_units = (uint32_t)n;
     g.njobs = (int)kv.second.size();
-    cudaError_t e = cudaMalloc(&g.d_jobs, sizeof(PanaJobDev) * kv.second.size());
+    cudaError_t e = rsb_dev_alloc(&g.d_jobs, sizeof(PanaJobDev) * kv.second.size());
     if (e == cudaSuccess)
       e = cudaMemcpy(g.d_jobs, kv.second.data(), sizeof(PanaJobDev) * kv.second.size(),
                      cudaMemcpyHostToDevice);
@@ -1062,9 +1153,9 @@ extern "C" int rsb200_pana_plan_create(rsb200_ctx* ctx, const rsb200_pana_job* j
     p->pana_groups.push_back(g);
   }
   if (p->pana_zero_slots) {
-    cudaError_t e = cudaMalloc(&p->d_pana_zero_count, sizeof(uint32_t) * (size_t)p->pana_zero_slots);
+    cudaError_t e = rsb_dev_alloc(&p->d_pana_zero_count, sizeof(uint32_t) * (size_t)p->pana_zero_slots);
     if (e == cudaSuccess)
-      e = cudaMalloc(&p->d_pana_zero_list,
+      e = rsb_dev_alloc(&p->d_pana_zero_list,
                      sizeof(uint32_t) * (size_t)PANA_ZERO_CAP * (size_t)p->pana_zero_slots);
     if (e != cudaSuccess) {
       rsb200_plan_destroy(p);
@@ -1185,19 +1276,19 @@ extern "C" int rsb200_arw2_plan_create(rsb200_ctx* ctx, const rsb200_arw2_job* j
     }
     cudaError_t e = cudaMemcpyToSymbol(c_arw2_jump, jump, sizeof jump);
     if (e == cudaSuccess)
-      e = cudaMalloc(&p->d_arw2_jobs, sizeof(Arw2JobDev) * dev.size());
+      e = rsb_dev_alloc(&p->d_arw2_jobs, sizeof(Arw2JobDev) * dev.size());
     if (e == cudaSuccess)
       e = cudaMemcpy(p->d_arw2_jobs, dev.data(), sizeof(Arw2JobDev) * dev.size(),
                      cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
-      e = cudaMalloc(&p->d_arw2_tables, tcut.size() * sizeof(uint16_t) + 16);
+      e = rsb_dev_alloc(&p->d_arw2_tables, tcut.size() * sizeof(uint16_t) + 16);
     if (e == cudaSuccess && !tcut.empty())
       e = cudaMemcpy(p->d_arw2_tables, tcut.data(), tcut.size() * sizeof(uint16_t),
                      cudaMemcpyHostToDevice);
     if (e == cudaSuccess)
-      e = cudaMalloc(&p->d_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
+      e = rsb_dev_alloc(&p->d_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
     if (e == cudaSuccess)
-      e = cudaMallocHost((void**)&p->h_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
+      e = rsb_host_alloc((void**)&p->h_arw2_bad, sizeof(uint32_t) * (size_t)njobs);
     if (e != cudaSuccess) {
       rsb200_plan_destroy(p);
       return set_err(ctx, RSB200_ERR_CUDA, "arw2 plan upload failed: %s", cudaGetErrorString(e));
@@ -1471,6 +1562,14 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     }
   }
   p->nthread = (int)thread_ids.size();
+  if (!thread_ids.empty()) {
+    uint64_t bytes = 0;
+    for (uint32_t i : thread_ids)
+      bytes += b.scans[i].in_size;
+    p->clean2 = bytes / thread_ids.size() >= 4096; // DNG-size segments
+    if (const char* e = getenv("RSB200_CLEAN"))
+      p->clean2 = atoi(e) == 2;
+  }
   p->ntables = ntables;
   p->nbig = (int)big_ids.size();
   p->nranges = (int)ranges.size();
@@ -1479,13 +1578,13 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   auto up = [&](void** dptr, const void* src, size_t bytes) {
     if (e != cudaSuccess)
       return;
-    e = cudaMalloc(dptr, bytes ? bytes : 16);
+    e = rsb_dev_alloc(dptr, bytes ? bytes : 16);
     if (e == cudaSuccess && bytes)
       e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
   };
   auto alloc = [&](void** dptr, size_t bytes) {
     if (e == cudaSuccess)
-      e = cudaMalloc(dptr, bytes ? bytes : 16);
+      e = rsb_dev_alloc(dptr, bytes ? bytes : 16);
   };
   up((void**)&p->d_tables, ht.data(), sizeof(DevTable) * ht.size());
   up((void**)&p->d_scans, b.scans.data(), sizeof(DevScan) * b.scans.size());
@@ -1528,11 +1627,11 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   alloc((void**)&p->d_colvals, (b.col_elems + 64) * sizeof(uint16_t));
   alloc((void**)&p->d_results, sizeof(DevResult) * b.scans.size());
   if (e == cudaSuccess)
-    e = cudaMallocHost((void**)&p->h_results, sizeof(DevResult) * b.scans.size());
+    e = rsb_host_alloc((void**)&p->h_results, sizeof(DevResult) * b.scans.size());
   if (p->has_pentax) {
     alloc((void**)&p->d_oob, sizeof(uint32_t) * b.scans.size());
     if (e == cudaSuccess)
-      e = cudaMallocHost((void**)&p->h_oob, sizeof(uint32_t) * b.scans.size());
+      e = rsb_host_alloc((void**)&p->h_oob, sizeof(uint32_t) * b.scans.size());
   }
   if (e != cudaSuccess) {
     rsb200_plan_destroy(p);
@@ -1668,7 +1767,7 @@ extern "C" int rsb200_nikon_plan_create(rsb200_ctx* ctx, const rsb200_huff_table
     return rc;
   {
     const size_t bytes = (size_t)nluts * 2u * 65536u * sizeof(uint16_t);
-    cudaError_t e = cudaMalloc((void**)&p->d_nikon_luts, bytes + 16);
+    cudaError_t e = rsb_dev_alloc((void**)&p->d_nikon_luts, bytes + 16);
     if (e == cudaSuccess && bytes)
       e = cudaMemcpy(p->d_nikon_luts, luts, bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
@@ -2000,6 +2099,13 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       ctx->launches += 1;
     }
     if (p->nthread) {
+      // unstuffing pre-pass: one CTA per segment with the tile kernel's stage B for DNG-size
+      // segments (k2_clean2_kernel), one warp per segment for small ones (k2_clean_kernel)
+      if (p->clean2)
+        k2_clean2_kernel<<<p->nthread, TL_NT, tile_smem_bytes<1>(), st>>>(
+            in, (uint64_t)in_bytes, p->d_scans, p->d_thread_ids, (uint32_t)p->nthread, p->d_tscans,
+            p->d_clean, p->d_anchors, p->d_tinfos);
+      else
       k2_clean_kernel<<<(p->nthread + C_WARPS - 1) / C_WARPS, 32 * C_WARPS, 0, st>>>(
           in, (uint64_t)in_bytes, p->d_scans, p->d_thread_ids, (uint32_t)p->nthread, p->d_tscans,
           p->d_clean, p->d_anchors, p->d_tinfos);
@@ -2128,25 +2234,26 @@ static bool host_is_pageable(const void* ptr) {
   }
   return a.type == cudaMemoryTypeUnregistered;
 }
-static void parallel_copy(uint8_t* dst, const uint8_t* src, size_t n) {
-  const size_t kSlice = 2ull << 20;
-  unsigned nt = (unsigned)std::min<size_t>(12, n / kSlice);
+static int copy_threads(size_t bytes) {
+  int nt = (int)std::min<size_t>(12, bytes / (1ull << 20));
   if (const char* e = getenv("RSB200_COPY_THREADS"))
-    nt = (unsigned)std::max(1, atoi(e));
-  if (nt <= 1) {
+    nt = std::max(1, atoi(e));
+  return std::max(nt, 1);
+}
+// (OpenMP: a persistent team -- spawning threads per call costs more than the copies)
+static void parallel_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+  const long kSlice = 1l << 20;
+  const long ns = (long)((n + kSlice - 1) / kSlice);
+  const int nt = copy_threads(n);
+  if (nt <= 1 || ns <= 1) {
     memcpy(dst, src, n);
     return;
   }
-  std::vector<std::thread> th;
-  const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
-  for (unsigned t = 1; t < nt; ++t) {
-    const size_t a = std::min(n, per * t), b = std::min(n, per * (t + 1));
-    if (b > a)
-      th.emplace_back([=] { memcpy(dst + a, src + a, b - a); });
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (long i = 0; i < ns; ++i) {
+    const size_t a = (size_t)i * kSlice, b2 = std::min(n, a + (size_t)kSlice);
+    memcpy(dst + a, src + a, b2 - a);
   }
-  memcpy(dst, src, std::min(n, per));
-  for (std::thread& t : th)
-    t.join();
 }
 // rows of row_bytes out of a pitch-strided source into a pitch-strided destination
 static void parallel_copy_rows(uint8_t* dst, const uint8_t* src, size_t pitch, size_t row_bytes,
@@ -2155,24 +2262,10 @@ static void parallel_copy_rows(uint8_t* dst, const uint8_t* src, size_t pitch, s
     parallel_copy(dst, src, pitch * rows);
     return;
   }
-  unsigned nt = (unsigned)std::min<size_t>(12, (row_bytes * rows) / (2ull << 20));
-  if (nt <= 1) {
-    for (size_t r = 0; r < rows; ++r)
-      memcpy(dst + r * pitch, src + r * pitch, row_bytes);
-    return;
-  }
-  std::vector<std::thread> th;
-  const size_t per = (rows + nt - 1) / nt;
-  auto work = [=](size_t r0, size_t r1) {
-    for (size_t r = r0; r < r1; ++r)
-      memcpy(dst + r * pitch, src + r * pitch, row_bytes);
-  };
-  for (unsigned t = 1; t < nt; ++t)
-    if (std::min(rows, per * t) < std::min(rows, per * (t + 1)))
-      th.emplace_back(work, std::min(rows, per * t), std::min(rows, per * (t + 1)));
-  work(0, std::min(rows, per));
-  for (std::thread& t : th)
-    t.join();
+  const int nt = copy_threads(row_bytes * rows);
+#pragma omp parallel for num_threads(nt) schedule(static) if (nt > 1)
+  for (long r = 0; r < (long)rows; ++r)
+    memcpy(dst + (size_t)r * pitch, src + (size_t)r * pitch, row_bytes);
 }
 static int ensure_host_cap(rsb200_ctx* ctx, uint8_t** buf, size_t* cap, size_t need) {
   need = (need + 4095) & ~(size_t)4095;
@@ -2723,63 +2816,65 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
     return;
   if (p->ctx)
     cudaSetDevice(p->ctx->device);
+  if (p->ran && p->last_stream)
+    cudaStreamSynchronize(p->last_stream); // (the frees below are stream ordered, not device-wide syncs)
   for (UnpackGroup& g : p->groups)
-    cudaFree(g.d_jobs);
+    rsb_dev_free(g.d_jobs);
   for (UnpackFastGroup& g : p->fast_groups)
-    cudaFree(g.d_jobs);
+    rsb_dev_free(g.d_jobs);
   for (RawGroup& g : p->raw_groups)
-    cudaFree(g.d_jobs);
+    rsb_dev_free(g.d_jobs);
   for (PanaGroup& g : p->pana_groups)
-    cudaFree(g.d_jobs);
+    rsb_dev_free(g.d_jobs);
   for (ScaleGroup& g : p->scale_groups)
-    cudaFree(g.d_jobs);
-  cudaFree(p->d_pana_zero_count);
-  cudaFree(p->d_pana_zero_list);
-  cudaFree(p->d_lookup_jobs);
-  cudaFree(p->d_lookup_tables);
-  cudaFree(p->d_badpix_jobs);
-  cudaFree(p->d_badpix_list);
-  cudaFree(p->d_badpix_maps);
-  cudaFree(p->d_dngop_jobs);
-  cudaFree(p->d_dngop_ops);
-  cudaFree(p->d_dngop_tables);
-  cudaFree(p->d_dngop_deltas);
-  cudaFree(p->d_p1_strips);
-  cudaFree(p->d_p1_jobs);
-  cudaFree(p->d_nikon_luts);
-  cudaFree(p->d_arw2_jobs);
-  cudaFree(p->d_arw2_tables);
-  cudaFree(p->d_arw2_bad);
+    rsb_dev_free(g.d_jobs);
+  rsb_dev_free(p->d_pana_zero_count);
+  rsb_dev_free(p->d_pana_zero_list);
+  rsb_dev_free(p->d_lookup_jobs);
+  rsb_dev_free(p->d_lookup_tables);
+  rsb_dev_free(p->d_badpix_jobs);
+  rsb_dev_free(p->d_badpix_list);
+  rsb_dev_free(p->d_badpix_maps);
+  rsb_dev_free(p->d_dngop_jobs);
+  rsb_dev_free(p->d_dngop_ops);
+  rsb_dev_free(p->d_dngop_tables);
+  rsb_dev_free(p->d_dngop_deltas);
+  rsb_dev_free(p->d_p1_strips);
+  rsb_dev_free(p->d_p1_jobs);
+  rsb_dev_free(p->d_nikon_luts);
+  rsb_dev_free(p->d_arw2_jobs);
+  rsb_dev_free(p->d_arw2_tables);
+  rsb_dev_free(p->d_arw2_bad);
   if (p->h_arw2_bad)
-    cudaFreeHost(p->h_arw2_bad);
+    rsb_host_free(p->h_arw2_bad);
   for (SrawGroup& g : p->sraw_groups)
-    cudaFree(g.d_jobs);
-  cudaFree(p->d_raw_tables);
-  cudaFree(p->d_tables);
-  cudaFree(p->d_scans);
-  cudaFree(p->d_strips);
-  cudaFree(p->d_rows);
-  cudaFree(p->d_diffs);
-  cudaFree(p->d_colvals);
-  cudaFree(p->d_results);
-  cudaFree(p->d_small_ids);
-  cudaFree(p->d_tile_ids);
-  cudaFree(p->d_tile_params);
-  cudaFree(p->d_thread_ids);
-  cudaFree(p->d_tscans);
-  cudaFree(p->d_tinfos);
-  cudaFree(p->d_clean);
-  cudaFree(p->d_anchors);
-  cudaFree(p->d_big_ids);
-  cudaFree(p->d_big);
-  cudaFree(p->d_ranges);
-  cudaFree(p->d_states);
-  cudaFree(p->d_finals);
-  cudaFree(p->d_fallback);
-  cudaFree(p->d_oob);
+    rsb_dev_free(g.d_jobs);
+  rsb_dev_free(p->d_raw_tables);
+  rsb_dev_free(p->d_tables);
+  rsb_dev_free(p->d_scans);
+  rsb_dev_free(p->d_strips);
+  rsb_dev_free(p->d_rows);
+  rsb_dev_free(p->d_diffs);
+  rsb_dev_free(p->d_colvals);
+  rsb_dev_free(p->d_results);
+  rsb_dev_free(p->d_small_ids);
+  rsb_dev_free(p->d_tile_ids);
+  rsb_dev_free(p->d_tile_params);
+  rsb_dev_free(p->d_thread_ids);
+  rsb_dev_free(p->d_tscans);
+  rsb_dev_free(p->d_tinfos);
+  rsb_dev_free(p->d_clean);
+  rsb_dev_free(p->d_anchors);
+  rsb_dev_free(p->d_big_ids);
+  rsb_dev_free(p->d_big);
+  rsb_dev_free(p->d_ranges);
+  rsb_dev_free(p->d_states);
+  rsb_dev_free(p->d_finals);
+  rsb_dev_free(p->d_fallback);
+  rsb_dev_free(p->d_oob);
   if (p->h_oob)
-    cudaFreeHost(p->h_oob);
+    rsb_host_free(p->h_oob);
   if (p->h_results)
-    cudaFreeHost(p->h_results);
+    rsb_host_free(p->h_results);
   delete p;
 }

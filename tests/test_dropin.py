@@ -37,16 +37,21 @@ def _lib(name):
     return lib
 
 
+_OUT = {}
+
+
 def decode_file(lib, file_bytes, threads=4):
     info = (C.c_int32 * 8)()
     err = C.create_string_buffer(512)
-    out = np.zeros(256 << 20, dtype=np.uint8)
+    if "buf" not in _OUT:
+        _OUT["buf"] = np.zeros(256 << 20, dtype=np.uint8)
+    out = _OUT["buf"]
     f = np.ascontiguousarray(file_bytes)
     rc = lib.rs_file_decode(f.ctypes.data, f.size, out.ctypes.data, out.size, info, err, 512, threads, 0, 0)
     if rc != 0:
         raise RuntimeError("rc %d: %s" % (rc, err.value.decode(errors="replace")))
     w, h, cpp, pitch = info[0], info[1], info[2], info[3]
-    return out[:pitch * h].view(np.uint16).reshape(h, pitch // 2), (w, h, cpp, pitch, info[6])
+    return out[:pitch * h].view(np.uint16).reshape(h, pitch // 2).copy(), (w, h, cpp, pitch, info[6])
 
 
 def ljpeg_dng(w, h, tile_w, tile_h, seed, **kw):

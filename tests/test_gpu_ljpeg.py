@@ -9,7 +9,7 @@ from helpers import dng_ljpeg_scans, gpu_run
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["auto", "tile2", "fused", "thread"])
+@pytest.fixture(autouse=True, params=["auto", "tile2", "fused", "thread", "thread_clean2"])
 def ljpeg_path(request, monkeypatch):
     """Every case runs four times: with the plan's own choice of kernel (k2_tile_kernel<1> for
     plain single-table tiles, k2_fused_kernel for the rest, at these sizes), with the second
@@ -17,8 +17,12 @@ def ljpeg_path(request, monkeypatch):
     everything (RSB200_LJPEG_PATH=fused) and with the one-thread-per-segment path (K2C + K2T)."""
     monkeypatch.delenv("RSB200_LJPEG_PATH", raising=False)
     monkeypatch.delenv("RSB200_TILE_R", raising=False)
+    monkeypatch.setenv("RSB200_CLEAN", "1")   # (the plan picks by segment size; here: both, explicitly)
     if request.param == "tile2":
         monkeypatch.setenv("RSB200_TILE_R", "2")
+    elif request.param == "thread_clean2":
+        monkeypatch.setenv("RSB200_LJPEG_PATH", "thread")
+        monkeypatch.setenv("RSB200_CLEAN", "2")
     elif request.param != "auto":
         monkeypatch.setenv("RSB200_LJPEG_PATH", request.param)
     return request.param

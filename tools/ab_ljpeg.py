@@ -28,7 +28,7 @@ def build(name, flags):
     os.makedirs(AB, exist_ok=True)
     out = os.path.join(AB, name + ".so")
     subprocess.check_call([b._nvcc()] + b.NVCC_FLAGS + list(flags) + ["-o", out,
-                          os.path.join(ROOT, "rawspeed_b200", "csrc", "rsb200.cu")], cwd=ROOT)
+                          os.path.join(ROOT, "rawspeed_b200", "csrc", "rsb200.cu"), "-ldl", "-lgomp"], cwd=ROOT)
     print(out)
 
 
