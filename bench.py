@@ -32,9 +32,6 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-# the reference arm / cpu_baseline: stable thread placement for the reference's OpenMP loops
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -283,6 +280,12 @@ def _gen_frame(job):
             [int(o) for o in t.offsets], [int(n) for n in t.lengths])
 
 
+def _worker_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ.pop("OMP_PROC_BIND", None)
+    os.environ.pop("OMP_PLACES", None)
+
+
 def gen_frames(seeds, procs):
     """Distinct synthetic frames, generated on the host cores in parallel (before CUDA is
     touched).  Returns (shared block, per-frame capacity, per-frame records)."""
@@ -291,7 +294,8 @@ def gen_frames(seeds, procs):
     shm = shared_memory.SharedMemory(create=True, size=max(1, len(seeds)) * cap)
     jobs = [(sd, shm.name, k * cap, cap) for k, sd in enumerate(seeds)]
     if procs > 1 and len(seeds) > 1:
-        with get_context("fork").Pool(min(procs, len(seeds))) as pool:
+        # one thread per worker: the pool is the parallelism (the oracle library is an OpenMP build)
+        with get_context("fork").Pool(min(procs, len(seeds)), initializer=_worker_init) as pool:
             recs = pool.map(_gen_frame, jobs, chunksize=1)
     else:
         recs = [_gen_frame(j) for j in jobs]
@@ -397,6 +401,27 @@ def cpu_reference_ljpeg(shm, cap, recs, reps=5, warm=1):
             "sample": "%d frame(s), oracle C port with %d OpenMP threads" % (len(frames), ncores)}
 
 
+def cpu_baseline_children(args):
+    """cpu_baseline of the GPU arm = the reference arm itself on a smaller sample (child processes,
+    one per CPU placement; this process's OpenMP runtime and affinity are torch's business)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--ref-frames", str(max(1, args.cpu_frames))]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    try:
+        os_aff = None
+        if hasattr(os, "sched_getaffinity"):
+            os_aff = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))  # children start from the whole box
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        if os_aff:
+            os.sched_setaffinity(0, os_aff)
+        return json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception as ex:  # noqa: BLE001
+        return {"kind": "reference", "error": str(ex)[:200]}
+
+
 def cpu_reference_c1():
     """BASELINE configs[0]: UncompressedDecompressor 12-bit packed, 4000x3000, CPU only --
     the reference's own accounting (items = pixels, bytes = bps*pixels/8,
@@ -476,6 +501,9 @@ def run_reference(args):
         except Exception:
             pass
         os.environ["OMP_NUM_THREADS"] = str(len(cpus))
+    # stable placement of the reference's OpenMP team (set before the runtime starts)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "threads")
     nsample = max(1, args.ref_frames)
     shm, cap, recs = gen_frames([SEED0 + i for i in range(nsample)], procs=min(nsample, os.cpu_count() or 1))
     try:
@@ -682,8 +710,7 @@ def main():
         if rank == 0:
             cpu = None
             if not args.skip_cpu:
-                nc = max(1, min(args.cpu_frames, len(recs)))
-                cpu = cpu_reference_ljpeg(shm, cap, recs[:nc])
+                cpu = cpu_baseline_children(args)
                 c1 = cpu_reference_c1()
                 if c1:
                     others["configs[0] 12-bit packed 4000x3000, CPU only"] = c1

@@ -145,7 +145,7 @@ __device__ __forceinline__ void
 thread_body(ThreadShared& sh, const DevScan* __restrict__ scp, const DevTScan& ts,
             const DevTInfo info, const uint8_t* __restrict__ in,
             const uint32_t* __restrict__ clean, const uint32_t* __restrict__ anchors,
-            uint8_t* __restrict__ out, DevResult* __restrict__ res) {
+            uint8_t* __restrict__ out, DevResult* __restrict__ res, uint32_t* __restrict__ redo) {
   const uint4* cb = reinterpret_cast<const uint4*>(clean + ts.clean_off); // 16-byte blocks
   const uint32_t bmax = (ts.cap_words >> 2) - 1u;
   const uint32_t ringb = smem_u32(&sh.ring[0][threadIdx.x]);
@@ -255,9 +255,16 @@ thread_body(ThreadShared& sh, const DevScan* __restrict__ scp, const DevTScan& t
     }
     orow += out_pitch;
   }
-  // status: a needed symbol used bits that are not there (DESIGN.md "known deviations")
+  // A needed symbol used bits that are not there.  Whether the reference reads them as zero bits
+  // or throws depends on the refill cadence of its pump (BitStreamer.h:120-127,
+  // BitStreamerJPEG.h:155-183): segments the tile kernel can take are flagged and decoded again
+  // by it (exact, tl_replay in ljpeg_tile.cuh); for the others the answer stays IOException
+  // (DESIGN.md "known deviations").
   const bool over = p > 8u * info.clean_len;
-  res->status = bad ? 1u : (over ? 2u : 0u);
+  const bool again = over && !bad && redo && ts.pad;
+  if (redo)
+    *redo = again ? 1u : 0u;
+  res->status = bad ? 1u : ((over && !again) ? 2u : 0u);
   {
     const uint64_t in_offset = scp->in_offset;
     const uint64_t abase = in_offset & ~15ull;
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(T_NT, RSB200_T_LB)
                      DevResult* __restrict__ results, const uint32_t* __restrict__ scan_ids,
                      uint32_t nids, const DevTScan* __restrict__ tscans,
                      const DevTInfo* __restrict__ infos, const uint32_t* __restrict__ clean,
-                     const uint32_t* __restrict__ anchors) {
+                     const uint32_t* __restrict__ anchors, uint32_t* __restrict__ redo) {
   extern __shared__ __align__(16) uint8_t t_smem_raw[];
   ThreadShared& sh = *reinterpret_cast<ThreadShared*>(t_smem_raw);
   const int tid = threadIdx.x;
@@ -299,11 +306,11 @@ __global__ void __launch_bounds__(T_NT, RSB200_T_LB)
   const DevTInfo info = infos[id];
   const uint32_t G = scp->group;
   if (G == 1)
-    thread_body<1>(sh, scp, ts, info, in, clean, anchors, out, res);
+    thread_body<1>(sh, scp, ts, info, in, clean, anchors, out, res, redo ? redo + id : nullptr);
   else if (G == 2)
-    thread_body<2>(sh, scp, ts, info, in, clean, anchors, out, res);
+    thread_body<2>(sh, scp, ts, info, in, clean, anchors, out, res, redo ? redo + id : nullptr);
   else
-    thread_body<4>(sh, scp, ts, info, in, clean, anchors, out, res);
+    thread_body<4>(sh, scp, ts, info, in, clean, anchors, out, res, redo ? redo + id : nullptr);
 }
 
 } // namespace rsb200

@@ -1272,8 +1272,13 @@ __device__ __forceinline__ void tile_entry(TileShared<R>& sh, const uint8_t* __r
                                            uint8_t* __restrict__ out,
                                            DevResult* __restrict__ results_all,
                                            const uint32_t* __restrict__ scan_ids,
-                                           const DevTileParam* __restrict__ params) {
+                                           const DevTileParam* __restrict__ params,
+                                           const uint32_t* __restrict__ redo = nullptr) {
   const int tid = threadIdx.x;
+  // second opinion for the one-thread-per-segment path: only the segments it flagged (their last
+  // symbols read behind the data, where the reference's refill cadence decides) are decoded again
+  if (redo && !redo[blockIdx.x])
+    return;
   const uint32_t scan_idx = scan_ids ? scan_ids[blockIdx.x] : blockIdx.x;
   DevResult* res = results_all + scan_idx;
   {
@@ -1332,10 +1337,11 @@ __global__ void __launch_bounds__(TL_NT, (R == 1 ? RSB200_TILE_CTAS1 : 2))
     k2_tile_kernel(const uint8_t* __restrict__ in, uint64_t in_total,
                    const DevScan* __restrict__ scans, const DevTable* __restrict__ tables,
                    uint8_t* __restrict__ out, DevResult* __restrict__ results_all,
-                   const uint32_t* __restrict__ scan_ids, const DevTileParam* __restrict__ params) {
+                   const uint32_t* __restrict__ scan_ids, const DevTileParam* __restrict__ params,
+                   const uint32_t* __restrict__ redo) {
   extern __shared__ __align__(128) uint8_t tl_smem_raw[];
   TileShared<R>& sh = *reinterpret_cast<TileShared<R>*>(tl_smem_raw);
-  tile_entry<R>(sh, in, in_total, scans, tables, out, results_all, scan_ids, params);
+  tile_entry<R>(sh, in, in_total, scans, tables, out, results_all, scan_ids, params, redo);
 }
 #endif
 

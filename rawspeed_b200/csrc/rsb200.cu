@@ -292,6 +292,9 @@ struct rsb200_plan {
   int ntile = 0;
   int tile_r = 1;
   bool clean2 = false; // thread path: k2_clean2_kernel instead of k2_clean_kernel
+  DevTileParam* d_thread_tile_params = nullptr; // thread path: parameters of the exact second opinion
+  uint32_t* d_redo = nullptr;                   // ... and which segments need it (written by K2T)
+  int nthread_redo = 0;                         // segments of the thread path the tile kernel can take
   uint32_t* d_thread_ids = nullptr; // segments decoded one per thread (K2C + K2T)
   DevTScan* d_tscans = nullptr;
   DevTInfo* d_tinfos = nullptr;
@@ -1566,7 +1569,10 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     uint64_t bytes = 0;
     for (uint32_t i : thread_ids)
       bytes += b.scans[i].in_size;
-    p->clean2 = bytes / thread_ids.size() >= 4096; // DNG-size segments
+    // measured (r2_run7, 256 frames): k2_clean_kernel 7.8 ms, k2_clean2_kernel ~12 ms (one CTA per
+    // segment is latency bound here) -> the warp-per-segment pre-pass stays the default
+    (void)bytes;
+    p->clean2 = false;
     if (const char* e = getenv("RSB200_CLEAN"))
       p->clean2 = atoi(e) == 2;
   }
@@ -1605,7 +1611,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
       t.cap_words = (((d.in_size + 15u) & ~15u) + 64u) / 4u;
       t.anchor_off = (uint32_t)n_anchor;
       t.n_anchor = ((skew + d.in_size) >> T_ANCHOR_SHIFT) + 1u;
-      t.pad = 0;
+      t.pad = tile_eligible(d, TileGeom<1>::MIN_RS) ? 1u : 0u; // may get the tile kernel's second opinion
       clean_words += t.cap_words;
       n_anchor += t.n_anchor;
       tsc[k] = t;
@@ -1613,6 +1619,16 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     if (n_anchor >= (1ull << 32))
       e = cudaErrorInvalidValue;
     up((void**)&p->d_tscans, tsc.data(), sizeof(DevTScan) * tsc.size());
+    {
+      std::vector<DevTileParam> tp(tsc.size());
+      for (size_t k = 0; k < tsc.size(); ++k) {
+        tile_params(b.scans[thread_ids[k]], TileGeom<1>::NPIECE, TileGeom<1>::DCAP, -1, tp[k].npieces,
+                    tp[k].preroll);
+        p->nthread_redo += tsc[k].pad ? 1 : 0;
+      }
+      up((void**)&p->d_thread_tile_params, tp.data(), sizeof(DevTileParam) * tp.size());
+      alloc((void**)&p->d_redo, sizeof(uint32_t) * tsc.size());
+    }
     alloc((void**)&p->d_tinfos, sizeof(DevTInfo) * tsc.size());
     alloc((void**)&p->d_clean, clean_words * 4 + 256);
     alloc((void**)&p->d_anchors, n_anchor * 4 + 256);
@@ -1638,7 +1654,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
                    cudaGetErrorString(e));
   }
-  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->ntile ? 1 : 0) + (p->nthread ? 2 : 0) +
+  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->ntile ? 1 : 0) + (p->nthread ? 2 + (p->nthread_redo ? 1 : 0) : 0) +
                         (p->nbig ? 5 + (p->has_k3 ? 2 : 0) + (p->has_pentax ? 2 : 0) + (p->has_nikon ? 2 : 0) : 0);
   return RSB200_OK;
 }
@@ -2083,11 +2099,11 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       if (p->tile_r == 2)
         k2_tile_kernel<2><<<p->ntile, TL_NT, tile_smem_bytes<2>(), st>>>(
             in, (uint64_t)in_bytes, p->d_scans, p->d_tables, outp, p->d_results, p->d_tile_ids,
-            p->d_tile_params);
+            p->d_tile_params, nullptr);
       else
         k2_tile_kernel<1><<<p->ntile, TL_NT, tile_smem_bytes<1>(), st>>>(
             in, (uint64_t)in_bytes, p->d_scans, p->d_tables, outp, p->d_results, p->d_tile_ids,
-            p->d_tile_params);
+            p->d_tile_params, nullptr);
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 1;
     }
@@ -2111,9 +2127,17 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
           p->d_clean, p->d_anchors, p->d_tinfos);
       k2_thread_kernel<<<(p->nthread + T_NT - 1) / T_NT, T_NT, thread_smem_bytes(p->ntables), st>>>(
           in, p->d_scans, p->d_tables, p->ntables, outp, p->d_results, p->d_thread_ids,
-          (uint32_t)p->nthread, p->d_tscans, p->d_tinfos, p->d_clean, p->d_anchors);
+          (uint32_t)p->nthread, p->d_tscans, p->d_tinfos, p->d_clean, p->d_anchors, p->d_redo);
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 2;
+      if (p->nthread_redo) {
+        // exact end-of-stream semantics for the segments K2T flagged (CTAs of the others exit at once)
+        k2_tile_kernel<1><<<p->nthread, TL_NT, tile_smem_bytes<1>(), st>>>(
+            in, (uint64_t)in_bytes, p->d_scans, p->d_tables, outp, p->d_results, p->d_thread_ids,
+            p->d_thread_tile_params, p->d_redo);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 1;
+      }
     }
     if (p->nbig) {
       k2_clear_results_kernel<<<(p->nbig + 127) / 128, 128, 0, st>>>(p->d_big, p->nbig,
@@ -2286,11 +2310,11 @@ static cudaError_t launch_tile_range(const rsb200_plan* p, const uint8_t* d_in, 
   if (p->tile_r == 2)
     k2_tile_kernel<2><<<count, TL_NT, tile_smem_bytes<2>(), st>>>(
         d_in, in_bytes, p->d_scans, p->d_tables, d_out, p->d_results, p->d_tile_ids + first,
-        p->d_tile_params + first);
+        p->d_tile_params + first, nullptr);
   else
     k2_tile_kernel<1><<<count, TL_NT, tile_smem_bytes<1>(), st>>>(
         d_in, in_bytes, p->d_scans, p->d_tables, d_out, p->d_results, p->d_tile_ids + first,
-        p->d_tile_params + first);
+        p->d_tile_params + first, nullptr);
   return cudaGetLastError();
 }
 
@@ -2860,6 +2884,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   rsb_dev_free(p->d_small_ids);
   rsb_dev_free(p->d_tile_ids);
   rsb_dev_free(p->d_tile_params);
+  rsb_dev_free(p->d_thread_tile_params);
+  rsb_dev_free(p->d_redo);
   rsb_dev_free(p->d_thread_ids);
   rsb_dev_free(p->d_tscans);
   rsb_dev_free(p->d_tinfos);
