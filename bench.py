@@ -778,7 +778,7 @@ def bench_gather_abi(torch, dist, rs, ctx, batch, world, rank, args, total_pixel
     slab = batch.out_bytes
     d_all = torch.zeros(world * slab, dtype=torch.uint8, device="cuda")
     out = {"what": "decode + gather of the uint16 images over NVLink (rsb200_plan_run_gather: per group of "
-                   "tiles, grouped ncclBroadcast / ncclSend+ncclRecv on a side stream, overlapping the decode)",
+                   "tiles (or per 512 MB of the slab when the plan is one launch), grouped ncclSend/ncclRecv on a side stream)",
            "gathered_bytes_total": int(world * slab)}
     for name, mode in (("to_all_ranks", rs.GATHER_ALL), ("to_rank0", rs.GATHER_ROOT)):
         def step():
