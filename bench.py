@@ -843,7 +843,12 @@ def bench_single_frame(torch, rs, ctx, port, synth, args, shm, cap, recs, peak, 
            "compressed_bytes_per_pixel": in_b / pixels,
            "roofline": {"bound": "hbm", "achieved": (in_b + out_b) / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": (in_b + out_b) / (ms * 1e-3) / 1e9 / peak,
-                        "read_only_frac": in_b / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src}}
+                        "read_only_frac": in_b / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                        "traffic": None}}
+    tr = ncu_traffic(ent["kernel"].split(" ")[0])
+    if tr:
+        ent["roofline"]["traffic"] = tr["dram_bytes_per_frame"]
+        ent["roofline"]["traffic_source"] = tr["source"]
     del flush
     # host buffers through the C ABI: pinned and pageable
     h_out = torch.empty(b1.out_bytes, dtype=torch.uint8, pin_memory=True)

@@ -43,7 +43,10 @@
 
 namespace rsb200 {
 
-constexpr int TL_NT = 256;     // threads per CTA
+#ifndef RSB200_TILE_NT
+#define RSB200_TILE_NT 256
+#endif
+constexpr int TL_NT = RSB200_TILE_NT; // threads per CTA
 constexpr int TL_PIECE = 64;   // raw bytes per unstuff piece
 constexpr int TL_LA = 16;      // clean bytes deferred to the next chunk (see tl_replay)
 constexpr int TL_ZEXT = 24;    // zero bytes behind the data the reference can still supply (192 bits)
