@@ -685,7 +685,7 @@ def main():
                "h2d_bytes_per_step": int(batch.in_bytes), "d2h_bytes_per_step": int(batch.out_bytes),
                "steps": e2e_steps, "ms_per_step": ms_e / e2e_steps,
                "api": "rsb200_plan_run_host: pinned host buffers; upload, decode and download of consecutive "
-                      "groups of tiles (~8 MB of pixels) overlap on three streams"}
+                      "groups of tiles (8-32 MB of pixels) overlap on eight streams"}
         got = d_out.cpu().numpy()
         e2e["bit_exact"] = bool(np.array_equal(h_out.numpy()[:H * batch.out_pitch], got[:H * batch.out_pitch])) and \
             bool(np.array_equal(h_out.numpy()[(batch.n - 1) * batch.ob:(batch.n - 1) * batch.ob + H * batch.out_pitch],
@@ -869,11 +869,19 @@ def bench_single_frame(torch, rs, ctx, port, synth, args, shm, cap, recs, peak, 
     himg = port.new_image(W, H)
     host.dng_decompress(blob, r[6], r[7], himg, W, 1, 256, 256, 7)
     ok_m = bool(np.array_equal(himg[:, :W], img))
-    ms_m = wall_steps(torch, lambda: host.dng_decompress(blob, r[6], r[7], himg, W, 1, 256, 256, 7), n, 1) / n
+    inner = []
+
+    def mirror_call():
+        host.dng_decompress(blob, r[6], r[7], himg, W, 1, 256, 256, 7)
+        inner.append(host.last_call_ms())
+    ms_h = wall_steps(torch, mirror_call, n, 1) / n
+    ms_m = float(np.median(inner[1:]))
     ent["e2e_host_mirror"] = {"value": PIX / (ms_m * 1e-3) / 1e6, "unit": "MPixels/s", "ms_per_frame": ms_m,
-                              "bit_exact": ok_m,
+                              "ms_per_frame_with_test_harness": ms_h, "bit_exact": ok_m,
                               "api": "rawspeed_b200::AbstractDngDecompressor::decompress() (C++ host mirror, pageable "
-                                     "RawImage): parse + plan + H2D + decode + D2H + results, per call"}
+                                     "RawImage): parse + plan + H2D + decode + D2H + results, per call; timed "
+                                     "around the member call (the ctypes harness around it allocates a RawImage "
+                                     "and copies the numpy image in and out: ms_per_frame_with_test_harness)"}
     return ent
 
 

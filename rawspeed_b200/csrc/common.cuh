@@ -89,6 +89,14 @@ __device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
   return r;
 }
 
+// PRMT in its generic form: nibble n of sel picks byte (sel_n & 7) of {b, a}; bit 3 of the nibble
+// replicates that byte's sign bit instead (0x00 / 0xFF).  Only sel[15:0] is used.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP) ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),

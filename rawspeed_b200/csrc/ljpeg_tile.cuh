@@ -1282,7 +1282,8 @@ __device__ __forceinline__ void tile_entry(TileShared<R>& sh, const uint8_t* __r
   // symbols read behind the data, where the reference's refill cadence decides) are decoded again
   if (redo && !redo[blockIdx.x])
     return;
-  const uint32_t scan_idx = scan_ids ? scan_ids[blockIdx.x] : blockIdx.x;
+  // (bit 31 of an id is a flag of the thread path's list, see k2_stream_kernel)
+  const uint32_t scan_idx = scan_ids ? (scan_ids[blockIdx.x] & 0x7FFFFFFFu) : blockIdx.x;
   DevResult* res = results_all + scan_idx;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&scans[scan_idx]);

@@ -8,6 +8,7 @@
 #include "ljpeg_fused.cuh"
 #include "ljpeg_ranges.cuh"
 #include "ljpeg_thread.cuh"
+#include "ljpeg_stream.cuh"
 #include "ljpeg_tile.cuh"
 #include "ljpeg_host.h"
 #include "rawforms.cuh"
@@ -121,6 +122,7 @@ static cudaError_t rsb_host_free(void* p) {
 }
 
 // ------------------------------------------------------------------
+constexpr int N_PIPE = 8;
 struct rsb200_ctx {
   int device = 0;
   int sm_count = 0;
@@ -132,7 +134,10 @@ struct rsb200_ctx {
   uint8_t* d_out = nullptr;
   size_t d_out_cap = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr}; // H2D / kernel / D2H overlap
+  // H2D / kernel / D2H overlap of pipelined host-buffer runs: a group's upload, decode and download
+  // are chained on one stream; a decode of ~70 tiles takes ~0.25 ms however few CTAs it has, so it
+  // takes more than three groups in flight to keep the D2H engine busy
+  cudaStream_t pipe[N_PIPE] = {};
   // pinned staging for callers whose buffers are pageable (a RawImage is): grow only
   uint8_t* h_in = nullptr;
   size_t h_in_cap = 0;
@@ -292,6 +297,9 @@ struct rsb200_plan {
   int ntile = 0;
   int tile_r = 1;
   bool clean2 = false; // thread path: k2_clean2_kernel instead of k2_clean_kernel
+  bool use_stream = false; // thread path: k2_stream_kernel (unstuffing inside the thread) instead of K2C + K2T
+  bool host_tiles_only = false; // tile_groups / d_tile_ids describe the thread path's segments for host-buffer runs only
+  std::vector<uint32_t> h_in_size; // per scan: bytes of a plain LJPEG segment (kind 0), else 0xFFFFFFFF
   DevTileParam* d_thread_tile_params = nullptr; // thread path: parameters of the exact second opinion
   uint32_t* d_redo = nullptr;                   // ... and which segments need it (written by K2T)
   int nthread_redo = 0;                         // segments of the thread path the tile kernel can take
@@ -341,7 +349,7 @@ extern "C" int rsb200_create(int device, rsb200_ctx** out) {
   }
   if (e == cudaSuccess)
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+  for (int i = 0; i < N_PIPE && e == cudaSuccess; ++i)
     e = cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     fprintf(stderr, "rsb200_create: no usable CUDA device (%s); there is no CPU "
@@ -394,7 +402,7 @@ extern "C" void rsb200_destroy(rsb200_ctx* c) {
     cudaEventDestroy(e);
   if (c->stream)
     cudaStreamDestroy(c->stream);
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < N_PIPE; ++i)
     if (c->pipe[i])
       cudaStreamDestroy(c->pipe[i]);
   delete c;
@@ -1431,6 +1439,9 @@ constexpr uint32_t BIG_SEGMENT_BYTES = 256u << 10; // above this a segment gets 
 
 // Segments the one-thread-per-segment kernel handles: plain LJPEG tiles whose rows
 // are whole 8-sample units written with aligned 128-bit stores.
+#ifndef RSB200_STREAM_DEFAULT
+#define RSB200_STREAM_DEFAULT 0
+#endif
 constexpr size_t K2T_MIN_SEGMENTS = 16384; // measured crossover on B200: ~22 frames of 726 tiles
 static bool thread_eligible(const DevScan& d) {
   return d.kind == 0 && d.pump == 0 && d.mcu_h == 1 &&
@@ -1469,11 +1480,22 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
         ++n_el;
     use_thread = n_el >= K2T_MIN_SEGMENTS;
     if (const char* e = getenv("RSB200_LJPEG_PATH")) {
-      if (!strcmp(e, "thread"))
+      if (!strcmp(e, "thread") || !strcmp(e, "stream"))
         use_thread = true;
       else if (!strcmp(e, "fused") || !strcmp(e, "tile"))
         use_thread = false;
     }
+  }
+  // the thread path's kernel: k2_stream_kernel (raw bytes, unstuffed by the thread itself) or
+  // k2_clean_kernel + k2_thread_kernel; RSB200_LJPEG_PATH=stream|thread forces one (tests run both)
+  p->use_stream = RSB200_STREAM_DEFAULT != 0;
+  if (const char* e = getenv("RSB200_THREAD_KERNEL"))
+    p->use_stream = !strcmp(e, "stream");
+  if (const char* e = getenv("RSB200_LJPEG_PATH")) {
+    if (!strcmp(e, "stream"))
+      p->use_stream = true;
+    else if (!strcmp(e, "thread"))
+      p->use_stream = false;
   }
   // k2_tile_kernel<R> takes the plain single-table tiles; RSB200_LJPEG_PATH=fused keeps them on
   // k2_fused_kernel (tests run both), RSB200_TILE_R=1|2 picks the geometry, RSB200_TILE_PREROLL /
@@ -1540,13 +1562,17 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   }
   p->nsmall = (int)small_ids.size();
   p->ntile = (int)tile_ids.size();
-  if (!tile_ids.empty() && small_ids.empty() && thread_ids.empty() && big_ids.empty()) {
-    // groups of consecutive segments worth ~8 MB of output each
-    const uint64_t kGroupOut = 8ull << 20;
+  // host-buffer runs of a plan made of tile-kernel segments only are pipelined: groups of
+  // consecutive segments worth ~8 MB of output each (32 MB in plans of more than 1 GB)
+  auto build_groups = [&](const std::vector<uint32_t>& ids) {
+    uint64_t total = 0;
+    for (uint32_t i : ids)
+      total += (uint64_t)b.scans[i].rows * b.scans[i].store_w * 2;
+    const uint64_t kGroupOut = total > (1ull << 30) ? (32ull << 20) : (8ull << 20);
     rsb200_plan::TileGroup g{0, 0, ~0ull, 0, ~0ull, 0};
     uint64_t acc = 0;
-    for (size_t k = 0; k < tile_ids.size(); ++k) {
-      const DevScan& d = b.scans[tile_ids[k]];
+    for (size_t k = 0; k < ids.size(); ++k) {
+      const DevScan& d = b.scans[ids[k]];
       const uint64_t i0 = d.in_offset & ~15ull, i1 = (d.in_offset + d.in_size + 15) & ~15ull;
       const uint64_t o0 = d.out_offset + (uint64_t)d.out_y * d.out_pitch + 2ull * d.out_x;
       const uint64_t o1 = d.out_offset + ((uint64_t)d.out_y + d.rows - 1) * d.out_pitch +
@@ -1557,13 +1583,36 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
       g.out_hi = std::max(g.out_hi, o1);
       ++g.count;
       acc += (uint64_t)d.rows * d.store_w * 2;
-      if (acc >= kGroupOut || k + 1 == tile_ids.size()) {
+      if (acc >= kGroupOut || k + 1 == ids.size()) {
         p->tile_groups.push_back(g);
         g = rsb200_plan::TileGroup{(uint32_t)(k + 1), 0, ~0ull, 0, ~0ull, 0};
         acc = 0;
       }
     }
+  };
+  if (!tile_ids.empty() && small_ids.empty() && thread_ids.empty() && big_ids.empty())
+    build_groups(tile_ids);
+  // A plan on the thread path decodes device-resident input fastest with one thread per segment,
+  // but a host-buffer run is bound by the PCIe link (2 B/px down at ~50 GB/s): there the tile
+  // kernel, group by group between the upload and the download, hides the decode completely.
+  if (!thread_ids.empty() && tile_ids.empty() && small_ids.empty() && big_ids.empty() && use_tile &&
+      tile_r == 1 && !getenv("RSB200_NO_HOST_TILES")) {
+    bool all = true;
+    for (uint32_t i : thread_ids)
+      all = all && tile_eligible(b.scans[i], TileGeom<1>::MIN_RS);
+    if (all) {
+      tile_ids = thread_ids;
+      tile_prm.resize(tile_ids.size());
+      for (size_t k = 0; k < tile_ids.size(); ++k)
+        tile_params(b.scans[tile_ids[k]], TileGeom<1>::NPIECE, TileGeom<1>::DCAP, -1, tile_prm[k].npieces,
+                    tile_prm[k].preroll);
+      build_groups(tile_ids);
+      p->host_tiles_only = true;
+    }
   }
+  p->h_in_size.resize(b.scans.size());
+  for (size_t i = 0; i < b.scans.size(); ++i)
+    p->h_in_size[i] = b.scans[i].kind == 0 ? b.scans[i].in_size : 0xFFFFFFFFu;
   p->nthread = (int)thread_ids.size();
   if (!thread_ids.empty()) {
     uint64_t bytes = 0;
@@ -1597,7 +1646,15 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   up((void**)&p->d_strips, b.strips.data(), sizeof(DevStrip) * b.strips.size());
   up((void**)&p->d_rows, b.rows.data(), sizeof(K3RowRef) * b.rows.size());
   up((void**)&p->d_small_ids, small_ids.data(), sizeof(uint32_t) * small_ids.size());
-  up((void**)&p->d_thread_ids, thread_ids.data(), sizeof(uint32_t) * thread_ids.size());
+  {
+    // k2_stream_kernel reads "the tile kernel can give this segment a second opinion" from bit 31
+    std::vector<uint32_t> ids = thread_ids;
+    if (p->use_stream)
+      for (uint32_t& i : ids)
+        if (tile_eligible(b.scans[i], TileGeom<1>::MIN_RS))
+          i |= 0x80000000u;
+    up((void**)&p->d_thread_ids, ids.data(), sizeof(uint32_t) * ids.size());
+  }
   up((void**)&p->d_tile_ids, tile_ids.data(), sizeof(uint32_t) * tile_ids.size());
   up((void**)&p->d_tile_params, tile_prm.data(), sizeof(DevTileParam) * tile_prm.size());
   if (!thread_ids.empty()) {
@@ -1616,9 +1673,10 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
       n_anchor += t.n_anchor;
       tsc[k] = t;
     }
-    if (n_anchor >= (1ull << 32))
+    if (n_anchor >= (1ull << 32) && !p->use_stream)
       e = cudaErrorInvalidValue;
-    up((void**)&p->d_tscans, tsc.data(), sizeof(DevTScan) * tsc.size());
+    if (!p->use_stream)
+      up((void**)&p->d_tscans, tsc.data(), sizeof(DevTScan) * tsc.size());
     {
       std::vector<DevTileParam> tp(tsc.size());
       for (size_t k = 0; k < tsc.size(); ++k) {
@@ -1629,9 +1687,11 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
       up((void**)&p->d_thread_tile_params, tp.data(), sizeof(DevTileParam) * tp.size());
       alloc((void**)&p->d_redo, sizeof(uint32_t) * tsc.size());
     }
-    alloc((void**)&p->d_tinfos, sizeof(DevTInfo) * tsc.size());
-    alloc((void**)&p->d_clean, clean_words * 4 + 256);
-    alloc((void**)&p->d_anchors, n_anchor * 4 + 256);
+    if (!p->use_stream) {
+      alloc((void**)&p->d_tinfos, sizeof(DevTInfo) * tsc.size());
+      alloc((void**)&p->d_clean, clean_words * 4 + 256);
+      alloc((void**)&p->d_anchors, n_anchor * 4 + 256);
+    }
   }
   up((void**)&p->d_big_ids, big_ids.data(), sizeof(uint32_t) * big_ids.size());
   up((void**)&p->d_big, big.data(), sizeof(BigScanInfo) * big.size());
@@ -1654,7 +1714,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     return set_err(ctx, RSB200_ERR_CUDA, "ljpeg plan allocation failed: %s",
                    cudaGetErrorString(e));
   }
-  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->ntile ? 1 : 0) + (p->nthread ? 2 + (p->nthread_redo ? 1 : 0) : 0) +
+  p->launches_per_run = (p->nsmall ? 1 : 0) + (p->ntile ? 1 : 0) + (p->nthread ? (p->use_stream ? 1 : 2) + (p->nthread_redo ? 1 : 0) : 0) +
                         (p->nbig ? 5 + (p->has_k3 ? 2 : 0) + (p->has_pentax ? 2 : 0) + (p->has_nikon ? 2 : 0) : 0);
   return RSB200_OK;
 }
@@ -2114,7 +2174,13 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 1;
     }
-    if (p->nthread) {
+    if (p->nthread && p->use_stream) {
+      k2_stream_kernel<<<(p->nthread + T_NT - 1) / T_NT, T_NT, stream_smem_bytes(p->ntables), st>>>(
+          in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->ntables, outp, p->d_results,
+          p->d_thread_ids, (uint32_t)p->nthread, p->d_redo);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    } else if (p->nthread) {
       // unstuffing pre-pass: one CTA per segment with the tile kernel's stage B for DNG-size
       // segments (k2_clean2_kernel), one warp per segment for small ones (k2_clean_kernel)
       if (p->clean2)
@@ -2130,6 +2196,8 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
           (uint32_t)p->nthread, p->d_tscans, p->d_tinfos, p->d_clean, p->d_anchors, p->d_redo);
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 2;
+    }
+    if (p->nthread) {
       if (p->nthread_redo) {
         // exact end-of-stream semantics for the segments K2T flagged (CTAs of the others exit at once)
         k2_tile_kernel<1><<<p->nthread, TL_NT, tile_smem_bytes<1>(), st>>>(
@@ -2225,7 +2293,7 @@ static int run_host_unpack_pipelined(rsb200_plan* p, const uint8_t* in, size_t i
   const UnpackFastGroup& g = p->fast_groups[0];
   for (size_t j = 0; j < g.h_jobs.size(); ++j) {
     const UnpackFastJobDev& jb = g.h_jobs[j];
-    cudaStream_t st = ctx->pipe[j % 3];
+    cudaStream_t st = ctx->pipe[j % N_PIPE];
     const uint64_t i0 = jb.in_offset & ~15ull;
     uint64_t i1 = jb.in_offset + (uint64_t)jb.rows * jb.in_pitch;
     i1 = std::min<uint64_t>((i1 + 15) & ~15ull, in_bytes);
@@ -2237,7 +2305,7 @@ static int run_host_unpack_pipelined(rsb200_plan* p, const uint8_t* in, size_t i
     ctx->launches++;
     CUDA_TRY(ctx, cudaMemcpyAsync(out + o0, ctx->d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, st));
   }
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < N_PIPE; ++i)
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->pipe[i]));
   p->last_stream = ctx->pipe[0];
   p->ran = true;
@@ -2346,7 +2414,7 @@ static int run_host_tile_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_
   const bool rows2d = pitch && row_bytes && row_bytes < pitch;
   for (size_t gi = 0; gi < p->tile_groups.size(); ++gi) {
     const rsb200_plan::TileGroup& g = p->tile_groups[gi];
-    cudaStream_t st = ctx->pipe[gi % 3];
+    cudaStream_t st = ctx->pipe[gi % N_PIPE];
     const uint64_t i1c = std::min<uint64_t>(g.in_hi, in_bytes);
     const uint64_t o1 = std::min<uint64_t>(g.out_hi, out_bytes);
     if (i1c > g.in_lo) {
@@ -2391,7 +2459,7 @@ static int run_host_tile_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_
       }
     }
   }
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < N_PIPE; ++i)
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->pipe[i]));
   p->last_stream = ctx->pipe[0];
   p->ran = true;
@@ -2792,6 +2860,13 @@ extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, 
       }
       continue;
     }
+    // The reference skips `consumed` bytes of its input when a scan is done
+    // (LJpegDecompressor.cpp:339 inputStream.skipBytes(bs.getStreamPosition())) and throws when
+    // the buffer is shorter: a buffer that ends inside the last refill of the pump is an
+    // IOException even though every symbol was there.  One rule for every LJPEG kernel.
+    if (p->h_results[i].status == 0 && (size_t)i < p->h_in_size.size() &&
+        p->h_results[i].consumed > p->h_in_size[(size_t)i])
+      p->h_results[i].status = RSB200_ERR_IOE;
     if (results && i < n) {
       results[i].status = p->h_results[i].status;
       results[i].consumed = p->h_results[i].consumed;

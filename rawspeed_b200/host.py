@@ -33,7 +33,7 @@ EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white",
            "rsb200h_panasonic_v4", "rsb200h_dng_opcodes", "rsb200h_dngop_lower",
            "rsb200h_fix_bad_pixels", "rsb200h_sixteen_bit_lookup",
-           "rsb200h_dng_ljpeg_host_half"]
+           "rsb200h_dng_ljpeg_host_half", "rsb200h_last_call_ms"]
 
 _lib = None
 
@@ -139,6 +139,14 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h, 
                                          compression, int(fix_ljpeg), bps, int(big_endian),
                                          C.byref(e)))
     return img
+
+
+def last_call_ms():
+    """Wall time of the decompressor's member call inside the last dng_decompress() of this thread
+    (the harness around it allocates a RawImage and copies the numpy array in and out)."""
+    L = lib()
+    L.rsb200h_last_call_ms.restype = C.c_double
+    return float(L.rsb200h_last_call_ms())
 
 
 def pentax_decompress(img, w, data, meta=None, meta_be=True):

@@ -380,6 +380,7 @@ template <int OFF = 0> static inline void sts_v2(uint32_t saddr, const uint2& v)
 template <int OFF = 0> static inline void sts_v4(uint32_t saddr, const uint4& v) {
   memcpy(emu_saddr(saddr, OFF, 16), &v, 16);
 }
+static inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel & 0xFFFFu); }
 static inline uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {
   return (uint32_t)(((uint64_t)a * b) >> 32) + c;
 }
