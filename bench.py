@@ -747,9 +747,7 @@ def main():
 
 
 def kernel_name(plan, nframes):
-    if plan.launches == 1:
-        return "k2_tile_kernel<%s> (one CTA per tile)" % os.environ.get("RSB200_TILE_R", "1")
-    return "k2_clean_kernel + k2_thread_kernel (one thread per tile)"
+    return plan.kernels
 
 
 def pin_rank_to_numa(local):
@@ -1313,6 +1311,40 @@ def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
                                     "MPixels/s": w * h / (msr * 1e-3) / 1e6,
                                     "sample": "PhaseOneDecompressor::decompress (OpenMP over rows), best of 2"}
     out["8(f)4 PhaseOneDecompressor 11608x8708"] = ent
+    del plan, d_in, d_out
+    # ---- HasselbladDecompressor, 8272x6200 (H5D-50c class, 51 MP): one MSB32 pair stream per frame ----
+    w, h = 8272, 6200
+    himg = synth.image_model(w, 200, seed=41, bits=14)
+    himg = np.tile(himg, (h // 200, 1))          # (rows restart their predictors: any rows will do)
+    hht = port.Huff(synth.DEFAULT_NCPL, synth.DEFAULT_VALUES, full=False)
+    hdata = synth.make_hasselblad_fast(himg, hht, 0x8000)
+    hj = rs.HasselbladJob()
+    hj.in_offset, hj.in_size, hj.width, hj.height = 0, hdata.size, w, h
+    hj.out_pitch, hj.out_offset, hj.init_pred, hj.table = rs.image_pitch(w), 0, 0x8000, 0
+    plan = rs.hasselblad_plan(ctx, [rs.huff_table(bytes(synth.DEFAULT_NCPL), bytes(synth.DEFAULT_VALUES), False)], [hj])
+    d_in = torch.zeros(hdata.size + 64, dtype=torch.uint8, device="cuda")
+    d_in[:hdata.size] = torch.from_numpy(hdata)
+    d_out = torch.zeros(h * rs.image_pitch(w), dtype=torch.uint8, device="cuda")
+    plan.run((d_in.data_ptr(), hdata.size), d_out)
+    res = plan.results()
+    got = d_out.cpu().numpy().view(np.uint16).reshape(h, rs.image_pitch(w) // 2)
+    exact = res[0][0] == 0 and bool(np.array_equal(got[:, :w], himg))
+    ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), hdata.size), d_out), steps, 3, dist)
+    per = ms / steps
+    ent = {"MPixels/s": w * h / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": bool(exact),
+           "compressed_bytes_per_pixel": hdata.size / (w * h), "launches_per_frame": plan.launches,
+           "achieved_GBps": (hdata.size + 2 * w * h) / (per * 1e-3) / 1e9,
+           "roofline_frac": (hdata.size + 2 * w * h) / (per * 1e-3) / 1e9 / peak,
+           "kernel": "hass_parse/link x6 + scan + hass_decode + hass_rows (one thread per 2 KiB of stream)"}
+    if not args.skip_cpu and rank0:
+        tmp = port.new_image(w, h)
+        t0 = time.perf_counter()
+        port.hasselblad_decompress(tmp, w, hht, 0x8000, hdata)
+        msr = (time.perf_counter() - t0) * 1e3
+        ent["cpu_reference"] = {"kind": "port", "cores": 1, "MPixels/s": w * h / (msr * 1e-3) / 1e6,
+                                "sample": "the oracle's HasselbladDecompressor restatement (single threaded by "
+                                          "design: one stream), 1 frame"}
+    out["8(f)2 HasselbladDecompressor 8272x6200"] = ent
     del plan, d_in, d_out
     # ---- SonyArw2Decompressor, 9568x6376 (61 MP, A7R IV class), dithered curve, 4 frames ----
     w, h, nf = 9568, 6376, 4

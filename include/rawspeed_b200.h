@@ -563,8 +563,37 @@ int rsb200_plan_results(rsb200_plan* plan, rsb200_scan_result* results,
  * for roofline accounting. */
 int rsb200_plan_bytes(const rsb200_plan* plan, uint64_t* in_bytes,
                       uint64_t* out_bytes, uint64_t* pixels);
+/* ------------------------------------------------------------------ */
+/* HasselbladDecompressor (reference: decompressors/HasselbladDecompressor.h:37-64 ctor + decompress(),
+ * HasselbladDecompressor.cpp:39-100; caller HasselbladLJpegDecoder::decodeScan,
+ * HasselbladLJpegDecoder.cpp:50-69).  One frame is ONE Huffman stream over the MSB32 bit source
+ * (32-bit little-endian chunks, most significant bit first), per pair of pixels
+ * [len1 code][len2 code][len1 bits][len2 bits]; both predictors restart at init_pred in every row.
+ * The table's values are difference lengths 0..16; a difference of 16 one-bits means -32768.
+ * rsb200_plan_results: per job RSB200_ERR_RDE for a code that is not in the table ("bad Huffman
+ * code"), RSB200_ERR_IOE where the reference's replenisher throws (a refill more than 8 bytes behind
+ * the buffer), whichever comes first in stream order; consumed = the reference's
+ * BitStreamerMSB32::getStreamPosition() after the last pair. */
+typedef struct rsb200_hasselblad_job {
+  uint64_t in_offset;  /* first byte of the stream in the input buffer; multiple of 4 */
+  uint32_t in_size;    /* bytes of the stream (what the reference's Array1DRef input holds) */
+  uint32_t width;      /* pixels, even, <= 12000 */
+  uint32_t height;     /* <= 8842 */
+  uint32_t out_pitch;  /* bytes, multiple of 4 */
+  uint64_t out_offset; /* first byte of the image in the output buffer; multiple of 4 */
+  uint16_t init_pred;  /* PerComponentRecipe::initPred */
+  uint8_t table;       /* index into `tables` */
+  uint8_t reserved[5];
+} rsb200_hasselblad_job;
+int rsb200_hasselblad_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables, int ntables,
+                                  const rsb200_hasselblad_job* jobs, int njobs, rsb200_plan** plan);
+
 /* Kernels launched by one rsb200_plan_run(). */
 int rsb200_plan_launches(const rsb200_plan* plan);
+/* Which kernels one rsb200_plan_run() of this plan launches, as a short static string (for logs and
+ * the benchmark's JSON line), e.g. "k2_stream_kernel (one thread per segment) [+ k2_tile_kernel<1>
+ * second opinion]"; "" for a null plan. */
+const char* rsb200_plan_kernels(const rsb200_plan* plan);
 void rsb200_plan_destroy(rsb200_plan* plan);
 
 /* ------------------------------------------------------------------ */

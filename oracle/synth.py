@@ -384,6 +384,43 @@ def make_hasselblad(img, ht, init_pred):
     return np.frombuffer(words.tobytes() + bytes(16), dtype=np.uint8).copy()
 
 
+def make_hasselblad_fast(img, ht, init_pred):
+    """make_hasselblad() with numpy (same bytes; for frames of megapixels)."""
+    codes = {v: cl for v, cl in zip(ht.values, ht.symbols())}
+    h, w = img.shape
+    a = img.astype(np.int64).reshape(h, w // 2, 2)
+    prev = np.concatenate([np.full((h, 1, 2), init_pred, dtype=np.int64), a[:, :-1, :]], axis=1)
+    d = (a - prev + 32768) % 65536 - 32768                      # differences mod 2^16, per component
+    n = np.zeros(d.shape, dtype=np.int64)
+    ad = np.abs(d)
+    nz = ad > 0
+    n[nz] = np.floor(np.log2(ad[nz])).astype(np.int64) + 1
+    m = np.where(d > 0, d, d + (1 << n) - 1)
+    m = np.where(d == -32768, 0xFFFF, m)
+    n = np.where(d == -32768, 16, n)
+    m = np.where(n == 0, 0, m)
+    code_v = np.zeros(17, dtype=np.int64)
+    code_l = np.zeros(17, dtype=np.int64)
+    for v, (c, l) in codes.items():
+        code_v[v], code_l[v] = c, l
+    # tokens per pair in stream order: code1, code2, mantissa1, mantissa2
+    val = np.stack([code_v[n[..., 0]], code_v[n[..., 1]], m[..., 0], m[..., 1]], axis=-1).reshape(-1)
+    nb = np.stack([code_l[n[..., 0]], code_l[n[..., 1]], n[..., 0], n[..., 1]], axis=-1).reshape(-1)
+    pos = np.concatenate([[0], np.cumsum(nb)])
+    total = int(pos[-1])
+    pos = pos[:-1]
+    nwords = (total + 31) // 32 + 1
+    off = pos & 31
+    widx = pos >> 5
+    v64 = val.astype(np.uint64) << (64 - off - nb).astype(np.uint64)  # left aligned in 64 bits at its offset
+    hi = (v64 >> np.uint64(32)).astype(np.float64)
+    lo = (v64 & np.uint64(0xFFFFFFFF)).astype(np.float64)
+    words = np.bincount(widx, weights=hi, minlength=nwords + 1)[:nwords + 1] + \
+        np.concatenate([[0.0], np.bincount(widx, weights=lo, minlength=nwords)[:nwords]])
+    words = words[:(total + 31) // 32].astype(np.uint64).astype("<u4")
+    return np.frombuffer(words.tobytes() + bytes(16), dtype=np.uint8).copy()
+
+
 def _canonical(ncpl, values):
     """value -> (code, length) by T.81 C.1/C.2 (the first occurrence of a value wins)."""
     out, code, k = {}, 0, 0

@@ -113,6 +113,12 @@ class PhaseOneJob(C.Structure):
                 ("height", C.c_uint32), ("first_strip", C.c_uint32)]
 
 
+class HasselbladJob(C.Structure):
+    _fields_ = [("in_offset", C.c_uint64), ("in_size", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("out_pitch", C.c_uint32), ("out_offset", C.c_uint64),
+                ("init_pred", C.c_uint16), ("table", C.c_uint8), ("reserved", C.c_uint8 * 5)]
+
+
 class Arw2Job(C.Structure):
     _fields_ = [("in_offset", C.c_uint64), ("out_offset", C.c_uint64),
                 ("out_pitch", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32),
@@ -157,10 +163,10 @@ EXPORTS = [
     "rsb200_kernel_launches", "rsb200_device_sm_count", "rsb200_unpack_plan_create",
     "rsb200_raw_plan_create", "rsb200_sraw_plan_create",
     "rsb200_pentax_plan_create", "rsb200_arw2_plan_create", "rsb200_nikon_plan_create",
-    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_scale_plan_create", "rsb200_plan_bad_pixels", "rsb200_dngop_plan_create", "rsb200_badpix_plan_create", "rsb200_lookup_plan_create",
+    "rsb200_pana_plan_create", "rsb200_phaseone_plan_create", "rsb200_hasselblad_plan_create", "rsb200_scale_plan_create", "rsb200_plan_bad_pixels", "rsb200_dngop_plan_create", "rsb200_badpix_plan_create", "rsb200_lookup_plan_create",
     "rsb200_ljpeg_plan_create", "rsb200_cr2_plan_create", "rsb200_plan_run",
     "rsb200_plan_run_host", "rsb200_plan_run_host_image", "rsb200_plan_results", "rsb200_plan_bytes",
-    "rsb200_plan_launches", "rsb200_plan_destroy",
+    "rsb200_plan_launches", "rsb200_plan_kernels", "rsb200_plan_destroy",
     "rsb200_comm_unique_id", "rsb200_comm_create", "rsb200_comm_destroy", "rsb200_plan_run_gather",
 ]
 
@@ -199,6 +205,8 @@ def load():
     L.rsb200_nikon_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32, C.POINTER(NikonJob), i32,
                                            C.POINTER(C.c_uint16), i32, C.POINTER(vp)]
     L.rsb200_pana_plan_create.argtypes = [vp, C.POINTER(PanaJob), i32, C.POINTER(vp)]
+    L.rsb200_hasselblad_plan_create.argtypes = [vp, C.POINTER(HuffTable), i32, C.POINTER(HasselbladJob), i32,
+                                                C.POINTER(vp)]
     L.rsb200_phaseone_plan_create.argtypes = [vp, C.POINTER(PhaseOneJob), i32,
                                               C.POINTER(PhaseOneStrip), i32, C.POINTER(vp)]
     L.rsb200_arw2_plan_create.argtypes = [vp, C.POINTER(Arw2Job), i32, C.POINTER(C.c_uint16),
@@ -224,6 +232,8 @@ def load():
     L.rsb200_plan_bad_pixels.argtypes = [vp, i32, u32p, C.c_uint32, u32p]
     L.rsb200_plan_bytes.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.rsb200_plan_launches.argtypes = [vp]
+    L.rsb200_plan_kernels.argtypes = [vp]
+    L.rsb200_plan_kernels.restype = C.c_char_p
     L.rsb200_plan_destroy.argtypes = [vp]
     L.rsb200_plan_destroy.restype = None
     L.rsb200_comm_unique_id.argtypes = [vp]

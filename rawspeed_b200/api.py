@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (Arw2Job, NikonJob, PanaJob, ScaleJob, DngOp, DngOpJob, BadPixJob, LookupJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
+from ._abi import (Arw2Job, HasselbladJob, NikonJob, PanaJob, ScaleJob, DngOp, DngOpJob, BadPixJob, LookupJob, PhaseOneJob, PhaseOneStrip, Cr2Job, HuffTable, LJpegScan, PentaxJob, RawJob, ScanResult, SrawJob, UnpackJob,  # noqa: F401
                    LSB, MSB, MSB16, MSB32)
 
 
@@ -167,6 +167,11 @@ class Plan:
     def launches(self):
         return int(self.ctx._lib.rsb200_plan_launches(self.h))
 
+    @property
+    def kernels(self):
+        """Which kernels one run of this plan launches (a short description)."""
+        return self.ctx._lib.rsb200_plan_kernels(self.h).decode()
+
 
 GATHER_NONE, GATHER_ALL, GATHER_ROOT = 0, 1, 2
 
@@ -310,6 +315,16 @@ def phaseone_plan(ctx, jobs, strips):
     h = C.c_void_p()
     ctx.check(ctx._lib.rsb200_phaseone_plan_create(ctx.h, ja, len(jobs), sa, len(strips),
                                                    C.byref(h)))
+    return Plan(ctx, h, len(jobs))
+
+
+def hasselblad_plan(ctx, tables, jobs):
+    """Hasselblad 3FR frames (HasselbladDecompressor::decompress), one job per frame: one MSB32
+    Huffman stream of pixel pairs.  plan.results(): per job (status, consumed)."""
+    ta = (HuffTable * len(tables))(*tables)
+    ja = (HasselbladJob * len(jobs))(*jobs)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.rsb200_hasselblad_plan_create(ctx.h, ta, len(tables), ja, len(jobs), C.byref(h)))
     return Plan(ctx, h, len(jobs))
 
 

@@ -307,6 +307,18 @@ int rsb200h_cr2_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_
   });
 }
 
+// HasselbladLJpegDecoder(bs, img).decode(): the LJPEG container walk on the host, the pair stream on
+// the device
+int rsb200h_hasselblad_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_data, int w, int h,
+                                    int pitch, rsb200h_err* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(img_data, w, h, 1, pitch, true, 1, 1);
+    HasselbladLJpegDecoder d(ByteStream(in, in_size), img);
+    d.decode();
+    copyOut(img, img_data);
+  });
+}
+
 int rsb200h_pentax_decompress(uint16_t* img_data, int w, int h, int pitch, const uint8_t* meta,
                               int meta_size, int meta_be, const uint8_t* data, uint32_t size,
                               rsb200h_err* e) {

@@ -2169,6 +2169,84 @@ void Cr2LJpegDecoder::decode(const Cr2SliceWidths& slicing_) {
   decodeSOI();
 }
 
+// ------------------------------------------------------------------ Hasselblad
+// ctor (decompressors/HasselbladDecompressor.cpp:39-58)
+HasselbladDecompressor::HasselbladDecompressor(RawImage mRaw_, const PerComponentRecipe& rec_, Buffer input_)
+    : mRaw(std::move(mRaw_)), rec(rec_), input(input_) {
+  if (mRaw->getDataType() != RawImageType::UINT16)
+    ThrowRDE("Unexpected data type");
+  if (mRaw->getCpp() != 1 || mRaw->getBpp() != sizeof(uint16_t))
+    ThrowRDE("Unexpected cpp: %u", mRaw->getCpp());
+  // FIXME (reference): could be wrong. max "active pixels" - "100 MP"
+  if (!mRaw->dim.hasPositiveArea() || mRaw->dim.x % 2 != 0 || mRaw->dim.x > 12000 || mRaw->dim.y > 8842)
+    ThrowRDE("Unexpected image dimensions found: (%d; %d)", mRaw->dim.x, mRaw->dim.y);
+  if (rec.ht.isFullDecode())
+    ThrowRDE("Huffman table is of a full decoding variety");
+}
+
+// decompress (:72-100)
+uint32_t HasselbladDecompressor::decompress() {
+  // ht.verifyCodeValuesAsDiffLengths() (codes/AbstractPrefixCode.h)
+  for (const uint8_t v : rec.ht.code.codeValues)
+    if (v > 16)
+      ThrowRDE("Corrupt Huffman code: difference length %u longer than 16", (unsigned)v);
+  if (input.getSize() < 4) // BitStreamerMSB32 ctor
+    ThrowIOE("Bit stream size is smaller than MaxProcessBytes");
+  rsb200_huff_table t = rec.ht.deviceTable();
+  rsb200_hasselblad_job j;
+  std::memset(&j, 0, sizeof j);
+  j.in_offset = 0;
+  j.in_size = input.getSize();
+  j.width = (uint32_t)mRaw->dim.x;
+  j.height = (uint32_t)mRaw->dim.y;
+  j.out_pitch = (uint32_t)mRaw->pitch;
+  j.out_offset = 0;
+  j.init_pred = rec.initPred;
+  j.table = 0;
+  PlanGuard pg;
+  engineCheck(rsb200_hasselblad_plan_create(engine(), &t, 1, &j, 1, &pg.p), "rsb200_hasselblad_plan_create");
+  RawImage img = mRaw;
+  runOnImage(pg.p, input.begin(), input.getSize(), img, /*partial=*/false);
+  rsb200_scan_result res{};
+  (void)rsb200_plan_results(pg.p, &res, 1);
+  if (res.status == RSB200_ERR_RDE)
+    ThrowRDE("bad Huffman code");
+  if (res.status == RSB200_ERR_IOE)
+    ThrowIOE("Buffer overflow read in BitStreamer");
+  if (res.status != RSB200_OK)
+    ThrowRDE("device error %u", res.status);
+  return res.consumed;
+}
+
+// HasselbladLJpegDecoder.cpp:35-48
+HasselbladLJpegDecoder::HasselbladLJpegDecoder(ByteStream bs, const RawImage& img)
+    : AbstractLJpegDecoder(bs, img) {
+  if (mRaw->getCpp() != 1 || mRaw->getDataType() != RawImageType::UINT16 || mRaw->getBpp() != sizeof(uint16_t))
+    ThrowRDE("Unexpected component count / data type");
+  if (!mRaw->dim.hasPositiveArea() || mRaw->dim.x % 2 != 0 || mRaw->dim.x > 12000 || mRaw->dim.y > 8842)
+    ThrowRDE("Unexpected image dimensions found: (%d; %d)", mRaw->dim.x, mRaw->dim.y);
+}
+
+// decodeScan (:50-69)
+void HasselbladLJpegDecoder::prepareScan() {
+  if (numMCUsPerRestartInterval != 0)
+    ThrowRDE("Non-zero restart interval not supported.");
+  if (frame.w != (unsigned)mRaw->dim.x || frame.h != (unsigned)mRaw->dim.y)
+    ThrowRDE("LJPEG frame does not match EXIF dimensions: (%u; %u) vs (%i; %i)", frame.w, frame.h,
+             mRaw->dim.x, mRaw->dim.y);
+  const HasselbladDecompressor::PerComponentRecipe rec = {*getPrefixCodeDecoders(1)[0],
+                                                          getInitialPredictors(1)[0]};
+  d = std::make_unique<HasselbladDecompressor>(mRaw, rec, input.peekRemainingBuffer());
+}
+
+uint32_t HasselbladLJpegDecoder::runScan() { return d->decompress(); }
+
+// decode (:71-77): the pair stream cannot use a fully decoding table
+void HasselbladLJpegDecoder::decode() {
+  fullDecodeHT = false;
+  decodeSOI();
+}
+
 // ------------------------------------------------------------------ DNG
 namespace {
 // the byte span of the file covered by the tiles (they all view one file buffer)

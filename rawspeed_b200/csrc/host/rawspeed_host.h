@@ -531,6 +531,36 @@ private:
   std::unique_ptr<Cr2Decompressor<>> d;
 };
 
+// ---------------------------------------------------------------- Hasselblad
+// decompressors/HasselbladDecompressor.h:37-64 / HasselbladLJpegDecoder.h: same constructors and
+// decompress() / decode().  Header walk and validation on the host, the pair stream on the device
+// (rsb200_hasselblad_plan_create).
+class HasselbladDecompressor final {
+public:
+  struct PerComponentRecipe {
+    const PrefixCodeDecoder<>& ht;
+    uint16_t initPred;
+  };
+  HasselbladDecompressor(RawImage mRaw, const PerComponentRecipe& rec, Buffer input);
+  uint32_t decompress(); // returns BitStreamerMSB32::getStreamPosition()
+
+private:
+  RawImage mRaw;
+  PerComponentRecipe rec;
+  Buffer input;
+};
+
+class HasselbladLJpegDecoder final : public AbstractLJpegDecoder {
+public:
+  HasselbladLJpegDecoder(ByteStream bs, const RawImage& img);
+  void decode();
+
+private:
+  void prepareScan() override;
+  uint32_t runScan() override;
+  std::unique_ptr<HasselbladDecompressor> d;
+};
+
 // ---------------------------------------------------------------- Pentax
 // decompressors/PentaxDecompressor.h: same constructor (image + optional table
 // description from the maker note) and decompress(ByteStream).  Table set-up and

@@ -39,8 +39,7 @@ namespace rsb200 {
 constexpr uint32_t S_OPEN = 0x1FFFFFFFu; // clean_len while the end of the data has not been seen
 constexpr uint32_t S_MIN = 44;   // whole clean words (bytes) that a unit needs ahead of its first bit
 constexpr uint32_t S_LOW = 64;   // a lane below this asks the warp for a fill step
-constexpr uint32_t S_LOW2 = 56;  // ... and takes two blocks in it
-constexpr uint32_t S_ROOM = 104; // a lane at or below this takes part (ring: 128 bytes; see s_ring_note)
+constexpr uint32_t S_ROOM = 88;  // a lane at or below this takes part: two blocks (ring: 128 bytes; see s_ring_note)
 // idx*4 of the 4 "remove" flags (bits 7, 15, 23, 31) in bits 2..5 of the high product word
 constexpr uint32_t S_IDXMUL = (1u << 27) | (1u << 20) | (1u << 13) | (1u << 6);
 
@@ -234,9 +233,11 @@ __device__ __noinline__ SFill s_fill_now(SFill f, uint32_t ringb, uint32_t selb,
                                          const uint8_t* __restrict__ gbase, uint32_t bmax, uint32_t skew,
                                          uint32_t limit) {
   const uint32_t blk = f.nblk;
-  const uint4 q = __ldg(reinterpret_cast<const uint4*>(gbase) + min(blk, bmax));
+  uint4 q = make_uint4(0, 0, 0, 0);
+  if (16u * (blk + 1u) > skew) // (a block wholly before the segment is not read)
+    q = __ldg(reinterpret_cast<const uint4*>(gbase) + min(blk, bmax));
   f.nblk = blk + 1u;
-  if (blk == 0u || blk >= f.slow_from) {
+  if (16u * blk < skew || blk >= f.slow_from) { // bytes before the segment (skew <= 31) / the end
     f = s_slow_block(f, ringb, einfo, q, blk, skew, limit);
   } else {
     s_block(f, ringb, selb, einfo, q, blk, gbase, skew, limit);
@@ -312,19 +313,103 @@ __device__ __forceinline__ bool s_any(bool want) { return __any_sync(__activemas
     val = pred[c];                                                              \
   } while (0)
 
-template <int G>
+// The same without control flow, for the straight-line unit: a code the LUT does not resolve
+// (longer than LUT_BITS, SSSS = 16, corrupt) leaves p where it is, so every later symbol of the
+// unit sees the same window and misses too; nok counts the symbols before the first miss and the
+// unit is finished symbol by symbol (S_SYM) from there.  Without a branch per symbol the eight
+// decodes are one basic block: the difference arithmetic of symbol k is scheduled into the
+// latency of symbol k+1's LUT load.
+#define S_SYMF(c, val)                                                          \
+  do {                                                                          \
+    const uint32_t x_ = __funnelshift_l(nxt, cur, p);                           \
+    const uint32_t e_ = lds_u16<0>(                                             \
+        mad_hi(x_ & ~((1u << (32 - LUT_BITS)) - 1u), 1u << (LUT_BITS + 1), lutb[c])); \
+    const bool hit_ = e_ != 0u;                                                 \
+    nok += hit_ ? 1u : 0u;                                                      \
+    const uint32_t tt_ = __funnelshift_l(0u, x_, e_);                           \
+    const uint32_t f_ = (uint32_t)((int32_t)~tt_ >> 31);                        \
+    uint32_t d_ = __funnelshift_l(tt_, f_, e_ >> 5) - f_;                       \
+    d_ = hit_ ? d_ : 0u;                                                        \
+    last_tl = e_ >> 10;                                                         \
+    const uint32_t pn_ = p + last_tl;                                           \
+    if ((pn_ ^ p) & 32u) {                                                      \
+      cur = nxt;                                                                \
+      nxt = nn;                                                                 \
+      nn = lds_u32<0>(ringb + (wv & T_RMASK));                                  \
+      wv += T_WSTRIDE;                                                          \
+    }                                                                           \
+    p = pn_;                                                                    \
+    pred[c] += d_;                                                              \
+    val = pred[c];                                                              \
+  } while (0)
+
+#ifndef RSB200_S_STRAIGHT
+#define RSB200_S_STRAIGHT 1
+#endif
+#ifndef RSB200_S_PREFETCH
+#define RSB200_S_PREFETCH 8 // blocks ahead of a requested sector that are pulled into L2 when the launch is small
+#endif
+#ifndef RSB200_S_LD256
+#define RSB200_S_LD256 1 // one 256-bit load per sector
+#endif
+#ifndef RSB200_S_ST256
+#define RSB200_S_ST256 1 // 0: never use the 256-bit stores (A/B)
+#endif
+
+__device__ __forceinline__ void stg_cs_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                          uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+#ifndef RSB200_EMU
+  asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c),
+               "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+#else
+  const uint32_t v[8] = {a, b, c, d, e, f, g, h};
+  memcpy(p, v, 32);
+#endif
+}
+
+__device__ __forceinline__ void s_prefetch_l2(const void* p) {
+#ifndef RSB200_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+// A lane's next two 16-byte blocks = one 32-byte sector, with ONE 256-bit load (sm_100:
+// LDG.E.ENL2.256).  Measured (ncu, 256 frames, profiles/r2_ncu_ljpeg.md): with a 16-byte load per
+// block 37 % of all warp samples sat on the first instruction that uses the block.  113 k streams
+// of lane-private requests are bound by the NUMBER of sector requests the memory system serves
+// (an L2 prefetch per block made small batches faster, -13 % at 32 frames, and full ones slower,
+// +6 % at 256 frames: it adds requests); asking for each sector once halves them.
+__device__ __forceinline__ void s_ldg_sector(const uint4* cb, uint32_t blk, uint32_t bmax, uint4& a,
+                                             uint4& b) {
+#if !defined(RSB200_EMU) && RSB200_S_LD256
+  if (blk < bmax) { // (blk even, cb 32-byte aligned; the last readable block may be the sector's first half)
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(cb + blk));
+    return;
+  }
+#endif
+  a = __ldg(cb + min(blk, bmax));
+  b = __ldg(cb + min(blk + 1u, bmax));
+}
+
+template <int G, bool WIDE>
 __device__ __forceinline__ void
-stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_redo,
+stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_redo, const bool prefetch,
             const uint8_t* __restrict__ in, uint64_t in_total, uint8_t* __restrict__ out,
             DevResult* __restrict__ res, uint32_t* __restrict__ redo) {
-  const uint64_t in_offset = scp->in_offset;
-  const uint64_t abase = in_offset & ~15ull;
-  const uint32_t skew = (uint32_t)(in_offset - abase);
+  // raw offsets count from the 32-byte boundary at or before the segment's first byte
+  const uint8_t* first = in + scp->in_offset;
+  const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 31u);
   const uint32_t limit = skew + scp->in_size;
-  const uint8_t* gbase = in + abase;
+  const uint8_t* gbase = first - skew;
   const uint4* cb = reinterpret_cast<const uint4*>(gbase);
-  // the caller's buffer is readable up to the next 16-byte boundary behind in_total
-  const uint64_t nreadable = (((in_total + 15ull) & ~15ull) - abase) >> 4;
+  // the caller's buffer is readable up to the next 16-byte boundary behind in_total; a block that
+  // lies wholly before the segment (skew >= 16) is never loaded, so nothing before `in` is touched
+  const uint64_t nreadable = (uint64_t)((in + ((in_total + 15ull) & ~15ull)) - gbase) >> 4;
   const uint32_t bmax = (nreadable > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)nreadable) - 1u;
   const uint32_t ringb = smem_u32(&sh.ring[0][threadIdx.x]);
   const uint32_t selb = smem_u32(sh.sel);
@@ -339,7 +424,7 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
   f.slow_from = limit >> 4;
   f.clean_len = S_OPEN;
   // prefill
-  while ((f.wo >> 7) < S_LOW)
+  while ((f.wo >> 7) < S_LOW || (f.nblk & 1u)) // (sectors are taken whole from here on: nblk stays even)
     f = s_fill_now(f, ringb, selb, einfo, gbase, bmax, skew, limit);
   uint32_t cur = sh.ring[0][threadIdx.x], nxt = sh.ring[1][threadIdx.x],
            nn = sh.ring[2][threadIdx.x];
@@ -360,6 +445,9 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
   const uint32_t out_pitch = scp->out_pitch;
   uint8_t* orow = out + scp->out_offset + (uint64_t)scp->out_y * out_pitch + 2ull * scp->out_x;
   uint32_t bad = 0, last_tl = 0;
+  // (WIDE: pairs of units leave with one 256-bit store where the rows allow it)
+  const bool wide = WIDE && RSB200_S_ST256 && ((reinterpret_cast<uintptr_t>(orow) | out_pitch) & 31u) == 0u;
+  uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
 
   for (uint32_t r = 0; r < rows; ++r) {
 #pragma unroll
@@ -372,24 +460,51 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
       //      word W may replace word W - T_RING once that one was fetched (< (p >> 5) + 3):
       //      ahead <= 121 (two blocks: 105) before the step. ----
       uint32_t ahead = (f.wo >> 7) - (p >> 3);
-      while (ahead < S_MIN) { // ran dry (more than 16 bytes per unit for a while): fill on my own
+      while (ahead < S_MIN) { // ran dry (more than 32 bytes per unit for a while): fill on my own
+        f = s_fill_now(f, ringb, selb, einfo, gbase, bmax, skew, limit);
         f = s_fill_now(f, ringb, selb, einfo, gbase, bmax, skew, limit);
         ahead = (f.wo >> 7) - (p >> 3);
       }
       // blocks requested here go into the ring at the END of the unit: no load is in flight
       // across the loop edge and the decode of the unit hides their latency
       uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-      uint32_t pend = 0;
+      bool pend = false;
       if (s_any(ahead < S_LOW) && ahead <= S_ROOM) {
-        q0 = __ldg(cb + min(f.nblk, bmax));
-        pend = 1u;
-        if (ahead < S_LOW2) {
-          q1 = __ldg(cb + min(f.nblk + 1u, bmax));
-          pend = 3u;
-        }
+        s_ldg_sector(cb, f.nblk, bmax, q0, q1);
+        pend = true;
+        if (RSB200_S_PREFETCH && prefetch)
+          s_prefetch_l2(cb + min(f.nblk + (uint32_t)RSB200_S_PREFETCH, bmax));
       }
       // 8 samples, straight line (component of sample k = k % G)
       uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
+#if RSB200_S_STRAIGHT
+      uint32_t nok = 0;
+      S_SYMF(0 % G, v0);
+      S_SYMF(1 % G, v1);
+      S_SYMF(2 % G, v2);
+      S_SYMF(3 % G, v3);
+      S_SYMF(4 % G, v4);
+      S_SYMF(5 % G, v5);
+      S_SYMF(6 % G, v6);
+      S_SYMF(7 % G, v7);
+      if (nok != 8u) { // rare: the symbols from the first miss on, one by one
+        if (nok <= 0u)
+          S_SYM(0 % G, v0);
+        if (nok <= 1u)
+          S_SYM(1 % G, v1);
+        if (nok <= 2u)
+          S_SYM(2 % G, v2);
+        if (nok <= 3u)
+          S_SYM(3 % G, v3);
+        if (nok <= 4u)
+          S_SYM(4 % G, v4);
+        if (nok <= 5u)
+          S_SYM(5 % G, v5);
+        if (nok <= 6u)
+          S_SYM(6 % G, v6);
+        S_SYM(7 % G, v7);
+      }
+#else
       S_SYM(0 % G, v0);
       S_SYM(1 % G, v1);
       S_SYM(2 % G, v2);
@@ -398,6 +513,7 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
       S_SYM(5 % G, v5);
       S_SYM(6 % G, v6);
       S_SYM(7 % G, v7);
+#endif
       const uint32_t o0 = __byte_perm(v0, v1, 0x5410), o1 = __byte_perm(v2, v3, 0x5410),
                      o2 = __byte_perm(v4, v5, 0x5410), o3 = __byte_perm(v6, v7, 0x5410);
       if (u == 0) { // the first MCU of the row predicts the first MCU of the next row
@@ -410,16 +526,23 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
         }
       }
       // ---- end of the unit: the requested blocks are unstuffed into the ring ----
-      if (pend & 1u) {
+      if (pend) {
         s_block(f, ringb, selb, einfo, q0, f.nblk, gbase, skew, limit);
-        f.nblk += 1u;
-      }
-      if (pend & 2u) {
-        s_block(f, ringb, selb, einfo, q1, f.nblk, gbase, skew, limit);
-        f.nblk += 1u;
+        s_block(f, ringb, selb, einfo, q1, f.nblk + 1u, gbase, skew, limit);
+        f.nblk += 2u;
       }
       const uint32_t s = u << 3;
-      if (s + 8 <= store_w) {
+      // two units = one 32-byte sector of the output row: the even unit waits in registers for the
+      // odd one and both leave with one 256-bit store (half the write requests; r2_run13: 256 frames
+      // 20.7 -> 18.3 ms, but 32 frames 5.27 -> 5.64 ms: the plan picks by launch size)
+      if (WIDE && wide && !(u & 1u) && s + 16u <= store_w) {
+        h0 = o0;
+        h1 = o1;
+        h2 = o2;
+        h3 = o3;
+      } else if (WIDE && wide && (u & 1u) && s + 8u <= store_w) {
+        stg_cs_v8(orow + 16ull * (u - 1u), h0, h1, h2, h3, o0, o1, o2, o3);
+      } else if (s + 8 <= store_w) {
         stg_cs_v4(orow + 16ull * u, make_uint4(o0, o1, o2, o3));
       } else if (s < store_w) {
         uint16_t* o16 = reinterpret_cast<uint16_t*>(orow) + s;
@@ -458,16 +581,19 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
   }
 }
 #undef S_SYM
+#undef S_SYMF
 
 #ifndef RSB200_S_LB
 #define RSB200_S_LB 6
 #endif
 // entry: one CTA of T_NT threads (the GPU kernel below; tests/emu replays it on the CPU)
+template <bool WIDE>
 __device__ __forceinline__ void
 stream_entry(StreamShared& sh, const uint8_t* __restrict__ in, uint64_t in_total,
              const DevScan* __restrict__ scans, const DevTable* __restrict__ tables, int ntab,
              uint8_t* __restrict__ out, DevResult* __restrict__ results,
-             const uint32_t* __restrict__ scan_ids, uint32_t nids, uint32_t* __restrict__ redo) {
+             const uint32_t* __restrict__ scan_ids, uint32_t nids, uint32_t* __restrict__ redo,
+             const bool prefetch) {
   const int tid = threadIdx.x;
   {
     const uint4* src = reinterpret_cast<const uint4*>(tables);
@@ -490,22 +616,23 @@ stream_entry(StreamShared& sh, const uint8_t* __restrict__ in, uint64_t in_total
   DevResult* res = results + scan_idx;
   const uint32_t G = scp->group;
   if (G == 1)
-    stream_body<1>(sh, scp, may_redo, in, in_total, out, res, redo ? redo + id : nullptr);
+    stream_body<1, WIDE>(sh, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
   else if (G == 2)
-    stream_body<2>(sh, scp, may_redo, in, in_total, out, res, redo ? redo + id : nullptr);
+    stream_body<2, WIDE>(sh, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
   else
-    stream_body<4>(sh, scp, may_redo, in, in_total, out, res, redo ? redo + id : nullptr);
+    stream_body<4, WIDE>(sh, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
 }
 
 #ifndef RSB200_EMU
+template <bool WIDE>
 __global__ void __launch_bounds__(T_NT, RSB200_S_LB)
     k2_stream_kernel(const uint8_t* __restrict__ in, uint64_t in_total, const DevScan* __restrict__ scans,
                      const DevTable* __restrict__ tables, int ntab, uint8_t* __restrict__ out,
                      DevResult* __restrict__ results, const uint32_t* __restrict__ scan_ids,
-                     uint32_t nids, uint32_t* __restrict__ redo) {
+                     uint32_t nids, uint32_t* __restrict__ redo, int prefetch) {
   extern __shared__ __align__(128) uint8_t s_smem_raw[];
   StreamShared& sh = *reinterpret_cast<StreamShared*>(s_smem_raw);
-  stream_entry(sh, in, in_total, scans, tables, ntab, out, results, scan_ids, nids, redo);
+  stream_entry<WIDE>(sh, in, in_total, scans, tables, ntab, out, results, scan_ids, nids, redo, prefetch != 0);
 }
 #endif
 

@@ -9,6 +9,7 @@
 #include "ljpeg_ranges.cuh"
 #include "ljpeg_thread.cuh"
 #include "ljpeg_stream.cuh"
+#include "hasselblad.cuh"
 #include "ljpeg_tile.cuh"
 #include "ljpeg_host.h"
 #include "rawforms.cuh"
@@ -37,6 +38,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -217,7 +219,7 @@ struct UnpackFastGroup {
 
 struct rsb200_plan {
   rsb200_ctx* ctx = nullptr;
-  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place), 8 DNG opcode list (in place), 9 bad-pixel interpolation (in place), 10 whole-image table lookup (in place)
+  int kind = 0; // 0 unpack, 1 ljpeg/cr2, 2 fixed-layout raw forms, 3 sRaw interpolation, 4 ARW2, 5 Panasonic, 6 Phase One, 7 black/white scaling (in place), 8 DNG opcode list (in place), 9 bad-pixel interpolation (in place), 10 whole-image table lookup (in place), 11 Hasselblad
   int nunits = 0;
   uint64_t in_bytes = 0, out_bytes = 0, pixels = 0;
   int launches_per_run = 0;
@@ -259,6 +261,15 @@ struct rsb200_plan {
   int badpix_njobs = 0;
   uint32_t badpix_total = 0;
   // Phase One (shares d_arw2_bad / h_arw2_bad as the per-job error flags)
+  // Hasselblad (K2H)
+  DevHassJob* d_hass_jobs = nullptr;
+  DevHassCta* d_hass_ctas = nullptr;
+  DevHassState* d_hass_states = nullptr;
+  DevHassState* h_hass_states = nullptr; // pinned
+  uint32_t* d_hass_seg_job = nullptr;
+  uint32_t* d_hass_u32 = nullptr;        // start | parsed | exit | count (nseg each) | cta_sum | cta_base | changed
+  uint32_t* d_hass_row_begin = nullptr;
+  uint32_t hass_nseg = 0, hass_ncta = 0, hass_rows = 0;
   P1StripDev* d_p1_strips = nullptr;
   P1JobDev* d_p1_jobs = nullptr;
   uint32_t p1_nstrips = 0;
@@ -981,6 +992,135 @@ extern "C" int rsb200_sraw_plan_create(rsb200_ctx* ctx, const rsb200_sraw_job* j
 }
 
 // ------------------------------------------------------------------
+// Hasselblad (K2H, hasselblad.cuh)
+// ------------------------------------------------------------------
+extern "C" int rsb200_hasselblad_plan_create(rsb200_ctx* ctx, const rsb200_huff_table* tables, int ntables,
+                                             const rsb200_hasselblad_job* jobs, int njobs,
+                                             rsb200_plan** out) {
+  if (!ctx || !tables || ntables <= 0 || !jobs || njobs <= 0 || !out)
+    return set_err(ctx, RSB200_ERR_ARG, "hasselblad_plan_create: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::vector<DevTable> ht((size_t)ntables);
+  for (int i = 0; i < ntables; ++i)
+    if (!build_dev_table(tables[i], ht[(size_t)i]))
+      return set_err(ctx, RSB200_ERR_ARG, "huffman table %d is malformed", i);
+  rsb200_plan* p = new (std::nothrow) rsb200_plan();
+  if (!p)
+    return RSB200_ERR_CUDA;
+  p->ctx = ctx;
+  p->kind = 11;
+  p->nunits = njobs;
+  std::vector<DevHassJob> dj((size_t)njobs);
+  std::vector<DevHassCta> ctas;
+  std::vector<uint32_t> seg_job, row_begin((size_t)njobs + 1, 0);
+  uint64_t nseg_total = 0, rows_total = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const rsb200_hasselblad_job& j = jobs[i];
+    // HasselbladDecompressor ctor (HasselbladDecompressor.cpp:39-58) + what the kernels need
+    const bool ok = j.width > 0 && j.height > 0 && j.width % 2 == 0 && j.width <= 12000 && j.height <= 8842 &&
+                    (j.in_offset % 4) == 0 && j.in_size < (1u << 28) && (j.out_offset % 4) == 0 &&
+                    (j.out_pitch % 4) == 0 && (uint64_t)j.width * 2 <= j.out_pitch && j.table < ntables;
+    if (!ok) {
+      delete p;
+      return set_err(ctx, RSB200_ERR_ARG, "hasselblad job %d: malformed descriptor", i);
+    }
+    DevHassJob& d = dj[(size_t)i];
+    memset(&d, 0, sizeof d);
+    d.in_offset = j.in_offset;
+    d.in_size = j.in_size;
+    d.w = j.width;
+    d.h = j.height;
+    d.out_pitch = j.out_pitch;
+    d.out_offset = j.out_offset;
+    d.init_pred = j.init_pred;
+    d.table = j.table;
+    d.seg_begin = (uint32_t)nseg_total;
+    // the pump may read (as zero) up to 12 bytes behind the buffer before it throws
+    d.nseg = (uint32_t)((((uint64_t)j.in_size + 24) * 8 + H_SEG_BITS - 1) / H_SEG_BITS);
+    d.cta_begin = (uint32_t)ctas.size();
+    for (uint32_t s0 = 0; s0 < d.nseg; s0 += H_NT)
+      ctas.push_back(DevHassCta{(uint32_t)i, s0});
+    seg_job.insert(seg_job.end(), d.nseg, (uint32_t)i);
+    nseg_total += d.nseg;
+    row_begin[(size_t)i] = (uint32_t)rows_total;
+    rows_total += j.height;
+    p->h_in_size.push_back(j.in_size);
+    p->in_bytes += j.in_size;
+    p->out_bytes += (uint64_t)j.width * j.height * 2;
+    p->pixels += (uint64_t)j.width * j.height;
+    p->need_in = std::max<uint64_t>(p->need_in, sat_add(j.in_offset, j.in_size));
+    p->need_out = std::max<uint64_t>(p->need_out, sat_add(j.out_offset, ((uint64_t)j.height - 1) * j.out_pitch +
+                                                                            (uint64_t)j.width * 2));
+  }
+  row_begin[(size_t)njobs] = (uint32_t)rows_total;
+  if (nseg_total >= 0x7FFFFFFFull || rows_total >= 0x7FFFFFFull) {
+    delete p;
+    return set_err(ctx, RSB200_ERR_ARG, "hasselblad plan: too large");
+  }
+  p->hass_nseg = (uint32_t)nseg_total;
+  p->hass_ncta = (uint32_t)ctas.size();
+  p->hass_rows = (uint32_t)rows_total;
+  p->ntables = ntables;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** dptr, const void* src, size_t bytes) {
+    if (e != cudaSuccess)
+      return;
+    e = rsb_dev_alloc(dptr, bytes ? bytes : 16);
+    if (e == cudaSuccess && bytes)
+      e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+  };
+  up((void**)&p->d_tables, ht.data(), sizeof(DevTable) * ht.size());
+  up((void**)&p->d_hass_jobs, dj.data(), sizeof(DevHassJob) * dj.size());
+  up((void**)&p->d_hass_ctas, ctas.data(), sizeof(DevHassCta) * ctas.size());
+  up((void**)&p->d_hass_seg_job, seg_job.data(), sizeof(uint32_t) * seg_job.size());
+  up((void**)&p->d_hass_row_begin, row_begin.data(), sizeof(uint32_t) * row_begin.size());
+  if (e == cudaSuccess)
+    e = rsb_dev_alloc((void**)&p->d_hass_u32,
+                      sizeof(uint32_t) * (4ull * nseg_total + 2ull * ctas.size() + H_ROUNDS + 8));
+  if (e == cudaSuccess)
+    e = rsb_dev_alloc((void**)&p->d_hass_states, sizeof(DevHassState) * (size_t)njobs);
+  if (e == cudaSuccess)
+    e = rsb_host_alloc((void**)&p->h_hass_states, sizeof(DevHassState) * (size_t)njobs);
+  if (e != cudaSuccess) {
+    rsb200_plan_destroy(p);
+    return set_err(ctx, RSB200_ERR_CUDA, "hasselblad plan allocation failed: %s", cudaGetErrorString(e));
+  }
+  p->launches_per_run = 1 + 2 * H_ROUNDS + 1 + 2 + 1 + 1;
+  *out = p;
+  return RSB200_OK;
+}
+
+static cudaError_t run_hasselblad(const rsb200_plan* p, const uint8_t* in, uint8_t* outp, cudaStream_t st) {
+  const uint32_t n = p->hass_nseg, nc = p->hass_ncta;
+  uint32_t* start = p->d_hass_u32;
+  uint32_t* parsed = start + n;
+  uint32_t* exitp = parsed + n;
+  uint32_t* count = exitp + n;
+  uint32_t* cta_sum = count + n;
+  uint32_t* cta_base = cta_sum + nc;
+  uint32_t* changed = cta_base + nc;
+  const size_t smem = sizeof(HassShared);
+  const uint32_t nb = (std::max<uint32_t>(std::max<uint32_t>(n, (uint32_t)p->nunits), H_ROUNDS + 1) + 255) / 256;
+  hass_init_kernel<<<nb, 256, 0, st>>>(p->d_hass_jobs, p->nunits, n, p->d_hass_seg_job, start, parsed,
+                                       p->d_hass_states, changed);
+  for (int r = 0; r < H_ROUNDS; ++r) {
+    hass_parse_kernel<<<nc, H_NT, smem, st>>>(in, p->d_hass_jobs, p->d_tables, p->d_hass_ctas, start, parsed,
+                                              exitp, count);
+    hass_link_kernel<<<(n + 255) / 256, 256, 0, st>>>(p->d_hass_jobs, p->nunits, n, p->d_hass_seg_job, start,
+                                                      exitp, changed + r);
+  }
+  hass_serial_kernel<<<p->nunits, 32, 0, st>>>(in, p->d_hass_jobs, p->d_tables, start, parsed, exitp, count,
+                                               changed + (H_ROUNDS - 1));
+  hass_ctasum_kernel<<<nc, H_NT, smem, st>>>(p->d_hass_jobs, p->d_hass_ctas, count, cta_sum);
+  hass_ctascan_kernel<<<(p->nunits + 63) / 64, 64, 0, st>>>(p->d_hass_jobs, p->nunits, cta_sum, cta_base);
+  hass_decode_kernel<<<nc, H_NT, smem, st>>>(in, p->d_hass_jobs, p->d_tables, p->d_hass_ctas, start, exitp,
+                                             count, cta_base, outp, p->d_hass_states);
+  hass_rows_kernel<<<(p->hass_rows * 32 + 255) / 256, 256, 0, st>>>(p->d_hass_jobs, p->nunits,
+                                                                   p->d_hass_row_begin, outp);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------
 // Phase One (K8)
 // ------------------------------------------------------------------
 extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseone_job* jobs,
@@ -1440,8 +1580,11 @@ constexpr uint32_t BIG_SEGMENT_BYTES = 256u << 10; // above this a segment gets 
 // Segments the one-thread-per-segment kernel handles: plain LJPEG tiles whose rows
 // are whole 8-sample units written with aligned 128-bit stores.
 #ifndef RSB200_STREAM_DEFAULT
-#define RSB200_STREAM_DEFAULT 0
+#define RSB200_STREAM_DEFAULT 1
 #endif
+// k2_stream_kernel: an L2 prefetch ahead of every sector pays while the launch is latency bound
+// (r2_run12: 32 frames 6.67 -> 5.81 ms) and costs once the machine is full (128 frames 10.8 -> 11.9 ms)
+constexpr int K2S_PREFETCH_MAX = 56832; // half a wave of 148 SMs x 6 CTAs x 128 threads
 constexpr size_t K2T_MIN_SEGMENTS = 16384; // measured crossover on B200: ~22 frames of 726 tiles
 static bool thread_eligible(const DevScan& d) {
   return d.kind == 0 && d.pump == 0 && d.mcu_h == 1 &&
@@ -1563,12 +1706,15 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
   p->nsmall = (int)small_ids.size();
   p->ntile = (int)tile_ids.size();
   // host-buffer runs of a plan made of tile-kernel segments only are pipelined: groups of
-  // consecutive segments worth ~8 MB of output each (32 MB in plans of more than 1 GB)
+  // consecutive segments worth ~16 MB of output each (32 MB in plans of more than 1 GB; measured,
+  // r2_run11: one frame 2.95 ms with 8 MB groups, 2.68 ms with 16 MB -- a download costs ~40 us + 23 us/MB)
   auto build_groups = [&](const std::vector<uint32_t>& ids) {
     uint64_t total = 0;
     for (uint32_t i : ids)
       total += (uint64_t)b.scans[i].rows * b.scans[i].store_w * 2;
-    const uint64_t kGroupOut = total > (1ull << 30) ? (32ull << 20) : (8ull << 20);
+    uint64_t kGroupOut = total > (1ull << 30) ? (32ull << 20) : (16ull << 20);
+    if (const char* e = getenv("RSB200_GROUP_MB"))
+      kGroupOut = (uint64_t)std::max(1, atoi(e)) << 20;
     rsb200_plan::TileGroup g{0, 0, ~0ull, 0, ~0ull, 0};
     uint64_t acc = 0;
     for (size_t k = 0; k < ids.size(); ++k) {
@@ -2130,6 +2276,9 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches++;
     }
+  } else if (p->kind == 11) {
+    CUDA_TRY(ctx, run_hasselblad(p, in, outp, st));
+    ctx->launches += (uint64_t)p->launches_per_run;
   } else if (p->kind == 6) {
     CUDA_TRY(ctx, run_phaseone(p, in, outp, st));
     ctx->launches++;
@@ -2175,9 +2324,16 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       ctx->launches += 1;
     }
     if (p->nthread && p->use_stream) {
-      k2_stream_kernel<<<(p->nthread + T_NT - 1) / T_NT, T_NT, stream_smem_bytes(p->ntables), st>>>(
-          in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->ntables, outp, p->d_results,
-          p->d_thread_ids, (uint32_t)p->nthread, p->d_redo);
+      // small launches are latency bound (L2 prefetch ahead, 128-bit stores), full ones are bound
+      // by the number of memory requests (no prefetch, 256-bit stores)
+      if (p->nthread <= K2S_PREFETCH_MAX)
+        k2_stream_kernel<false><<<(p->nthread + T_NT - 1) / T_NT, T_NT, stream_smem_bytes(p->ntables), st>>>(
+            in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->ntables, outp, p->d_results,
+            p->d_thread_ids, (uint32_t)p->nthread, p->d_redo, 1);
+      else
+        k2_stream_kernel<true><<<(p->nthread + T_NT - 1) / T_NT, T_NT, stream_smem_bytes(p->ntables), st>>>(
+            in, (uint64_t)in_bytes, p->d_scans, p->d_tables, p->ntables, outp, p->d_results,
+            p->d_thread_ids, (uint32_t)p->nthread, p->d_redo, 0);
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 1;
     } else if (p->nthread) {
@@ -2412,6 +2568,24 @@ static int run_host_tile_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_
     }
   }
   const bool rows2d = pitch && row_bytes && row_bytes < pitch;
+  // RSB200_PIPE_TRACE=1: a timeline of the groups on stderr (timed events after every upload,
+  // kernel and download; debugging aid for the pipeline itself, slows the run down a little)
+  const bool trace = getenv("RSB200_PIPE_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t s) {
+    if (!trace)
+      return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    tev.push_back(e);
+  };
+  if (trace) {
+    for (int i = 0; i < N_PIPE; ++i)
+      cudaStreamSynchronize(ctx->pipe[i]);
+    mark(ctx->pipe[0]);
+  }
+  const auto trace_t0 = std::chrono::steady_clock::now();
   for (size_t gi = 0; gi < p->tile_groups.size(); ++gi) {
     const rsb200_plan::TileGroup& g = p->tile_groups[gi];
     cudaStream_t st = ctx->pipe[gi % N_PIPE];
@@ -2425,8 +2599,10 @@ static int run_host_tile_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_
       }
       CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in + g.in_lo, src, i1c - g.in_lo, cudaMemcpyHostToDevice, st));
     }
+    mark(st);
     CUDA_TRY(ctx, launch_tile_range(p, ctx->d_in, (uint64_t)in_bytes, ctx->d_out, g.first, g.count, st));
     ctx->launches++;
+    mark(st);
     if (o1 > g.out_lo) {
       uint8_t* dst = (stage_out ? ctx->h_out : out) + g.out_lo;
       if (rows2d && !stage_out) {
@@ -2440,7 +2616,10 @@ static int run_host_tile_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_
       if (stage_out)
         CUDA_TRY(ctx, cudaEventRecord(ctx->stage_events[gi], st));
     }
+    mark(st);
   }
+  const double trace_submit_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - trace_t0).count();
   if (stage_out) {
     // copy every group out of the staging as soon as its download has landed
     for (size_t gi = 0; gi < p->tile_groups.size(); ++gi) {
@@ -2461,6 +2640,22 @@ static int run_host_tile_pipelined(rsb200_plan* p, const uint8_t* in, size_t in_
   }
   for (int i = 0; i < N_PIPE; ++i)
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+  if (trace) {
+    const double total_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - trace_t0).count();
+    fprintf(stderr, "PIPE_TRACE groups %zu submit %.3f ms total %.3f ms (group: upload done, kernel done, download done; ms)\n",
+            p->tile_groups.size(), trace_submit_ms, total_ms);
+    for (size_t gi = 0; gi < p->tile_groups.size() && 3 * gi + 3 < tev.size(); ++gi) {
+      float a = 0, b = 0, c = 0;
+      cudaEventElapsedTime(&a, tev[0], tev[3 * gi + 1]);
+      cudaEventElapsedTime(&b, tev[0], tev[3 * gi + 2]);
+      cudaEventElapsedTime(&c, tev[0], tev[3 * gi + 3]);
+      if (gi < 16 || gi + 4 > p->tile_groups.size())
+        fprintf(stderr, "PIPE_TRACE %3zu  %8.3f %8.3f %8.3f\n", gi, a, b, c);
+    }
+    for (cudaEvent_t e : tev)
+      cudaEventDestroy(e);
+  }
   p->last_stream = ctx->pipe[0];
   p->ran = true;
   return RSB200_OK;
@@ -2480,7 +2675,7 @@ extern "C" int rsb200_plan_run_host(rsb200_plan* p, const uint8_t* in, size_t in
     return rc;
   if (in_bytes < p->need_in || out_bytes < p->need_out)
     return set_err(ctx, RSB200_ERR_ARG, "plan_run_host: buffers too small");
-  if (p->kind >= 7)
+  if (p->kind >= 7 && p->kind <= 10)
     partial = 1; // in-place plans work on the image the caller holds: it always goes up first
   if (!partial && unpack_pipeline_ok(p))
     return run_host_unpack_pipelined(p, in, in_bytes, out, out_bytes);
@@ -2530,7 +2725,7 @@ extern "C" int rsb200_plan_run_host_image(rsb200_plan* p, const uint8_t* in, siz
   rsb200_ctx* ctx = p->ctx;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   const size_t out_bytes = (size_t)pitch * rows;
-  if (p->kind >= 7)
+  if (p->kind >= 7 && p->kind <= 10)
     partial = 1; // in-place plans: the image always goes up first
   int rc = ensure_cap(ctx, &ctx->d_in, &ctx->d_in_cap, in_bytes + 16);
   if (rc)
@@ -2761,7 +2956,7 @@ extern "C" int rsb200_plan_run_gather(rsb200_plan* p, rsb200_comm* c, const void
   // the transfers start behind whatever the caller queued on `stream` so far
   CUDA_TRY(ctx, cudaEventRecord(c->done, st));
   CUDA_TRY(ctx, cudaStreamWaitEvent(c->stream, c->done, 0));
-  if (p->kind == 1 && !p->tile_groups.empty()) {
+  if (p->kind == 1 && !p->tile_groups.empty() && !p->host_tiles_only) {
     if (in_bytes < p->need_in)
       return set_err(ctx, RSB200_ERR_ARG, "plan_run_gather: input too small");
     while (c->events.size() < p->tile_groups.size()) {
@@ -2825,6 +3020,30 @@ extern "C" int rsb200_plan_results(rsb200_plan* p, rsb200_scan_result* results, 
                                   "ARW2 invariant failed, same pixel is both min and max"
                                 : "Too many errors encountered. Giving up. First Error:\n"
                                   "a Phase One row cannot be decoded (lengths / bit stream)");
+      }
+    }
+    return first;
+  }
+  if (p->kind == 11) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(p->h_hass_states, p->d_hass_states, sizeof(DevHassState) * (size_t)p->nunits,
+                                  cudaMemcpyDeviceToHost, p->last_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(p->last_stream));
+    int first = RSB200_OK;
+    for (int i = 0; i < p->nunits; ++i) {
+      const DevHassState& hs = p->h_hass_states[i];
+      // the first failure in stream order decides (a refill is checked before the code it feeds)
+      // (a stream shorter than one chunk: the BitStreamerMSB32 constructor throws, BitStreamer.h:60-64)
+      const int status = (p->h_in_size[(size_t)i] < 4 || (hs.key_ioe != H_NOKEY && hs.key_ioe <= hs.key_bad))
+                             ? RSB200_ERR_IOE
+                             : (hs.key_bad != H_NOKEY ? RSB200_ERR_RDE : RSB200_OK);
+      if (results && i < n) {
+        results[i].status = (uint32_t)status;
+        results[i].consumed = status == RSB200_OK ? hs.consumed : 0u;
+      }
+      if (status != RSB200_OK && first == RSB200_OK) {
+        first = status;
+        set_err(ctx, first, status == RSB200_ERR_RDE ? "job %d: bad Huffman code"
+                                                     : "job %d: Buffer overflow read in BitStreamer", i);
       }
     }
     return first;
@@ -2925,6 +3144,27 @@ extern "C" int rsb200_plan_launches(const rsb200_plan* p) {
   return p ? p->launches_per_run : 0;
 }
 
+extern "C" const char* rsb200_plan_kernels(const rsb200_plan* p) {
+  if (!p)
+    return "";
+  if (p->kind != 1)
+    return "(not an LJPEG plan)";
+  const bool only_thread = p->nthread && !p->ntile && !p->nsmall && !p->nbig;
+  const bool only_tile = p->ntile && !p->nthread && !p->nsmall && !p->nbig;
+  if (only_thread && p->use_stream)
+    return p->nthread_redo ? "k2_stream_kernel (one thread per segment, unstuffing in the thread) + "
+                             "k2_tile_kernel<1> for flagged ends of stream"
+                           : "k2_stream_kernel (one thread per segment, unstuffing in the thread)";
+  if (only_thread)
+    return p->clean2 ? "k2_clean2_kernel + k2_thread_kernel (one thread per segment)"
+                     : "k2_clean_kernel + k2_thread_kernel (one thread per segment)";
+  if (only_tile)
+    return p->tile_r == 2 ? "k2_tile_kernel<2> (one CTA per tile)" : "k2_tile_kernel<1> (one CTA per tile)";
+  if (p->nsmall && !p->nthread && !p->ntile && !p->nbig)
+    return "k2_fused_kernel (one CTA per segment)";
+  return "mixed (k2_fused / k2_tile / thread path / multi-CTA ranges + K3)";
+}
+
 extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   if (!p)
     return;
@@ -2953,6 +3193,13 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   rsb_dev_free(p->d_dngop_ops);
   rsb_dev_free(p->d_dngop_tables);
   rsb_dev_free(p->d_dngop_deltas);
+  rsb_dev_free(p->d_hass_jobs);
+  rsb_dev_free(p->d_hass_ctas);
+  rsb_dev_free(p->d_hass_states);
+  rsb_host_free(p->h_hass_states);
+  rsb_dev_free(p->d_hass_seg_job);
+  rsb_dev_free(p->d_hass_u32);
+  rsb_dev_free(p->d_hass_row_begin);
   rsb_dev_free(p->d_p1_strips);
   rsb_dev_free(p->d_p1_jobs);
   rsb_dev_free(p->d_nikon_luts);

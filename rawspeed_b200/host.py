@@ -33,7 +33,7 @@ EXPORTS = ["rsb200h_unpack", "rsb200h_ljpeg_decompress", "rsb200h_ljpeg_decode",
            "rsb200h_panasonic", "rsb200h_phaseone", "rsb200h_scale_black_white",
            "rsb200h_panasonic_v4", "rsb200h_dng_opcodes", "rsb200h_dngop_lower",
            "rsb200h_fix_bad_pixels", "rsb200h_sixteen_bit_lookup",
-           "rsb200h_dng_ljpeg_host_half", "rsb200h_last_call_ms"]
+           "rsb200h_dng_ljpeg_host_half", "rsb200h_last_call_ms", "rsb200h_hasselblad_ljpeg_decode"]
 
 _lib = None
 
@@ -138,6 +138,19 @@ def dng_decompress(file_bytes, tile_off, tile_len, img, w, cpp, tile_w, tile_h, 
                                          img.shape[1] * img.itemsize, tile_w, tile_h,
                                          compression, int(fix_ljpeg), bps, int(big_endian),
                                          C.byref(e)))
+    return img
+
+
+def hasselblad_ljpeg_decode(data, img, w):
+    """HasselbladLJpegDecoder(data, img).decode() of the C++ host mirror into img (uint16, pitch =
+    img.shape[1] * 2)."""
+    p, n = _u8(data)
+    e = _Err()
+    L = lib()
+    L.rsb200h_hasselblad_ljpeg_decode.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                  C.c_void_p]
+    e.check(L.rsb200h_hasselblad_ljpeg_decode(p, C.c_uint32(n), C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                              img.shape[1] * 2, C.byref(e)))
     return img
 
 

@@ -5,6 +5,10 @@
 // is no GPU; parity of the real kernel is the GPU tests' job.
 #include "cuda_emu.h"
 
+#ifndef RSB200_EMU_WIDE
+#define RSB200_EMU_WIDE false
+#endif
+
 #include "../../rawspeed_b200/csrc/ljpeg_stream.cuh"
 #include "../../rawspeed_b200/csrc/ljpeg_host.h"
 
@@ -44,8 +48,8 @@ extern "C" int stream_emu_run(const uint8_t* in, uint64_t in_total, const rsb200
   for (unsigned b = 0; b < nblocks; ++b)
     cuemu::run_cta(b, nblocks, T_NT, sizeof(StreamShared), reverse != 0, [&](uint8_t* smem) {
       StreamShared& sh = *reinterpret_cast<StreamShared*>(smem);
-      stream_entry(sh, base, in_total, ds.data(), ht.data(), ntables, out, res.data(), ids.data(),
-                   (uint32_t)nscans, redo.data());
+      stream_entry<RSB200_EMU_WIDE>(sh, base, in_total, ds.data(), ht.data(), ntables, out, res.data(), ids.data(),
+                   (uint32_t)nscans, redo.data(), (any_mode & 1) != 0);
     });
   for (int i = 0; i < nscans; ++i) {
     results[i].status = res[(size_t)i].status;

@@ -27,13 +27,16 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h")] + [
     os.path.join(CSRC, f) for f in ("ljpeg_stream.cuh", "ljpeg_lane.cuh", "ljpeg_host.h", "ljpeg_types.h")]
 
 
-@pytest.fixture(scope="module")
-def emu():
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
-        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+@pytest.fixture(scope="module", params=["default", "st256"])
+def emu(request):
+    """Both instantiations of the kernel: 128-bit output stores, and 256-bit ones (two units per store)."""
+    out = OUT if request.param == "default" else OUT.replace(".so", "_st256.so")
+    flags = [] if request.param == "default" else ["-DRSB200_EMU_WIDE=true"]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
-                               "-Wno-unused-function", "-fPIC", "-shared", "-o", OUT, SRC])
-    lib = C.CDLL(OUT)
+                               "-Wno-unused-function", "-fPIC", "-shared"] + flags + ["-o", out, SRC])
+    lib = C.CDLL(out)
     lib.stream_emu_run.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return lib
