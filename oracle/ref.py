@@ -215,6 +215,19 @@ def nikon_decompress(img, w, meta, meta_be, bits, data, uncorrected=False, reps=
     return ms.value
 
 
+def hasselblad_ljpeg_decode(blob, img, w):
+    """Reference HasselbladLJpegDecoder(blob, img).decode() (ref_hasselblad_ljpeg_decode)."""
+    p, n = _u8(blob)
+    e = Err()
+    L = lib()
+    L.ref_hasselblad_ljpeg_decode.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p]
+    rc = L.ref_hasselblad_ljpeg_decode(p, C.c_uint32(n), C.c_void_p(img.ctypes.data), w, img.shape[0],
+                                       img.shape[1] * 2, C.byref(e))
+    e.check(rc)
+    return img
+
+
 def hasselblad_decompress(img, w, ncpl, values, full, init_pred, data):
     """Reference HasselbladDecompressor (ref_hasselblad_decompress); returns the stream position."""
     p, n = _u8(data)

@@ -45,6 +45,7 @@
 #include "decompressors/SonyArw2Decompressor.h"
 #include "decompressors/NikonDecompressor.h"
 #include "decompressors/HasselbladDecompressor.h"
+#include "decompressors/HasselbladLJpegDecoder.h"
 #include "decompressors/PhaseOneDecompressor.h"
 #include "decompressors/PanasonicV4Decompressor.h"
 #include "decompressors/PanasonicV5Decompressor.h"
@@ -345,6 +346,19 @@ int ref_hasselblad_decompress(uint16_t* img_data, int w, int h, int pitch, const
     }
     if (best_ms)
       *best_ms = best;
+    copyOut(img, img_data, pitch);
+  });
+}
+
+// HasselbladLJpegDecoder(bs, img).decode(): the LJPEG container (SOI, DHT, SOF3, SOS, pair stream,
+// EOI) around HasselbladDecompressor.
+int ref_hasselblad_ljpeg_decode(const uint8_t* in, uint32_t in_size, uint16_t* img_data, int w, int h,
+                                int pitch, RefErr* e) {
+  return guarded(e, [&] {
+    RawImage img = makeImage(w, h, 1, true, 1, 1);
+    copyIn(img, img_data, pitch);
+    HasselbladLJpegDecoder d(ByteStream(DataBuffer(Buffer(in, in_size), Endianness::big)), img);
+    d.decode();
     copyOut(img, img_data, pitch);
   });
 }

@@ -421,6 +421,23 @@ def make_hasselblad_fast(img, ht, init_pred):
     return np.frombuffer(words.tobytes() + bytes(16), dtype=np.uint8).copy()
 
 
+def hasselblad_ljpeg_container(w, h, data, ncpl, values, prec=16, predictor=1, frame_w=None, frame_h=None,
+                               dri=None):
+    """The LJPEG container HasselbladLJpegDecoder reads (HasselbladLJpegDecoder.cpp:50-77,
+    AbstractLJpegDecoder.cpp:65-230): SOI, DHT (class 0, id 0), SOF3 (one component), [DRI], SOS, the
+    pair stream as it is (no byte stuffing in this format), EOI."""
+    def seg(marker, payload):
+        return bytes([0xFF, marker]) + (len(payload) + 2).to_bytes(2, "big") + payload
+    fw, fh = frame_w or w, frame_h or h
+    dht = bytes([0x00]) + bytes(ncpl) + bytes(values)
+    sof = bytes([prec]) + fh.to_bytes(2, "big") + fw.to_bytes(2, "big") + bytes([1, 1, 0x11, 0])
+    sos = bytes([1, 1, 0x00, predictor, 0, 0])
+    out = b"\xFF\xD8" + seg(0xC4, dht) + seg(0xC3, sof)
+    if dri is not None:
+        out += seg(0xDD, int(dri).to_bytes(2, "big"))
+    return np.frombuffer(out + seg(0xDA, sos) + bytes(data) + b"\xFF\xD9", dtype=np.uint8).copy()
+
+
 def _canonical(ncpl, values):
     """value -> (code, length) by T.81 C.1/C.2 (the first occurrence of a value wins)."""
     out, code, k = {}, 0, 0

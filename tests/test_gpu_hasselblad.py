@@ -6,6 +6,7 @@ import pytest
 import torch
 
 import rawspeed_b200 as rs
+from rawspeed_b200 import host
 from oracle import port, synth
 
 pytestmark = pytest.mark.gpu
@@ -118,3 +119,25 @@ def test_hasselblad_rejects_malformed_jobs(ctx):
         kw.update(bad)
         with pytest.raises(Exception):
             rs.hasselblad_plan(ctx, [tab], [_job(**kw)])
+
+
+def test_hasselblad_ljpeg_decoder_of_the_host_mirror(ctx):
+    """rawspeed_b200::HasselbladLJpegDecoder(bs, img).decode(): container walk on the host, pair
+    stream on the device; the container is pinned against the reference's own decoder in
+    tests/test_oracle_hasselblad.py."""
+    w, h = 1024, 96
+    img = synth.image_model(w, h, seed=3)
+    ht = port.Huff(NCPL, VALS, full=False)
+    data = synth.make_hasselblad_fast(img, ht, 0x8000)
+    o = port.new_image(w, h)
+    host.hasselblad_ljpeg_decode(synth.hasselblad_ljpeg_container(w, h, data, NCPL, VALS), o, w)
+    assert np.array_equal(o[:, :w], img)
+    with pytest.raises(host.RawDecoderException):      # frame does not match the image
+        host.hasselblad_ljpeg_decode(synth.hasselblad_ljpeg_container(w, h, data, NCPL, VALS, frame_w=w + 2),
+                                     port.new_image(w, h), w)
+    with pytest.raises(host.RawDecoderException):      # restart interval
+        host.hasselblad_ljpeg_decode(synth.hasselblad_ljpeg_container(w, h, data, NCPL, VALS, dri=4),
+                                     port.new_image(w, h), w)
+    with pytest.raises(host.IOException):              # the stream ends early
+        host.hasselblad_ljpeg_decode(synth.hasselblad_ljpeg_container(w, h, data[:len(data) // 2], NCPL, VALS),
+                                     port.new_image(w, h), w)

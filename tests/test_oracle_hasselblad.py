@@ -65,3 +65,21 @@ def test_hasselblad_error_classes():
                                                        data[:40])):
         with pytest.raises(port.IOException):          # stream ends early
             f()
+
+
+def test_hasselblad_ljpeg_container_through_the_reference():
+    """The container tests/test_gpu_hasselblad.py feeds the host mirror is what the reference's own
+    HasselbladLJpegDecoder accepts, and its error classes for the two checks of decodeScan()."""
+    w, h = 130, 21
+    img = synth.image_model(w, h, seed=3)
+    ht = port.Huff(NCPL, VALS, full=False)
+    data = synth.make_hasselblad(img, ht, 0x8000)
+    o = port.new_image(w, h)
+    oracle.ref.hasselblad_ljpeg_decode(synth.hasselblad_ljpeg_container(w, h, data, NCPL, VALS), o, w)
+    assert np.array_equal(o[:, :w], img)
+    with pytest.raises(port.RawDecoderException):      # frame does not match the image
+        oracle.ref.hasselblad_ljpeg_decode(
+            synth.hasselblad_ljpeg_container(w, h, data, NCPL, VALS, frame_w=w + 2), port.new_image(w, h), w)
+    with pytest.raises(port.RawDecoderException):      # restart interval
+        oracle.ref.hasselblad_ljpeg_decode(
+            synth.hasselblad_ljpeg_container(w, h, data, NCPL, VALS, dri=4), port.new_image(w, h), w)
