@@ -43,15 +43,28 @@ constexpr uint32_t S_ROOM = 88;  // a lane at or below this takes part: two bloc
 // idx*4 of the 4 "remove" flags (bits 7, 15, 23, 31) in bits 2..5 of the high product word
 constexpr uint32_t S_IDXMUL = (1u << 27) | (1u << 20) | (1u << 13) | (1u << 6);
 
+#ifndef RSB200_S_LUT32
+#define RSB200_S_LUT32 0 // 32-bit LUT entries laid out for IMAD.HI field extraction (A/B)
+#endif
+
 struct StreamShared {
   uint32_t sel[16];            // [remove flags of a word] -> PRMT selector | 8 * kept bytes << 16
   uint32_t endinfo[2][T_NT];   // per thread: block where the data ended, clean bytes before that block
   uint32_t ring[T_RING][T_NT]; // word w of a stream at ring[w % T_RING][thread]
   DevTable tab[T_MAXTAB];
+  // (RSB200_S_LUT32: behind the tables in use, uint32_t lut32[ntab][1 << LUT_BITS])
 };
 
 __host__ __device__ inline size_t stream_smem_bytes(int ntab) {
-  return sizeof(uint32_t) * (16 + 2 * T_NT + T_RING * T_NT) + sizeof(DevTable) * (size_t)ntab;
+  return sizeof(uint32_t) * (16 + 2 * T_NT + T_RING * T_NT) + sizeof(DevTable) * (size_t)ntab +
+         (RSB200_S_LUT32 ? sizeof(uint32_t) * (size_t)ntab * (1u << LUT_BITS) : 0);
+}
+// LUT entry for the straight-line decode: [4:0] code length, [12:8] SSSS, bit 16 = 1 (a hit; eight
+// of them add up in a counter without touching the other fields' sums), [31:26] bits of code +
+// mantissa.  The fields a symbol needs come out with IMAD.HI (FMA pipe): e >> 8 as a shift amount
+// (SHF takes it modulo 32), p + (e >> 26).
+__host__ __device__ inline uint32_t s_lut32_entry(uint32_t e16) {
+  return e16 ? ((e16 & 31u) | (((e16 >> 5) & 31u) << 8) | (1u << 16) | ((e16 >> 10) << 26)) : 0u;
 }
 
 // entry of the selector table for remove-mask m (bit i = byte i of the little-endian word, i.e.
@@ -343,6 +356,31 @@ __device__ __forceinline__ bool s_any(bool want) { return __any_sync(__activemas
     val = pred[c];                                                              \
   } while (0)
 
+#if RSB200_S_LUT32
+#undef S_SYMF
+#define S_SYMF(c, val)                                                          \
+  do {                                                                          \
+    const uint32_t x_ = __funnelshift_l(nxt, cur, p);                           \
+    const uint32_t e_ = lds_u32<0>(                                             \
+        mad_hi(x_ & ~((1u << (32 - LUT_BITS)) - 1u), 1u << (LUT_BITS + 2), lut32b[c])); \
+    nok += e_; /* hits in bits 19:16 */                                         \
+    const uint32_t tt_ = __funnelshift_l(0u, x_, e_);                           \
+    const uint32_t f_ = (uint32_t)((int32_t)~tt_ >> 31);                        \
+    const uint32_t d_ = __funnelshift_l(tt_, f_, mad_hi(e_, 1u << 24, 0u)) - f_; \
+    const uint32_t pn_ = mad_hi(e_, 1u << 6, p);                                \
+    last_tl = pn_ - p;                                                          \
+    if ((pn_ ^ p) & 32u) {                                                      \
+      cur = nxt;                                                                \
+      nxt = nn;                                                                 \
+      nn = lds_u32<0>(ringb + (wv & T_RMASK));                                  \
+      wv += T_WSTRIDE;                                                          \
+    }                                                                           \
+    p = pn_;                                                                    \
+    pred[c] += d_;                                                              \
+    val = pred[c];                                                              \
+  } while (0)
+#endif
+
 #ifndef RSB200_S_STRAIGHT
 #define RSB200_S_STRAIGHT 1
 #endif
@@ -398,7 +436,7 @@ __device__ __forceinline__ void s_ldg_sector(const uint4* cb, uint32_t blk, uint
 
 template <int G, bool WIDE>
 __device__ __forceinline__ void
-stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_redo, const bool prefetch,
+stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp, const bool may_redo, const bool prefetch,
             const uint8_t* __restrict__ in, uint64_t in_total, uint8_t* __restrict__ out,
             DevResult* __restrict__ res, uint32_t* __restrict__ redo) {
   // raw offsets count from the 32-byte boundary at or before the segment's first byte
@@ -413,6 +451,9 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
   const uint32_t bmax = (nreadable > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)nreadable) - 1u;
   const uint32_t ringb = smem_u32(&sh.ring[0][threadIdx.x]);
   const uint32_t selb = smem_u32(sh.sel);
+#if RSB200_S_LUT32
+  const uint32_t* lut32 = reinterpret_cast<const uint32_t*>(&sh.tab[ntab_sh]);
+#endif
   const uint32_t einfo = smem_u32(&sh.endinfo[0][threadIdx.x]);
 
   SFill f;
@@ -431,12 +472,18 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
   uint32_t wv = 3u * T_WSTRIDE, p = 0; // wv: ring byte offset of the next word to fetch (unwrapped)
 
   uint32_t lutb[G];
+#if RSB200_S_LUT32
+  uint32_t lut32b[G];
+#endif
   const DevTable* tabp[G];
   uint32_t rowstart[G], pred[G];
 #pragma unroll
   for (int c = 0; c < G; ++c) {
     tabp[c] = &sh.tab[scp->table_idx[scp->table_of[c]]];
     lutb[c] = smem_u32(tabp[c]->lut);
+#if RSB200_S_LUT32
+    lut32b[c] = smem_u32(lut32 + (size_t)scp->table_idx[scp->table_of[c]] * (1u << LUT_BITS));
+#endif
     rowstart[c] = scp->init_pred[c];
   }
   const uint32_t rows = scp->rows;
@@ -479,6 +526,11 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
       uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
 #if RSB200_S_STRAIGHT
       uint32_t nok = 0;
+#if RSB200_S_LUT32
+#define S_NOK ((nok >> 16) & 15u)
+#else
+#define S_NOK nok
+#endif
       S_SYMF(0 % G, v0);
       S_SYMF(1 % G, v1);
       S_SYMF(2 % G, v2);
@@ -487,23 +539,25 @@ stream_body(StreamShared& sh, const DevScan* __restrict__ scp, const bool may_re
       S_SYMF(5 % G, v5);
       S_SYMF(6 % G, v6);
       S_SYMF(7 % G, v7);
-      if (nok != 8u) { // rare: the symbols from the first miss on, one by one
-        if (nok <= 0u)
+      if (S_NOK != 8u) { // rare: the symbols from the first miss on, one by one
+        const uint32_t k_ = S_NOK;
+        if (k_ <= 0u)
           S_SYM(0 % G, v0);
-        if (nok <= 1u)
+        if (k_ <= 1u)
           S_SYM(1 % G, v1);
-        if (nok <= 2u)
+        if (k_ <= 2u)
           S_SYM(2 % G, v2);
-        if (nok <= 3u)
+        if (k_ <= 3u)
           S_SYM(3 % G, v3);
-        if (nok <= 4u)
+        if (k_ <= 4u)
           S_SYM(4 % G, v4);
-        if (nok <= 5u)
+        if (k_ <= 5u)
           S_SYM(5 % G, v5);
-        if (nok <= 6u)
+        if (k_ <= 6u)
           S_SYM(6 % G, v6);
         S_SYM(7 % G, v7);
       }
+#undef S_NOK
 #else
       S_SYM(0 % G, v0);
       S_SYM(1 % G, v1);
@@ -605,6 +659,14 @@ stream_entry(StreamShared& sh, const uint8_t* __restrict__ in, uint64_t in_total
       sh.sel[tid] = s_sel_entry((uint32_t)tid);
   }
   __syncthreads();
+#if RSB200_S_LUT32
+  {
+    uint32_t* l32 = reinterpret_cast<uint32_t*>(&sh.tab[ntab]);
+    for (int i = tid; i < ntab * (1 << LUT_BITS); i += T_NT)
+      l32[i] = s_lut32_entry(sh.tab[i >> LUT_BITS].lut[i & ((1 << LUT_BITS) - 1)]);
+  }
+  __syncthreads();
+#endif
   const uint32_t id = blockIdx.x * T_NT + tid;
   if (id >= nids)
     return;
@@ -616,11 +678,11 @@ stream_entry(StreamShared& sh, const uint8_t* __restrict__ in, uint64_t in_total
   DevResult* res = results + scan_idx;
   const uint32_t G = scp->group;
   if (G == 1)
-    stream_body<1, WIDE>(sh, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
+    stream_body<1, WIDE>(sh, ntab, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
   else if (G == 2)
-    stream_body<2, WIDE>(sh, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
+    stream_body<2, WIDE>(sh, ntab, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
   else
-    stream_body<4, WIDE>(sh, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
+    stream_body<4, WIDE>(sh, ntab, scp, may_redo, prefetch, in, in_total, out, res, redo ? redo + id : nullptr);
 }
 
 #ifndef RSB200_EMU

@@ -46,7 +46,7 @@ extern "C" int stream_emu_run(const uint8_t* in, uint64_t in_total, const rsb200
   g_emu_any_mode = any_mode;
   const unsigned nblocks = (unsigned)((nscans + T_NT - 1) / T_NT);
   for (unsigned b = 0; b < nblocks; ++b)
-    cuemu::run_cta(b, nblocks, T_NT, sizeof(StreamShared), reverse != 0, [&](uint8_t* smem) {
+    cuemu::run_cta(b, nblocks, T_NT, std::max(sizeof(StreamShared), stream_smem_bytes(T_MAXTAB)), reverse != 0, [&](uint8_t* smem) {
       StreamShared& sh = *reinterpret_cast<StreamShared*>(smem);
       stream_entry<RSB200_EMU_WIDE>(sh, base, in_total, ds.data(), ht.data(), ntables, out, res.data(), ids.data(),
                    (uint32_t)nscans, redo.data(), (any_mode & 1) != 0);
