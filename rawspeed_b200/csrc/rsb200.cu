@@ -9,6 +9,7 @@
 #include "ljpeg_ranges.cuh"
 #include "ljpeg_thread.cuh"
 #include "ljpeg_stream.cuh"
+#include "ljpeg_par.cuh"
 #include "hasselblad.cuh"
 #include "ljpeg_tile.cuh"
 #include "ljpeg_host.h"
@@ -308,6 +309,7 @@ struct rsb200_plan {
   int ntile = 0;
   int tile_r = 1;
   bool clean2 = false; // thread path: k2_clean2_kernel instead of k2_clean_kernel
+  bool use_par = false;    // thread path for small launches: k2_clean_kernel + k2_par_kernel (one CTA per segment)
   bool use_stream = false; // thread path: k2_stream_kernel (unstuffing inside the thread) instead of K2C + K2T
   bool host_tiles_only = false; // tile_groups / d_tile_ids describe the thread path's segments for host-buffer runs only
   std::vector<uint32_t> h_in_size; // per scan: bytes of a plain LJPEG segment (kind 0), else 0xFFFFFFFF
@@ -1584,12 +1586,19 @@ constexpr uint32_t BIG_SEGMENT_BYTES = 256u << 10; // above this a segment gets 
 #endif
 // k2_stream_kernel: an L2 prefetch ahead of every sector pays while the launch is latency bound
 // (r2_run12: 32 frames 6.67 -> 5.81 ms) and costs once the machine is full (128 frames 10.8 -> 11.9 ms)
+constexpr size_t K2P_MAX_SEGMENTS = 0; // (k2_par_kernel: off by default until measured; RSB200_PAR_MAX / RSB200_LJPEG_PATH=par)
 constexpr int K2S_PREFETCH_MAX = 56832; // half a wave of 148 SMs x 6 CTAs x 128 threads
 constexpr size_t K2T_MIN_SEGMENTS = 16384; // measured crossover on B200: ~22 frames of 726 tiles
 static bool thread_eligible(const DevScan& d) {
   return d.kind == 0 && d.pump == 0 && d.mcu_h == 1 &&
          (d.group == 1 || d.group == 2 || d.group == 4) && (d.row_samples & 7u) == 0 &&
          ((d.out_offset | d.out_pitch) & 15u) == 0 && (d.out_x & 7u) == 0;
+}
+
+// k2_par_kernel additionally needs one table for all components (the speculative parse does not
+// know its component phase)
+static bool par_eligible(const DevScan& d) {
+  return thread_eligible(d) && !d.multi_table && d.n_samples >= 8 && d.in_size >= 8;
 }
 
 static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
@@ -1629,9 +1638,31 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
         use_thread = false;
     }
   }
+  // small launches: one CTA per segment on the clean stream (k2_par_kernel) when every plain
+  // segment qualifies; RSB200_LJPEG_PATH=par forces it, RSB200_PAR_MAX moves the threshold (A/B)
+  {
+    size_t n_plain = 0, n_par = 0;
+    for (const DevScan& d : b.scans)
+      if (d.kind == 0 && d.in_size <= BIG_SEGMENT_BYTES) {
+        ++n_plain;
+        n_par += par_eligible(d) ? 1 : 0;
+      }
+    size_t par_max = K2P_MAX_SEGMENTS;
+    if (const char* e = getenv("RSB200_PAR_MAX"))
+      par_max = (size_t)atoll(e);
+    p->use_par = ntables <= T_MAXTAB && n_plain > 0 && n_par == n_plain && n_plain <= par_max;
+    if (const char* e = getenv("RSB200_LJPEG_PATH")) {
+      if (!strcmp(e, "par"))
+        p->use_par = ntables <= T_MAXTAB && n_par > 0;
+      else
+        p->use_par = false;
+    }
+    if (p->use_par)
+      use_thread = true;
+  }
   // the thread path's kernel: k2_stream_kernel (raw bytes, unstuffed by the thread itself) or
   // k2_clean_kernel + k2_thread_kernel; RSB200_LJPEG_PATH=stream|thread forces one (tests run both)
-  p->use_stream = RSB200_STREAM_DEFAULT != 0;
+  p->use_stream = RSB200_STREAM_DEFAULT != 0 && !p->use_par;
   if (const char* e = getenv("RSB200_THREAD_KERNEL"))
     p->use_stream = !strcmp(e, "stream");
   if (const char* e = getenv("RSB200_LJPEG_PATH")) {
@@ -1640,6 +1671,8 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     else if (!strcmp(e, "thread"))
       p->use_stream = false;
   }
+  if (p->use_par)
+    p->use_stream = false;
   // k2_tile_kernel<R> takes the plain single-table tiles; RSB200_LJPEG_PATH=fused keeps them on
   // k2_fused_kernel (tests run both), RSB200_TILE_R=1|2 picks the geometry, RSB200_TILE_PREROLL /
   // RSB200_TILE_NPIECES override the plan-time parameters (A/B runs)
@@ -1669,8 +1702,12 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     if (is_big)
       (d.kind == 2 ? p->has_pentax : (d.kind == 3 ? p->has_nikon : p->has_k3)) = true;
     if (!is_big) {
-      if (use_thread && thread_eligible(d)) {
+      if (use_thread && (p->use_par ? par_eligible(d) : thread_eligible(d))) {
         thread_ids.push_back((uint32_t)i);
+        if (p->use_par) { // differences in stream order (scratch), groups of 8
+          d.diff_offset = b.diff_elems;
+          b.diff_elems += (((uint64_t)d.rows * d.row_samples) + 7) & ~7ull;
+        }
       } else if (use_tile && tile_eligible(d, tile_min_rs)) {
         DevTileParam tp;
         tile_params(d, tile_npiece, tile_dcap, preroll_override, tp.npieces, tp.preroll);
@@ -2336,6 +2373,15 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
             p->d_thread_ids, (uint32_t)p->nthread, p->d_redo, 0);
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 1;
+    } else if (p->nthread && p->use_par) {
+      k2_clean_kernel<<<(p->nthread + C_WARPS - 1) / C_WARPS, 32 * C_WARPS, 0, st>>>(
+          in, (uint64_t)in_bytes, p->d_scans, p->d_thread_ids, (uint32_t)p->nthread, p->d_tscans,
+          p->d_clean, p->d_anchors, p->d_tinfos);
+      k2_par_kernel<<<p->nthread, P_NT, 0, st>>>(in, p->d_scans, p->d_tables, outp, p->d_results,
+                                                 p->d_thread_ids, p->d_tscans, p->d_tinfos, p->d_clean,
+                                                 p->d_anchors, p->d_diffs, p->d_redo);
+      CUDA_TRY(ctx, cudaGetLastError());
+      ctx->launches += 2;
     } else if (p->nthread) {
       // unstuffing pre-pass: one CTA per segment with the tile kernel's stage B for DNG-size
       // segments (k2_clean2_kernel), one warp per segment for small ones (k2_clean_kernel)
@@ -3151,6 +3197,9 @@ extern "C" const char* rsb200_plan_kernels(const rsb200_plan* p) {
     return "(not an LJPEG plan)";
   const bool only_thread = p->nthread && !p->ntile && !p->nsmall && !p->nbig;
   const bool only_tile = p->ntile && !p->nthread && !p->nsmall && !p->nbig;
+  if (only_thread && p->use_par)
+    return "k2_clean_kernel + k2_par_kernel (one CTA per segment: speculative parse of the clean stream to a "
+           "fixed point, decode, row sums)";
   if (only_thread && p->use_stream)
     return p->nthread_redo ? "k2_stream_kernel (one thread per segment, unstuffing in the thread) + "
                              "k2_tile_kernel<1> for flagged ends of stream"

@@ -9,13 +9,14 @@ from helpers import dng_ljpeg_scans, gpu_run
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["auto", "tile2", "fused", "thread", "thread_clean2", "stream"])
+@pytest.fixture(autouse=True, params=["auto", "tile2", "fused", "thread", "thread_clean2", "stream", "par"])
 def ljpeg_path(request, monkeypatch):
-    """Every case runs six times: with the plan's own choice of kernel (k2_tile_kernel<1> for
+    """Every case runs seven times: with the plan's own choice of kernel (k2_tile_kernel<1> for
     plain single-table tiles, k2_fused_kernel for the rest, at these sizes), with the second
     geometry of the tile kernel (RSB200_TILE_R=2), with the round-1 block-per-segment kernel for
-    everything (RSB200_LJPEG_PATH=fused) and with the one-thread-per-segment path in its three
-    forms (K2C + K2T, K2C2 + K2T, and k2_stream_kernel which unstuffs inside the thread)."""
+    everything (RSB200_LJPEG_PATH=fused), with the one-thread-per-segment path in its three
+    forms (K2C + K2T, K2C2 + K2T, and k2_stream_kernel which unstuffs inside the thread) and with
+    the one-CTA-per-segment speculative parse on the clean stream (K2C + k2_par_kernel)."""
     monkeypatch.delenv("RSB200_LJPEG_PATH", raising=False)
     monkeypatch.delenv("RSB200_TILE_R", raising=False)
     monkeypatch.delenv("RSB200_THREAD_KERNEL", raising=False)
