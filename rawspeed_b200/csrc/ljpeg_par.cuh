@@ -312,39 +312,47 @@ par_body(ParShared& sh, const DevScan* __restrict__ scp, const DevTScan& ts, con
   }
 }
 
+// Persistent CTAs: the grid is a few CTAs per SM and every CTA takes segments blockIdx.x,
+// blockIdx.x + gridDim.x, ... -- the slices the resident CTAs walk (64 KiB per DNG tile) then fit
+// the L1 cache (r2_run18: with five CTAs per SM the L1 hit rate was 32 % and every window load that
+// missed stalled its whole warp).
 __global__ void __launch_bounds__(P_NT)
     k2_par_kernel(const uint8_t* __restrict__ in, const DevScan* __restrict__ scans,
                   const DevTable* __restrict__ tables, uint8_t* __restrict__ out,
-                  DevResult* __restrict__ results, const uint32_t* __restrict__ scan_ids,
+                  DevResult* __restrict__ results, const uint32_t* __restrict__ scan_ids, uint32_t nids,
                   const DevTScan* __restrict__ tscans, const DevTInfo* __restrict__ infos,
                   const uint32_t* __restrict__ clean, const uint32_t* __restrict__ anchors,
                   uint16_t* __restrict__ diffs, uint32_t* __restrict__ redo) {
   __shared__ ParShared sh;
-  const uint32_t id = blockIdx.x;
-  const uint32_t sid = scan_ids[id];
-  const uint32_t scan_idx = sid & 0x7FFFFFFFu;
-  const DevScan* scp = scans + scan_idx;
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(tables + scp->table_idx[0]);
-    uint4* dst = reinterpret_cast<uint4*>(&sh.tab);
-    for (int i = threadIdx.x; i < (int)(sizeof(DevTable) / 16); i += P_NT)
-      dst[i] = src[i];
+  int32_t loaded_table = -1;
+  for (uint32_t id = blockIdx.x; id < nids; id += gridDim.x) {
+    const uint32_t sid = scan_ids[id];
+    const uint32_t scan_idx = sid & 0x7FFFFFFFu;
+    const DevScan* scp = scans + scan_idx;
+    __syncthreads(); // (the previous segment is done with the shared state)
+    if (scp->table_idx[0] != loaded_table) {
+      const uint4* src = reinterpret_cast<const uint4*>(tables + scp->table_idx[0]);
+      uint4* dst = reinterpret_cast<uint4*>(&sh.tab);
+      for (int i = threadIdx.x; i < (int)(sizeof(DevTable) / 16); i += P_NT)
+        dst[i] = src[i];
+      loaded_table = scp->table_idx[0];
+    }
     if (threadIdx.x == 0)
       sh.flags = 0;
+    __syncthreads();
+    const DevTScan ts = tscans[id];
+    const DevTInfo info = infos[id];
+    const bool may_redo = ts.pad != 0u;
+    DevResult* res = results + scan_idx;
+    uint32_t* rd = redo ? redo + id : nullptr;
+    const uint32_t G = scp->group;
+    if (G == 1)
+      par_body<1>(sh, scp, ts, info, may_redo, in, clean, anchors, diffs, out, res, rd);
+    else if (G == 2)
+      par_body<2>(sh, scp, ts, info, may_redo, in, clean, anchors, diffs, out, res, rd);
+    else
+      par_body<4>(sh, scp, ts, info, may_redo, in, clean, anchors, diffs, out, res, rd);
   }
-  __syncthreads();
-  const DevTScan ts = tscans[id];
-  const DevTInfo info = infos[id];
-  const bool may_redo = ts.pad != 0u;
-  DevResult* res = results + scan_idx;
-  uint32_t* rd = redo ? redo + id : nullptr;
-  const uint32_t G = scp->group;
-  if (G == 1)
-    par_body<1>(sh, scp, ts, info, may_redo, in, clean, anchors, diffs, out, res, rd);
-  else if (G == 2)
-    par_body<2>(sh, scp, ts, info, may_redo, in, clean, anchors, diffs, out, res, rd);
-  else
-    par_body<4>(sh, scp, ts, info, may_redo, in, clean, anchors, diffs, out, res, rd);
 }
 
 } // namespace rsb200

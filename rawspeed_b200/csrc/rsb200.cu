@@ -254,6 +254,7 @@ struct rsb200_plan {
   int lookup_njobs = 0;
   uint32_t lookup_quads = 0;
   bool lookup_dither = false;
+  bool lookup_smem = false; // RSB200_LUT_SMEM=1 at plan creation: the shared-memory-table kernel (A/B candidate, lookup.cuh)
   int lookup_ntables = 0;
   // bad-pixel interpolation (K11)
   BadPixJobDev* d_badpix_jobs = nullptr;
@@ -309,6 +310,7 @@ struct rsb200_plan {
   int ntile = 0;
   int tile_r = 1;
   bool clean2 = false; // thread path: k2_clean2_kernel instead of k2_clean_kernel
+  int par_ctas = 2;        // k2_par_kernel: persistent CTAs per SM (RSB200_PAR_CTAS)
   bool use_par = false;    // thread path for small launches: k2_clean_kernel + k2_par_kernel (one CTA per segment)
   bool use_stream = false; // thread path: k2_stream_kernel (unstuffing inside the thread) instead of K2C + K2T
   bool host_tiles_only = false; // tile_groups / d_tile_ids describe the thread path's segments for host-buffer runs only
@@ -740,6 +742,10 @@ extern "C" int rsb200_lookup_plan_create(rsb200_ctx* ctx, const rsb200_lookup_jo
   p->kind = 10;
   p->nunits = njobs;
   p->lookup_dither = dither != 0;
+  {
+    const char* smem_env = getenv("RSB200_LUT_SMEM");
+    p->lookup_smem = smem_env && smem_env[0] == '1';
+  }
   p->lookup_ntables = ntables;
   std::vector<LookupJobDev> hj((size_t)njobs);
   uint64_t quads = 0;
@@ -1659,6 +1665,8 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     }
     if (p->use_par)
       use_thread = true;
+    if (const char* e = getenv("RSB200_PAR_CTAS"))
+      p->par_ctas = std::max(1, std::min(8, atoi(e)));
   }
   // the thread path's kernel: k2_stream_kernel (raw bytes, unstuffed by the thread itself) or
   // k2_clean_kernel + k2_thread_kernel; RSB200_LJPEG_PATH=stream|thread forces one (tests run both)
@@ -2272,8 +2280,7 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
     }
   } else if (p->kind == 10) {
     const uint32_t nb = (p->lookup_quads + LUT_WARPS - 1) / LUT_WARPS;
-    const char* smem_env = getenv("RSB200_LUT_SMEM"); // A/B candidate, see lookup.cuh
-    if (smem_env && smem_env[0] == '1' && !p->lookup_dither && p->lookup_ntables == 1) {
+    if (p->lookup_smem && !p->lookup_dither && p->lookup_ntables == 1) {
       const int sms = ctx->sm_count;
       lookup_smem_kernel<<<(unsigned)std::max(1, sms), LUT_SMEM_NT, LUT_SMEM_BYTES, st>>>(
           outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads, p->d_lookup_tables);
@@ -2377,9 +2384,9 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       k2_clean_kernel<<<(p->nthread + C_WARPS - 1) / C_WARPS, 32 * C_WARPS, 0, st>>>(
           in, (uint64_t)in_bytes, p->d_scans, p->d_thread_ids, (uint32_t)p->nthread, p->d_tscans,
           p->d_clean, p->d_anchors, p->d_tinfos);
-      k2_par_kernel<<<p->nthread, P_NT, 0, st>>>(in, p->d_scans, p->d_tables, outp, p->d_results,
-                                                 p->d_thread_ids, p->d_tscans, p->d_tinfos, p->d_clean,
-                                                 p->d_anchors, p->d_diffs, p->d_redo);
+      k2_par_kernel<<<std::min(p->nthread, ctx->sm_count * p->par_ctas), P_NT, 0, st>>>(
+          in, p->d_scans, p->d_tables, outp, p->d_results, p->d_thread_ids, (uint32_t)p->nthread, p->d_tscans,
+          p->d_tinfos, p->d_clean, p->d_anchors, p->d_diffs, p->d_redo);
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches += 2;
     } else if (p->nthread) {
