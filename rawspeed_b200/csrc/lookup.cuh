@@ -24,9 +24,13 @@ constexpr int LUT_NT = 32 * LUT_WARPS;
 template <bool DITHER>
 __global__ void __launch_bounds__(LUT_NT)
     lookup_kernel(uint8_t* __restrict__ img, const LookupJobDev* __restrict__ jobs, int njobs,
-                  uint32_t total_quads, const uint16_t* __restrict__ tables) {
+                  uint32_t total_quads, const uint16_t* __restrict__ tables, uint32_t nseg) {
+  // a warp = four rows x one of nseg column segments (the dither generator can be started at any
+  // sample, lut_mwc_state: rows need not be walked from their first sample; r2_run11 ncu: with
+  // whole rows per warp a 45 MP frame had 9 warps per SM, 15 % of the slots)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t quad = blockIdx.x * LUT_WARPS + warp;
+  const uint32_t item = blockIdx.x * LUT_WARPS + warp;
+  const uint32_t quad = item / nseg, seg = item - quad * nseg;
   if (quad >= total_quads)
     return;
   int lo = 0, hi = njobs - 1;
@@ -41,15 +45,19 @@ __global__ void __launch_bounds__(LUT_NT)
   const uint32_t y0 = (quad - j.quad_begin) * SCALE_ROWS;
   uint8_t* const base = img + j.offset + (uint64_t)y0 * j.pitch;
   const uint16_t* const table = tables + (size_t)j.table * (DITHER ? 131072u : 65536u);
-  const uint32_t iters = (j.ngroups + 31) / 32;
+  const uint32_t gps = (((j.ngroups + nseg - 1) / nseg) + 31u) & ~31u; // groups per segment
+  const uint32_t g0 = seg * gps, g1 = min(g0 + gps, j.ngroups);
+  if (g0 >= g1)
+    return;
+  const uint32_t iters = (g1 - g0 + 31) / 32;
   const uint32_t jump = DITHER ? lut_powmod(248u) : 0u;
   uint32_t st[SCALE_ROWS];
 #pragma unroll
   for (int r = 0; r < SCALE_ROWS; ++r)
-    st[r] = DITHER ? lut_mwc_state(j.width, y0 + r, 8u * (uint32_t)lane) : 0u;
+    st[r] = DITHER ? lut_mwc_state(j.width, y0 + r, 8u * (g0 + (uint32_t)lane)) : 0u;
   for (uint32_t it = 0; it < iters; ++it) {
-    const uint32_t g = it * 32 + lane;
-    if (g < j.ngroups) {
+    const uint32_t g = g0 + it * 32 + lane;
+    if (g < g1) {
       ScaleVec v[SCALE_ROWS];
 #pragma unroll
       for (int r = 0; r < SCALE_ROWS; ++r)

@@ -207,6 +207,7 @@ struct ScaleGroup {
   ScaleJobDev* d_jobs = nullptr;
   int njobs = 0;
   uint32_t total_quads = 0;
+  uint32_t nseg = 1; // column segments per row quad (mode 1)
 };
 
 struct UnpackFastGroup {
@@ -253,6 +254,7 @@ struct rsb200_plan {
   uint16_t* d_lookup_tables = nullptr;
   int lookup_njobs = 0;
   uint32_t lookup_quads = 0;
+  uint32_t lookup_nseg = 1; // column segments per row quad (more warps for few rows)
   bool lookup_dither = false;
   bool lookup_smem = false; // RSB200_LUT_SMEM=1 at plan creation: the shared-memory-table kernel (A/B candidate, lookup.cuh)
   int lookup_ntables = 0;
@@ -763,6 +765,16 @@ extern "C" int rsb200_lookup_plan_create(rsb200_ctx* ctx, const rsb200_lookup_jo
   }
   p->lookup_njobs = njobs;
   p->lookup_quads = (uint32_t)quads;
+  {
+    // enough warps to fill the machine (~32 per SM), but at least 2 iterations of 32 groups each
+    uint32_t min_groups = 0xFFFFFFFFu;
+    for (int i = 0; i < njobs; ++i)
+      min_groups = std::min(min_groups, hj[(size_t)i].ngroups);
+    const uint32_t want = (uint32_t)((32ull * (uint64_t)ctx->sm_count + quads - 1) / std::max<uint64_t>(quads, 1));
+    p->lookup_nseg = std::max(1u, std::min(std::min(want, 8u), std::max(1u, min_groups / 64u)));
+    if (const char* e = getenv("RSB200_LUT_NSEG"))
+      p->lookup_nseg = (uint32_t)std::max(1, std::min(64, atoi(e)));
+  }
   const size_t tbytes = sizeof(uint16_t) * (size_t)ntables * (dither ? 131072u : 65536u);
   CUDA_TRY(ctx, rsb_dev_alloc((void**)&p->d_lookup_jobs, sizeof(LookupJobDev) * hj.size()));
   CUDA_TRY(ctx, cudaMemcpy(p->d_lookup_jobs, hj.data(), sizeof(LookupJobDev) * hj.size(),
@@ -911,6 +923,13 @@ extern "C" int rsb200_scale_plan_create(rsb200_ctx* ctx, const rsb200_scale_job*
     g.mode = mode;
     g.njobs = (int)dev[mode].size();
     g.total_quads = quads[mode];
+    {
+      uint32_t min_groups = 0xFFFFFFFFu;
+      for (const ScaleJobDev& d : dev[mode])
+        min_groups = std::min(min_groups, d.ngroups);
+      const uint32_t want = (uint32_t)((32ull * (uint64_t)ctx->sm_count + g.total_quads - 1) / std::max(g.total_quads, 1u));
+      g.nseg = mode == 0 ? 1u : std::max(1u, std::min(std::min(want, 8u), std::max(1u, min_groups / 64u)));
+    }
     CUDA_TRY(ctx, rsb_dev_alloc((void**)&g.d_jobs, sizeof(ScaleJobDev) * dev[mode].size()));
     p->scale_groups.push_back(g); // owned by the plan from here on
     CUDA_TRY(ctx, cudaMemcpy(g.d_jobs, dev[mode].data(), sizeof(ScaleJobDev) * dev[mode].size(),
@@ -2279,17 +2298,17 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       ctx->launches++;
     }
   } else if (p->kind == 10) {
-    const uint32_t nb = (p->lookup_quads + LUT_WARPS - 1) / LUT_WARPS;
+    const uint32_t nbs = (uint32_t)(((uint64_t)p->lookup_quads * p->lookup_nseg + LUT_WARPS - 1) / LUT_WARPS);
     if (p->lookup_smem && !p->lookup_dither && p->lookup_ntables == 1) {
       const int sms = ctx->sm_count;
       lookup_smem_kernel<<<(unsigned)std::max(1, sms), LUT_SMEM_NT, LUT_SMEM_BYTES, st>>>(
           outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads, p->d_lookup_tables);
     } else if (p->lookup_dither)
-      lookup_kernel<true><<<nb, LUT_NT, 0, st>>>(outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads,
-                                                 p->d_lookup_tables);
+      lookup_kernel<true><<<nbs, LUT_NT, 0, st>>>(outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads,
+                                                  p->d_lookup_tables, p->lookup_nseg);
     else
-      lookup_kernel<false><<<nb, LUT_NT, 0, st>>>(outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads,
-                                                  p->d_lookup_tables);
+      lookup_kernel<false><<<nbs, LUT_NT, 0, st>>>(outp, p->d_lookup_jobs, p->lookup_njobs, p->lookup_quads,
+                                                   p->d_lookup_tables, p->lookup_nseg);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
   } else if (p->kind == 9) {
@@ -2314,9 +2333,10 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
     for (const ScaleGroup& g : p->scale_groups) {
       const uint32_t nb = (g.total_quads + SCALE_WARPS - 1) / SCALE_WARPS;
       if (g.mode == 0)
-        scale_kernel<0><<<nb, SCALE_NT, 0, st>>>(outp, g.d_jobs, g.njobs, g.total_quads);
+        scale_kernel<0><<<nb, SCALE_NT, 0, st>>>(outp, g.d_jobs, g.njobs, g.total_quads, 1u);
       else
-        scale_kernel<1><<<nb, SCALE_NT, 0, st>>>(outp, g.d_jobs, g.njobs, g.total_quads);
+        scale_kernel<1><<<(uint32_t)(((uint64_t)g.total_quads * g.nseg + SCALE_WARPS - 1) / SCALE_WARPS), SCALE_NT,
+                          0, st>>>(outp, g.d_jobs, g.njobs, g.total_quads, g.nseg);
       CUDA_TRY(ctx, cudaGetLastError());
       ctx->launches++;
     }

@@ -50,16 +50,24 @@ __device__ __forceinline__ int scale_find_job(const ScaleJobDev* jobs, int njobs
 template <int MODE>
 __global__ void __launch_bounds__(SCALE_NT)
     scale_kernel(uint8_t* __restrict__ img, const ScaleJobDev* __restrict__ jobs, int njobs,
-                 uint32_t total_quads) {
+                 uint32_t total_quads, uint32_t nseg) {
+  // MODE 1: a warp = four rows x one of nseg column segments (the plain loop's generator can be
+  // started at any sample, scale_mwc_state); MODE 0: nseg = 1 (the SSE2 loop's 16-bit generator
+  // has no jump, a row is walked from its first sample)
   __shared__ __align__(16) uint8_t s_rnd[MODE == 0 ? SCALE_WARPS : 1][SCALE_ROWS * SCALE_RND_STRIDE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t quad = blockIdx.x * SCALE_WARPS + warp;
+  const uint32_t item = blockIdx.x * SCALE_WARPS + warp;
+  const uint32_t quad = MODE == 0 ? item : item / nseg, seg = MODE == 0 ? 0u : item - quad * nseg;
   if (quad >= total_quads)
     return;
   const ScaleJobDev j = jobs[scale_find_job(jobs, njobs, quad)];
   const uint32_t y0 = (quad - j.quad_begin) * SCALE_ROWS;
   uint8_t* const base = img + j.offset + (uint64_t)(j.off_y + y0) * j.pitch + (uint64_t)j.group0 * 16;
-  const uint32_t iters = (j.ngroups + 31) / 32;
+  const uint32_t gps = MODE == 0 ? j.ngroups : ((((j.ngroups + nseg - 1) / nseg) + 31u) & ~31u);
+  const uint32_t g0 = seg * gps, g1 = min(g0 + gps, j.ngroups);
+  if (g0 >= g1)
+    return;
+  const uint32_t iters = (g1 - g0 + 31) / 32;
 
   if (MODE == 0) {
     uint8_t* const rnd = s_rnd[MODE == 0 ? warp : 0];
@@ -94,14 +102,14 @@ __global__ void __launch_bounds__(SCALE_NT)
     // state before the first sample of this lane's first group, per row; the jump from the end
     // of one group to the start of the lane's next one is 31 groups = 248 samples
     const uint32_t jump = scale_powmod(248u);
-    const int32_t x_first = (int32_t)(8u * (uint32_t)lane) - (int32_t)j.skip;
+    const int32_t x_first = (int32_t)(8u * (g0 + (uint32_t)lane)) - (int32_t)j.skip;
     uint32_t st[SCALE_ROWS];
 #pragma unroll
     for (int r = 0; r < SCALE_ROWS; ++r)
       st[r] = j.dither ? scale_mwc_state(j.crop_w, y0 + r, (uint32_t)max(x_first, 0)) : 0u;
     for (uint32_t it = 0; it < iters; ++it) {
-      const uint32_t g = it * 32 + lane;
-      if (g < j.ngroups) {
+      const uint32_t g = g0 + it * 32 + lane;
+      if (g < g1) {
         ScaleVec v[SCALE_ROWS];
 #pragma unroll
         for (int r = 0; r < SCALE_ROWS; ++r)
