@@ -312,10 +312,10 @@ par_body(ParShared& sh, const DevScan* __restrict__ scp, const DevTScan& ts, con
   }
 }
 
-// Persistent CTAs: the grid is a few CTAs per SM and every CTA takes segments blockIdx.x,
-// blockIdx.x + gridDim.x, ... -- the slices the resident CTAs walk (64 KiB per DNG tile) then fit
-// the L1 cache (r2_run18: with five CTAs per SM the L1 hit rate was 32 % and every window load that
-// missed stalled its whole warp).
+// A CTA takes segments blockIdx.x, blockIdx.x + gridDim.x, ...: the plan launches one CTA per segment.
+// (A persistent grid of 2..5 CTAs per SM, so that the slices the resident CTAs walk fit the L1
+// cache, was measured SLOWER -- r2_run20: 0.50-0.66 ms per frame against 0.34 ms; the kernel wants
+// more warps in flight, not fewer: RSB200_PAR_CTAS keeps the experiment.)
 __global__ void __launch_bounds__(P_NT)
     k2_par_kernel(const uint8_t* __restrict__ in, const DevScan* __restrict__ scans,
                   const DevTable* __restrict__ tables, uint8_t* __restrict__ out,

@@ -312,7 +312,7 @@ struct rsb200_plan {
   int ntile = 0;
   int tile_r = 1;
   bool clean2 = false; // thread path: k2_clean2_kernel instead of k2_clean_kernel
-  int par_ctas = 2;        // k2_par_kernel: persistent CTAs per SM (RSB200_PAR_CTAS)
+  int par_ctas = 0;        // k2_par_kernel: 0 = one CTA per segment; n = persistent, n CTAs per SM (RSB200_PAR_CTAS; measured slower, r2_run20)
   bool use_par = false;    // thread path for small launches: k2_clean_kernel + k2_par_kernel (one CTA per segment)
   bool use_stream = false; // thread path: k2_stream_kernel (unstuffing inside the thread) instead of K2C + K2T
   bool host_tiles_only = false; // tile_groups / d_tile_ids describe the thread path's segments for host-buffer runs only
@@ -1685,7 +1685,7 @@ static int finish_ljpeg_plan(rsb200_ctx* ctx, rsb200_plan* p,
     if (p->use_par)
       use_thread = true;
     if (const char* e = getenv("RSB200_PAR_CTAS"))
-      p->par_ctas = std::max(1, std::min(8, atoi(e)));
+      p->par_ctas = std::max(0, std::min(8, atoi(e)));
   }
   // the thread path's kernel: k2_stream_kernel (raw bytes, unstuffed by the thread itself) or
   // k2_clean_kernel + k2_thread_kernel; RSB200_LJPEG_PATH=stream|thread forces one (tests run both)
@@ -2404,7 +2404,7 @@ extern "C" int rsb200_plan_run(rsb200_plan* p, const void* d_in, size_t in_bytes
       k2_clean_kernel<<<(p->nthread + C_WARPS - 1) / C_WARPS, 32 * C_WARPS, 0, st>>>(
           in, (uint64_t)in_bytes, p->d_scans, p->d_thread_ids, (uint32_t)p->nthread, p->d_tscans,
           p->d_clean, p->d_anchors, p->d_tinfos);
-      k2_par_kernel<<<std::min(p->nthread, ctx->sm_count * p->par_ctas), P_NT, 0, st>>>(
+      k2_par_kernel<<<p->par_ctas > 0 ? std::min(p->nthread, ctx->sm_count * p->par_ctas) : p->nthread, P_NT, 0, st>>>(
           in, p->d_scans, p->d_tables, outp, p->d_results, p->d_thread_ids, (uint32_t)p->nthread, p->d_tscans,
           p->d_tinfos, p->d_clean, p->d_anchors, p->d_diffs, p->d_redo);
       CUDA_TRY(ctx, cudaGetLastError());
