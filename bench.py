@@ -750,17 +750,55 @@ def kernel_name(plan, nframes):
     return plan.kernels
 
 
+def _cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            out += list(range(int(a), int(b) + 1))
+        elif part:
+            out.append(int(part))
+    return out
+
+
+def gpu_numa_cpus(local):
+    """The CPUs of the NUMA node GPU `local` hangs off: its PCI address from nvidia-smi (the
+    CUDA_VISIBLE_DEVICES order is the order nvidia-smi lists the visible GPUs in), the node from
+    sysfs.  None when any of that is unavailable."""
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                           capture_output=True, text=True, timeout=20).stdout.split()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if all(v.isdigit() for v in ids) and local < len(ids):
+                idx = int(ids[local])
+        bus = q[idx].lower()
+        if len(bus.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        return _cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read())
+    except Exception:
+        return None
+
+
 def pin_rank_to_numa(local):
-    """GPUs 0-3 hang off NUMA node 0, GPUs 4-7 off node 1 on the 8-GPU boxes (SCALE_r01.json
-    topology): keep this rank's threads, and therefore its pinned staging buffers (first touch), on
-    the cores of its GPU's node."""
+    """Keep this rank's threads, and therefore its pinned staging buffers (first touch), on the cores
+    of the NUMA node its GPU hangs off (sysfs; r2_run15: on a 4-GPU allocation GPUs 2 and 3 sit on
+    node 1).  Fallback when sysfs / nvidia-smi do not tell: GPUs 0-3 on node 0, 4-7 on node 1 (the
+    8-GPU boxes, SCALE_r01.json topology)."""
     try:
         ncpu = os.cpu_count() or 1
         if ncpu < 64 or not hasattr(os, "sched_setaffinity"):
             return
-        half, q = ncpu // 2, ncpu // 4
-        node = 0 if local < 4 else 1
-        cores = list(range(node * q, (node + 1) * q)) + list(range(half + node * q, half + (node + 1) * q))
+        cores = gpu_numa_cpus(local)
+        if not cores:
+            half, q = ncpu // 2, ncpu // 4
+            node = 0 if local < 4 else 1
+            cores = list(range(node * q, (node + 1) * q)) + list(range(half + node * q, half + (node + 1) * q))
         os.sched_setaffinity(0, cores)
     except Exception:
         pass

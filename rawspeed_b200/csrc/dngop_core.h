@@ -126,13 +126,12 @@ RSD_HD void dngop_apply_group_v1(const DngOpDev* ops, uint32_t nops, const uint1
   }
 }
 
-// ---- second version of the walk (RSB200_DNGOP_V2; same results, fewer instructions) ----------
+// ---- second version of the walk (the default since r2_run22; -DRSB200_DNGOP_V1 selects the first) ----
 // The first version pays, per opcode and SAMPLE, a division by the run-time column pitch and a
 // switch on the opcode kind.  Here the lattice position of the group's first column is computed
 // once per opcode (one division) and stepped incrementally as the column advances, and the
 // kind is dispatched once per opcode, outside the sample loop.  First measured on a B200 the
-// first version was issue bound (0.51 ms per 45 MP frame with eight opcodes); this one is the
-// candidate to A/B against it (tools/ab_ljpeg.py build NAME -DRSB200_DNGOP_V2).
+// first version was issue bound (0.51 ms per 45 MP frame with eight opcodes); this one: 0.47 ms.
 template <class Sink>
 RSD_HD void dngop_apply_group_v2(const DngOpDev* ops, uint32_t nops, const uint16_t* tables,
                                  const uint32_t* deltas, const DngOpJobDev& jb, uint32_t r,
@@ -232,10 +231,11 @@ template <class Sink>
 RSD_HD void dngop_apply_group(const DngOpDev* ops, uint32_t nops, const uint16_t* tables,
                               const uint32_t* deltas, const DngOpJobDev& jb, uint32_t r,
                               uint32_t s0, uint32_t (&v)[8], Sink& sink) {
-#if defined(RSB200_DNGOP_V2)
-  dngop_apply_group_v2(ops, nops, tables, deltas, jb, r, s0, v, sink);
-#else
+  // (r2_run22, 45 MP frame with eight opcodes: the second walk 96.9 GPix/s, the first 88.6; both exact)
+#if defined(RSB200_DNGOP_V1)
   dngop_apply_group_v1(ops, nops, tables, deltas, jb, r, s0, v, sink);
+#else
+  dngop_apply_group_v2(ops, nops, tables, deltas, jb, r, s0, v, sink);
 #endif
 }
 
