@@ -7,8 +7,8 @@
 // One frame is ONE Huffman stream without restart points (up to 100 MP):
 //     per pair of pixels:  [len1 code][len2 code][len1 bits of diff1][len2 bits of diff2]
 //     p1 += diff1, p2 += diff2 (both start at initPred in every row), out(row, 2k) = p1, out(row, 2k+1) = p2
-// The reference decodes it on one CPU thread.  Here the stream is cut into segments of 16384 bits and
-// every segment gets a thread (the stream is read through L1; a thread walks its 2 KiB sequentially):
+// The reference decodes it on one CPU thread.  Here the stream is cut into segments of 4096 bits and
+// every segment gets a thread (the stream is read through L1; a thread walks its 512 bytes sequentially):
 //   H1  parse   thread i parses pairs (lengths only) from start[i] until it passes the end of its
 //               segment: exit[i] = bit where the first pair of the next segment starts, count[i] =
 //               pairs that start in [start[i], exit[i]).  start[0] = 0 is exact; start[i > 0] begins
@@ -16,7 +16,7 @@
 //               pairs the guessed parse usually runs on true pair boundaries.
 //   H1b link    start[i] <- exit[i-1] wherever they differ; a flag says whether anything changed.
 //               Rounds of (parse, link) reach the fixed point start[i] == exit[i-1] for all i, and by
-//               induction from segment 0 the fixed point IS the sequential parse.  Six rounds are
+//               induction from segment 0 the fixed point IS the sequential parse.  Eight rounds are
 //               launched unconditionally (a CTA whose starts did not change returns at once); if the
 //               last link still changed something, one thread walks the rest sequentially (exact,
 //               never observed).
@@ -42,10 +42,15 @@ namespace rsb200 {
 constexpr int H_NT = 128;                 // threads = segments per CTA
 // bits per segment.  A guessed parse locks onto the true pair boundaries with probability ~1 / (bits
 // per pair) per pair: ~16 pairs for camera data (16 bits per pair), ~50 pairs for 16-bit noise (48
-// bits per pair, 2400 bits) -- 16384 bits leave a segment that never locks at < 0.1 % even then; such
-// a segment costs one more round.
-constexpr uint32_t H_SEG_BITS = 16384;
-constexpr int H_ROUNDS = 6;               // (parse, link) rounds launched unconditionally
+// bits per pair, 2400 bits).  A segment that does not lock costs its successors one more round;
+// CPU replay, 2048 x 256 px: camera-like data settles in 2 rounds at any size, 16-bit noise needs 2 / 3 /
+// 5 / 7 rounds at 16384 / 8192 / 4096 / 2048 bits.  Shorter segments = more threads (a 50 MB stream
+// has only 24 k segments of 16384 bits: 0.1 waves, each thread walking 2 KiB): 4096 bits, 8 rounds.
+#ifndef RSB200_H_SEG_BITS
+#define RSB200_H_SEG_BITS 4096
+#endif
+constexpr uint32_t H_SEG_BITS = RSB200_H_SEG_BITS;
+constexpr int H_ROUNDS = 8;               // (parse, link) rounds launched unconditionally
 constexpr uint32_t H_NOKEY = 0xFFFFFFFFu; // no failure recorded
 
 struct DevHassJob {
