@@ -328,10 +328,12 @@ __device__ __forceinline__ bool s_any(bool want) { return __any_sync(__activemas
 
 // The same without control flow, for the straight-line unit: a code the LUT does not resolve
 // (longer than LUT_BITS, SSSS = 16, corrupt) leaves p where it is, so every later symbol of the
-// unit sees the same window and misses too; nok counts the symbols before the first miss and the
-// unit is finished symbol by symbol (S_SYM) from there.  Without a branch per symbol the eight
-// decodes are one basic block: the difference arithmetic of symbol k is scheduled into the
-// latency of symbol k+1's LUT load.
+// unit sees the same window and -- LOOKING IT UP IN THE SAME TABLE -- misses too; nok counts the
+// symbols before the first miss and the unit is finished symbol by symbol (S_SYM) from there.
+// Without a branch per symbol the eight decodes are one basic block: the difference arithmetic of
+// symbol k is scheduled into the latency of symbol k+1's LUT load.  A segment whose components
+// use DIFFERENT tables does not take this form (a window that starts with a long code of one
+// table can be a short code of the other: the miss would not stick); it goes symbol by symbol.
 #define S_SYMF(c, val)                                                          \
   do {                                                                          \
     const uint32_t x_ = __funnelshift_l(nxt, cur, p);                           \
@@ -486,6 +488,11 @@ stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp
 #endif
     rowstart[c] = scp->init_pred[c];
   }
+  // the straight-line unit relies on "a miss repeats": true when every component reads the same LUT
+  bool one_table = true;
+#pragma unroll
+  for (int c = 1; c < G; ++c)
+    one_table = one_table && lutb[c] == lutb[0];
   const uint32_t rows = scp->rows;
   const uint32_t units = scp->row_samples >> 3; // row_samples is a multiple of 8
   const uint32_t store_w = scp->store_w;
@@ -531,16 +538,19 @@ stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp
 #else
 #define S_NOK nok
 #endif
-      S_SYMF(0 % G, v0);
-      S_SYMF(1 % G, v1);
-      S_SYMF(2 % G, v2);
-      S_SYMF(3 % G, v3);
-      S_SYMF(4 % G, v4);
-      S_SYMF(5 % G, v5);
-      S_SYMF(6 % G, v6);
-      S_SYMF(7 % G, v7);
-      if (S_NOK != 8u) { // rare: the symbols from the first miss on, one by one
-        const uint32_t k_ = S_NOK;
+      uint32_t k_ = 0; // samples of the unit that are done
+      if (G == 1 || one_table) {
+        S_SYMF(0 % G, v0);
+        S_SYMF(1 % G, v1);
+        S_SYMF(2 % G, v2);
+        S_SYMF(3 % G, v3);
+        S_SYMF(4 % G, v4);
+        S_SYMF(5 % G, v5);
+        S_SYMF(6 % G, v6);
+        S_SYMF(7 % G, v7);
+        k_ = S_NOK;
+      }
+      if (k_ != 8u) { // rare: the symbols from the first miss on, one by one
         if (k_ <= 0u)
           S_SYM(0 % G, v0);
         if (k_ <= 1u)

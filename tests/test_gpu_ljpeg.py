@@ -88,6 +88,19 @@ def test_two_tables(ctx):
     _check_tiles(ctx, img, 100, 50, ncomp=4, tabs=tabs, tab_of_comp=[1, 0, 0, 1])
 
 
+def test_two_tables_long_code_of_one_is_a_short_code_of_the_other(ctx):
+    """Component 0: wild noise with the default table (codes of 12-14 bits, resolved outside the LUT);
+    component 1: a COMPLETE table of eight 3-bit codes, in which every window is a valid code.  A decoder
+    that looks a window up again after a miss -- with the next component's table -- must not take the hit."""
+    rng = np.random.default_rng(5)
+    img = np.zeros((64, 256), np.uint16)
+    img[:, 0::2] = rng.integers(0, 1 << 14, (64, 128))
+    img[:, 1::2] = 8192 + rng.integers(0, 60, (64, 128))
+    tabs = [synth.default_tables(1)[0], port.Huff(bytes([0, 0, 8] + [0] * 13), bytes(range(8)))]
+    _check_tiles(ctx, img, 128, 32, tabs=tabs, tab_of_comp=[0, 1])
+    _check_tiles(ctx, img, 256, 32, ncomp=4, tabs=tabs, tab_of_comp=[0, 1, 0, 1])
+
+
 def test_restart_intervals(ctx):
     img = synth.image_model(160, 96, 17)
     _check_tiles(ctx, img, 80, 48, restart_rows=1)

@@ -103,6 +103,19 @@ def test_components_1_and_4(emu):
     check_tiles(emu, img, 512, 48, ncomp=4)
 
 
+def test_two_tables_long_code_of_one_is_a_short_code_of_the_other(emu):
+    """The straight-line unit counts on "a miss repeats" (same window, same table).  With two tables a
+    window that starts with a 12-bit code of the first can be a 3-bit code of the second: such segments
+    must go symbol by symbol (found in round 2: the shipped kernel decoded garbage here)."""
+    rng = np.random.default_rng(5)
+    img = np.zeros((32, 256), np.uint16)
+    img[:, 0::2] = rng.integers(0, 1 << 14, (32, 128))
+    img[:, 1::2] = 8192 + rng.integers(0, 60, (32, 128))
+    tabs = [synth.default_tables(1)[0], port.Huff(bytes([0, 0, 8] + [0] * 13), bytes(range(8)))]
+    check_tiles(emu, img, 256, 32, tabs=tabs, tab_of_comp=[0, 1])
+    check_tiles(emu, img, 256, 32, ncomp=4, tabs=tabs, tab_of_comp=[0, 1, 0, 1])
+
+
 def test_restart_intervals(emu):
     img = synth.image_model(320, 96, 17)
     check_tiles(emu, img, 160, 48, restart_rows=1)
