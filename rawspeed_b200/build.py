@@ -45,7 +45,7 @@ def _sources(sub, exts):
 
 def build(force=False, verbose=False):
     hdr = os.path.join(ROOT, "include", "rawspeed_b200.h")
-    dev_src = _sources("", (".cu", ".cuh")) + [hdr]
+    dev_src = _sources("", (".cu", ".cuh", ".h")) + [hdr]
     if force or _newer(LIB, dev_src):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
             "-o", LIB, os.path.join(HERE, "csrc", "rsb200.cu"), "-ldl", "-lgomp"]

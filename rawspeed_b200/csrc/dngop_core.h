@@ -226,6 +226,112 @@ RSD_HD void dngop_apply_group_v2(const DngOpDev* ops, uint32_t nops, const uint1
   }
 }
 
+// ---- third version of the walk: one sample per pixel (cpp = 1, every CFA image) ----
+// ncu on the second version (r2_postdecode_ncu_metrics.csv): issue bound at ~300 thread-instructions
+// per opcode and group -- eight rounds of range / lattice / plane tests, eight delta indices, and
+// twelve scalar loads of the opcode.  With one sample per pixel the eight samples of a group are
+// eight consecutive columns, so the opcode's footprint in the group is a bit mask with a closed
+// form: columns [lo, hi) of the group lie in [left, right), and inside that range every
+// col_pitch-th one from the first lattice column on.  The mask is built once per opcode (no
+// division for pitch 1, one otherwise), the delta index of a hit is the index of the first hit
+// plus the number of hits before it, and the opcode is read with three 128-bit loads.
+
+template <class Sink>
+RSD_HD void dngop_apply_group_v3(const DngOpDev* ops, uint32_t nops, const uint16_t* tables,
+                                 const uint32_t* deltas, const DngOpJobDev& jb, uint32_t r,
+                                 uint32_t s0, uint32_t (&v)[8], Sink& sink) {
+  const uint32_t col0 = s0; // cpp == 1
+  const uint32_t nvalid = jb.samples - s0 < 8u ? jb.samples - s0 : 8u;
+  for (uint32_t k = 0; k < nops; ++k) {
+    DngOpDev op;
+#if defined(__CUDA_ARCH__)
+    {
+      static_assert(sizeof(DngOpDev) == 48, "three 16-byte loads");
+      const uint4* q = reinterpret_cast<const uint4*>(ops + k); // (the array is 16-byte aligned: plan allocation)
+      const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+      op.kind = a.x; op.top = a.y; op.left = a.z; op.bottom = a.w;
+      op.right = b.x; op.first_plane = b.y; op.planes = b.z; op.row_pitch = b.w;
+      op.col_pitch = c.x; op.table = c.y; op.value = c.z; op.slot = c.w;
+    }
+#else
+    op = ops[k];
+#endif
+    if (r < op.top || r >= op.bottom || op.first_plane != 0u || op.planes == 0u)
+      continue; // (plane 0 is the only plane)
+    const uint32_t ry = r - op.top;
+    const uint32_t yi = op.row_pitch == 1 ? ry : ry / op.row_pitch;
+    if (yi * op.row_pitch != ry)
+      continue;
+    // samples [lo, hi) of the group lie in [left, right)
+    const uint32_t lo = op.left > col0 ? op.left - col0 : 0u;
+    uint32_t hi = op.right > col0 ? op.right - col0 : 0u;
+    hi = hi < nvalid ? hi : nvalid;
+    if (lo >= hi)
+      continue;
+    // first lattice column at or behind col0 + lo, its index on the lattice
+    const uint32_t pit = op.col_pitch;
+    const uint32_t d = col0 + lo - op.left;
+    uint32_t xi0 = d, i0 = lo, hit;
+    if (pit == 1u) {
+      hit = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+    } else {
+      xi0 = d / pit;
+      const uint32_t rem = d - xi0 * pit;
+      if (rem) {
+        i0 += pit - rem;
+        ++xi0;
+      }
+      hit = 0;
+      for (uint32_t i = i0; i < hi; i += pit)
+        hit |= 1u << i;
+      if (!hit)
+        continue;
+    }
+    if (op.kind == DNGOP_LOOKUP) {
+      const uint16_t* t = tables + (size_t)op.table * 65536u;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; ++i)
+        if ((hit >> i) & 1u)
+          v[i] = t[v[i]];
+    } else if (op.kind == DNGOP_BAD_CONSTANT) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; ++i)
+        if (((hit >> i) & 1u) && v[i] == op.value)
+          sink.hit(op.slot, r, s0 + (uint32_t)i);
+    } else {
+      const bool by_row = op.kind == DNGOP_OFFSET_ROW || op.kind == DNGOP_SCALE_ROW;
+      const bool scale = op.kind == DNGOP_SCALE_ROW || op.kind == DNGOP_SCALE_COL;
+      const uint32_t* dl = deltas + op.table + (by_row ? yi : xi0);
+      const uint32_t row_dv = dl[0]; // a row delta is the same for every hit
+      uint32_t nth = 0;              // hits before sample i: the column delta of a hit is dl[nth]
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int i = 0; i < 8; ++i) {
+        if (!((hit >> i) & 1u))
+          continue;
+        const uint32_t dv = by_row ? row_dv : dl[nth];
+        ++nth;
+        if (jb.is_f32) {
+          union { uint32_t u; float f; } a, dd;
+          a.u = v[i];
+          dd.u = dv;
+          a.f = scale ? dd.f * a.f : dd.f + a.f;
+          v[i] = a.u;
+        } else if (scale) {
+          v[i] = dngop_clamp16(((int32_t)dv * (int32_t)v[i] + 512) >> 10);
+        } else {
+          v[i] = dngop_clamp16((int32_t)dv + (int32_t)v[i]);
+        }
+      }
+    }
+  }
+}
+
 // the walk the kernel (and its CPU replay) uses
 template <class Sink>
 RSD_HD void dngop_apply_group(const DngOpDev* ops, uint32_t nops, const uint16_t* tables,
@@ -234,8 +340,13 @@ RSD_HD void dngop_apply_group(const DngOpDev* ops, uint32_t nops, const uint16_t
   // (r2_run22, 45 MP frame with eight opcodes: the second walk 96.9 GPix/s, the first 88.6; both exact)
 #if defined(RSB200_DNGOP_V1)
   dngop_apply_group_v1(ops, nops, tables, deltas, jb, r, s0, v, sink);
-#else
+#elif defined(RSB200_DNGOP_V2)
   dngop_apply_group_v2(ops, nops, tables, deltas, jb, r, s0, v, sink);
+#else
+  if (jb.cpp == 1u)
+    dngop_apply_group_v3(ops, nops, tables, deltas, jb, r, s0, v, sink);
+  else
+    dngop_apply_group_v2(ops, nops, tables, deltas, jb, r, s0, v, sink);
 #endif
 }
 

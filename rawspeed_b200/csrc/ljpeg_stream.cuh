@@ -300,6 +300,31 @@ __device__ __noinline__ uint32_t s_stream_position(const uint8_t* __restrict__ g
   return rawp - skew;
 }
 
+// The straight-line unit stopped at bit p1 (its first miss; every symbol before it was a hit and is
+// done): how many symbols lie between p0, where the unit began, and p1.  The words from p0 >> 5 on
+// are still in the ring: nothing is written inside a unit, and a fill step at the end of the unit
+// before (taken with at most S_ROOM bytes ahead) leaves the ring starting 8 bytes or more BEHIND
+// the read position.  Rare path (codes longer than LUT_BITS, SSSS = 16, corrupt data).
+__device__ __noinline__ uint32_t s_count_hits(uint32_t ringb, uint32_t lutb, uint32_t p0, uint32_t p1) {
+  uint32_t k = 0, q = p0;
+  while (q != p1 && k < 8u) {
+    const uint32_t w = (q >> 5) * T_WSTRIDE;
+    const uint32_t a = lds_u32<0>(ringb + (w & T_RMASK));
+    const uint32_t b = lds_u32<0>(ringb + ((w + T_WSTRIDE) & T_RMASK));
+    const uint32_t x = __funnelshift_l(b, a, q);
+    const uint32_t e = lds_u16<0>(mad_hi(x & ~((1u << (32 - LUT_BITS)) - 1u), 1u << (LUT_BITS + 1), lutb));
+#ifdef RSB200_EMU
+    if (e == 0u || q > p1)
+      abort(); // the re-walk left the path of the unit: the ring no longer held its words
+#endif
+    if (e == 0u)
+      break;
+    q += e >> 10;
+    ++k;
+  }
+  return k;
+}
+
 // "does any lane that is here with me want a fill step" -- a scheduling hint only: results do
 // not depend on it (a lane that runs dry fills on its own, s_fill_now)
 #ifdef RSB200_EMU
@@ -328,25 +353,59 @@ __device__ __forceinline__ bool s_any(bool want) { return __any_sync(__activemas
 
 // The same without control flow, for the straight-line unit: a code the LUT does not resolve
 // (longer than LUT_BITS, SSSS = 16, corrupt) leaves p where it is, so every later symbol of the
-// unit sees the same window and -- LOOKING IT UP IN THE SAME TABLE -- misses too; nok counts the
-// symbols before the first miss and the unit is finished symbol by symbol (S_SYM) from there.
+// unit sees the same window and -- LOOKING IT UP IN THE SAME TABLE -- misses too: the unit is
+// complete iff its last symbol hit; otherwise the symbols before the first miss are counted
+// (s_count_hits) and the unit is finished symbol by symbol (S_SYM) from there.
 // Without a branch per symbol the eight decodes are one basic block: the difference arithmetic of
 // symbol k is scheduled into the latency of symbol k+1's LUT load.  A segment whose components
 // use DIFFERENT tables does not take this form (a window that starts with a long code of one
 // table can be a short code of the other: the miss would not stick); it goes symbol by symbol.
+// RSB200_S_PIPE (A/B): the unit is bound by the ALU pipe (SHF / LOP3 / LEA / IADD3: one warp
+// instruction every two cycles; ncu at 256 frames: 76 % of its cycles against 25 % of the FMA pipe's,
+// profiles/r2_ncu_ljpeg.md).  ptxas turns every multiply by a constant power of two back into ALU
+// forms, so the multipliers come from the constant bank (s_pipe_k), where it cannot see them:
+//   1: LUT address = (x >> 21) * 2 + base as SHF + IMAD (was LOP3 + LEA.HI); the sign mask from
+//      tt + 0x80000000 (IMAD) instead of ~tt (LOP3)
+//   2: + p + (e >> 10) and e >> 5 as IMAD.HI (were LEA.HI, SHF)
+#ifndef RSB200_S_PIPE
+#define RSB200_S_PIPE 0
+#endif
+#ifdef RSB200_EMU
+static const uint32_t s_pipe_k[4] = {2u, 1u, 1u << 22, 1u << 27};
+__device__ __forceinline__ uint32_t s_mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+#else
+__constant__ uint32_t s_pipe_k[4] = {2u, 1u, 1u << 22, 1u << 27};
+__device__ __forceinline__ uint32_t s_mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+#endif
+#if RSB200_S_PIPE >= 1
+#define S_LUT_ADDR(x, base) s_mad_lo((x) >> (32 - LUT_BITS), s_pipe_k[0], (base))
+#define S_SIGN_MASK(tt) ((uint32_t)((int32_t)s_mad_lo((tt), s_pipe_k[1], 0x80000000u) >> 31))
+#else
+#define S_LUT_ADDR(x, base) mad_hi((x) & ~((1u << (32 - LUT_BITS)) - 1u), 1u << (LUT_BITS + 1), (base))
+#define S_SIGN_MASK(tt) ((uint32_t)((int32_t)~(tt) >> 31))
+#endif
+#if RSB200_S_PIPE >= 2
+#define S_ADD_TOTAL(e, p) mad_hi((e), s_pipe_k[2], (p))
+#define S_SSSS(e) mad_hi((e), s_pipe_k[3], 0u)
+#else
+#define S_ADD_TOTAL(e, p) ((p) + ((e) >> 10))
+#define S_SSSS(e) ((e) >> 5)
+#endif
 #define S_SYMF(c, val)                                                          \
   do {                                                                          \
     const uint32_t x_ = __funnelshift_l(nxt, cur, p);                           \
-    const uint32_t e_ = lds_u16<0>(                                             \
-        mad_hi(x_ & ~((1u << (32 - LUT_BITS)) - 1u), 1u << (LUT_BITS + 1), lutb[c])); \
-    const bool hit_ = e_ != 0u;                                                 \
-    nok += hit_ ? 1u : 0u;                                                      \
+    const uint32_t e_ = lds_u16<0>(S_LUT_ADDR(x_, lutb[c]));                    \
+    elast = e_;                                                                 \
     const uint32_t tt_ = __funnelshift_l(0u, x_, e_);                           \
-    const uint32_t f_ = (uint32_t)((int32_t)~tt_ >> 31);                        \
-    uint32_t d_ = __funnelshift_l(tt_, f_, e_ >> 5) - f_;                       \
-    d_ = hit_ ? d_ : 0u;                                                        \
-    last_tl = e_ >> 10;                                                         \
-    const uint32_t pn_ = p + last_tl;                                           \
+    const uint32_t f_ = S_SIGN_MASK(tt_);                                       \
+    /* a miss (e_ = 0) needs no select: both shifts are by 0, d_ = f_ - f_ */   \
+    const uint32_t d_ = __funnelshift_l(tt_, f_, S_SSSS(e_)) - f_;              \
+    const uint32_t pn_ = S_ADD_TOTAL(e_, p);                                    \
+    last_tl = pn_ - p;                                                          \
     if ((pn_ ^ p) & 32u) {                                                      \
       cur = nxt;                                                                \
       nxt = nn;                                                                 \
@@ -365,7 +424,7 @@ __device__ __forceinline__ bool s_any(bool want) { return __any_sync(__activemas
     const uint32_t x_ = __funnelshift_l(nxt, cur, p);                           \
     const uint32_t e_ = lds_u32<0>(                                             \
         mad_hi(x_ & ~((1u << (32 - LUT_BITS)) - 1u), 1u << (LUT_BITS + 2), lut32b[c])); \
-    nok += e_; /* hits in bits 19:16 */                                         \
+    elast += e_; /* hits in bits 19:16 */                                       \
     const uint32_t tt_ = __funnelshift_l(0u, x_, e_);                           \
     const uint32_t f_ = (uint32_t)((int32_t)~tt_ >> 31);                        \
     const uint32_t d_ = __funnelshift_l(tt_, f_, mad_hi(e_, 1u << 24, 0u)) - f_; \
@@ -532,14 +591,11 @@ stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp
       // 8 samples, straight line (component of sample k = k % G)
       uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
 #if RSB200_S_STRAIGHT
-      uint32_t nok = 0;
-#if RSB200_S_LUT32
-#define S_NOK ((nok >> 16) & 15u)
-#else
-#define S_NOK nok
-#endif
       uint32_t k_ = 0; // samples of the unit that are done
       if (G == 1 || one_table) {
+        // a miss repeats (same window, same table): the unit is complete iff its LAST symbol hit
+        const uint32_t p0 = p;
+        uint32_t elast = 0;
         S_SYMF(0 % G, v0);
         S_SYMF(1 % G, v1);
         S_SYMF(2 % G, v2);
@@ -548,7 +604,13 @@ stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp
         S_SYMF(5 % G, v5);
         S_SYMF(6 % G, v6);
         S_SYMF(7 % G, v7);
-        k_ = S_NOK;
+#if RSB200_S_LUT32
+        k_ = (elast >> 16) & 15u; // (hit flags added up)
+#else
+        k_ = 8u;
+        if (elast == 0u)
+          k_ = s_count_hits(ringb, lutb[0], p0, p);
+#endif
       }
       if (k_ != 8u) { // rare: the symbols from the first miss on, one by one
         if (k_ <= 0u)
@@ -567,7 +629,6 @@ stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp
           S_SYM(6 % G, v6);
         S_SYM(7 % G, v7);
       }
-#undef S_NOK
 #else
       S_SYM(0 % G, v0);
       S_SYM(1 % G, v1);

@@ -24,14 +24,15 @@ DEPS = [SRC] + [os.path.join(HERE, "..", "rawspeed_b200", "csrc", f)
                 for f in ("dngop_core.h", "dngop_host.h")]
 
 
-@pytest.fixture(scope="module", params=["", "_v1"])
+@pytest.fixture(scope="module", params=["", "_v1", "_v2"])
 def emu(request):
-    """Both versions of the opcode walk: the one the library ships (the second, since r2_run22) and
-    the first one behind -DRSB200_DNGOP_V1 (both validated on the GPU)."""
+    """The versions of the opcode walk: the one the library ships (the third -- closed-form hit masks --
+    where a pixel is one sample, the second elsewhere), the second alone (-DRSB200_DNGOP_V2) and the
+    first one (-DRSB200_DNGOP_V1)."""
     out = OUT % request.param
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        flags = ["-DRSB200_DNGOP_V1"] if request.param else []
+        flags = ["-DRSB200_DNGOP" + request.param.upper()] if request.param else []
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared"] + flags + ["-o", out, SRC])
     lib = C.CDLL(out)
     lib.dngop_emu_run.argtypes = [C.c_void_p, C.POINTER(DngOpJob), C.c_int, C.POINTER(DngOp), C.c_int,

@@ -27,13 +27,14 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h")] + [
     os.path.join(CSRC, f) for f in ("ljpeg_stream.cuh", "ljpeg_lane.cuh", "ljpeg_host.h", "ljpeg_types.h")]
 
 
-@pytest.fixture(scope="module", params=["default", "st256", "lut32"])
+@pytest.fixture(scope="module", params=["default", "st256", "lut32", "pipe2"])
 def emu(request):
     """The instantiations of the kernel: 128-bit output stores, 256-bit ones (two units per store), and
-    the 32-bit LUT entries of the straight-line decode."""
+    the 32-bit LUT entries of the straight-line decode, and the FMA-pipe forms of its field arithmetic."""
     out = OUT if request.param == "default" else OUT.replace(".so", "_%s.so" % request.param)
     flags = {"default": [], "st256": ["-DRSB200_EMU_WIDE=true"],
-             "lut32": ["-DRSB200_EMU_WIDE=true", "-DRSB200_S_LUT32=1"]}[request.param]
+             "lut32": ["-DRSB200_EMU_WIDE=true", "-DRSB200_S_LUT32=1"],
+             "pipe2": ["-DRSB200_EMU_WIDE=true", "-DRSB200_S_PIPE=2"]}[request.param]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",

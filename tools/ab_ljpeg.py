@@ -12,6 +12,7 @@ with two Huffman tables (phase-carrying synchronisation), LJPEG batches and the
 Environment: AB_FRAMES=8,32,128   batch sizes (frames of the 45 MP DNG in one plan)
              AB_PATHS=fused,thread|auto   kernel path(s) per batch (RSB200_LJPEG_PATH)
              AB_KERNELS=1         per-kernel durations of one run (torch profiler / CUPTI)
+             AB_ONLY=batch        only the single-table frame and its batches (no second table, no CR2)
 """
 import json
 import os
@@ -59,7 +60,10 @@ def one():
 
     img = synth.image_model(W, H, 12345)
     out_pitch = rs.image_pitch(W)
+    only_batch = os.environ.get("AB_ONLY") == "batch"
     for label, kw in (("dng1", {}), ("dng1_2tab", dict(tabs=synth.default_tables(2), tab_of_comp=[0, 1]))):
+        if only_batch and label != "dng1":
+            continue
         t = synth.make_dng_ljpeg(img, 256, 256, **kw)
         tabs, scans = dng_ljpeg_scans(t, out_pitch)
         plan = rs.ljpeg_plan(ctx, tabs.tabs, scans)
@@ -121,6 +125,8 @@ def one():
     # one shared table (positions-only synchronisation) and two tables
     for label, hts, sel in (("cr2_1tab", synth.default_tables(1), [0, 0]),
                             ("cr2_2tab", synth.default_tables(2), [0, 1])):
+        if only_batch:
+            break
         blob = port.cr2_encode(cimg, cw, (2, 1, 1), (3360, 4480), (3, 2240, 2240), 14, hts, sel)
         ts = TableSet()
         job = cr2_job(blob, cw, ch, (2, 1, 1), (3, 2240, 2240), cimg.shape[1] * 2, ts)
