@@ -191,9 +191,51 @@ __device__ __noinline__ uint2 s_find_marker(const uint8_t* __restrict__ gbase, u
   return make_uint2(c, cc0); // (not reached: the caller saw a non-zero removed byte)
 }
 
+// multipliers ptxas cannot see (constant bank): see RSB200_S_PIPE below
+#ifdef RSB200_EMU
+static const uint32_t s_pipe_k[4] = {2u, 1u, 1u << 22, 1u << 27};
+__device__ __forceinline__ uint32_t s_mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+#else
+__constant__ uint32_t s_pipe_k[4] = {2u, 1u, 1u << 22, 1u << 27};
+__device__ __forceinline__ uint32_t s_mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+#endif
+
 // One block the fast way (4 words); returns the OR of the removed bytes (non-zero: a marker).
+// RSB200_S_FILL2 (A/B): the add of the FF test on the FMA pipe, and the byte count of the
+// accumulator kept unwrapped inside the block (the shifts take it modulo 32 by themselves, "a word is
+// full" is a change of bit 5) and wrapped once at the end.
+#ifndef RSB200_S_FILL2
+#define RSB200_S_FILL2 0
+#endif
 __device__ __forceinline__ uint32_t s_fast_block(SFill& f, uint32_t ringb, uint32_t selb, const uint4& q) {
   uint32_t chk = 0;
+#if RSB200_S_FILL2
+  uint32_t u = f.sh;
+#define S_WORD(w)                                                                        \
+  do {                                                                                   \
+    const uint32_t ffm_ = s_mad_lo((w) & 0x7F7F7F7Fu, s_pipe_k[1], 0x01010101u) & (w) & 0x80808080u; \
+    const uint32_t rem_ = __funnelshift_l(f.pffm, ffm_, 8);                              \
+    f.pffm = ffm_;                                                                       \
+    chk |= (w) & prmt(rem_, 0u, 0xBA98u); /* sign replication: FF where a flag is */     \
+    const uint32_t e_ = lds_u32<0>((mad_hi(rem_, S_IDXMUL, 0u) & 0x3Cu) | selb);         \
+    const uint32_t out_ = prmt((w), 0u, e_);                                             \
+    const uint32_t hi_ = f.acc | __funnelshift_r(out_, 0u, u);                           \
+    const uint32_t lo_ = __funnelshift_r(0u, out_, u);                                   \
+    const uint32_t tot_ = u + (e_ >> 16);                                                \
+    if ((tot_ ^ u) & 32u) {                                                              \
+      sts_u32<0>(ringb + (f.wo & T_RMASK), hi_);                                         \
+      f.wo += T_WSTRIDE;                                                                 \
+      f.acc = lo_;                                                                       \
+    } else {                                                                             \
+      f.acc = hi_;                                                                       \
+    }                                                                                    \
+    u = tot_;                                                                            \
+  } while (0)
+#else
 #define S_WORD(w)                                                                        \
   do {                                                                                   \
     const uint32_t ffm_ = (((w) & 0x7F7F7F7Fu) + 0x01010101u) & (w) & 0x80808080u;       \
@@ -214,11 +256,15 @@ __device__ __forceinline__ uint32_t s_fast_block(SFill& f, uint32_t ringb, uint3
     }                                                                                    \
     f.sh = tot_ & 31u;                                                                   \
   } while (0)
+#endif
   S_WORD(q.x);
   S_WORD(q.y);
   S_WORD(q.z);
   S_WORD(q.w);
 #undef S_WORD
+#if RSB200_S_FILL2
+  f.sh = u & 31u;
+#endif
   return chk;
 }
 
@@ -367,19 +413,10 @@ __device__ __forceinline__ bool s_any(bool want) { return __any_sync(__activemas
 //   1: LUT address = (x >> 21) * 2 + base as SHF + IMAD (was LOP3 + LEA.HI); the sign mask from
 //      tt + 0x80000000 (IMAD) instead of ~tt (LOP3)
 //   2: + p + (e >> 10) and e >> 5 as IMAD.HI (were LEA.HI, SHF)
+// Measured (r2_run24, 256 frames, bit-exact): 0: 17.83 ms, 1: 17.18 ms (the default), 2: 18.26 ms
+// (IMAD.HI with a 64-bit addend costs two FMA-pipe instructions and is the slower form).
 #ifndef RSB200_S_PIPE
-#define RSB200_S_PIPE 0
-#endif
-#ifdef RSB200_EMU
-static const uint32_t s_pipe_k[4] = {2u, 1u, 1u << 22, 1u << 27};
-__device__ __forceinline__ uint32_t s_mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
-#else
-__constant__ uint32_t s_pipe_k[4] = {2u, 1u, 1u << 22, 1u << 27};
-__device__ __forceinline__ uint32_t s_mad_lo(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t r;
-  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-  return r;
-}
+#define RSB200_S_PIPE 1
 #endif
 #if RSB200_S_PIPE >= 1
 #define S_LUT_ADDR(x, base) s_mad_lo((x) >> (32 - LUT_BITS), s_pipe_k[0], (base))

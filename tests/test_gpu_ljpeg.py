@@ -101,6 +101,27 @@ def test_two_tables_long_code_of_one_is_a_short_code_of_the_other(ctx):
     _check_tiles(ctx, img, 256, 32, ncomp=4, tabs=tabs, tab_of_comp=[0, 1, 0, 1])
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_tables_and_components(ctx, seed):
+    """Differential fuzz (the CPU replays run the same generator, tests/test_ljpeg_stream_emu.py): 1 / 2 / 4
+    components, one to four random COMPLETE canonical codes of up to 16 bits, noise from a few bits to the
+    full 14-bit range."""
+    from test_ljpeg_stream_emu import _random_table
+    rng = np.random.default_rng(7000 + seed)
+    ncomp = int(rng.choice([1, 2, 4]))
+    ntab = int(rng.integers(1, min(ncomp, 4) + 1))
+    bits = int(rng.choice([3, 6, 10, 14]))
+    h, tw = int(rng.choice([8, 16, 24])), int(rng.choice([64, 128, 256]))
+    w = tw * int(rng.integers(1, 3))
+    img = (8192 + rng.integers(0, 1 << bits, (h, w)) - (1 << bits) // 2).astype(np.uint16) & 0x3FFF
+    tabs = [_random_table(rng, 16) for _ in range(ntab)]
+    tab_of_comp = [int(rng.integers(0, ntab)) for _ in range(ncomp)]
+    for t in range(ntab):
+        if t not in tab_of_comp:
+            tab_of_comp[t % ncomp] = t
+    _check_tiles(ctx, img, tw, h, ncomp=ncomp, tabs=tabs, tab_of_comp=tab_of_comp)
+
+
 def test_restart_intervals(ctx):
     img = synth.image_model(160, 96, 17)
     _check_tiles(ctx, img, 80, 48, restart_rows=1)

@@ -240,3 +240,18 @@ def test_bad_huffman_code(emu):
     for R in (1, 2):
         (status, _), = run_emu(emu, blob, tabs.tabs, scans[:1], port.new_image(256, 32), R=R)
         assert status == 1
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_tables(emu, seed):
+    """Differential fuzz with random COMPLETE canonical codes (lengths up to 16 bits, values in random
+    order): the self-synchronising parse must lock onto the true symbol boundaries whatever the code
+    looks like, 1 / 2 / 4 components, noise from a few bits to the full 14-bit range."""
+    from test_ljpeg_stream_emu import _random_table
+    rng = np.random.default_rng(9000 + seed)
+    ncomp = int(rng.choice([1, 2, 4]))
+    bits = int(rng.choice([3, 6, 10, 14]))
+    h, tw = int(rng.choice([16, 32])), int(rng.choice([128, 256]))
+    w = tw * int(rng.integers(1, 3))
+    img = (8192 + rng.integers(0, 1 << bits, (h, w)) - (1 << bits) // 2).astype(np.uint16) & 0x3FFF
+    check_tiles(emu, img, tw, h, Rs=(1,), ncomp=ncomp, tabs=[_random_table(rng, 16)])
