@@ -1309,7 +1309,7 @@ def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
                                         "sample": "PanasonicV%dDecompressor::decompress (OpenMP), 1 frame, best of 3" % ver}
         out["8(f)4 PanasonicV%dDecompressor %dx%d %d-bit" % (ver, w, h, bps)] = ent
         del plan, d_in, d_out
-    # ---- PhaseOneDecompressor, 11608x8708 (IQ3 100MP class): one thread per row ----
+    # ---- PhaseOneDecompressor, 11608x8708 (IQ3 100MP class): group headers per row, pixels in parallel ----
     w, h = 11608, 8708
     rowimg = (synth.image_model(w, 4, seed=31, bits=14)).astype(np.uint16)
     rows4 = [np.frombuffer(synth.phaseone_row(rowimg[k]), dtype=np.uint8) for k in range(4)]
@@ -1333,12 +1333,16 @@ def bench_codecs(torch, rs, ctx, port, synth, args, dist, peak):
     plan.run((d_in.data_ptr(), blob.size), d_out)
     res = plan.results()
     got = d_out.cpu().numpy().view(np.uint16).reshape(h, rs.image_pitch(w) // 2)
-    exact = res[0][0] == 0 and all(bool(np.array_equal(got[r, :w], rowimg[r % 4])) for r in (0, 1, 2, 3, h - 1))
+    exact = res[0][0] == 0 and all(bool(np.array_equal(got[k::4, :w], np.broadcast_to(rowimg[k], (len(range(k, h, 4)), w))))
+                                   for k in range(4))   # every row of the frame
     ms = time_steps(torch, lambda: plan.run((d_in.data_ptr(), blob.size), d_out), 3, 1, dist)
     per = ms / 3
     ent = {"MPixels/s": w * h / (per * 1e-3) / 1e6, "ms_per_frame": per, "bit_exact": bool(exact),
            "compressed_bytes_per_pixel": blob.size / (w * h),
-           "kernel": "p1_kernel (one thread per row: 8708 threads, latency bound)"}
+           "kernel": ("p1_kernel_v2 (one thread per row: 8708 threads, latency bound)"
+                      if os.environ.get("RSB200_P1") in ("1", "2") else
+                      "p1_walk_kernel (one thread per row reads the group headers) + p1_decode_kernel (one warp "
+                      "per row, 32 groups per step, segmented scan of the predictors)")}
     if not args.skip_cpu and rank0:
         import oracle
         if oracle.HAVE_REF:

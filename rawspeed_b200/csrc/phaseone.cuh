@@ -14,7 +14,10 @@
 // is part of the result).
 #pragma once
 
+#ifndef RSB200_EMU
 #include "common.cuh"
+#endif
+#include <stdint.h>
 
 namespace rsb200 {
 
@@ -50,6 +53,7 @@ __device__ __forceinline__ uint32_t p1_chunk(const uint8_t* __restrict__ base, u
   return v;
 }
 
+#ifndef RSB200_EMU
 __global__ void __launch_bounds__(P1_NT)
     p1_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
               const P1StripDev* __restrict__ strips, uint32_t nstrips,
@@ -231,5 +235,253 @@ __global__ void __launch_bounds__(P1_NT)
   if (bad && live)
     atomicOr(bad_jobs + st.job, 1u);
 }
+
+#endif // !RSB200_EMU (the first two versions have no CPU replay; the third is developed against one)
+
+// ---- third version (round 2): the pixels of a row in parallel ----
+// One thread per row leaves the machine almost empty (a 101 MP frame has 8708 rows: 272 warps on 148
+// SMs, every one walking 11608 pixels one after the other: 3.9 ms, 26 GPix/s).  What is serial in a
+// row is only WHERE its groups of 8 pixels start: the two length codes in front of a group (2 .. 12
+// bits) say how long it is.  So the row is decoded in two steps:
+//   p1_walk_kernel    one thread per row reads nothing but the group headers and writes, per group,
+//                     one word: bit position of its first pixel | len0 | len1 | header bits
+//                     (1451 short steps per row instead of 11608 long ones);
+//   p1_decode_kernel  one warp per row, 32 groups per step: the bytes of the 32 groups are staged in
+//                     shared memory with coalesced loads, a lane extracts the 8 fields of its group,
+//                     and the predictors -- "pred += difference" per column parity, restarted by every
+//                     group whose length is 14 (raw 16-bit values) -- become a segmented warp scan over
+//                     (restarts, sum) pairs with a carry from step to step; a lane stores its 8 pixels.
+// The over-read rule in closed form as in the second version: a pixel may start at bit T <= tmax = 32 *
+// ((size + 8) / 4) (the group's first pixel is checked where its header starts); positions grow along
+// the row, so a pair is stored iff its second pixel passes, and the row has failed iff its last pixel
+// does not.  A 1 bit in the length prefixes at column 0, or a strip below 4 bytes, fails the row before
+// anything is stored.
+constexpr int P1W_NT = 64;          // walk: rows per CTA
+constexpr int P1D_NT = 128;         // decode: 4 warps = 4 rows per CTA
+constexpr int P1_STAGE_WORDS = 148; // 32 groups x (12 + 8 x 16) bits = 140 words, + the funnel's second word
+constexpr uint32_t P1_POS_MASK = 0xFFFFFu; // a row has < 2^20 bits (width <= 11976: 209 580)
+
+// 32 bits of the strip from bit p (MSB32 order: 32-bit little-endian chunks, most significant bit first)
+__device__ __forceinline__ uint32_t p1_window(const uint8_t* __restrict__ base, uint32_t size, uint32_t p) {
+  const uint32_t c = p >> 5;
+  return __funnelshift_l(p1_chunk(base, size, 4u * c + 4u), p1_chunk(base, size, 4u * c), p);
+}
+__device__ __forceinline__ uint32_t p1_bits_of_len(uint32_t len) { return (len == 14u || len == 0u) ? 16u : len; }
+
+// one length code at the top of x: .x = bits used, .y = new length (0: keep), .z = a 1 bit was met
+// before five zeros (fatal at column 0).  PhaseOneDecompressor.cpp:104-118
+__device__ __forceinline__ void p1_len_code(uint32_t x, uint32_t& used, uint32_t& len, bool& one) {
+  const uint32_t j = (uint32_t)min(__clz((int)x), 5);
+  one = j < 5u;
+  if (j == 0u) {
+    used = 1u;
+    return;
+  }
+  // j zeros, (the 1 that ended them when j < 5), one more bit: length[2 * (j - 1) + bit]
+  used = j < 5u ? j + 2u : 6u;
+  const uint32_t bit = (x >> (32u - used)) & 1u;
+  const uint32_t idx = 2u * (j - 1u) + bit;
+  len = (uint32_t)((0xDEC5AB9678ull >> (4u * idx)) & 15u);
+}
+
+__device__ __forceinline__ void
+p1_walk_entry(const uint8_t* __restrict__ in, const P1StripDev* __restrict__ strips, uint32_t nstrips,
+              const P1JobDev* __restrict__ jobs, uint32_t gstride, uint32_t* __restrict__ gdesc,
+              uint32_t* __restrict__ rowflag) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nstrips)
+    return;
+  const P1StripDev st = strips[s];
+  const P1JobDev jb = jobs[st.job];
+  const uint8_t* base = in + st.in_offset;
+  const uint32_t size = st.in_size;
+  const uint32_t ngroups = jb.width >> 3;
+  uint32_t* desc = gdesc + (uint64_t)s * gstride;
+  if (size < 4u) { // BitStreamer ctor: "Bit stream size is smaller than MaxProcessBytes"
+    rowflag[s] = 1u;
+    return;
+  }
+  uint32_t p = 0, len0 = 0, len1 = 0;
+  bool fatal = false;
+  for (uint32_t g = 0; g < ngroups; ++g) {
+    const uint32_t x = p1_window(base, size, p);
+    uint32_t u0, u1;
+    bool o0, o1;
+    p1_len_code(x, u0, len0, o0);
+    p1_len_code(x << u0, u1, len1, o1);
+    if (g == 0u && (o0 || o1))
+      fatal = true; // "Can not initialize lengths. Data is corrupt."
+    const uint32_t hdr = u0 + u1, p0 = p + hdr;
+    desc[g] = (p0 & P1_POS_MASK) | (len0 << 20) | (len1 << 24) | (hdr << 28);
+    p = p0 + 4u * (p1_bits_of_len(len0) + p1_bits_of_len(len1));
+  }
+  desc[ngroups] = p; // where the last width % 8 pixels (raw) start
+  rowflag[s] = fatal ? 1u : 0u;
+}
+
+struct P1DecodeShared {
+  uint32_t stage[P1D_NT / 32][P1_STAGE_WORDS];
+};
+
+// 1 <= n <= 16 bits at bit `rel` of the staged words
+__device__ __forceinline__ uint32_t p1_field(const uint32_t* stage, uint32_t rel, uint32_t n) {
+  const uint32_t wi = rel >> 5;
+  return __funnelshift_l(stage[wi + 1u], stage[wi], rel) >> (32u - n);
+}
+
+// inclusive segmented scan over the lanes of (restart, value): a lane's result is absolute when some
+// lane at or before it restarted, else a sum still to be added to the carry of the step before
+__device__ __forceinline__ void p1_seg_scan(uint32_t& r, uint32_t& a, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t ru = __shfl_up_sync(0xFFFFFFFFu, r, d);
+    const uint32_t au = __shfl_up_sync(0xFFFFFFFFu, a, d);
+    if (lane >= d) {
+      if (!r)
+        a += au;
+      r |= ru;
+    }
+  }
+}
+
+__device__ __forceinline__ void
+p1_decode_entry(P1DecodeShared& sh, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                const P1StripDev* __restrict__ strips, uint32_t nstrips, const P1JobDev* __restrict__ jobs,
+                uint32_t gstride, const uint32_t* __restrict__ gdesc, const uint32_t* __restrict__ rowflag,
+                uint32_t* __restrict__ bad_jobs) {
+  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = (int)(threadIdx.x & 31u);
+  if (s >= nstrips)
+    return;
+  const P1StripDev st = strips[s];
+  const P1JobDev jb = jobs[st.job];
+  if (rowflag[s]) {
+    if (lane == 0)
+      atomicOr(bad_jobs + st.job, 1u);
+    return;
+  }
+  const uint8_t* base = in + st.in_offset;
+  const uint32_t size = st.in_size, w = jb.width;
+  const uint32_t ngroups = w >> 3;
+  const uint32_t tmax = 32u * ((size + 8u) / 4u);
+  const uint32_t* desc = gdesc + (uint64_t)s * gstride;
+  uint32_t* o32 = reinterpret_cast<uint32_t*>(out + jb.out_offset + (uint64_t)st.row * jb.out_pitch);
+  uint32_t* stage = sh.stage[threadIdx.x >> 5];
+  uint32_t run0 = 0, run1 = 0; // the two predictors behind the groups done so far
+  bool over = false;
+  for (uint32_t g0 = 0; g0 < ngroups; g0 += 32u) {
+    const uint32_t g = g0 + (uint32_t)lane;
+    const bool have = g < ngroups;
+    const uint32_t d = have ? __ldg(desc + g) : 0u;
+    const uint32_t p0 = d & P1_POS_MASK, l0 = (d >> 20) & 15u, l1 = (d >> 24) & 15u, hdr = d >> 28;
+    const uint32_t b0 = p1_bits_of_len(l0), b1 = p1_bits_of_len(l1);
+    const uint32_t pend = p0 + 4u * (b0 + b1);
+    // the words that hold the groups of this step
+    const uint32_t nhere = min(32u, ngroups - g0);
+    const uint32_t wfirst = __shfl_sync(0xFFFFFFFFu, p0, 0) >> 5;
+    const uint32_t wlast = (__shfl_sync(0xFFFFFFFFu, pend, (int)nhere - 1) + 31u) >> 5;
+    __syncwarp();
+    for (uint32_t i = (uint32_t)lane; i <= wlast - wfirst + 1u; i += 32u)
+      stage[i] = p1_chunk(base, size, 4u * (wfirst + i));
+    __syncwarp();
+    uint32_t c[8];
+    uint32_t tlast = 0, t1 = 0, t3 = 0, t5 = 0;
+    {
+      uint32_t rel = p0 - 32u * wfirst;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t n = (k & 1) ? b1 : b0, len = (k & 1) ? l1 : l0;
+        uint32_t v = have ? p1_field(stage, rel, n) : 0u;
+        if (n != 16u)
+          v = v + 1u - (1u << (len - 1u));
+        c[k] = v;
+        if (k == 1) t1 = rel;
+        if (k == 3) t3 = rel;
+        if (k == 5) t5 = rel;
+        if (k == 7) tlast = rel;
+        rel += n;
+      }
+    }
+    const uint32_t off = 32u * wfirst; // (positions of the odd pixels, for the over-read rule)
+    t1 += off; t3 += off; t5 += off; tlast += off;
+    (void)hdr;
+    // per parity: prefix inside the group, then the scan over the groups
+    const uint32_t raw0 = (have && b0 == 16u) ? 1u : 0u, raw1 = (have && b1 == 16u) ? 1u : 0u;
+    if (!raw0) {
+      c[2] += c[0];
+      c[4] += c[2];
+      c[6] += c[4];
+    }
+    if (!raw1) {
+      c[3] += c[1];
+      c[5] += c[3];
+      c[7] += c[5];
+    }
+    uint32_t r0 = raw0, a0 = have ? c[6] : 0u, r1 = raw1, a1 = have ? c[7] : 0u;
+    p1_seg_scan(r0, a0, lane);
+    p1_seg_scan(r1, a1, lane);
+    // what the predictors hold behind lane i: absolute after a restart, else carry + sum
+    const uint32_t out0 = r0 ? a0 : run0 + a0, out1 = r1 ? a1 : run1 + a1;
+    uint32_t base0 = __shfl_up_sync(0xFFFFFFFFu, out0, 1), base1 = __shfl_up_sync(0xFFFFFFFFu, out1, 1);
+    if (lane == 0) {
+      base0 = run0;
+      base1 = run1;
+    }
+    run0 = __shfl_sync(0xFFFFFFFFu, out0, 31);
+    run1 = __shfl_sync(0xFFFFFFFFu, out1, 31);
+    if (have) {
+      if (!raw0) {
+        c[0] += base0;
+        c[2] += base0;
+        c[4] += base0;
+        c[6] += base0;
+      }
+      if (!raw1) {
+        c[1] += base1;
+        c[3] += base1;
+        c[5] += base1;
+        c[7] += base1;
+      }
+      uint32_t* o = o32 + 4u * g;
+      if (t1 <= tmax)
+        o[0] = (c[0] & 0xFFFFu) | (c[1] << 16);
+      if (t3 <= tmax)
+        o[1] = (c[2] & 0xFFFFu) | (c[3] << 16);
+      if (t5 <= tmax)
+        o[2] = (c[4] & 0xFFFFu) | (c[5] << 16);
+      if (tlast <= tmax)
+        o[3] = (c[6] & 0xFFFFu) | (c[7] << 16);
+      over = over || tlast > tmax;
+    }
+  }
+  // the last width % 8 pixels: raw 16-bit values (an even number: the width is even)
+  const uint32_t ntail = w & 7u;
+  if ((uint32_t)lane * 2u < ntail) {
+    const uint32_t pt = __ldg(desc + ngroups) + 32u * (uint32_t)lane; // my pair
+    const uint32_t a = p1_window(base, size, pt) >> 16, b = p1_window(base, size, pt + 16u) >> 16;
+    if (pt + 16u <= tmax)
+      o32[4u * ngroups + (uint32_t)lane] = a | (b << 16);
+    over = over || pt + 16u > tmax;
+  }
+  if (__ballot_sync(0xFFFFFFFFu, over) != 0u && lane == 0)
+    atomicOr(bad_jobs + st.job, 1u);
+}
+
+#ifndef RSB200_EMU
+__global__ void __launch_bounds__(P1W_NT)
+    p1_walk_kernel(const uint8_t* __restrict__ in, const P1StripDev* __restrict__ strips, uint32_t nstrips,
+                   const P1JobDev* __restrict__ jobs, uint32_t gstride, uint32_t* __restrict__ gdesc,
+                   uint32_t* __restrict__ rowflag) {
+  p1_walk_entry(in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+}
+__global__ void __launch_bounds__(P1D_NT)
+    p1_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                     const P1StripDev* __restrict__ strips, uint32_t nstrips,
+                     const P1JobDev* __restrict__ jobs, uint32_t gstride, const uint32_t* __restrict__ gdesc,
+                     const uint32_t* __restrict__ rowflag, uint32_t* __restrict__ bad_jobs) {
+  __shared__ P1DecodeShared sh;
+  p1_decode_entry(sh, in, out, strips, nstrips, jobs, gstride, gdesc, rowflag, bad_jobs);
+}
+#endif
 
 } // namespace rsb200

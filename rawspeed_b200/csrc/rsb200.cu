@@ -276,6 +276,10 @@ struct rsb200_plan {
   uint32_t hass_nseg = 0, hass_ncta = 0, hass_rows = 0;
   P1StripDev* d_p1_strips = nullptr;
   P1JobDev* d_p1_jobs = nullptr;
+  uint32_t* d_p1_gdesc = nullptr;   // third version: one word per group of 8 pixels (+ 1 per row)
+  uint32_t* d_p1_rowflag = nullptr; // ... and per row: failed before anything was stored
+  uint32_t p1_gstride = 0;          // words of gdesc per row
+  int p1_ver = 3;                   // which version of the kernel this plan runs (RSB200_P1)
   uint32_t p1_nstrips = 0;
   // Sony ARW2
   Arw2JobDev* d_arw2_jobs = nullptr;
@@ -1150,6 +1154,14 @@ static cudaError_t run_hasselblad(const rsb200_plan* p, const uint8_t* in, uint8
 // ------------------------------------------------------------------
 // Phase One (K8)
 // ------------------------------------------------------------------
+// RSB200_P1 = 1 / 2 select the first (per-lane refills) / second (a thread per row, loads at group
+// boundaries) version for A/B runs; default: the third (group headers walked per row, pixels in parallel)
+// (read when a plan is created)
+static int p1_version() {
+  const char* e = getenv("RSB200_P1");
+  return (e && (e[0] == '1' || e[0] == '2') && !e[1]) ? e[0] - '0' : 3;
+}
+
 extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseone_job* jobs,
                                            int njobs, const rsb200_phaseone_strip* strips,
                                            int nstrips, rsb200_plan** out) {
@@ -1201,7 +1213,13 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
                                                       2ull * j.width));
   }
   p->p1_nstrips = (uint32_t)ds.size();
+  for (int i = 0; i < njobs; ++i)
+    p->p1_gstride = std::max<uint32_t>(p->p1_gstride, jobs[i].width / 8u + 1u);
   cudaError_t e = rsb_dev_alloc((void**)&p->d_p1_strips, sizeof(P1StripDev) * ds.size());
+  if (e == cudaSuccess)
+    e = rsb_dev_alloc((void**)&p->d_p1_gdesc, sizeof(uint32_t) * (size_t)p->p1_gstride * ds.size());
+  if (e == cudaSuccess)
+    e = rsb_dev_alloc((void**)&p->d_p1_rowflag, sizeof(uint32_t) * ds.size());
   if (e == cudaSuccess)
     e = cudaMemcpy(p->d_p1_strips, ds.data(), sizeof(P1StripDev) * ds.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
@@ -1216,7 +1234,8 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
     rsb200_plan_destroy(p);
     return set_err(ctx, RSB200_ERR_CUDA, "phaseone plan upload failed: %s", cudaGetErrorString(e));
   }
-  p->launches_per_run = 1;
+  p->p1_ver = p1_version();
+  p->launches_per_run = p->p1_ver == 3 ? 2 : 1;
   *out = p;
   return RSB200_OK;
 }
@@ -1226,18 +1245,21 @@ static cudaError_t run_phaseone(const rsb200_plan* p, const uint8_t* in, uint8_t
   cudaError_t e = cudaMemsetAsync(p->d_arw2_bad, 0, sizeof(uint32_t) * (size_t)p->nunits, st);
   if (e != cudaSuccess)
     return e;
-  // RSB200_P1=1 selects the first version (per-lane refills) for A/B runs
-  static const bool v1 = [] {
-    const char* e = getenv("RSB200_P1");
-    return e && e[0] == '1';
-  }();
+  const int v = p->p1_ver;
   const uint32_t nb = (p->p1_nstrips + P1_NT - 1) / P1_NT;
-  if (v1)
+  if (v == 1) {
     p1_kernel<<<nb, P1_NT, 0, st>>>(in, outp, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs,
                                     p->d_arw2_bad);
-  else
+  } else if (v == 2) {
     p1_kernel_v2<<<nb, P1_NT, 0, st>>>(in, outp, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs,
                                        p->d_arw2_bad);
+  } else {
+    p1_walk_kernel<<<(p->p1_nstrips + P1W_NT - 1) / P1W_NT, P1W_NT, 0, st>>>(
+        in, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs, p->p1_gstride, p->d_p1_gdesc, p->d_p1_rowflag);
+    p1_decode_kernel<<<(p->p1_nstrips * 32u + P1D_NT - 1) / P1D_NT, P1D_NT, 0, st>>>(
+        in, outp, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs, p->p1_gstride, p->d_p1_gdesc,
+        p->d_p1_rowflag, p->d_arw2_bad);
+  }
   return cudaGetLastError();
 }
 
@@ -3278,6 +3300,8 @@ extern "C" void rsb200_plan_destroy(rsb200_plan* p) {
   rsb_dev_free(p->d_hass_row_begin);
   rsb_dev_free(p->d_p1_strips);
   rsb_dev_free(p->d_p1_jobs);
+  rsb_dev_free(p->d_p1_gdesc);
+  rsb_dev_free(p->d_p1_rowflag);
   rsb_dev_free(p->d_nikon_luts);
   rsb_dev_free(p->d_arw2_jobs);
   rsb_dev_free(p->d_arw2_tables);

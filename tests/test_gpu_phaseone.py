@@ -11,6 +11,15 @@ from helpers import gpu_run
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["3", "2"])
+def p1_version(request, monkeypatch):
+    """Every case with the kernel the plans take by default (the third version: group headers walked per
+    row, pixels in parallel) and with the second (one thread per row); RSB200_P1 is read when a plan is
+    created."""
+    monkeypatch.setenv("RSB200_P1", request.param)
+    return request.param
+
+
 def _plan(ctx, w, h, strips, out_offset=0, first=0):
     j = rs.PhaseOneJob()
     j.out_offset, j.out_pitch, j.width, j.height, j.first_strip = out_offset, port.image_pitch(w), w, h, first
