@@ -1,7 +1,7 @@
 """Timing of the Hasselblad decode (K2H) and the DNG opcode pass (K10) for the library in RSB200_LIB
 (development tool for A/B runs, not the benchmark; bench.py --all-legs has the numbers of record).
 
-    RSB200_LIB=tools/_ab/NAME.so python tools/hass_time.py [hass] [dngop]
+    RSB200_LIB=tools/_ab/NAME.so python tools/hass_time.py [hass] [dngop] [p1]
 """
 import json
 import os
@@ -97,6 +97,40 @@ def main():
             it[0] += 1
         ms = timeit(torch, step, reps=12, warm=4)
         res["dngop_8256x5504_8ops"] = {"ms": round(ms, 4), "GPix/s": round(W * H / ms / 1e6, 1), "exact": ok}
+    if "p1" in what:
+        w, h = 11608, 8708
+        rowimg = synth.image_model(w, 4, seed=31, bits=14).astype(np.uint16)
+        rows4 = [np.frombuffer(synth.phaseone_row(rowimg[k]), dtype=np.uint8) for k in range(4)]
+        offs, blobs, pos = [], [], 0
+        for r in range(h):
+            offs.append((pos, rows4[r % 4].size, r))
+            blobs.append(rows4[r % 4])
+            pos += rows4[r % 4].size
+        blob = np.concatenate(blobs)
+        pj = rs.PhaseOneJob()
+        pj.out_offset, pj.out_pitch, pj.width, pj.height, pj.first_strip = 0, rs.image_pitch(w), w, h, 0
+        pstrips = []
+        for off, size, row in offs:
+            ps = rs.PhaseOneStrip()
+            ps.in_offset, ps.in_size, ps.row = off, size, row
+            pstrips.append(ps)
+        d_in = torch.zeros(blob.size + 64, dtype=torch.uint8, device="cuda")
+        d_in[:blob.size] = torch.from_numpy(blob)
+        d_out = torch.zeros(h * rs.image_pitch(w), dtype=torch.uint8, device="cuda")
+        for ver in ("3", "2"):
+            os.environ["RSB200_P1"] = ver   # (read when the plan is created)
+            plan = rs.phaseone_plan(ctx, [pj], pstrips)
+            d_out.zero_()
+            plan.run((d_in.data_ptr(), blob.size), d_out)
+            st = plan.results()
+            got = d_out.cpu().numpy().view(np.uint16).reshape(h, rs.image_pitch(w) // 2)
+            ok = st[0][0] == 0 and all(bool(np.array_equal(
+                got[k::4, :w], np.broadcast_to(rowimg[k], (len(range(k, h, 4)), w)))) for k in range(4))
+            ms = timeit(torch, lambda: plan.run((d_in.data_ptr(), blob.size), d_out), reps=5, warm=2)
+            res["phaseone_11608x8708_v" + ver] = {"ms": round(ms, 4), "GPix/s": round(w * h / ms / 1e6, 1),
+                                                  "exact": ok, "launches": plan.launches}
+            del plan
+        os.environ.pop("RSB200_P1", None)
     print("HT " + os.path.basename(os.environ.get("RSB200_LIB", "default")) + " " + json.dumps(res))
 
 
