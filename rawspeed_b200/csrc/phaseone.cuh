@@ -284,10 +284,43 @@ __device__ __forceinline__ void p1_len_code(uint32_t x, uint32_t& used, uint32_t
   len = (uint32_t)((0xDEC5AB9678ull >> (4u * idx)) & 15u);
 }
 
+// the same without control flow (the walk is one dependent chain per row with about two warps per SM:
+// every branch and every instruction on the chain is paid in full)
+__device__ __forceinline__ void p1_len_code_bf(uint32_t x, uint32_t& used, uint32_t& len, bool& one) {
+  const uint32_t j = (uint32_t)min(__clz((int)x), 5);
+  one = j < 5u;
+  used = j == 0u ? 1u : (j < 5u ? j + 2u : 6u);
+  const uint32_t bit = (x >> (32u - used)) & 1u;
+  const uint32_t idx = j == 0u ? 0u : 2u * (j - 1u) + bit;
+  const uint32_t nl = (uint32_t)((0xDEC5AB9678ull >> (4u * idx)) & 15u);
+  len = j == 0u ? len : nl;
+}
+
+// FAST: the window comes from three aligned words where they lie wholly inside the strip (all but the last
+// groups of a row), and the length codes are decoded without branches; !FAST: the first form of the walk
+// (generic chunk loads, branches), kept for A/B runs (RSB200_P1W=1).  r2_run25: the first form needs
+// about 170 instructions per group on a chain nobody hides.
+// A length code is decided by the 6 bits at the top of the window: 64 entries, bits used | a 1 bit came
+// before five zeros << 3 | new length << 4 (0: keep) -- one shared-memory load instead of a dozen
+// dependent instructions.
+struct P1WalkShared {
+  uint32_t code6[64];
+};
+
+template <bool FAST>
 __device__ __forceinline__ void
-p1_walk_entry(const uint8_t* __restrict__ in, const P1StripDev* __restrict__ strips, uint32_t nstrips,
-              const P1JobDev* __restrict__ jobs, uint32_t gstride, uint32_t* __restrict__ gdesc,
-              uint32_t* __restrict__ rowflag) {
+p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev* __restrict__ strips,
+              uint32_t nstrips, const P1JobDev* __restrict__ jobs, uint32_t gstride,
+              uint32_t* __restrict__ gdesc, uint32_t* __restrict__ rowflag) {
+  if (FAST) {
+    for (uint32_t i = threadIdx.x; i < 64u; i += blockDim.x) {
+      uint32_t used, len = 0;
+      bool one;
+      p1_len_code_bf(i << 26, used, len, one);
+      sh.code6[i] = used | (one ? 8u : 0u) | (len << 4);
+    }
+    __syncthreads();
+  }
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nstrips)
     return;
@@ -301,14 +334,35 @@ p1_walk_entry(const uint8_t* __restrict__ in, const P1StripDev* __restrict__ str
     rowflag[s] = 1u;
     return;
   }
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(base) & 3u);
+  const uint32_t* aw = reinterpret_cast<const uint32_t*>(base - mis); // (inside the caller's buffer: its start is aligned)
+  const uint32_t sh8 = 8u * mis;
   uint32_t p = 0, len0 = 0, len1 = 0;
   bool fatal = false;
   for (uint32_t g = 0; g < ngroups; ++g) {
-    const uint32_t x = p1_window(base, size, p);
+    uint32_t x;
+    const uint32_t c = p >> 5;
+    if (FAST && 4u * c + 16u <= size) { // the bytes [4c - mis, 4c - mis + 12) lie inside the strip
+      const uint32_t a0 = __ldg(aw + c), a1 = __ldg(aw + c + 1u), a2 = __ldg(aw + c + 2u);
+      x = __funnelshift_l(__funnelshift_r(a1, a2, sh8), __funnelshift_r(a0, a1, sh8), p);
+    } else {
+      x = p1_window(base, size, p);
+    }
     uint32_t u0, u1;
     bool o0, o1;
-    p1_len_code(x, u0, len0, o0);
-    p1_len_code(x << u0, u1, len1, o1);
+    if (FAST) {
+      const uint32_t e0 = sh.code6[x >> 26];
+      u0 = e0 & 7u;
+      const uint32_t e1 = sh.code6[(x << u0) >> 26];
+      u1 = e1 & 7u;
+      o0 = (e0 & 8u) != 0u;
+      o1 = (e1 & 8u) != 0u;
+      len0 = (e0 >> 4) ? (e0 >> 4) : len0;
+      len1 = (e1 >> 4) ? (e1 >> 4) : len1;
+    } else {
+      p1_len_code(x, u0, len0, o0);
+      p1_len_code(x << u0, u1, len1, o1);
+    }
     if (g == 0u && (o0 || o1))
       fatal = true; // "Can not initialize lengths. Data is corrupt."
     const uint32_t hdr = u0 + u1, p0 = p + hdr;
@@ -471,8 +525,12 @@ p1_decode_entry(P1DecodeShared& sh, const uint8_t* __restrict__ in, uint8_t* __r
 __global__ void __launch_bounds__(P1W_NT)
     p1_walk_kernel(const uint8_t* __restrict__ in, const P1StripDev* __restrict__ strips, uint32_t nstrips,
                    const P1JobDev* __restrict__ jobs, uint32_t gstride, uint32_t* __restrict__ gdesc,
-                   uint32_t* __restrict__ rowflag) {
-  p1_walk_entry(in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+                   uint32_t* __restrict__ rowflag, int first_form) {
+  __shared__ P1WalkShared sh;
+  if (first_form)
+    p1_walk_entry<false>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+  else
+    p1_walk_entry<true>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
 }
 __global__ void __launch_bounds__(P1D_NT)
     p1_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,

@@ -280,6 +280,7 @@ struct rsb200_plan {
   uint32_t* d_p1_rowflag = nullptr; // ... and per row: failed before anything was stored
   uint32_t p1_gstride = 0;          // words of gdesc per row
   int p1_ver = 3;                   // which version of the kernel this plan runs (RSB200_P1)
+  int p1_walk1 = 0;                 // RSB200_P1W=1: the first form of the third version's walk (A/B)
   uint32_t p1_nstrips = 0;
   // Sony ARW2
   Arw2JobDev* d_arw2_jobs = nullptr;
@@ -1235,6 +1236,10 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
     return set_err(ctx, RSB200_ERR_CUDA, "phaseone plan upload failed: %s", cudaGetErrorString(e));
   }
   p->p1_ver = p1_version();
+  {
+    const char* e = getenv("RSB200_P1W");
+    p->p1_walk1 = (e && e[0] == '1' && !e[1]) ? 1 : 0;
+  }
   p->launches_per_run = p->p1_ver == 3 ? 2 : 1;
   *out = p;
   return RSB200_OK;
@@ -1255,7 +1260,8 @@ static cudaError_t run_phaseone(const rsb200_plan* p, const uint8_t* in, uint8_t
                                        p->d_arw2_bad);
   } else {
     p1_walk_kernel<<<(p->p1_nstrips + P1W_NT - 1) / P1W_NT, P1W_NT, 0, st>>>(
-        in, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs, p->p1_gstride, p->d_p1_gdesc, p->d_p1_rowflag);
+        in, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs, p->p1_gstride, p->d_p1_gdesc, p->d_p1_rowflag,
+        p->p1_walk1);
     p1_decode_kernel<<<(p->p1_nstrips * 32u + P1D_NT - 1) / P1D_NT, P1D_NT, 0, st>>>(
         in, outp, p->d_p1_strips, p->p1_nstrips, p->d_p1_jobs, p->p1_gstride, p->d_p1_gdesc,
         p->d_p1_rowflag, p->d_arw2_bad);

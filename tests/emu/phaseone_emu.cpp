@@ -12,7 +12,7 @@ using namespace rsb200;
 // strips: (offset, size, row) triples; returns the job's failure flag in *bad
 extern "C" int p1_emu_run(const uint8_t* in, uint64_t in_total, const uint64_t* offs, const uint32_t* sizes,
                           const uint32_t* rows, int nstrips, int width, int out_pitch, uint8_t* out,
-                          uint32_t* bad, int reverse) {
+                          uint32_t* bad, int reverse, int first_form) {
   // the file at a 4-byte aligned address, exactly in_total bytes readable (+ the slack the ABI promises)
   std::vector<uint8_t> buf((size_t)in_total + 64);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~(uintptr_t)15);
@@ -31,8 +31,12 @@ extern "C" int p1_emu_run(const uint8_t* in, uint64_t in_total, const uint64_t* 
   *bad = 0;
   const uint32_t nbw = ((uint32_t)nstrips + P1W_NT - 1) / P1W_NT;
   for (uint32_t b = 0; b < nbw; ++b)
-    cuemu::run_cta(b, nbw, P1W_NT, 16, reverse != 0, [&](uint8_t*) {
-      p1_walk_entry(base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
+    cuemu::run_cta(b, nbw, P1W_NT, sizeof(P1WalkShared), reverse != 0, [&](uint8_t* smem) {
+      P1WalkShared& wsh = *reinterpret_cast<P1WalkShared*>(smem);
+      if (first_form)
+        p1_walk_entry<false>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
+      else
+        p1_walk_entry<true>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
     });
   const uint32_t nbd = ((uint32_t)nstrips * 32u + P1D_NT - 1) / P1D_NT;
   for (uint32_t b = 0; b < nbd; ++b)

@@ -19,8 +19,18 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h"),
         os.path.join(HERE, "..", "rawspeed_b200", "csrc", "phaseone.cuh")]
 
 
-@pytest.fixture(scope="module")
-def emu():
+FORM = {"fast": 0, "first": 1}
+
+
+@pytest.fixture(scope="module", params=["fast", "first"])
+def emu(request):
+    """Both forms of the header walk (aligned-word windows + branch-free length codes, and the first one)."""
+    lib = _load()
+    lib.form = FORM[request.param]
+    return lib
+
+
+def _load():
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
@@ -28,7 +38,7 @@ def emu():
     lib = C.CDLL(OUT)
     lib.p1_emu_run.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
                                C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int, C.c_void_p,
-                               C.POINTER(C.c_uint32), C.c_int]
+                               C.POINTER(C.c_uint32), C.c_int, C.c_int]
     return lib
 
 
@@ -41,7 +51,7 @@ def run_emu(lib, blob, strips, w, h, reverse=False):
     out = port.new_image(w, h)
     bad = C.c_uint32(9)
     rc = lib.p1_emu_run(blob.ctypes.data, blob.size, offs, sizes, rows, n, w, out.shape[1] * 2,
-                        out.ctypes.data, C.byref(bad), int(reverse))
+                        out.ctypes.data, C.byref(bad), int(reverse), getattr(lib, "form", 0))
     assert rc == 0
     return out, bad.value
 
