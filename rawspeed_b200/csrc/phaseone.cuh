@@ -311,7 +311,21 @@ struct P1WalkShared {
 // into a value nobody needs): L1 is filled sector by sector on demand, and a row advances about half a
 // sector per group, so without it every second step waits for L2 and every fourth for DRAM, with nothing
 // else on the SM to run meanwhile (r2_run26: 1250 cycles per step).  The touch is ten steps ahead.
-template <bool FAST, bool TOUCH>
+__device__ __forceinline__ void p1_prefetch(const void* q, int level) {
+#ifndef RSB200_EMU
+  if (level == 1)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+  else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+#else
+  (void)q;
+  (void)level;
+#endif
+}
+
+// TOUCH: 0 nothing, 1 the look-ahead load described above, 2 prefetch.global.L1 192 bytes ahead, 3
+// prefetch.global.L2 512 bytes ahead + prefetch.global.L1 128 bytes ahead (no register waits for either)
+template <bool FAST, int TOUCH>
 __device__ __forceinline__ void
 p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev* __restrict__ strips,
               uint32_t nstrips, const P1JobDev* __restrict__ jobs, uint32_t gstride,
@@ -348,9 +362,14 @@ p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev
   for (uint32_t g = 0; g < ngroups; ++g) {
     uint32_t x;
     const uint32_t c = p >> 5;
-    if (TOUCH) {
+    if (TOUCH == 1) {
       sink ^= touched;
       touched = __ldg(aw + min(c + 48u, wlast));
+    } else if (TOUCH == 2) {
+      p1_prefetch(aw + min(c + 48u, wlast), 1);
+    } else if (TOUCH == 3) {
+      p1_prefetch(aw + min(c + 128u, wlast), 2);
+      p1_prefetch(aw + min(c + 32u, wlast), 1);
     }
     if (FAST && 4u * c + 16u <= size) { // the bytes [4c - mis, 4c - mis + 12) lie inside the strip
       const uint32_t a0 = __ldg(aw + c), a1 = __ldg(aw + c + 1u), a2 = __ldg(aw + c + 2u);
@@ -381,7 +400,7 @@ p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev
   }
   desc[ngroups] = p; // where the last width % 8 pixels (raw) start
   // (bit 1 is never set: the touched words only have to be used by something)
-  rowflag[s] = (fatal ? 1u : 0u) | (TOUCH && (sink ^ touched) == 0x5EC7095Eu && p == 0xFFFFFFFFu ? 2u : 0u);
+  rowflag[s] = (fatal ? 1u : 0u) | (TOUCH == 1 && (sink ^ touched) == 0x5EC7095Eu && p == 0xFFFFFFFFu ? 2u : 0u);
 }
 
 struct P1DecodeShared {
@@ -539,11 +558,15 @@ __global__ void __launch_bounds__(P1W_NT)
                    uint32_t* __restrict__ rowflag, int first_form) {
   __shared__ P1WalkShared sh;
   if (first_form == 1)
-    p1_walk_entry<false, false>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+    p1_walk_entry<false, 0>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else if (first_form == 2)
-    p1_walk_entry<true, false>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+    p1_walk_entry<true, 0>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+  else if (first_form == 3)
+    p1_walk_entry<true, 2>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+  else if (first_form == 4)
+    p1_walk_entry<true, 3>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else
-    p1_walk_entry<true, true>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+    p1_walk_entry<true, 1>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
 }
 __global__ void __launch_bounds__(P1D_NT)
     p1_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,

@@ -1,13 +1,10 @@
 #!/usr/bin/env bash
-# round 2, GPU call 27: the third Phase One kernel with the second form of its walk (aligned-word windows,
+# round 2, GPU call 28: the third Phase One kernel with the second form of its walk (aligned-word windows,
 # table-driven length codes): tests of every version, timing, per-kernel durations.
 set -u
-OUT=gpurun_out/r2_run27
+OUT=gpurun_out/r2_run28
 mkdir -p "$OUT"
 timeout 300 python -m pytest tests/test_gpu_phaseone.py -q > "$OUT/test_gpu_phaseone.log" 2>&1
 echo "test_gpu_phaseone exit $?" | tee -a "$OUT/summary.txt"; tail -3 "$OUT/test_gpu_phaseone.log"
 timeout 300 python tools/hass_time.py p1 > "$OUT/ht_p1.log" 2>&1
 echo "ht p1 exit $?" | tee -a "$OUT/summary.txt"; grep "^HT" "$OUT/ht_p1.log" | tee -a "$OUT/summary.txt"; tail -2 "$OUT/ht_p1.log"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"p1_" -c 16 --csv --log-file "$OUT/p1_launches.csv" \
-    python tools/hass_time.py p1 > "$OUT/ncu_p1.log" 2>&1
-echo "ncu p1 exit $?" | tee -a "$OUT/summary.txt"; grep -o '"p1_[a-z0-9_]*[^,]*,[^,]*,[^,]*,[^,]*$' "$OUT/p1_launches.csv" | head -12
