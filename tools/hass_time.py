@@ -117,7 +117,10 @@ def main():
         d_in = torch.zeros(blob.size + 64, dtype=torch.uint8, device="cuda")
         d_in[:blob.size] = torch.from_numpy(blob)
         d_out = torch.zeros(h * rs.image_pitch(w), dtype=torch.uint8, device="cuda")
-        for ver in ("3", "3w2", "3w3", "3w4", "3w1", "2"):
+        vers = ("3", "3w2", "3w3", "3w4", "3w1", "2")
+        if os.environ.get("RSB200_P1W"):   # (one variant only: profiling runs)
+            vers = ("3w" + os.environ["RSB200_P1W"],)
+        for ver in vers:
             os.environ["RSB200_P1"] = ver[0]   # (read when the plan is created)
             os.environ["RSB200_P1W"] = ver[2] if len(ver) == 3 else "0"
             plan = rs.phaseone_plan(ctx, [pj], pstrips)
