@@ -1215,7 +1215,7 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
   }
   p->p1_nstrips = (uint32_t)ds.size();
   for (int i = 0; i < njobs; ++i)
-    p->p1_gstride = std::max<uint32_t>(p->p1_gstride, jobs[i].width / 8u + 1u);
+    p->p1_gstride = std::max<uint32_t>(p->p1_gstride, (jobs[i].width / 8u + 1u + 3u) & ~3u); // (16-byte rows)
   cudaError_t e = rsb_dev_alloc((void**)&p->d_p1_strips, sizeof(P1StripDev) * ds.size());
   if (e == cudaSuccess)
     e = rsb_dev_alloc((void**)&p->d_p1_gdesc, sizeof(uint32_t) * (size_t)p->p1_gstride * ds.size());
@@ -1238,7 +1238,7 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
   p->p1_ver = p1_version();
   {
     const char* e = getenv("RSB200_P1W");
-    p->p1_walk1 = (e && e[0] >= '1' && e[0] <= '4' && !e[1]) ? e[0] - '0' : 0;
+    p->p1_walk1 = (e && e[0] >= '1' && e[0] <= '5' && !e[1]) ? e[0] - '0' : 0;
   }
   p->launches_per_run = p->p1_ver == 3 ? 2 : 1;
   *out = p;

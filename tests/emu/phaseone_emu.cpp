@@ -26,8 +26,10 @@ extern "C" int p1_emu_run(const uint8_t* in, uint64_t in_total, const uint64_t* 
     st[(size_t)i].pad = 0;
   }
   P1JobDev jb{0, (uint32_t)out_pitch, (uint32_t)width};
-  const uint32_t gstride = (uint32_t)width / 8u + 1u;
-  std::vector<uint32_t> gdesc((size_t)gstride * (size_t)nstrips, 0xCDCDCDCDu), rowflag((size_t)nstrips, 0xCDu);
+  const uint32_t gstride = ((uint32_t)width / 8u + 1u + 3u) & ~3u; // (rows of descriptors at multiples of 16 bytes)
+  std::vector<uint32_t> gdesc_buf((size_t)gstride * (size_t)nstrips + 4, 0xCDCDCDCDu), rowflag((size_t)nstrips, 0xCDu);
+  uint32_t* const gdesc_p = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(gdesc_buf.data()) + 15) & ~(uintptr_t)15);
+  struct { uint32_t* p; uint32_t* data() const { return p; } } gdesc{gdesc_p};
   *bad = 0;
   const uint32_t nbw = ((uint32_t)nstrips + P1W_NT - 1) / P1W_NT;
   for (uint32_t b = 0; b < nbw; ++b)
@@ -37,8 +39,10 @@ extern "C" int p1_emu_run(const uint8_t* in, uint64_t in_total, const uint64_t* 
         p1_walk_entry<false, 0>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else if (first_form == 2)
         p1_walk_entry<true, 0>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
-      else
+      else if (first_form == 5)
         p1_walk_entry<true, 1>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
+      else
+        p1_walk_entry<true, 4>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
     });
   const uint32_t nbd = ((uint32_t)nstrips * 32u + P1D_NT - 1) / P1D_NT;
   for (uint32_t b = 0; b < nbd; ++b)

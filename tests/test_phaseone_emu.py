@@ -19,10 +19,10 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h"),
         os.path.join(HERE, "..", "rawspeed_b200", "csrc", "phaseone.cuh")]
 
 
-FORM = {"fast": 0, "first": 1, "fast_no_touch": 2}
+FORM = {"blocks": 0, "first": 1, "fast_no_touch": 2, "fast_touch": 5}
 
 
-@pytest.fixture(scope="module", params=["fast", "first", "fast_no_touch"])
+@pytest.fixture(scope="module", params=["blocks", "first", "fast_no_touch", "fast_touch"])
 def emu(request):
     """Both forms of the header walk (aligned-word windows + branch-free length codes, and the first one)."""
     lib = _load()
