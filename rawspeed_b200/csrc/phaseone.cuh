@@ -369,23 +369,30 @@ p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev
   const uint4* a16 = reinterpret_cast<const uint4*>(base - mis16);
   const uint32_t woff = mis16 >> 2;                   // aligned word of byte 0, counted from a16
   const uint32_t blast = (mis16 + size - 1u) >> 4;    // the last block that holds a byte of the strip
-  uint32_t B = 0;                                     // b0 = block B, b1 = block B + 1 (where it exists)
-  uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+  uint32_t B = 0;                                     // b0 .. b3 = blocks B .. B + 3 (where they exist)
+  uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0, b2 = b0, b3 = b0;
   uint32_t q0 = 0, q1 = 0, q2 = 0;                    // descriptor words waiting for the fourth
   if (TOUCH == 4) {
     b0 = __ldg(a16);
     b1 = __ldg(a16 + min(1u, blast));
+    b2 = __ldg(a16 + min(2u, blast));
+    b3 = __ldg(a16 + min(3u, blast));
   }
   for (uint32_t g = 0; g < ngroups; ++g) {
     uint32_t x;
     const uint32_t c = p >> 5;
     const uint32_t ca = c + woff, k = ca & 3u;
     if (TOUCH == 4) {
-      while (B < (ca >> 2)) { // (a group is at most 140 bits: one or two blocks further)
+      // (a group is at most 140 bits: one or two blocks further.  The block loaded here is used two
+      //  blocks -- about seven steps -- later: run 30 showed that a block fetched one step before its use
+      //  is waited for just like the window loads of the other forms)
+      while (B < (ca >> 2)) {
         ++B;
         b0 = b1;
-        b1 = __ldg(a16 + min(B + 1u, blast));
-        p1_prefetch(a16 + min(B + 12u, blast), 1);
+        b1 = b2;
+        b2 = b3;
+        b3 = __ldg(a16 + min(B + 3u, blast));
+        p1_prefetch(a16 + min(B + 16u, blast), 2);
       }
     }
     if (TOUCH == 1) {

@@ -1,8 +1,8 @@
 #!/usr/bin/env bash
-# round 2, GPU call 30: the third Phase One kernel with the second form of its walk (aligned-word windows,
+# round 2, GPU call 31: the third Phase One kernel with the second form of its walk (aligned-word windows,
 # table-driven length codes): tests of every version, timing, per-kernel durations.
 set -u
-OUT=gpurun_out/r2_run30
+OUT=gpurun_out/r2_run31
 mkdir -p "$OUT"
 timeout 300 python -m pytest tests/test_gpu_phaseone.py -q > "$OUT/test_gpu_phaseone.log" 2>&1
 echo "test_gpu_phaseone exit $?" | tee -a "$OUT/summary.txt"; tail -3 "$OUT/test_gpu_phaseone.log"
