@@ -280,7 +280,7 @@ struct rsb200_plan {
   uint32_t* d_p1_rowflag = nullptr; // ... and per row: failed before anything was stored
   uint32_t p1_gstride = 0;          // words of gdesc per row
   int p1_ver = 3;                   // which version of the kernel this plan runs (RSB200_P1)
-  int p1_walk1 = 0;                 // RSB200_P1W=1: the first form of the third version's walk, 2: the second without look-ahead loads (A/B)
+  int p1_walk1 = 0;                 // RSB200_P1W = 1 .. 6: other forms of the third version's walk (A/B; see p1_walk_kernel)
   uint32_t p1_nstrips = 0;
   // Sony ARW2
   Arw2JobDev* d_arw2_jobs = nullptr;
@@ -1238,7 +1238,7 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
   p->p1_ver = p1_version();
   {
     const char* e = getenv("RSB200_P1W");
-    p->p1_walk1 = (e && e[0] >= '1' && e[0] <= '5' && !e[1]) ? e[0] - '0' : 0;
+    p->p1_walk1 = (e && e[0] >= '1' && e[0] <= '6' && !e[1]) ? e[0] - '0' : 0;
   }
   p->launches_per_run = p->p1_ver == 3 ? 2 : 1;
   *out = p;

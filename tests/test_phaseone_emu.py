@@ -19,12 +19,13 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h"),
         os.path.join(HERE, "..", "rawspeed_b200", "csrc", "phaseone.cuh")]
 
 
-FORM = {"blocks": 0, "first": 1, "fast_no_touch": 2, "fast_touch": 5}
+FORM = {"default": 0, "first": 1, "fast_no_touch": 2, "fast_touch": 5, "blocks": 6}
 
 
-@pytest.fixture(scope="module", params=["blocks", "first", "fast_no_touch", "fast_touch"])
+@pytest.fixture(scope="module", params=["default", "first", "fast_touch", "blocks"])
 def emu(request):
-    """Both forms of the header walk (aligned-word windows + branch-free length codes, and the first one)."""
+    """Forms of the header walk: the default (aligned-word windows, table-driven length codes, prefetch),
+    the first one (generic chunk loads, branches), look-ahead loads, and 16-byte blocks cached in registers."""
     lib = _load()
     lib.form = FORM[request.param]
     return lib
