@@ -351,13 +351,16 @@ __device__ __noinline__ uint32_t s_stream_position(const uint8_t* __restrict__ g
 // are still in the ring: nothing is written inside a unit, and a fill step at the end of the unit
 // before (taken with at most S_ROOM bytes ahead) leaves the ring starting 8 bytes or more BEHIND
 // the read position.  Rare path (codes longer than LUT_BITS, SSSS = 16, corrupt data).
-__device__ __noinline__ uint32_t s_count_hits(uint32_t ringb, uint32_t lutb, uint32_t p0, uint32_t p1) {
+__device__ __noinline__ uint32_t s_count_hits(uint32_t ringb, uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3,
+                                              uint32_t gm1, uint32_t p0, uint32_t p1) {
   uint32_t k = 0, q = p0;
   while (q != p1 && k < 8u) {
     const uint32_t w = (q >> 5) * T_WSTRIDE;
     const uint32_t a = lds_u32<0>(ringb + (w & T_RMASK));
     const uint32_t b = lds_u32<0>(ringb + ((w + T_WSTRIDE) & T_RMASK));
     const uint32_t x = __funnelshift_l(b, a, q);
+    const uint32_t c = k & gm1; // component of sample k (G = 1, 2 or 4)
+    const uint32_t lutb = c == 0u ? l0 : (c == 1u ? l1 : (c == 2u ? l2 : l3));
     const uint32_t e = lds_u16<0>(mad_hi(x & ~((1u << (32 - LUT_BITS)) - 1u), 1u << (LUT_BITS + 1), lutb));
 #ifdef RSB200_EMU
     if (e == 0u || q > p1)
@@ -403,9 +406,11 @@ __device__ __forceinline__ bool s_any(bool want) { return __any_sync(__activemas
 // complete iff its last symbol hit; otherwise the symbols before the first miss are counted
 // (s_count_hits) and the unit is finished symbol by symbol (S_SYM) from there.
 // Without a branch per symbol the eight decodes are one basic block: the difference arithmetic of
-// symbol k is scheduled into the latency of symbol k+1's LUT load.  A segment whose components
-// use DIFFERENT tables does not take this form (a window that starts with a long code of one
-// table can be a short code of the other: the miss would not stick); it goes symbol by symbol.
+// symbol k is scheduled into the latency of symbol k+1's LUT load.  With SEVERAL tables a window
+// that starts with a long code of one can be a short code of another and the miss would not stick
+// (the kernel of run 23 decoded garbage there): the shared-memory copies of a plan's LUTs are
+// therefore reduced to the windows that ALL of them resolve (stream_entry); a window dropped from
+// a LUT just takes the symbol-by-symbol path, which walks the code lengths.
 // RSB200_S_PIPE (A/B): the unit is bound by the ALU pipe (SHF / LOP3 / LEA / IADD3: one warp
 // instruction every two cycles; ncu at 256 frames: 76 % of its cycles against 25 % of the FMA pipe's,
 // profiles/r2_ncu_ljpeg.md).  ptxas turns every multiply by a constant power of two back into ALU
@@ -584,11 +589,8 @@ stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp
 #endif
     rowstart[c] = scp->init_pred[c];
   }
-  // the straight-line unit relies on "a miss repeats": true when every component reads the same LUT
-  bool one_table = true;
-#pragma unroll
-  for (int c = 1; c < G; ++c)
-    one_table = one_table && lutb[c] == lutb[0];
+  // (the straight-line unit relies on "a miss repeats": the LUTs of a plan with several tables are made
+  //  to miss on the same windows, see stream_entry)
   const uint32_t rows = scp->rows;
   const uint32_t units = scp->row_samples >> 3; // row_samples is a multiple of 8
   const uint32_t store_w = scp->store_w;
@@ -629,8 +631,8 @@ stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp
       uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
 #if RSB200_S_STRAIGHT
       uint32_t k_ = 0; // samples of the unit that are done
-      if (G == 1 || one_table) {
-        // a miss repeats (same window, same table): the unit is complete iff its LAST symbol hit
+      {
+        // a miss repeats (same window; every LUT of the plan misses on it): complete iff the LAST symbol hit
         const uint32_t p0 = p;
         uint32_t elast = 0;
         S_SYMF(0 % G, v0);
@@ -646,7 +648,7 @@ stream_body(StreamShared& sh, const int ntab_sh, const DevScan* __restrict__ scp
 #else
         k_ = 8u;
         if (elast == 0u)
-          k_ = s_count_hits(ringb, lutb[0], p0, p);
+          k_ = s_count_hits(ringb, lutb[0], lutb[1 % G], lutb[2 % G], lutb[3 % G], (uint32_t)G - 1u, p0, p);
 #endif
       }
       if (k_ != 8u) { // rare: the symbols from the first miss on, one by one
@@ -767,6 +769,17 @@ stream_entry(StreamShared& sh, const uint8_t* __restrict__ in, uint64_t in_total
       sh.sel[tid] = s_sel_entry((uint32_t)tid);
   }
   __syncthreads();
+  if (ntab > 1) { // a window is a hit only if every table of the plan resolves it (see S_SYMF)
+    for (int i = tid; i < (1 << LUT_BITS); i += T_NT) {
+      bool all = true;
+      for (int t = 0; t < ntab; ++t)
+        all = all && sh.tab[t].lut[i] != 0;
+      if (!all)
+        for (int t = 0; t < ntab; ++t)
+          sh.tab[t].lut[i] = 0;
+    }
+    __syncthreads();
+  }
 #if RSB200_S_LUT32
   {
     uint32_t* l32 = reinterpret_cast<uint32_t*>(&sh.tab[ntab]);
