@@ -303,8 +303,10 @@ __device__ __forceinline__ void p1_len_code_bf(uint32_t x, uint32_t& used, uint3
 // A length code is decided by the 6 bits at the top of the window: 64 entries, bits used | a 1 bit came
 // before five zeros << 3 | new length << 4 (0: keep) -- one shared-memory load instead of a dozen
 // dependent instructions.
+constexpr int P1W_RING = 64; // words per row in shared memory: two lines of 128 bytes (form "lines")
 struct P1WalkShared {
   uint32_t code6[64];
+  uint32_t ring[P1W_NT][P1W_RING + 1]; // (+1: the rows of a warp start in different banks)
 };
 
 // TOUCH: every step also loads one word 192 bytes further down the row and uses it a step later (an XOR
@@ -329,7 +331,10 @@ __device__ __forceinline__ void p1_prefetch(const void* q, int level) {
 // lane-private window loads of every step although 92 % of their sectors hit L1.  So the row is read in
 // aligned 16-byte blocks, two of them cached in registers (one 128-bit load every three to four steps, a
 // prefetch 192 bytes ahead at the same moment), the window's three words are selected from the eight
-// cached ones, and four descriptor words leave with one 128-bit store.
+// cached ones, and four descriptor words leave with one 128-bit store.  5 "lines": the row is read in
+// aligned lines of 128 bytes (eight 128-bit loads issued together, consumed a whole line -- about seven
+// steps -- later), two lines per row wait in shared memory and the window comes from there: the walk's
+// chain holds shared-memory loads only.
 template <bool FAST, int TOUCH>
 __device__ __forceinline__ void
 p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev* __restrict__ strips,
@@ -372,6 +377,27 @@ p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev
   uint32_t B = 0;                                     // b0 .. b3 = blocks B .. B + 3 (where they exist)
   uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0, b2 = b0, b3 = b0;
   uint32_t q0 = 0, q1 = 0, q2 = 0;                    // descriptor words waiting for the fourth
+  // TOUCH == 5: lines of 128 bytes from the 128-byte boundary at or before the strip
+  const uint32_t mis128 = (uint32_t)(reinterpret_cast<uintptr_t>(base) & 127u);
+  const uint4* a128 = reinterpret_cast<const uint4*>(base - mis128);
+  const uint32_t woff128 = mis128 >> 2;
+  const uint32_t blast128 = (mis128 + size - 1u) >> 4; // the last 16-byte block (from a128) with a byte of the strip
+  uint32_t* ring = sh.ring[threadIdx.x];
+  uint32_t L = 0;                                      // ring: lines L and L + 1; pend: line L + 2
+  uint4 pend[8];
+  if (TOUCH == 5) {
+#pragma unroll
+    for (uint32_t i = 0; i < 16u; ++i) {
+      const uint4 v = __ldg(a128 + min(i, blast128));
+      ring[4u * i] = v.x;
+      ring[4u * i + 1u] = v.y;
+      ring[4u * i + 2u] = v.z;
+      ring[4u * i + 3u] = v.w;
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < 8u; ++i)
+      pend[i] = __ldg(a128 + min(16u + i, blast128));
+  }
   if (TOUCH == 4) {
     b0 = __ldg(a16);
     b1 = __ldg(a16 + min(1u, blast));
@@ -404,7 +430,30 @@ p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev
       p1_prefetch(aw + min(c + 128u, wlast), 2);
       p1_prefetch(aw + min(c + 32u, wlast), 1);
     }
-    if (FAST && TOUCH == 4 && 4u * c + 16u <= size) {
+    if (TOUCH == 5) {
+      const uint32_t cl = c + woff128;
+      if ((cl >> 5) > L) { // into line L + 1: line L + 2 replaces line L, line L + 3 is asked for
+        ++L;
+        uint32_t* slot = ring + 32u * ((L + 1u) & 1u);
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i) {
+          slot[4u * i] = pend[i].x;
+          slot[4u * i + 1u] = pend[i].y;
+          slot[4u * i + 2u] = pend[i].z;
+          slot[4u * i + 3u] = pend[i].w;
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i)
+          pend[i] = __ldg(a128 + min(8u * (L + 2u) + i, blast128));
+        p1_prefetch(a128 + min(8u * (L + 6u), blast128), 2);
+      }
+    }
+    if (FAST && TOUCH == 5 && 4u * c + 16u <= size) {
+      // (the three words hold strip bytes only: their lines are L or L + 1, loaded without clamping)
+      const uint32_t cl = c + woff128;
+      const uint32_t a0 = ring[cl & 63u], a1 = ring[(cl + 1u) & 63u], a2 = ring[(cl + 2u) & 63u];
+      x = __funnelshift_l(__funnelshift_r(a1, a2, sh8), __funnelshift_r(a0, a1, sh8), p);
+    } else if (FAST && TOUCH == 4 && 4u * c + 16u <= size) {
       // (the three words hold strip bytes only, so their blocks exist: b1 is block B + 1 if it is needed)
       const uint32_t a0 = k == 0u ? b0.x : (k == 1u ? b0.y : (k == 2u ? b0.z : b0.w));
       const uint32_t a1 = k == 0u ? b0.y : (k == 1u ? b0.z : (k == 2u ? b0.w : b1.x));
@@ -628,6 +677,8 @@ __global__ void __launch_bounds__(P1W_NT)
     p1_walk_entry<true, 1>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else if (first_form == 6)
     p1_walk_entry<true, 4>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+  else if (first_form == 7)
+    p1_walk_entry<true, 5>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else
     p1_walk_entry<true, 2>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
 }

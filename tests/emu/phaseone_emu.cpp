@@ -14,8 +14,9 @@ extern "C" int p1_emu_run(const uint8_t* in, uint64_t in_total, const uint64_t* 
                           const uint32_t* rows, int nstrips, int width, int out_pitch, uint8_t* out,
                           uint32_t* bad, int reverse, int first_form) {
   // the file at a 4-byte aligned address, exactly in_total bytes readable (+ the slack the ABI promises)
-  std::vector<uint8_t> buf((size_t)in_total + 64);
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(buf.data()) + 15) & ~(uintptr_t)15);
+  // (128-byte aligned like a device allocation: the "lines" form of the walk reads whole aligned lines)
+  std::vector<uint8_t> buf((size_t)in_total + 512);
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(buf.data()) + 127) & ~(uintptr_t)127);
   memcpy(base, in, (size_t)in_total);
   std::vector<P1StripDev> st((size_t)nstrips);
   for (int i = 0; i < nstrips; ++i) {
@@ -43,6 +44,8 @@ extern "C" int p1_emu_run(const uint8_t* in, uint64_t in_total, const uint64_t* 
         p1_walk_entry<true, 1>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else if (first_form == 6)
         p1_walk_entry<true, 4>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
+      else if (first_form == 7)
+        p1_walk_entry<true, 5>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else
         p1_walk_entry<true, 2>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
     });

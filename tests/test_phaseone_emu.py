@@ -19,10 +19,10 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h"),
         os.path.join(HERE, "..", "rawspeed_b200", "csrc", "phaseone.cuh")]
 
 
-FORM = {"default": 0, "first": 1, "fast_no_touch": 2, "fast_touch": 5, "blocks": 6}
+FORM = {"default": 0, "first": 1, "fast_no_touch": 2, "fast_touch": 5, "blocks": 6, "lines": 7}
 
 
-@pytest.fixture(scope="module", params=["default", "first", "fast_touch", "blocks"])
+@pytest.fixture(scope="module", params=["default", "first", "fast_touch", "blocks", "lines"])
 def emu(request):
     """Forms of the header walk: the default (aligned-word windows, table-driven length codes, prefetch),
     the first one (generic chunk loads, branches), look-ahead loads, and 16-byte blocks cached in registers."""
