@@ -664,23 +664,23 @@ __global__ void __launch_bounds__(P1W_NT)
                    const P1JobDev* __restrict__ jobs, uint32_t gstride, uint32_t* __restrict__ gdesc,
                    uint32_t* __restrict__ rowflag, int first_form) {
   __shared__ P1WalkShared sh;
-  // 0 (default): aligned-word windows, table-driven length codes, prefetch.global.L1 192 bytes ahead --
-  // the fastest of the forms measured (r2_run28 .. r2_run31, 101 MP frame: 1 first form 1.35 ms, 2 no
-  // look-ahead 1.20, 5 look-ahead load 1.00, 3 = 0 prefetch 0.94, 4 two prefetches 0.94, 6 blocks 1.20)
+  // 0 (default) = 7: "lines" (128-byte lines through a per-row ring in shared memory) -- the fastest of the
+  // forms measured (r2_run28 .. r2_run34, 101 MP frame: 1 first form 1.35 ms, 2 aligned words + table 1.20,
+  // 5 + look-ahead load 1.00, 3 + prefetch.global.L1 0.94, 4 two prefetches 0.94, 6 blocks 1.20, 7 lines 0.86)
   if (first_form == 1)
     p1_walk_entry<false, 0>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else if (first_form == 2)
     p1_walk_entry<true, 0>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+  else if (first_form == 3)
+    p1_walk_entry<true, 2>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else if (first_form == 4)
     p1_walk_entry<true, 3>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else if (first_form == 5)
     p1_walk_entry<true, 1>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else if (first_form == 6)
     p1_walk_entry<true, 4>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
-  else if (first_form == 7)
-    p1_walk_entry<true, 5>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
   else
-    p1_walk_entry<true, 2>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
+    p1_walk_entry<true, 5>(sh, in, strips, nstrips, jobs, gstride, gdesc, rowflag);
 }
 __global__ void __launch_bounds__(P1D_NT)
     p1_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,

@@ -40,14 +40,14 @@ extern "C" int p1_emu_run(const uint8_t* in, uint64_t in_total, const uint64_t* 
         p1_walk_entry<false, 0>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else if (first_form == 2)
         p1_walk_entry<true, 0>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
+      else if (first_form == 3)
+        p1_walk_entry<true, 2>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else if (first_form == 5)
         p1_walk_entry<true, 1>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else if (first_form == 6)
         p1_walk_entry<true, 4>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
-      else if (first_form == 7)
-        p1_walk_entry<true, 5>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else
-        p1_walk_entry<true, 2>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
+        p1_walk_entry<true, 5>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
     });
   const uint32_t nbd = ((uint32_t)nstrips * 32u + P1D_NT - 1) / P1D_NT;
   for (uint32_t b = 0; b < nbd; ++b)

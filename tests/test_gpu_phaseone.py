@@ -11,10 +11,10 @@ from helpers import gpu_run
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["3", "3w1", "3w6", "3w7", "2"])
+@pytest.fixture(autouse=True, params=["3", "3w1", "3w3", "3w6", "2"])
 def p1_version(request, monkeypatch):
     """Every case with the kernel the plans take by default (the third version: group headers walked per
-    row, pixels in parallel), with the first form of its walk, and with the second version (one thread per
+    row, pixels in parallel), with other forms of its walk, and with the second version (one thread per
     row); RSB200_P1 / RSB200_P1W are read when a plan is created."""
     monkeypatch.setenv("RSB200_P1", request.param[0])
     monkeypatch.setenv("RSB200_P1W", request.param[2] if len(request.param) == 3 else "0")

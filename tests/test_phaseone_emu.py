@@ -19,13 +19,14 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h"),
         os.path.join(HERE, "..", "rawspeed_b200", "csrc", "phaseone.cuh")]
 
 
-FORM = {"default": 0, "first": 1, "fast_no_touch": 2, "fast_touch": 5, "blocks": 6, "lines": 7}
+FORM = {"default": 0, "first": 1, "fast_no_touch": 2, "prefetch": 3, "fast_touch": 5, "blocks": 6}
 
 
-@pytest.fixture(scope="module", params=["default", "first", "fast_touch", "blocks", "lines"])
+@pytest.fixture(scope="module", params=["default", "first", "prefetch", "fast_touch", "blocks"])
 def emu(request):
-    """Forms of the header walk: the default (aligned-word windows, table-driven length codes, prefetch),
-    the first one (generic chunk loads, branches), look-ahead loads, and 16-byte blocks cached in registers."""
+    """Forms of the header walk: the default (128-byte lines through a per-row ring in shared memory, table-driven
+    length codes), the first one (generic chunk loads, branches), aligned-word windows with a prefetch or with
+    look-ahead loads, and 16-byte blocks cached in registers."""
     lib = _load()
     lib.form = FORM[request.param]
     return lib
