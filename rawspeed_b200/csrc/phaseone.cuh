@@ -303,10 +303,14 @@ __device__ __forceinline__ void p1_len_code_bf(uint32_t x, uint32_t& used, uint3
 // A length code is decided by the 6 bits at the top of the window: 64 entries, bits used | a 1 bit came
 // before five zeros << 3 | new length << 4 (0: keep) -- one shared-memory load instead of a dozen
 // dependent instructions.
-constexpr int P1W_RING = 64; // words per row in shared memory: two lines of 128 bytes (form "lines")
+constexpr int P1W_RING = 64;   // words per row in shared memory: two lines of 128 bytes (form "lines")
+constexpr int P1W_RING4 = 128; // ... four lines (form "cadence"; rows 16-byte aligned for 128-bit stores)
 struct P1WalkShared {
   uint32_t code6[64];
-  uint32_t ring[P1W_NT][P1W_RING + 1]; // (+1: the rows of a warp start in different banks)
+  union {
+    uint32_t ring[P1W_NT][P1W_RING + 1]; // (+1: the rows of a warp start in different banks)
+    uint4 ring4[P1W_NT][P1W_RING4 / 4 + 1];
+  };
 };
 
 // TOUCH: every step also loads one word 192 bytes further down the row and uses it a step later (an XOR
@@ -334,7 +338,12 @@ __device__ __forceinline__ void p1_prefetch(const void* q, int level) {
 // cached ones, and four descriptor words leave with one 128-bit store.  5 "lines": the row is read in
 // aligned lines of 128 bytes (eight 128-bit loads issued together, consumed a whole line -- about seven
 // steps -- later), two lines per row wait in shared memory and the window comes from there: the walk's
-// chain holds shared-memory loads only.
+// chain holds shared-memory loads only.  6 "cadence": ncu of "lines" (r2_run35): the rows of a warp cross
+// their line boundaries at different steps, so SOME lane refills at nearly every step, the whole warp runs
+// the refill code (twice the instructions) and -- the scoreboard of a load's destination register being
+// per warp -- every store of a pending line waits for the loads another lane issued a step ago.  So every
+// lane refills at the SAME steps, every fourth (a row advances at most 70 bytes in four steps, a refill
+// brings 128): a ring of four lines per row, the line loaded at one refill point is stored at the next.
 template <bool FAST, int TOUCH>
 __device__ __forceinline__ void
 p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev* __restrict__ strips,
@@ -398,6 +407,18 @@ p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev
     for (uint32_t i = 0; i < 8u; ++i)
       pend[i] = __ldg(a128 + min(16u + i, blast128));
   }
+  // TOUCH == 6: ring4 = lines [Lc, Lf) of the row, pend = line Lf (asked for at the last refill point)
+  uint4* ring4 = sh.ring4[threadIdx.x];
+  uint32_t Lf = 0;
+  if (TOUCH == 6) {
+#pragma unroll
+    for (uint32_t i = 0; i < 24u; ++i) // three lines to start with
+      ring4[i] = __ldg(a128 + min(i, blast128));
+    Lf = 3;
+#pragma unroll
+    for (uint32_t i = 0; i < 8u; ++i)
+      pend[i] = __ldg(a128 + min(24u + i, blast128));
+  }
   if (TOUCH == 4) {
     b0 = __ldg(a16);
     b1 = __ldg(a16 + min(1u, blast));
@@ -448,7 +469,28 @@ p1_walk_entry(P1WalkShared& sh, const uint8_t* __restrict__ in, const P1StripDev
         p1_prefetch(a128 + min(8u * (L + 6u), blast128), 2);
       }
     }
-    if (FAST && TOUCH == 5 && 4u * c + 16u <= size) {
+    if (TOUCH == 6 && (g & 3u) == 0u && g != 0u) { // refill point (the same step for every row of the warp)
+      const uint32_t Lc = (c + woff128) >> 5;
+      if (Lf - Lc < 4u) { // the slot of line Lf is free (it held line Lf - 4 < Lc)
+        uint4* slot = ring4 + 8u * (Lf & 3u);
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i)
+          slot[i] = pend[i];
+        ++Lf;
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i)
+          pend[i] = __ldg(a128 + min(8u * Lf + i, blast128));
+        p1_prefetch(a128 + min(8u * (Lf + 4u), blast128), 2);
+      }
+    }
+    if (FAST && TOUCH == 6 && 4u * c + 16u <= size) {
+      // (the window's words hold strip bytes only; their lines are in the ring: a row is at most 70 bytes
+      //  further at the next refill point, and at least two whole lines lie ahead of it after each)
+      const uint32_t cl = c + woff128;
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(ring4);
+      const uint32_t a0 = r32[cl & 127u], a1 = r32[(cl + 1u) & 127u], a2 = r32[(cl + 2u) & 127u];
+      x = __funnelshift_l(__funnelshift_r(a1, a2, sh8), __funnelshift_r(a0, a1, sh8), p);
+    } else if (FAST && TOUCH == 5 && 4u * c + 16u <= size) {
       // (the three words hold strip bytes only: their lines are L or L + 1, loaded without clamping)
       const uint32_t cl = c + woff128;
       const uint32_t a0 = ring[cl & 63u], a1 = ring[(cl + 1u) & 63u], a2 = ring[(cl + 2u) & 63u];

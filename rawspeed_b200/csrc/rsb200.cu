@@ -1238,7 +1238,7 @@ extern "C" int rsb200_phaseone_plan_create(rsb200_ctx* ctx, const rsb200_phaseon
   p->p1_ver = p1_version();
   {
     const char* e = getenv("RSB200_P1W");
-    p->p1_walk1 = (e && e[0] >= '1' && e[0] <= '7' && !e[1]) ? e[0] - '0' : 0;
+    p->p1_walk1 = (e && e[0] >= '1' && e[0] <= '8' && !e[1]) ? e[0] - '0' : 0;
   }
   p->launches_per_run = p->p1_ver == 3 ? 2 : 1;
   *out = p;

@@ -44,6 +44,8 @@ extern "C" int p1_emu_run(const uint8_t* in, uint64_t in_total, const uint64_t* 
         p1_walk_entry<true, 2>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else if (first_form == 5)
         p1_walk_entry<true, 1>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
+      else if (first_form == 8)
+        p1_walk_entry<true, 6>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else if (first_form == 6)
         p1_walk_entry<true, 4>(wsh, base, st.data(), (uint32_t)nstrips, &jb, gstride, gdesc.data(), rowflag.data());
       else

@@ -11,7 +11,7 @@ from helpers import gpu_run
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["3", "3w1", "3w3", "3w6", "2"])
+@pytest.fixture(autouse=True, params=["3", "3w1", "3w3", "3w6", "3w8", "2"])
 def p1_version(request, monkeypatch):
     """Every case with the kernel the plans take by default (the third version: group headers walked per
     row, pixels in parallel), with other forms of its walk, and with the second version (one thread per

@@ -19,10 +19,10 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h"),
         os.path.join(HERE, "..", "rawspeed_b200", "csrc", "phaseone.cuh")]
 
 
-FORM = {"default": 0, "first": 1, "fast_no_touch": 2, "prefetch": 3, "fast_touch": 5, "blocks": 6}
+FORM = {"default": 0, "first": 1, "fast_no_touch": 2, "prefetch": 3, "fast_touch": 5, "blocks": 6, "cadence": 8}
 
 
-@pytest.fixture(scope="module", params=["default", "first", "prefetch", "fast_touch", "blocks"])
+@pytest.fixture(scope="module", params=["default", "first", "prefetch", "fast_touch", "blocks", "cadence"])
 def emu(request):
     """Forms of the header walk: the default (128-byte lines through a per-row ring in shared memory, table-driven
     length codes), the first one (generic chunk loads, branches), aligned-word windows with a prefetch or with

@@ -117,7 +117,7 @@ def main():
         d_in = torch.zeros(blob.size + 64, dtype=torch.uint8, device="cuda")
         d_in[:blob.size] = torch.from_numpy(blob)
         d_out = torch.zeros(h * rs.image_pitch(w), dtype=torch.uint8, device="cuda")
-        vers = ("3", "3w3", "2")
+        vers = ("3", "3w8", "3w3", "2")
         if os.environ.get("RSB200_P1W"):   # (one variant only: profiling runs)
             vers = ("3w" + os.environ["RSB200_P1W"],)
         for ver in vers:
