@@ -128,3 +128,20 @@ def gpu_run(plan, in_np, out_np):
     torch.cuda.synchronize()
     res = plan.results()
     return d_out.cpu().numpy().view(np.uint16), res
+
+
+def compile_shared(cmd):
+    """Run a compiler command whose output file follows "-o": the library is written under a private name and
+    renamed into place, so that test processes running side by side (pytest-xdist) never load a half-written
+    file or overwrite one another's output in the middle of a link."""
+    import os
+    import subprocess
+    i = cmd.index("-o")
+    out = cmd[i + 1]
+    tmp = "%s.tmp.%d" % (out, os.getpid())
+    try:
+        subprocess.check_call(cmd[:i + 1] + [tmp] + cmd[i + 2:])
+        os.replace(tmp, out)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)

@@ -12,6 +12,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from helpers import compile_shared
+
 from oracle import port
 from rawspeed_b200 import host
 from rawspeed_b200._abi import DngOp, DngOpJob
@@ -33,7 +35,7 @@ def emu(request):
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         flags = ["-DRSB200_DNGOP" + request.param.upper()] if request.param else []
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared"] + flags + ["-o", out, SRC])
+        compile_shared(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared"] + flags + ["-o", out, SRC])
     lib = C.CDLL(out)
     lib.dngop_emu_run.argtypes = [C.c_void_p, C.POINTER(DngOpJob), C.c_int, C.POINTER(DngOp), C.c_int,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32,

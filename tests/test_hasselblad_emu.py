@@ -9,6 +9,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from helpers import compile_shared
+
 import rawspeed_b200 as rs
 from rawspeed_b200 import _abi
 from oracle import port, synth
@@ -26,7 +28,7 @@ NCPL, VALS = synth.DEFAULT_NCPL, synth.DEFAULT_VALUES
 def emu():
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
+        compile_shared(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
                                "-Wno-unused-function", "-fPIC", "-shared", "-o", OUT, SRC])
     lib = C.CDLL(OUT)
     lib.hass_emu_run.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -17,7 +17,7 @@ import pytest
 import rawspeed_b200 as rs
 from rawspeed_b200 import _abi
 from oracle import port, synth
-from helpers import dng_ljpeg_scans
+from helpers import dng_ljpeg_scans, compile_shared
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "ljpeg_stream_emu.cpp")
@@ -38,7 +38,7 @@ def emu(request):
              "pipe2": ["-DRSB200_EMU_WIDE=true", "-DRSB200_S_PIPE=2", "-DRSB200_S_FILL2=1"]}[request.param]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
+        compile_shared(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
                                "-Wno-unused-function", "-fPIC", "-shared"] + flags + ["-o", out, SRC])
     lib = C.CDLL(out)
     lib.stream_emu_run.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int,

@@ -16,7 +16,7 @@ import pytest
 import rawspeed_b200 as rs
 from rawspeed_b200 import _abi
 from oracle import port, synth
-from helpers import dng_ljpeg_scans
+from helpers import dng_ljpeg_scans, compile_shared
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "emu", "ljpeg_tile_emu.cpp")
@@ -30,7 +30,7 @@ DEPS = [SRC, os.path.join(HERE, "emu", "cuda_emu.h")] + [
 def emu():
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
+        compile_shared(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
                                "-Wno-unused-function", "-fPIC", "-shared", "-o", OUT, SRC])
     lib = C.CDLL(OUT)
     lib.tile_emu_run.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_int,

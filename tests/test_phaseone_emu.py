@@ -10,6 +10,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from helpers import compile_shared
+
 from oracle import port, synth
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -35,7 +37,7 @@ def emu(request):
 def _load():
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
+        compile_shared(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas",
                                "-Wno-unused-function", "-fPIC", "-shared", "-o", OUT, SRC])
     lib = C.CDLL(OUT)
     lib.p1_emu_run.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),

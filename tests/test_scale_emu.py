@@ -10,6 +10,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from helpers import compile_shared
+
 from oracle import port
 from rawspeed_b200._abi import ScaleJob, SCALE_AUTO, SCALE_PLAIN, SCALE_SSE2
 
@@ -24,7 +26,7 @@ DEPS = [SRC] + [os.path.join(HERE, "..", "rawspeed_b200", "csrc", f)
 def emu():
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-o", OUT, SRC])
+        compile_shared(["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-o", OUT, SRC])
     lib = C.CDLL(OUT)
     lib.scale_emu_run.argtypes = [C.c_void_p, C.POINTER(ScaleJob), C.c_int, C.c_char_p, C.c_int]
     lib.scale_emu_mwc_direct.argtypes = lib.scale_emu_mwc_state.argtypes = [C.c_uint32] * 3
