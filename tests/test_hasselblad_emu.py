@@ -118,3 +118,23 @@ def test_truncated_streams(emu, cut):
         if n <= 0:
             continue
         check(emu, data[:n], 192, 16, 0x8000)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_tables(emu, seed):
+    """Random COMPLETE canonical codes over the difference lengths 0 .. 16 (codes of up to 16 bits, values in
+    random order; 17 values: "Hasselblad uses 17"), noise from a few bits to the full range: the speculative
+    segment parse has to settle on the sequential one whatever the code looks like."""
+    from test_ljpeg_stream_emu import _random_table
+    rng = np.random.default_rng(4000 + seed)
+    w, h = int(rng.choice([64, 130, 512])), int(rng.integers(3, 24))
+    bits = int(rng.choice([4, 9, 16]))
+    img = ((0x8000 + rng.integers(0, 1 << bits, (h, w)) - (1 << bits) // 2) & 0xFFFF).astype(np.uint16)
+    t = _random_table(rng, 17)
+    ncpl, vals = bytes(t.ncpl), bytes(t.values)
+    ht = port.Huff(ncpl, vals, full=False)
+    data = synth.make_hasselblad(img, ht, 0x8000)
+    want = oracle_outcome(data, w, h, 0x8000, ncpl=ncpl, vals=vals)
+    assert want[0] == 0 and np.array_equal(want[2][:, :w], img)
+    status, consumed, out, rounds = run_emu(emu, data, w, h, 0x8000, ncpl=ncpl, vals=vals)
+    assert status == 0 and consumed == want[1] and np.array_equal(out, want[2])
